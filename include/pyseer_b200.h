@@ -1,0 +1,182 @@
+/*
+ * pyseer_b200.h -- C ABI of libpyseer_b200.so
+ *
+ * Drop-in boundary for pyseer's per-variant association loop.  pyseer itself has no
+ * FFI; the seam is the two Python call signatures its worker map invokes
+ * (pyseer/__main__.py:541-544 -> lmm.fit_lmm, :777-780 -> model.fixed_effects_regression)
+ * plus the namedtuples they return (pyseer/classes.py:3-22).  Each entry point below
+ * names the reference interface it replaces.  Plain C: pointers and sizes only, no
+ * exceptions across the boundary, every function returns an int status
+ * (PSB_OK or a negative psb_status; text via psb_last_error()).
+ *
+ * Ownership: every pointer passed in is caller-owned and only read (or written, for
+ * outputs) during the call, except psb_submit_device() whose device buffer must stay
+ * valid until the next psb_submit*() / psb_destroy().  The library owns all device
+ * memory it allocates.  One psb_ctx drives one GPU on one stream; contexts are
+ * independent (one per process under torchrun, or several in one process).
+ */
+#ifndef PYSEER_B200_H
+#define PYSEER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB_ABI_VERSION 1
+
+typedef enum psb_status {
+    PSB_OK = 0,
+    PSB_ERR_CUDA = -1,      /* CUDA runtime / driver error                       */
+    PSB_ERR_ARG = -2,       /* bad argument (shape mismatch, null pointer ...)   */
+    PSB_ERR_STATE = -3,     /* call out of order (run before setup/submit ...)   */
+    PSB_ERR_H2 = -4,        /* h2 outside [0,1): lmm_cov.py:667-670 (KeyError)   */
+    PSB_ERR_NOMEM = -5,
+    PSB_ERR_UNSUPPORTED = -6
+} psb_status;
+
+/* Per-variant flag word.  Bits map 1:1 onto the reference's `notes` strings and the
+ * `prefilter` / `filter` booleans of classes.Seer / classes.LMM. */
+#define PSB_F_AF_FILTER        0x0001u  /* 'af-filter'            model.py:255 lmm.py:163 */
+#define PSB_F_PREFILTER_FAILED 0x0002u  /* 'pre-filtering-failed' model.py:266 lmm.py:174 */
+#define PSB_F_BAD_CHISQ        0x0004u  /* 'bad-chisq'            model.py:264 lmm.py:172 */
+#define PSB_F_HIGH_BSE         0x0008u  /* 'high-bse'             model.py:332            */
+#define PSB_F_PERFECT_SEP      0x0010u  /* 'perfectly-separable-data' model.py:345        */
+#define PSB_F_MATRIX_INV       0x0020u  /* 'matrix-inversion-error'   model.py:349        */
+#define PSB_F_FIRTH_FAIL       0x0040u  /* 'firth-fail'           model.py:357            */
+#define PSB_F_MISSING_DATA     0x0080u  /* 'missing-data-error'   model.py:371            */
+#define PSB_F_LRT_FAILED       0x0100u  /* 'lrt-filtering-failed' model.py:384 lmm.py:201 */
+#define PSB_F_PREFILTER        0x0200u  /* .prefilter == True                             */
+#define PSB_F_FILTER           0x0400u  /* .filter == True                                */
+#define PSB_F_TESTED           0x0800u  /* counted in `tested` (__main__.py:558/793)      */
+#define PSB_F_FIRTH_USED       0x1000u  /* informational: result came from fit_firth      */
+
+typedef struct psb_ctx psb_ctx;
+
+/* Thresholds of one run: pyseer options --min-af --max-af --max-missing
+ * --filter-pvalue --lrt-pvalue (__main__.py:180-206) and the `continuous` switch. */
+typedef struct psb_params {
+    double min_af;
+    double max_af;
+    double max_missing;
+    double filter_pvalue;
+    double lrt_pvalue;
+    int32_t continuous;     /* phenotype treated as continuous by pre_filtering()   */
+    int32_t options;        /* PSB_OPT_* bits                                        */
+} psb_params;
+
+/* fit every submitted variant, no AF filter and no pre_filtering(): the semantics of a
+ * direct lmm.fit_lmm_block call (lmm.py:228-260), which filters nothing */
+#define PSB_OPT_NO_PREFILTER 0x1
+
+/* Result table, structure-of-arrays, one entry per submitted variant in submission
+ * order.  Any pointer may be NULL (that column is skipped).  Doubles follow the
+ * reference: NaN where the reference leaves the namedtuple field at NaN. */
+typedef struct psb_results {
+    int32_t  *carriers;   /* len(kstrains): samples with the variant, missing included (input.py:439) */
+    int32_t  *missing;    /* samples with NaN genotype                                               */
+    double   *af;         /* carriers / N (input.py:446)                                             */
+    double   *prep;       /* filter-pvalue (model.pre_filtering)                                     */
+    double   *pvalue;     /* lrt-pvalue                                                              */
+    double   *beta;       /* kbeta                                                                   */
+    double   *bse;        /* beta-std-err                                                            */
+    double   *extra;      /* LMM: frac_h2 (variant_h2); fixed effects: intercept                     */
+    double   *betas;      /* fixed effects only: n_variants x (q-1) row-major covariate slopes       */
+    uint32_t *flags;      /* PSB_F_*                                                                 */
+} psb_results;
+
+/* ---- library / context ------------------------------------------------------ */
+int psb_abi_version(void);
+const char *psb_last_error(void);
+int psb_device_count(int *count);
+/* replaces multiprocessing.Pool(options.cpu) (__main__.py:517-519): one context per GPU */
+int psb_create(int device_id, psb_ctx **out);
+int psb_destroy(psb_ctx *ctx);
+int psb_sync(psb_ctx *ctx);
+
+/* ---- once-per-run model state ------------------------------------------------ */
+/* LMM state after lmm.initialise_lmm (lmm.py:26-122): covariates X (N x D row-major,
+ * last column ones, lmm.py:95-99), phenotype y, kernel eigenvectors U (N x (N-D)
+ * row-major) and eigenvalues S (lmm_cov.py:88-103) and h2 (lmm_cov.findH2).  Builds
+ * the rotated operands used by fit_lmm_block (lmm.py:228-260).
+ * precision: 0 = FP64 CUDA-core contraction; k in [3,8] = exact k-slice int8
+ * tensor-core contraction (tcgen05).  Returns PSB_ERR_H2 when h2 is outside [0,1). */
+int psb_lmm_setup(psb_ctx *ctx, int32_t n_samples, int32_t n_cov, const double *X,
+                  const double *y, const double *U, const double *S, double h2,
+                  int32_t precision);
+
+/* Fixed-effects state shared by every fixed_effects_regression call (model.py:202-205):
+ * Z = [1, m, c] (N x q row-major, column 0 ones; model.py:274-297 minus the variant
+ * column), phenotype y, `continuous`, null log-likelihoods null_res / null_firth
+ * (model.fit_null; __main__.py:378-380, 449-450). */
+int psb_fixed_setup(psb_ctx *ctx, int32_t n_samples, int32_t q, const double *Z,
+                    const double *y, int32_t continuous, double null_llf,
+                    double null_firth_llf);
+
+/* Null model fits on the device with the same solver (model.fit_null, model.py:73-148).
+ * Design Z (N x q row-major), no variant column.  out_params: q doubles; out_bse: q
+ * doubles; out_llf: log-likelihood; firth != 0 -> Firth-penalised fit (out_llf only).
+ * Returns PSB_OK and *out_status = PSB_F_* bits (0 = fitted). */
+int psb_fit_null(psb_ctx *ctx, int32_t n_samples, int32_t q, const double *Z,
+                 const double *y, int32_t continuous, int32_t firth, double *out_params,
+                 double *out_bse, double *out_llf, uint32_t *out_status);
+
+/* ---- variants ---------------------------------------------------------------- */
+/* Packed presence/absence rows replacing the tuples of input.iter_variants /
+ * load_var_block (input.py:505-707): n_variants rows of words_per_row uint32, bit
+ * (i % 32) of word (i / 32) = sample i of the phenotype index order; words_per_row
+ * >= ceil(N/32) and a multiple of 4 (16-byte rows); padding bits must be zero.
+ * `missing` (same shape, nullable) marks NaN genotypes (Rtab '.', VCF no-call).
+ * psb_submit copies host->device asynchronously on the context stream (pass pinned
+ * memory to overlap); psb_submit_device adopts device-resident rows without a copy. */
+int psb_submit(psb_ctx *ctx, const uint32_t *bits, const uint32_t *missing,
+               int64_t n_variants, int32_t words_per_row);
+int psb_submit_device(psb_ctx *ctx, const void *d_bits, const void *d_missing,
+                      int64_t n_variants, int32_t words_per_row);
+
+/* ---- the hot path ------------------------------------------------------------ */
+/* replaces lmm.fit_lmm (lmm.py:125-226) for every submitted variant */
+int psb_run_lmm(psb_ctx *ctx, const psb_params *params);
+/* replaces model.fixed_effects_regression (model.py:202-394) for every submitted variant */
+int psb_run_fixed(psb_ctx *ctx, const psb_params *params);
+
+/* Copies the result table to host arrays (synchronises the context stream). */
+int psb_fetch(psb_ctx *ctx, const psb_results *out);
+/* Device pointers of the result table of the last run (valid until the next run);
+ * lets the caller gather tables across ranks with NCCL without a host round trip. */
+int psb_results_device(psb_ctx *ctx, psb_results *out_device_ptrs);
+/* counters of the last run: [0] loaded, [1] pre-filtered, [2] tested, [3] passed filter
+ * (__main__.py:831-834 semantics, printed == tested - filtered unless --print-filtered) */
+int psb_counts(psb_ctx *ctx, int64_t out[4]);
+
+/* ---- measurement ------------------------------------------------------------- */
+/* CUDA-event timers on the context stream.  which: 0 = whole last psb_run_*,
+ * 1 = dominant kernel of the last run (LMM: the rotation/quadratic-form contraction;
+ * fixed effects: the regression kernel).  Returns milliseconds. */
+int psb_last_ms(psb_ctx *ctx, int32_t which, float *ms);
+/* number of kernels the library launched on this context since creation */
+int psb_launch_count(psb_ctx *ctx, int64_t *n);
+
+/* ---- synthetic inputs (bench / tests) ----------------------------------------- */
+/* Fills a library-owned device buffer with seeded Bernoulli(af_s) rows, af_s ~
+ * U(af_lo, af_hi); variant id = first_variant + row (counter-based, so shards do not
+ * depend on the GPU count).  planted_every > 0 plants a phenotype-correlated variant at
+ * ids divisible by it (needs y_sign: N int8 of +1/-1/0, host pointer).  The rows are
+ * left submitted (as by psb_submit_device).  Same generator on host: psb_synth_host. */
+int psb_synth_device(psb_ctx *ctx, uint64_t seed, int64_t first_variant,
+                     int64_t n_variants, int32_t n_samples, double af_lo, double af_hi,
+                     int32_t planted_every, const int8_t *y_sign);
+int psb_synth_host(uint64_t seed, int64_t first_variant, int64_t n_variants,
+                   int32_t n_samples, double af_lo, double af_hi, int32_t planted_every,
+                   const int8_t *y_sign, uint32_t *out_bits, int32_t words_per_row);
+
+/* ---- host-evaluated special functions (same code the kernels run; CPU tests) ---- */
+double psb_host_chi2_sf1(double x);                 /* scipy.stats.chi2.sf(x, 1)        */
+double psb_host_f_sf_1(double x, double dfd);       /* scipy.stats.f.sf(x, 1, dfd)      */
+double psb_host_t2_sf(double t, double df);         /* 2 * scipy.stats.t.sf(|t|, df)    */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYSEER_B200_H */

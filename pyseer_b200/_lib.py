@@ -1,0 +1,127 @@
+"""ctypes binding of libpyseer_b200.so (C ABI: include/pyseer_b200.h).
+
+The library is the product; this module fails loudly when it is missing.  It never falls
+back to a CPU implementation.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64,
+                    c_int8, c_uint32, c_uint64, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libpyseer_b200.so')
+
+PSB_OK = 0
+PSB_ERR_CUDA, PSB_ERR_ARG, PSB_ERR_STATE, PSB_ERR_H2, PSB_ERR_NOMEM, PSB_ERR_UNSUPPORTED = \
+    -1, -2, -3, -4, -5, -6
+
+F_AF_FILTER = 0x0001
+F_PREFILTER_FAILED = 0x0002
+F_BAD_CHISQ = 0x0004
+F_HIGH_BSE = 0x0008
+F_PERFECT_SEP = 0x0010
+F_MATRIX_INV = 0x0020
+F_FIRTH_FAIL = 0x0040
+F_MISSING_DATA = 0x0080
+F_LRT_FAILED = 0x0100
+F_PREFILTER = 0x0200
+F_FILTER = 0x0400
+F_TESTED = 0x0800
+F_FIRTH_USED = 0x1000
+OPT_NO_PREFILTER = 0x1
+
+#: flag bit -> reference note string (model.py / lmm.py)
+NOTE_BITS = [
+    (F_AF_FILTER, 'af-filter'),
+    (F_PREFILTER_FAILED, 'pre-filtering-failed'),
+    (F_BAD_CHISQ, 'bad-chisq'),
+    (F_HIGH_BSE, 'high-bse'),
+    (F_PERFECT_SEP, 'perfectly-separable-data'),
+    (F_MATRIX_INV, 'matrix-inversion-error'),
+    (F_FIRTH_FAIL, 'firth-fail'),
+    (F_MISSING_DATA, 'missing-data-error'),
+    (F_LRT_FAILED, 'lrt-filtering-failed'),
+]
+
+
+class PsbParams(Structure):
+    _fields_ = [('min_af', c_double), ('max_af', c_double), ('max_missing', c_double),
+                ('filter_pvalue', c_double), ('lrt_pvalue', c_double),
+                ('continuous', c_int32), ('options', c_int32)]
+
+
+class PsbResults(Structure):
+    _fields_ = [('carriers', c_void_p), ('missing', c_void_p), ('af', c_void_p),
+                ('prep', c_void_p), ('pvalue', c_void_p), ('beta', c_void_p),
+                ('bse', c_void_p), ('extra', c_void_p), ('betas', c_void_p),
+                ('flags', c_void_p)]
+
+
+class LibraryMissing(ImportError):
+    pass
+
+
+class PsbError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, 'libpyseer_b200 error %d: %s' % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+#: every symbol include/pyseer_b200.h declares
+SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create', 'psb_destroy',
+           'psb_sync', 'psb_lmm_setup', 'psb_fixed_setup', 'psb_fit_null', 'psb_submit',
+           'psb_submit_device', 'psb_run_lmm', 'psb_run_fixed', 'psb_fetch',
+           'psb_results_device', 'psb_counts', 'psb_last_ms', 'psb_launch_count',
+           'psb_synth_device', 'psb_synth_host', 'psb_host_chi2_sf1', 'psb_host_f_sf_1',
+           'psb_host_t2_sf']
+
+
+def load():
+    """Load the shared library (once) and declare its prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            '%s not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            'or `make -C pyseer_b200/csrc`.  pyseer_b200 has no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    dp = POINTER(c_double)
+    lib.psb_abi_version.restype = c_int
+    lib.psb_last_error.restype = c_char_p
+    lib.psb_device_count.argtypes = [POINTER(c_int)]
+    lib.psb_create.argtypes = [c_int, POINTER(c_void_p)]
+    lib.psb_destroy.argtypes = [c_void_p]
+    lib.psb_sync.argtypes = [c_void_p]
+    lib.psb_lmm_setup.argtypes = [c_void_p, c_int32, c_int32, dp, dp, dp, dp, c_double, c_int32]
+    lib.psb_fixed_setup.argtypes = [c_void_p, c_int32, c_int32, dp, dp, c_int32, c_double, c_double]
+    lib.psb_fit_null.argtypes = [c_void_p, c_int32, c_int32, dp, dp, c_int32, c_int32, dp, dp, dp,
+                                 POINTER(c_uint32)]
+    lib.psb_submit.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32]
+    lib.psb_submit_device.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32]
+    lib.psb_run_lmm.argtypes = [c_void_p, POINTER(PsbParams)]
+    lib.psb_run_fixed.argtypes = [c_void_p, POINTER(PsbParams)]
+    lib.psb_fetch.argtypes = [c_void_p, POINTER(PsbResults)]
+    lib.psb_results_device.argtypes = [c_void_p, POINTER(PsbResults)]
+    lib.psb_counts.argtypes = [c_void_p, POINTER(c_int64)]
+    lib.psb_last_ms.argtypes = [c_void_p, c_int32, POINTER(c_float)]
+    lib.psb_launch_count.argtypes = [c_void_p, POINTER(c_int64)]
+    lib.psb_synth_device.argtypes = [c_void_p, c_uint64, c_int64, c_int64, c_int32, c_double,
+                                     c_double, c_int32, POINTER(c_int8)]
+    lib.psb_synth_host.argtypes = [c_uint64, c_int64, c_int64, c_int32, c_double, c_double,
+                                   c_int32, POINTER(c_int8), POINTER(c_uint32), c_int32]
+    for f in ('psb_host_chi2_sf1',):
+        getattr(lib, f).restype = c_double
+        getattr(lib, f).argtypes = [c_double]
+    for f in ('psb_host_f_sf_1', 'psb_host_t2_sf'):
+        getattr(lib, f).restype = c_double
+        getattr(lib, f).argtypes = [c_double, c_double]
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != PSB_OK:
+        raise PsbError(code, load().psb_last_error().decode('utf-8', 'replace'))

@@ -1,0 +1,295 @@
+// psb_api.cu -- context lifecycle, staging, result table and measurement entry points
+// of the C ABI declared in include/pyseer_b200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "psb_internal.cuh"
+#include "psb_math.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void psb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int psb_abi_version(void) { return PSB_ABI_VERSION; }
+const char *psb_last_error(void) { return g_err; }
+
+int psb_device_count(int *count) {
+    PSB_REQUIRE(count, PSB_ERR_ARG, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return PSB_OK;
+}
+
+int psb_create(int device_id, psb_ctx **out) {
+    PSB_REQUIRE(out, PSB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    PSB_CUDA(cudaGetDeviceCount(&n));
+    PSB_REQUIRE(device_id >= 0 && device_id < n, PSB_ERR_ARG,
+                "device %d not available (%d visible); libpyseer_b200 has no CPU fallback",
+                device_id, n);
+    PSB_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    PSB_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    PSB_REQUIRE(prop.major >= 10, PSB_ERR_UNSUPPORTED,
+                "device %d is sm_%d%d; this library is built for sm_100a only", device_id,
+                prop.major, prop.minor);
+    psb_ctx *c = new psb_ctx();
+    c->device = device_id;
+    c->sm_count = prop.multiProcessorCount;
+    PSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PSB_CUDA(cudaEventCreate(&c->ev_run0));
+    PSB_CUDA(cudaEventCreate(&c->ev_run1));
+    PSB_CUDA(cudaEventCreate(&c->ev_k0));
+    PSB_CUDA(cudaEventCreate(&c->ev_k1));
+    PSB_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
+    *out = c;
+    return PSB_OK;
+}
+
+}  // extern "C"
+
+static void free_dev(void *p) {
+    if (p) cudaFree(p);
+}
+
+int psb_free_model(psb_ctx *c) {
+    free_dev(c->d_y1bits); c->d_y1bits = nullptr;
+    free_dev(c->d_y0bits); c->d_y0bits = nullptr;
+    free_dev(c->d_valid); c->d_valid = nullptr;
+    free_dev(c->d_cols); c->d_cols = nullptr;
+    free_dev(c->d_L); c->d_L = nullptr;
+    psb_lmm_tc_free(c);
+    free_dev(c->d_Z); c->d_Z = nullptr;
+    free_dev(c->d_yv); c->d_yv = nullptr;
+    free_dev(c->d_fixed_const); c->d_fixed_const = nullptr;
+    free_dev(c->d_sums); c->d_sums = nullptr; c->sums_cap = 0;
+    c->model = PSB_MODEL_NONE;
+    c->ran = false;
+    return PSB_OK;
+}
+
+static void free_tables(psb_ctx *c);
+extern "C" {
+}
+static void free_tables(psb_ctx *c) {
+    free_dev(c->d_carriers); free_dev(c->d_missing); free_dev(c->d_af); free_dev(c->d_prep);
+    free_dev(c->d_pvalue); free_dev(c->d_beta); free_dev(c->d_bse); free_dev(c->d_extra);
+    free_dev(c->d_betas); free_dev(c->d_flags); free_dev(c->d_tab); free_dev(c->d_idx);
+    free_dev(c->d_idx2); free_dev(c->d_a);
+    c->d_carriers = c->d_missing = nullptr;
+    c->d_af = c->d_prep = c->d_pvalue = c->d_beta = c->d_bse = c->d_extra = c->d_betas = nullptr;
+    c->d_flags = nullptr; c->d_tab = nullptr; c->d_idx = c->d_idx2 = nullptr; c->d_a = nullptr;
+    c->cap = 0; c->betas_cols = 0;
+}
+
+extern "C" {
+int psb_destroy(psb_ctx *c) {
+    if (!c) return PSB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    psb_free_model(c);
+    free_tables(c);
+    free_dev(c->own_bits); free_dev(c->own_miss); free_dev(c->d_counters);
+    cudaEventDestroy(c->ev_run0); cudaEventDestroy(c->ev_run1);
+    cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return PSB_OK;
+}
+
+int psb_sync(psb_ctx *c) {
+    PSB_REQUIRE(c, PSB_ERR_ARG, "ctx is NULL");
+    PSB_CUDA(cudaSetDevice(c->device));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    return PSB_OK;
+}
+
+}  // extern "C"
+
+int psb_ensure_capacity(psb_ctx *c, int64_t S, int betas_cols) {
+    if (S > c->cap || betas_cols > c->betas_cols) {
+        PSB_CUDA(cudaStreamSynchronize(c->stream));
+        free_tables(c);
+        int64_t cap = S < 1024 ? 1024 : S;
+        PSB_CUDA(cudaMalloc(&c->d_carriers, cap * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_missing, cap * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_af, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->d_prep, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->d_pvalue, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->d_beta, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->d_bse, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->d_extra, cap * sizeof(double)));
+        if (betas_cols > 0)
+            PSB_CUDA(cudaMalloc(&c->d_betas, cap * betas_cols * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->d_flags, cap * sizeof(uint32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_tab, cap * 4 * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_idx, (cap + 256) * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_idx2, (cap + 256) * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_a, cap * sizeof(double)));
+        c->cap = cap;
+        c->betas_cols = betas_cols;
+    }
+    size_t need = (size_t)c->cap * (size_t)(c->C > 0 ? c->C : 1) * sizeof(double);
+    if (need > c->sums_cap) {
+        PSB_CUDA(cudaStreamSynchronize(c->stream));
+        free_dev(c->d_sums);
+        c->d_sums = nullptr;
+        PSB_CUDA(cudaMalloc(&c->d_sums, need));
+        c->sums_cap = need;
+    }
+    return PSB_OK;
+}
+
+extern "C" {
+
+static int check_rows(psb_ctx *c, int64_t n_variants, int32_t words_per_row) {
+    PSB_REQUIRE(c, PSB_ERR_ARG, "ctx is NULL");
+    PSB_REQUIRE(c->model != PSB_MODEL_NONE, PSB_ERR_STATE,
+                "psb_submit before psb_lmm_setup / psb_fixed_setup");
+    PSB_REQUIRE(n_variants >= 0 && n_variants < (1ll << 31) - 512, PSB_ERR_ARG,
+                "n_variants %lld out of range", (long long)n_variants);
+    PSB_REQUIRE(words_per_row >= c->Wn && words_per_row % 4 == 0, PSB_ERR_ARG,
+                "words_per_row %d must be a multiple of 4 and >= ceil(N/32) = %d",
+                words_per_row, c->Wn);
+    return PSB_OK;
+}
+
+int psb_submit(psb_ctx *c, const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
+               int32_t words_per_row) {
+    int rc = check_rows(c, n_variants, words_per_row);
+    if (rc) return rc;
+    PSB_REQUIRE(bits || n_variants == 0, PSB_ERR_ARG, "bits is NULL");
+    PSB_CUDA(cudaSetDevice(c->device));
+    size_t bytes = (size_t)n_variants * words_per_row * sizeof(uint32_t);
+    if (bytes > c->own_bits_cap) {
+        PSB_CUDA(cudaStreamSynchronize(c->stream));
+        free_dev(c->own_bits);
+        c->own_bits = nullptr;
+        c->own_bits_cap = 0;
+        PSB_CUDA(cudaMalloc(&c->own_bits, bytes));
+        c->own_bits_cap = bytes;
+    }
+    if (bytes) PSB_CUDA(cudaMemcpyAsync(c->own_bits, bits, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->d_bits = c->own_bits;
+    c->d_miss = nullptr;
+    if (missing) {
+        if (bytes > c->own_miss_cap) {
+            PSB_CUDA(cudaStreamSynchronize(c->stream));
+            free_dev(c->own_miss);
+            c->own_miss = nullptr;
+            c->own_miss_cap = 0;
+            PSB_CUDA(cudaMalloc(&c->own_miss, bytes));
+            c->own_miss_cap = bytes;
+        }
+        if (bytes)
+            PSB_CUDA(cudaMemcpyAsync(c->own_miss, missing, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->d_miss = c->own_miss;
+    }
+    c->S = n_variants;
+    c->Wrow = words_per_row;
+    c->ran = false;
+    return PSB_OK;
+}
+
+int psb_submit_device(psb_ctx *c, const void *d_bits, const void *d_missing, int64_t n_variants,
+                      int32_t words_per_row) {
+    int rc = check_rows(c, n_variants, words_per_row);
+    if (rc) return rc;
+    PSB_REQUIRE(d_bits || n_variants == 0, PSB_ERR_ARG, "d_bits is NULL");
+    c->d_bits = (const uint32_t *)d_bits;
+    c->d_miss = (const uint32_t *)d_missing;
+    c->S = n_variants;
+    c->Wrow = words_per_row;
+    c->ran = false;
+    return PSB_OK;
+}
+
+int psb_fetch(psb_ctx *c, const psb_results *out) {
+    PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->ran, PSB_ERR_STATE, "psb_fetch before psb_run_*");
+    PSB_CUDA(cudaSetDevice(c->device));
+    int64_t S = c->S;
+    cudaStream_t st = c->stream;
+#define CP(field, src, type)                                                                 \
+    if (out->field && S > 0)                                                                 \
+        PSB_CUDA(cudaMemcpyAsync(out->field, src, S * sizeof(type), cudaMemcpyDeviceToHost, st));
+    CP(carriers, c->d_carriers, int32_t)
+    CP(missing, c->d_missing, int32_t)
+    CP(af, c->d_af, double)
+    CP(prep, c->d_prep, double)
+    CP(pvalue, c->d_pvalue, double)
+    CP(beta, c->d_beta, double)
+    CP(bse, c->d_bse, double)
+    CP(extra, c->d_extra, double)
+    CP(flags, c->d_flags, uint32_t)
+#undef CP
+    if (out->betas && S > 0 && c->model == PSB_MODEL_FIXED && c->q > 1)
+        PSB_CUDA(cudaMemcpyAsync(out->betas, c->d_betas, S * (c->q - 1) * sizeof(double),
+                                 cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    return PSB_OK;
+}
+
+int psb_results_device(psb_ctx *c, psb_results *o) {
+    PSB_REQUIRE(c && o, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->ran, PSB_ERR_STATE, "psb_results_device before psb_run_*");
+    o->carriers = c->d_carriers; o->missing = c->d_missing; o->af = c->d_af; o->prep = c->d_prep;
+    o->pvalue = c->d_pvalue; o->beta = c->d_beta; o->bse = c->d_bse; o->extra = c->d_extra;
+    o->betas = c->d_betas; o->flags = c->d_flags;
+    return PSB_OK;
+}
+
+int psb_counts(psb_ctx *c, int64_t out[4]) {
+    PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->ran, PSB_ERR_STATE, "psb_counts before psb_run_*");
+    PSB_CUDA(cudaSetDevice(c->device));
+    int h[8];
+    PSB_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    out[0] = c->S;       // loaded
+    out[1] = h[1];       // pre-filtered (af + prefilter)
+    out[2] = h[0];       // tested
+    out[3] = h[0] - h[2];  // tested and passed the lrt filter
+    return PSB_OK;
+}
+
+int psb_last_ms(psb_ctx *c, int32_t which, float *ms) {
+    PSB_REQUIRE(c && ms, PSB_ERR_ARG, "NULL argument");
+    PSB_CUDA(cudaSetDevice(c->device));
+    *ms = 0.f;
+    if (which == 0) {
+        PSB_REQUIRE(c->have_run_ev, PSB_ERR_STATE, "no run recorded");
+        PSB_CUDA(cudaEventSynchronize(c->ev_run1));
+        PSB_CUDA(cudaEventElapsedTime(ms, c->ev_run0, c->ev_run1));
+    } else {
+        PSB_REQUIRE(c->have_k_ev, PSB_ERR_STATE, "no kernel timing recorded");
+        PSB_CUDA(cudaEventSynchronize(c->ev_k1));
+        PSB_CUDA(cudaEventElapsedTime(ms, c->ev_k0, c->ev_k1));
+    }
+    return PSB_OK;
+}
+
+int psb_launch_count(psb_ctx *c, int64_t *n) {
+    PSB_REQUIRE(c && n, PSB_ERR_ARG, "NULL argument");
+    *n = c->launches;
+    return PSB_OK;
+}
+
+double psb_host_chi2_sf1(double x) { return psb_chi2_sf1(x); }
+double psb_host_f_sf_1(double x, double dfd) { return psb_t2_sf(x, dfd); }
+double psb_host_t2_sf(double t, double df) { return psb_t2_sf(t * t, df); }
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// psb_internal.cuh -- context layout and helpers shared by the translation units of
+// libpyseer_b200.so.  Not part of the public ABI (see include/pyseer_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pyseer_b200.h"
+
+#define PSB_MODEL_NONE 0
+#define PSB_MODEL_LMM 1
+#define PSB_MODEL_FIXED 2
+
+// mask kinds for k_bitsums columns
+#define PSB_MASK_RAW 0   // x (NaN genotypes count as absent)
+#define PSB_MASK_K1 1    // x & ~missing            (k == 1)
+#define PSB_MASK_K0 2    // ~x & ~missing & valid   (k == 0)
+
+void psb_set_error(const char *fmt, ...);
+
+#define PSB_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e_ = (call);                                                    \
+        if (e_ != cudaSuccess) {                                                    \
+            psb_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__,            \
+                          cudaGetErrorName(e_), cudaGetErrorString(e_));            \
+            return PSB_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define PSB_REQUIRE(cond, code, ...)                                                \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            psb_set_error(__VA_ARGS__);                                             \
+            return (code);                                                          \
+        }                                                                           \
+    } while (0)
+
+struct psb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    bool have_run_ev = false, have_k_ev = false;
+    int64_t launches = 0;
+
+    int model = PSB_MODEL_NONE;
+    int N = 0;    // samples
+    int Wn = 0;   // ceil(N / 32)
+
+    // phenotype helpers (both models)
+    uint32_t *d_y1bits = nullptr, *d_y0bits = nullptr, *d_valid = nullptr;  // Wn words
+    // column matrix for k_bitsums: [C][Npad] fp64
+    double *d_cols = nullptr;
+    uint64_t colmask_lo = 0, colmask_hi = 0;   // 2 bits per column: PSB_MASK_*
+    int C = 0, Npad = 0;
+    int col_b = -1, col_q0 = -1, col_w0 = -1;   // LMM: b column, first Q column; Welch cols
+    double y_mean = 0.0;
+
+    // ---- LMM ----
+    int D = 0, J = 0, Jpad = 0, Kpad = 0;
+    int precision = 0;
+    double h2 = 0.0, YKY = 0.0;
+    double *d_L = nullptr;        // [Npad32][Jpad64] fp64, L = P U Sd^-1/2
+    int Lrows = 0;
+    // tensor-core operands (psb_lmm_tc.cu)
+    int8_t *d_Lq = nullptr;       // [jtiles][slices][32 comps][Kpad] int8 (K-major)
+    double *d_scale2 = nullptr;   // [Jpad32] (s_j 2^-B)^2
+    int n_slices = 0, jtiles = 0;
+    void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B)
+
+    // ---- fixed effects ----
+    int q = 0;
+    int continuous = 0;
+    double null_llf = 0.0, null_firth = 0.0;
+    double *d_Z = nullptr;        // [q][Npad] (column c contiguous)
+    double *d_yv = nullptr;       // [Npad]
+    double *d_fixed_const = nullptr;  // OLS precomputed: see psb_fixed.cu
+    std::vector<double> h_ZtZinv; // q x q
+    std::vector<double> h_Zty;    // q
+
+    // ---- variants ----
+    const uint32_t *d_bits = nullptr, *d_miss = nullptr;
+    uint32_t *own_bits = nullptr, *own_miss = nullptr;
+    size_t own_bits_cap = 0, own_miss_cap = 0;   // bytes
+    int64_t S = 0;
+    int Wrow = 0;
+
+    // ---- result table + workspace (capacity in variants) ----
+    int64_t cap = 0;
+    int32_t *d_carriers = nullptr, *d_missing = nullptr;
+    double *d_af = nullptr, *d_prep = nullptr, *d_pvalue = nullptr, *d_beta = nullptr,
+           *d_bse = nullptr, *d_extra = nullptr, *d_betas = nullptr;
+    uint32_t *d_flags = nullptr;
+    int betas_cols = 0;
+    int32_t *d_tab = nullptr;     // [cap][4] 2x2 table n11 n10 n01 n00
+    double *d_sums = nullptr;     // [cap][C]
+    size_t sums_cap = 0;
+    int32_t *d_idx = nullptr;     // compacted tested variant ids (cap + 256)
+    int32_t *d_idx2 = nullptr;    // second list (Firth candidates)
+    int *d_counters = nullptr;    // [8] device counters
+    double *d_a = nullptr;        // [cap] quadratic forms
+    int64_t counts[4] = {0, 0, 0, 0};
+    bool ran = false;
+};
+
+int psb_ensure_capacity(psb_ctx *ctx, int64_t S, int betas_cols);
+int psb_free_model(psb_ctx *ctx);
+
+// psb_varstats.cu
+int psb_launch_bitsums(psb_ctx *ctx);
+int psb_launch_prefilter(psb_ctx *ctx, const psb_params *prm, int lmm_rule);
+
+// psb_lmm_tc.cu
+int psb_lmm_tc_setup(psb_ctx *ctx);
+int psb_lmm_tc_run(psb_ctx *ctx, int n_tested);
+void psb_lmm_tc_free(psb_ctx *ctx);
+
+static inline int psb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,217 @@
+// psb_varstats.cu -- per-variant popcounts, 2x2 table and masked column sums.
+//
+// Replaces the tail of input.read_variant (input.py:439-452: kstrains count, af, missing),
+// the table building of model.pre_filtering (model.py:57-61) and every O(N) masked
+// reduction the models need (x'v for the LMM score, Z'x / y'x for OLS, Welch sums).
+//
+// One warp per variant.  The packed row is read once, coalesced (lane l owns word l of
+// each 32-word chunk); for the fp64 column sums the chunk's words are broadcast by
+// shuffle and lane l takes bit l of word t, so the column read col[32 t + l] is a
+// coalesced 256-byte line that stays in L1/L2 (the columns are shared by all variants).
+#include "psb_internal.cuh"
+
+#define BITSUMS_MAXC 40
+
+template <int HAS_MISS>
+__global__ void __launch_bounds__(256)
+k_bitsums(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ miss, int64_t S,
+          int Wrow, int Wn, const uint32_t *__restrict__ y1, const uint32_t *__restrict__ y0,
+          const uint32_t *__restrict__ valid, const double *__restrict__ cols,
+          uint64_t mask_lo, uint64_t mask_hi, int C, int Npad, int32_t *__restrict__ carriers,
+          int32_t *__restrict__ nmissing, int32_t *__restrict__ tab, double *__restrict__ sums) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (; v < S; v += warps_total) {
+        const uint32_t *row = bits + v * Wrow;
+        const uint32_t *mrow = HAS_MISS ? miss + v * Wrow : nullptr;
+        int c_all = 0, c_miss = 0, n11 = 0, n10 = 0, n01 = 0, n00 = 0;
+        double acc[BITSUMS_MAXC];
+#pragma unroll
+        for (int c = 0; c < BITSUMS_MAXC; ++c) acc[c] = 0.0;
+        for (int w0 = 0; w0 < Wn; w0 += 32) {
+            int w = w0 + lane;
+            uint32_t x = 0, m = 0, vb = 0, a1 = 0, a0 = 0;
+            if (w < Wn) {
+                x = __ldg(row + w);
+                if (HAS_MISS) m = __ldg(mrow + w);
+                vb = __ldg(valid + w);
+                a1 = __ldg(y1 + w);
+                a0 = __ldg(y0 + w);
+            }
+            m &= vb;
+            x &= vb & ~m;          // a NaN genotype is not a carrier bit
+            uint32_t k1 = x & ~m, k0 = ~x & ~m & vb;
+            c_all += __popc(x | m);
+            c_miss += __popc(m);
+            n11 += __popc(a1 & k1);
+            n10 += __popc(a1 & k0);
+            n01 += __popc(a0 & k1);
+            n00 += __popc(a0 & k0);
+            if (C > 0) {
+                int tmax = min(32, Wn - w0);
+                for (int t = 0; t < tmax; ++t) {
+                    uint32_t xt = __shfl_sync(0xffffffffu, x, t);
+                    uint32_t k1t = __shfl_sync(0xffffffffu, k1, t);
+                    uint32_t k0t = __shfl_sync(0xffffffffu, k0, t);
+                    bool bx = (xt >> lane) & 1u, b1 = (k1t >> lane) & 1u, b0 = (k0t >> lane) & 1u;
+                    const double *cp = cols + (size_t)(w0 + t) * 32 + lane;
+#pragma unroll
+                    for (int c = 0; c < BITSUMS_MAXC; ++c) {
+                        if (c < C) {
+                            int mk = c < 32 ? (int)((mask_lo >> (2 * c)) & 3u) : (int)((mask_hi >> (2 * (c - 32))) & 3u);
+                            bool on = mk == PSB_MASK_RAW ? bx : (mk == PSB_MASK_K1 ? b1 : b0);
+                            double val = __ldg(cp + (size_t)c * Npad);
+                            if (on) acc[c] += val;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_all += __shfl_xor_sync(0xffffffffu, c_all, o);
+            c_miss += __shfl_xor_sync(0xffffffffu, c_miss, o);
+            n11 += __shfl_xor_sync(0xffffffffu, n11, o);
+            n10 += __shfl_xor_sync(0xffffffffu, n10, o);
+            n01 += __shfl_xor_sync(0xffffffffu, n01, o);
+            n00 += __shfl_xor_sync(0xffffffffu, n00, o);
+        }
+#pragma unroll
+        for (int c = 0; c < BITSUMS_MAXC; ++c) {
+            if (c < C) {
+                double a = acc[c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+                if (lane == 0) sums[v * C + c] = a;
+            }
+        }
+        if (lane == 0) {
+            carriers[v] = c_all;
+            nmissing[v] = c_miss;
+            tab[v * 4 + 0] = n11;
+            tab[v * 4 + 1] = n10;
+            tab[v * 4 + 2] = n01;
+            tab[v * 4 + 3] = n00;
+        }
+    }
+}
+
+int psb_launch_bitsums(psb_ctx *c) {
+    uint64_t mask_lo = c->colmask_lo, mask_hi = c->colmask_hi;
+    PSB_REQUIRE(c->C <= BITSUMS_MAXC, PSB_ERR_UNSUPPORTED,
+                "too many covariate columns for the device path (%d > %d)", c->C, BITSUMS_MAXC);
+    if (c->S == 0) return PSB_OK;
+    int warps_per_block = 8;
+    int64_t blocks = (c->S + warps_per_block - 1) / warps_per_block;
+    int64_t maxb = (int64_t)c->sm_count * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (c->d_miss)
+        k_bitsums<1><<<(int)blocks, 256, 0, c->stream>>>(
+            c->d_bits, c->d_miss, c->S, c->Wrow, c->Wn, c->d_y1bits, c->d_y0bits, c->d_valid,
+            c->d_cols, mask_lo, mask_hi, c->C, c->Npad, c->d_carriers, c->d_missing, c->d_tab, c->d_sums);
+    else
+        k_bitsums<0><<<(int)blocks, 256, 0, c->stream>>>(
+            c->d_bits, nullptr, c->S, c->Wrow, c->Wn, c->d_y1bits, c->d_y0bits, c->d_valid,
+            c->d_cols, mask_lo, mask_hi, c->C, c->Npad, c->d_carriers, c->d_missing, c->d_tab, c->d_sums);
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    return PSB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// AF filter + pre_filtering (input.py:608 / :693, model.py:31-70) + compaction of the
+// variants that go on to a model fit.  One thread per variant.
+// ---------------------------------------------------------------------------------
+#include "psb_math.cuh"
+
+__global__ void __launch_bounds__(256)
+k_prefilter(int64_t S, int N, const int32_t *__restrict__ carriers,
+            const int32_t *__restrict__ nmissing, const int32_t *__restrict__ tab,
+            const double *__restrict__ sums, int C, int col_w0, psb_params prm, int lmm_rule,
+            double *__restrict__ af_out, double *__restrict__ prep_out,
+            double *__restrict__ pvalue, double *__restrict__ beta, double *__restrict__ bse,
+            double *__restrict__ extra, uint32_t *__restrict__ flags, int32_t *__restrict__ idx,
+            int *__restrict__ counters) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= S) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    int carr = carriers[v], nm = nmissing[v];
+    double af = (double)carr / (double)N;           // input.py:446
+    double missing = (double)nm / (double)N;        // input.py:452
+    uint32_t f = 0;
+    double prep = nan;
+    if (prm.options & PSB_OPT_NO_PREFILTER) {
+        f = PSB_F_TESTED;
+        int pos = atomicAdd(&counters[0], 1);
+        idx[pos] = (int32_t)v;
+    } else if (!(prm.min_af <= af && af <= prm.max_af) || missing > prm.max_missing) {
+        f = PSB_F_AF_FILTER | PSB_F_PREFILTER;
+    } else {
+        if (prm.continuous) {
+            // Welch t-test, scipy.stats.ttest_ind(p[k==1], p[k==0], equal_var=False)
+            const double *s = sums + v * C + col_w0;
+            double n1 = (double)(carr - nm), n0 = (double)(N - carr);
+            if (n1 < 1.0 || n0 < 1.0) {
+                prep = nan;
+            } else {
+                double m1 = s[0] / n1, m0 = s[2] / n0;
+                double v1 = (s[1] - s[0] * m1) / (n1 - 1.0);   // nan when n1 == 1
+                double v0 = (s[3] - s[2] * m0) / (n0 - 1.0);
+                if (n1 < 2.0) v1 = nan;
+                if (n0 < 2.0) v0 = nan;
+                double vn1 = v1 / n1, vn0 = v0 / n0;
+                double df = (vn1 + vn0) * (vn1 + vn0) /
+                            (vn1 * vn1 / (n1 - 1.0) + vn0 * vn0 / (n0 - 1.0));
+                if (isnan(df)) df = 1.0;
+                double t = (m1 - m0) / sqrt(vn1 + vn0);
+                prep = psb_t2_sf(t * t, df);
+            }
+        } else {
+            int n11 = tab[v * 4 + 0], n10 = tab[v * 4 + 1], n01 = tab[v * 4 + 2], n00 = tab[v * 4 + 3];
+            int le1 = (n11 <= 1) + (n10 <= 1) + (n01 <= 1) + (n00 <= 1);
+            int le5 = (n11 <= 5) + (n10 <= 5) + (n01 <= 5) + (n00 <= 5);
+            if (le1 > 0 || le5 > 1) f |= PSB_F_BAD_CHISQ;      // model.py:65-66
+            double r1 = (double)(n11 + n10), r0 = (double)(n01 + n00);
+            double c1 = (double)(n11 + n01), c0 = (double)(n10 + n00);
+            double n = r1 + r0;
+            double e11 = r1 * c1 / n, e10 = r1 * c0 / n, e01 = r0 * c1 / n, e00 = r0 * c0 / n;
+            if (n > 0.0 && (e11 == 0.0 || e10 == 0.0 || e01 == 0.0 || e00 == 0.0)) {
+                prep = nan;   // scipy raises ValueError here; reported as a failed pre-filter
+            } else {
+                double d11 = n11 - e11, d10 = n10 - e10, d01 = n01 - e01, d00 = n00 - e00;
+                double chi2 = d11 * d11 / e11 + d10 * d10 / e10 + d01 * d01 / e01 + d00 * d00 / e00;
+                prep = psb_chi2_sf1(chi2);
+            }
+        }
+        bool fail = lmm_rule ? (prep >= prm.filter_pvalue) : (prep > prm.filter_pvalue);
+        if (fail || !isfinite(prep)) {
+            f |= PSB_F_PREFILTER_FAILED | PSB_F_PREFILTER;
+        } else {
+            f |= PSB_F_TESTED;
+            int pos = atomicAdd(&counters[0], 1);
+            idx[pos] = (int32_t)v;
+        }
+    }
+    if (f & PSB_F_PREFILTER) atomicAdd(&counters[1], 1);
+    af_out[v] = af;
+    prep_out[v] = prep;
+    pvalue[v] = nan;
+    beta[v] = nan;
+    bse[v] = nan;
+    extra[v] = nan;
+    flags[v] = f;
+}
+
+int psb_launch_prefilter(psb_ctx *c, const psb_params *prm, int lmm_rule) {
+    PSB_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(int), c->stream));
+    if (c->S == 0) return PSB_OK;
+    int blocks = psb_div_up(c->S, 256);
+    k_prefilter<<<blocks, 256, 0, c->stream>>>(c->S, c->N, c->d_carriers, c->d_missing, c->d_tab,
+                                               c->d_sums, c->C, c->col_w0, *prm, lmm_rule, c->d_af,
+                                               c->d_prep, c->d_pvalue, c->d_beta, c->d_bse,
+                                               c->d_extra, c->d_flags, c->d_idx, c->d_counters);
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    return PSB_OK;
+}

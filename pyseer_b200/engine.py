@@ -1,0 +1,255 @@
+"""Thin Python driver over the C ABI: one :class:`Engine` per GPU.
+
+This is plumbing only -- packing presence/absence vectors into the bit rows the library
+expects, moving result columns back into NumPy arrays, translating flag bits into the
+reference's note strings.  All per-variant arithmetic happens in the CUDA library.
+"""
+import ctypes
+from ctypes import c_float, c_int, c_int64, c_int8, c_uint32, c_void_p, byref
+
+import numpy as np
+
+from . import _lib
+from ._lib import PsbParams, PsbResults, check
+
+
+def words_per_row(n_samples):
+    """uint32 words per packed row: ceil(N/32) rounded up to 16-byte rows."""
+    w = (n_samples + 31) // 32
+    return (w + 3) // 4 * 4
+
+
+def pack_rows(k):
+    """Pack presence/absence rows into the library's bit layout.
+
+    k: (S, N) array; non-zero finite entries are carriers, NaN entries are missing
+    genotypes (input.py:428-430).  Returns (bits, missing_or_None), uint32 (S, W) arrays
+    with bit (i % 32) of word (i // 32) = sample i."""
+    k = np.asarray(k)
+    if k.ndim == 1:
+        k = k.reshape(1, -1)
+    S, N = k.shape
+    W = words_per_row(N)
+    miss = None
+    if k.dtype.kind == 'f':
+        nanmask = np.isnan(k)
+        present = (k == 1) | ((k != 0) & ~nanmask)
+        if nanmask.any():
+            miss = _pack_bool(nanmask, W)
+    else:
+        present = k != 0
+    return _pack_bool(present, W), miss
+
+
+def _pack_bool(b, W):
+    S, N = b.shape
+    by = np.packbits(b, axis=1, bitorder='little')
+    out = np.zeros((S, W * 4), dtype=np.uint8)
+    out[:, :by.shape[1]] = by
+    return np.ascontiguousarray(out).view('<u4').reshape(S, W)
+
+
+def unpack_rows(bits, n_samples):
+    """Inverse of pack_rows for the presence bits -> (S, N) uint8."""
+    by = np.ascontiguousarray(bits).view(np.uint8).reshape(bits.shape[0], -1)
+    return np.unpackbits(by, axis=1, bitorder='little')[:, :n_samples]
+
+
+def notes_from_flags(f):
+    return set(s for bit, s in _lib.NOTE_BITS if f & bit)
+
+
+class Results(object):
+    """Result table of one run (NumPy columns, submission order)."""
+    __slots__ = ['carriers', 'missing', 'af', 'prep', 'pvalue', 'beta', 'bse', 'extra', 'betas',
+                 'flags', 'counts']
+
+
+class Engine(object):
+    """One GPU context (``psb_ctx``)."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self._ctx = c_void_p()
+        check(self.lib.psb_create(int(device), byref(self._ctx)))
+        self.device = device
+        self.n_samples = 0
+        self.q = 0
+        self.model = None
+        self._keep = []          # host buffers that must outlive async copies
+
+    # -- lifecycle -------------------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            self.lib.psb_destroy(self._ctx)
+            self._ctx = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def sync(self):
+        check(self.lib.psb_sync(self._ctx))
+
+    # -- model state -----------------------------------------------------------------
+    @staticmethod
+    def _dptr(a):
+        return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+    def lmm_setup(self, X, y, U, S, h2, precision=0):
+        """State of lmm_cov.LMM after lmm.initialise_lmm (lmm.py:114-116)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        n, d = X.shape
+        if y.shape[0] != n or U.shape != (n, n - d) or S.shape[0] != n - d:
+            raise ValueError('shape mismatch: X %s y %s U %s S %s' %
+                             (X.shape, y.shape, U.shape, S.shape))
+        check(self.lib.psb_lmm_setup(self._ctx, n, d, self._dptr(X), self._dptr(y),
+                                     self._dptr(U), self._dptr(S), float(h2), int(precision)))
+        self.n_samples, self.q, self.model = n, 0, 'lmm'
+
+    def fixed_setup(self, Z, y, continuous, null_llf, null_firth):
+        """Shared arguments of fixed_effects_regression (model.py:202-205)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        n, q = Z.shape
+        if y.shape[0] != n:
+            raise ValueError('shape mismatch')
+        check(self.lib.psb_fixed_setup(self._ctx, n, q, self._dptr(Z), self._dptr(y),
+                                       int(bool(continuous)), float(null_llf),
+                                       float(null_firth)))
+        self.n_samples, self.q, self.model = n, q, 'fixed'
+
+    def fit_null(self, Z, y, continuous, firth=False):
+        """model.fit_null on the device.  Returns (params, bse, llf, status_flags)."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
+        n, q = Z.shape
+        params = np.zeros(q)
+        bse = np.zeros(q)
+        llf = ctypes.c_double(0.0)
+        st = c_uint32(0)
+        check(self.lib.psb_fit_null(self._ctx, n, q, self._dptr(Z), self._dptr(y),
+                                    int(bool(continuous)), int(bool(firth)), self._dptr(params),
+                                    self._dptr(bse), byref(llf), byref(st)))
+        return params, bse, llf.value, st.value
+
+    # -- variants ----------------------------------------------------------------------
+    def submit(self, bits, missing=None):
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        if bits.ndim != 2:
+            raise ValueError('bits must be (n_variants, words_per_row)')
+        mp = None
+        if missing is not None:
+            missing = np.ascontiguousarray(missing, dtype=np.uint32)
+            if missing.shape != bits.shape:
+                raise ValueError('missing must have the shape of bits')
+            mp = missing.ctypes.data_as(c_void_p)
+        self._keep = [bits, missing]
+        check(self.lib.psb_submit(self._ctx, bits.ctypes.data_as(c_void_p), mp,
+                                  bits.shape[0], bits.shape[1]))
+        self.n_variants = bits.shape[0]
+
+    def submit_device(self, d_bits_ptr, n_variants, wpr, d_missing_ptr=None):
+        check(self.lib.psb_submit_device(self._ctx, c_void_p(d_bits_ptr),
+                                         c_void_p(d_missing_ptr) if d_missing_ptr else None,
+                                         int(n_variants), int(wpr)))
+        self.n_variants = int(n_variants)
+
+    def synth_device(self, seed, first_variant, n_variants, af_lo=0.02, af_hi=0.98,
+                     planted_every=0, y_sign=None):
+        ys = None
+        if y_sign is not None:
+            y_sign = np.ascontiguousarray(y_sign, dtype=np.int8)
+            ys = y_sign.ctypes.data_as(ctypes.POINTER(c_int8))
+        check(self.lib.psb_synth_device(self._ctx, int(seed), int(first_variant), int(n_variants),
+                                        self.n_samples, af_lo, af_hi, int(planted_every), ys))
+        self.n_variants = int(n_variants)
+
+    # -- run ---------------------------------------------------------------------------
+    @staticmethod
+    def _params(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous):
+        return PsbParams(float(min_af), float(max_af), float(max_missing), float(filter_pvalue),
+                         float(lrt_pvalue), int(bool(continuous)), 0)
+
+    def run_lmm(self, min_af=0.01, max_af=0.99, max_missing=0.05, filter_pvalue=1.0,
+                lrt_pvalue=1.0, continuous=False):
+        p = self._params(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous)
+        check(self.lib.psb_run_lmm(self._ctx, byref(p)))
+
+    def run_fixed(self, min_af=0.01, max_af=0.99, max_missing=0.05, filter_pvalue=1.0,
+                  lrt_pvalue=1.0, continuous=False):
+        p = self._params(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous)
+        check(self.lib.psb_run_fixed(self._ctx, byref(p)))
+
+    def fetch(self, columns=None):
+        S = self.n_variants
+        r = Results()
+        r.carriers = np.empty(S, dtype=np.int32)
+        r.missing = np.empty(S, dtype=np.int32)
+        r.flags = np.empty(S, dtype=np.uint32)
+        for f in ('af', 'prep', 'pvalue', 'beta', 'bse', 'extra'):
+            setattr(r, f, np.empty(S, dtype=np.float64))
+        nb = self.q - 1 if self.model == 'fixed' and self.q > 1 else 0
+        r.betas = np.empty((S, nb), dtype=np.float64)
+        out = PsbResults()
+        for f in ('carriers', 'missing', 'af', 'prep', 'pvalue', 'beta', 'bse', 'extra', 'flags'):
+            if columns is None or f in columns:
+                setattr(out, f, getattr(r, f).ctypes.data_as(c_void_p))
+        if nb and (columns is None or 'betas' in columns):
+            out.betas = r.betas.ctypes.data_as(c_void_p)
+        check(self.lib.psb_fetch(self._ctx, byref(out)))
+        r.counts = self.counts()
+        return r
+
+    def results_device(self):
+        out = PsbResults()
+        check(self.lib.psb_results_device(self._ctx, byref(out)))
+        return out
+
+    def counts(self):
+        c = (c_int64 * 4)()
+        check(self.lib.psb_counts(self._ctx, c))
+        return {'loaded': c[0], 'prefiltered': c[1], 'tested': c[2], 'passed': c[3]}
+
+    def last_ms(self, which=0):
+        ms = c_float(0)
+        check(self.lib.psb_last_ms(self._ctx, which, byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = c_int64(0)
+        check(self.lib.psb_launch_count(self._ctx, byref(n)))
+        return n.value
+
+
+def device_count():
+    n = c_int(0)
+    check(_lib.load().psb_device_count(byref(n)))
+    return n.value
+
+
+def synth_host(seed, first_variant, n_variants, n_samples, af_lo=0.02, af_hi=0.98,
+               planted_every=0, y_sign=None):
+    """Host twin of Engine.synth_device (same generator, same rows)."""
+    lib = _lib.load()
+    W = words_per_row(n_samples)
+    out = np.zeros((n_variants, W), dtype=np.uint32)
+    ys = None
+    if y_sign is not None:
+        y_sign = np.ascontiguousarray(y_sign, dtype=np.int8)
+        ys = y_sign.ctypes.data_as(ctypes.POINTER(c_int8))
+    check(lib.psb_synth_host(int(seed), int(first_variant), int(n_variants), int(n_samples),
+                             af_lo, af_hi, int(planted_every), ys,
+                             out.ctypes.data_as(ctypes.POINTER(c_uint32)), W))
+    return out
