@@ -18,6 +18,7 @@
 #ifndef PYSEER_B200_H
 #define PYSEER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -141,7 +142,9 @@ int psb_run_lmm(psb_ctx *ctx, const psb_params *params);
 /* replaces model.fixed_effects_regression (model.py:202-394) for every submitted variant */
 int psb_run_fixed(psb_ctx *ctx, const psb_params *params);
 
-/* Copies the result table to host arrays (synchronises the context stream). */
+/* Copies the result table to caller arrays (synchronises the context stream).  The
+ * destination pointers may be host memory (pinned or pageable) or device memory (e.g. a
+ * buffer that is then gathered across ranks with NCCL). */
 int psb_fetch(psb_ctx *ctx, const psb_results *out);
 /* Device pointers of the result table of the last run (valid until the next run);
  * lets the caller gather tables across ranks with NCCL without a host round trip. */
@@ -150,11 +153,24 @@ int psb_results_device(psb_ctx *ctx, psb_results *out_device_ptrs);
  * (__main__.py:831-834 semantics, printed == tested - filtered unless --print-filtered) */
 int psb_counts(psb_ctx *ctx, int64_t out[4]);
 
+/* ---- pinned host staging -------------------------------------------------------- */
+/* Page-locked host buffers for psb_submit / psb_fetch (input.py's k-mer streaming becomes
+ * a pinned-host -> device staging pipeline).  psb_download_bits copies the currently
+ * submitted device rows (e.g. made by psb_synth_device) into a host buffer of
+ * n_variants * words_per_row uint32. */
+int psb_host_alloc(size_t bytes, void **out);
+int psb_host_free(void *ptr);
+int psb_download_bits(psb_ctx *ctx, uint32_t *out_bits);
+
 /* ---- measurement ------------------------------------------------------------- */
 /* CUDA-event timers on the context stream.  which: 0 = whole last psb_run_*,
  * 1 = dominant kernel of the last run (LMM: the rotation/quadratic-form contraction;
  * fixed effects: the regression kernel).  Returns milliseconds. */
 int psb_last_ms(psb_ctx *ctx, int32_t which, float *ms);
+/* User event slots (0..7) recorded on the context stream, for timing a region that spans
+ * several calls with CUDA events; psb_event_elapsed synchronises on slot b. */
+int psb_event_record(psb_ctx *ctx, int32_t slot);
+int psb_event_elapsed(psb_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
 /* number of kernels the library launched on this context since creation */
 int psb_launch_count(psb_ctx *ctx, int64_t *n);
 

@@ -74,6 +74,8 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_sync', 'psb_lmm_setup', 'psb_fixed_setup', 'psb_fit_null', 'psb_submit',
            'psb_submit_device', 'psb_run_lmm', 'psb_run_fixed', 'psb_fetch',
            'psb_results_device', 'psb_counts', 'psb_last_ms', 'psb_launch_count',
+           'psb_host_alloc', 'psb_host_free', 'psb_download_bits', 'psb_event_record',
+           'psb_event_elapsed',
            'psb_synth_device', 'psb_synth_host', 'psb_host_chi2_sf1', 'psb_host_f_sf_1',
            'psb_host_t2_sf']
 
@@ -108,6 +110,11 @@ def load():
     lib.psb_counts.argtypes = [c_void_p, POINTER(c_int64)]
     lib.psb_last_ms.argtypes = [c_void_p, c_int32, POINTER(c_float)]
     lib.psb_launch_count.argtypes = [c_void_p, POINTER(c_int64)]
+    lib.psb_host_alloc.argtypes = [ctypes.c_size_t, POINTER(c_void_p)]
+    lib.psb_host_free.argtypes = [c_void_p]
+    lib.psb_download_bits.argtypes = [c_void_p, c_void_p]
+    lib.psb_event_record.argtypes = [c_void_p, c_int32]
+    lib.psb_event_elapsed.argtypes = [c_void_p, c_int32, c_int32, POINTER(c_float)]
     lib.psb_synth_device.argtypes = [c_void_p, c_uint64, c_int64, c_int64, c_int32, c_double,
                                      c_double, c_int32, POINTER(c_int8)]
     lib.psb_synth_host.argtypes = [c_uint64, c_int64, c_int64, c_int32, c_double, c_double,

@@ -54,6 +54,7 @@ int psb_create(int device_id, psb_ctx **out) {
     PSB_CUDA(cudaEventCreate(&c->ev_run1));
     PSB_CUDA(cudaEventCreate(&c->ev_k0));
     PSB_CUDA(cudaEventCreate(&c->ev_k1));
+    for (int i = 0; i < 8; ++i) PSB_CUDA(cudaEventCreate(&c->ev_user[i]));
     PSB_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
     *out = c;
     return PSB_OK;
@@ -105,6 +106,7 @@ int psb_destroy(psb_ctx *c) {
     free_dev(c->own_bits); free_dev(c->own_miss); free_dev(c->d_counters);
     cudaEventDestroy(c->ev_run0); cudaEventDestroy(c->ev_run1);
     cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev_user[i]);
     cudaStreamDestroy(c->stream);
     delete c;
     return PSB_OK;
@@ -225,7 +227,7 @@ int psb_fetch(psb_ctx *c, const psb_results *out) {
     cudaStream_t st = c->stream;
 #define CP(field, src, type)                                                                 \
     if (out->field && S > 0)                                                                 \
-        PSB_CUDA(cudaMemcpyAsync(out->field, src, S * sizeof(type), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaMemcpyAsync(out->field, src, S * sizeof(type), cudaMemcpyDefault, st));
     CP(carriers, c->d_carriers, int32_t)
     CP(missing, c->d_missing, int32_t)
     CP(af, c->d_af, double)
@@ -238,7 +240,7 @@ int psb_fetch(psb_ctx *c, const psb_results *out) {
 #undef CP
     if (out->betas && S > 0 && c->model == PSB_MODEL_FIXED && c->q > 1)
         PSB_CUDA(cudaMemcpyAsync(out->betas, c->d_betas, S * (c->q - 1) * sizeof(double),
-                                 cudaMemcpyDeviceToHost, st));
+                                 cudaMemcpyDefault, st));
     PSB_CUDA(cudaStreamSynchronize(st));
     return PSB_OK;
 }
@@ -279,6 +281,44 @@ int psb_last_ms(psb_ctx *c, int32_t which, float *ms) {
         PSB_CUDA(cudaEventSynchronize(c->ev_k1));
         PSB_CUDA(cudaEventElapsedTime(ms, c->ev_k0, c->ev_k1));
     }
+    return PSB_OK;
+}
+
+int psb_event_record(psb_ctx *c, int32_t slot) {
+    PSB_REQUIRE(c && slot >= 0 && slot < 8, PSB_ERR_ARG, "bad event slot");
+    PSB_CUDA(cudaSetDevice(c->device));
+    PSB_CUDA(cudaEventRecord(c->ev_user[slot], c->stream));
+    return PSB_OK;
+}
+
+int psb_event_elapsed(psb_ctx *c, int32_t a, int32_t b, float *ms) {
+    PSB_REQUIRE(c && ms && a >= 0 && a < 8 && b >= 0 && b < 8, PSB_ERR_ARG, "bad event slot");
+    PSB_CUDA(cudaSetDevice(c->device));
+    PSB_CUDA(cudaEventSynchronize(c->ev_user[b]));
+    PSB_CUDA(cudaEventElapsedTime(ms, c->ev_user[a], c->ev_user[b]));
+    return PSB_OK;
+}
+
+int psb_host_alloc(size_t bytes, void **out) {
+    PSB_REQUIRE(out, PSB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    PSB_CUDA(cudaHostAlloc(out, bytes > 0 ? bytes : 1, cudaHostAllocPortable));
+    return PSB_OK;
+}
+
+int psb_host_free(void *ptr) {
+    if (ptr) PSB_CUDA(cudaFreeHost(ptr));
+    return PSB_OK;
+}
+
+int psb_download_bits(psb_ctx *c, uint32_t *out_bits) {
+    PSB_REQUIRE(c && out_bits, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "no rows submitted");
+    PSB_CUDA(cudaSetDevice(c->device));
+    size_t bytes = (size_t)c->S * c->Wrow * sizeof(uint32_t);
+    if (bytes)
+        PSB_CUDA(cudaMemcpyAsync(out_bits, c->d_bits, bytes, cudaMemcpyDeviceToHost, c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
     return PSB_OK;
 }
 

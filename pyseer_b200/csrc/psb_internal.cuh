@@ -43,6 +43,7 @@ struct psb_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_run0 = nullptr, ev_run1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_user[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool have_run_ev = false, have_k_ev = false;
     int64_t launches = 0;
 

@@ -212,6 +212,27 @@ class Engine(object):
         r.counts = self.counts()
         return r
 
+    def fetch_into(self, pointers):
+        """psb_fetch into caller-owned buffers: ``pointers`` maps column name -> raw address
+        (host or device, e.g. ``torch.Tensor.data_ptr()``)."""
+        out = PsbResults()
+        for f, ptr in pointers.items():
+            setattr(out, f, c_void_p(int(ptr)))
+        check(self.lib.psb_fetch(self._ctx, byref(out)))
+
+    def download_bits(self, out):
+        """Copy the submitted device rows into ``out`` (uint32 (S, W) array, ideally pinned)."""
+        assert out.dtype == np.uint32 and out.flags['C_CONTIGUOUS']
+        check(self.lib.psb_download_bits(self._ctx, out.ctypes.data_as(c_void_p)))
+
+    def event_record(self, slot):
+        check(self.lib.psb_event_record(self._ctx, int(slot)))
+
+    def event_elapsed(self, a, b):
+        ms = c_float(0)
+        check(self.lib.psb_event_elapsed(self._ctx, int(a), int(b), byref(ms)))
+        return ms.value
+
     def results_device(self):
         out = PsbResults()
         check(self.lib.psb_results_device(self._ctx, byref(out)))
@@ -231,6 +252,31 @@ class Engine(object):
         n = c_int64(0)
         check(self.lib.psb_launch_count(self._ctx, byref(n)))
         return n.value
+
+
+class PinnedBuffer(object):
+    """Page-locked host array (cudaHostAlloc) for psb_submit / psb_fetch staging."""
+
+    def __init__(self, shape, dtype):
+        self.lib = _lib.load()
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        self._ptr = c_void_p()
+        check(self.lib.psb_host_alloc(nbytes, byref(self._ptr)))
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            self.lib.psb_host_free(self._ptr)
+            self._ptr = c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def device_count():
