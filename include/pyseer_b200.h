@@ -101,7 +101,7 @@ int psb_sync(psb_ctx *ctx);
  * last column ones, lmm.py:95-99), phenotype y, kernel eigenvectors U (N x (N-D)
  * row-major) and eigenvalues S (lmm_cov.py:88-103) and h2 (lmm_cov.findH2).  Builds
  * the rotated operands used by fit_lmm_block (lmm.py:228-260).
- * precision: 0 = FP64 CUDA-core contraction; k in [3,8] = exact k-slice int8
+ * precision: 0 = FP64 CUDA-core contraction; k in [3,7] = exact k-slice int8
  * tensor-core contraction (tcgen05).  Returns PSB_ERR_H2 when h2 is outside [0,1). */
 int psb_lmm_setup(psb_ctx *ctx, int32_t n_samples, int32_t n_cov, const double *X,
                   const double *y, const double *U, const double *S, double h2,

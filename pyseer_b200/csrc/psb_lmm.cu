@@ -284,8 +284,8 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
                              const double *U, const double *S, double h2, int32_t precision) {
     PSB_REQUIRE(c && X && y && U && S, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(N > 1 && D >= 1 && D < N, PSB_ERR_ARG, "bad shape N=%d D=%d", N, D);
-    PSB_REQUIRE(precision == 0 || (precision >= 3 && precision <= 8), PSB_ERR_ARG,
-                "precision must be 0 (fp64) or 3..8 int8 slices, got %d", precision);
+    PSB_REQUIRE(precision == 0 || (precision >= 3 && precision <= 7), PSB_ERR_ARG,
+                "precision must be 0 (fp64) or 3..7 int8 slices, got %d", precision);
     // lmm_cov.py:667-670: nLLeval returns no 'beta' for h2 outside [0,1) -> KeyError in
     // fit_lmm_block (tests/lmm_test.py:416-417)
     PSB_REQUIRE(h2 >= 0.0 && h2 < 1.0, PSB_ERR_H2, "h2 = %g outside [0, 1)", h2);

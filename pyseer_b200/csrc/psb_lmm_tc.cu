@@ -1,5 +1,518 @@
-// placeholder, replaced below
+// psb_lmm_tc.cu -- the LMM rotation / quadratic form on the 5th-generation tensor cores.
+//
+// Replaces the dense contraction of fastlmm nLLeval: rotate() `U.T.dot(P snps)`
+// (lmm_cov.py:165-194) followed by computeAKA `(Usnps / Sd * Usnps).sum(0)`
+// (lmm_cov.py:885-899), i.e. for every tested variant x (a 0/1 column)
+//        a = || L' x ||^2 ,      L = P U diag(Sd^-1/2)   (N x J, J = N - D).
+//
+// Exactness.  x is 0/1, so L'x is a sum of selected rows of L.  Every column j of L is
+// scaled by a power of two and rounded to a (8k-2)-bit integer, which is split into k
+// balanced base-256 digits d_s in [-128,127] ("slices").  int8 x {0,1} products
+// accumulate exactly in int32 (|sum| <= 128 N), and the epilogue recombines
+// g_j = sum_s 256^s D_s in fp64 -- exact below 2^53 -- so the only error left is the
+// rounding of L to 8k-2 bits relative to its column maximum (k = 5: 2^-38).  This is an
+// integer GEMM by construction; it is not a reduced-precision approximation of an fp GEMM.
+//
+// Kernel structure (one persistent CTA per SM, 128 variants per tile, 10 warps):
+//   warp 0      TMA producer: streams the k-sliced int8 operand (B, K-major, 128B swizzle)
+//               through an smem ring with cp.async.bulk.tensor + mbarrier complete_tx.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::i8, M=128, N=32k, K=32;
+//               A (the variants) comes from TENSOR MEMORY, B from shared memory,
+//               accumulators (int32) live in TMEM, double buffered.
+//   warps 2-5   expanders: each thread owns one variant (= one TMEM lane); it turns its
+//               packed presence/absence bits (staged once per tile in smem, 1 bit/sample)
+//               into 0/1 bytes in registers and writes them straight into TMEM with
+//               tcgen05.st -- the expanded operand never touches shared memory or HBM.
+//   warps 6-9   epilogue: tcgen05.ld the int32 accumulators, recombine the slices in fp64,
+//               square, scale and accumulate a[v] in a register across all component tiles.
+// HBM sees N/8 bytes per variant; L2 serves the sliced operand to all CTAs.
+#include <cuda.h>
+
+#include <algorithm>
+
 #include "psb_internal.cuh"
-int psb_lmm_tc_setup(psb_ctx *c) { psb_set_error("int8 tensor path not built yet"); return PSB_ERR_UNSUPPORTED; }
-int psb_lmm_tc_run(psb_ctx *c, int n) { return PSB_ERR_UNSUPPORTED; }
-void psb_lmm_tc_free(psb_ctx *c) {}
+
+#define TC_THREADS 320
+#define TC_TILE_V 128          // variants per CTA tile (UMMA M)
+#define TC_JT 32               // components per accumulator tile
+#define TC_KSTAGE 128          // samples per pipeline stage (one 128-byte swizzle row)
+#define TC_MAX_BSTAGES 12
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a pipeline bug becomes a trapped launch (reported through cudaGetLastError)
+// instead of a hung GPU.  The bound is minutes of spinning, far above any legitimate wait.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                            int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory operand descriptor (rows of 128 bytes, 8-row
+// groups 1024 bytes apart).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+    return d;
+}
+
+struct TcArgs {
+    const uint32_t *bits;     // packed rows
+    const int32_t *idx;       // tested variant ids
+    const double *scale2;     // per component (s_j)^2
+    double *a_out;            // [variant id]
+    int Wrow;                 // words per packed row in global memory
+    int n_tested;
+    int nks;                  // K stages (Kpad / 128)
+    int jtiles;
+    int pitch;                // smem bit-row pitch in words (== 4 mod 32)
+    int n_bstages;
+};
+
+// ---------------------------------------------------------------------------------------
+template <int NSL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
+    constexpr int UMMA_N = TC_JT * NSL;                 // accumulator columns per buffer
+    constexpr int A_COL0 = 2 * UMMA_N;                  // first TMEM column of the A ring
+    constexpr int NA = (512 - A_COL0) / 32;             // A ring stages (32 columns = 128 samples)
+    constexpr uint32_t STAGE_BYTES = UMMA_N * TC_KSTAGE;
+    static_assert(NA >= 2, "too many slices for the TMEM budget");
+    // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N, M = 128
+    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UMMA_N >> 3) << 17) |
+                               ((uint32_t)(TC_TILE_V >> 4) << 24);
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nb = args.n_bstages;
+    uint8_t *sB = smem;                                               // nb stages
+    uint32_t *sBits = (uint32_t *)(sB + (size_t)nb * STAGE_BYTES);    // 128 x pitch words
+    uint64_t *bars = (uint64_t *)(sBits + (size_t)TC_TILE_V * args.pitch);
+    uint64_t *fullB = bars;                       // [nb]
+    uint64_t *emptyB = fullB + TC_MAX_BSTAGES;    // [nb]
+    uint64_t *aFull = emptyB + TC_MAX_BSTAGES;    // [NA] (<= 16)
+    uint64_t *aEmpty = aFull + 16;
+    uint64_t *accFull = aEmpty + 16;              // [2]
+    uint64_t *accEmpty = accFull + 2;             // [2]
+    uint32_t *tmem_slot = (uint32_t *)(accEmpty + 2);
+    int32_t *sRows = (int32_t *)(tmem_slot + 2);  // [128]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = (args.n_tested + TC_TILE_V - 1) / TC_TILE_V;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nb; ++i) {
+            mbar_init(smem_u32(&fullB[i]), 1);
+            mbar_init(smem_u32(&emptyB[i]), 1);
+        }
+        for (int i = 0; i < NA; ++i) {
+            mbar_init(smem_u32(&aFull[i]), 4);
+            mbar_init(smem_u32(&aEmpty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&accFull[i]), 1);
+            mbar_init(smem_u32(&accEmpty[i]), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(tmem_slot)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int jt = 0; jt < args.jtiles; ++jt)
+                    for (int ks = 0; ks < args.nks; ++ks) {
+                        mbar_wait(smem_u32(&emptyB[st]), ph ^ 1);
+                        uint32_t bar = smem_u32(&fullB[st]);
+                        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+                        tma_load_2d(smem_u32(sB + (size_t)st * STAGE_BYTES), &tmap, bar,
+                                    ks * TC_KSTAGE, jt * UMMA_N);
+                        if (++st == nb) { st = 0; ph ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int sb = 0, sa = 0, acc = 0;
+            uint32_t phb = 0, pha = 0, phacc = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int jt = 0; jt < args.jtiles; ++jt) {
+                    mbar_wait(smem_u32(&accEmpty[acc]), phacc ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * UMMA_N);
+                    for (int ks = 0; ks < args.nks; ++ks) {
+                        mbar_wait(smem_u32(&fullB[sb]), phb);
+                        mbar_wait(smem_u32(&aFull[sa]), pha);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_b_desc(smem_u32(sB + (size_t)sb * STAGE_BYTES));
+                        const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + sa * 32);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            tc_mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc + (uint64_t)(kk * 2), IDESC,
+                                         (ks | kk) != 0 ? 1u : 0u);
+                        tc_commit(smem_u32(&emptyB[sb]));
+                        tc_commit(smem_u32(&aEmpty[sa]));
+                        if (++sb == nb) { sb = 0; phb ^= 1; }
+                        if (++sa == NA) { sa = 0; pha ^= 1; }
+                    }
+                    tc_commit(smem_u32(&accFull[acc]));
+                    if (++acc == 2) { acc = 0; phacc ^= 1; }
+                }
+        }
+    } else if (warp < 6) {
+        // ===================== expanders (warps 2..5) =====================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int v = q * 32 + lane;                  // variant (= TMEM lane) within the tile
+        const int et = (warp - 2) * 32 + lane;        // 0..127 cooperative-copy index
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int chunks_per_row = args.nks;          // 16-byte chunks (4 words = 128 samples)
+        int sa = 0;
+        uint32_t pha = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // all expanders are done reading the previous tile's bits
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            {
+                int t = tile * TC_TILE_V + et;
+                sRows[et] = t < args.n_tested ? args.idx[t] : -1;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int total = TC_TILE_V * chunks_per_row;
+            for (int e = et; e < total; e += 128) {
+                int r = e / chunks_per_row, ch = e - r * chunks_per_row;
+                int row = sRows[r];
+                uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                if (row >= 0 && ch * 4 < args.Wrow)
+                    val = __ldg(reinterpret_cast<const uint4 *>(args.bits + (size_t)row * args.Wrow) + ch);
+                *reinterpret_cast<uint4 *>(sBits + (size_t)r * args.pitch + ch * 4) = val;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const uint32_t *myrow = sBits + (size_t)v * args.pitch;
+            for (int jt = 0; jt < args.jtiles; ++jt)
+                for (int ks = 0; ks < args.nks; ++ks) {
+                    const uint4 w4 = *reinterpret_cast<const uint4 *>(myrow + ks * 4);
+                    mbar_wait(smem_u32(&aEmpty[sa]), pha ^ 1);
+                    tc_fence_after();
+                    const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                    const uint32_t base = lane_addr + (uint32_t)(A_COL0 + sa * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t r[8];
+#pragma unroll
+                        for (int b = 0; b < 8; ++b)
+                            r[b] = (((ws[i] >> (4 * b)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                        tc_st8(base + i * 8, r);
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&aFull[sa]));
+                    if (++sa == NA) { sa = 0; pha ^= 1; }
+                }
+        }
+    } else {
+        // ===================== epilogue (warps 6..9) =====================
+        const int q = warp & 3;
+        const int v = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        int acc = 0;
+        uint32_t phacc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            double a = 0.0;
+            for (int jt = 0; jt < args.jtiles; ++jt) {
+                mbar_wait(smem_u32(&accFull[acc]), phacc);
+                tc_fence_after();
+                const uint32_t col0 = (uint32_t)(acc * UMMA_N);
+#pragma unroll
+                for (int c0 = 0; c0 < TC_JT; c0 += 16) {
+                    int32_t d[NSL][16];
+#pragma unroll
+                    for (int s = 0; s < NSL; ++s) tc_ld16(lane_addr + col0 + s * TC_JT + c0, d[s]);
+                    tc_wait_ld();
+                    const double *sc = args.scale2 + jt * TC_JT + c0;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        double g = (double)d[NSL - 1][c];
+#pragma unroll
+                        for (int s = NSL - 2; s >= 0; --s) g = fma(g, 256.0, (double)d[s][c]);
+                        a = fma(g * g, __ldg(sc + c), a);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&accEmpty[acc]));
+                if (++acc == 2) { acc = 0; phacc ^= 1; }
+            }
+            int t = tile * TC_TILE_V + v;
+            if (t < args.n_tested) args.a_out[args.idx[t]] = a;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Quantisation of L into k balanced base-256 digits, K-major:
+//   Lq[(jt * k + s) * 32 + c][i] = digit s of rint(L[i][jt*32+c] * 2^(8k-2-e_j)),
+// e_j = exponent with max_i |L[i][j]| < 2^e_j;  scale2[j] = 2^(2 (e_j - 8k + 2)).
+// ---------------------------------------------------------------------------------------
+__global__ void k_tc_colexp(const double *__restrict__ L, int N, int Jpad, int J, int nsl,
+                            int *__restrict__ expo, double *__restrict__ scale2, int Jq) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= Jq) return;
+    double mx = 0.0;
+    if (j < J)
+        for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(L[(size_t)i * Jpad + j]));
+    int e = 0;
+    if (mx > 0.0) {
+        frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
+    }
+    expo[j] = e;
+    scale2[j] = (mx > 0.0) ? ldexp(1.0, 2 * (e - (8 * nsl - 2))) : 0.0;
+}
+
+__global__ void k_tc_quantise(const double *__restrict__ L, int N, int Jpad, int J, int nsl,
+                              const int *__restrict__ expo, int8_t *__restrict__ Lq, int Kpad,
+                              int Jq) {
+    // thread per (i, j): i fastest so that the int8 stores of a warp are contiguous
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)Jq * Kpad;
+    if (e >= total) return;
+    int j = (int)(e / Kpad);
+    int i = (int)(e - (size_t)j * Kpad);
+    long long qv = 0;
+    if (i < N && j < J) {
+        double x = L[(size_t)i * Jpad + j];
+        qv = llrint(ldexp(x, (8 * nsl - 2) - expo[j]));
+    }
+    int jt = j / TC_JT, c = j - jt * TC_JT;
+    for (int s = 0; s < nsl; ++s) {
+        long long d = ((qv + 128) & 255) - 128;       // balanced digit in [-128, 127]
+        qv = (qv - d) >> 8;
+        Lq[((size_t)(jt * nsl + s) * TC_JT + c) * Kpad + i] = (int8_t)d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                    const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                    const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static size_t tc_smem_bytes(int nsl, int nb, int pitch) {
+    size_t stage = (size_t)TC_JT * nsl * TC_KSTAGE;
+    return 1024 + (size_t)nb * stage + (size_t)TC_TILE_V * pitch * 4 +
+           (2 * TC_MAX_BSTAGES + 32 + 4) * 8 + 16 + TC_TILE_V * 4 + 64;
+}
+
+template <int NSL>
+static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
+    PSB_CUDA(cudaFuncSetAttribute(k_lmm_quadform_tc<NSL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    k_lmm_quadform_tc<NSL><<<grid, TC_THREADS, smem, c->stream>>>(*(const CUtensorMap *)c->tmap_Lq, args);
+    return PSB_OK;
+}
+
+int psb_lmm_tc_setup(psb_ctx *c) {
+    const int nsl = c->precision;
+    PSB_REQUIRE(nsl >= 3 && nsl <= 7, PSB_ERR_ARG, "int8 slice count must be in 3..7, got %d", nsl);
+    const int N = c->N, J = c->J;
+    c->n_slices = nsl;
+    c->jtiles = (J + TC_JT - 1) / TC_JT;
+    const int Jq = c->jtiles * TC_JT;
+    c->Kpad = ((N + TC_KSTAGE - 1) / TC_KSTAGE) * TC_KSTAGE;
+    int *d_expo = nullptr;
+    PSB_CUDA(cudaMalloc(&d_expo, Jq * sizeof(int)));
+    PSB_CUDA(cudaMalloc(&c->d_scale2, Jq * sizeof(double)));
+    size_t lq_bytes = (size_t)Jq * nsl * c->Kpad;
+    PSB_CUDA(cudaMalloc(&c->d_Lq, lq_bytes));
+    k_tc_colexp<<<psb_div_up(Jq, 128), 128, 0, c->stream>>>(c->d_L, N, c->Jpad, J, nsl, d_expo,
+                                                           c->d_scale2, Jq);
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    size_t total = (size_t)Jq * c->Kpad;
+    k_tc_quantise<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_L, N, c->Jpad, J, nsl,
+                                                                         d_expo, c->d_Lq, c->Kpad, Jq);
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_expo);
+
+    // tensor map over Lq: inner dim = samples (bytes), outer = (jtile, slice, comp) rows
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PSB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, PSB_ERR_CUDA,
+                "cuTensorMapEncodeTiled not available from the driver");
+    CUtensorMap *tm = new CUtensorMap;
+    cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jq * nsl};
+    cuuint64_t gstr[1] = {(cuuint64_t)c->Kpad};
+    cuuint32_t box[2] = {TC_KSTAGE, (cuuint32_t)(TC_JT * nsl)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        delete tm;
+        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return PSB_ERR_CUDA;
+    }
+    c->tmap_Lq = tm;
+    return PSB_OK;
+}
+
+int psb_lmm_tc_run(psb_ctx *c, int n_tested) {
+    const int nsl = c->n_slices;
+    TcArgs a;
+    a.bits = c->d_bits;
+    a.idx = c->d_idx;
+    a.scale2 = c->d_scale2;
+    a.a_out = c->d_a;
+    a.Wrow = c->Wrow;
+    a.n_tested = n_tested;
+    a.nks = c->Kpad / TC_KSTAGE;
+    a.jtiles = c->jtiles;
+    int pitch = a.nks * 4;
+    while (pitch % 32 != 4) pitch += 4;
+    a.pitch = pitch;
+    int smem_max = 0;
+    PSB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    int nb = TC_MAX_BSTAGES;
+    while (nb > 2 && tc_smem_bytes(nsl, nb, pitch) > (size_t)smem_max) --nb;
+    PSB_REQUIRE(tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max, PSB_ERR_UNSUPPORTED,
+                "n_samples = %d needs more shared memory than the tensor path has; use precision 0",
+                c->N);
+    a.n_bstages = nb;
+    const size_t smem = tc_smem_bytes(nsl, nb, pitch);
+    const int tiles = psb_div_up(n_tested, TC_TILE_V);
+    const int grid = std::min(tiles, c->sm_count);
+    int rc = PSB_OK;
+    switch (nsl) {
+        case 3: rc = tc_launch<3>(c, a, grid, smem); break;
+        case 4: rc = tc_launch<4>(c, a, grid, smem); break;
+        case 5: rc = tc_launch<5>(c, a, grid, smem); break;
+        case 6: rc = tc_launch<6>(c, a, grid, smem); break;
+        case 7: rc = tc_launch<7>(c, a, grid, smem); break;
+        default:
+            psb_set_error("unsupported slice count %d", nsl);
+            return PSB_ERR_ARG;
+    }
+    if (rc) return rc;
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    return PSB_OK;
+}
+
+void psb_lmm_tc_free(psb_ctx *c) {
+    if (c->d_Lq) cudaFree(c->d_Lq);
+    if (c->d_scale2) cudaFree(c->d_scale2);
+    c->d_Lq = nullptr;
+    c->d_scale2 = nullptr;
+    if (c->tmap_Lq) delete (CUtensorMap *)c->tmap_Lq;
+    c->tmap_Lq = nullptr;
+}
