@@ -59,6 +59,11 @@ struct psb_ctx {
     int C = 0, Npad = 0;
     int col_b = -1, col_q0 = -1, col_w0 = -1;   // LMM: b column, first Q column; Welch cols
     double y_mean = 0.0;
+    // fast stats pass (psb_varstats.cu k_bitstats): Welch columns transposed [32][Wn] x
+    // (yc, yc^2), their totals, and the phenotype class counts
+    double *d_wcolsT = nullptr;
+    double welch_T1 = 0.0, welch_T2 = 0.0;
+    int n_y1 = 0, n_y0 = 0;
 
     // ---- LMM ----
     int D = 0, J = 0, Jpad = 0, Kpad = 0;
@@ -70,6 +75,7 @@ struct psb_ctx {
     int8_t *d_Lq = nullptr;       // [jtiles][slices][32 comps][Kpad] int8 (K-major)
     double *d_scale2 = nullptr;   // [Jpad32] (s_j 2^-B)^2
     int n_slices = 0, jtiles = 0;
+    int tc_special = 0;           // hi/lo column pairs carried by the special tile (0 = none)
     void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B)
 
     // ---- fixed effects ----
@@ -103,6 +109,8 @@ struct psb_ctx {
     int32_t *d_idx2 = nullptr;    // second list (Firth candidates)
     int *d_counters = nullptr;    // [8] device counters
     double *d_a = nullptr;        // [cap] quadratic forms
+    double *d_b = nullptr;        // [cap] x'v from the tensor path
+    double *d_pp = nullptr;       // [cap] ||Q'x||^2 from the tensor path
     int64_t counts[4] = {0, 0, 0, 0};
     bool ran = false;
 };
@@ -113,9 +121,12 @@ int psb_free_model(psb_ctx *ctx);
 // psb_varstats.cu
 int psb_launch_bitsums(psb_ctx *ctx);
 int psb_launch_prefilter(psb_ctx *ctx, const psb_params *prm, int lmm_rule);
+int psb_upload_welch_T(psb_ctx *ctx, const double *yc, const double *yc2);
+bool psb_bitstats_fits(psb_ctx *ctx);
+int psb_launch_bitstats(psb_ctx *ctx, int continuous);
 
 // psb_lmm_tc.cu
-int psb_lmm_tc_setup(psb_ctx *ctx);
+int psb_lmm_tc_setup(psb_ctx *ctx, const double *h_v, const double *h_Q, int r, int ldq);
 int psb_lmm_tc_run(psb_ctx *ctx, int n_tested);
 void psb_lmm_tc_free(psb_ctx *ctx);
 

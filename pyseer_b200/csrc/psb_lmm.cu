@@ -152,6 +152,7 @@ k_lmm_quadform_fp64(const uint32_t *__restrict__ bits, int Wrow, const int32_t *
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_lmm_epilogue(int n_tested, const int32_t *__restrict__ idx, const double *__restrict__ a_in,
+               const double *__restrict__ b_in, const double *__restrict__ pp_in,
                const double *__restrict__ sums, int C, int col_b, int col_q0, int nq, int N,
                const int32_t *__restrict__ carriers, const int32_t *__restrict__ nmissing,
                double YKY, double dof1, double lrt_pvalue, double *__restrict__ pvalue,
@@ -170,11 +171,18 @@ k_lmm_epilogue(int n_tested, const int32_t *__restrict__ idx, const double *__re
     } else {
         const double *s = sums + (size_t)v * C;
         double a = a_in[v];
-        double b = s[col_b];
+        // b = x'v and ||Q'x||^2: from the tensor pass when it carries them, else from the
+        // masked column sums
+        double b, pp = 0.0;
+        if (b_in) {
+            b = b_in[v];
+            pp = pp_in[v];
+        } else {
+            b = s[col_b];
+            for (int d = 0; d < nq; ++d) pp = fma(s[col_q0 + d], s[col_q0 + d], pp);
+        }
         // rotate(): columns with std(P x) <= 1e-10 are zeroed (lmm_cov.py:179-181)
         double c = (double)carriers[v];
-        double pp = 0.0;
-        for (int d = 0; d < nq; ++d) pp = fma(s[col_q0 + d], s[col_q0 + d], pp);
         double ss = c - pp;   // || P x ||^2
         if (ss <= fmax(1e-20 * (double)N, 1e-12 * c)) {
             a = 0.0;
@@ -220,6 +228,11 @@ static void pack_pheno_bits(const double *y, int N, int Wn, std::vector<uint32_t
 int psb_upload_pheno(psb_ctx *c, const double *y) {
     std::vector<uint32_t> y1, y0, valid;
     pack_pheno_bits(y, c->N, c->Wn, y1, y0, valid);
+    c->n_y1 = c->n_y0 = 0;
+    for (int i = 0; i < c->N; ++i) {
+        c->n_y1 += (y[i] == 1.0);
+        c->n_y0 += (y[i] == 0.0);
+    }
     PSB_CUDA(cudaMalloc(&c->d_y1bits, c->Wn * sizeof(uint32_t)));
     PSB_CUDA(cudaMalloc(&c->d_y0bits, c->Wn * sizeof(uint32_t)));
     PSB_CUDA(cudaMalloc(&c->d_valid, c->Wn * sizeof(uint32_t)));
@@ -350,6 +363,7 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
     for (int j = 0; j < J; ++j) YKY += UY[j] / Sd[j] * UY[j];       // computeAKA
     c->YKY = YKY;
 
+    int rc0 = PSB_OK;
     // column matrix for k_bitsums: v | Q_0..Q_{r-1} | Welch(4)
     c->Npad = c->Wn * 32;
     c->C = 1 + r + 4;
@@ -371,6 +385,8 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
     for (int e = 0; e < r; ++e)
         std::copy(&Q[(size_t)e * N], &Q[(size_t)e * N] + N, &cols[(size_t)(1 + e) * c->Npad]);
     psb_fill_welch_cols(y, N, c->Npad, cols.data(), c->col_w0, &c->colmask_lo, &c->colmask_hi);
+    rc0 = psb_upload_welch_T(c, &cols[(size_t)c->col_w0 * c->Npad], &cols[(size_t)(c->col_w0 + 1) * c->Npad]);
+    if (rc0) return rc0;
     PSB_CUDA(cudaMalloc(&c->d_cols, cols.size() * sizeof(double)));
     PSB_CUDA(cudaMemcpy(c->d_cols, cols.data(), cols.size() * sizeof(double), cudaMemcpyHostToDevice));
     int rc = psb_upload_pheno(c, y);
@@ -394,7 +410,7 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
                           cudaMemcpyHostToDevice));
     c->model = PSB_MODEL_LMM;
     if (precision > 0) {
-        rc = psb_lmm_tc_setup(c);
+        rc = psb_lmm_tc_setup(c, cols.data(), cols.data() + c->Npad, r, c->Npad);
         if (rc) {
             psb_free_model(c);
             return rc;
@@ -411,7 +427,13 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
     int rc = psb_ensure_capacity(c, c->S, 0);
     if (rc) return rc;
     PSB_CUDA(cudaEventRecord(c->ev_run0, c->stream));
-    rc = psb_launch_bitsums(c);
+    // With the tensor path carrying x'v and Q'x, the stats pass only needs popcounts and
+    // (continuous phenotype) the two Welch sums; otherwise all masked column sums.
+    const bool tc_sums = c->precision > 0 && c->tc_special > 0;
+    if (tc_sums && !c->d_miss && psb_bitstats_fits(c))
+        rc = psb_launch_bitstats(c, prm->continuous);
+    else
+        rc = psb_launch_bitsums(c);
     if (rc) return rc;
     rc = psb_launch_prefilter(c, prm, /*lmm_rule=*/1);
     if (rc) return rc;
@@ -437,7 +459,8 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
     c->have_k_ev = true;
     if (n_tested > 0) {
         k_lmm_epilogue<<<psb_div_up(n_tested, 256), 256, 0, c->stream>>>(
-            n_tested, c->d_idx, c->d_a, c->d_sums, c->C, c->col_b, c->col_q0, c->col_w0 - c->col_q0,
+            n_tested, c->d_idx, c->d_a, tc_sums ? c->d_b : nullptr, tc_sums ? c->d_pp : nullptr,
+            c->d_sums, c->C, c->col_b, c->col_q0, c->col_w0 - c->col_q0,
             c->N, c->d_carriers, c->d_missing, c->YKY, (double)(c->J - 1), prm->lrt_pvalue,
             c->d_pvalue, c->d_beta, c->d_bse, c->d_extra, c->d_flags, c->d_counters);
         c->launches++;

@@ -13,26 +13,37 @@
 // rounding of L to 8k-2 bits relative to its column maximum (k = 5: 2^-38).  This is an
 // integer GEMM by construction; it is not a reduced-precision approximation of an fp GEMM.
 //
-// Kernel structure (one persistent CTA per SM, 128 variants per tile, 10 warps):
+// Kernel structure (one persistent CTA per SM, 128 variants per tile, 14 warps):
 //   warp 0      TMA producer: streams the k-sliced int8 operand (B, K-major, 128B swizzle)
 //               through an smem ring with cp.async.bulk.tensor + mbarrier complete_tx.
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::i8, M=128, N=32k, K=32;
 //               A (the variants) comes from TENSOR MEMORY, B from shared memory,
 //               accumulators (int32) live in TMEM, double buffered.
-//   warps 2-5   expanders: each thread owns one variant (= one TMEM lane); it turns its
-//               packed presence/absence bits (staged once per tile in smem, 1 bit/sample)
-//               into 0/1 bytes in registers and writes them straight into TMEM with
-//               tcgen05.st -- the expanded operand never touches shared memory or HBM.
-//   warps 6-9   epilogue: tcgen05.ld the int32 accumulators, recombine the slices in fp64,
+//   warps 2-9   expanders (two groups of four warps taking alternate K stages): each thread
+//               owns one variant (= one TMEM lane); it turns its packed presence/absence
+//               bits (staged once per tile in smem, 1 bit/sample) into 0/1 bytes in
+//               registers -- (w >> s) & 0x01010101, two ALU ops per 4 samples, with the
+//               matching sample permutation baked into the B operand -- and writes them
+//               straight into TMEM with tcgen05.st: the expanded operand never touches
+//               shared memory or HBM.
+//   warps 10-13 epilogue: tcgen05.ld the int32 accumulators, recombine the slices in fp64,
 //               square, scale and accumulate a[v] in a register across all component tiles.
+// One extra component tile carries v = M y (score numerator b = x'v, computeAKB
+// lmm_cov.py:902-916) and the covariate basis Q (for rotate()'s constant-column rule), each
+// as a hi + lo pair of sliced columns, i.e. to 2 x (8k-2) bits: b and ||Q'x||^2 come out of
+// the same pass at fp64 accuracy.
 // HBM sees N/8 bytes per variant; L2 serves the sliced operand to all CTAs.
 #include <cuda.h>
 
+#include <math.h>
+
 #include <algorithm>
+#include <vector>
 
 #include "psb_internal.cuh"
 
-#define TC_THREADS 320
+#define TC_THREADS 448
+#define TC_EXP_WARPS 8         // expander warps (2 groups x 4 lane quarters)
 #define TC_TILE_V 128          // variants per CTA tile (UMMA M)
 #define TC_JT 32               // components per accumulator tile
 #define TC_KSTAGE 128          // samples per pipeline stage (one 128-byte swizzle row)
@@ -74,6 +85,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
     }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -131,6 +153,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int32_t (&r)[16]) {
         : "memory");
 }
 
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, int32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+}
+
 // K-major, 128-byte swizzle shared-memory operand descriptor (rows of 128 bytes, 8-row
 // groups 1024 bytes apart).
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
@@ -146,8 +176,11 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
 struct TcArgs {
     const uint32_t *bits;     // packed rows
     const int32_t *idx;       // tested variant ids
-    const double *scale2;     // per component (s_j)^2
-    double *a_out;            // [variant id]
+    const double *scale2;     // per component (s_j)^2; plain s_j for the special tile
+    double *a_out;            // [variant id]  || L'x ||^2
+    double *b_out;            // [variant id]  x'v            (special tile; may be null)
+    double *pp_out;           // [variant id]  || Q'x ||^2    (special tile; may be null)
+    int n_special;            // hi/lo column pairs in the special tile (0 = no special tile)
     int Wrow;                 // words per packed row in global memory
     int n_tested;
     int nks;                  // K stages (Kpad / 128)
@@ -171,15 +204,16 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int nb = args.n_bstages;
-    uint8_t *sB = smem;                                               // nb stages
-    uint32_t *sBits = (uint32_t *)(sB + (size_t)nb * STAGE_BYTES);    // 128 x pitch words
+    const int ns = args.n_bstages;                 // pipeline depth (<= NA)
+    uint8_t *sB = smem;                                               // ns stages
+    uint32_t *sBits = (uint32_t *)(sB + (size_t)ns * STAGE_BYTES);    // 128 x pitch words
     uint64_t *bars = (uint64_t *)(sBits + (size_t)TC_TILE_V * args.pitch);
-    uint64_t *fullB = bars;                       // [nb]
-    uint64_t *emptyB = fullB + TC_MAX_BSTAGES;    // [nb]
-    uint64_t *aFull = emptyB + TC_MAX_BSTAGES;    // [NA] (<= 16)
-    uint64_t *aEmpty = aFull + 16;
-    uint64_t *accFull = aEmpty + 16;              // [2]
+    // One ring for both operands of a K stage: full[s] completes when the TMA bytes of the
+    // B stage have landed AND the four expander warps have stored the A stage in TMEM;
+    // empty[s] is signalled by tcgen05.commit once the stage's MMAs have retired.
+    uint64_t *full = bars;                        // [ns]
+    uint64_t *empty = full + 16;                  // [ns]
+    uint64_t *accFull = empty + 16;               // [2]
     uint64_t *accEmpty = accFull + 2;             // [2]
     uint32_t *tmem_slot = (uint32_t *)(accEmpty + 2);
     int32_t *sRows = (int32_t *)(tmem_slot + 2);  // [128]
@@ -189,13 +223,9 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
     const int n_tiles = (args.n_tested + TC_TILE_V - 1) / TC_TILE_V;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < nb; ++i) {
-            mbar_init(smem_u32(&fullB[i]), 1);
-            mbar_init(smem_u32(&emptyB[i]), 1);
-        }
-        for (int i = 0; i < NA; ++i) {
-            mbar_init(smem_u32(&aFull[i]), 4);
-            mbar_init(smem_u32(&aEmpty[i]), 1);
+        for (int i = 0; i < ns; ++i) {
+            mbar_init(smem_u32(&full[i]), 1 + 4);
+            mbar_init(smem_u32(&empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&accFull[i]), 1);
@@ -213,71 +243,71 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+    const uint32_t sB0 = smem_u32(sB);
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int jt = 0; jt < args.jtiles; ++jt)
-                    for (int ks = 0; ks < args.nks; ++ks) {
-                        mbar_wait(smem_u32(&emptyB[st]), ph ^ 1);
-                        uint32_t bar = smem_u32(&fullB[st]);
+        // ===================== TMA producer (whole warp loops, one lane issues) ==========
+        int st = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int jt = 0; jt < args.jtiles; ++jt)
+                for (int ks = 0; ks < args.nks; ++ks) {
+                    mbar_wait(empty0 + st * 8, ph ^ 1);
+                    if (elect_one()) {
+                        const uint32_t bar = full0 + st * 8;
                         mbar_arrive_expect_tx(bar, STAGE_BYTES);
-                        tma_load_2d(smem_u32(sB + (size_t)st * STAGE_BYTES), &tmap, bar,
-                                    ks * TC_KSTAGE, jt * UMMA_N);
-                        if (++st == nb) { st = 0; ph ^= 1; }
+                        tma_load_2d(sB0 + st * STAGE_BYTES, &tmap, bar, ks * TC_KSTAGE, jt * UMMA_N);
                     }
-        }
+                    __syncwarp();
+                    if (++st == ns) { st = 0; ph ^= 1; }
+                }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int sb = 0, sa = 0, acc = 0;
-            uint32_t phb = 0, pha = 0, phacc = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int jt = 0; jt < args.jtiles; ++jt) {
-                    mbar_wait(smem_u32(&accEmpty[acc]), phacc ^ 1);
+        // ===================== MMA issuer (whole warp loops, one lane issues) ============
+        int st = 0, acc = 0;
+        uint32_t ph = 0, phacc = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int jt = 0; jt < args.jtiles; ++jt) {
+                mbar_wait(smem_u32(&accEmpty[acc]), phacc ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * UMMA_N);
+                for (int ks = 0; ks < args.nks; ++ks) {
+                    mbar_wait(full0 + st * 8, ph);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(acc * UMMA_N);
-                    for (int ks = 0; ks < args.nks; ++ks) {
-                        mbar_wait(smem_u32(&fullB[sb]), phb);
-                        mbar_wait(smem_u32(&aFull[sa]), pha);
-                        tc_fence_after();
-                        const uint64_t bdesc = make_b_desc(smem_u32(sB + (size_t)sb * STAGE_BYTES));
-                        const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + sa * 32);
+                    if (elect_one()) {
+                        const uint64_t bdesc = make_b_desc(sB0 + st * STAGE_BYTES);
+                        const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + st * 32);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             tc_mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc + (uint64_t)(kk * 2), IDESC,
                                          (ks | kk) != 0 ? 1u : 0u);
-                        tc_commit(smem_u32(&emptyB[sb]));
-                        tc_commit(smem_u32(&aEmpty[sa]));
-                        if (++sb == nb) { sb = 0; phb ^= 1; }
-                        if (++sa == NA) { sa = 0; pha ^= 1; }
+                        tc_commit(empty0 + st * 8);
+                        if (ks == args.nks - 1) tc_commit(smem_u32(&accFull[acc]));
                     }
-                    tc_commit(smem_u32(&accFull[acc]));
-                    if (++acc == 2) { acc = 0; phacc ^= 1; }
+                    __syncwarp();
+                    if (++st == ns) { st = 0; ph ^= 1; }
                 }
-        }
-    } else if (warp < 6) {
-        // ===================== expanders (warps 2..5) =====================
+                if (++acc == 2) { acc = 0; phacc ^= 1; }
+            }
+    } else if (warp < 2 + TC_EXP_WARPS) {
+        // ===================== expanders (warps 2..9) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;              // group 0 / 1: even / odd K stages
         const int v = q * 32 + lane;                  // variant (= TMEM lane) within the tile
-        const int et = (warp - 2) * 32 + lane;        // 0..127 cooperative-copy index
+        const int et = (warp - 2) * 32 + lane;        // 0..255 cooperative-copy index
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const int chunks_per_row = args.nks;          // 16-byte chunks (4 words = 128 samples)
-        int sa = 0;
-        uint32_t pha = 0;
+        uint32_t stage_ctr = 0;                       // global K-stage counter (all tiles)
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // all expanders are done reading the previous tile's bits
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et < TC_TILE_V) {
                 int t = tile * TC_TILE_V + et;
                 sRows[et] = t < args.n_tested ? args.idx[t] : -1;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const int total = TC_TILE_V * chunks_per_row;
-            for (int e = et; e < total; e += 128) {
+            for (int e = et; e < total; e += 32 * TC_EXP_WARPS) {
                 int r = e / chunks_per_row, ch = e - r * chunks_per_row;
                 int row = sRows[r];
                 uint4 val = make_uint4(0u, 0u, 0u, 0u);
@@ -285,56 +315,84 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     val = __ldg(reinterpret_cast<const uint4 *>(args.bits + (size_t)row * args.Wrow) + ch);
                 *reinterpret_cast<uint4 *>(sBits + (size_t)r * args.pitch + ch * 4) = val;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const uint32_t *myrow = sBits + (size_t)v * args.pitch;
             for (int jt = 0; jt < args.jtiles; ++jt)
-                for (int ks = 0; ks < args.nks; ++ks) {
+                for (int ks = 0; ks < args.nks; ++ks, ++stage_ctr) {
+                    if ((int)(stage_ctr & 1u) != grp) continue;
+                    const int sa = (int)(stage_ctr % (uint32_t)ns);
+                    const uint32_t pha = (stage_ctr / (uint32_t)ns) & 1u;
                     const uint4 w4 = *reinterpret_cast<const uint4 *>(myrow + ks * 4);
-                    mbar_wait(smem_u32(&aEmpty[sa]), pha ^ 1);
+                    mbar_wait(empty0 + sa * 8, pha ^ 1);
                     tc_fence_after();
                     const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
                     const uint32_t base = lane_addr + (uint32_t)(A_COL0 + sa * 32);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
+                        // register b, byte t <- sample 8 t + b of the word (the B operand is
+                        // stored with the same permutation, see k_tc_quantise)
                         uint32_t r[8];
 #pragma unroll
-                        for (int b = 0; b < 8; ++b)
-                            r[b] = (((ws[i] >> (4 * b)) & 0xFu) * 0x00204081u) & 0x01010101u;
+                        for (int b = 0; b < 8; ++b) r[b] = (ws[i] >> b) & 0x01010101u;
                         tc_st8(base + i * 8, r);
                     }
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&aFull[sa]));
-                    if (++sa == NA) { sa = 0; pha ^= 1; }
+                    if (lane == 0) mbar_arrive(full0 + sa * 8);
                 }
         }
     } else {
-        // ===================== epilogue (warps 6..9) =====================
+        // ===================== epilogue (warps 10..13) =====================
+        constexpr int CH = NSL <= 5 ? 16 : 8;         // accumulator columns per TMEM load
         const int q = warp & 3;
         const int v = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int jt_special = args.n_special > 0 ? args.jtiles - 1 : -1;
         int acc = 0;
         uint32_t phacc = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            double a = 0.0;
+            double a = 0.0, bsum = 0.0, pp = 0.0;
             for (int jt = 0; jt < args.jtiles; ++jt) {
                 mbar_wait(smem_u32(&accFull[acc]), phacc);
                 tc_fence_after();
                 const uint32_t col0 = (uint32_t)(acc * UMMA_N);
+                double prev = 0.0;                    // hi part of the current hi/lo pair
 #pragma unroll
-                for (int c0 = 0; c0 < TC_JT; c0 += 16) {
-                    int32_t d[NSL][16];
+                for (int c0 = 0; c0 < TC_JT; c0 += CH) {
+                    int32_t d[NSL][CH];
 #pragma unroll
-                    for (int s = 0; s < NSL; ++s) tc_ld16(lane_addr + col0 + s * TC_JT + c0, d[s]);
+                    for (int s = 0; s < NSL; ++s) {
+                        if constexpr (CH == 16) tc_ld16(lane_addr + col0 + s * TC_JT + c0, d[s]);
+                        else tc_ld8(lane_addr + col0 + s * TC_JT + c0, d[s]);
+                    }
                     tc_wait_ld();
                     const double *sc = args.scale2 + jt * TC_JT + c0;
+                    if (jt != jt_special) {
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        double g = (double)d[NSL - 1][c];
+                        for (int c = 0; c < CH; ++c) {
+                            double g = (double)d[NSL - 1][c];
 #pragma unroll
-                        for (int s = NSL - 2; s >= 0; --s) g = fma(g, 256.0, (double)d[s][c]);
-                        a = fma(g * g, __ldg(sc + c), a);
+                            for (int s = NSL - 2; s >= 0; --s) g = fma(g, 256.0, (double)d[s][c]);
+                            a = fma(g * g, __ldg(sc + c), a);
+                        }
+                    } else {
+                        // columns come in (hi, lo) pairs: pair 0 = v, pairs 1.. = Q_e
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            double g = (double)d[NSL - 1][c];
+#pragma unroll
+                            for (int s = NSL - 2; s >= 0; --s) g = fma(g, 256.0, (double)d[s][c]);
+                            g *= __ldg(sc + c);
+                            if ((c & 1) == 0) {
+                                prev = g;
+                            } else {
+                                double val = prev + g;
+                                int pair = (c0 + c) >> 1;
+                                if (pair == 0) bsum = val;
+                                else if (pair <= args.n_special - 1) pp = fma(val, val, pp);
+                            }
+                        }
                     }
                 }
                 tc_fence_before();
@@ -343,7 +401,14 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 if (++acc == 2) { acc = 0; phacc ^= 1; }
             }
             int t = tile * TC_TILE_V + v;
-            if (t < args.n_tested) args.a_out[args.idx[t]] = a;
+            if (t < args.n_tested) {
+                int row = args.idx[t];
+                args.a_out[row] = a;
+                if (jt_special >= 0) {
+                    args.b_out[row] = bsum;
+                    args.pp_out[row] = pp;
+                }
+            }
         }
     }
 
@@ -357,9 +422,17 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
 
 // ---------------------------------------------------------------------------------------
 // Quantisation of L into k balanced base-256 digits, K-major:
-//   Lq[(jt * k + s) * 32 + c][i] = digit s of rint(L[i][jt*32+c] * 2^(8k-2-e_j)),
+//   Lq[(jt * k + s) * 32 + c][kpos(i)] = digit s of rint(L[i][jt*32+c] * 2^(8k-2-e_j)),
 // e_j = exponent with max_i |L[i][j]| < 2^e_j;  scale2[j] = 2^(2 (e_j - 8k + 2)).
+// kpos permutes the samples inside every group of 32 so that the expanders can produce
+// register b of a word with (w >> b) & 0x01010101: byte t of that register is sample
+// 8 t + b, and it is operand position 4 b + t.
 // ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int tc_kpos(int i) {
+    int i32 = i & 31;
+    return (i & ~31) | (((i32 & 7) << 2) | (i32 >> 3));
+}
+
 __global__ void k_tc_colexp(const double *__restrict__ L, int N, int Jpad, int J, int nsl,
                             int *__restrict__ expo, double *__restrict__ scale2, int Jq) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -393,7 +466,7 @@ __global__ void k_tc_quantise(const double *__restrict__ L, int N, int Jpad, int
     for (int s = 0; s < nsl; ++s) {
         long long d = ((qv + 128) & 255) - 128;       // balanced digit in [-128, 127]
         qv = (qv - d) >> 8;
-        Lq[((size_t)(jt * nsl + s) * TC_JT + c) * Kpad + i] = (int8_t)d;
+        Lq[((size_t)(jt * nsl + s) * TC_JT + c) * Kpad + tc_kpos(i)] = (int8_t)d;
     }
 }
 
@@ -406,7 +479,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
 static size_t tc_smem_bytes(int nsl, int nb, int pitch) {
     size_t stage = (size_t)TC_JT * nsl * TC_KSTAGE;
     return 1024 + (size_t)nb * stage + (size_t)TC_TILE_V * pitch * 4 +
-           (2 * TC_MAX_BSTAGES + 32 + 4) * 8 + 16 + TC_TILE_V * 4 + 64;
+           (32 + 4) * 8 + 16 + TC_TILE_V * 4 + 64;
 }
 
 template <int NSL>
@@ -417,18 +490,48 @@ static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
     return PSB_OK;
 }
 
-int psb_lmm_tc_setup(psb_ctx *c) {
+// Special tile (host side, exact): each source column u (v = M y, then the orthonormal
+// covariate basis Q_e) becomes a pair of sliced columns hi = quantised u and lo = quantised
+// (u - hi), so that g_hi s_hi + g_lo s_lo reproduces x'u to 2 (8k-2) bits.
+static void tc_special_column(const double *u, int N, int nsl, int Kpad, int8_t *tile, int comp,
+                              double *scale) {
+    const int B = 8 * nsl - 2;
+    std::vector<double> rem(u, u + N);
+    for (int part = 0; part < 2; ++part) {
+        double mx = 0.0;
+        for (int i = 0; i < N; ++i) mx = std::max(mx, fabs(rem[i]));
+        int e = 0;
+        if (mx > 0.0) frexp(mx, &e);
+        scale[comp + part] = mx > 0.0 ? ldexp(1.0, e - B) : 0.0;
+        for (int i = 0; i < N; ++i) {
+            long long qv = mx > 0.0 ? llrint(ldexp(rem[i], B - e)) : 0;
+            rem[i] -= ldexp((double)qv, e - B);          // exact
+            for (int s = 0; s < nsl; ++s) {
+                long long d = ((qv + 128) & 255) - 128;
+                qv = (qv - d) >> 8;
+                tile[((size_t)s * TC_JT + comp + part) * Kpad + tc_kpos(i)] = (int8_t)d;
+            }
+        }
+    }
+}
+
+int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, int ldq) {
     const int nsl = c->precision;
     PSB_REQUIRE(nsl >= 3 && nsl <= 7, PSB_ERR_ARG, "int8 slice count must be in 3..7, got %d", nsl);
     const int N = c->N, J = c->J;
     c->n_slices = nsl;
-    c->jtiles = (J + TC_JT - 1) / TC_JT;
-    const int Jq = c->jtiles * TC_JT;
+    const int jt_reg = (J + TC_JT - 1) / TC_JT;
+    // the special tile holds 1 + r hi/lo pairs; with more than 15 covariate columns the
+    // masked column sums stay on the CUDA-core path (psb_varstats.cu)
+    c->tc_special = (1 + r) * 2 <= TC_JT ? 1 + r : 0;
+    c->jtiles = jt_reg + (c->tc_special ? 1 : 0);
+    const int Jq = jt_reg * TC_JT;
+    const int Jall = c->jtiles * TC_JT;
     c->Kpad = ((N + TC_KSTAGE - 1) / TC_KSTAGE) * TC_KSTAGE;
     int *d_expo = nullptr;
     PSB_CUDA(cudaMalloc(&d_expo, Jq * sizeof(int)));
-    PSB_CUDA(cudaMalloc(&c->d_scale2, Jq * sizeof(double)));
-    size_t lq_bytes = (size_t)Jq * nsl * c->Kpad;
+    PSB_CUDA(cudaMalloc(&c->d_scale2, Jall * sizeof(double)));
+    size_t lq_bytes = (size_t)Jall * nsl * c->Kpad;
     PSB_CUDA(cudaMalloc(&c->d_Lq, lq_bytes));
     k_tc_colexp<<<psb_div_up(Jq, 128), 128, 0, c->stream>>>(c->d_L, N, c->Jpad, J, nsl, d_expo,
                                                            c->d_scale2, Jq);
@@ -439,6 +542,19 @@ int psb_lmm_tc_setup(psb_ctx *c) {
                                                                          d_expo, c->d_Lq, c->Kpad, Jq);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
+    if (c->tc_special) {
+        size_t tile_bytes = (size_t)nsl * TC_JT * c->Kpad;
+        std::vector<int8_t> tile(tile_bytes, 0);
+        std::vector<double> sc(TC_JT, 0.0);
+        tc_special_column(h_v, N, nsl, c->Kpad, tile.data(), 0, sc.data());
+        for (int e = 0; e < r; ++e)
+            tc_special_column(h_Q + (size_t)e * ldq, N, nsl, c->Kpad, tile.data(), 2 + 2 * e, sc.data());
+        PSB_CUDA(cudaMemcpyAsync(c->d_Lq + (size_t)jt_reg * tile_bytes, tile.data(), tile_bytes,
+                                 cudaMemcpyHostToDevice, c->stream));
+        PSB_CUDA(cudaMemcpyAsync(c->d_scale2 + Jq, sc.data(), TC_JT * sizeof(double),
+                                 cudaMemcpyHostToDevice, c->stream));
+        PSB_CUDA(cudaStreamSynchronize(c->stream));
+    }
     PSB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_expo);
 
@@ -449,17 +565,17 @@ int psb_lmm_tc_setup(psb_ctx *c) {
     PSB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, PSB_ERR_CUDA,
                 "cuTensorMapEncodeTiled not available from the driver");
     CUtensorMap *tm = new CUtensorMap;
-    cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jq * nsl};
+    cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jall * nsl};
     cuuint64_t gstr[1] = {(cuuint64_t)c->Kpad};
     cuuint32_t box[2] = {TC_KSTAGE, (cuuint32_t)(TC_JT * nsl)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
+    CUresult cr = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
+    if (cr != CUDA_SUCCESS) {
         delete tm;
-        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
         return PSB_ERR_CUDA;
     }
     c->tmap_Lq = tm;
@@ -473,6 +589,9 @@ int psb_lmm_tc_run(psb_ctx *c, int n_tested) {
     a.idx = c->d_idx;
     a.scale2 = c->d_scale2;
     a.a_out = c->d_a;
+    a.b_out = c->d_b;
+    a.pp_out = c->d_pp;
+    a.n_special = c->tc_special;
     a.Wrow = c->Wrow;
     a.n_tested = n_tested;
     a.nks = c->Kpad / TC_KSTAGE;
@@ -482,8 +601,8 @@ int psb_lmm_tc_run(psb_ctx *c, int n_tested) {
     a.pitch = pitch;
     int smem_max = 0;
     PSB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    int nb = TC_MAX_BSTAGES;
-    while (nb > 2 && tc_smem_bytes(nsl, nb, pitch) > (size_t)smem_max) --nb;
+    int nb = (512 - 2 * TC_JT * nsl) / 32;      // TMEM A-ring depth bounds the pipeline
+    while (nb > 1 && tc_smem_bytes(nsl, nb, pitch) > (size_t)smem_max) --nb;
     PSB_REQUIRE(tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max, PSB_ERR_UNSUPPORTED,
                 "n_samples = %d needs more shared memory than the tensor path has; use precision 0",
                 c->N);

@@ -8,6 +8,9 @@
 // each 32-word chunk); for the fp64 column sums the chunk's words are broadcast by
 // shuffle and lane l takes bit l of word t, so the column read col[32 t + l] is a
 // coalesced 256-byte line that stays in L1/L2 (the columns are shared by all variants).
+#include <algorithm>
+#include <vector>
+
 #include "psb_internal.cuh"
 
 #define BITSUMS_MAXC 40
@@ -211,6 +214,152 @@ int psb_launch_prefilter(psb_ctx *c, const psb_params *prm, int lmm_rule) {
                                                c->d_sums, c->C, c->col_w0, *prm, lmm_rule, c->d_af,
                                                c->d_prep, c->d_pvalue, c->d_beta, c->d_bse,
                                                c->d_extra, c->d_flags, c->d_idx, c->d_counters);
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    return PSB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Fast stats pass (no missing genotypes): carriers, 2x2 table and -- continuous phenotype
+// only -- the Welch sums over carriers.  Used when the tensor pass carries x'v and Q'x, so
+// the only fp64 columns left are (yc, yc^2).  The two columns live in shared memory,
+// transposed to [bit][word] so that lane l (word l of a 32-word chunk) reads consecutive
+// 16-byte cells; a warp walks 4 variants at a time so every cell read serves 4 rows.
+// Non-carrier sums follow from the totals (T - sum over carriers).
+// ---------------------------------------------------------------------------------
+#define BST_VPW 4
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+k_bitstats(const uint32_t *__restrict__ bits, int64_t S, int Wrow, int Wn,
+           const uint32_t *__restrict__ y1, const uint32_t *__restrict__ y0,
+           const uint32_t *__restrict__ valid, const double2 *__restrict__ colsT, double T1, double T2,
+           int n_y1, int n_y0, int C, int col_w0, int32_t *__restrict__ carriers,
+           int32_t *__restrict__ nmissing, int32_t *__restrict__ tab, double *__restrict__ sums) {
+    extern __shared__ __align__(16) unsigned char bst_smem[];
+    double2 *sT = reinterpret_cast<double2 *>(bst_smem);
+    if (NC) {
+        for (int e = threadIdx.x; e < 32 * Wn; e += blockDim.x) sT[e] = colsT[e];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BST_VPW;
+    for (; base < S; base += warps_total * BST_VPW) {
+        int c_all[BST_VPW], n11[BST_VPW], n01[BST_VPW];
+        double s1[BST_VPW], s2[BST_VPW];
+#pragma unroll
+        for (int u = 0; u < BST_VPW; ++u) {
+            c_all[u] = n11[u] = n01[u] = 0;
+            s1[u] = s2[u] = 0.0;
+        }
+        for (int w = lane; w < Wn; w += 32) {
+            const uint32_t vb = __ldg(valid + w), a1 = __ldg(y1 + w), a0 = __ldg(y0 + w);
+            uint32_t x[BST_VPW];
+#pragma unroll
+            for (int u = 0; u < BST_VPW; ++u) {
+                x[u] = (base + u < S) ? (__ldg(bits + (base + u) * Wrow + w) & vb) : 0u;
+                c_all[u] += __popc(x[u]);
+                n11[u] += __popc(x[u] & a1);
+                n01[u] += __popc(x[u] & a0);
+            }
+            if (NC) {
+                const double2 *cp = sT + w;
+#pragma unroll 8
+                for (int b = 0; b < 32; ++b) {
+                    const double2 yv = cp[b * Wn];
+#pragma unroll
+                    for (int u = 0; u < BST_VPW; ++u) {
+                        if ((x[u] >> b) & 1u) {
+                            s1[u] += yv.x;
+                            s2[u] += yv.y;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < BST_VPW; ++u) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c_all[u] += __shfl_xor_sync(0xffffffffu, c_all[u], o);
+                n11[u] += __shfl_xor_sync(0xffffffffu, n11[u], o);
+                n01[u] += __shfl_xor_sync(0xffffffffu, n01[u], o);
+                if (NC) {
+                    s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+                    s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+                }
+            }
+        }
+        if (lane < BST_VPW && base + lane < S) {
+            // lane u publishes variant base + u (static indexing keeps the arrays in registers)
+            int ca = 0, a11 = 0, a01 = 0;
+            double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+            for (int u = 0; u < BST_VPW; ++u)
+                if (lane == u) {
+                    ca = c_all[u]; a11 = n11[u]; a01 = n01[u]; r1 = s1[u]; r2 = s2[u];
+                }
+            const int64_t v = base + lane;
+            carriers[v] = ca;
+            nmissing[v] = 0;
+            tab[v * 4 + 0] = a11;
+            tab[v * 4 + 1] = n_y1 - a11;
+            tab[v * 4 + 2] = a01;
+            tab[v * 4 + 3] = n_y0 - a01;
+            if (NC) {
+                double *s = sums + v * C + col_w0;
+                s[0] = r1;
+                s[1] = r2;
+                s[2] = T1 - r1;
+                s[3] = T2 - r2;
+            }
+        }
+    }
+}
+
+int psb_upload_welch_T(psb_ctx *c, const double *yc, const double *yc2) {
+    const int Wn = c->Wn, N = c->N;
+    std::vector<double> t((size_t)32 * Wn * 2, 0.0);
+    double T1 = 0.0, T2 = 0.0;
+    for (int i = 0; i < N; ++i) {
+        int w = i >> 5, b = i & 31;
+        t[((size_t)b * Wn + w) * 2 + 0] = yc[i];
+        t[((size_t)b * Wn + w) * 2 + 1] = yc2[i];
+        T1 += yc[i];
+        T2 += yc2[i];
+    }
+    c->welch_T1 = T1;
+    c->welch_T2 = T2;
+    PSB_CUDA(cudaMalloc(&c->d_wcolsT, t.size() * sizeof(double)));
+    PSB_CUDA(cudaMemcpy(c->d_wcolsT, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return PSB_OK;
+}
+
+static size_t bitstats_smem(const psb_ctx *c) { return (size_t)32 * c->Wn * sizeof(double2); }
+
+bool psb_bitstats_fits(psb_ctx *c) {
+    return c->d_wcolsT != nullptr && bitstats_smem(c) <= 200 * 1024;
+}
+
+int psb_launch_bitstats(psb_ctx *c, int continuous) {
+    if (c->S == 0) return PSB_OK;
+    const size_t smem = continuous ? bitstats_smem(c) : 0;
+    int per_sm = continuous ? (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / (smem + 1024))) : 8;
+    int64_t blocks = (c->S + 8 * BST_VPW - 1) / (8 * BST_VPW);
+    int64_t maxb = (int64_t)c->sm_count * per_sm;
+    if (blocks > maxb) blocks = maxb;
+    const double2 *ct = reinterpret_cast<const double2 *>(c->d_wcolsT);
+    if (continuous) {
+        PSB_CUDA(cudaFuncSetAttribute(k_bitstats<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_bitstats<2><<<(int)blocks, 256, smem, c->stream>>>(
+            c->d_bits, c->S, c->Wrow, c->Wn, c->d_y1bits, c->d_y0bits, c->d_valid, ct, c->welch_T1,
+            c->welch_T2, c->n_y1, c->n_y0, c->C, c->col_w0, c->d_carriers, c->d_missing, c->d_tab, c->d_sums);
+    } else {
+        k_bitstats<0><<<(int)blocks, 256, 0, c->stream>>>(
+            c->d_bits, c->S, c->Wrow, c->Wn, c->d_y1bits, c->d_y0bits, c->d_valid, ct, c->welch_T1,
+            c->welch_T2, c->n_y1, c->n_y0, c->C, c->col_w0, c->d_carriers, c->d_missing, c->d_tab, c->d_sums);
+    }
     c->launches++;
     PSB_CUDA(cudaGetLastError());
     return PSB_OK;

@@ -199,7 +199,8 @@ def test_oracle_parity_full_path(n, nv, binary, precision):
     m.close()
 
 
-def test_missing_genotypes():
+@pytest.mark.parametrize('precision', PREC2)
+def test_missing_genotypes(precision):
     """NaN genotypes: excluded from the 2x2 table, counted as carriers in af, NaN statistics
     and 'lrt-filtering-failed' (lmm.py:201; input.py:439-452)."""
     from oracle import lmm_oracle as lo
@@ -214,7 +215,7 @@ def test_missing_genotypes():
     k[4, :3] = np.nan
     bits, miss = pack_rows(k)
     Kn = K * (float(n) / np.diag(K).sum())
-    m = plmm.KinshipLMM(np.ones((n, 1)), y.reshape(-1, 1), Kn.copy())
+    m = plmm.KinshipLMM(np.ones((n, 1)), y.reshape(-1, 1), Kn.copy(), precision=precision)
     h2 = m.findH2()['h2']
     r = plmm.run_lmm_bits(m, h2, bits, miss, False, 1, 1, 0.01, 0.99, 0.05)
     for s in (3, 4):
