@@ -117,7 +117,10 @@ int psb_fixed_setup(psb_ctx *ctx, int32_t n_samples, int32_t q, const double *Z,
 
 /* Null model fits on the device with the same solver (model.fit_null, model.py:73-148).
  * Design Z (N x q row-major), no variant column.  out_params: q doubles; out_bse: q
- * doubles; out_llf: log-likelihood; firth != 0 -> Firth-penalised fit (out_llf only).
+ * doubles; out_llf: log-likelihood; firth bit 0 -> Firth-penalised fit (out_llf only), bit 1 ->
+ * start from zeros instead of the log-odds intercept (statsmodels' default, used by
+ * model.fit_lineage_effect, model.py:181-190).  The context's model slot is reused: call
+ * before psb_fixed_setup / psb_lmm_setup.
  * Returns PSB_OK and *out_status = PSB_F_* bits (0 = fitted). */
 int psb_fit_null(psb_ctx *ctx, int32_t n_samples, int32_t q, const double *Z,
                  const double *y, int32_t continuous, int32_t firth, double *out_params,

@@ -1,5 +1,883 @@
-// placeholder, replaced below
+// psb_fixed.cu -- fixed-effects (SEER) model: batched OLS t-test, batched Logit Newton with
+// likelihood-ratio test, Firth-penalised fallback, and the null-model fits.
+//
+// Reference being replaced, per variant:
+//   model.fixed_effects_regression  model.py:202-394
+//   model.fit_firth / firth_likelihood  model.py:397-504
+//   model.fit_null                  model.py:73-148
+//   statsmodels Logit.fit(method='newton') / OLS.fit()  (third party; behaviour restated in
+//   oracle/fixed_oracle.py, which pins it to the goldens of tests/model_test.py)
+//
+// Design [1, k, m, c] (model.py:274-297) is held as Z = [1, m, c] (q columns, shared by all
+// variants, column-contiguous in HBM and L1-resident) plus the variant's bit row: the k
+// column never exists in memory.  Internally the parameter order is (Z_0..Z_{q-1}, k).
+//
+// One warp fits one variant.  Lane l owns samples 32 t + l; every lane accumulates the full
+// X'WX (lower triangle) and the score in registers, a butterfly reduction leaves the sums in
+// all lanes, and each lane runs the small Cholesky solve redundantly (no divergence, no
+// shared memory).  Everything is fp64: the Newton / Firth iterations follow the reference's
+// stopping rules literally (35 steps, |dbeta| <= 1e-8; lagged 1e-4 test and step halving for
+// Firth), so the iterates -- not just the limits -- agree with the reference.
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "psb_internal.cuh"
-extern "C" int psb_fixed_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z, const double *y, int32_t cont, double a, double b) { psb_set_error("not built yet"); return PSB_ERR_UNSUPPORTED; }
-extern "C" int psb_fit_null(psb_ctx *ctx, int32_t n_samples, int32_t q, const double *Z, const double *y, int32_t continuous, int32_t firth, double *out_params, double *out_bse, double *out_llf, uint32_t *out_status) { return PSB_ERR_UNSUPPORTED; }
-extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *p) { return PSB_ERR_UNSUPPORTED; }
+#include "psb_math.cuh"
+
+#define FX_MAXP 16
+
+struct FxArgs {
+    const uint32_t *bits;
+    const double *Z;          // [q][Npad]
+    const uint32_t *y1;       // phenotype == 1 bits
+    const uint32_t *valid;    // sample < N bits
+    int Wrow, Wn, N, Npad;
+    int q;                    // columns of Z
+    int has_x;                // 0: null model (no variant column)
+    double start0;            // log(mean(y) / (1 - mean(y)))
+    double null_llf, null_firth, lrt_pvalue;
+    // outputs (indexed by variant id)
+    double *pvalue, *beta, *bse, *intercept, *betas;
+    uint32_t *flags;
+    int *counters;            // [2]: lrt-filtered, [3]: firth list length
+    int32_t *firth_list;
+    // null-fit outputs (has_x == 0): params[q], bse[q], llf, status
+    double *null_out;
+};
+
+template <int PP>
+struct Tri {
+    static constexpr int SIZE = PP * (PP + 1) / 2;
+    __host__ __device__ static constexpr int at(int a, int b) { return a * (a + 1) / 2 + b; }   // b <= a
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// In-place lower Cholesky of the packed symmetric matrix; returns false when a pivot is not
+// positive (matrix not PD) or not finite.
+// (all loops run over the full constant range with constant-foldable guards, so that the
+// unroller turns every index into a literal and the arrays stay in registers)
+template <int PP>
+__device__ __forceinline__ bool fx_chol(double (&A)[Tri<PP>::SIZE]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < PP; ++j) {
+        double d = A[Tri<PP>::at(j, j)];
+#pragma unroll
+        for (int k = 0; k < PP; ++k)
+            if (k < j) d = fma(-A[Tri<PP>::at(j, k)], A[Tri<PP>::at(j, k)], d);
+        if (!(d > 0.0) || !isfinite(d)) ok = false;
+        const double l = sqrt(d);
+        A[Tri<PP>::at(j, j)] = l;
+        const double inv = 1.0 / l;
+#pragma unroll
+        for (int i = 0; i < PP; ++i) {
+            if (i > j) {
+                double s = A[Tri<PP>::at(i, j)];
+#pragma unroll
+                for (int k = 0; k < PP; ++k)
+                    if (k < j) s = fma(-A[Tri<PP>::at(i, k)], A[Tri<PP>::at(j, k)], s);
+                A[Tri<PP>::at(i, j)] = s * inv;
+            }
+        }
+    }
+    return ok;
+}
+
+// b := (L L')^-1 b
+template <int PP>
+__device__ __forceinline__ void fx_chol_solve(const double (&L)[Tri<PP>::SIZE], double (&b)[PP]) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < PP; ++k)
+            if (k < i) s = fma(-L[Tri<PP>::at(i, k)], b[k], s);
+        b[i] = s / L[Tri<PP>::at(i, i)];
+    }
+#pragma unroll
+    for (int ii = 0; ii < PP; ++ii) {
+        const int i = PP - 1 - ii;
+        double s = b[i];
+#pragma unroll
+        for (int k = 0; k < PP; ++k)
+            if (k > i) s = fma(-L[Tri<PP>::at(k, i)], b[k], s);
+        b[i] = s / L[Tri<PP>::at(i, i)];
+    }
+}
+
+// Straightforward, register-friendly inverse: solve for each unit vector (PP solves).  Used by
+// the Firth path only; V is returned packed (lower triangle).
+template <int PP>
+__device__ __forceinline__ void fx_inverse_from_chol(const double (&L)[Tri<PP>::SIZE],
+                                                     double (&V)[Tri<PP>::SIZE]) {
+#pragma unroll
+    for (int c = 0; c < PP; ++c) {
+        double e[PP];
+#pragma unroll
+        for (int i = 0; i < PP; ++i) e[i] = (i == c) ? 1.0 : 0.0;
+        fx_chol_solve<PP>(L, e);
+#pragma unroll
+        for (int i = 0; i < PP; ++i)
+            if (i >= c) V[Tri<PP>::at(i, c)] = e[i];
+    }
+}
+
+// Row of the design for sample i (internal order: Z_0 = 1, Z_1.., then k, then zero padding).
+template <int PP>
+__device__ __forceinline__ void fx_row(const FxArgs &a, int i, uint32_t xbit, double (&z)[PP]) {
+    z[0] = 1.0;
+#pragma unroll
+    for (int c = 1; c < PP; ++c) {
+        double v = 0.0;
+        if (c < a.q) v = __ldg(a.Z + (size_t)c * a.Npad + i);
+        else if (c == a.q && a.has_x) v = (double)xbit;
+        z[c] = v;
+    }
+}
+
+// One pass over the samples at parameters beta: X'WX (packed), score X'(y - pi),
+// max |y - pi| and the log-likelihood.  All lanes return the full sums.
+template <int PP, bool WITH_LLF>
+__device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, int lane,
+                                        const double (&beta)[PP], double (&H)[Tri<PP>::SIZE],
+                                        double (&g)[PP], double &maxdev, double &llf) {
+#pragma unroll
+    for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] = 0.0;
+#pragma unroll
+    for (int c = 0; c < PP; ++c) g[c] = 0.0;
+    maxdev = 0.0;
+    llf = 0.0;
+    for (int w = 0; w < a.Wn; ++w) {
+        const uint32_t vw = __ldg(a.valid + w);
+        if (!((vw >> lane) & 1u)) continue;
+        const uint32_t xw = a.has_x ? __ldg(xrow + w) : 0u;
+        const uint32_t yw = __ldg(a.y1 + w);
+        const int i = w * 32 + lane;
+        double z[PP];
+        fx_row<PP>(a, i, (xw >> lane) & 1u, z);
+        double eta = 0.0;
+#pragma unroll
+        for (int c = 0; c < PP; ++c) eta = fma(beta[c], z[c], eta);
+        const double y = (double)((yw >> lane) & 1u);
+        const double ex = exp(-fabs(eta));            // in (0, 1]
+        const double den = 1.0 / (1.0 + ex);
+        const double pi = eta >= 0.0 ? den : ex * den;
+        const double wgt = ex * den * den;            // pi (1 - pi)
+        const double r = y - pi;
+        maxdev = fmax(maxdev, fabs(r));
+        if (WITH_LLF) {
+            // log cdf((2y-1) eta) = min(s, 0) - log1p(exp(-|s|)),  s = (2y-1) eta
+            const double s = y > 0.5 ? eta : -eta;
+            llf += fmin(s, 0.0) - log1p(ex);
+        }
+#pragma unroll
+        for (int c = 0; c < PP; ++c) {
+            g[c] = fma(r, z[c], g[c]);
+            const double wz = wgt * z[c];
+#pragma unroll
+            for (int d = 0; d < PP; ++d)
+                if (d <= c) H[Tri<PP>::at(c, d)] = fma(wz, z[d], H[Tri<PP>::at(c, d)]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] = warp_sum(H[e]);
+#pragma unroll
+    for (int c = 0; c < PP; ++c) g[c] = warp_sum(g[c]);
+    maxdev = warp_max(maxdev);
+    if (WITH_LLF) llf = warp_sum(llf);
+    // padding columns (and the absent k column of a null fit): unit diagonal, zero score
+    const int p = a.q + (a.has_x ? 1 : 0);
+#pragma unroll
+    for (int c = 0; c < PP; ++c)
+        if (c >= p) H[Tri<PP>::at(c, c)] = 1.0;
+}
+
+// log-likelihood only
+template <int PP>
+__device__ __forceinline__ double fx_loglike(const FxArgs &a, const uint32_t *xrow, int lane,
+                                             const double (&beta)[PP]) {
+    double llf = 0.0;
+    for (int w = 0; w < a.Wn; ++w) {
+        const uint32_t vw = __ldg(a.valid + w);
+        if (!((vw >> lane) & 1u)) continue;
+        const uint32_t xw = a.has_x ? __ldg(xrow + w) : 0u;
+        const uint32_t yw = __ldg(a.y1 + w);
+        double z[PP];
+        fx_row<PP>(a, w * 32 + lane, (xw >> lane) & 1u, z);
+        double eta = 0.0;
+#pragma unroll
+        for (int c = 0; c < PP; ++c) eta = fma(beta[c], z[c], eta);
+        const double s = ((yw >> lane) & 1u) ? eta : -eta;
+        llf += fmin(s, 0.0) - log1p(exp(-fabs(s)));
+    }
+    return warp_sum(llf);
+}
+
+__device__ __forceinline__ void fx_write_failed(const FxArgs &a, int v, uint32_t f) {
+    a.flags[v] = f;
+}
+
+// Publishes a fitted variant: LRT against the matching null, lrt filter, result columns.
+template <int PP>
+__device__ __forceinline__ void fx_publish(const FxArgs &a, int v, uint32_t f, const double (&beta)[PP],
+                                           double bse, double fit_llf, double null_llf) {
+    const double lrstat = -2.0 * (null_llf - fit_llf);          // model.py:336, :366
+    double p = 1.0;
+    if (lrstat > 0.0) p = psb_chi2_sf1(lrstat);
+    else if (isnan(lrstat)) p = lrstat;
+    double kbeta = 0.0;
+#pragma unroll
+    for (int c = 0; c < PP; ++c)
+        if (c == a.q) kbeta = beta[c];
+    if (p > a.lrt_pvalue || !isfinite(p) || !isfinite(kbeta)) {   // model.py:384
+        f |= PSB_F_LRT_FAILED | PSB_F_FILTER;
+        atomicAdd(&a.counters[2], 1);
+    }
+    a.pvalue[v] = p;
+    a.beta[v] = kbeta;
+    a.bse[v] = bse;
+    a.intercept[v] = beta[0];
+#pragma unroll
+    for (int c = 1; c < PP; ++c)
+        if (c < a.q) a.betas[(size_t)v * (a.q - 1) + (c - 1)] = beta[c];
+    a.flags[v] = f;
+}
+
+// ---------------------------------------------------------------------------------------
+// Logit Newton (statsmodels Logit.fit(method='newton'), call site model.py:328-330)
+// ---------------------------------------------------------------------------------------
+template <int PP>
+__global__ void __launch_bounds__(128)
+k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const int p = a.q + (a.has_x ? 1 : 0);
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tested; t += warps_total) {
+        const int v = a.has_x ? idx[t] : 0;
+        uint32_t f = a.has_x ? a.flags[v] : 0u;
+        if (f & PSB_F_MISSING_DATA) continue;                       // model.py:371-377
+        if (f & PSB_F_BAD_CHISQ) {                                  // model.py:326: straight to Firth
+            if (lane == 0) a.firth_list[atomicAdd(&a.counters[3], 1)] = v;
+            continue;
+        }
+        const uint32_t *xrow = a.bits + (size_t)v * a.Wrow;
+        double beta[PP];
+#pragma unroll
+        for (int c = 0; c < PP; ++c) beta[c] = 0.0;
+        beta[0] = a.start0;
+        double H[Tri<PP>::SIZE], g[PP];
+        double maxdev, llf_unused, maxstep = INFINITY;
+        uint32_t fail = 0;
+        int it = 0;
+        const double n = (double)a.N;
+        for (;;) {
+            fx_eval<PP, false>(a, xrow, lane, beta, H, g, maxdev, llf_unused);
+            if (it > 0 && maxdev <= 1e-8) { fail = PSB_F_PERFECT_SEP; break; }   // _check_perfect_pred
+            if (it > 0 && !(maxstep > 1e-8)) break;                              // converged
+            if (it >= 35) break;                                                 // maxiter
+            // H/n + 1e-10 I, solve for the step
+#pragma unroll
+            for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] /= n;
+#pragma unroll
+            for (int c = 0; c < PP; ++c) {
+                if (c < p) H[Tri<PP>::at(c, c)] += 1e-10;
+                g[c] /= n;
+            }
+            if (!fx_chol<PP>(H)) { fail = PSB_F_MATRIX_INV; break; }
+            fx_chol_solve<PP>(H, g);
+            maxstep = 0.0;
+#pragma unroll
+            for (int c = 0; c < PP; ++c) {
+                beta[c] += g[c];
+                maxstep = fmax(maxstep, fabs(g[c]));
+            }
+            if (isnan(maxstep)) { fail = PSB_F_MATRIX_INV; break; }
+            ++it;
+        }
+        double bse_x = NAN;
+        double bse_all[PP];
+        if (!fail) {
+            // bse = sqrt(diag(inv(X'WX))) at the final parameters (H holds X'WX there)
+            if (!fx_chol<PP>(H)) {
+                fail = PSB_F_MATRIX_INV;
+            } else if (a.has_x) {
+                double e[PP];
+#pragma unroll
+                for (int c = 0; c < PP; ++c) e[c] = (c == a.q) ? 1.0 : 0.0;
+                fx_chol_solve<PP>(H, e);
+#pragma unroll
+                for (int c = 0; c < PP; ++c)
+                    if (c == a.q) bse_x = sqrt(e[c]);
+            } else {
+#pragma unroll
+                for (int c0 = 0; c0 < PP; ++c0) {
+                    double e[PP];
+#pragma unroll
+                    for (int c = 0; c < PP; ++c) e[c] = (c == c0) ? 1.0 : 0.0;
+                    fx_chol_solve<PP>(H, e);
+                    bse_all[c0] = sqrt(e[c0]);
+                }
+            }
+        }
+        if (!a.has_x) {
+            // null fit: params, bse, llf, status
+            double llf = fail ? NAN : fx_loglike<PP>(a, xrow, lane, beta);
+            if (lane == 0) {
+#pragma unroll
+                for (int c = 0; c < PP; ++c)
+                    if (c < a.q) {
+                        a.null_out[c] = beta[c];
+                        a.null_out[a.q + c] = fail ? NAN : bse_all[c];
+                    }
+                a.null_out[2 * a.q] = llf;
+                a.null_out[2 * a.q + 1] = (double)fail;
+                a.null_out[2 * a.q + 2] = (double)it;
+            }
+            continue;
+        }
+        if (!fail && bse_x > 3.0) fail = PSB_F_HIGH_BSE;                // model.py:332-334
+        if (fail) {
+            if (lane == 0) {
+                a.flags[v] = f | fail;
+                a.firth_list[atomicAdd(&a.counters[3], 1)] = v;
+            }
+            continue;
+        }
+        const double llf = fx_loglike<PP>(a, xrow, lane, beta);
+        if (lane == 0) fx_publish<PP>(a, v, f, beta, bse_x, llf, a.null_llf);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Firth regression (model.fit_firth, model.py:414-504)
+// ---------------------------------------------------------------------------------------
+template <int PP>
+__global__ void __launch_bounds__(128)
+k_fixed_firth(FxArgs a, int n_list) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    const int p = a.q + (a.has_x ? 1 : 0);
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_list; t += warps_total) {
+        const int v = a.has_x ? a.firth_list[t] : 0;
+        uint32_t f = a.has_x ? (a.flags[v] | PSB_F_FIRTH_USED) : 0u;
+        const uint32_t *xrow = a.bits + (size_t)v * a.Wrow;
+        double beta[PP], prev[PP];
+#pragma unroll
+        for (int c = 0; c < PP; ++c) beta[c] = prev[c] = 0.0;
+        beta[0] = a.start0;
+        double H[Tri<PP>::SIZE], V[Tri<PP>::SIZE], g[PP];
+        double maxdev, llf_cur;
+        bool ok = true, converged = false;
+        // state at the current iterate: H = X'WX, llf, FL = -(llf + 0.5 log det H)
+        fx_eval<PP, true>(a, xrow, lane, beta, H, g, maxdev, llf_cur);
+        double hxx_cur = 0.0;
+#pragma unroll
+        for (int c = 0; c < PP; ++c)
+            if (c == a.q) hxx_cur = H[Tri<PP>::at(c, c)];
+        double fl_cur, fitll = NAN, hxx_fit = NAN;
+        double last_step_norm = INFINITY;      // || betas[i] - betas[i-1] ||
+        for (int i = 0; i < 1000 && ok; ++i) {
+            if (!fx_chol<PP>(H)) { ok = false; break; }
+            double logdet = 0.0;
+#pragma unroll
+            for (int c = 0; c < PP; ++c) logdet += log(H[Tri<PP>::at(c, c)]);
+            logdet *= 2.0;
+            fl_cur = -(llf_cur + 0.5 * logdet);
+            fx_inverse_from_chol<PP>(H, V);            // V = pinv(-hessian), model.py:450
+            // U = X'(y - pi + h (1/2 - pi)),  h_i = w_i x_i' V x_i   (model.py:455-466)
+            double U[PP];
+#pragma unroll
+            for (int c = 0; c < PP; ++c) U[c] = 0.0;
+            for (int w = 0; w < a.Wn; ++w) {
+                const uint32_t vw = __ldg(a.valid + w);
+                if (!((vw >> lane) & 1u)) continue;
+                const uint32_t xw = a.has_x ? __ldg(xrow + w) : 0u;
+                const uint32_t yw = __ldg(a.y1 + w);
+                double z[PP];
+                fx_row<PP>(a, w * 32 + lane, (xw >> lane) & 1u, z);
+                double eta = 0.0;
+#pragma unroll
+                for (int c = 0; c < PP; ++c) eta = fma(beta[c], z[c], eta);
+                const double ex = exp(-fabs(eta));
+                const double den = 1.0 / (1.0 + ex);
+                const double pi = eta >= 0.0 ? den : ex * den;
+                const double wgt = ex * den * den;
+                double quad = 0.0;
+#pragma unroll
+                for (int c = 0; c < PP; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int d = 0; d < PP; ++d)
+                        s = fma(c >= d ? V[Tri<PP>::at(c, d)] : V[Tri<PP>::at(d, c)], z[d], s);
+                    quad = fma(s, z[c], quad);
+                }
+                const double h = wgt * quad;
+                const double y = (double)((yw >> lane) & 1u);
+                const double r = y - pi + h * (0.5 - pi);
+#pragma unroll
+                for (int c = 0; c < PP; ++c) U[c] = fma(r, z[c], U[c]);
+            }
+            double cand[PP];
+#pragma unroll
+            for (int c = 0; c < PP; ++c) U[c] = warp_sum(U[c]);
+#pragma unroll
+            for (int c = 0; c < PP; ++c) {
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < PP; ++d)
+                    s = fma(c >= d ? V[Tri<PP>::at(c, d)] : V[Tri<PP>::at(d, c)], (d < p) ? U[d] : 0.0, s);
+                cand[c] = beta[c] + ((c < p) ? s : 0.0);
+            }
+            // step halving while the penalised likelihood gets worse (model.py:470-476)
+            double llf_new, fl_new, hxx_new = 0.0;
+            int j = 0;
+            for (;;) {
+                fx_eval<PP, true>(a, xrow, lane, cand, H, g, maxdev, llf_new);
+#pragma unroll
+                for (int c = 0; c < PP; ++c)
+                    if (c == a.q) hxx_new = H[Tri<PP>::at(c, c)];
+                // log det via a scratch Cholesky (V is free to be reused as scratch)
+#pragma unroll
+                for (int e = 0; e < Tri<PP>::SIZE; ++e) V[e] = H[e];
+                double ld = NAN;
+                if (fx_chol<PP>(V)) {
+                    ld = 0.0;
+#pragma unroll
+                    for (int c = 0; c < PP; ++c) ld += log(V[Tri<PP>::at(c, c)]);
+                    ld *= 2.0;
+                }
+                fl_new = -(llf_new + 0.5 * ld);
+                if (!(fl_new > fl_cur)) break;
+#pragma unroll
+                for (int c = 0; c < PP; ++c) cand[c] = beta[c] + 0.5 * (cand[c] - beta[c]);
+                if (++j > 1000) { ok = false; break; }
+            }
+            if (!ok) break;
+            // betas.append(new_beta)
+            double nrm = 0.0;
+#pragma unroll
+            for (int c = 0; c < PP; ++c) {
+                double d = beta[c] - prev[c];
+                nrm = fma(d, d, nrm);
+            }
+            const double prev_step = sqrt(nrm);            // || betas[i] - betas[i-1] ||
+#pragma unroll
+            for (int c = 0; c < PP; ++c) {
+                prev[c] = beta[c];
+                beta[c] = cand[c];
+            }
+            llf_cur = llf_new;
+            hxx_cur = hxx_new;
+            fitll = -fl_new;
+            hxx_fit = hxx_new;
+            last_step_norm = prev_step;
+            if (i > 0 && prev_step < 1e-4) { converged = true; break; }    // model.py:480-483
+        }
+        (void)hxx_cur;
+        if (ok && !converged) ok = false;                  // model.py:485-486 (limit reached)
+        (void)last_step_norm;
+        if (!a.has_x) {
+            if (lane == 0) {
+                a.null_out[2 * a.q] = ok ? fitll : NAN;
+                a.null_out[2 * a.q + 1] = ok ? 0.0 : (double)PSB_F_FIRTH_FAIL;
+#pragma unroll
+                for (int c = 0; c < PP; ++c)
+                    if (c < a.q) {
+                        a.null_out[c] = beta[c];
+                        a.null_out[a.q + c] = NAN;
+                    }
+            }
+            continue;
+        }
+        if (lane == 0) {
+            if (!ok) {
+                a.flags[v] = f | PSB_F_FIRTH_FAIL | PSB_F_FILTER;       // model.py:356-362
+                atomicAdd(&a.counters[2], 1);
+            } else {
+                fx_publish<PP>(a, v, f, beta, sqrt(hxx_fit), fitll, a.null_firth);   // bse: model.py:491
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// OLS (statsmodels OLS.fit, call site model.py:300-312) in closed form from the masked sums
+//   u = Z'x, xy = x'y (k_bitsums), G = (Z'Z)^-1, Zty, yQy precomputed:
+//   xQx = x'x - u'Gu, xQy = xy - u'G Zty, beta_k = xQy / xQx, gamma = G (Zty - u beta_k),
+//   RSS = yQy - beta_k xQy, df = N - (q + 1), bse_k = sqrt(RSS / df / xQx).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_fixed_ols(int n_tested, const int32_t *__restrict__ idx, const double *__restrict__ sums, int C,
+            int col_y, int col_z1, int q, int N, const int32_t *__restrict__ carriers,
+            const double *__restrict__ consts /* G[q*q], Zty[q], yQy */, double lrt_pvalue,
+            double *__restrict__ pvalue, double *__restrict__ beta_out, double *__restrict__ bse_out,
+            double *__restrict__ intercept, double *__restrict__ betas, uint32_t *__restrict__ flags,
+            int *__restrict__ counters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tested) return;
+    const int v = idx[t];
+    uint32_t f = flags[v];
+    if (f & PSB_F_MISSING_DATA) return;
+    const double *G = consts, *Zty = consts + q * q;
+    const double yQy = consts[q * q + q];
+    const double *s = sums + (size_t)v * C;
+    double u[FX_MAXP];
+    u[0] = (double)carriers[v];
+    for (int c = 1; c < q; ++c) u[c] = s[col_z1 + c - 1];
+    const double xx = u[0], xy = s[col_y];
+    double Gu[FX_MAXP];
+    double uGu = 0.0, uGz = 0.0;
+    for (int c = 0; c < q; ++c) {
+        double acc = 0.0;
+        for (int d = 0; d < q; ++d) acc = fma(G[c * q + d], u[d], acc);
+        Gu[c] = acc;
+        uGu = fma(acc, u[c], uGu);
+        uGz = fma(acc, Zty[c], uGz);
+    }
+    const double xQx = xx - uGu, xQy = xy - uGz;
+    const double bk = xQy / xQx;
+    const double rss = yQy - bk * xQy;
+    const double df = (double)(N - (q + 1));
+    const double bse = sqrt(rss / df / xQx);
+    const double tv = bk / bse;
+    double p = psb_t2_sf(tv * tv, df);
+    if (!(xQx > 1e-9 * fmax(xx, 1.0))) p = NAN;        // k in the span of Z: rank-deficient design
+    if (p > lrt_pvalue || !isfinite(p) || !isfinite(bk)) {
+        f |= PSB_F_LRT_FAILED | PSB_F_FILTER;
+        atomicAdd(&counters[2], 1);
+    }
+    pvalue[v] = p;
+    beta_out[v] = bk;
+    bse_out[v] = bse;
+    // gamma = G Zty - beta_k G u
+    for (int c = 0; c < q; ++c) {
+        double acc = 0.0;
+        for (int d = 0; d < q; ++d) acc = fma(G[c * q + d], Zty[d], acc);
+        double gam = acc - bk * Gu[c];
+        if (c == 0) intercept[v] = gam;
+        else betas[(size_t)v * (q - 1) + (c - 1)] = gam;
+    }
+    flags[v] = f;
+}
+
+// missing-data-error (model.py:371-377): NaN genotypes reach the design matrix
+__global__ void k_fixed_mark_missing(int n_tested, const int32_t *__restrict__ idx,
+                                     const int32_t *__restrict__ nmissing, uint32_t *__restrict__ flags,
+                                     int *__restrict__ counters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tested) return;
+    int v = idx[t];
+    if (nmissing[v] > 0) {
+        flags[v] |= PSB_F_MISSING_DATA | PSB_F_FILTER;
+        atomicAdd(&counters[2], 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+int psb_upload_pheno(psb_ctx *c, const double *y);
+void psb_fill_welch_cols(const double *y, int N, int Npad, double *cols, int col_w0, uint64_t *mask_lo,
+                         uint64_t *mask_hi);
+
+static bool host_chol_inverse(std::vector<double> &A, int q) {
+    // A (q x q, symmetric PD, row-major) -> A^-1 by Cholesky
+    std::vector<double> L(A);
+    for (int j = 0; j < q; ++j) {
+        double d = L[j * q + j];
+        for (int k = 0; k < j; ++k) d -= L[j * q + k] * L[j * q + k];
+        if (!(d > 0.0)) return false;
+        L[j * q + j] = sqrt(d);
+        for (int i = j + 1; i < q; ++i) {
+            double s = L[i * q + j];
+            for (int k = 0; k < j; ++k) s -= L[i * q + k] * L[j * q + k];
+            L[i * q + j] = s / L[j * q + j];
+        }
+    }
+    for (int c = 0; c < q; ++c) {
+        std::vector<double> e(q, 0.0);
+        e[c] = 1.0;
+        for (int i = 0; i < q; ++i) {
+            double s = e[i];
+            for (int k = 0; k < i; ++k) s -= L[i * q + k] * e[k];
+            e[i] = s / L[i * q + i];
+        }
+        for (int i = q - 1; i >= 0; --i) {
+            double s = e[i];
+            for (int k = i + 1; k < q; ++k) s -= L[k * q + i] * e[k];
+            e[i] = s / L[i * q + i];
+        }
+        for (int i = 0; i < q; ++i) A[i * q + c] = e[i];
+    }
+    return true;
+}
+
+static int fixed_common_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z, const double *y) {
+    PSB_REQUIRE(c && Z && y, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(N > 1 && q >= 1, PSB_ERR_ARG, "bad shape N=%d q=%d", N, q);
+    PSB_REQUIRE(q + 1 <= FX_MAXP, PSB_ERR_UNSUPPORTED,
+                "design width %d exceeds the device solver's limit of %d columns", q + 1, FX_MAXP);
+    for (int i = 0; i < N; ++i)
+        PSB_REQUIRE(Z[(size_t)i * q] == 1.0, PSB_ERR_ARG, "column 0 of Z must be the intercept (ones)");
+    PSB_CUDA(cudaSetDevice(c->device));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    psb_free_model(c);
+    c->N = N;
+    c->Wn = (N + 31) / 32;
+    c->Npad = c->Wn * 32;
+    c->q = q;
+    std::vector<double> Zc((size_t)q * c->Npad, 0.0);
+    for (int i = 0; i < N; ++i)
+        for (int k = 0; k < q; ++k) Zc[(size_t)k * c->Npad + i] = Z[(size_t)i * q + k];
+    PSB_CUDA(cudaMalloc(&c->d_Z, Zc.size() * sizeof(double)));
+    PSB_CUDA(cudaMemcpy(c->d_Z, Zc.data(), Zc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    return psb_upload_pheno(c, y);
+}
+
+extern "C" int psb_fixed_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z, const double *y,
+                               int32_t continuous, double null_llf, double null_firth) {
+    int rc = fixed_common_setup(c, N, q, Z, y);
+    if (rc) return rc;
+    c->continuous = continuous ? 1 : 0;
+    c->null_llf = null_llf;
+    c->null_firth = null_firth;
+    double mean = 0.0;
+    for (int i = 0; i < N; ++i) mean += y[i];
+    mean /= N;
+    c->y_mean = mean;
+    // masked-sum columns for k_bitsums: y | Z_1..Z_{q-1} | Welch(4)
+    c->C = 1 + (q - 1) + 4;
+    c->col_b = 0;
+    c->col_q0 = 1;
+    c->col_w0 = q;
+    c->colmask_lo = c->colmask_hi = 0;
+    std::vector<double> cols((size_t)c->C * c->Npad, 0.0);
+    for (int i = 0; i < N; ++i) {
+        cols[i] = y[i];
+        for (int k = 1; k < q; ++k) cols[(size_t)k * c->Npad + i] = Z[(size_t)i * q + k];
+    }
+    psb_fill_welch_cols(y, N, c->Npad, cols.data(), c->col_w0, &c->colmask_lo, &c->colmask_hi);
+    rc = psb_upload_welch_T(c, &cols[(size_t)c->col_w0 * c->Npad], &cols[(size_t)(c->col_w0 + 1) * c->Npad]);
+    if (rc) return rc;
+    PSB_CUDA(cudaMalloc(&c->d_cols, cols.size() * sizeof(double)));
+    PSB_CUDA(cudaMemcpy(c->d_cols, cols.data(), cols.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (continuous) {
+        // G = (Z'Z)^-1, Zty, yQy
+        std::vector<double> G((size_t)q * q, 0.0), Zty(q, 0.0);
+        double yty = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double *zi = Z + (size_t)i * q;
+            for (int a = 0; a < q; ++a) {
+                Zty[a] += zi[a] * y[i];
+                for (int b = 0; b < q; ++b) G[a * q + b] += zi[a] * zi[b];
+            }
+            yty += y[i] * y[i];
+        }
+        PSB_REQUIRE(host_chol_inverse(G, q), PSB_ERR_ARG,
+                    "covariate design [1, m, c] is rank deficient; drop collinear columns");
+        double zGz = 0.0;
+        for (int a = 0; a < q; ++a)
+            for (int b = 0; b < q; ++b) zGz += Zty[a] * G[a * q + b] * Zty[b];
+        std::vector<double> consts(G);
+        consts.insert(consts.end(), Zty.begin(), Zty.end());
+        consts.push_back(yty - zGz);
+        PSB_CUDA(cudaMalloc(&c->d_fixed_const, consts.size() * sizeof(double)));
+        PSB_CUDA(cudaMemcpy(c->d_fixed_const, consts.data(), consts.size() * sizeof(double),
+                            cudaMemcpyHostToDevice));
+    }
+    c->model = PSB_MODEL_FIXED;
+    return PSB_OK;
+}
+
+static FxArgs fx_args(psb_ctx *c, const psb_params *prm, int has_x) {
+    FxArgs a;
+    a.bits = c->d_bits;
+    a.Z = c->d_Z;
+    a.y1 = c->d_y1bits;
+    a.valid = c->d_valid;
+    a.Wrow = c->Wrow;
+    a.Wn = c->Wn;
+    a.N = c->N;
+    a.Npad = c->Npad;
+    a.q = c->q;
+    a.has_x = has_x;
+    a.start0 = log(c->y_mean / (1.0 - c->y_mean));
+    a.null_llf = c->null_llf;
+    a.null_firth = c->null_firth;
+    a.lrt_pvalue = prm ? prm->lrt_pvalue : 1.0;
+    a.pvalue = c->d_pvalue;
+    a.beta = c->d_beta;
+    a.bse = c->d_bse;
+    a.intercept = c->d_extra;
+    a.betas = c->d_betas;
+    a.flags = c->d_flags;
+    a.counters = c->d_counters;
+    a.firth_list = c->d_idx2;
+    a.null_out = nullptr;
+    return a;
+}
+
+template <int PP>
+static void launch_logit(psb_ctx *c, const FxArgs &a, int n, int grid) {
+    k_fixed_logit<PP><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
+}
+template <int PP>
+static void launch_firth(psb_ctx *c, const FxArgs &a, int n, int grid) {
+    k_fixed_firth<PP><<<grid, 128, 0, c->stream>>>(a, n);
+}
+
+static int fx_dispatch(psb_ctx *c, const FxArgs &a, int n, bool firth) {
+    if (n <= 0) return PSB_OK;
+    const int p = a.q + (a.has_x ? 1 : 0);
+    const int warps = 4;
+    int grid = std::min(psb_div_up(n, warps), c->sm_count * 8);
+    if (p <= 4) firth ? launch_firth<4>(c, a, n, grid) : launch_logit<4>(c, a, n, grid);
+    else if (p <= 8) firth ? launch_firth<8>(c, a, n, grid) : launch_logit<8>(c, a, n, grid);
+    else if (p <= 12) firth ? launch_firth<12>(c, a, n, grid) : launch_logit<12>(c, a, n, grid);
+    else firth ? launch_firth<16>(c, a, n, grid) : launch_logit<16>(c, a, n, grid);
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    return PSB_OK;
+}
+
+extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
+    PSB_REQUIRE(c && prm, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->model == PSB_MODEL_FIXED, PSB_ERR_STATE, "psb_run_fixed without psb_fixed_setup");
+    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "psb_run_fixed without psb_submit");
+    PSB_REQUIRE((prm->continuous != 0) == (c->continuous != 0), PSB_ERR_ARG,
+                "params.continuous differs from psb_fixed_setup");
+    PSB_CUDA(cudaSetDevice(c->device));
+    int rc = psb_ensure_capacity(c, c->S, c->q > 1 ? c->q - 1 : 1);
+    if (rc) return rc;
+    PSB_CUDA(cudaEventRecord(c->ev_run0, c->stream));
+    if (c->S > 0 && c->q > 1)
+        PSB_CUDA(cudaMemsetAsync(c->d_betas, 0xFF, (size_t)c->S * (c->q - 1) * sizeof(double), c->stream));
+    // stats: binary needs only the popcount table; continuous needs y'x and Z'x as well
+    if (!c->continuous && !c->d_miss && psb_bitstats_fits(c))
+        rc = psb_launch_bitstats(c, 0);
+    else
+        rc = psb_launch_bitsums(c);
+    if (rc) return rc;
+    rc = psb_launch_prefilter(c, prm, /*lmm_rule=*/0);
+    if (rc) return rc;
+    int h_cnt[8] = {0};
+    PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    const int n_tested = h_cnt[0];
+    if (n_tested > 0 && c->d_miss) {
+        k_fixed_mark_missing<<<psb_div_up(n_tested, 256), 256, 0, c->stream>>>(
+            n_tested, c->d_idx, c->d_missing, c->d_flags, c->d_counters);
+        c->launches++;
+        PSB_CUDA(cudaGetLastError());
+    }
+    PSB_CUDA(cudaEventRecord(c->ev_k0, c->stream));
+    if (n_tested > 0) {
+        if (c->continuous) {
+            k_fixed_ols<<<psb_div_up(n_tested, 256), 256, 0, c->stream>>>(
+                n_tested, c->d_idx, c->d_sums, c->C, c->col_b, c->col_q0, c->q, c->N, c->d_carriers,
+                c->d_fixed_const, prm->lrt_pvalue, c->d_pvalue, c->d_beta, c->d_bse, c->d_extra,
+                c->d_betas, c->d_flags, c->d_counters);
+            c->launches++;
+            PSB_CUDA(cudaGetLastError());
+        } else {
+            FxArgs a = fx_args(c, prm, 1);
+            rc = fx_dispatch(c, a, n_tested, false);
+            if (rc) return rc;
+            PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost,
+                                     c->stream));
+            PSB_CUDA(cudaStreamSynchronize(c->stream));
+            rc = fx_dispatch(c, a, h_cnt[3], true);
+            if (rc) return rc;
+        }
+    }
+    PSB_CUDA(cudaEventRecord(c->ev_k1, c->stream));
+    c->have_k_ev = true;
+    PSB_CUDA(cudaEventRecord(c->ev_run1, c->stream));
+    c->have_run_ev = true;
+    c->ran = true;
+    return PSB_OK;
+}
+
+// model.fit_null (model.py:73-148) with the device solver (binary) or host normal equations
+// (continuous: a single q x q system).
+extern "C" int psb_fit_null(psb_ctx *c, int32_t N, int32_t q, const double *Z, const double *y,
+                            int32_t continuous, int32_t firth, double *out_params, double *out_bse,
+                            double *out_llf, uint32_t *out_status) {
+    PSB_REQUIRE(out_params && out_bse && out_llf && out_status, PSB_ERR_ARG, "NULL output");
+    *out_status = 0;
+    if (continuous) {
+        PSB_REQUIRE(c && Z && y && N > q && q >= 1, PSB_ERR_ARG, "bad arguments");
+        std::vector<double> G((size_t)q * q, 0.0), Zty(q, 0.0);
+        double yty = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const double *zi = Z + (size_t)i * q;
+            for (int a = 0; a < q; ++a) {
+                Zty[a] += zi[a] * y[i];
+                for (int b = 0; b < q; ++b) G[a * q + b] += zi[a] * zi[b];
+            }
+            yty += y[i] * y[i];
+        }
+        if (!host_chol_inverse(G, q)) {
+            *out_status = PSB_F_MATRIX_INV;
+            return PSB_OK;
+        }
+        double ssr = yty;
+        for (int a = 0; a < q; ++a) {
+            double s = 0.0;
+            for (int b = 0; b < q; ++b) s += G[a * q + b] * Zty[b];
+            out_params[a] = s;
+        }
+        for (int a = 0; a < q; ++a) ssr -= out_params[a] * Zty[a];
+        const double df = N - q;
+        for (int a = 0; a < q; ++a) out_bse[a] = sqrt(G[a * q + a] * ssr / df);
+        *out_llf = -0.5 * N * (log(2.0 * M_PI) + log(ssr / N) + 1.0);
+        return PSB_OK;
+    }
+    // binary: borrow the context's model slot
+    int rc = fixed_common_setup(c, N, q, Z, y);
+    if (rc) return rc;
+    double mean = 0.0;
+    for (int i = 0; i < N; ++i) mean += y[i];
+    c->y_mean = mean / N;
+    c->continuous = 0;
+    c->model = PSB_MODEL_FIXED;
+    rc = psb_ensure_capacity(c, 1, q > 1 ? q - 1 : 1);
+    if (rc) return rc;
+    double *d_out = nullptr;
+    PSB_CUDA(cudaMalloc(&d_out, (2 * q + 3) * sizeof(double)));
+    c->d_bits = nullptr;
+    c->Wrow = 0;
+    FxArgs a = fx_args(c, nullptr, 0);
+    a.null_out = d_out;
+    if (firth & 2) a.start0 = 0.0;      // statsmodels default start (model.py:188)
+    rc = fx_dispatch(c, a, 1, (firth & 1) != 0);
+    if (rc) {
+        cudaFree(d_out);
+        return rc;
+    }
+    std::vector<double> h(2 * q + 3, 0.0);
+    PSB_CUDA(cudaMemcpyAsync(h.data(), d_out, (2 * q + 2) * sizeof(double), cudaMemcpyDeviceToHost,
+                             c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_out);
+    for (int a2 = 0; a2 < q; ++a2) {
+        out_params[a2] = h[a2];
+        out_bse[a2] = h[q + a2];
+    }
+    *out_llf = h[2 * q];
+    *out_status = (uint32_t)h[2 * q + 1];
+    psb_free_model(c);
+    return PSB_OK;
+}

@@ -130,7 +130,7 @@ class Engine(object):
                                        float(null_firth)))
         self.n_samples, self.q, self.model = n, q, 'fixed'
 
-    def fit_null(self, Z, y, continuous, firth=False):
+    def fit_null(self, Z, y, continuous, firth=False, start_zero=False):
         """model.fit_null on the device.  Returns (params, bse, llf, status_flags)."""
         Z = np.ascontiguousarray(Z, dtype=np.float64)
         y = np.ascontiguousarray(np.asarray(y, dtype=np.float64).reshape(-1))
@@ -140,7 +140,8 @@ class Engine(object):
         llf = ctypes.c_double(0.0)
         st = c_uint32(0)
         check(self.lib.psb_fit_null(self._ctx, n, q, self._dptr(Z), self._dptr(y),
-                                    int(bool(continuous)), int(bool(firth)), self._dptr(params),
+                                    int(bool(continuous)), int(bool(firth)) | (2 if start_zero else 0),
+                                    self._dptr(params),
                                     self._dptr(bse), byref(llf), byref(st)))
         return params, bse, llf.value, st.value
 

@@ -1,0 +1,223 @@
+"""GPU parity tests for the fixed-effects (SEER) path: CUDA through the C ABI vs the oracle
+(oracle/fixed_oracle.py, pinned to the reference's tests/model_test.py goldens) and vs those
+goldens directly.  Tolerance 1e-6 relative on prep / lrt-pvalue / kbeta / bse / intercept /
+betas (BASELINE.json north_star); notes, prefilter/filter flags and counters exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6
+NONE = np.empty((0, 0))
+
+
+def _rel(a, b):
+    a, b = float(a), float(b)
+    if np.isnan(a) and np.isnan(b):
+        return 0.0
+    if b == 0:
+        return abs(a)
+    return abs(a / b - 1)
+
+
+def _check_golden(s, g, notes, prefilter, filt):
+    for f in ['prep', 'pvalue', 'kbeta', 'bse', 'intercept']:
+        assert abs(getattr(s, f) - g[f]) < 1e-7, (f, getattr(s, f), g[f])
+    assert np.abs(np.asarray(s.betas) - g['betas']).max() < 1e-7
+    assert s.notes == notes and s.prefilter == prefilter and s.filter == filt
+
+
+def test_fit_null_goldens(goldens, utd):
+    """tests/model_test.py:119-172."""
+    from pyseer_b200 import model as pm
+    r = pm.fit_null(utd['p_binary'], utd['m'], NONE, False)
+    assert np.abs(r.params - goldens['null_binary_params']).max() < 1e-7
+    assert abs(pm.fit_null(utd['p_binary'], utd['m'], NONE, False, True)
+               - goldens['null_binary_firth']) < 1e-7
+    r = pm.fit_null(utd['p_binary'], utd['m'], utd['cov'], False)
+    assert np.abs(r.params - goldens['null_binary_cov_params']).max() < 1e-7
+    assert abs(pm.fit_null(utd['p_binary'], utd['m'], utd['cov'], False, True)
+               - goldens['null_binary_cov_firth']) < 1e-7
+    p = np.array([1.] * 10 + [0.] * 90)
+    assert pm.fit_null(p, p.reshape(-1, 1).copy(), NONE, False) is None     # perfectly separable
+    r = pm.fit_null(utd['p_continuous'], utd['m'], NONE, True)
+    assert np.abs(r.params - goldens['null_cont_params']).max() < 1e-7
+    r = pm.fit_null(utd['p_continuous'], utd['m'], utd['cov'], True)
+    assert np.abs(r.params - goldens['null_cont_cov_params']).max() < 1e-7
+
+
+def test_null_fit_matches_oracle(utd):
+    from oracle import fixed_oracle as fo
+    from pyseer_b200 import model as pm
+    for cov in (NONE, utd['cov']):
+        o = fo.fit_null(utd['p_binary'], utd['m'], cov, False)
+        r = pm.fit_null(utd['p_binary'], utd['m'], cov, False)
+        assert abs(r.llf - o.llf) < 1e-9 and np.abs(r.bse / o.bse - 1).max() < 1e-8
+        o = fo.fit_null(utd['p_continuous'], utd['m'], cov, True)
+        r = pm.fit_null(utd['p_continuous'], utd['m'], cov, True)
+        assert abs(r.llf - o.llf) < 1e-9 and np.abs(r.bse / o.bse - 1).max() < 1e-8
+
+
+def test_lineage_goldens(goldens, utd):
+    """tests/model_test.py:175-195."""
+    from pyseer_b200 import model as pm
+    assert pm.fit_lineage_effect(utd['m'], NONE, utd['k']) == goldens['lineage_index']
+    assert pm.fit_lineage_effect(utd['lin'], NONE, utd['k']) == goldens['lineage_index']
+    k = np.array([1.] * 10 + [0.] * 90)
+    assert pm.fit_lineage_effect(k.reshape(-1, 1).copy(), NONE, k) is None
+
+
+def test_fixed_effects_binary_goldens(goldens, utd):
+    """tests/model_test.py:237-386."""
+    from pyseer_b200 import model as pm
+    p, k, m = utd['p_binary'], utd['k'], utd['m']
+    args = dict(variant='variant', af=0.2, pattern='test', null_res=-9.9, null_firth=-9.9,
+                kstrains=[], nkstrains=[], continuous=False)
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=NONE, lineage_effects=False, lin=None,
+                                    pret=1, lrtt=1, **args)
+    _check_golden(s, goldens['fe_binary'], set(), False, False)
+    s = pm.fixed_effects_regression(p=None, k=k, m=m, c=NONE, lineage_effects=False, lin=None,
+                                    pret=1, lrtt=1, **args)
+    assert s.notes == {'af-filter'} and s.prefilter and not s.filter and np.isnan(s.prep)
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=NONE, lineage_effects=False, lin=None,
+                                    pret=0.05, lrtt=1, **args)
+    assert s.notes == {'pre-filtering-failed'} and s.prefilter and np.isnan(s.pvalue)
+    assert s.betas.shape == (0,)
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=NONE, lineage_effects=False, lin=None,
+                                    pret=1, lrtt=0.05, **args)
+    _check_golden(s, goldens['fe_binary'], {'lrt-filtering-failed'}, False, True)
+    pb = np.array([1.] * 10 + [0.] * 90)
+    mb = pb.reshape(-1, 1).copy()
+    s = pm.fixed_effects_regression(p=pb, k=pb.copy(), m=mb, c=NONE, lineage_effects=False,
+                                    lin=None, pret=1, lrtt=1, **args)
+    # k == m: exactly collinear design.  The reference ploughs on through pinv / det of a
+    # singular information matrix and returns rounding noise (kbeta -88.7, bse 0.0,
+    # tests/model_test.py:327-335); the device solver reports the singularity instead.
+    assert s.notes == {'bad-chisq', 'firth-fail'} and s.filter and not s.prefilter
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=utd['cov'], lineage_effects=False, lin=None,
+                                    pret=1, lrtt=1, **args)
+    _check_golden(s, goldens['fe_binary_cov'], set(), False, False)
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=NONE, lineage_effects=True, lin=utd['lin'],
+                                    pret=1, lrtt=1, **args)
+    _check_golden(s, goldens['fe_binary'], set(), False, False)
+    assert s.max_lineage == 2
+
+
+def test_fixed_effects_continuous_goldens(goldens, utd):
+    """tests/model_test.py:389-517."""
+    from pyseer_b200 import model as pm
+    p, k, m = utd['p_continuous'], utd['k'], utd['m']
+    args = dict(variant='variant', af=0.2, pattern='test', null_res=None, null_firth=-9.9,
+                kstrains=[], nkstrains=[], continuous=True, lineage_effects=False, lin=None)
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=NONE, pret=1, lrtt=1, **args)
+    _check_golden(s, goldens['fe_cont'], set(), False, False)
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=NONE, pret=0.05, lrtt=1, **args)
+    assert s.notes == {'pre-filtering-failed'} and abs(s.prep - goldens['fe_cont']['prep']) < 1e-9
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=NONE, pret=1, lrtt=1e-50, **args)
+    _check_golden(s, goldens['fe_cont'], {'lrt-filtering-failed'}, False, True)
+    s = pm.fixed_effects_regression(p=p, k=k, m=m, c=utd['cov'], pret=1, lrtt=1, **args)
+    _check_golden(s, goldens['fe_cont_cov'], set(), False, False)
+
+
+def _problem(n, dims, seed, binary):
+    rng = np.random.RandomState(seed)
+    m = rng.uniform(-1, 1, size=(n, dims)) if dims else NONE
+    if dims:
+        m = m / np.abs(m).max(0)                      # input.py:135-136
+    lin = (m[:, :min(dims, 3)].sum(1) if dims else 0) + rng.normal(size=n)
+    if binary:
+        y = (lin + 0.3 * rng.normal(size=n) > np.median(lin)).astype(float)
+    else:
+        y = lin
+    return m, y, rng
+
+
+def _variants(n, nv, y, rng, binary):
+    from pyseer_b200.engine import synth_host
+    ys = np.where(y > (0.5 if binary else np.median(y)), 1, -1).astype(np.int8)
+    bits = synth_host(20261017, 0, nv, n, af_lo=0.0, af_hi=1.0, planted_every=7, y_sign=ys)
+    from pyseer_b200.engine import unpack_rows, pack_rows
+    x = unpack_rows(bits, n).astype(float)
+    # edge rows: rare carriers (bad-chisq -> Firth), perfect / quasi-perfect separation
+    x[1] = 0; x[1, :4] = 1
+    hi = ys > 0
+    x[2] = hi.astype(float)                                       # x == y (binary): separable
+    x[3] = x[2]
+    flip = rng.choice(n, 3, replace=False)
+    x[3, flip] = 1 - x[3, flip]                                   # nearly separable
+    x[4] = 0; x[4, np.where(hi)[0][:8]] = 1                       # carriers are all cases
+    x[5] = 1; x[5, np.where(~hi)[0][:3]] = 0                      # non-carriers all controls
+    bits2, _ = pack_rows(x)
+    return bits2, x
+
+
+@pytest.mark.parametrize('n,dims,nv', [(100, 0, 120), (333, 3, 200), (1000, 10, 160), (257, 14, 60)])
+@pytest.mark.parametrize('binary', [True, False])
+def test_oracle_parity_fixed(n, dims, nv, binary):
+    from oracle import fixed_oracle as fo
+    from pyseer_b200 import model as pm, _lib
+    from pyseer_b200.engine import notes_from_flags
+    m, y, rng = _problem(n, dims, 7 + n, binary)
+    bits, x = _variants(n, nv, y, rng, binary)
+    continuous = not binary
+    mm = m if dims else NONE
+    onull = fo.fit_null(y, mm, NONE, continuous)
+    ofirth = fo.fit_null(y, mm, NONE, continuous, True) if binary else -9.9
+    assert onull is not None and ofirth is not None
+    gnull = pm.fit_null(y, mm, NONE, continuous)
+    assert _rel(gnull.llf, onull.llf) < 1e-9
+    if binary:
+        gf = pm.fit_null(y, mm, NONE, continuous, True)
+        assert _rel(gf, ofirth) < 1e-8
+    null_llf = onull.llf
+    min_af, max_af, pret, lrtt = 0.02, 0.98, 0.6, 0.5
+    model = pm.FixedModel(y, mm, NONE, continuous, null_llf, float(ofirth))
+    r = pm.run_fixed_bits(model, bits, None, pret, lrtt, min_af, max_af, 0.05)
+    af = x.sum(1) / float(n)
+    n_pref = n_tested = n_firth = 0
+    for s in range(nv):
+        ok = min_af <= af[s] <= max_af
+        o = fo.fixed_effects_regression('v', y if ok else None, x[s], mm, NONE, af[s], 'pat', False,
+                                        None, pret, lrtt, null_llf, ofirth, [], [], continuous)
+        f = int(r.flags[s])
+        assert notes_from_flags(f) == o.notes, (s, notes_from_flags(f), o.notes)
+        assert bool(f & _lib.F_PREFILTER) == o.prefilter and bool(f & _lib.F_FILTER) == o.filter, s
+        n_pref += o.prefilter
+        n_tested += not o.prefilter
+        n_firth += bool(f & _lib.F_FIRTH_USED)
+        assert r.af[s] == af[s]
+        if ok:
+            assert _rel(r.prep[s], o.prep) < RTOL, (s, r.prep[s], o.prep)
+        if o.prefilter or 'firth-fail' in o.notes:
+            continue
+        for fld, val in (('pvalue', r.pvalue[s]), ('kbeta', r.beta[s]), ('bse', r.bse[s]),
+                         ('intercept', r.extra[s])):
+            ref = getattr(o, fld)
+            if np.isfinite(ref) and abs(ref) > 1e-290:
+                # relative, with an absolute floor for coefficients that are zero up to rounding
+                assert abs(val - ref) <= RTOL * max(abs(ref), 1e-9), (s, fld, val, ref, o.notes)
+        if dims:
+            ob = np.asarray(o.betas, dtype=float)
+            big = np.abs(ob) > 1e-9
+            assert np.abs(r.betas[s][big] / ob[big] - 1).max() < 1e-5, (s, r.betas[s], ob)
+    assert r.counts['loaded'] == nv and r.counts['prefiltered'] == n_pref
+    assert r.counts['tested'] == n_tested
+    if binary:
+        assert n_firth >= 2, n_firth              # the Firth fallback is exercised
+    model.close()
+
+
+def test_missing_data_error():
+    """NaN genotypes reach the design matrix -> 'missing-data-error' (model.py:371-377)."""
+    from pyseer_b200 import model as pm, _lib
+    from pyseer_b200.engine import pack_rows, notes_from_flags
+    m, y, rng = _problem(150, 2, 3, True)
+    k = (rng.uniform(size=(6, 150)) < 0.4).astype(float)
+    k[2, 5] = np.nan
+    bits, miss = pack_rows(k)
+    model = pm.FixedModel(y, m, NONE, False, -50.0, -49.0)
+    r = pm.run_fixed_bits(model, bits, miss, 1, 1, 0.01, 0.99, 0.05)
+    assert notes_from_flags(int(r.flags[2])) == {'missing-data-error'}
+    assert r.flags[2] & _lib.F_FILTER and not (r.flags[2] & _lib.F_PREFILTER)
+    assert np.isfinite(r.pvalue[[0, 1, 3]]).all()
+    model.close()
