@@ -49,8 +49,11 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--samples', type=int, default=5000)
-    ap.add_argument('--kmers-per-gpu', type=int, default=6250000)
+    ap.add_argument('--model', default='lmm', choices=['lmm', 'fixed'],
+                    help="lmm: BASELINE configs[3] (headline); fixed: configs[2], logistic + Firth, "
+                         "N=2000, 10 MDS covariates, 10M k-mers")
+    ap.add_argument('--samples', type=int, default=0, help='0 = the config default')
+    ap.add_argument('--kmers-per-gpu', type=int, default=0, help='0 = the config default')
     ap.add_argument('--precision', type=int,
                     default=int(os.environ.get('PYSEER_B200_LMM_PRECISION', '5')),
                     help='0 = FP64 CUDA-core contraction, 3..8 = exact int8-slice tcgen05 path')
@@ -86,6 +89,58 @@ def spectral_state(X, y, K):
     res = m.findH2()
     S, U = m.getSU()
     return np.ascontiguousarray(U), np.ascontiguousarray(S), float(res['h2'])
+
+
+def make_fixed_problem(n, dims=10):
+    """configs[2]: binary phenotype with population structure carried by 10 MDS components
+    scaled as input.py:135-136."""
+    rng = np.random.RandomState(SEED % (2 ** 31) + 2)
+    m = rng.uniform(-1, 1, size=(n, dims))
+    m = m / np.abs(m).max(0)
+    lin = m[:, :3].sum(1) + rng.normal(size=n)
+    y = (lin > np.median(lin)).astype(float)
+    return m, y
+
+
+def _cpu_fixed_block(b):
+    from oracle import fixed_oracle as fo
+    from pyseer_b200.engine import unpack_rows
+    n = _CPU['n']
+    x = unpack_rows(_CPU['blocks'][b], n).astype(float)
+    af = x.sum(1) / float(n)
+    none = np.empty((0, 0))
+    tested = 0
+    for s in range(x.shape[0]):
+        ok = 0.01 <= af[s] <= 0.99
+        o = fo.fixed_effects_regression('k', _CPU['y'] if ok else None, x[s], _CPU['m'], none, af[s],
+                                        'p', False, None, 1.0, 1.0, _CPU['null_llf'],
+                                        _CPU['null_firth'], [], [], False)
+        tested += not o.prefilter
+    return tested
+
+
+class CpuFixedPath(object):
+    """Oracle port of model.fixed_effects_regression, one variant per task as pyseer's
+    starmap does (__main__.py:777-780), `cores` workers."""
+
+    def __init__(self, n, m, y, null_llf, null_firth, cores, ys, per_block=150):
+        import multiprocessing as mp
+        from pyseer_b200.engine import synth_host
+        self.cores = cores
+        self.per_block = per_block
+        _CPU.update(n=n, y=y, m=m, null_llf=null_llf, null_firth=null_firth)
+        _CPU['blocks'] = [synth_host(SEED, b * per_block, per_block, n, 0.02, 0.98, 1000, ys)
+                          for b in range(cores)]
+        self.pool = mp.get_context('fork').Pool(cores, initializer=_cpu_init)
+
+    def step(self):
+        t0 = time.perf_counter()
+        tested = sum(self.pool.map(_cpu_fixed_block, range(self.cores), chunksize=1))
+        return tested, time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 # ----------------------------------------------------------------------------------------
@@ -230,22 +285,179 @@ def peaks():
 
 
 # ----------------------------------------------------------------------------------------
+# workloads: what differs between the LMM headline config and the fixed-effects config
+# ----------------------------------------------------------------------------------------
+class LmmWorkload(object):
+    name = 'lmm'
+    default_n, default_kpg = 5000, 6250000
+    continuous = True
+
+    def __init__(self, a, n, kpg, world):
+        self.a, self.n, self.kpg = a, n, kpg
+        self.config = {
+            'workload': 'LMM continuous phenotype, N=%d samples, %d synthetic k-mers per GPU '
+                        '(BASELINE configs[3]: 50M k-mers x 5000 samples sharded by k-mer over 8 '
+                        'GPUs), similarity kinship, D=1' % (n, kpg),
+            'n_samples': n, 'kmers_per_gpu': kpg, 'kmers_total': kpg * world,
+            'af': 'U(0.02,0.98), 0.1% planted causal',
+            'filters': 'min_af 0.01 max_af 0.99 filter_pvalue 1 lrt_pvalue 1', 'block_size_cpu': BLOCK,
+            'cache': 'inputs (%.2f GB packed rows per GPU) larger than L2'
+                     % (kpg * ((n + 127) // 128 * 16) / 1e9)}
+
+    def build_state(self):
+        X, y, K = make_problem(self.n)
+        U, S, h2 = spectral_state(X, y, K)
+        return {'U': U, 'S': S, 'y': y, 'meta': np.array([h2])}
+
+    def state_shapes(self):
+        n = self.n
+        return {'U': (n, n - 1), 'S': (n - 1,), 'y': (n,), 'meta': (1,)}
+
+    def y_sign(self, st):
+        return np.where(st['y'] > np.median(st['y']), 1, -1).astype(np.int8)
+
+    def cpu_path(self, st, cores, ys):
+        return CpuPath(self.n, np.ones((self.n, 1)), st['y'], st['U'], st['S'], float(st['meta'][0]),
+                       cores, ys), \
+            ('blocks of %d k-mers (one block per worker, BLAS pinned to 1 thread as pyseer does), '
+             'oracle/lmm_oracle.fit_lmm' % BLOCK)
+
+    def setup_engine(self, eng, st):
+        eng.lmm_setup(np.ones((self.n, 1)), st['y'], st['U'], st['S'], float(st['meta'][0]),
+                      self.a.precision)
+
+    def run(self, eng):
+        eng.run_lmm(min_af=0.01, max_af=0.99, max_missing=0.05, filter_pvalue=1.0, lrt_pvalue=1.0,
+                    continuous=True)
+
+    def dtype(self):
+        k = self.a.precision
+        return ('s8 x%d slices -> s32 (tcgen05) -> f64' % k) if k else 'f64'
+
+    def check(self, st, bits_head, cols):
+        from oracle import lmm_oracle as lo
+        from pyseer_b200.engine import unpack_rows
+        olmm = lo.OracleLMM(np.ones((self.n, 1)), st['y'].reshape(-1, 1), None)
+        olmm.U, olmm.S = st['U'], st['S']
+        x = unpack_rows(bits_head, self.n)
+        ref = lo.fit_lmm_block(olmm, float(st['meta'][0]), np.ascontiguousarray(x.T, dtype=float))
+        pv, be = cols['pvalue'], cols['beta']
+        ok = np.isfinite(pv) & (ref['p_values'] > 1e-290)
+        return {'variants': int(ok.sum()),
+                'max_rel_err_pvalue': float(np.max(np.abs(pv[ok] / ref['p_values'][ok] - 1))),
+                'max_rel_err_beta': float(np.max(np.abs(be[ok] / ref['beta'][ok] - 1))),
+                'min_pvalue': float(np.min(pv[ok]))}
+
+    def roofline(self, tested, k_ms, run_ms, W, pk, pk_kind):
+        n, J, k = self.n, self.n - 1, self.a.precision
+        achieved = 2.0 * n * J * tested / (k_ms / 1e3) / 1e12     # 2 N (N-D) flop per tested k-mer
+        peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+        return {'bound': 'tensor', 'kernel': 'k_lmm_quadform_tc' if k else 'k_lmm_quadform_fp64',
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                'peak_source': ('%s bf16 dense sustained GEMM (MEASURED_PEAKS.json).  achieved = '
+                                'algorithmic fp64-equivalent flops 2 N (N-D) per tested k-mer; the '
+                                'kernel executes them as %d exact int8 slices on kind::i8 (nominal '
+                                '2x the bf16 rate), so frac ~ 2/%d is the ceiling'
+                                % (pk_kind, k, k)) if k else
+                               '%s bf16 dense sustained; FP64 CUDA-core kernel' % pk_kind,
+                'algorithmic_flops_per_kmer': 2.0 * n * J,
+                'executed_int8_tops': achieved * k if k else None,
+                'kernel_ms': k_ms, 'run_ms': run_ms, 'kernel_share_of_step': k_ms / run_ms,
+                'hbm_read_frac': (tested * (W * 4 + 56) / (k_ms / 1e3) / 1e9) / pk['hbm_gbs'],
+                'traffic': None}
+
+
+class FixedWorkload(object):
+    name = 'fixed'
+    default_n, default_kpg = 2000, 10000000
+    continuous = False
+    DIMS = 10
+
+    def __init__(self, a, n, kpg, world):
+        self.a, self.n, self.kpg = a, n, kpg
+        self.config = {
+            'workload': 'fixed-effects logistic + Firth, N=%d samples, %d MDS covariates, %d '
+                        'synthetic k-mers per GPU (BASELINE configs[2])' % (n, self.DIMS, kpg),
+            'n_samples': n, 'kmers_per_gpu': kpg, 'kmers_total': kpg * world,
+            'af': 'U(0.02,0.98), 0.1% planted causal',
+            'filters': 'min_af 0.01 max_af 0.99 filter_pvalue 1 lrt_pvalue 1',
+            'cache': 'inputs (%.2f GB packed rows per GPU) larger than L2'
+                     % (kpg * ((n + 127) // 128 * 16) / 1e9)}
+
+    def build_state(self):
+        from oracle import fixed_oracle as fo
+        m, y = make_fixed_problem(self.n, self.DIMS)
+        none = np.empty((0, 0))
+        null = fo.fit_null(y, m, none, False)
+        firth = fo.fit_null(y, m, none, False, True)
+        return {'m': m, 'y': y, 'meta': np.array([null.llf, firth])}
+
+    def state_shapes(self):
+        return {'m': (self.n, self.DIMS), 'y': (self.n,), 'meta': (2,)}
+
+    def y_sign(self, st):
+        return np.where(st['y'] > 0.5, 1, -1).astype(np.int8)
+
+    def cpu_path(self, st, cores, ys):
+        return CpuFixedPath(self.n, st['m'], st['y'], float(st['meta'][0]), float(st['meta'][1]),
+                            cores, ys), \
+            'blocks of 150 k-mers per worker, oracle/fixed_oracle.fixed_effects_regression per variant'
+
+    def setup_engine(self, eng, st):
+        Z = np.c_[np.ones(self.n), st['m']]
+        eng.fixed_setup(Z, st['y'], False, float(st['meta'][0]), float(st['meta'][1]))
+
+    def run(self, eng):
+        eng.run_fixed(min_af=0.01, max_af=0.99, max_missing=0.05, filter_pvalue=1.0, lrt_pvalue=1.0,
+                      continuous=False)
+
+    def dtype(self):
+        return 'f64'
+
+    def check(self, st, bits_head, cols):
+        from oracle import fixed_oracle as fo
+        from pyseer_b200.engine import unpack_rows
+        x = unpack_rows(bits_head[:300], self.n).astype(float)
+        none = np.empty((0, 0))
+        errp, errb, nf = 0.0, 0.0, 0
+        for s in range(x.shape[0]):
+            o = fo.fixed_effects_regression('k', st['y'], x[s], st['m'], none, 0.5, 'p', False, None,
+                                            1.0, 1.0, float(st['meta'][0]), float(st['meta'][1]),
+                                            [], [], False)
+            if o.prefilter or not np.isfinite(o.pvalue):
+                continue
+            errp = max(errp, abs(cols['pvalue'][s] / o.pvalue - 1))
+            errb = max(errb, abs(cols['beta'][s] / o.kbeta - 1))
+            nf += 'bad-chisq' in o.notes or 'high-bse' in o.notes
+        return {'variants': int(x.shape[0]), 'max_rel_err_pvalue': float(errp),
+                'max_rel_err_beta': float(errb), 'firth_fits': int(nf)}
+
+    def roofline(self, tested, k_ms, run_ms, W, pk, pk_kind):
+        n, p = self.n, self.DIMS + 2
+        per_eval = n * (p * (p + 1) / 2 + 2 * p + 30) * 2.0       # X'WX + score + eta, exp/div
+        flops = per_eval * 7.0 * tested                           # ~6 Newton steps + final Hessian
+        achieved = flops / (k_ms / 1e3) / 1e12
+        return {'bound': 'tensor', 'kernel': 'k_fixed_logit(+k_fixed_firth)', 'achieved': achieved,
+                'peak': 40.0, 'unit': 'TFLOP/s', 'frac': achieved / 40.0,
+                'peak_source': 'FP64 CUDA-core pipe, B200 nominal ~40 TFLOP/s (no measured fp64 peak '
+                               'in MEASURED_PEAKS.json); the kernel is FP64-pipe bound, not tensor '
+                               'or HBM: flops estimated at 7 evaluations x N (p(p+1)/2 + 2p + 30) FMA',
+                'kernel_ms': k_ms, 'run_ms': run_ms, 'kernel_share_of_step': k_ms / run_ms,
+                'hbm_read_frac': (tested * (W * 4 + 8 * (6 + p)) / (k_ms / 1e3) / 1e9) / pk['hbm_gbs'],
+                'traffic': None}
+
+
+# ----------------------------------------------------------------------------------------
 def main():
     a = parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    n = a.samples
-    kpg = a.kmers_per_gpu
-
-    config = {'workload': 'LMM continuous phenotype, N=%d samples, %d synthetic k-mers per GPU '
-                          '(BASELINE configs[3]: 50M k-mers x 5000 samples sharded by k-mer '
-                          'over 8 GPUs), similarity kinship, D=1' % (n, kpg),
-              'n_samples': n, 'kmers_per_gpu': kpg, 'kmers_total': kpg * world,
-              'af': 'U(0.02,0.98), 0.1% planted causal', 'filters': 'min_af 0.01 max_af 0.99 '
-              'filter_pvalue 1 lrt_pvalue 1', 'block_size_cpu': BLOCK,
-              'cache': 'inputs (%.2f GB packed rows per GPU) larger than L2'
-                       % (kpg * ((n + 127) // 128 * 16) / 1e9)}
+    wcls = LmmWorkload if a.model == 'lmm' else FixedWorkload
+    n = a.samples or wcls.default_n
+    kpg = a.kmers_per_gpu or wcls.default_kpg
+    wl = wcls(a, n, kpg, world)
+    config = wl.config
 
     if a.impl == 'reference' and rank != 0:
         return 0
@@ -260,35 +472,28 @@ def main():
 
     # ---- once-per-run state: rank 0 builds it, the other ranks receive it ---------------
     t_setup = time.time()
-    if rank == 0:
-        X, y, K = make_problem(n)
-        U, S, h2 = spectral_state(X, y, K)
-        del K
+    st = wl.build_state() if rank == 0 else None
     if dist is not None:
         dev = torch.device('cuda', local_rank)
-        meta = torch.zeros(1, dtype=torch.float64, device=dev)
-        if rank == 0:
-            meta[0] = h2
-            tU, tS, ty = (torch.from_numpy(v).to(dev) for v in (U, S, y))
-        else:
-            tU = torch.empty((n, n - 1), dtype=torch.float64, device=dev)
-            tS = torch.empty(n - 1, dtype=torch.float64, device=dev)
-            ty = torch.empty(n, dtype=torch.float64, device=dev)
-        for t in (meta, tU, tS, ty):
+        out = {}
+        for key, shape in wl.state_shapes().items():
+            if rank == 0:
+                t = torch.from_numpy(np.ascontiguousarray(st[key], dtype=np.float64)).to(dev)
+            else:
+                t = torch.empty(shape, dtype=torch.float64, device=dev)
             dist.broadcast(t, 0)
-        if rank != 0:
-            U, S, y, h2 = tU.cpu().numpy(), tS.cpu().numpy(), ty.cpu().numpy(), float(meta[0])
-            X = np.ones((n, 1))
-        del tU, tS, ty
+            out[key] = t.cpu().numpy()
+            del t
+        st = out
         torch.cuda.empty_cache()
-    ys = np.where(y > np.median(y), 1, -1).astype(np.int8)
+    ys = wl.y_sign(st)
     t_setup = time.time() - t_setup
 
     # ---- CPU path (before any CUDA context exists in this process: it forks) ------------
     cpu_line = None
     if rank == 0 and (a.impl == 'reference' or (world == 1 and not a.no_cpu_baseline)):
         cores = cpu_cores(a.cpu_cores)
-        cp = CpuPath(n, X, y, U, S, h2, cores, ys)
+        cp, what = wl.cpu_path(st, cores, ys)
         if a.impl == 'reference':
             W, Kst = max(a.warmup, 0), max(a.steps, 1)
         else:
@@ -304,9 +509,7 @@ def main():
         cp.close()
         rate = tested / secs
         cpu_line = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                    'sample': '%d steps x %d blocks of %d k-mers (one block per worker, BLAS '
-                              'pinned to 1 thread as pyseer does), oracle/lmm_oracle.fit_lmm'
-                              % (Kst, cores, BLOCK)}
+                    'sample': '%d steps x %d %s' % (Kst, cores, what)}
         if a.impl == 'reference':
             line = {'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': UNIT,
                     'n_gpus': a.gpus, 'steps': Kst, 'warmup': W,
@@ -320,13 +523,11 @@ def main():
             return 0
 
     # ---- GPU engine -------------------------------------------------------------------
-    from pyseer_b200.engine import Engine, PinnedBuffer, words_per_row, unpack_rows
+    from pyseer_b200.engine import Engine, PinnedBuffer, words_per_row
     eng = Engine(local_rank)
-    eng.lmm_setup(X, y, U, S, h2, a.precision)
+    wl.setup_engine(eng, st)
     eng.synth_device(SEED, rank * kpg, kpg, 0.02, 0.98, 1000, ys)
     W = words_per_row(n)
-    run_kw = dict(min_af=0.01, max_af=0.99, max_missing=0.05, filter_pvalue=1.0,
-                  lrt_pvalue=1.0, continuous=True)
 
     COLS = (('carriers', 4), ('missing', 4), ('af', 8), ('prep', 8), ('pvalue', 8), ('beta', 8),
             ('bse', 8), ('extra', 8), ('flags', 4))
@@ -346,7 +547,7 @@ def main():
             dist.barrier()
 
     def step():
-        eng.run_lmm(**run_kw)
+        wl.run(eng)
         if dist is not None:
             # the one collective of the path: gather the per-variant result table on rank 0
             eng.fetch_into(ptrs)
@@ -361,11 +562,9 @@ def main():
     if sampler:
         sampler.start()
     l0 = eng.launch_count()
-    kern_ms = []
     eng.event_record(0)
     for _ in range(a.steps):
         step()
-        kern_ms.append(None)
     eng.event_record(1)
     eng.sync()
     barrier()
@@ -374,8 +573,8 @@ def main():
     clocks = sampler.stop() if sampler else None
     counts = eng.counts()
     tested = counts['tested']
-    # dominant-kernel time, CUDA events on the library stream around the contraction launch
-    # of the last timed step (every step launches the same grid on the same rows)
+    # dominant-kernel time, CUDA events on the library stream around the dominant launch of
+    # the last timed step (every step launches the same grid on the same rows)
     k_ms = eng.last_ms(1)
     run_ms = eng.last_ms(0)
     if dist is not None:
@@ -392,6 +591,7 @@ def main():
 
     # ---- end to end through the C ABI with host buffers -----------------------------------
     e2e = None
+    check = None
     if not a.no_e2e:
         pin = PinnedBuffer((kpg, W), np.uint32)
         eng.download_bits(pin.array)
@@ -401,7 +601,7 @@ def main():
 
         def e2e_step():
             eng.submit(pin.array)
-            eng.run_lmm(**run_kw)
+            wl.run(eng)
             eng.fetch_into(optr)
 
         e2e_step()
@@ -421,49 +621,22 @@ def main():
         e2e = {'value': tested_all * a.steps / (ems / 1e3), 'unit': UNIT,
                'h2d_bytes_per_step': int(kpg * W * 4), 'd2h_bytes_per_step': int(kpg * row_bytes),
                'ms_per_step': ems / a.steps}
-        pvals_host = outs['pvalue'].array[:a.check].copy()
-        beta_host = outs['beta'].array[:a.check].copy()
-        bits_head = pin.array[:a.check].copy()
-
-    # ---- spot check of the timed output against the oracle (not timed) ----------------------
-    check = None
-    if rank == 0 and not a.no_e2e and a.check > 0:
-        from oracle import lmm_oracle as lo
-        olmm = lo.OracleLMM(X, y.reshape(-1, 1), None)
-        olmm.U, olmm.S = U, S
-        x = unpack_rows(bits_head, n)
-        ref = lo.fit_lmm_block(olmm, h2, np.ascontiguousarray(x.T, dtype=float))
-        ok = np.isfinite(pvals_host) & (ref['p_values'] > 1e-290)
-        check = {'variants': int(ok.sum()),
-                 'max_rel_err_pvalue': float(np.max(np.abs(pvals_host[ok] / ref['p_values'][ok] - 1))),
-                 'max_rel_err_beta': float(np.max(np.abs(beta_host[ok] / ref['beta'][ok] - 1))),
-                 'min_pvalue': float(np.min(pvals_host[ok]))}
+        # spot check of the timed output against the oracle (not timed)
+        if rank == 0 and a.check > 0:
+            cols = {name: outs[name].array[:a.check].copy() for name in ('pvalue', 'beta')}
+            check = wl.check(st, pin.array[:a.check].copy(), cols)
 
     if rank == 0:
         pk, pk_kind = peaks()
-        J = n - 1
-        flops_alg = 2.0 * n * J * tested            # per launch: 2 N (N-D) per tested k-mer
-        achieved = flops_alg / (k_ms / 1e3) / 1e12
-        peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
-        slices = a.precision
-        roof = {'bound': 'tensor', 'kernel': 'k_lmm_quadform_tc' if slices else 'k_lmm_quadform_fp64',
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'peak_source': '%s bf16 dense sustained (MEASURED_PEAKS.json); the kernel runs '
-                               'kind::i8 (nominal 2x bf16) on %d exact slices, so frac <= %.2f'
-                               % (pk_kind, slices, 2.0 / slices) if slices else
-                               '%s bf16 dense sustained; FP64 CUDA-core kernel' % pk_kind,
-                'algorithmic_flops_per_kmer': 2.0 * n * J,
-                'executed_int8_tops': achieved * slices if slices else None,
-                'kernel_ms': k_ms, 'run_ms': run_ms, 'kernel_share_of_step': k_ms / run_ms,
-                'hbm_read_frac': (tested * (W * 4 + 56) / (k_ms / 1e3) / 1e9) / pk['hbm_gbs'],
-                'traffic': None}
+        roof = wl.roofline(tested, k_ms, run_ms, W, pk, pk_kind)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps,
                 'warmup': a.warmup, 'ms_per_step': ms / a.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None,
-                'dtype': ('s8 x%d slices -> s32 (tcgen05) -> f64' % slices) if slices else 'f64',
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': wl.dtype(),
                 'data': 'synthetic', 'config': config, 'clocks': clocks, 'e2e': e2e,
                 'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu_line,
-                'counts': counts, 'h2': h2, 'check': check, 'setup_s': t_setup}
+                'counts': counts, 'check': check, 'setup_s': t_setup}
+        if a.model == 'lmm':
+            line['h2'] = float(st['meta'][0])
         print(json.dumps(line))
     eng.close()
     if dist is not None:
