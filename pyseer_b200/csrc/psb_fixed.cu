@@ -37,6 +37,8 @@ struct FxArgs {
     int q;                    // columns of Z
     int has_x;                // 0: null model (no variant column)
     double start0;            // log(mean(y) / (1 - mean(y)))
+    int use_warm;             // start Newton from the null-model parameters (exact fallback below)
+    double warm[FX_MAXP];     // null-model parameters (Z order)
     double null_llf, null_firth, lrt_pvalue;
     // outputs (indexed by variant id)
     double *pvalue, *beta, *bse, *intercept, *betas;
@@ -68,53 +70,59 @@ __device__ __forceinline__ double warp_max(double v) {
 // positive (matrix not PD) or not finite.
 // (all loops run over the full constant range with constant-foldable guards, so that the
 // unroller turns every index into a literal and the arrays stay in registers)
+//
+// Right-looking (outer-product) form: after column j is scaled, the trailing submatrix
+// update is (PP-j)^2/2 independent FMAs, so the dependency chain per column is just
+// sqrt -> reciprocal -> multiply -> FMA.  The diagonal is stored as 1 / L_jj.
 template <int PP>
 __device__ __forceinline__ bool fx_chol(double (&A)[Tri<PP>::SIZE]) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < PP; ++j) {
-        double d = A[Tri<PP>::at(j, j)];
-#pragma unroll
-        for (int k = 0; k < PP; ++k)
-            if (k < j) d = fma(-A[Tri<PP>::at(j, k)], A[Tri<PP>::at(j, k)], d);
+        const double d = A[Tri<PP>::at(j, j)];
         if (!(d > 0.0) || !isfinite(d)) ok = false;
-        const double l = sqrt(d);
-        A[Tri<PP>::at(j, j)] = l;
-        const double inv = 1.0 / l;
+        const double inv = rsqrt(d);
+        A[Tri<PP>::at(j, j)] = inv;
 #pragma unroll
-        for (int i = 0; i < PP; ++i) {
-            if (i > j) {
-                double s = A[Tri<PP>::at(i, j)];
+        for (int i = 0; i < PP; ++i)
+            if (i > j) A[Tri<PP>::at(i, j)] *= inv;
 #pragma unroll
-                for (int k = 0; k < PP; ++k)
-                    if (k < j) s = fma(-A[Tri<PP>::at(i, k)], A[Tri<PP>::at(j, k)], s);
-                A[Tri<PP>::at(i, j)] = s * inv;
-            }
-        }
+        for (int i = 0; i < PP; ++i)
+#pragma unroll
+            for (int k = 0; k < PP; ++k)
+                if (i > j && k > j && k <= i)
+                    A[Tri<PP>::at(i, k)] = fma(-A[Tri<PP>::at(i, j)], A[Tri<PP>::at(k, j)], A[Tri<PP>::at(i, k)]);
     }
     return ok;
 }
 
-// b := (L L')^-1 b
+// b := (L L')^-1 b   (column-oriented substitutions; diagonal of L holds reciprocals)
 template <int PP>
 __device__ __forceinline__ void fx_chol_solve(const double (&L)[Tri<PP>::SIZE], double (&b)[PP]) {
 #pragma unroll
     for (int i = 0; i < PP; ++i) {
-        double s = b[i];
+        b[i] *= L[Tri<PP>::at(i, i)];
 #pragma unroll
         for (int k = 0; k < PP; ++k)
-            if (k < i) s = fma(-L[Tri<PP>::at(i, k)], b[k], s);
-        b[i] = s / L[Tri<PP>::at(i, i)];
+            if (k > i) b[k] = fma(-L[Tri<PP>::at(k, i)], b[i], b[k]);
     }
 #pragma unroll
     for (int ii = 0; ii < PP; ++ii) {
         const int i = PP - 1 - ii;
-        double s = b[i];
+        b[i] *= L[Tri<PP>::at(i, i)];
 #pragma unroll
         for (int k = 0; k < PP; ++k)
-            if (k > i) s = fma(-L[Tri<PP>::at(k, i)], b[k], s);
-        b[i] = s / L[Tri<PP>::at(i, i)];
+            if (k < i) b[k] = fma(-L[Tri<PP>::at(i, k)], b[i], b[k]);
     }
+}
+
+// log det of the factored matrix: -2 sum log(1 / L_jj)
+template <int PP>
+__device__ __forceinline__ double fx_chol_logdet(const double (&L)[Tri<PP>::SIZE]) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < PP; ++c) s += log(L[Tri<PP>::at(c, c)]);
+    return -2.0 * s;
 }
 
 // Straightforward, register-friendly inverse: solve for each unit vector (PP solves).  Used by
@@ -149,10 +157,11 @@ __device__ __forceinline__ void fx_row(const FxArgs &a, int i, uint32_t xbit, do
 
 // One pass over the samples at parameters beta: X'WX (packed), score X'(y - pi),
 // max |y - pi| and the log-likelihood.  All lanes return the full sums.
-template <int PP, bool WITH_LLF>
+template <int PP>
 __device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, int lane,
                                         const double (&beta)[PP], double (&H)[Tri<PP>::SIZE],
-                                        double (&g)[PP], double &maxdev, double &llf) {
+                                        double (&g)[PP], double &maxdev, double &llf,
+                                        const bool WITH_LLF) {
 #pragma unroll
     for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] = 0.0;
 #pragma unroll
@@ -274,37 +283,53 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
         }
         const uint32_t *xrow = a.bits + (size_t)v * a.Wrow;
         double beta[PP];
-#pragma unroll
-        for (int c = 0; c < PP; ++c) beta[c] = 0.0;
-        beta[0] = a.start0;
         double H[Tri<PP>::SIZE], g[PP];
-        double maxdev, llf_unused, maxstep = INFINITY;
+        double maxdev, llf = NAN, maxstep = INFINITY;
         uint32_t fail = 0;
         int it = 0;
-        const double n = (double)a.N;
-        for (;;) {
-            fx_eval<PP, false>(a, xrow, lane, beta, H, g, maxdev, llf_unused);
-            if (it > 0 && maxdev <= 1e-8) { fail = PSB_F_PERFECT_SEP; break; }   // _check_perfect_pred
-            if (it > 0 && !(maxstep > 1e-8)) break;                              // converged
-            if (it >= 35) break;                                                 // maxiter
-            // H/n + 1e-10 I, solve for the step
+        bool have_llf = false;
+        const double inv_n = 1.0 / (double)a.N;
+        // The log-likelihood is concave, so a converged Newton run ends at the same (unique)
+        // maximiser whatever the start.  Attempt 0 starts from the null-model parameters and
+        // saves about half of the iterations; unless it converges cleanly within 12 steps the
+        // fit is redone from the reference's start vector with the reference's 35-step rule
+        // (attempt 1), so separation / non-convergence are flagged exactly as statsmodels does.
+        for (int attempt = (a.use_warm && a.has_x) ? 0 : 1; attempt < 2; ++attempt) {
 #pragma unroll
-            for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] /= n;
+            for (int c = 0; c < PP; ++c) beta[c] = (attempt == 0 && c < a.q) ? a.warm[c] : 0.0;
+            if (attempt == 1) beta[0] = a.start0;
+            const int maxit = attempt == 0 ? 12 : 35;
+            fail = 0;
+            it = 0;
+            maxstep = INFINITY;
+            bool converged = false;
+            for (;;) {
+                const bool want_llf = maxstep <= 1e-3;       // very likely the last evaluation
+                fx_eval<PP>(a, xrow, lane, beta, H, g, maxdev, llf, want_llf);
+                have_llf = want_llf;
+                if (it > 0 && maxdev <= 1e-8) { fail = PSB_F_PERFECT_SEP; break; }   // _check_perfect_pred
+                if (it > 0 && !(maxstep > 1e-8)) { converged = true; break; }        // converged
+                if (it >= maxit) break;                                              // maxiter
+                // H/n + 1e-10 I, solve for the step
 #pragma unroll
-            for (int c = 0; c < PP; ++c) {
-                if (c < p) H[Tri<PP>::at(c, c)] += 1e-10;
-                g[c] /= n;
+                for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] *= inv_n;
+#pragma unroll
+                for (int c = 0; c < PP; ++c) {
+                    if (c < p) H[Tri<PP>::at(c, c)] += 1e-10;
+                    g[c] *= inv_n;
+                }
+                if (!fx_chol<PP>(H)) { fail = PSB_F_MATRIX_INV; break; }
+                fx_chol_solve<PP>(H, g);
+                maxstep = 0.0;
+#pragma unroll
+                for (int c = 0; c < PP; ++c) {
+                    beta[c] += g[c];
+                    maxstep = fmax(maxstep, fabs(g[c]));
+                }
+                if (isnan(maxstep)) { fail = PSB_F_MATRIX_INV; break; }
+                ++it;
             }
-            if (!fx_chol<PP>(H)) { fail = PSB_F_MATRIX_INV; break; }
-            fx_chol_solve<PP>(H, g);
-            maxstep = 0.0;
-#pragma unroll
-            for (int c = 0; c < PP; ++c) {
-                beta[c] += g[c];
-                maxstep = fmax(maxstep, fabs(g[c]));
-            }
-            if (isnan(maxstep)) { fail = PSB_F_MATRIX_INV; break; }
-            ++it;
+            if (attempt == 0 && converged && !fail) break;     // accept the warm-started fit
         }
         double bse_x = NAN;
         double bse_all[PP];
@@ -333,7 +358,8 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
         }
         if (!a.has_x) {
             // null fit: params, bse, llf, status
-            double llf = fail ? NAN : fx_loglike<PP>(a, xrow, lane, beta);
+            if (fail) llf = NAN;
+            else if (!have_llf) llf = fx_loglike<PP>(a, xrow, lane, beta);
             if (lane == 0) {
 #pragma unroll
                 for (int c = 0; c < PP; ++c)
@@ -355,7 +381,7 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
             }
             continue;
         }
-        const double llf = fx_loglike<PP>(a, xrow, lane, beta);
+        if (!have_llf) llf = fx_loglike<PP>(a, xrow, lane, beta);
         if (lane == 0) fx_publish<PP>(a, v, f, beta, bse_x, llf, a.null_llf);
     }
 }
@@ -381,7 +407,7 @@ k_fixed_firth(FxArgs a, int n_list) {
         double maxdev, llf_cur;
         bool ok = true, converged = false;
         // state at the current iterate: H = X'WX, llf, FL = -(llf + 0.5 log det H)
-        fx_eval<PP, true>(a, xrow, lane, beta, H, g, maxdev, llf_cur);
+        fx_eval<PP>(a, xrow, lane, beta, H, g, maxdev, llf_cur, true);
         double hxx_cur = 0.0;
 #pragma unroll
         for (int c = 0; c < PP; ++c)
@@ -390,10 +416,7 @@ k_fixed_firth(FxArgs a, int n_list) {
         double last_step_norm = INFINITY;      // || betas[i] - betas[i-1] ||
         for (int i = 0; i < 1000 && ok; ++i) {
             if (!fx_chol<PP>(H)) { ok = false; break; }
-            double logdet = 0.0;
-#pragma unroll
-            for (int c = 0; c < PP; ++c) logdet += log(H[Tri<PP>::at(c, c)]);
-            logdet *= 2.0;
+            const double logdet = fx_chol_logdet<PP>(H);
             fl_cur = -(llf_cur + 0.5 * logdet);
             fx_inverse_from_chol<PP>(H, V);            // V = pinv(-hessian), model.py:450
             // U = X'(y - pi + h (1/2 - pi)),  h_i = w_i x_i' V x_i   (model.py:455-466)
@@ -444,7 +467,7 @@ k_fixed_firth(FxArgs a, int n_list) {
             double llf_new, fl_new, hxx_new = 0.0;
             int j = 0;
             for (;;) {
-                fx_eval<PP, true>(a, xrow, lane, cand, H, g, maxdev, llf_new);
+                fx_eval<PP>(a, xrow, lane, cand, H, g, maxdev, llf_new, true);
 #pragma unroll
                 for (int c = 0; c < PP; ++c)
                     if (c == a.q) hxx_new = H[Tri<PP>::at(c, c)];
@@ -452,12 +475,7 @@ k_fixed_firth(FxArgs a, int n_list) {
 #pragma unroll
                 for (int e = 0; e < Tri<PP>::SIZE; ++e) V[e] = H[e];
                 double ld = NAN;
-                if (fx_chol<PP>(V)) {
-                    ld = 0.0;
-#pragma unroll
-                    for (int c = 0; c < PP; ++c) ld += log(V[Tri<PP>::at(c, c)]);
-                    ld *= 2.0;
-                }
+                if (fx_chol<PP>(V)) ld = fx_chol_logdet<PP>(V);
                 fl_new = -(llf_new + 0.5 * ld);
                 if (!(fl_new > fl_cur)) break;
 #pragma unroll
@@ -592,6 +610,8 @@ int psb_upload_pheno(psb_ctx *c, const double *y);
 void psb_fill_welch_cols(const double *y, int N, int Npad, double *cols, int col_w0, uint64_t *mask_lo,
                          uint64_t *mask_hi);
 
+static int fx_run_null(psb_ctx *c, int mode, std::vector<double> &h);
+
 static bool host_chol_inverse(std::vector<double> &A, int q) {
     // A (q x q, symmetric PD, row-major) -> A^-1 by Cholesky
     std::vector<double> L(A);
@@ -698,6 +718,14 @@ extern "C" int psb_fixed_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z
                             cudaMemcpyHostToDevice));
     }
     c->model = PSB_MODEL_FIXED;
+    c->h_warm.clear();
+    if (!continuous) {
+        // null-model parameters: warm start for every variant's Newton run
+        std::vector<double> h;
+        rc = fx_run_null(c, 0, h);
+        if (rc) return rc;
+        if (h[2 * q + 1] == 0.0) c->h_warm.assign(h.begin(), h.begin() + q);
+    }
     return PSB_OK;
 }
 
@@ -714,6 +742,8 @@ static FxArgs fx_args(psb_ctx *c, const psb_params *prm, int has_x) {
     a.q = c->q;
     a.has_x = has_x;
     a.start0 = log(c->y_mean / (1.0 - c->y_mean));
+    a.use_warm = (has_x && (int)c->h_warm.size() == c->q) ? 1 : 0;
+    for (int k = 0; k < FX_MAXP; ++k) a.warm[k] = (a.use_warm && k < c->q) ? c->h_warm[k] : 0.0;
     a.null_llf = c->null_llf;
     a.null_firth = c->null_firth;
     a.lrt_pvalue = prm ? prm->lrt_pvalue : 1.0;
@@ -749,6 +779,36 @@ static int fx_dispatch(psb_ctx *c, const FxArgs &a, int n, bool firth) {
     else firth ? launch_firth<16>(c, a, n, grid) : launch_logit<16>(c, a, n, grid);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
+    return PSB_OK;
+}
+
+// Null-model fit (no variant column) with the device solver on the context's current design.
+// mode bit 0: Firth; bit 1: start from zeros.  h = params[q], bse[q], llf, status, iterations.
+static int fx_run_null(psb_ctx *c, int mode, std::vector<double> &h) {
+    const int q = c->q;
+    int rc = psb_ensure_capacity(c, 1, q > 1 ? q - 1 : 1);
+    if (rc) return rc;
+    double *d_out = nullptr;
+    PSB_CUDA(cudaMalloc(&d_out, (2 * q + 3) * sizeof(double)));
+    const uint32_t *save_bits = c->d_bits;
+    const int save_wrow = c->Wrow;
+    c->d_bits = nullptr;
+    c->Wrow = 0;
+    FxArgs a = fx_args(c, nullptr, 0);
+    c->d_bits = save_bits;
+    c->Wrow = save_wrow;
+    a.null_out = d_out;
+    if (mode & 2) a.start0 = 0.0;      // statsmodels default start (model.py:188)
+    rc = fx_dispatch(c, a, 1, (mode & 1) != 0);
+    if (rc) {
+        cudaFree(d_out);
+        return rc;
+    }
+    h.assign(2 * q + 3, 0.0);
+    PSB_CUDA(cudaMemcpyAsync(h.data(), d_out, (2 * q + 3) * sizeof(double), cudaMemcpyDeviceToHost,
+                             c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_out);
     return PSB_OK;
 }
 
@@ -853,25 +913,9 @@ extern "C" int psb_fit_null(psb_ctx *c, int32_t N, int32_t q, const double *Z, c
     c->y_mean = mean / N;
     c->continuous = 0;
     c->model = PSB_MODEL_FIXED;
-    rc = psb_ensure_capacity(c, 1, q > 1 ? q - 1 : 1);
+    std::vector<double> h;
+    rc = fx_run_null(c, firth, h);
     if (rc) return rc;
-    double *d_out = nullptr;
-    PSB_CUDA(cudaMalloc(&d_out, (2 * q + 3) * sizeof(double)));
-    c->d_bits = nullptr;
-    c->Wrow = 0;
-    FxArgs a = fx_args(c, nullptr, 0);
-    a.null_out = d_out;
-    if (firth & 2) a.start0 = 0.0;      // statsmodels default start (model.py:188)
-    rc = fx_dispatch(c, a, 1, (firth & 1) != 0);
-    if (rc) {
-        cudaFree(d_out);
-        return rc;
-    }
-    std::vector<double> h(2 * q + 3, 0.0);
-    PSB_CUDA(cudaMemcpyAsync(h.data(), d_out, (2 * q + 2) * sizeof(double), cudaMemcpyDeviceToHost,
-                             c->stream));
-    PSB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_out);
     for (int a2 = 0; a2 < q; ++a2) {
         out_params[a2] = h[a2];
         out_bse[a2] = h[q + a2];

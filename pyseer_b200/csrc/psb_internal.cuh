@@ -87,6 +87,7 @@ struct psb_ctx {
     double *d_fixed_const = nullptr;  // OLS precomputed: see psb_fixed.cu
     std::vector<double> h_ZtZinv; // q x q
     std::vector<double> h_Zty;    // q
+    std::vector<double> h_warm;   // null-model Logit parameters (warm start), q
 
     // ---- variants ----
     const uint32_t *d_bits = nullptr, *d_miss = nullptr;
