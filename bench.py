@@ -529,18 +529,12 @@ def main():
     eng.synth_device(SEED, rank * kpg, kpg, 0.02, 0.98, 1000, ys)
     W = words_per_row(n)
 
-    COLS = (('carriers', 4), ('missing', 4), ('af', 8), ('prep', 8), ('pvalue', 8), ('beta', 8),
-            ('bse', 8), ('extra', 8), ('flags', 4))
-    row_bytes = sum(b for _, b in COLS)
-    gather_buf = None
+    from pyseer_b200 import sharding
+    COLS = tuple((name, b) for name, b, _ in sharding.TABLE_COLUMNS)
+    row_bytes = sharding.ROW_BYTES
     if dist is not None:
         table = torch.empty(kpg * row_bytes, dtype=torch.uint8, device=dev)
-        ptrs, off = {}, 0
-        for name, b in COLS:
-            ptrs[name] = table.data_ptr() + off
-            off += kpg * b
-        if rank == 0:
-            gather_buf = [torch.empty_like(table) for _ in range(world)]
+        ptrs = sharding.table_pointers(table.data_ptr(), kpg)
 
     def barrier():
         if dist is not None:
@@ -551,7 +545,7 @@ def main():
         if dist is not None:
             # the one collective of the path: gather the per-variant result table on rank 0
             eng.fetch_into(ptrs)
-            dist.gather(table, gather_buf, dst=0)
+            sharding.gather_tables(table, [kpg] * world, dst=0)
             torch.cuda.synchronize()
 
     for _ in range(max(a.warmup, 0)):
