@@ -1,0 +1,260 @@
+"""``python -m pyseer_b200`` -- pyseer's association CLI (pyseer/__main__.py) with the per-variant
+loop running on the GPU.
+
+Same options, same TSV on stdout, same counters on stderr for the fixed-effects (SEER) and
+``--lmm`` models with ``--kmers`` / ``--pres`` input.  What the reference does with a
+``multiprocessing.Pool`` over variants (``__main__.py:517-593, 762-827``) is done here by
+submitting blocks of packed variants to the engine; ``--cpu`` is accepted and ignored.
+Whole-genome models (``--wg``), VCF / burden input and lineage effects are not part of this
+path and are rejected with a message.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+
+from . import __version__
+from . import _lib
+from . import classes as var_obj
+from .engine import notes_from_flags
+from .input import (VariantReader, hash_pattern, load_covariates, load_phenotypes,
+                    load_structure)
+from .utils import format_output
+
+
+def get_options(argv=None):
+    ap = argparse.ArgumentParser(prog='pyseer_b200',
+                                 description='SEER / LMM association tests on B200 (pyseer CLI)')
+    ph = ap.add_argument_group('Phenotype')
+    ph.add_argument('--phenotypes', required=True)
+    ph.add_argument('--phenotype-column', default=None)
+    va = ap.add_argument_group('Variants')
+    g = va.add_mutually_exclusive_group(required=True)
+    g.add_argument('--kmers', default=None)
+    g.add_argument('--vcf', default=None)
+    g.add_argument('--pres', default=None)
+    va.add_argument('--burden')
+    di = ap.add_argument_group('Distances')
+    d = di.add_mutually_exclusive_group()
+    d.add_argument('--distances')
+    d.add_argument('--load-m')
+    di.add_argument('--similarity')
+    di.add_argument('--load-lmm')
+    di.add_argument('--save-m')
+    di.add_argument('--save-lmm')
+    di.add_argument('--mds', default='classic')
+    di.add_argument('--max-dimensions', type=int, default=10)
+    di.add_argument('--no-distances', action='store_true', default=False)
+    mo = ap.add_argument_group('Association options')
+    mo.add_argument('--continuous', action='store_true', default=False)
+    mo.add_argument('--lmm', action='store_true', default=False)
+    mo.add_argument('--wg', default=None)
+    mo.add_argument('--lineage', action='store_true', default=False)
+    mo.add_argument('--lineage-clusters', default=None)
+    mo.add_argument('--lineage-file', default='lineage_effects.txt')
+    fi = ap.add_argument_group('Filtering options')
+    fi.add_argument('--min-af', type=float, default=0.01)
+    fi.add_argument('--max-af', type=float, default=0.99)
+    fi.add_argument('--max-missing', type=float, default=0.05)
+    fi.add_argument('--filter-pvalue', type=float, default=1)
+    fi.add_argument('--lrt-pvalue', type=float, default=1)
+    co = ap.add_argument_group('Covariates')
+    co.add_argument('--covariates', default=None)
+    co.add_argument('--use-covariates', default=None, nargs='*')
+    ot = ap.add_argument_group('Other')
+    ot.add_argument('--print-samples', action='store_true', default=False)
+    ot.add_argument('--print-filtered', action='store_true', default=False)
+    ot.add_argument('--output-patterns', default=False)
+    ot.add_argument('--uncompressed', action='store_true', default=False)
+    ot.add_argument('--cpu', type=int, default=1, help='accepted for compatibility; unused')
+    ot.add_argument('--block_size', type=int, default=3000)
+    ot.add_argument('--gpu', type=int, default=0, help='CUDA device index')
+    ot.add_argument('--gpu-batch', type=int, default=48000,
+                    help='variants per GPU submission (rounded to a multiple of --block_size)')
+    ot.add_argument('--lmm-precision', type=int, default=None,
+                    help='0 = FP64 contraction, 3..7 = exact int8-slice tensor-core contraction '
+                         '(default 5)')
+    ot.add_argument('--version', action='version', version='%(prog)s ' + __version__)
+    return ap.parse_args(argv)
+
+
+def _die(msg):
+    sys.stderr.write(msg + '\n')
+    sys.exit(1)
+
+
+def main(argv=None):
+    o = get_options(argv)
+    # option checks of __main__.py:257-306 that concern the supported models
+    if o.wg:
+        _die('Whole-genome models (--wg) are not part of the GPU path; use pyseer for them')
+    if o.vcf or o.burden:
+        _die('VCF / burden input needs pysam, which this build does not use; convert to --pres')
+    if o.lineage or o.lineage_clusters:
+        _die('Lineage effects are not wired into this CLI yet')
+    if o.max_dimensions < 1:
+        _die('Minimum number of dimensions after MDS is 1')
+    if o.lmm and not o.similarity and not o.load_lmm:
+        _die('Must provide a similarity matrix or lmm cache for random effects')
+    if not o.no_distances:
+        if (o.lmm and (o.distances or o.load_m)) or (not o.lmm and (o.similarity or o.load_lmm)):
+            _die('Must use distance matrix with fixed effects, or similarity matrix with random effects')
+        if not o.lmm and not o.distances and not o.load_m:
+            _die('Option --no-distances must be used when no distance matrix is provided')
+    else:
+        if o.distances or o.load_m:
+            _die('Cannot use --no-distances with --distances or --load-m')
+        if o.lmm:
+            _die('Cannot use --no-distances with --lmm')
+    if o.block_size < 1:
+        _die('Block size must be at least 1')
+
+    p = load_phenotypes(o.phenotypes, o.phenotype_column)
+    sys.stderr.write('Read ' + str(len(p)) + ' phenotypes\n')
+    if not o.continuous:
+        if p.values[(p.values != 0) & (p.values != 1)].size > 0:
+            o.continuous = True
+            sys.stderr.write('Detected continuous phenotype\n')
+        else:
+            sys.stderr.write('Detected binary phenotype\n')
+
+    if o.covariates is not None:
+        cov = load_covariates(o.covariates, o.use_covariates, p)
+        if cov is None:
+            sys.exit(1)
+    else:
+        cov = pd.DataFrame([])
+
+    model = None
+    lmm = None
+    if not o.lmm:
+        from . import model as fx
+        if not o.no_distances:
+            if o.load_m and os.path.isfile(o.load_m):
+                m = pd.read_pickle(o.load_m)
+                sys.stderr.write('Loaded projection with dimension ' + str(m.shape) + '\n')
+            else:
+                seed = os.environ.get('PYSEERSEED', None)
+                m = load_structure(o.distances, p, o.max_dimensions, o.mds, o.cpu,
+                                   int(seed) if seed is not None else None)
+                if o.save_m:
+                    m.to_pickle(o.save_m + '.pkl')
+            if o.max_dimensions > m.shape[1]:
+                sys.stderr.write('Population MDS scaling restricted to %d dimensions instead of '
+                                 'requested %d\n' % (m.shape[1], o.max_dimensions))
+                o.max_dimensions = m.shape[1]
+            common = p.index.intersection(m.index)
+            sys.stderr.write('Analysing ' + str(len(common)) + ' samples found in both phenotype '
+                             'and structure matrix\n')
+            p = p.loc[common]
+            m = m.loc[p.index].values[:, :o.max_dimensions]
+        else:
+            m = np.empty(shape=(0, 0))
+        if cov.shape[1] > 0:
+            cov = cov.loc[p.index]
+        null_fit = fx.fit_null(p.values, m, cov, o.continuous, device=o.gpu)
+        firth_null = fx.fit_null(p.values, m, cov, o.continuous, True, device=o.gpu) \
+            if not o.continuous else True
+        if null_fit is None or firth_null is None:
+            _die('Could not fit null model, exiting')
+        model = fx.FixedModel(p.values, m, cov, o.continuous, null_fit.llf,
+                              firth_null if not o.continuous else 0.0, device=o.gpu)
+    else:
+        from . import lmm as lm
+        sys.stderr.write('Setting up LMM\n')
+        p, lmm, h2 = lm.initialise_lmm(p, cov, o.similarity, o.load_lmm, o.save_lmm, None,
+                                       device=o.gpu, precision=o.lmm_precision)
+        sys.stderr.write('h^2 = ' + '{0:.2f}'.format(h2) + '\n')
+
+    var_type = 'kmers' if o.kmers else 'Rtab'
+    reader = VariantReader(var_type, o.kmers or o.pres, p, o.uncompressed)
+
+    header = ['variant', 'af', 'filter-pvalue', 'lrt-pvalue', 'beta', 'beta-std-err']
+    if not o.lmm:
+        header.append('intercept')
+        if not o.no_distances:
+            header += ['PC%d' % i for i in range(1, o.max_dimensions + 1)]
+        if o.covariates is not None:
+            header += [x for x in cov.columns]
+    else:
+        header.append('variant_h2')
+    if o.print_samples:
+        header += ['k-samples', 'nk-samples']
+    header.append('notes')
+    print('\t'.join(header))
+
+    patterns = open(o.output_patterns, 'wb') if o.output_patterns else None
+    prefilter = tested = printed = 0
+    out = sys.stdout
+    nan = np.nan
+    model_name = 'lmm' if o.lmm else 'seer'
+    gpu_batch = max(1, o.gpu_batch // o.block_size) * o.block_size
+
+    def samples_of(batch, j):
+        return reader.sample_lists(batch, j) if o.print_samples else ([], [])
+
+    for batch in reader.batches(gpu_batch):
+        if o.lmm:
+            r = lm.run_lmm_bits(lmm, h2, batch.bits, batch.missing, o.continuous, o.filter_pvalue,
+                                o.lrt_pvalue, o.min_af, o.max_af, o.max_missing)
+        else:
+            r = fx.run_fixed_bits(model, batch.bits, batch.missing, o.filter_pvalue, o.lrt_pvalue,
+                                  o.min_af, o.max_af, o.max_missing)
+        flags = r.flags
+        # the reference emits each block of --block_size variants as: filtered ones first
+        # (LMM only, lmm.py:158-226), then the tested ones; fixed effects keep input order
+        for b0 in range(0, batch.n, o.block_size):
+            idx = range(b0, min(b0 + o.block_size, batch.n))
+            if o.lmm:
+                order = [j for j in idx if flags[j] & _lib.F_PREFILTER] + \
+                        [j for j in idx if not (flags[j] & _lib.F_PREFILTER)]
+            else:
+                order = idx
+            for j in order:
+                f = int(flags[j])
+                if f & _lib.F_PREFILTER:
+                    prefilter += 1
+                    if not o.print_filtered:
+                        continue
+                else:
+                    tested += 1
+                    if patterns is not None:
+                        patterns.write(hash_pattern(reader.k_vector(batch, j)))
+                    if (f & _lib.F_FILTER) and not o.print_filtered:
+                        continue
+                ks, nks = samples_of(batch, j)
+                notes = notes_from_flags(f)
+                if o.lmm:
+                    if f & _lib.F_PREFILTER:
+                        item = var_obj.LMM(batch.names[j], None, r.af[j], r.prep[j], nan, nan, nan, nan,
+                                           None, ks, nks, notes, True, False)
+                    elif f & _lib.F_FILTER:
+                        item = var_obj.LMM(batch.names[j], None, r.af[j], r.prep[j], r.pvalue[j], nan,
+                                           nan, nan, None, ks, nks, notes, False, True)
+                    else:
+                        item = var_obj.LMM(batch.names[j], None, r.af[j], r.prep[j], r.pvalue[j],
+                                           r.beta[j], r.bse[j], r.extra[j], None, ks, nks, notes,
+                                           False, False)
+                else:
+                    item = fx.seer_from_row(r, j, batch.names[j], None, r.af[j], ks, nks)
+                printed += 1
+                out.write(format_output(item, None, model_name, o.print_samples) + '\n')
+    reader.close()
+    if patterns is not None:
+        patterns.close()
+    if model is not None:
+        model.close()
+    if lmm is not None:
+        lmm.close()
+
+    sys.stderr.write('%d loaded variants\n' % (prefilter + tested))
+    sys.stderr.write('%d pre-filtered variants\n' % prefilter)
+    sys.stderr.write('%d tested variants\n' % tested)
+    sys.stderr.write('%d printed variants\n' % printed)
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,226 @@
+"""Host-side loaders and the variant reader of the CLI.
+
+Behaviour follows pyseer/input.py (phenotypes :24-59, structure :62-137, covariates :195-247,
+k-mer / Rtab lines :301-454) but the variant stream is produced as *batches of packed bit rows*
+(what ``psb_submit`` takes) instead of one NumPy vector per variant: sample names are mapped to
+bit positions once, and per-variant sample lists are only materialised when asked for
+(``--print-samples``).
+"""
+import binascii
+import gzip
+import hashlib
+import sys
+
+import numpy as np
+import pandas as pd
+
+from .cmdscale import cmdscale
+from .engine import words_per_row
+
+
+def load_phenotypes(infile, column):
+    """input.py:24-59: phenotype Series indexed by sample name (last column by default)."""
+    p = pd.read_csv(infile, index_col=0, sep='\t')
+    if p.shape[1] < 1:
+        sys.stderr.write('Phenotype file must contain at least one phenotype column\n')
+        sys.exit(1)
+    p.index = p.index.astype(str)
+    if np.any(p.index.duplicated()):
+        sys.stderr.write('Phenotype file contains duplicated sample names\n')
+        sys.exit(1)
+    p = p[p.columns[-1]] if column is None else p[column]
+    p = p.dropna()
+    if not pd.api.types.is_numeric_dtype(p.values.dtype):
+        sys.stderr.write('Phenotypes must be numeric\n')
+        sys.exit(1)
+    return p
+
+
+def load_structure(infile, p, max_dimensions, mds_type='classic', n_cpus=1, seed=None):
+    """input.py:62-137: distance matrix -> MDS projection restricted to phenotyped samples,
+    every component scaled to max |value| 1."""
+    m = pd.read_csv(infile, index_col=0, sep='\t')
+    m.index = m.index.astype(str)
+    if np.any(m.index.duplicated()):
+        sys.stderr.write('Structure file contains duplicated sample names\n')
+        sys.exit(1)
+    sys.stderr.write('Structure matrix has dimension ' + str(m.shape) + '\n')
+    common = p.index.intersection(m.index).intersection(m.columns)
+    m = m.loc[common, common]
+    if len(common) == 0:
+        sys.stderr.write('None of the phenotyped samples were found in population structure matrix\n')
+        sys.exit(1)
+    if mds_type == 'classic':
+        projection, _ = cmdscale(m.values)
+    else:
+        from sklearn import manifold
+        metric = mds_type != 'non-metric'
+        if mds_type not in ('metric', 'non-metric'):
+            sys.stderr.write('Unsupported mds type chosen. Assuming metric\n')
+        try:
+            mds = manifold.MDS(n_components=max_dimensions, metric_mds=metric, metric='precomputed',
+                               n_jobs=n_cpus, normalized_stress='auto', random_state=seed, n_init=1)
+        except TypeError:
+            mds = manifold.MDS(n_components=max_dimensions, metric=metric, n_jobs=n_cpus,
+                               random_state=seed, dissimilarity='precomputed')
+        projection = mds.fit_transform(m.values)
+    m = pd.DataFrame(projection, index=m.index)
+    for i in range(m.shape[1]):
+        m[i] = m[i] / max(abs(m[i]))
+    return m
+
+
+def load_covariates(infile, covariates, p):
+    """input.py:195-247: quantitative columns as they are ('Nq'), categorical ones
+    dummy-encoded with one level dropped."""
+    c = pd.read_csv(infile, index_col=0, header=0, sep='\t')
+    c.index = c.index.astype(str)
+    if np.any(c.index.duplicated()):
+        sys.stderr.write('Covariate file contains duplicated sample names\n')
+        sys.exit(1)
+    if len(p.index.difference(c.index)) > 0:
+        sys.stderr.write('All samples with a phenotype must be present in covariate file\n')
+        sys.exit(1)
+    c = c.loc[p.index.intersection(c.index)]
+    if covariates is None:
+        return pd.DataFrame([])
+    cov = []
+    for col in covariates:
+        cnum = int(col.rstrip('q'))
+        if cnum == 1 or cnum > c.shape[1] + 1:
+            sys.stderr.write('Covariates columns values should be > 1 and less than or equal to '
+                             'total number of columns (%d)\n' % (c.shape[1] + 1))
+            return None
+        series = c.iloc[:, cnum - 2]
+        if col[-1] == 'q':
+            cov.append(series)
+        else:
+            categories = set(series)
+            categories.pop()
+            for i, categ in enumerate(categories):
+                cov.append(pd.Series([1 if x == categ else 0 for x in series.values], index=c.index,
+                                     name=c.columns[cnum - 2] + '_' + str(i)))
+    return pd.concat(cov, axis=1) if len(cov) > 0 else pd.DataFrame([])
+
+
+def hash_pattern(k):
+    """input.py:710-723: base64 of the MD5 of the int64 (float64 when NaN present) byte image."""
+    return binascii.b2a_base64(hashlib.md5(np.ascontiguousarray(k).view(np.uint8)).digest())
+
+
+class VariantBatch(object):
+    """``n`` variants as packed rows plus what the result loop needs to print them."""
+    __slots__ = ['names', 'bits', 'missing', 'n']
+
+    def __init__(self, names, bits, missing):
+        self.names = names
+        self.bits = bits
+        self.missing = missing
+        self.n = len(names)
+
+
+class VariantReader(object):
+    """Streams a k-mer (``name | s1:1 s2:1 ...``) or Rtab file as VariantBatch objects.
+
+    The sample order of the bit rows is the phenotype index order (``p.index``), as the
+    reference builds ``k`` (input.py:450)."""
+
+    def __init__(self, var_type, path, p, uncompressed=False):
+        self.var_type = var_type
+        self.samples = list(p.index)
+        self.index = {s: i for i, s in enumerate(self.samples)}
+        self.n_samples = len(self.samples)
+        self.W = words_per_row(self.n_samples)
+        if var_type == 'kmers':
+            self.fh = open(path, 'rt') if uncompressed else gzip.open(path, 'rt')
+            self.sample_order = None
+        elif var_type == 'Rtab':
+            self.fh = gzip.open(path, 'rt') if path.endswith('.gz') else open(path, 'rt')
+            header = self.fh.readline().rstrip().split()
+            self.sample_order = [str(x) for x in header[1:]]
+            self.col_index = np.array([self.index.get(s, -1) for s in self.sample_order])
+        else:
+            raise ValueError('unsupported variant type %s (VCF input needs pysam, which this '
+                             'build does not use)' % var_type)
+
+    def close(self):
+        self.fh.close()
+
+    def batches(self, size):
+        while True:
+            b = self._read(size)
+            if b is None:
+                return
+            yield b
+
+    def _read(self, size):
+        names = []
+        rows = np.zeros((size, self.W * 32), dtype=bool)
+        miss = None
+        n = 0
+        for line in self.fh:
+            if not line.strip():
+                continue
+            if self.var_type == 'kmers':
+                name = line.split()[0]
+                fields = line.rstrip().split('|')[1].split()
+                idx = [self.index[s] for s in (f.split(':')[0] for f in fields) if s in self.index]
+                if idx:
+                    rows[n, idx] = True
+                else:
+                    sys.stderr.write('No observations of ' + name + ' in selected samples\n')
+            else:
+                cells = line.rstrip().split('\t')
+                name, vals = cells[0], cells[1:]
+                if len(vals) == 0:
+                    raise ValueError('No sample data found; is this a Rtab file?')
+                if len(vals) != len(self.sample_order):
+                    raise ValueError('Unexpected mismatch between header and data row')
+                v = np.array(vals)
+                if not np.all(np.isin(v, ['0', '1', '.', ''])):
+                    raise ValueError('Rtab file not binary')
+                sel = self.col_index >= 0
+                present = sel & (v == '1')
+                absent_nan = sel & ((v == '.') | (v == ''))
+                rows[n, self.col_index[present]] = True
+                if absent_nan.any():
+                    if miss is None:
+                        miss = np.zeros((size, self.W * 32), dtype=bool)
+                    miss[n, self.col_index[absent_nan]] = True
+                if not (present.any() or absent_nan.any()):
+                    sys.stderr.write('No observations of ' + name + ' in selected samples\n')
+            names.append(name)
+            n += 1
+            if n == size:
+                break
+        if n == 0:
+            return None
+        bits = np.packbits(rows[:n], axis=1, bitorder='little').view('<u4')
+        mbits = None
+        if miss is not None:
+            mbits = np.packbits(miss[:n], axis=1, bitorder='little').view('<u4')
+        return VariantBatch(names, np.ascontiguousarray(bits), mbits)
+
+    # -- per-variant detail, only when needed ------------------------------------------
+    def sample_lists(self, batch, j):
+        """(kstrains, nkstrains) of variant j: sorted names, missing counted as carriers
+        (input.py:439-440)."""
+        by = batch.bits[j].view(np.uint8)
+        present = np.unpackbits(by, bitorder='little')[:self.n_samples].astype(bool)
+        if batch.missing is not None:
+            present |= np.unpackbits(batch.missing[j].view(np.uint8), bitorder='little')[:self.n_samples].astype(bool)
+        ks = sorted(s for s, on in zip(self.samples, present) if on)
+        nks = sorted(s for s, on in zip(self.samples, present) if not on)
+        return ks, nks
+
+    def k_vector(self, batch, j):
+        """The reference's ``k`` array of variant j: int64, or float64 with NaN when the
+        variant has missing genotypes (input.py:450)."""
+        x = np.unpackbits(batch.bits[j].view(np.uint8), bitorder='little')[:self.n_samples]
+        if batch.missing is not None:
+            m = np.unpackbits(batch.missing[j].view(np.uint8), bitorder='little')[:self.n_samples]
+            if m.any():
+                k = x.astype(np.float64)
+                k[m.astype(bool)] = np.nan
+                return k
+        return x.astype(np.int64)

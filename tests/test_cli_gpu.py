@@ -1,0 +1,105 @@
+"""End-to-end CLI parity against the reference's own baseline logs (tests/baseline/*.log and
+*.err of the reference, produced by the real pyseer + statsmodels; copied to
+tests/golden/baseline/).  Inputs are the reference's fixtures restricted to the 50 phenotyped
+samples (pyseer intersects samples before MDS / kinship normalisation, so results are the
+same).  Values are printed at '%.2E': they must agree to one unit of the last digit; PC
+coefficients are defined up to the sign of the MDS eigenvectors."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+G = lambda f: os.path.join(GOLDEN, f)
+FIXED = ['--kmers', G('kmers.gz'), '--phenotypes', G('subset.pheno')]
+CASES = {
+    # run_test.sh:19
+    '1': FIXED + ['--distances', G('distances50.tsv')],
+    # run_test.sh:24-25 (pop_struct.pkl is the saved MDS of the same distances)
+    '5': FIXED + ['--max-dimensions', '3', '--distances', G('distances50.tsv'),
+                  '--phenotype-column', 'continuous'],
+    '6': FIXED + ['--max-dimensions', '3', '--continuous', '--distances', G('distances50.tsv')],
+    # run_test.sh:28
+    '9': FIXED + ['--max-dimensions', '3', '--covariates', G('covariates.txt'), '--use-covariates',
+                  '2q', '3', '--distances', G('distances50.tsv')],
+    # run_test.sh:33
+    '14': ['--pres', G('presence_absence.Rtab.gz'), '--phenotypes', G('subset.pheno'),
+           '--distances', G('distances50.tsv'), '--max-dimensions', '3'],
+    # run_test.sh:34
+    '15': FIXED + ['--distances', G('distances50.tsv'), '--max-dimensions', '3', '--mds', 'classic',
+                   '--continuous'],
+    # run_test.sh:42
+    '20': FIXED + ['--similarity', G('similarity50.tsv'), '--lmm'],
+    # run_test.sh:46-47
+    '24': ['--pres', G('presence_absence.Rtab.gz'), '--phenotypes', G('subset.pheno'), '--lmm',
+           '--similarity', G('similarity50.tsv')],
+    '25': FIXED + ['--lmm', '--similarity', G('similarity50.tsv'), '--covariates',
+                   G('covariates.txt'), '--use-covariates', '2q', '3'],
+    # run_test.sh:50-51
+    '28': FIXED + ['--no-distances'],
+    '29': FIXED + ['--no-distances', '--use-covariates', '3', '--covariates', G('covariates.txt')],
+}
+
+
+def _table(text):
+    lines = [l for l in text.split('\n') if l]
+    header = lines[0].split('\t')
+    rows = {}
+    for l in lines[1:]:
+        f = l.split('\t')
+        rows[f[0]] = dict(zip(header[1:], f[1:]))
+    return header, rows
+
+
+def _counters(err):
+    out = {}
+    for l in err.split('\n'):
+        for key in ('loaded', 'pre-filtered', 'tested', 'printed'):
+            if l.endswith(key + ' variants'):
+                out[key] = int(l.split()[0])
+    return out
+
+
+def _same(a, b, abs_only=False):
+    if a == b:
+        return True
+    if a == '' or b == '':
+        return False
+    x, y = float(a), float(b)
+    if abs_only:
+        x, y = abs(x), abs(y)
+    if abs(x) < 1e-12 and abs(y) < 1e-12:          # zero up to rounding noise
+        return True
+    # one unit of the third significant digit
+    return abs(x - y) <= 1.5e-2 * max(abs(y), 1e-300)
+
+
+@pytest.mark.parametrize('case', sorted(CASES, key=int))
+def test_baseline(case):
+    from pyseer_b200.__main__ import main
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        main(CASES[case])
+    ref_out = open(os.path.join(GOLDEN, 'baseline', case + '.log')).read()
+    ref_err = open(os.path.join(GOLDEN, 'baseline', case + '.err')).read()
+    assert _counters(err.getvalue()) == _counters(ref_err)
+    h, rows = _table(out.getvalue())
+    rh, rrows = _table(ref_out)
+    assert h == rh
+    assert list(rows) == list(rrows)                   # same variants, same order
+    bad = []
+    for name, ref in rrows.items():
+        got = rows[name]
+        for col in rh[1:]:
+            if col == 'notes':
+                ok = set(got[col].split(',')) == set(ref[col].split(','))
+            else:
+                ok = _same(got[col], ref[col], abs_only=col.startswith('PC'))
+            if not ok:
+                bad.append((name[:20], col, got[col], ref[col]))
+    assert not bad, bad[:10]
