@@ -276,6 +276,16 @@ def visible_device(local_rank):
     return str(local_rank)
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the
+    committed ncu --set full capture of the same workload (profiles/ncu_traffic.json), else None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        return d[key]['traffic_bytes_per_launch']
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -364,7 +374,8 @@ class LmmWorkload(object):
                 'executed_int8_tops': achieved * k if k else None,
                 'kernel_ms': k_ms, 'run_ms': run_ms, 'kernel_share_of_step': k_ms / run_ms,
                 'hbm_read_frac': (tested * (W * 4 + 56) / (k_ms / 1e3) / 1e9) / pk['hbm_gbs'],
-                'traffic': None}
+                'algorithmic_bytes': tested * (W * 4 + 24.0),
+                'traffic': ncu_traffic('lmm:n=%d:kmers=%d:k=%d' % (n, self.kpg, k))}
 
 
 class FixedWorkload(object):

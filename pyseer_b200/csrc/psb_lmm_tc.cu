@@ -297,7 +297,11 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         const int et = (warp - 2) * 32 + lane;        // 0..255 cooperative-copy index
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const int chunks_per_row = args.nks;          // 16-byte chunks (4 words = 128 samples)
-        uint32_t stage_ctr = 0;                       // global K-stage counter (all tiles)
+        // ring position of the next stage this group handles (the group takes every second
+        // stage of the global sequence; ns is even, so it stays on slots of its own parity)
+        int sa = grp;
+        uint32_t pha = 0;
+        uint32_t parity = 0;                          // parity of the global stage counter
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // all expanders are done reading the previous tile's bits
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -318,10 +322,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const uint32_t *myrow = sBits + (size_t)v * args.pitch;
             for (int jt = 0; jt < args.jtiles; ++jt)
-                for (int ks = 0; ks < args.nks; ++ks, ++stage_ctr) {
-                    if ((int)(stage_ctr & 1u) != grp) continue;
-                    const int sa = (int)(stage_ctr % (uint32_t)ns);
-                    const uint32_t pha = (stage_ctr / (uint32_t)ns) & 1u;
+                for (int ks = 0; ks < args.nks; ++ks, parity ^= 1u) {
+                    if ((int)parity != grp) continue;
                     const uint4 w4 = *reinterpret_cast<const uint4 *>(myrow + ks * 4);
                     mbar_wait(empty0 + sa * 8, pha ^ 1);
                     tc_fence_after();
@@ -340,6 +342,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(full0 + sa * 8);
+                    sa += 2;
+                    if (sa >= ns) { sa -= ns; pha ^= 1u; }
                 }
         }
     } else {
@@ -602,7 +606,8 @@ int psb_lmm_tc_run(psb_ctx *c, int n_tested) {
     int smem_max = 0;
     PSB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     int nb = (512 - 2 * TC_JT * nsl) / 32;      // TMEM A-ring depth bounds the pipeline
-    while (nb > 1 && tc_smem_bytes(nsl, nb, pitch) > (size_t)smem_max) --nb;
+    // (kept even: the two expander groups own the slots of their own parity)
+    while (nb > 2 && tc_smem_bytes(nsl, nb, pitch) > (size_t)smem_max) nb -= 2;
     PSB_REQUIRE(tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max, PSB_ERR_UNSUPPORTED,
                 "n_samples = %d needs more shared memory than the tensor path has; use precision 0",
                 c->N);
