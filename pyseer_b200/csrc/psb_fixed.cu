@@ -155,6 +155,21 @@ __device__ __forceinline__ void fx_row(const FxArgs &a, int i, uint32_t xbit, do
     }
 }
 
+// beta'z with four interleaved accumulation chains (shorter dependency chain than one FMA
+// chain of length PP; the summation order is irrelevant at the 1e-6 tolerance).
+template <int PP>
+__device__ __forceinline__ double fx_dot(const double (&beta)[PP], const double (&z)[PP]) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < PP; c += 4) {
+        s0 = fma(beta[c], z[c], s0);
+        if (c + 1 < PP) s1 = fma(beta[c + 1], z[c + 1], s1);
+        if (c + 2 < PP) s2 = fma(beta[c + 2], z[c + 2], s2);
+        if (c + 3 < PP) s3 = fma(beta[c + 3], z[c + 3], s3);
+    }
+    return (s0 + s1) + (s2 + s3);
+}
+
 // One pass over the samples at parameters beta: X'WX (packed), score X'(y - pi),
 // max |y - pi| and the log-likelihood.  All lanes return the full sums.
 template <int PP>
@@ -176,9 +191,7 @@ __device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, i
         const int i = w * 32 + lane;
         double z[PP];
         fx_row<PP>(a, i, (xw >> lane) & 1u, z);
-        double eta = 0.0;
-#pragma unroll
-        for (int c = 0; c < PP; ++c) eta = fma(beta[c], z[c], eta);
+        const double eta = fx_dot<PP>(beta, z);
         const double y = (double)((yw >> lane) & 1u);
         const double ex = exp(-fabs(eta));            // in (0, 1]
         const double den = 1.0 / (1.0 + ex);
@@ -225,9 +238,7 @@ __device__ __forceinline__ double fx_loglike(const FxArgs &a, const uint32_t *xr
         const uint32_t yw = __ldg(a.y1 + w);
         double z[PP];
         fx_row<PP>(a, w * 32 + lane, (xw >> lane) & 1u, z);
-        double eta = 0.0;
-#pragma unroll
-        for (int c = 0; c < PP; ++c) eta = fma(beta[c], z[c], eta);
+        const double eta = fx_dot<PP>(beta, z);
         const double s = ((yw >> lane) & 1u) ? eta : -eta;
         llf += fmin(s, 0.0) - log1p(exp(-fabs(s)));
     }
@@ -308,7 +319,9 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
                 fx_eval<PP>(a, xrow, lane, beta, H, g, maxdev, llf, want_llf);
                 have_llf = want_llf;
                 if (it > 0 && maxdev <= 1e-8) { fail = PSB_F_PERFECT_SEP; break; }   // _check_perfect_pred
-                if (it > 0 && !(maxstep > 1e-8)) { converged = true; break; }        // converged
+                // reference rule |dbeta| <= 1e-8; the warm attempt stops one quadratic step
+                // earlier (|dbeta| <= 1e-6 leaves an error of order 1e-12)
+                if (it > 0 && !(maxstep > (attempt == 0 ? 1e-6 : 1e-8))) { converged = true; break; }
                 if (it >= maxit) break;                                              // maxiter
                 // H/n + 1e-10 I, solve for the step
 #pragma unroll
@@ -430,9 +443,7 @@ k_fixed_firth(FxArgs a, int n_list) {
                 const uint32_t yw = __ldg(a.y1 + w);
                 double z[PP];
                 fx_row<PP>(a, w * 32 + lane, (xw >> lane) & 1u, z);
-                double eta = 0.0;
-#pragma unroll
-                for (int c = 0; c < PP; ++c) eta = fma(beta[c], z[c], eta);
+                const double eta = fx_dot<PP>(beta, z);
                 const double ex = exp(-fabs(eta));
                 const double den = 1.0 / (1.0 + ex);
                 const double pi = eta >= 0.0 ? den : ex * den;
