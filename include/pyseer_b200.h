@@ -165,6 +165,23 @@ int psb_host_alloc(size_t bytes, void **out);
 int psb_host_free(void *ptr);
 int psb_download_bits(psb_ctx *ctx, uint32_t *out_bits);
 
+/* ---- native variant-file reader ------------------------------------------------- */
+/* Replaces the per-line Python of input.read_variant (input.py:301-454) for the k-mer text
+ * format (`name | s1:1 s2:1 ...`, var_type 0) and Rtab (var_type 1); plain or gzip files.
+ * sample_names: the phenotype index order (bit i of a row = sample_names[i]).
+ * psb_reader_next fills up to max_variants packed rows (bits, and missing when non-NULL; both
+ * max_variants x words_per_row, zeroed by the call), the NUL-terminated names back to back in
+ * `names` with name_off[v] their offsets, and info[v] (bit 0: row has missing genotypes,
+ * bit 1: no observation in the selected samples, input.py:447-448).  *n_read == 0 at end of
+ * file; *any_missing != 0 when at least one row had missing genotypes. */
+typedef struct psb_reader psb_reader;
+int psb_reader_open(const char *path, int32_t var_type, const char *const *sample_names,
+                    int32_t n_samples, psb_reader **out);
+int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, uint32_t *missing,
+                    int32_t words_per_row, char *names, int64_t names_cap, int64_t *name_off,
+                    int32_t *info, int64_t *n_read, int32_t *any_missing);
+int psb_reader_close(psb_reader *reader);
+
 /* ---- measurement ------------------------------------------------------------- */
 /* CUDA-event timers on the context stream.  which: 0 = whole last psb_run_*,
  * 1 = dominant kernel of the last run (LMM: the rotation/quadratic-form contraction;

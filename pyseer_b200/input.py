@@ -7,7 +7,6 @@ bit positions once, and per-variant sample lists are only materialised when aske
 (``--print-samples``).
 """
 import binascii
-import gzip
 import hashlib
 import sys
 
@@ -120,86 +119,56 @@ class VariantBatch(object):
 
 
 class VariantReader(object):
-    """Streams a k-mer (``name | s1:1 s2:1 ...``) or Rtab file as VariantBatch objects.
-
-    The sample order of the bit rows is the phenotype index order (``p.index``), as the
-    reference builds ``k`` (input.py:450)."""
+    """Streams a k-mer (``name | s1:1 s2:1 ...``) or Rtab file as VariantBatch objects through
+    the library's native reader (``psb_reader_*``: zlib + hash-map lookup straight into packed
+    rows).  The sample order of the bit rows is the phenotype index order (``p.index``), as
+    the reference builds ``k`` (input.py:450)."""
 
     def __init__(self, var_type, path, p, uncompressed=False):
-        self.var_type = var_type
-        self.samples = list(p.index)
-        self.index = {s: i for i, s in enumerate(self.samples)}
-        self.n_samples = len(self.samples)
-        self.W = words_per_row(self.n_samples)
-        if var_type == 'kmers':
-            self.fh = open(path, 'rt') if uncompressed else gzip.open(path, 'rt')
-            self.sample_order = None
-        elif var_type == 'Rtab':
-            self.fh = gzip.open(path, 'rt') if path.endswith('.gz') else open(path, 'rt')
-            header = self.fh.readline().rstrip().split()
-            self.sample_order = [str(x) for x in header[1:]]
-            self.col_index = np.array([self.index.get(s, -1) for s in self.sample_order])
-        else:
+        import ctypes
+        from . import _lib
+        if var_type not in ('kmers', 'Rtab'):
             raise ValueError('unsupported variant type %s (VCF input needs pysam, which this '
                              'build does not use)' % var_type)
+        self.var_type = var_type
+        self.samples = [str(s) for s in p.index]
+        self.n_samples = len(self.samples)
+        self.W = words_per_row(self.n_samples)
+        self._lib = _lib.load()
+        names = (ctypes.c_char_p * self.n_samples)(*[s.encode() for s in self.samples])
+        self._h = ctypes.c_void_p()
+        _lib.check(self._lib.psb_reader_open(str(path).encode(), 0 if var_type == 'kmers' else 1,
+                                             names, self.n_samples, ctypes.byref(self._h)))
 
     def close(self):
-        self.fh.close()
+        if self._h:
+            self._lib.psb_reader_close(self._h)
+            self._h = None
 
-    def batches(self, size):
+    def batches(self, size, names_cap=None):
+        import ctypes
+        from . import _lib
+        cap = int(names_cap or max(1 << 20, 160 * size))
         while True:
-            b = self._read(size)
-            if b is None:
+            bits = np.empty((size, self.W), dtype=np.uint32)
+            miss = np.empty((size, self.W), dtype=np.uint32) if self.var_type == 'Rtab' else None
+            names = ctypes.create_string_buffer(cap)
+            off = np.empty(size, dtype=np.int64)
+            info = np.empty(size, dtype=np.int32)
+            n = ctypes.c_int64(0)
+            anym = ctypes.c_int32(0)
+            _lib.check(self._lib.psb_reader_next(
+                self._h, size, bits.ctypes.data, miss.ctypes.data if miss is not None else None,
+                self.W, ctypes.addressof(names), cap, off.ctypes.data, info.ctypes.data,
+                ctypes.byref(n), ctypes.byref(anym)))
+            n = n.value
+            if n == 0:
                 return
-            yield b
-
-    def _read(self, size):
-        names = []
-        rows = np.zeros((size, self.W * 32), dtype=bool)
-        miss = None
-        n = 0
-        for line in self.fh:
-            if not line.strip():
-                continue
-            if self.var_type == 'kmers':
-                name = line.split()[0]
-                fields = line.rstrip().split('|')[1].split()
-                idx = [self.index[s] for s in (f.split(':')[0] for f in fields) if s in self.index]
-                if idx:
-                    rows[n, idx] = True
-                else:
-                    sys.stderr.write('No observations of ' + name + ' in selected samples\n')
-            else:
-                cells = line.rstrip().split('\t')
-                name, vals = cells[0], cells[1:]
-                if len(vals) == 0:
-                    raise ValueError('No sample data found; is this a Rtab file?')
-                if len(vals) != len(self.sample_order):
-                    raise ValueError('Unexpected mismatch between header and data row')
-                v = np.array(vals)
-                if not np.all(np.isin(v, ['0', '1', '.', ''])):
-                    raise ValueError('Rtab file not binary')
-                sel = self.col_index >= 0
-                present = sel & (v == '1')
-                absent_nan = sel & ((v == '.') | (v == ''))
-                rows[n, self.col_index[present]] = True
-                if absent_nan.any():
-                    if miss is None:
-                        miss = np.zeros((size, self.W * 32), dtype=bool)
-                    miss[n, self.col_index[absent_nan]] = True
-                if not (present.any() or absent_nan.any()):
-                    sys.stderr.write('No observations of ' + name + ' in selected samples\n')
-            names.append(name)
-            n += 1
-            if n == size:
-                break
-        if n == 0:
-            return None
-        bits = np.packbits(rows[:n], axis=1, bitorder='little').view('<u4')
-        mbits = None
-        if miss is not None:
-            mbits = np.packbits(miss[:n], axis=1, bitorder='little').view('<u4')
-        return VariantBatch(names, np.ascontiguousarray(bits), mbits)
+            raw = names.raw
+            nm = [raw[off[i]:raw.index(b'\0', off[i])].decode() for i in range(n)]
+            for i in np.nonzero(info[:n] & 2)[0]:
+                sys.stderr.write('No observations of ' + nm[i] + ' in selected samples\n')
+            yield VariantBatch(nm, bits[:n], miss[:n] if (miss is not None and anym.value) else None)
 
     # -- per-variant detail, only when needed ------------------------------------------
     def sample_lists(self, batch, j):

@@ -1,0 +1,86 @@
+"""The native k-mer / Rtab reader (psb_reader_*, host code of the shared library) against a
+plain-Python parse of the same files that follows input.read_variant (input.py:377-452)."""
+import gzip
+import io
+import os
+import contextlib
+
+import numpy as np
+import pandas as pd
+
+from conftest import GOLDEN
+from pyseer_b200.engine import unpack_rows
+from pyseer_b200.input import VariantReader, hash_pattern, load_phenotypes
+
+
+def _pheno():
+    return load_phenotypes(os.path.join(GOLDEN, 'subset.pheno'), None)
+
+
+def test_kmers_reader_matches_python_parse():
+    p = _pheno()
+    samples = list(p.index)
+    rd = VariantReader('kmers', os.path.join(GOLDEN, 'kmers.gz'), p)
+    err = io.StringIO()
+    with contextlib.redirect_stderr(err):
+        batches = list(rd.batches(64))
+    rd.close()
+    names = [n for b in batches for n in b.names]
+    x = np.concatenate([unpack_rows(b.bits, len(samples)) for b in batches])
+    assert [b.n for b in batches] == [64, 64, 64, 8] and all(b.missing is None for b in batches)
+    none_seen = []
+    with gzip.open(os.path.join(GOLDEN, 'kmers.gz'), 'rt') as fh:
+        for i, line in enumerate(fh):
+            name = line.split()[0]
+            d = {t.split(':')[0] for t in line.rstrip().split('|')[1].split()}
+            k = np.array([1 if s in d else 0 for s in samples])
+            assert names[i] == name
+            assert np.array_equal(x[i], k), name
+            if k.sum() == 0:
+                none_seen.append(name)
+    assert i + 1 == len(names) == 200
+    assert err.getvalue().count('No observations of') == len(none_seen) == 6
+
+
+def test_rtab_reader_and_missing(tmp_path):
+    p = _pheno()
+    samples = list(p.index)
+    rd = VariantReader('Rtab', os.path.join(GOLDEN, 'presence_absence.Rtab.gz'), p)
+    with contextlib.redirect_stderr(io.StringIO()):
+        batches = list(rd.batches(1000))
+    rd.close()
+    tab = pd.read_csv(os.path.join(GOLDEN, 'presence_absence.Rtab.gz'), sep='\t', index_col=0)
+    tab = tab[samples]
+    names = [n for b in batches for n in b.names]
+    x = np.concatenate([unpack_rows(b.bits, len(samples)) for b in batches])
+    assert names == [str(s) for s in tab.index]
+    assert np.array_equal(x, (tab.values == 1).astype(np.uint8))
+    # a small file with missing cells, plain text
+    f = tmp_path / 'm.Rtab'
+    f.write_text('Gene\t' + '\t'.join(samples[:4]) + '\textra\n'
+                 'g1\t1\t0\t.\t1\t1\n'
+                 'g2\t0\t0\t0\t0\t1\n'
+                 'g3\t1\t\t1\t0\t0\n')
+    rd = VariantReader('Rtab', str(f), p)
+    err = io.StringIO()
+    with contextlib.redirect_stderr(err):
+        (b,) = list(rd.batches(10))
+    assert b.names == ['g1', 'g2', 'g3'] and b.missing is not None
+    xb, mb = unpack_rows(b.bits, len(samples)), unpack_rows(b.missing, len(samples))
+    assert xb[0, :4].tolist() == [1, 0, 0, 1] and mb[0, :4].tolist() == [0, 0, 1, 0]
+    assert xb[1].sum() == 0 and 'No observations of g2' in err.getvalue()
+    assert xb[2, :4].tolist() == [1, 0, 1, 0] and mb[2, :4].tolist() == [0, 1, 0, 0]
+    k = rd.k_vector(b, 0)
+    assert k.dtype == np.float64 and np.isnan(k[2]) and k[0] == 1
+    ks, nks = rd.sample_lists(b, 0)
+    assert set(ks) == {samples[0], samples[2], samples[3]}      # missing counts as a carrier
+    assert rd.k_vector(b, 1).dtype == np.int64
+    rd.close()
+
+
+def test_hash_pattern_golden(goldens):
+    """input.py:710-723 / tests/input_test.py: MD5 of the 8-byte-per-sample image, base64."""
+    assert hash_pattern(np.ones(50, dtype=np.int64)) == b'xxPKpdegG31U5Mx9EHcYXg==\n'
+    # tests/input_test.py:840-845: the 'binary' column of subset.pheno
+    pb = pd.read_csv(os.path.join(GOLDEN, 'subset.pheno'), index_col=0, sep='\t')['binary']
+    assert hash_pattern(pb.values) == goldens['hash_pattern_k'].encode()
