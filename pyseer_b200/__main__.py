@@ -2,11 +2,11 @@
 loop running on the GPU.
 
 Same options, same TSV on stdout, same counters on stderr for the fixed-effects (SEER) and
-``--lmm`` models with ``--kmers`` / ``--pres`` input.  What the reference does with a
+``--lmm`` models with ``--kmers`` / ``--pres`` / ``--vcf`` (``--burden``) input.  What the reference does with a
 ``multiprocessing.Pool`` over variants (``__main__.py:517-593, 762-827``) is done here by
 submitting blocks of packed variants to the engine; ``--cpu`` is accepted and ignored.
-Whole-genome models (``--wg``), VCF / burden input and lineage effects are not part of this
-path and are rejected with a message.
+Whole-genome models (``--wg``) and lineage effects are not part of this path and are
+rejected with a message.
 """
 import argparse
 import os
@@ -19,7 +19,7 @@ from . import __version__
 from . import _lib
 from . import classes as var_obj
 from .engine import notes_from_flags
-from .input import (VariantReader, hash_pattern, load_covariates, load_phenotypes,
+from .input import (VariantReader, VcfReader, hash_pattern, load_covariates, load_phenotypes,
                     load_structure)
 from .utils import format_output
 
@@ -90,8 +90,8 @@ def main(argv=None):
     # option checks of __main__.py:257-306 that concern the supported models
     if o.wg:
         _die('Whole-genome models (--wg) are not part of the GPU path; use pyseer for them')
-    if o.vcf or o.burden:
-        _die('VCF / burden input needs pysam, which this build does not use; convert to --pres')
+    if o.burden and not o.vcf:
+        _die('Burden test can only be performed with VCF input')
     if o.lineage or o.lineage_clusters:
         _die('Lineage effects are not wired into this CLI yet')
     if o.max_dimensions < 1:
@@ -168,8 +168,10 @@ def main(argv=None):
                                        device=o.gpu, precision=o.lmm_precision)
         sys.stderr.write('h^2 = ' + '{0:.2f}'.format(h2) + '\n')
 
-    var_type = 'kmers' if o.kmers else 'Rtab'
-    reader = VariantReader(var_type, o.kmers or o.pres, p, o.uncompressed)
+    if o.vcf:
+        reader = VcfReader(o.vcf, p, o.burden)
+    else:
+        reader = VariantReader('kmers' if o.kmers else 'Rtab', o.kmers or o.pres, p, o.uncompressed)
 
     header = ['variant', 'af', 'filter-pvalue', 'lrt-pvalue', 'beta', 'beta-std-err']
     if not o.lmm:

@@ -193,3 +193,139 @@ class VariantReader(object):
                 k[m.astype(bool)] = np.nan
                 return k
         return x.astype(np.int64)
+
+
+class VcfReader(object):
+    """VCF (and burden-region) input without pysam: plain or gzip text VCF, dominant encoding.
+
+    Follows input.read_vcf_var (input.py:457-502): a sample carries the variant if any haplotype
+    of its GT is a non-reference allele; '.' haplotypes mark the genotype missing unless a
+    called haplotype follows; multi-allelic records and records whose FILTER is neither empty
+    nor PASS are skipped (they still count as loaded, and end up AF-filtered like the
+    reference's ``None`` sentinel).  With ``burden_file`` each row is the OR over every record
+    overlapping the region(s) of one line ``name contig:start-end[,contig:start-end...]``
+    (input.py:395-411, load_burden :250-266); the whole VCF is held in memory for that.
+    Produces the same VariantBatch objects as VariantReader."""
+
+    def __init__(self, path, p, burden_file=None):
+        import gzip
+        self.samples = [str(s) for s in p.index]
+        self.index = {s: i for i, s in enumerate(self.samples)}
+        self.n_samples = len(self.samples)
+        self.W = words_per_row(self.n_samples)
+        with open(path, 'rb') as fh:
+            magic = fh.read(2)
+        self.fh = gzip.open(path, 'rt') if magic == b'\x1f\x8b' else open(path, 'rt')
+        self.cols = None
+        for line in self.fh:
+            if line.startswith('#CHROM'):
+                names = line.rstrip('\n').split('\t')[9:]
+                self.cols = [(9 + j, self.index[s]) for j, s in enumerate(names) if s in self.index]
+                break
+        if self.cols is None:
+            raise ValueError('no #CHROM header line found; is this a VCF file?')
+        self.regions = None
+        if burden_file:
+            self.regions = []
+            with open(burden_file) as rf:
+                for line in rf:
+                    name, spec = line.rstrip().split()
+                    self.regions.append((name, spec.split(',')))
+            self.records = [self._split(line) for line in self.fh if line.strip()]
+
+    def close(self):
+        self.fh.close()
+
+    @staticmethod
+    def _split(line):
+        f = line.rstrip('\n').split('\t')
+        return f
+
+    def _apply(self, f, state):
+        """read_vcf_var on one record: updates the per-sample state in place
+        (0 = not in d, 1 = present, 2 = NaN); returns the variant name or None if skipped."""
+        contig, pos, ref, alt, filt = f[0], f[1], f[3], f[4], f[6]
+        alts = [] if alt == '.' else alt.split(',')
+        name = '_'.join([contig, pos, ref] + alts)
+        if len(alts) > 1:
+            sys.stderr.write('Multiple alleles at %s_%s. Skipping\n' % (contig, pos))
+            return None
+        filters = [] if filt in ('.', '') else filt.split(';')
+        if len(filters) > 0 and 'PASS' not in filters:
+            return None
+        fmt = f[8].split(':')
+        gi = fmt.index('GT') if 'GT' in fmt else -1
+        for col, s in self.cols:
+            if gi < 0:
+                haps = [None]
+            else:
+                gt = f[col].split(':')[gi]
+                haps = gt.replace('|', '/').split('/')
+            st = state[s]
+            for h in haps:
+                if h is None or h == '.':
+                    if st == 0:
+                        st = 2
+                elif h != '0':
+                    st = 1
+                    break
+                elif st == 2:
+                    st = 0
+            state[s] = st
+        return name
+
+    def _rows(self):
+        if self.regions is None:
+            for line in self.fh:
+                if not line.strip():
+                    continue
+                state = np.zeros(self.n_samples, dtype=np.int8)
+                name = self._apply(self._split(line), state)
+                yield name, state
+        else:
+            import re
+            for rname, specs in self.regions:
+                state = np.zeros(self.n_samples, dtype=np.int8)
+                ok = True
+                for spec in specs:
+                    mt = re.match(r'^(.+):(\d+)-(\d+)$', spec)
+                    if not mt:
+                        sys.stderr.write('Could not parse region %s\n' % str(spec))
+                        ok = False
+                        break
+                    contig, lo, hi = mt.group(1), int(mt.group(2)) - 1, int(mt.group(3))
+                    for f in self.records:
+                        start = int(f[1]) - 1
+                        if f[0] == contig and start < hi and start + len(f[3]) > lo:
+                            self._apply(f, state)
+                yield (rname if ok else None), state
+
+    def batches(self, size):
+        names, states = [], []
+        for name, state in self._rows():
+            if name is None:
+                # skipped record: the reference yields its None sentinel (counted as loaded and
+                # pre-filtered); an empty row takes the same route through the AF filter
+                state = np.zeros(self.n_samples, dtype=np.int8)
+                name = 'NA'
+            elif not state.any():
+                sys.stderr.write('No observations of ' + name + ' in selected samples\n')
+            names.append(name)
+            states.append(state)
+            if len(names) == size:
+                yield self._pack(names, states)
+                names, states = [], []
+        if names:
+            yield self._pack(names, states)
+
+    def _pack(self, names, states):
+        st = np.zeros((len(names), self.W * 32), dtype=np.int8)
+        st[:, :self.n_samples] = np.array(states)
+        bits = np.packbits(st == 1, axis=1, bitorder='little').view('<u4')
+        miss = None
+        if (st == 2).any():
+            miss = np.ascontiguousarray(np.packbits(st == 2, axis=1, bitorder='little').view('<u4'))
+        return VariantBatch(names, np.ascontiguousarray(bits), miss)
+
+    sample_lists = VariantReader.sample_lists
+    k_vector = VariantReader.k_vector

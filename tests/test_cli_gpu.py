@@ -40,6 +40,20 @@ CASES = {
            '--similarity', G('similarity50.tsv')],
     '25': FIXED + ['--lmm', '--similarity', G('similarity50.tsv'), '--covariates',
                    G('covariates.txt'), '--use-covariates', '2q', '3'],
+    # run_test.sh:31-32, :59 (VCF, burden regions), :45 (LMM with VCF)
+    '12': ['--vcf', G('variants50.vcf.gz'), '--phenotypes', G('subset.pheno'), '--distances',
+           G('distances50.tsv'), '--max-dimensions', '3'],
+    '13': ['--vcf', G('variants50.vcf.gz'), '--burden', G('burden_regions.txt'), '--phenotypes',
+           G('subset.pheno'), '--distances', G('distances50.tsv'), '--max-dimensions', '3'],
+    '37': ['--vcf', G('variants50.vcf.gz'), '--burden', G('burden_regions_multiple.txt'),
+           '--phenotypes', G('subset.pheno'), '--distances', G('distances50.tsv'),
+           '--max-dimensions', '3'],
+    '23': ['--vcf', G('variants50.vcf.gz'), '--phenotypes', G('subset.pheno'), '--lmm',
+           '--similarity', G('similarity50.tsv')],
+    # run_test.sh:22 (filters), :49 (pattern output)
+    '3': FIXED + ['--filter-pvalue', '1E-5', '--lrt-pvalue', '1E-8', '--distances',
+                  G('distances50.tsv')],
+    '27': FIXED + ['--lmm', '--similarity', G('similarity50.tsv')],
     # run_test.sh:50-51
     '28': FIXED + ['--no-distances'],
     '29': FIXED + ['--no-distances', '--use-covariates', '3', '--covariates', G('covariates.txt')],
@@ -80,11 +94,18 @@ def _same(a, b, abs_only=False):
 
 
 @pytest.mark.parametrize('case', sorted(CASES, key=int))
-def test_baseline(case):
+def test_baseline(case, tmp_path):
     from pyseer_b200.__main__ import main
     out, err = io.StringIO(), io.StringIO()
+    args = list(CASES[case])
+    if case == '27':
+        args += ['--output-patterns', str(tmp_path / 'patterns.txt')]
     with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
-        main(CASES[case])
+        main(args)
+    if case == '27':
+        # one base64 MD5 line per tested variant (__main__.py:559-560; scripts/count_patterns.py)
+        pats = open(str(tmp_path / 'patterns.txt'), 'rb').read().split(b'\n')[:-1]
+        assert len(pats) == _counters(err.getvalue())['tested'] and all(len(x) == 24 for x in pats)
     ref_out = open(os.path.join(GOLDEN, 'baseline', case + '.log')).read()
     ref_err = open(os.path.join(GOLDEN, 'baseline', case + '.err')).read()
     assert _counters(err.getvalue()) == _counters(ref_err)
