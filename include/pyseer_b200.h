@@ -145,6 +145,18 @@ int psb_run_lmm(psb_ctx *ctx, const psb_params *params);
 /* replaces model.fixed_effects_regression (model.py:202-394) for every submitted variant */
 int psb_run_fixed(psb_ctx *ctx, const psb_params *params);
 
+/* Lineage effects, model.fit_lineage_effect (model.py:151-199; called from model.py:379-380 and
+ * lmm.py:209-211): Logit of the VARIANT on Zlin = [1, lineage columns, covariates] (N x q
+ * row-major, n_lineage lineage columns after the intercept).  psb_lineage_setup goes after the
+ * model set-up; psb_run_lineage after psb_run_* on the same submitted rows (mode 0: every
+ * tested variant that produced a fit, the fixed-effects rule; mode 1: tested variants that
+ * passed the lrt filter, the LMM rule); psb_fetch_lineage returns, per submitted variant, the
+ * index of the lineage with the largest Wald statistic or -1 (None). */
+int psb_lineage_setup(psb_ctx *ctx, int32_t n_samples, int32_t q, const double *Zlin,
+                      int32_t n_lineage);
+int psb_run_lineage(psb_ctx *ctx, int32_t mode);
+int psb_fetch_lineage(psb_ctx *ctx, int32_t *out);
+
 /* Copies the result table to caller arrays (synchronises the context stream).  The
  * destination pointers may be host memory (pinned or pageable) or device memory (e.g. a
  * buffer that is then gathered across ranks with NCCL). */

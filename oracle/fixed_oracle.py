@@ -7,7 +7,7 @@ lines it follows.  statsmodels behaviour restated here (published algorithm):
 
 * ``Logit.fit(start_params, method='newton')`` -- ``base/optimizer.py:_fit_newton``:
   ``while it < 35 and any(|new-old| > 1e-8)``: ``H = hessian/n; H[diag] += 1e-10;
-  new = old - solve(H, score/n)``; callback ``_check_perfect_pred`` raises
+  new = old - solve(H, score/n)`` (newton gets the *positive* score and hessian); callback ``_check_perfect_pred`` raises
   ``PerfectSeparationError`` iff ``allclose(cdf(X new) - y, 0)``.
   ``llf = sum(log cdf((2y-1) X b))``; ``bse = sqrt(diag(inv(X' W X)))`` at the
   final parameters.
@@ -76,6 +76,12 @@ def logit_newton(X, y, start, maxiter=35, tol=1e-8, raise_perfect=True):
     old = np.full_like(new, np.inf)
     it = 0
     while it < maxiter and np.any(np.abs(new - old) > tol):
+        # statsmodels base/model.py:fit hands _fit_newton score = +score/n and hess =
+        # +hessian/n (negative definite; "TODO: why are score and hess positive?"), and
+        # base/optimizer.py:_fit_newton adds ridge_factor = 1e-10 to that diagonal: the step
+        # is (X'WX/n - 1e-10 I)^-1 score/n.  In separated data the matrix goes indefinite and
+        # the iterates run away, which is what trips the perfect-prediction check (pinned by
+        # the reference's baseline 18: three separated variants report lineage NA).
         H = logit_hessian(new, X) / n
         H[np.diag_indices(H.shape[0])] += 1e-10
         old = new

@@ -35,6 +35,11 @@ def main():
                     f[i] = f[i].split(':')[gi]
                 f[8] = 'GT'
             fout.write('\t'.join(f[i] for i in cols) + '\n')
+    with open(os.path.join(REF, 'lineage_clusters.txt')) as fin, \
+            open(os.path.join(OUT, 'lineage_clusters50.txt'), 'w') as fout:
+        for line in fin:
+            if line.split()[0] in keep:
+                fout.write(line)
     for name in ('burden_regions.txt', 'burden_regions_multiple.txt'):
         shutil.copy(os.path.join(REF, name), os.path.join(OUT, name))
     os.makedirs(os.path.join(OUT, 'baseline'), exist_ok=True)

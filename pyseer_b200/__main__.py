@@ -9,6 +9,7 @@ Whole-genome models (``--wg``) and lineage effects are not part of this path and
 rejected with a message.
 """
 import argparse
+import operator
 import os
 import sys
 
@@ -19,8 +20,8 @@ from . import __version__
 from . import _lib
 from . import classes as var_obj
 from .engine import notes_from_flags
-from .input import (VariantReader, VcfReader, hash_pattern, load_covariates, load_phenotypes,
-                    load_structure)
+from .input import (VariantReader, VcfReader, hash_pattern, load_covariates, load_lineage,
+                    load_phenotypes, load_structure)
 from .utils import format_output
 
 
@@ -92,15 +93,17 @@ def main(argv=None):
         _die('Whole-genome models (--wg) are not part of the GPU path; use pyseer for them')
     if o.burden and not o.vcf:
         _die('Burden test can only be performed with VCF input')
-    if o.lineage or o.lineage_clusters:
-        _die('Lineage effects are not wired into this CLI yet')
     if o.max_dimensions < 1:
         _die('Minimum number of dimensions after MDS is 1')
     if o.lmm and not o.similarity and not o.load_lmm:
         _die('Must provide a similarity matrix or lmm cache for random effects')
     if not o.no_distances:
-        if (o.lmm and (o.distances or o.load_m)) or (not o.lmm and (o.similarity or o.load_lmm)):
-            _die('Must use distance matrix with fixed effects, or similarity matrix with random effects')
+        if (o.lmm and (o.distances or o.load_m) and not o.lineage) or \
+                (not o.lmm and (o.similarity or o.load_lmm)):
+            _die('Must use distance matrix with fixed effects, or similarity matrix with random '
+                 'effects\nUnless performing a lineage analysis with random effects')
+        if o.lmm and not (o.distances or o.load_m) and o.lineage and not o.lineage_clusters:
+            _die('Must also provide a distance matrix to report lineage effects')
         if not o.lmm and not o.distances and not o.load_m:
             _die('Option --no-distances must be used when no distance matrix is provided')
     else:
@@ -108,6 +111,9 @@ def main(argv=None):
             _die('Cannot use --no-distances with --distances or --load-m')
         if o.lmm:
             _die('Cannot use --no-distances with --lmm')
+        if not o.lmm and not o.lineage_clusters and o.lineage:
+            _die('Must provide a lineage clusters file when --no-distances and --lineage are used '
+                 'together in fixed-effects mode')
     if o.block_size < 1:
         _die('Block size must be at least 1')
 
@@ -127,10 +133,13 @@ def main(argv=None):
     else:
         cov = pd.DataFrame([])
 
+    from . import model as fx
     model = None
     lmm = None
-    if not o.lmm:
-        from . import model as fx
+    m = np.empty(shape=(0, 0))
+    null_fit = firth_null = None
+    # fixed effects, or lineage effects from the MDS components, need p ~ m
+    if (o.lineage and not o.lineage_clusters) or not o.lmm:
         if not o.no_distances:
             if o.load_m and os.path.isfile(o.load_m):
                 m = pd.read_pickle(o.load_m)
@@ -150,21 +159,58 @@ def main(argv=None):
                              'and structure matrix\n')
             p = p.loc[common]
             m = m.loc[p.index].values[:, :o.max_dimensions]
-        else:
-            m = np.empty(shape=(0, 0))
         if cov.shape[1] > 0:
             cov = cov.loc[p.index]
         null_fit = fx.fit_null(p.values, m, cov, o.continuous, device=o.gpu)
         firth_null = fx.fit_null(p.values, m, cov, o.continuous, True, device=o.gpu) \
-            if not o.continuous else True
+            if (not o.continuous and not o.lmm) else True
         if null_fit is None or firth_null is None:
             _die('Could not fit null model, exiting')
+
+    # lineage effects (__main__.py:388-446)
+    lineage_clusters = None
+    lineage_dict = None
+    lineage_samples = None
+    if o.lineage_clusters:
+        lineage_clusters, lineage_dict = load_lineage(o.lineage_clusters, p)
+    if o.lineage:
+        lineage_samples = p.index
+        lineage_wald = {}
+        if o.lineage_clusters:
+            # the cluster design is not full rank: drop the lineage least associated with
+            # the phenotype (single-predictor fits, the clusters being orthogonal)
+            for lineage, design in zip(lineage_dict, lineage_clusters.T):
+                fit = fx.fit_null(p.values, design.reshape(-1, 1).astype(float), cov, o.continuous,
+                                  device=o.gpu)
+                if fit is None:
+                    _die('Could not fit lineage null model, exiting')
+                lineage_wald[lineage] = np.absolute(fit.params[1]) / fit.bse[1]
+            min_lineage = min(lineage_wald.items(), key=operator.itemgetter(1))[0]
+            min_index = lineage_dict.index(min_lineage)
+            lineage_clusters = np.delete(lineage_clusters, min_index, 1)
+            del lineage_dict[min_index]
+        else:
+            lineage_dict = ['MDS' + str(i + 1) for i in range(o.max_dimensions)]
+            lineage_clusters = m
+            for lineage, slope, se in zip(lineage_dict, null_fit.params[1:], null_fit.bse[1:]):
+                lineage_wald[lineage] = np.absolute(slope) / se
+        sys.stderr.write('Writing lineage effects to %s\n' % o.lineage_file)
+        from scipy.stats import norm
+        with open(o.lineage_file, 'w') as lineage_out:
+            lineage_out.write('\t'.join(['lineage', 'wald_test', 'p-value']) + '\n')
+            for lineage, wald in sorted(lineage_wald.items(), key=operator.itemgetter(1),
+                                        reverse=True):
+                pval = 2 * (1 - norm.cdf(wald))
+                lineage_out.write('\t'.join([lineage, str(wald), str(pval)]) + '\n')
+
+    if not o.lmm:
         model = fx.FixedModel(p.values, m, cov, o.continuous, null_fit.llf,
-                              firth_null if not o.continuous else 0.0, device=o.gpu)
+                              firth_null if not o.continuous else 0.0, device=o.gpu,
+                              lineage=(lineage_clusters, cov) if o.lineage else None)
     else:
         from . import lmm as lm
         sys.stderr.write('Setting up LMM\n')
-        p, lmm, h2 = lm.initialise_lmm(p, cov, o.similarity, o.load_lmm, o.save_lmm, None,
+        p, lmm, h2 = lm.initialise_lmm(p, cov, o.similarity, o.load_lmm, o.save_lmm, lineage_samples,
                                        device=o.gpu, precision=o.lmm_precision)
         sys.stderr.write('h^2 = ' + '{0:.2f}'.format(h2) + '\n')
 
@@ -182,6 +228,8 @@ def main(argv=None):
             header += [x for x in cov.columns]
     else:
         header.append('variant_h2')
+    if o.lineage:
+        header.append('lineage')
     if o.print_samples:
         header += ['k-samples', 'nk-samples']
     header.append('notes')
@@ -203,15 +251,21 @@ def main(argv=None):
                                 o.lrt_pvalue, o.min_af, o.max_af, o.max_missing)
         else:
             r = fx.run_fixed_bits(model, batch.bits, batch.missing, o.filter_pvalue, o.lrt_pvalue,
-                                  o.min_af, o.max_af, o.max_missing)
+                                  o.min_af, o.max_af, o.max_missing, lineage=o.lineage)
         flags = r.flags
         # the reference emits each block of --block_size variants as: filtered ones first
         # (LMM only, lmm.py:158-226), then the tested ones; fixed effects keep input order
         for b0 in range(0, batch.n, o.block_size):
             idx = range(b0, min(b0 + o.block_size, batch.n))
+            block_lineage = None
             if o.lmm:
                 order = [j for j in idx if flags[j] & _lib.F_PREFILTER] + \
                         [j for j in idx if not (flags[j] & _lib.F_PREFILTER)]
+                if o.lineage:
+                    # lmm.py:160-162 / :209-211: every variant of a block is reported with the
+                    # lineage of the block's LAST variant (the loop variable `k` is reused)
+                    block_lineage = fx.fit_lineage_effect(lineage_clusters, cov.values,
+                                                          reader.k_vector(batch, idx[-1]), device=o.gpu)
             else:
                 order = idx
             for j in order:
@@ -237,12 +291,15 @@ def main(argv=None):
                                            nan, nan, None, ks, nks, notes, False, True)
                     else:
                         item = var_obj.LMM(batch.names[j], None, r.af[j], r.prep[j], r.pvalue[j],
-                                           r.beta[j], r.bse[j], r.extra[j], None, ks, nks, notes,
-                                           False, False)
+                                           r.beta[j], r.bse[j], r.extra[j], block_lineage, ks, nks,
+                                           notes, False, False)
                 else:
                     item = fx.seer_from_row(r, j, batch.names[j], None, r.af[j], ks, nks)
+                    if o.lineage and not (f & _lib.F_PREFILTER) and r.lineage[j] >= 0:
+                        item = item._replace(max_lineage=int(r.lineage[j]))
                 printed += 1
-                out.write(format_output(item, None, model_name, o.print_samples) + '\n')
+                out.write(format_output(item, lineage_dict if o.lineage else None, model_name,
+                                        o.print_samples) + '\n')
     reader.close()
     if patterns is not None:
         patterns.close()

@@ -75,6 +75,7 @@ int psb_free_model(psb_ctx *c) {
     free_dev(c->d_L); c->d_L = nullptr;
     psb_lmm_tc_free(c);
     free_dev(c->d_Z); c->d_Z = nullptr;
+    free_dev(c->d_Zlin); c->d_Zlin = nullptr; c->q_lin = c->n_lin = 0;
     free_dev(c->d_yv); c->d_yv = nullptr;
     free_dev(c->d_fixed_const); c->d_fixed_const = nullptr;
     free_dev(c->d_sums); c->d_sums = nullptr; c->sums_cap = 0;
@@ -91,10 +92,10 @@ static void free_tables(psb_ctx *c) {
     free_dev(c->d_carriers); free_dev(c->d_missing); free_dev(c->d_af); free_dev(c->d_prep);
     free_dev(c->d_pvalue); free_dev(c->d_beta); free_dev(c->d_bse); free_dev(c->d_extra);
     free_dev(c->d_betas); free_dev(c->d_flags); free_dev(c->d_tab); free_dev(c->d_idx);
-    free_dev(c->d_idx2); free_dev(c->d_a); free_dev(c->d_b); free_dev(c->d_pp);
+    free_dev(c->d_idx2); free_dev(c->d_a); free_dev(c->d_b); free_dev(c->d_pp); free_dev(c->d_lineage);
     c->d_carriers = c->d_missing = nullptr;
     c->d_af = c->d_prep = c->d_pvalue = c->d_beta = c->d_bse = c->d_extra = c->d_betas = nullptr;
-    c->d_flags = nullptr; c->d_tab = nullptr; c->d_idx = c->d_idx2 = nullptr; c->d_a = c->d_b = c->d_pp = nullptr;
+    c->d_flags = nullptr; c->d_tab = nullptr; c->d_idx = c->d_idx2 = nullptr; c->d_a = c->d_b = c->d_pp = nullptr; c->d_lineage = nullptr;
     c->cap = 0; c->betas_cols = 0;
 }
 
@@ -142,6 +143,7 @@ int psb_ensure_capacity(psb_ctx *c, int64_t S, int betas_cols) {
         PSB_CUDA(cudaMalloc(&c->d_tab, cap * 4 * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_idx, (cap + 256) * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_idx2, (cap + 256) * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_lineage, cap * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_a, cap * sizeof(double)));
         PSB_CUDA(cudaMalloc(&c->d_b, cap * sizeof(double)));
         PSB_CUDA(cudaMalloc(&c->d_pp, cap * sizeof(double)));

@@ -26,28 +26,7 @@
 #include "psb_internal.cuh"
 #include "psb_math.cuh"
 
-#define FX_MAXP 16
-
-struct FxArgs {
-    const uint32_t *bits;
-    const double *Z;          // [q][Npad]
-    const uint32_t *y1;       // phenotype == 1 bits
-    const uint32_t *valid;    // sample < N bits
-    int Wrow, Wn, N, Npad;
-    int q;                    // columns of Z
-    int has_x;                // 0: null model (no variant column)
-    double start0;            // log(mean(y) / (1 - mean(y)))
-    int use_warm;             // start Newton from the null-model parameters (exact fallback below)
-    double warm[FX_MAXP];     // null-model parameters (Z order)
-    double null_llf, null_firth, lrt_pvalue;
-    // outputs (indexed by variant id)
-    double *pvalue, *beta, *bse, *intercept, *betas;
-    uint32_t *flags;
-    int *counters;            // [2]: lrt-filtered, [3]: firth list length
-    int32_t *firth_list;
-    // null-fit outputs (has_x == 0): params[q], bse[q], llf, status
-    double *null_out;
-};
+#include "psb_fixed.cuh"
 
 template <int PP>
 struct Tri {
@@ -125,6 +104,53 @@ __device__ __forceinline__ double fx_chol_logdet(const double (&L)[Tri<PP>::SIZE
     return -2.0 * s;
 }
 
+// statsmodels' Newton step matrix X'WX/n - 1e-10 I (the ridge lands on the NEGATIVE definite
+// hessian, base/model.py:fit + base/optimizer.py:_fit_newton) can turn indefinite in separated
+// data, where the reference's LU solve simply carries on.  L D L' without pivoting solves the
+// same system for any matrix with non-zero leading minors; a zero / non-finite pivot is the
+// analogue of numpy's "Singular matrix".  Unit lower L below the diagonal, 1 / d_j on it.
+template <int PP>
+__device__ __forceinline__ bool fx_ldl(double (&A)[Tri<PP>::SIZE]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < PP; ++j) {
+        const double d = A[Tri<PP>::at(j, j)];
+        if (d == 0.0 || !isfinite(d)) ok = false;
+        const double inv = 1.0 / d;
+        A[Tri<PP>::at(j, j)] = inv;
+#pragma unroll
+        for (int i = 0; i < PP; ++i)
+#pragma unroll
+            for (int k = 0; k < PP; ++k)
+                if (i > j && k > j && k <= i)
+                    A[Tri<PP>::at(i, k)] = fma(-A[Tri<PP>::at(i, j)] * inv, A[Tri<PP>::at(k, j)], A[Tri<PP>::at(i, k)]);
+#pragma unroll
+        for (int i = 0; i < PP; ++i)
+            if (i > j) A[Tri<PP>::at(i, j)] *= inv;
+    }
+    return ok;
+}
+
+// b := (L D L')^-1 b
+template <int PP>
+__device__ __forceinline__ void fx_ldl_solve(const double (&L)[Tri<PP>::SIZE], double (&b)[PP]) {
+#pragma unroll
+    for (int i = 0; i < PP; ++i) {
+#pragma unroll
+        for (int k = 0; k < PP; ++k)
+            if (k > i) b[k] = fma(-L[Tri<PP>::at(k, i)], b[i], b[k]);
+    }
+#pragma unroll
+    for (int i = 0; i < PP; ++i) b[i] *= L[Tri<PP>::at(i, i)];
+#pragma unroll
+    for (int ii = 0; ii < PP; ++ii) {
+        const int i = PP - 1 - ii;
+#pragma unroll
+        for (int k = 0; k < PP; ++k)
+            if (k < i) b[k] = fma(-L[Tri<PP>::at(i, k)], b[i], b[k]);
+    }
+}
+
 // Straightforward, register-friendly inverse: solve for each unit vector (PP solves).  Used by
 // the Firth path only; V is returned packed (lower triangle).
 template <int PP>
@@ -176,7 +202,8 @@ template <int PP>
 __device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, int lane,
                                         const double (&beta)[PP], double (&H)[Tri<PP>::SIZE],
                                         double (&g)[PP], double &maxdev, double &llf,
-                                        const bool WITH_LLF) {
+                                        const bool WITH_LLF, const uint32_t *yrow = nullptr) {
+    if (!yrow) yrow = a.y1;
 #pragma unroll
     for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] = 0.0;
 #pragma unroll
@@ -187,22 +214,24 @@ __device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, i
         const uint32_t vw = __ldg(a.valid + w);
         if (!((vw >> lane) & 1u)) continue;
         const uint32_t xw = a.has_x ? __ldg(xrow + w) : 0u;
-        const uint32_t yw = __ldg(a.y1 + w);
+        const uint32_t yw = __ldg(yrow + w);
         const int i = w * 32 + lane;
         double z[PP];
         fx_row<PP>(a, i, (xw >> lane) & 1u, z);
         const double eta = fx_dot<PP>(beta, z);
         const double y = (double)((yw >> lane) & 1u);
-        const double ex = exp(-fabs(eta));            // in (0, 1]
-        const double den = 1.0 / (1.0 + ex);
-        const double pi = eta >= 0.0 ? den : ex * den;
-        const double wgt = ex * den * den;            // pi (1 - pi)
+        // statsmodels' own formulas (Logit.cdf = 1 / (1 + exp(-x)), hessian weight L (1 - L)):
+        // in saturated fits the weight rounds to exactly 0 for eta > ~36.7 and the reference
+        // then meets an exactly singular information matrix -- reproduced, not "improved"
+        const double ex = exp(-eta);
+        const double pi = 1.0 / (1.0 + ex);
+        const double wgt = pi * (1.0 - pi);
         const double r = y - pi;
         maxdev = fmax(maxdev, fabs(r));
         if (WITH_LLF) {
             // log cdf((2y-1) eta) = min(s, 0) - log1p(exp(-|s|)),  s = (2y-1) eta
             const double s = y > 0.5 ? eta : -eta;
-            llf += fmin(s, 0.0) - log1p(ex);
+            llf += fmin(s, 0.0) - log1p(eta >= 0.0 ? ex : 1.0 / ex);
         }
 #pragma unroll
         for (int c = 0; c < PP; ++c) {
@@ -323,16 +352,16 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
                 // earlier (|dbeta| <= 1e-6 leaves an error of order 1e-12)
                 if (it > 0 && !(maxstep > (attempt == 0 ? 1e-6 : 1e-8))) { converged = true; break; }
                 if (it >= maxit) break;                                              // maxiter
-                // H/n + 1e-10 I, solve for the step
+                // (X'WX/n - 1e-10 I) step = score/n: statsmodels' ridge sign, see fx_ldl
 #pragma unroll
                 for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] *= inv_n;
 #pragma unroll
                 for (int c = 0; c < PP; ++c) {
-                    if (c < p) H[Tri<PP>::at(c, c)] += 1e-10;
+                    if (c < p) H[Tri<PP>::at(c, c)] -= 1e-10;
                     g[c] *= inv_n;
                 }
-                if (!fx_chol<PP>(H)) { fail = PSB_F_MATRIX_INV; break; }
-                fx_chol_solve<PP>(H, g);
+                if (!fx_ldl<PP>(H)) { fail = PSB_F_MATRIX_INV; break; }
+                fx_ldl_solve<PP>(H, g);
                 maxstep = 0.0;
 #pragma unroll
                 for (int c = 0; c < PP; ++c) {
@@ -444,10 +473,8 @@ k_fixed_firth(FxArgs a, int n_list) {
                 double z[PP];
                 fx_row<PP>(a, w * 32 + lane, (xw >> lane) & 1u, z);
                 const double eta = fx_dot<PP>(beta, z);
-                const double ex = exp(-fabs(eta));
-                const double den = 1.0 / (1.0 + ex);
-                const double pi = eta >= 0.0 ? den : ex * den;
-                const double wgt = ex * den * den;
+                const double pi = 1.0 / (1.0 + exp(-eta));
+                const double wgt = pi * (1.0 - pi);
                 double quad = 0.0;
 #pragma unroll
                 for (int c = 0; c < PP; ++c) {
@@ -542,6 +569,85 @@ k_fixed_firth(FxArgs a, int n_list) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Lineage effects (model.fit_lineage_effect, model.py:151-199): Logit  k ~ [1, lineages, c]
+// with the VARIANT as the response, statsmodels' default zero start; result = index of the
+// lineage column with the largest Wald statistic |beta| / bse (np.argmax semantics: the first
+// NaN wins), or -1 (None) when the fit fails.  mode 0: every tested variant that produced a
+// fit (model.py:379-380); mode 1: tested variants that passed the lrt filter (lmm.py:208-211).
+// ---------------------------------------------------------------------------------------
+template <int PP>
+__global__ void __launch_bounds__(128)
+k_fixed_lineage(FxArgs a, const int32_t *__restrict__ idx, int n_tested, int mode, int n_lin,
+                const int32_t *__restrict__ nmissing, int32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n_tested; t += warps_total) {
+        const int v = idx[t];
+        const uint32_t f = a.flags[v];
+        const uint32_t skip = mode == 0 ? (PSB_F_PREFILTER | PSB_F_FIRTH_FAIL | PSB_F_MISSING_DATA)
+                                        : (PSB_F_PREFILTER | PSB_F_FILTER);
+        if ((f & skip) || nmissing[v] > 0) {
+            if (lane == 0) out[v] = -1;
+            continue;
+        }
+        const uint32_t *krow = a.bits + (size_t)v * a.Wrow;
+        double beta[PP];
+#pragma unroll
+        for (int c = 0; c < PP; ++c) beta[c] = 0.0;
+        double H[Tri<PP>::SIZE], g[PP];
+        double maxdev, llf, maxstep = INFINITY;
+        bool fail = false;
+        int it = 0;
+        const double inv_n = 1.0 / (double)a.N;
+        for (;;) {
+            fx_eval<PP>(a, krow, lane, beta, H, g, maxdev, llf, false, krow);
+            if (it > 0 && maxdev <= 1e-8) { fail = true; break; }
+            if (it > 0 && !(maxstep > 1e-8)) break;
+            if (it >= 35) break;
+#pragma unroll
+            for (int e = 0; e < Tri<PP>::SIZE; ++e) H[e] *= inv_n;
+#pragma unroll
+            for (int c = 0; c < PP; ++c) {
+                if (c < a.q) H[Tri<PP>::at(c, c)] -= 1e-10;
+                g[c] *= inv_n;
+            }
+            if (!fx_ldl<PP>(H)) { fail = true; break; }
+            fx_ldl_solve<PP>(H, g);
+            maxstep = 0.0;
+#pragma unroll
+            for (int c = 0; c < PP; ++c) {
+                beta[c] += g[c];
+                maxstep = fmax(maxstep, fabs(g[c]));
+            }
+            if (isnan(maxstep)) { fail = true; break; }
+            ++it;
+        }
+        int best = -1;
+        if (!fail && fx_chol<PP>(H)) {
+            double bestval = -INFINITY;
+            bool seen_nan = false;
+#pragma unroll
+            for (int c0 = 1; c0 < PP; ++c0) {
+                if (c0 <= n_lin) {
+                    double e[PP];
+#pragma unroll
+                    for (int c = 0; c < PP; ++c) e[c] = (c == c0) ? 1.0 : 0.0;
+                    fx_chol_solve<PP>(H, e);
+                    const double wald = fabs(beta[c0]) / sqrt(e[c0]);
+                    if (isnan(wald)) {
+                        if (!seen_nan) { best = c0 - 1; seen_nan = true; }
+                    } else if (!seen_nan && (best < 0 || wald > bestval)) {
+                        best = c0 - 1;
+                        bestval = wald;
+                    }
+                }
+            }
+        }
+        if (lane == 0) out[v] = best;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // OLS (statsmodels OLS.fit, call site model.py:300-312) in closed form from the masked sums
 //   u = Z'x, xy = x'y (k_bitsums), G = (Z'Z)^-1, Zty, yQy precomputed:
 //   xQx = x'x - u'Gu, xQy = xy - u'G Zty, beta_k = xQy / xQx, gamma = G (Zty - u beta_k),
@@ -562,11 +668,11 @@ k_fixed_ols(int n_tested, const int32_t *__restrict__ idx, const double *__restr
     const double *G = consts, *Zty = consts + q * q;
     const double yQy = consts[q * q + q];
     const double *s = sums + (size_t)v * C;
-    double u[FX_MAXP];
+    double u[FX_GEN_MAXP];
     u[0] = (double)carriers[v];
     for (int c = 1; c < q; ++c) u[c] = s[col_z1 + c - 1];
     const double xx = u[0], xy = s[col_y];
-    double Gu[FX_MAXP];
+    double Gu[FX_GEN_MAXP];
     double uGu = 0.0, uGz = 0.0;
     for (int c = 0; c < q; ++c) {
         double acc = 0.0;
@@ -658,8 +764,8 @@ static bool host_chol_inverse(std::vector<double> &A, int q) {
 static int fixed_common_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z, const double *y) {
     PSB_REQUIRE(c && Z && y, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(N > 1 && q >= 1, PSB_ERR_ARG, "bad shape N=%d q=%d", N, q);
-    PSB_REQUIRE(q + 1 <= FX_MAXP, PSB_ERR_UNSUPPORTED,
-                "design width %d exceeds the device solver's limit of %d columns", q + 1, FX_MAXP);
+    PSB_REQUIRE(q + 1 <= FX_GEN_MAXP, PSB_ERR_UNSUPPORTED,
+                "design width %d exceeds the device solver's limit of %d columns", q + 1, FX_GEN_MAXP);
     for (int i = 0; i < N; ++i)
         PSB_REQUIRE(Z[(size_t)i * q] == 1.0, PSB_ERR_ARG, "column 0 of Z must be the intercept (ones)");
     PSB_CUDA(cudaSetDevice(c->device));
@@ -753,7 +859,7 @@ static FxArgs fx_args(psb_ctx *c, const psb_params *prm, int has_x) {
     a.q = c->q;
     a.has_x = has_x;
     a.start0 = log(c->y_mean / (1.0 - c->y_mean));
-    a.use_warm = (has_x && (int)c->h_warm.size() == c->q) ? 1 : 0;
+    a.use_warm = (has_x && (int)c->h_warm.size() == c->q && c->q + 1 <= FX_MAXP) ? 1 : 0;
     for (int k = 0; k < FX_MAXP; ++k) a.warm[k] = (a.use_warm && k < c->q) ? c->h_warm[k] : 0.0;
     a.null_llf = c->null_llf;
     a.null_firth = c->null_firth;
@@ -787,7 +893,9 @@ static int fx_dispatch(psb_ctx *c, const FxArgs &a, int n, bool firth) {
     if (p <= 4) firth ? launch_firth<4>(c, a, n, grid) : launch_logit<4>(c, a, n, grid);
     else if (p <= 8) firth ? launch_firth<8>(c, a, n, grid) : launch_logit<8>(c, a, n, grid);
     else if (p <= 12) firth ? launch_firth<12>(c, a, n, grid) : launch_logit<12>(c, a, n, grid);
-    else firth ? launch_firth<16>(c, a, n, grid) : launch_logit<16>(c, a, n, grid);
+    else   // wider designs: generic shared-memory solver (psb_fixed_gen.cu)
+        return psb_fixed_gen_launch(c, a, firth ? (a.has_x ? FXG_FIRTH : FXG_NULL_FIRTH)
+                                                : (a.has_x ? FXG_LOGIT : FXG_NULL), n, 0, 0, nullptr);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
     return PSB_OK;
@@ -878,6 +986,77 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
     PSB_CUDA(cudaEventRecord(c->ev_run1, c->stream));
     c->have_run_ev = true;
     c->ran = true;
+    return PSB_OK;
+}
+
+template <int PP>
+static void launch_lineage(psb_ctx *c, const FxArgs &a, int n, int grid, int mode) {
+    k_fixed_lineage<PP><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n, mode, c->n_lin, c->d_missing,
+                                                     c->d_lineage);
+}
+
+// Lineage design [1, lineage columns, covariates] for model.fit_lineage_effect; call after
+// the model set-up (it shares the context's sample count and phenotype-order bit layout).
+extern "C" int psb_lineage_setup(psb_ctx *c, int32_t N, int32_t q, const double *Zlin,
+                                 int32_t n_lineage) {
+    PSB_REQUIRE(c && Zlin, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->model != PSB_MODEL_NONE && N == c->N, PSB_ERR_STATE,
+                "psb_lineage_setup needs a model set up with the same n_samples");
+    PSB_REQUIRE(q >= 2 && q <= FX_GEN_MAXP && n_lineage >= 1 && n_lineage <= q - 1, PSB_ERR_UNSUPPORTED,
+                "lineage design of %d columns (%d lineages) is outside the solver's range (<= %d)",
+                q, n_lineage, FX_GEN_MAXP);
+    PSB_CUDA(cudaSetDevice(c->device));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    const int Npad = ((N + 31) / 32) * 32;
+    std::vector<double> Zc((size_t)q * Npad, 0.0);
+    for (int i = 0; i < N; ++i) {
+        PSB_REQUIRE(Zlin[(size_t)i * q] == 1.0, PSB_ERR_ARG, "column 0 of the lineage design must be ones");
+        for (int k = 0; k < q; ++k) Zc[(size_t)k * Npad + i] = Zlin[(size_t)i * q + k];
+    }
+    if (c->d_Zlin) cudaFree(c->d_Zlin);
+    c->d_Zlin = nullptr;
+    PSB_CUDA(cudaMalloc(&c->d_Zlin, Zc.size() * sizeof(double)));
+    PSB_CUDA(cudaMemcpy(c->d_Zlin, Zc.data(), Zc.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->q_lin = q;
+    c->n_lin = n_lineage;
+    return PSB_OK;
+}
+
+extern "C" int psb_run_lineage(psb_ctx *c, int32_t mode) {
+    PSB_REQUIRE(c, PSB_ERR_ARG, "ctx is NULL");
+    PSB_REQUIRE(c->d_Zlin && c->ran, PSB_ERR_STATE, "psb_run_lineage needs psb_lineage_setup and a finished psb_run_*");
+    PSB_CUDA(cudaSetDevice(c->device));
+    int h_cnt[8] = {0};
+    PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    const int n = h_cnt[0];
+    if (c->S > 0) PSB_CUDA(cudaMemsetAsync(c->d_lineage, 0xFF, (size_t)c->S * sizeof(int32_t), c->stream));
+    if (n <= 0) return PSB_OK;
+    FxArgs a = fx_args(c, nullptr, 0);
+    a.Z = c->d_Zlin;
+    a.q = c->q_lin;
+    a.Npad = ((c->N + 31) / 32) * 32;
+    a.start0 = 0.0;
+    a.use_warm = 0;
+    const int grid = std::min(psb_div_up(n, 4), c->sm_count * 8);
+    const int p = c->q_lin;
+    if (p <= 4) launch_lineage<4>(c, a, n, grid, mode);
+    else if (p <= 8) launch_lineage<8>(c, a, n, grid, mode);
+    else if (p <= 12) launch_lineage<12>(c, a, n, grid, mode);
+    else return psb_fixed_gen_launch(c, a, FXG_LINEAGE, n, mode, c->n_lin, c->d_lineage);
+    c->launches++;
+    PSB_CUDA(cudaGetLastError());
+    return PSB_OK;
+}
+
+extern "C" int psb_fetch_lineage(psb_ctx *c, int32_t *out) {
+    PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->d_lineage && c->ran, PSB_ERR_STATE, "no lineage results");
+    PSB_CUDA(cudaSetDevice(c->device));
+    if (c->S > 0)
+        PSB_CUDA(cudaMemcpyAsync(out, c->d_lineage, (size_t)c->S * sizeof(int32_t), cudaMemcpyDefault,
+                                 c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
     return PSB_OK;
 }
 

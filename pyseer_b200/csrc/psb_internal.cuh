@@ -87,6 +87,8 @@ struct psb_ctx {
     double *d_fixed_const = nullptr;  // OLS precomputed: see psb_fixed.cu
     std::vector<double> h_ZtZinv; // q x q
     std::vector<double> h_Zty;    // q
+    double *d_Zlin = nullptr;     // lineage design [q_lin][Npad] (model.fit_lineage_effect)
+    int q_lin = 0, n_lin = 0;
     std::vector<double> h_warm;   // null-model Logit parameters (warm start), q
 
     // ---- variants ----
@@ -109,6 +111,7 @@ struct psb_ctx {
     int32_t *d_idx = nullptr;     // compacted tested variant ids (cap + 256)
     int32_t *d_idx2 = nullptr;    // second list (Firth candidates)
     int *d_counters = nullptr;    // [8] device counters
+    int32_t *d_lineage = nullptr; // [cap] index of the strongest lineage, -1 = None
     double *d_a = nullptr;        // [cap] quadratic forms
     double *d_b = nullptr;        // [cap] x'v from the tensor path
     double *d_pp = nullptr;       // [cap] ||Q'x||^2 from the tensor path

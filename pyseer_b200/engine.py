@@ -62,7 +62,7 @@ def notes_from_flags(f):
 class Results(object):
     """Result table of one run (NumPy columns, submission order)."""
     __slots__ = ['carriers', 'missing', 'af', 'prep', 'pvalue', 'beta', 'bse', 'extra', 'betas',
-                 'flags', 'counts']
+                 'flags', 'counts', 'lineage']
 
 
 class Engine(object):
@@ -129,6 +129,25 @@ class Engine(object):
                                        int(bool(continuous)), float(null_llf),
                                        float(null_firth)))
         self.n_samples, self.q, self.model = n, q, 'fixed'
+
+    def lineage_setup(self, lin, cov=None):
+        """Design of model.fit_lineage_effect: [1, lin, cov] (model.py:176-180)."""
+        lin = np.asarray(lin, dtype=float)
+        cols = [np.ones((lin.shape[0], 1)), lin]
+        if cov is not None:
+            cov = np.asarray(getattr(cov, 'values', cov), dtype=float)
+            if cov.ndim == 2 and cov.shape[0] == lin.shape[0] and cov.shape[1] > 0:
+                cols.append(cov)
+        Z = np.ascontiguousarray(np.concatenate(cols, axis=1))
+        check(self.lib.psb_lineage_setup(self._ctx, Z.shape[0], Z.shape[1], self._dptr(Z),
+                                         lin.shape[1]))
+
+    def run_lineage(self, lmm_rule=False):
+        """Index of the most associated lineage per submitted variant (-1 = None)."""
+        check(self.lib.psb_run_lineage(self._ctx, 1 if lmm_rule else 0))
+        out = np.empty(self.n_variants, dtype=np.int32)
+        check(self.lib.psb_fetch_lineage(self._ctx, out.ctypes.data_as(c_void_p)))
+        return out
 
     def fit_null(self, Z, y, continuous, firth=False, start_zero=False):
         """model.fit_null on the device.  Returns (params, bse, llf, status_flags)."""
@@ -211,6 +230,7 @@ class Engine(object):
             out.betas = r.betas.ctypes.data_as(c_void_p)
         check(self.lib.psb_fetch(self._ctx, byref(out)))
         r.counts = self.counts()
+        r.lineage = None
         return r
 
     def fetch_into(self, pointers):

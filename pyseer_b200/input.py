@@ -329,3 +329,20 @@ class VcfReader(object):
 
     sample_lists = VariantReader.sample_lists
     k_vector = VariantReader.k_vector
+
+
+def load_lineage(infile, p):
+    """input.py:139-177: `sample<TAB>cluster` file -> (binary design matrix with one column
+    per cluster in sorted label order, list of labels); rows follow the phenotype order."""
+    rows = [x.rstrip().split() for x in open(infile) if x.strip()]
+    lin = pd.Series([r[1] for r in rows], index=[str(r[0]) for r in rows])
+    if np.any(lin.index.duplicated()):
+        lin = lin.loc[~lin.index.duplicated()]
+    if len(p.index.difference(lin.index)) > 0:
+        sys.stderr.write('All samples with a phenotype must be present in lineage file\n')
+        sys.exit(1)
+    lin = lin.loc[p.index.intersection(lin.index)]
+    labels = sorted(set(lin.values))
+    design = np.array([[1 if x == lab else 0 for x in lin.values] for lab in labels]).T
+    assert np.all(lin.index == p.index)
+    return design, labels

@@ -73,7 +73,7 @@ class FixedModel(object):
     """Per-run state shared by every ``fixed_effects_regression`` call: covariate design,
     phenotype, null log-likelihoods -- resident on the GPU."""
 
-    def __init__(self, p, m, cov, continuous, null_res, null_firth, device=0):
+    def __init__(self, p, m, cov, continuous, null_res, null_firth, device=0, lineage=None):
         self.p = np.asarray(p, dtype=float).reshape(-1)
         self.Z = _design(self.p, m, cov)
         self.continuous = bool(continuous)
@@ -82,18 +82,25 @@ class FixedModel(object):
         self.engine.fixed_setup(self.Z, self.p, self.continuous,
                                 float(null_llf) if null_llf is not None and not continuous else 0.0,
                                 float(null_firth) if isinstance(null_firth, float) else 0.0)
+        if lineage is not None:
+            # (lineage design, covariates) of model.fit_lineage_effect, fitted per variant in
+            # one batched launch after the regression (model.py:379-380)
+            self.engine.lineage_setup(lineage[0], lineage[1])
 
     def close(self):
         self.engine.close()
 
 
 def run_fixed_bits(model, bits, missing, filter_pvalue, lrt_pvalue, min_af=-1.0, max_af=2.0,
-                   max_missing=2.0):
-    """Batched model.fixed_effects_regression over packed rows -> result table."""
+                   max_missing=2.0, lineage=False):
+    """Batched model.fixed_effects_regression over packed rows -> result table
+    (``.lineage``: index of the strongest lineage per variant, -1 = None, when asked)."""
     eng = model.engine
     eng.submit(bits, missing)
     eng.run_fixed(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, model.continuous)
-    return eng.fetch()
+    r = eng.fetch()
+    r.lineage = eng.run_lineage(False) if lineage else None
+    return r
 
 
 _cache = {'key': None, 'model': None}
