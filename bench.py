@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--model', default='lmm', choices=['lmm', 'fixed'],
+    ap.add_argument('--model', default='lmm', choices=['lmm', 'fixed', 'fixed-cont'],
                     help="lmm: BASELINE configs[3] (headline); fixed: configs[2], logistic + Firth, "
                          "N=2000, 10 MDS covariates, 10M k-mers")
     ap.add_argument('--samples', type=int, default=0, help='0 = the config default')
@@ -114,7 +114,7 @@ def _cpu_fixed_block(b):
         ok = 0.01 <= af[s] <= 0.99
         o = fo.fixed_effects_regression('k', _CPU['y'] if ok else None, x[s], _CPU['m'], none, af[s],
                                         'p', False, None, 1.0, 1.0, _CPU['null_llf'],
-                                        _CPU['null_firth'], [], [], False)
+                                        _CPU['null_firth'], [], [], _CPU.get('continuous', False))
         tested += not o.prefilter
     return tested
 
@@ -123,12 +123,12 @@ class CpuFixedPath(object):
     """Oracle port of model.fixed_effects_regression, one variant per task as pyseer's
     starmap does (__main__.py:777-780), `cores` workers."""
 
-    def __init__(self, n, m, y, null_llf, null_firth, cores, ys, per_block=150):
+    def __init__(self, n, m, y, null_llf, null_firth, cores, ys, per_block=150, continuous=False):
         import multiprocessing as mp
         from pyseer_b200.engine import synth_host
         self.cores = cores
         self.per_block = per_block
-        _CPU.update(n=n, y=y, m=m, null_llf=null_llf, null_firth=null_firth)
+        _CPU.update(n=n, y=y, m=m, null_llf=null_llf, null_firth=null_firth, continuous=continuous)
         _CPU['blocks'] = [synth_host(SEED, b * per_block, per_block, n, 0.02, 0.98, 1000, ys)
                           for b in range(cores)]
         self.pool = mp.get_context('fork').Pool(cores, initializer=_cpu_init)
@@ -458,13 +458,69 @@ class FixedWorkload(object):
                 'traffic': None}
 
 
+class FixedContWorkload(FixedWorkload):
+    """Fixed effects with a continuous phenotype: closed-form OLS t-test per variant."""
+    name = 'fixed-cont'
+    continuous = True
+
+    def __init__(self, a, n, kpg, world):
+        FixedWorkload.__init__(self, a, n, kpg, world)
+        self.config['workload'] = self.config['workload'].replace('logistic + Firth', 'OLS (continuous)')
+
+    def build_state(self):
+        rng = np.random.RandomState(SEED % (2 ** 31) + 3)
+        m, _ = make_fixed_problem(self.n, self.DIMS)
+        y = m[:, :3].sum(1) + rng.normal(size=self.n)
+        return {'m': m, 'y': y, 'meta': np.array([0.0, 0.0])}
+
+    def y_sign(self, st):
+        return np.where(st['y'] > np.median(st['y']), 1, -1).astype(np.int8)
+
+    def cpu_path(self, st, cores, ys):
+        cp = CpuFixedPath(self.n, st['m'], st['y'], 0.0, 0.0, cores, ys, per_block=1000, continuous=True)
+        return cp, 'blocks of 1000 k-mers per worker, oracle/fixed_oracle.fixed_effects_regression (OLS)'
+
+    def setup_engine(self, eng, st):
+        eng.fixed_setup(np.c_[np.ones(self.n), st['m']], st['y'], True, 0.0, 0.0)
+
+    def run(self, eng):
+        eng.run_fixed(min_af=0.01, max_af=0.99, max_missing=0.05, filter_pvalue=1.0, lrt_pvalue=1.0,
+                      continuous=True)
+
+    def check(self, st, bits_head, cols):
+        from oracle import fixed_oracle as fo
+        from pyseer_b200.engine import unpack_rows
+        x = unpack_rows(bits_head[:500], self.n).astype(float)
+        none = np.empty((0, 0))
+        errp = errb = 0.0
+        for s in range(x.shape[0]):
+            o = fo.fixed_effects_regression('k', st['y'], x[s], st['m'], none, 0.5, 'p', False, None,
+                                            1.0, 1.0, None, 0.0, [], [], True)
+            if o.prefilter or not np.isfinite(o.pvalue) or o.pvalue < 1e-290:
+                continue
+            errp = max(errp, abs(cols['pvalue'][s] / o.pvalue - 1))
+            errb = max(errb, abs(cols['beta'][s] / o.kbeta - 1))
+        return {'variants': int(x.shape[0]), 'max_rel_err_pvalue': float(errp),
+                'max_rel_err_beta': float(errb)}
+
+    def roofline(self, tested, k_ms, run_ms, W, pk, pk_kind):
+        q = self.DIMS + 1
+        bytes_alg = tested * (W * 4 + 8.0 * (6 + q))
+        achieved = bytes_alg / (run_ms / 1e3) / 1e9
+        return {'bound': 'hbm', 'kernel': 'k_bitstats + k_lmm_quadform_tc (linear tile) + k_fixed_ols (whole run)', 'achieved': achieved,
+                'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'],
+                'peak_source': '%s STREAM-style copy bandwidth (MEASURED_PEAKS.json); algorithmic bytes '
+                               '= packed row + result row per tested variant' % pk_kind,
+                'kernel_ms': k_ms, 'run_ms': run_ms, 'traffic': None}
+
+
 # ----------------------------------------------------------------------------------------
 def main():
     a = parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    wcls = LmmWorkload if a.model == 'lmm' else FixedWorkload
+    wcls = {'lmm': LmmWorkload, 'fixed': FixedWorkload, 'fixed-cont': FixedContWorkload}[a.model]
     n = a.samples or wcls.default_n
     kpg = a.kmers_per_gpu or wcls.default_kpg
     wl = wcls(a, n, kpg, world)

@@ -810,6 +810,11 @@ extern "C" int psb_fixed_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z
     if (rc) return rc;
     PSB_CUDA(cudaMalloc(&c->d_cols, cols.size() * sizeof(double)));
     PSB_CUDA(cudaMemcpy(c->d_cols, cols.data(), cols.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (continuous && q * 2 <= 32) {
+        // y'x and Z'x through one linear tensor pass instead of q masked fp64 column sums
+        rc = psb_tc_linear_setup(c, cols.data(), q, c->Npad);
+        if (rc) return rc;
+    }
     if (continuous) {
         // G = (Z'Z)^-1, Zty, yQy
         std::vector<double> G((size_t)q * q, 0.0), Zty(q, 0.0);
@@ -943,9 +948,11 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
     PSB_CUDA(cudaEventRecord(c->ev_run0, c->stream));
     if (c->S > 0 && c->q > 1)
         PSB_CUDA(cudaMemsetAsync(c->d_betas, 0xFF, (size_t)c->S * (c->q - 1) * sizeof(double), c->stream));
-    // stats: binary needs only the popcount table; continuous needs y'x and Z'x as well
-    if (!c->continuous && !c->d_miss && psb_bitstats_fits(c))
-        rc = psb_launch_bitstats(c, 0);
+    // stats: binary needs only the popcount table; continuous needs the Welch sums here and
+    // y'x, Z'x for the regression -- from the linear tensor pass when it is set up
+    const bool tc_linear = c->continuous && c->tmap_Lq && !c->d_miss && psb_bitstats_fits(c);
+    if (!c->d_miss && psb_bitstats_fits(c) && (!c->continuous || tc_linear))
+        rc = psb_launch_bitstats(c, c->continuous);
     else
         rc = psb_launch_bitsums(c);
     if (rc) return rc;
@@ -964,6 +971,10 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
     PSB_CUDA(cudaEventRecord(c->ev_k0, c->stream));
     if (n_tested > 0) {
         if (c->continuous) {
+            if (tc_linear) {
+                rc = psb_tc_run(c, n_tested, c->d_sums, c->C);
+                if (rc) return rc;
+            }
             k_fixed_ols<<<psb_div_up(n_tested, 256), 256, 0, c->stream>>>(
                 n_tested, c->d_idx, c->d_sums, c->C, c->col_b, c->col_q0, c->q, c->N, c->d_carriers,
                 c->d_fixed_const, prm->lrt_pvalue, c->d_pvalue, c->d_beta, c->d_bse, c->d_extra,

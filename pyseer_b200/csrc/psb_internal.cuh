@@ -132,6 +132,8 @@ int psb_launch_bitstats(psb_ctx *ctx, int continuous);
 // psb_lmm_tc.cu
 int psb_lmm_tc_setup(psb_ctx *ctx, const double *h_v, const double *h_Q, int r, int ldq);
 int psb_lmm_tc_run(psb_ctx *ctx, int n_tested);
+int psb_tc_linear_setup(psb_ctx *ctx, const double *cols, int ncols, int ld);
+int psb_tc_run(psb_ctx *ctx, int n_tested, double *lin_out, int lin_ld);
 void psb_lmm_tc_free(psb_ctx *ctx);
 
 static inline int psb_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -181,6 +181,8 @@ struct TcArgs {
     double *b_out;            // [variant id]  x'v            (special tile; may be null)
     double *pp_out;           // [variant id]  || Q'x ||^2    (special tile; may be null)
     int n_special;            // hi/lo column pairs in the special tile (0 = no special tile)
+    double *lin_out;          // raw pair sums x'u_p -> lin_out[variant id * lin_ld + p] (may be null)
+    int lin_ld;
     int Wrow;                 // words per packed row in global memory
     int n_tested;
     int nks;                  // K stages (Kpad / 128)
@@ -357,6 +359,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         uint32_t phacc = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             double a = 0.0, bsum = 0.0, pp = 0.0;
+            const int t_own = tile * TC_TILE_V + v;
+            const int row_own = t_own < args.n_tested ? args.idx[t_own] : -1;
             for (int jt = 0; jt < args.jtiles; ++jt) {
                 mbar_wait(smem_u32(&accFull[acc]), phacc);
                 tc_fence_after();
@@ -395,6 +399,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                                 int pair = (c0 + c) >> 1;
                                 if (pair == 0) bsum = val;
                                 else if (pair <= args.n_special - 1) pp = fma(val, val, pp);
+                                if (args.lin_out && row_own >= 0 && pair < args.n_special)
+                                    args.lin_out[(size_t)row_own * args.lin_ld + pair] = val;
                             }
                         }
                     }
@@ -404,13 +410,11 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 if (lane == 0) mbar_arrive(smem_u32(&accEmpty[acc]));
                 if (++acc == 2) { acc = 0; phacc ^= 1; }
             }
-            int t = tile * TC_TILE_V + v;
-            if (t < args.n_tested) {
-                int row = args.idx[t];
-                args.a_out[row] = a;
-                if (jt_special >= 0) {
-                    args.b_out[row] = bsum;
-                    args.pp_out[row] = pp;
+            if (row_own >= 0) {
+                if (args.a_out) args.a_out[row_own] = a;
+                if (jt_special >= 0 && args.b_out) {
+                    args.b_out[row_own] = bsum;
+                    args.pp_out[row_own] = pp;
                 }
             }
         }
@@ -494,6 +498,31 @@ static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
     return PSB_OK;
 }
 
+// Tensor map over Lq: inner dim = samples (bytes), outer = (jtile, slice, comp) rows.
+static int tc_make_tensor_map(psb_ctx *c, int Jall, int nsl) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    PSB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, PSB_ERR_CUDA,
+                "cuTensorMapEncodeTiled not available from the driver");
+    CUtensorMap *tm = new CUtensorMap;
+    cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jall * nsl};
+    cuuint64_t gstr[1] = {(cuuint64_t)c->Kpad};
+    cuuint32_t box[2] = {TC_KSTAGE, (cuuint32_t)(TC_JT * nsl)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        delete tm;
+        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        return PSB_ERR_CUDA;
+    }
+    c->tmap_Lq = tm;
+    return PSB_OK;
+}
+
 // Special tile (host side, exact): each source column u (v = M y, then the orthonormal
 // covariate basis Q_e) becomes a pair of sliced columns hi = quantised u and lo = quantised
 // (u - hi), so that g_hi s_hi + g_lo s_lo reproduces x'u to 2 (8k-2) bits.
@@ -562,39 +591,49 @@ int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, in
     PSB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_expo);
 
-    // tensor map over Lq: inner dim = samples (bytes), outer = (jtile, slice, comp) rows
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    PSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    PSB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, PSB_ERR_CUDA,
-                "cuTensorMapEncodeTiled not available from the driver");
-    CUtensorMap *tm = new CUtensorMap;
-    cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jall * nsl};
-    cuuint64_t gstr[1] = {(cuuint64_t)c->Kpad};
-    cuuint32_t box[2] = {TC_KSTAGE, (cuuint32_t)(TC_JT * nsl)};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult cr = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
-                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        delete tm;
-        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-        return PSB_ERR_CUDA;
-    }
-    c->tmap_Lq = tm;
-    return PSB_OK;
+    return tc_make_tensor_map(c, Jall, nsl);
 }
 
-int psb_lmm_tc_run(psb_ctx *c, int n_tested) {
+// Linear-only operand: `ncols` columns (each N doubles, column e at cols + e * ld) as hi/lo
+// sliced pairs in one component tile.  Used by the fixed-effects OLS path for y'x and Z'x
+// (model.py:300-312 needs nothing else from the variant): one tensor pass replaces ncols
+// masked fp64 column sums per variant.
+int psb_tc_linear_setup(psb_ctx *c, const double *cols, int ncols, int ld) {
+    const int nsl = 5;
+    PSB_REQUIRE(ncols >= 1 && ncols * 2 <= TC_JT, PSB_ERR_UNSUPPORTED, "too many linear columns");
+    psb_lmm_tc_free(c);
+    const int N = c->N;
+    c->n_slices = nsl;
+    c->tc_special = ncols;
+    c->jtiles = 1;
+    c->Kpad = ((N + TC_KSTAGE - 1) / TC_KSTAGE) * TC_KSTAGE;
+    const size_t tile_bytes = (size_t)nsl * TC_JT * c->Kpad;
+    std::vector<int8_t> tile(tile_bytes, 0);
+    std::vector<double> sc(TC_JT, 0.0);
+    for (int e = 0; e < ncols; ++e)
+        tc_special_column(cols + (size_t)e * ld, N, nsl, c->Kpad, tile.data(), 2 * e, sc.data());
+    PSB_CUDA(cudaMalloc(&c->d_Lq, tile_bytes));
+    PSB_CUDA(cudaMalloc(&c->d_scale2, TC_JT * sizeof(double)));
+    PSB_CUDA(cudaMemcpy(c->d_Lq, tile.data(), tile_bytes, cudaMemcpyHostToDevice));
+    PSB_CUDA(cudaMemcpy(c->d_scale2, sc.data(), TC_JT * sizeof(double), cudaMemcpyHostToDevice));
+    return tc_make_tensor_map(c, TC_JT, nsl);
+}
+
+int psb_lmm_tc_run(psb_ctx *c, int n_tested) { return psb_tc_run(c, n_tested, nullptr, 0); }
+
+// lin_out != null: linear-only use (psb_tc_linear_setup): the pair sums go to
+// lin_out[variant * lin_ld + pair] and no quadratic form is produced.
+int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     const int nsl = c->n_slices;
     TcArgs a;
     a.bits = c->d_bits;
     a.idx = c->d_idx;
     a.scale2 = c->d_scale2;
-    a.a_out = c->d_a;
-    a.b_out = c->d_b;
-    a.pp_out = c->d_pp;
+    a.a_out = lin_out ? nullptr : c->d_a;
+    a.b_out = lin_out ? nullptr : c->d_b;
+    a.pp_out = lin_out ? nullptr : c->d_pp;
+    a.lin_out = lin_out;
+    a.lin_ld = lin_ld;
     a.n_special = c->tc_special;
     a.Wrow = c->Wrow;
     a.n_tested = n_tested;
