@@ -80,6 +80,7 @@ int psb_free_model(psb_ctx *c) {
     free_dev(c->d_fixed_const); c->d_fixed_const = nullptr;
     free_dev(c->d_sums); c->d_sums = nullptr; c->sums_cap = 0;
     c->h_warm.clear();
+    c->logit_first_step = false;
     c->model = PSB_MODEL_NONE;
     c->ran = false;
     return PSB_OK;

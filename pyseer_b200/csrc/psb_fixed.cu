@@ -183,8 +183,8 @@ __device__ __forceinline__ void fx_row(const FxArgs &a, int i, uint32_t xbit, do
 
 // beta'z with four interleaved accumulation chains (shorter dependency chain than one FMA
 // chain of length PP; the summation order is irrelevant at the 1e-6 tolerance).
-template <int PP>
-__device__ __forceinline__ double fx_dot(const double (&beta)[PP], const double (&z)[PP]) {
+template <int PP, class BetaT>
+__device__ __forceinline__ double fx_dot(const BetaT &beta, const double (&z)[PP]) {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
     for (int c = 0; c < PP; c += 4) {
@@ -198,9 +198,10 @@ __device__ __forceinline__ double fx_dot(const double (&beta)[PP], const double 
 
 // One pass over the samples at parameters beta: X'WX (packed), score X'(y - pi),
 // max |y - pi| and the log-likelihood.  All lanes return the full sums.
-template <int PP>
+// (BetaT: a register array or a pointer to the warp's shared-memory copy of the parameters)
+template <int PP, class BetaT>
 __device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, int lane,
-                                        const double (&beta)[PP], double (&H)[Tri<PP>::SIZE],
+                                        const BetaT &beta, double (&H)[Tri<PP>::SIZE],
                                         double (&g)[PP], double &maxdev, double &llf,
                                         const bool WITH_LLF, const uint32_t *yrow = nullptr) {
     if (!yrow) yrow = a.y1;
@@ -218,7 +219,7 @@ __device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, i
         const int i = w * 32 + lane;
         double z[PP];
         fx_row<PP>(a, i, (xw >> lane) & 1u, z);
-        const double eta = fx_dot<PP>(beta, z);
+        const double eta = fx_dot<PP, BetaT>(beta, z);
         const double y = (double)((yw >> lane) & 1u);
         // statsmodels' own formulas (Logit.cdf = 1 / (1 + exp(-x)), hessian weight L (1 - L)):
         // in saturated fits the weight rounds to exactly 0 for eta > ~36.7 and the reference
@@ -256,9 +257,9 @@ __device__ __forceinline__ void fx_eval(const FxArgs &a, const uint32_t *xrow, i
 }
 
 // log-likelihood only
-template <int PP>
+template <int PP, class BetaT>
 __device__ __forceinline__ double fx_loglike(const FxArgs &a, const uint32_t *xrow, int lane,
-                                             const double (&beta)[PP]) {
+                                             const BetaT &beta) {
     double llf = 0.0;
     for (int w = 0; w < a.Wn; ++w) {
         const uint32_t vw = __ldg(a.valid + w);
@@ -267,7 +268,7 @@ __device__ __forceinline__ double fx_loglike(const FxArgs &a, const uint32_t *xr
         const uint32_t yw = __ldg(a.y1 + w);
         double z[PP];
         fx_row<PP>(a, w * 32 + lane, (xw >> lane) & 1u, z);
-        const double eta = fx_dot<PP>(beta, z);
+        const double eta = fx_dot<PP, BetaT>(beta, z);
         const double s = ((yw >> lane) & 1u) ? eta : -eta;
         llf += fmin(s, 0.0) - log1p(exp(-fabs(s)));
     }
@@ -279,8 +280,8 @@ __device__ __forceinline__ void fx_write_failed(const FxArgs &a, int v, uint32_t
 }
 
 // Publishes a fitted variant: LRT against the matching null, lrt filter, result columns.
-template <int PP>
-__device__ __forceinline__ void fx_publish(const FxArgs &a, int v, uint32_t f, const double (&beta)[PP],
+template <int PP, class BetaT>
+__device__ __forceinline__ void fx_publish(const FxArgs &a, int v, uint32_t f, const BetaT &beta,
                                            double bse, double fit_llf, double null_llf) {
     const double lrstat = -2.0 * (null_llf - fit_llf);          // model.py:336, :366
     double p = 1.0;
@@ -310,6 +311,10 @@ __device__ __forceinline__ void fx_publish(const FxArgs &a, int v, uint32_t f, c
 template <int PP>
 __global__ void __launch_bounds__(128)
 k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
+    // the parameter vector lives in shared memory (one copy per warp, read by broadcast in the
+    // sample loop): 2 PP registers less pressure on the X'WX accumulators
+    __shared__ double s_beta[4][PP];
+    double *beta = s_beta[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * (blockDim.x >> 5);
     const int p = a.q + (a.has_x ? 1 : 0);
@@ -322,7 +327,6 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
             continue;
         }
         const uint32_t *xrow = a.bits + (size_t)v * a.Wrow;
-        double beta[PP];
         double H[Tri<PP>::SIZE], g[PP];
         double maxdev, llf = NAN, maxstep = INFINITY;
         uint32_t fail = 0;
@@ -335,9 +339,43 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
         // fit is redone from the reference's start vector with the reference's 35-step rule
         // (attempt 1), so separation / non-convergence are flagged exactly as statsmodels does.
         for (int attempt = (a.use_warm && a.has_x) ? 0 : 1; attempt < 2; ++attempt) {
+            __syncwarp();
+            if (lane < PP) beta[lane] = (attempt == 0) ? (lane < a.q ? a.warm[lane] : 0.0)
+                                                       : (lane == 0 ? a.start0 : 0.0);
+            __syncwarp();
+            if (attempt == 0 && a.sums) {
+                // At the null parameters the Z-block of X'WX and the Z-part of the score are the
+                // same for every variant (Hzz, 0); the k-border is a set of masked sums that the
+                // linear tensor tile already delivered.  First Newton step in closed form:
+                //   schur = hxx - hx' Hzz^-1 hx,  d_k = g_k / schur,  d_z = -Hzz^-1 hx d_k
+                const double *sv = a.sums + (size_t)v * a.sums_ld;
+                double hx[PP], tz[PP];
 #pragma unroll
-            for (int c = 0; c < PP; ++c) beta[c] = (attempt == 0 && c < a.q) ? a.warm[c] : 0.0;
-            if (attempt == 1) beta[0] = a.start0;
+                for (int c = 0; c < PP; ++c) hx[c] = (c < a.q) ? sv[c] : 0.0;
+                const double gx = sv[a.q];
+                double quad = 0.0;
+#pragma unroll
+                for (int c = 0; c < PP; ++c) {
+                    double acc = 0.0;
+                    if (c < a.q) {
+#pragma unroll
+                        for (int d = 0; d < PP; ++d)
+                            if (d < a.q) acc = fma(__ldg(a.HzzInv + c * a.q + d), hx[d], acc);
+                    }
+                    tz[c] = acc;
+                    quad = fma(acc, hx[c], quad);
+                }
+                const double dk = gx / (hx[0] - quad);        // hxx = sum of w0 over carriers = hx[0]
+                if (isfinite(dk)) {
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < PP; ++c) {
+                        if (lane == 0 && c < a.q) beta[c] -= tz[c] * dk;
+                        if (lane == 0 && c == a.q) beta[c] = dk;
+                    }
+                    __syncwarp();
+                }
+            }
             const int maxit = attempt == 0 ? 12 : 35;
             fail = 0;
             it = 0;
@@ -363,11 +401,13 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
                 if (!fx_ldl<PP>(H)) { fail = PSB_F_MATRIX_INV; break; }
                 fx_ldl_solve<PP>(H, g);
                 maxstep = 0.0;
+                __syncwarp();
 #pragma unroll
                 for (int c = 0; c < PP; ++c) {
-                    beta[c] += g[c];
+                    if (lane == 0) beta[c] += g[c];
                     maxstep = fmax(maxstep, fabs(g[c]));
                 }
+                __syncwarp();
                 if (isnan(maxstep)) { fail = PSB_F_MATRIX_INV; break; }
                 ++it;
             }
@@ -847,6 +887,32 @@ extern "C" int psb_fixed_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z
         rc = fx_run_null(c, 0, h);
         if (rc) return rc;
         if (h[2 * q + 1] == 0.0) c->h_warm.assign(h.begin(), h.begin() + q);
+        c->logit_first_step = false;
+        if ((int)c->h_warm.size() == q && q + 1 <= FX_MAXP && (q + 1) * 2 <= 32) {
+            // operands of the closed-form first Newton step: Hzz^-1 and the masked-sum columns
+            // [w0 z_0 .. w0 z_{q-1}, y - pi0] for the linear tensor tile
+            std::vector<double> Hzz((size_t)q * q, 0.0), lc((size_t)(q + 1) * c->Npad, 0.0);
+            for (int i = 0; i < N; ++i) {
+                const double *zi = Z + (size_t)i * q;
+                double eta = 0.0;
+                for (int k = 0; k < q; ++k) eta += c->h_warm[k] * zi[k];
+                const double pi = 1.0 / (1.0 + exp(-eta));
+                const double w0 = pi * (1.0 - pi);
+                for (int a2 = 0; a2 < q; ++a2) {
+                    lc[(size_t)a2 * c->Npad + i] = w0 * zi[a2];
+                    for (int b2 = 0; b2 < q; ++b2) Hzz[a2 * q + b2] += w0 * zi[a2] * zi[b2];
+                }
+                lc[(size_t)q * c->Npad + i] = y[i] - pi;
+            }
+            if (host_chol_inverse(Hzz, q)) {
+                rc = psb_tc_linear_setup(c, lc.data(), q + 1, c->Npad);
+                if (rc) return rc;
+                PSB_CUDA(cudaMalloc(&c->d_fixed_const, Hzz.size() * sizeof(double)));
+                PSB_CUDA(cudaMemcpy(c->d_fixed_const, Hzz.data(), Hzz.size() * sizeof(double),
+                                    cudaMemcpyHostToDevice));
+                c->logit_first_step = true;
+            }
+        }
     }
     return PSB_OK;
 }
@@ -878,6 +944,9 @@ static FxArgs fx_args(psb_ctx *c, const psb_params *prm, int has_x) {
     a.counters = c->d_counters;
     a.firth_list = c->d_idx2;
     a.null_out = nullptr;
+    a.sums = nullptr;
+    a.HzzInv = nullptr;
+    a.sums_ld = 0;
     return a;
 }
 
@@ -983,6 +1052,13 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
             PSB_CUDA(cudaGetLastError());
         } else {
             FxArgs a = fx_args(c, prm, 1);
+            if (c->logit_first_step && a.use_warm && !c->d_miss) {
+                rc = psb_tc_run(c, n_tested, c->d_sums, c->C);
+                if (rc) return rc;
+                a.sums = c->d_sums;
+                a.sums_ld = c->C;
+                a.HzzInv = c->d_fixed_const;
+            }
             rc = fx_dispatch(c, a, n_tested, false);
             if (rc) return rc;
             PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost,

@@ -18,6 +18,11 @@ struct FxArgs {
     double start0;            // log(mean(y) / (1 - mean(y)))
     int use_warm;             // start Newton from the null-model parameters (exact fallback below)
     double warm[FX_MAXP];     // null-model parameters (Z order)
+    // first Newton step of the warm attempt from masked sums (linear tensor tile): per variant
+    // sums[v * sums_ld + a] = sum over carriers of w0 z_a (a < q), [q] = sum of y - pi0;
+    // HzzInv = (Z' W0 Z)^-1 at the null fit (q x q).  Null when not available.
+    const double *sums, *HzzInv;
+    int sums_ld;
     double null_llf, null_firth, lrt_pvalue;
     // outputs (indexed by variant id)
     double *pvalue, *beta, *bse, *intercept, *betas;

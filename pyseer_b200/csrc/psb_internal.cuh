@@ -89,6 +89,7 @@ struct psb_ctx {
     std::vector<double> h_Zty;    // q
     double *d_Zlin = nullptr;     // lineage design [q_lin][Npad] (model.fit_lineage_effect)
     int q_lin = 0, n_lin = 0;
+    bool logit_first_step = false; // closed-form first Newton step operands are set up
     std::vector<double> h_warm;   // null-model Logit parameters (warm start), q
 
     // ---- variants ----
