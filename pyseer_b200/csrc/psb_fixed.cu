@@ -332,6 +332,7 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
         uint32_t fail = 0;
         int it = 0;
         bool have_llf = false;
+        double fast_bse = -1.0;
         const double inv_n = 1.0 / (double)a.N;
         // The log-likelihood is concave, so a converged Newton run ends at the same (unique)
         // maximiser whatever the start.  Attempt 0 starts from the null-model parameters and
@@ -399,23 +400,51 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
                     g[c] *= inv_n;
                 }
                 if (!fx_ldl<PP>(H)) { fail = PSB_F_MATRIX_INV; break; }
+                double gs[PP];                       // score / n, kept for the llf correction
+#pragma unroll
+                for (int c = 0; c < PP; ++c) gs[c] = g[c];
                 fx_ldl_solve<PP>(H, g);
                 maxstep = 0.0;
+                double gd = 0.0;
                 __syncwarp();
 #pragma unroll
                 for (int c = 0; c < PP; ++c) {
                     if (lane == 0) beta[c] += g[c];
                     maxstep = fmax(maxstep, fabs(g[c]));
+                    gd = fma(gs[c], g[c], gd);
                 }
                 __syncwarp();
                 if (isnan(maxstep)) { fail = PSB_F_MATRIX_INV; break; }
                 ++it;
+                if (attempt == 0 && a.has_x && want_llf && maxstep <= 1e-7) {
+                    // The step just taken is below 1e-7: the fit has converged, and everything
+                    // the result needs follows from THIS evaluation without another pass --
+                    //   llf(beta + d) = llf(beta) + g'd/2 + O(d^3)   (since (X'WX) d = g),
+                    //   bse from the factored matrix (X'WX differs by O(d) relative).
+                    double e[PP];
+#pragma unroll
+                    for (int c = 0; c < PP; ++c) e[c] = (c == a.q) ? 1.0 : 0.0;
+                    fx_ldl_solve<PP>(H, e);
+                    double var_x = 0.0;
+#pragma unroll
+                    for (int c = 0; c < PP; ++c)
+                        if (c == a.q) var_x = e[c] * inv_n;
+                    if (var_x > 0.0 && isfinite(var_x)) {
+                        fast_bse = sqrt(var_x);
+                        llf += 0.5 * (double)a.N * gd;
+                        converged = true;
+                        break;
+                    }
+                }
             }
             if (attempt == 0 && converged && !fail) break;     // accept the warm-started fit
+            fast_bse = -1.0;
         }
         double bse_x = NAN;
         double bse_all[PP];
-        if (!fail) {
+        if (!fail && fast_bse > 0.0) {
+            bse_x = fast_bse;
+        } else if (!fail) {
             // bse = sqrt(diag(inv(X'WX))) at the final parameters (H holds X'WX there)
             if (!fx_chol<PP>(H)) {
                 fail = PSB_F_MATRIX_INV;
