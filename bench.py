@@ -299,6 +299,7 @@ def peaks():
 # ----------------------------------------------------------------------------------------
 class LmmWorkload(object):
     name = 'lmm'
+    stats = None
     default_n, default_kpg = 5000, 6250000
     continuous = True
 
@@ -380,6 +381,7 @@ class LmmWorkload(object):
 
 class FixedWorkload(object):
     name = 'fixed'
+    stats = None
     default_n, default_kpg = 2000, 10000000
     continuous = False
     DIMS = 10
@@ -446,13 +448,15 @@ class FixedWorkload(object):
     def roofline(self, tested, k_ms, run_ms, W, pk, pk_kind):
         n, p = self.n, self.DIMS + 2
         per_eval = n * (p * (p + 1) / 2 + 2 * p + 30) * 2.0       # X'WX + score + eta, exp/div
-        flops = per_eval * 7.0 * tested                           # ~6 Newton steps + final Hessian
+        evals = self.stats['newton_evaluations'] if self.stats else 3.0 * tested
+        flops = per_eval * evals                                  # measured evaluation count
         achieved = flops / (k_ms / 1e3) / 1e12
         return {'bound': 'tensor', 'kernel': 'k_fixed_logit(+k_fixed_firth)', 'achieved': achieved,
                 'peak': 40.0, 'unit': 'TFLOP/s', 'frac': achieved / 40.0,
                 'peak_source': 'FP64 CUDA-core pipe, B200 nominal ~40 TFLOP/s (no measured fp64 peak '
                                'in MEASURED_PEAKS.json); the kernel is FP64-pipe bound, not tensor '
-                               'or HBM: flops estimated at 7 evaluations x N (p(p+1)/2 + 2p + 30) FMA',
+                               'or HBM: flops = measured Newton evaluations x N (p(p+1)/2 + 2p + 30) FMA',
+                'newton_evaluations_per_variant': evals / max(tested, 1),
                 'kernel_ms': k_ms, 'run_ms': run_ms, 'kernel_share_of_step': k_ms / run_ms,
                 'hbm_read_frac': (tested * (W * 4 + 8 * (6 + p)) / (k_ms / 1e3) / 1e9) / pk['hbm_gbs'],
                 'traffic': None}
@@ -634,6 +638,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     counts = eng.counts()
     tested = counts['tested']
+    wl.stats = eng.last_stats() if a.model == 'fixed' else None
     # dominant-kernel time, CUDA events on the library stream around the dominant launch of
     # the last timed step (every step launches the same grid on the same rows)
     k_ms = eng.last_ms(1)

@@ -195,6 +195,10 @@ int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, ui
 int psb_reader_close(psb_reader *reader);
 
 /* ---- measurement ------------------------------------------------------------- */
+/* Work counters of the last psb_run_fixed: [0] Newton evaluations (passes over the samples)
+ * summed over variants, [1] variants handed to the Firth kernel, [2] variants that failed
+ * the lrt filter. */
+int psb_last_stats(psb_ctx *ctx, int64_t out[4]);
 /* CUDA-event timers on the context stream.  which: 0 = whole last psb_run_*,
  * 1 = dominant kernel of the last run (LMM: the rotation/quadratic-form contraction;
  * fixed effects: the regression kernel).  Returns milliseconds. */

@@ -275,6 +275,20 @@ int psb_counts(psb_ctx *c, int64_t out[4]) {
     return PSB_OK;
 }
 
+int psb_last_stats(psb_ctx *c, int64_t out[4]) {
+    PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->ran, PSB_ERR_STATE, "psb_last_stats before psb_run_*");
+    PSB_CUDA(cudaSetDevice(c->device));
+    int h[8];
+    PSB_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    out[0] = h[4];      // Newton evaluations (passes over the samples) of the Logit kernel
+    out[1] = h[3];      // variants handed to the Firth kernel
+    out[2] = h[2];      // variants that failed the lrt filter
+    out[3] = 0;
+    return PSB_OK;
+}
+
 int psb_last_ms(psb_ctx *c, int32_t which, float *ms) {
     PSB_REQUIRE(c && ms, PSB_ERR_ARG, "NULL argument");
     PSB_CUDA(cudaSetDevice(c->device));

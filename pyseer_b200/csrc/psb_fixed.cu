@@ -332,6 +332,7 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
         uint32_t fail = 0;
         int it = 0;
         bool have_llf = false;
+        int n_eval = 0;
         double fast_bse = -1.0;
         const double inv_n = 1.0 / (double)a.N;
         // The log-likelihood is concave, so a converged Newton run ends at the same (unique)
@@ -385,6 +386,7 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
             for (;;) {
                 const bool want_llf = maxstep <= 1e-3;       // very likely the last evaluation
                 fx_eval<PP>(a, xrow, lane, beta, H, g, maxdev, llf, want_llf);
+                ++n_eval;
                 have_llf = want_llf;
                 if (it > 0 && maxdev <= 1e-8) { fail = PSB_F_PERFECT_SEP; break; }   // _check_perfect_pred
                 // reference rule |dbeta| <= 1e-8; the warm attempt stops one quadratic step
@@ -440,6 +442,7 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
             if (attempt == 0 && converged && !fail) break;     // accept the warm-started fit
             fast_bse = -1.0;
         }
+        if (lane == 0 && a.has_x) atomicAdd(&a.counters[4], n_eval);     // measured, for the roofline
         double bse_x = NAN;
         double bse_all[PP];
         if (!fail && fast_bse > 0.0) {

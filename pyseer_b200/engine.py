@@ -264,6 +264,11 @@ class Engine(object):
         check(self.lib.psb_counts(self._ctx, c))
         return {'loaded': c[0], 'prefiltered': c[1], 'tested': c[2], 'passed': c[3]}
 
+    def last_stats(self):
+        c = (c_int64 * 4)()
+        check(self.lib.psb_last_stats(self._ctx, c))
+        return {'newton_evaluations': c[0], 'firth_fits': c[1], 'lrt_filtered': c[2]}
+
     def last_ms(self, which=0):
         ms = c_float(0)
         check(self.lib.psb_last_ms(self._ctx, which, byref(ms)))
