@@ -132,8 +132,11 @@ int psb_fit_null(psb_ctx *ctx, int32_t n_samples, int32_t q, const double *Z,
  * (i % 32) of word (i / 32) = sample i of the phenotype index order; words_per_row
  * >= ceil(N/32) and a multiple of 4 (16-byte rows); padding bits must be zero.
  * `missing` (same shape, nullable) marks NaN genotypes (Rtab '.', VCF no-call).
- * psb_submit copies host->device asynchronously on the context stream (pass pinned
- * memory to overlap); psb_submit_device adopts device-resident rows without a copy. */
+ * psb_submit copies host->device asynchronously on the context's COPY stream into one of two
+ * staging slots (pass pinned memory): the copy of batch i+1 overlaps the kernels of batch i,
+ * and the table of the previous run stays fetchable until the next psb_run_* adopts the new
+ * rows.  Pipelined use:  submit(0) run(0) | submit(1) fetch(0) run(1) | submit(2) fetch(1) ...
+ * psb_submit_device adopts device-resident rows without a copy. */
 int psb_submit(psb_ctx *ctx, const uint32_t *bits, const uint32_t *missing,
                int64_t n_variants, int32_t words_per_row);
 int psb_submit_device(psb_ctx *ctx, const void *d_bits, const void *d_missing,

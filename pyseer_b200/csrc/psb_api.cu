@@ -50,6 +50,11 @@ int psb_create(int device_id, psb_ctx **out) {
     c->device = device_id;
     c->sm_count = prop.multiProcessorCount;
     PSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PSB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        PSB_CUDA(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+        PSB_CUDA(cudaEventCreateWithFlags(&c->ev_used[i], cudaEventDisableTiming));
+    }
     PSB_CUDA(cudaEventCreate(&c->ev_run0));
     PSB_CUDA(cudaEventCreate(&c->ev_run1));
     PSB_CUDA(cudaEventCreate(&c->ev_k0));
@@ -105,8 +110,14 @@ int psb_destroy(psb_ctx *c) {
     if (!c) return PSB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
     psb_free_model(c);
     free_tables(c);
+    for (int i = 0; i < 2; ++i) {
+        free_dev(c->stage_bits[i]); free_dev(c->stage_miss[i]);
+        cudaEventDestroy(c->ev_copy[i]); cudaEventDestroy(c->ev_used[i]);
+    }
+    cudaStreamDestroy(c->copy_stream);
     free_dev(c->own_bits); free_dev(c->own_miss); free_dev(c->d_counters);
     cudaEventDestroy(c->ev_run0); cudaEventDestroy(c->ev_run1);
     cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1);
@@ -124,6 +135,34 @@ int psb_sync(psb_ctx *c) {
 }
 
 }  // extern "C"
+
+// Called by psb_run_*: order the compute stream after the pending psb_submit copy ...
+int psb_run_begin(psb_ctx *c) {
+    if (c->sub_valid) {
+        // adopt the submitted rows as the current batch
+        c->d_bits = c->sub_bits;
+        c->d_miss = c->sub_miss;
+        c->S = c->sub_S;
+        c->Wrow = c->sub_Wrow;
+        c->bits_slot = c->sub_slot;
+        c->copy_pending = c->sub_slot >= 0;
+        c->sub_valid = false;
+        c->ran = false;
+    }
+    if (c->copy_pending && c->bits_slot >= 0) {
+        PSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[c->bits_slot], 0));
+        c->copy_pending = false;
+    }
+    return PSB_OK;
+}
+// ... and mark the staging slot as read once the run's kernels are queued.
+int psb_run_end(psb_ctx *c) {
+    if (c->bits_slot >= 0) {
+        PSB_CUDA(cudaEventRecord(c->ev_used[c->bits_slot], c->stream));
+        c->used_valid[c->bits_slot] = true;
+    }
+    return PSB_OK;
+}
 
 int psb_ensure_capacity(psb_ctx *c, int64_t S, int betas_cols) {
     if (S > c->cap || betas_cols > c->betas_cols) {
@@ -176,40 +215,48 @@ static int check_rows(psb_ctx *c, int64_t n_variants, int32_t words_per_row) {
     return PSB_OK;
 }
 
+static int stage_reserve(psb_ctx *c, uint32_t **buf, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return PSB_OK;
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->copy_stream));
+    free_dev(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    PSB_CUDA(cudaMalloc(buf, bytes));
+    *cap = bytes;
+    return PSB_OK;
+}
+
 int psb_submit(psb_ctx *c, const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
                int32_t words_per_row) {
     int rc = check_rows(c, n_variants, words_per_row);
     if (rc) return rc;
     PSB_REQUIRE(bits || n_variants == 0, PSB_ERR_ARG, "bits is NULL");
     PSB_CUDA(cudaSetDevice(c->device));
-    size_t bytes = (size_t)n_variants * words_per_row * sizeof(uint32_t);
-    if (bytes > c->own_bits_cap) {
-        PSB_CUDA(cudaStreamSynchronize(c->stream));
-        free_dev(c->own_bits);
-        c->own_bits = nullptr;
-        c->own_bits_cap = 0;
-        PSB_CUDA(cudaMalloc(&c->own_bits, bytes));
-        c->own_bits_cap = bytes;
-    }
-    if (bytes) PSB_CUDA(cudaMemcpyAsync(c->own_bits, bits, bytes, cudaMemcpyHostToDevice, c->stream));
-    c->d_bits = c->own_bits;
-    c->d_miss = nullptr;
+    const size_t bytes = (size_t)n_variants * words_per_row * sizeof(uint32_t);
+    const int slot = c->stage_slot ^ 1;          // alternate: the other slot may still be in use
+    rc = stage_reserve(c, &c->stage_bits[slot], &c->stage_bits_cap[slot], bytes);
+    if (rc) return rc;
     if (missing) {
-        if (bytes > c->own_miss_cap) {
-            PSB_CUDA(cudaStreamSynchronize(c->stream));
-            free_dev(c->own_miss);
-            c->own_miss = nullptr;
-            c->own_miss_cap = 0;
-            PSB_CUDA(cudaMalloc(&c->own_miss, bytes));
-            c->own_miss_cap = bytes;
-        }
-        if (bytes)
-            PSB_CUDA(cudaMemcpyAsync(c->own_miss, missing, bytes, cudaMemcpyHostToDevice, c->stream));
-        c->d_miss = c->own_miss;
+        rc = stage_reserve(c, &c->stage_miss[slot], &c->stage_miss_cap[slot], bytes);
+        if (rc) return rc;
     }
-    c->S = n_variants;
-    c->Wrow = words_per_row;
-    c->ran = false;
+    // the kernels of the run that last read this slot must have finished before it is refilled
+    if (c->used_valid[slot]) PSB_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_used[slot], 0));
+    if (bytes) {
+        PSB_CUDA(cudaMemcpyAsync(c->stage_bits[slot], bits, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        if (missing)
+            PSB_CUDA(cudaMemcpyAsync(c->stage_miss[slot], missing, bytes, cudaMemcpyHostToDevice,
+                                     c->copy_stream));
+    }
+    PSB_CUDA(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+    c->stage_slot = slot;
+    c->sub_bits = c->stage_bits[slot];
+    c->sub_miss = missing ? c->stage_miss[slot] : nullptr;
+    c->sub_S = n_variants;
+    c->sub_Wrow = words_per_row;
+    c->sub_slot = slot;
+    c->sub_valid = true;
     return PSB_OK;
 }
 
@@ -218,11 +265,12 @@ int psb_submit_device(psb_ctx *c, const void *d_bits, const void *d_missing, int
     int rc = check_rows(c, n_variants, words_per_row);
     if (rc) return rc;
     PSB_REQUIRE(d_bits || n_variants == 0, PSB_ERR_ARG, "d_bits is NULL");
-    c->d_bits = (const uint32_t *)d_bits;
-    c->d_miss = (const uint32_t *)d_missing;
-    c->S = n_variants;
-    c->Wrow = words_per_row;
-    c->ran = false;
+    c->sub_bits = (const uint32_t *)d_bits;
+    c->sub_miss = (const uint32_t *)d_missing;
+    c->sub_S = n_variants;
+    c->sub_Wrow = words_per_row;
+    c->sub_slot = -1;
+    c->sub_valid = true;
     return PSB_OK;
 }
 
@@ -334,8 +382,10 @@ int psb_host_free(void *ptr) {
 
 int psb_download_bits(psb_ctx *c, uint32_t *out_bits) {
     PSB_REQUIRE(c && out_bits, PSB_ERR_ARG, "NULL argument");
-    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "no rows submitted");
     PSB_CUDA(cudaSetDevice(c->device));
+    int rc = psb_run_begin(c);
+    if (rc) return rc;
+    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "no rows submitted");
     size_t bytes = (size_t)c->S * c->Wrow * sizeof(uint32_t);
     if (bytes)
         PSB_CUDA(cudaMemcpyAsync(out_bits, c->d_bits, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -1040,11 +1040,13 @@ static int fx_run_null(psb_ctx *c, int mode, std::vector<double> &h) {
 extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
     PSB_REQUIRE(c && prm, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(c->model == PSB_MODEL_FIXED, PSB_ERR_STATE, "psb_run_fixed without psb_fixed_setup");
-    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "psb_run_fixed without psb_submit");
     PSB_REQUIRE((prm->continuous != 0) == (c->continuous != 0), PSB_ERR_ARG,
                 "params.continuous differs from psb_fixed_setup");
     PSB_CUDA(cudaSetDevice(c->device));
-    int rc = psb_ensure_capacity(c, c->S, c->q > 1 ? c->q - 1 : 1);
+    int rc = psb_run_begin(c);
+    if (rc) return rc;
+    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "psb_run_fixed without psb_submit");
+    rc = psb_ensure_capacity(c, c->S, c->q > 1 ? c->q - 1 : 1);
     if (rc) return rc;
     PSB_CUDA(cudaEventRecord(c->ev_run0, c->stream));
     if (c->S > 0 && c->q > 1)
@@ -1105,7 +1107,7 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
     PSB_CUDA(cudaEventRecord(c->ev_run1, c->stream));
     c->have_run_ev = true;
     c->ran = true;
-    return PSB_OK;
+    return psb_run_end(c);
 }
 
 template <int PP>
@@ -1162,10 +1164,13 @@ extern "C" int psb_run_lineage(psb_ctx *c, int32_t mode) {
     if (p <= 4) launch_lineage<4>(c, a, n, grid, mode);
     else if (p <= 8) launch_lineage<8>(c, a, n, grid, mode);
     else if (p <= 12) launch_lineage<12>(c, a, n, grid, mode);
-    else return psb_fixed_gen_launch(c, a, FXG_LINEAGE, n, mode, c->n_lin, c->d_lineage);
+    else {
+        int rc = psb_fixed_gen_launch(c, a, FXG_LINEAGE, n, mode, c->n_lin, c->d_lineage);
+        return rc ? rc : psb_run_end(c);
+    }
     c->launches++;
     PSB_CUDA(cudaGetLastError());
-    return PSB_OK;
+    return psb_run_end(c);
 }
 
 extern "C" int psb_fetch_lineage(psb_ctx *c, int32_t *out) {

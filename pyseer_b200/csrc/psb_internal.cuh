@@ -94,8 +94,25 @@ struct psb_ctx {
 
     // ---- variants ----
     const uint32_t *d_bits = nullptr, *d_miss = nullptr;
-    uint32_t *own_bits = nullptr, *own_miss = nullptr;
+    uint32_t *own_bits = nullptr, *own_miss = nullptr;       // psb_synth_device rows
     size_t own_bits_cap = 0, own_miss_cap = 0;   // bytes
+    // psb_submit staging: two slots filled on a copy stream, so that the copy of batch i+1
+    // overlaps the kernels of batch i (input.py's k-mer streaming as a pinned-host -> device
+    // pipeline).  ev_copy[s]: rows of slot s have landed; ev_used[s]: last run that read slot s.
+    cudaStream_t copy_stream = nullptr;
+    uint32_t *stage_bits[2] = {nullptr, nullptr}, *stage_miss[2] = {nullptr, nullptr};
+    size_t stage_bits_cap[2] = {0, 0}, stage_miss_cap[2] = {0, 0};
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_used[2] = {nullptr, nullptr};
+    bool used_valid[2] = {false, false};
+    // rows handed over by psb_submit* / psb_synth_device but not yet adopted by a run: a submit
+    // does not disturb the table of the previous run, which can still be fetched
+    const uint32_t *sub_bits = nullptr, *sub_miss = nullptr;
+    int64_t sub_S = 0;
+    int sub_Wrow = 0, sub_slot = -1;
+    bool sub_valid = false;
+    int stage_slot = 1;          // slot of the most recent psb_submit
+    int bits_slot = -1;          // staging slot d_bits points into (-1: not a staging slot)
+    bool copy_pending = false;   // the compute stream has not yet waited for ev_copy[bits_slot]
     int64_t S = 0;
     int Wrow = 0;
 
@@ -121,6 +138,8 @@ struct psb_ctx {
 };
 
 int psb_ensure_capacity(psb_ctx *ctx, int64_t S, int betas_cols);
+int psb_run_begin(psb_ctx *ctx);
+int psb_run_end(psb_ctx *ctx);
 int psb_free_model(psb_ctx *ctx);
 
 // psb_varstats.cu

@@ -47,8 +47,9 @@ __device__ __forceinline__ void cp_async_wait() {
 
 __global__ void __launch_bounds__(QF_THREADS, 1)
 k_lmm_quadform_fp64(const uint32_t *__restrict__ bits, int Wrow, const int32_t *__restrict__ idx,
-                    int n_tested, const double *__restrict__ L, int Lrows, int Jpad,
-                    double *__restrict__ a_out) {
+                    const int *__restrict__ n_tested_dev, const double *__restrict__ L, int Lrows,
+                    int Jpad, double *__restrict__ a_out) {
+    const int n_tested = *n_tested_dev;
     __shared__ __align__(16) double Ls[2][QF_BK][QF_BN];
     __shared__ uint32_t Xs[2][QF_BM];
     __shared__ int32_t rows[QF_BM];
@@ -151,7 +152,8 @@ k_lmm_quadform_fp64(const uint32_t *__restrict__ bits, int Wrow, const int32_t *
 // the lrt filter of fit_lmm (lmm.py:201-224).  One thread per tested variant.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_lmm_epilogue(int n_tested, const int32_t *__restrict__ idx, const double *__restrict__ a_in,
+k_lmm_epilogue(const int *__restrict__ n_tested_dev, const int32_t *__restrict__ idx,
+               const double *__restrict__ a_in,
                const double *__restrict__ b_in, const double *__restrict__ pp_in,
                const double *__restrict__ sums, int C, int col_b, int col_q0, int nq, int N,
                const int32_t *__restrict__ carriers, const int32_t *__restrict__ nmissing,
@@ -160,7 +162,7 @@ k_lmm_epilogue(int n_tested, const int32_t *__restrict__ idx, const double *__re
                double *__restrict__ frac_out, uint32_t *__restrict__ flags,
                int *__restrict__ counters) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tested) return;
+    if (t >= *n_tested_dev) return;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     int v = idx[t];
     uint32_t f = flags[v];
@@ -422,9 +424,11 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
 extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
     PSB_REQUIRE(c && prm, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(c->model == PSB_MODEL_LMM, PSB_ERR_STATE, "psb_run_lmm without psb_lmm_setup");
-    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "psb_run_lmm without psb_submit");
     PSB_CUDA(cudaSetDevice(c->device));
-    int rc = psb_ensure_capacity(c, c->S, 0);
+    int rc = psb_run_begin(c);
+    if (rc) return rc;
+    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "psb_run_lmm without psb_submit");
+    rc = psb_ensure_capacity(c, c->S, 0);
     if (rc) return rc;
     PSB_CUDA(cudaEventRecord(c->ev_run0, c->stream));
     // With the tensor path carrying x'v and Q'x, the stats pass only needs popcounts and
@@ -437,29 +441,28 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
     if (rc) return rc;
     rc = psb_launch_prefilter(c, prm, /*lmm_rule=*/1);
     if (rc) return rc;
-    int h_cnt[8] = {0};
-    PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));
-    PSB_CUDA(cudaStreamSynchronize(c->stream));
-    const int n_tested = h_cnt[0];
+    // The number of tested variants stays on the device (counters[0]): the whole run is queued
+    // without a host round trip, so the next psb_submit copy overlaps these kernels.
+    const int upper = (int)c->S;
     PSB_CUDA(cudaEventRecord(c->ev_k0, c->stream));
-    if (n_tested > 0) {
+    if (upper > 0) {
         if (c->precision == 0) {
-            int tiles = psb_div_up(n_tested, QF_BM);
+            int tiles = psb_div_up(upper, QF_BM);
             int grid = std::min(tiles, c->sm_count);
             k_lmm_quadform_fp64<<<grid, QF_THREADS, 0, c->stream>>>(
-                c->d_bits, c->Wrow, c->d_idx, n_tested, c->d_L, c->Lrows, c->Jpad, c->d_a);
+                c->d_bits, c->Wrow, c->d_idx, c->d_counters, c->d_L, c->Lrows, c->Jpad, c->d_a);
             c->launches++;
             PSB_CUDA(cudaGetLastError());
         } else {
-            rc = psb_lmm_tc_run(c, n_tested);
+            rc = psb_lmm_tc_run(c, upper);
             if (rc) return rc;
         }
     }
     PSB_CUDA(cudaEventRecord(c->ev_k1, c->stream));
     c->have_k_ev = true;
-    if (n_tested > 0) {
-        k_lmm_epilogue<<<psb_div_up(n_tested, 256), 256, 0, c->stream>>>(
-            n_tested, c->d_idx, c->d_a, tc_sums ? c->d_b : nullptr, tc_sums ? c->d_pp : nullptr,
+    if (upper > 0) {
+        k_lmm_epilogue<<<psb_div_up(upper, 256), 256, 0, c->stream>>>(
+            c->d_counters, c->d_idx, c->d_a, tc_sums ? c->d_b : nullptr, tc_sums ? c->d_pp : nullptr,
             c->d_sums, c->C, c->col_b, c->col_q0, c->col_w0 - c->col_q0,
             c->N, c->d_carriers, c->d_missing, c->YKY, (double)(c->J - 1), prm->lrt_pvalue,
             c->d_pvalue, c->d_beta, c->d_bse, c->d_extra, c->d_flags, c->d_counters);
@@ -469,5 +472,5 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
     PSB_CUDA(cudaEventRecord(c->ev_run1, c->stream));
     c->have_run_ev = true;
     c->ran = true;
-    return PSB_OK;
+    return psb_run_end(c);
 }

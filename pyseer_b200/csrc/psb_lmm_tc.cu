@@ -184,7 +184,8 @@ struct TcArgs {
     double *lin_out;          // raw pair sums x'u_p -> lin_out[variant id * lin_ld + p] (may be null)
     int lin_ld;
     int Wrow;                 // words per packed row in global memory
-    int n_tested;
+    int n_tested;             // upper bound used for the grid; the kernels read the real count:
+    const int *n_tested_dev;  // device counter written by k_prefilter (no host round trip)
     int nks;                  // K stages (Kpad / 128)
     int jtiles;
     int pitch;                // smem bit-row pitch in words (== 4 mod 32)
@@ -222,7 +223,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_tiles = (args.n_tested + TC_TILE_V - 1) / TC_TILE_V;
+    const int n_tested = args.n_tested_dev ? *args.n_tested_dev : args.n_tested;
+    const int n_tiles = (n_tested + TC_TILE_V - 1) / TC_TILE_V;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < ns; ++i) {
@@ -309,7 +311,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et < TC_TILE_V) {
                 int t = tile * TC_TILE_V + et;
-                sRows[et] = t < args.n_tested ? args.idx[t] : -1;
+                sRows[et] = t < n_tested ? args.idx[t] : -1;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int total = TC_TILE_V * chunks_per_row;
@@ -360,7 +362,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             double a = 0.0, bsum = 0.0, pp = 0.0;
             const int t_own = tile * TC_TILE_V + v;
-            const int row_own = t_own < args.n_tested ? args.idx[t_own] : -1;
+            const int row_own = t_own < n_tested ? args.idx[t_own] : -1;
             for (int jt = 0; jt < args.jtiles; ++jt) {
                 mbar_wait(smem_u32(&accFull[acc]), phacc);
                 tc_fence_after();
@@ -637,6 +639,7 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.n_special = c->tc_special;
     a.Wrow = c->Wrow;
     a.n_tested = n_tested;
+    a.n_tested_dev = c->d_counters;      // counters[0] = tested variants
     a.nks = c->Kpad / TC_KSTAGE;
     a.jtiles = c->jtiles;
     int pitch = a.nks * 4;

@@ -103,11 +103,12 @@ extern "C" int psb_synth_device(psb_ctx *c, uint64_t seed, int64_t first_variant
     }
     PSB_CUDA(cudaStreamSynchronize(c->stream));
     if (d_sign) cudaFree(d_sign);
-    c->d_bits = c->own_bits;
-    c->d_miss = nullptr;
-    c->S = n_variants;
-    c->Wrow = Wrow;
-    c->ran = false;
+    c->sub_bits = c->own_bits;
+    c->sub_miss = nullptr;
+    c->sub_S = n_variants;
+    c->sub_Wrow = Wrow;
+    c->sub_slot = -1;
+    c->sub_valid = true;
     return PSB_OK;
 }
 

@@ -145,7 +145,7 @@ class Engine(object):
     def run_lineage(self, lmm_rule=False):
         """Index of the most associated lineage per submitted variant (-1 = None)."""
         check(self.lib.psb_run_lineage(self._ctx, 1 if lmm_rule else 0))
-        out = np.empty(self.n_variants, dtype=np.int32)
+        out = np.empty(getattr(self, 'n_run', self.n_variants), dtype=np.int32)
         check(self.lib.psb_fetch_lineage(self._ctx, out.ctypes.data_as(c_void_p)))
         return out
 
@@ -206,14 +206,16 @@ class Engine(object):
                 lrt_pvalue=1.0, continuous=False):
         p = self._params(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous)
         check(self.lib.psb_run_lmm(self._ctx, byref(p)))
+        self.n_run = self.n_variants
 
     def run_fixed(self, min_af=0.01, max_af=0.99, max_missing=0.05, filter_pvalue=1.0,
                   lrt_pvalue=1.0, continuous=False):
         p = self._params(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous)
         check(self.lib.psb_run_fixed(self._ctx, byref(p)))
+        self.n_run = self.n_variants
 
     def fetch(self, columns=None):
-        S = self.n_variants
+        S = getattr(self, 'n_run', self.n_variants)      # rows of the last run, not of a later submit
         r = Results()
         r.carriers = np.empty(S, dtype=np.int32)
         r.missing = np.empty(S, dtype=np.int32)

@@ -201,6 +201,7 @@ def fit_lmm_block(lmm, h2, variant_block):
     p = eng._params(-1.0, 2.0, 2.0, np.inf, np.inf, False)
     p.options = _lib.OPT_NO_PREFILTER
     _lib.check(eng.lib.psb_run_lmm(eng._ctx, p))
+    eng.n_run = eng.n_variants
     r = eng.fetch(('pvalue', 'beta', 'bse', 'extra', 'flags'))
     return {'p_values': r.pvalue, 'beta': r.beta, 'bse': r.bse, 'frac_h2': r.extra}
 
