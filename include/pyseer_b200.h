@@ -180,6 +180,16 @@ int psb_host_alloc(size_t bytes, void **out);
 int psb_host_free(void *ptr);
 int psb_download_bits(psb_ctx *ctx, uint32_t *out_bits);
 
+/* ---- sample similarity (kinship) matrix ----------------------------------------------- */
+/* K = G G' of pyseer/similarity.py:99-116 over packed rows: K[i][j] = number of variants that
+ * pass the AF / missing filter (input.py:693) and are carried by both samples.  Independent of
+ * the association models: begin(N), add batches of host rows (same layout as psb_submit), fetch
+ * the N x N row-major matrix (exact integers as doubles). */
+int psb_kinship_begin(psb_ctx *ctx, int32_t n_samples);
+int psb_kinship_add(psb_ctx *ctx, const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
+                    int32_t words_per_row, double min_af, double max_af, double max_missing);
+int psb_kinship_fetch(psb_ctx *ctx, double *K_out);
+
 /* ---- native variant-file reader ------------------------------------------------- */
 /* Replaces the per-line Python of input.read_variant (input.py:301-454) for the k-mer text
  * format (`name | s1:1 s2:1 ...`, var_type 0) and Rtab (var_type 1); plain or gzip files.

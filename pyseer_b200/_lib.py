@@ -76,7 +76,7 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_results_device', 'psb_counts', 'psb_last_ms', 'psb_launch_count',
            'psb_host_alloc', 'psb_host_free', 'psb_download_bits', 'psb_event_record',
            'psb_event_elapsed', 'psb_reader_open', 'psb_reader_next', 'psb_reader_close',
-           'psb_lineage_setup', 'psb_run_lineage', 'psb_fetch_lineage', 'psb_last_stats',
+           'psb_lineage_setup', 'psb_run_lineage', 'psb_fetch_lineage', 'psb_last_stats', 'psb_kinship_begin', 'psb_kinship_add', 'psb_kinship_fetch',
            'psb_synth_device', 'psb_synth_host', 'psb_host_chi2_sf1', 'psb_host_f_sf_1',
            'psb_host_t2_sf']
 
@@ -124,6 +124,10 @@ def load():
     lib.psb_run_lineage.argtypes = [c_void_p, c_int32]
     lib.psb_fetch_lineage.argtypes = [c_void_p, c_void_p]
     lib.psb_last_stats.argtypes = [c_void_p, POINTER(c_int64)]
+    lib.psb_kinship_begin.argtypes = [c_void_p, c_int32]
+    lib.psb_kinship_add.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double,
+                                    c_double]
+    lib.psb_kinship_fetch.argtypes = [c_void_p, dp]
     lib.psb_synth_device.argtypes = [c_void_p, c_uint64, c_int64, c_int64, c_int32, c_double,
                                      c_double, c_int32, POINTER(c_int8)]
     lib.psb_synth_host.argtypes = [c_uint64, c_int64, c_int64, c_int32, c_double, c_double,

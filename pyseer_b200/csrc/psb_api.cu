@@ -111,6 +111,7 @@ int psb_destroy(psb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    psb_kinship_release(c);
     psb_free_model(c);
     free_tables(c);
     for (int i = 0; i < 2; ++i) {

@@ -135,12 +135,14 @@ struct psb_ctx {
     double *d_pp = nullptr;       // [cap] ||Q'x||^2 from the tensor path
     int64_t counts[4] = {0, 0, 0, 0};
     bool ran = false;
+    void *kin = nullptr;          // psb_kinship.cu state
 };
 
 int psb_ensure_capacity(psb_ctx *ctx, int64_t S, int betas_cols);
 int psb_run_begin(psb_ctx *ctx);
 int psb_run_end(psb_ctx *ctx);
 int psb_free_model(psb_ctx *ctx);
+void psb_kinship_release(psb_ctx *ctx);
 
 // psb_varstats.cu
 int psb_launch_bitsums(psb_ctx *ctx);

@@ -130,6 +130,26 @@ class Engine(object):
                                        float(null_firth)))
         self.n_samples, self.q, self.model = n, q, 'fixed'
 
+    # -- kinship ------------------------------------------------------------------------
+    def kinship_begin(self, n_samples):
+        check(self.lib.psb_kinship_begin(self._ctx, int(n_samples)))
+        self._kin_n = int(n_samples)
+
+    def kinship_add(self, bits, missing=None, min_af=0.01, max_af=0.99, max_missing=0.05):
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        mp = None
+        if missing is not None:
+            missing = np.ascontiguousarray(missing, dtype=np.uint32)
+            mp = missing.ctypes.data_as(c_void_p)
+        check(self.lib.psb_kinship_add(self._ctx, bits.ctypes.data_as(c_void_p), mp, bits.shape[0],
+                                       bits.shape[1], float(min_af), float(max_af),
+                                       float(max_missing)))
+
+    def kinship_fetch(self):
+        K = np.empty((self._kin_n, self._kin_n), dtype=np.float64)
+        check(self.lib.psb_kinship_fetch(self._ctx, self._dptr(K)))
+        return K
+
     def lineage_setup(self, lin, cov=None):
         """Design of model.fit_lineage_effect: [1, lin, cov] (model.py:176-180)."""
         lin = np.asarray(lin, dtype=float)

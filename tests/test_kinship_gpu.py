@@ -1,0 +1,51 @@
+"""Kinship matrix K = G G' (pyseer/similarity.py:99-116) on the GPU vs NumPy."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('n,nv', [(50, 333), (333, 5000), (1000, 4097)])
+def test_kinship_matches_numpy(n, nv):
+    from pyseer_b200.engine import Engine, synth_host, unpack_rows
+    bits = synth_host(11, 0, nv, n, af_lo=0.0, af_hi=1.0)
+    x = unpack_rows(bits, n).astype(np.int64)
+    af = x.sum(1) / float(n)
+    keep = ~((af < 0.05) | (af > 0.9))
+    G = x[keep].T
+    ref = G @ G.T
+    eng = Engine(0)
+    eng.kinship_begin(n)
+    half = nv // 3
+    eng.kinship_add(bits[:half], None, 0.05, 0.9, 0.05)       # accumulates over batches
+    eng.kinship_add(bits[half:], None, 0.05, 0.9, 0.05)
+    K = eng.kinship_fetch()
+    eng.close()
+    assert np.array_equal(K, ref.astype(float))
+
+
+def test_similarity_tool_on_reference_kmers(tmp_path):
+    from pyseer_b200.similarity import main
+    from pyseer_b200.input import VariantReader, load_phenotypes
+    from pyseer_b200.engine import unpack_rows
+    p = load_phenotypes(os.path.join(GOLDEN, 'subset.pheno'), None)
+    samples = tmp_path / 'samples.txt'
+    samples.write_text('\n'.join(p.index) + '\n')
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(io.StringIO()):
+        main([str(samples), '--kmers', os.path.join(GOLDEN, 'kmers.gz')])
+    K = pd.read_csv(io.StringIO(out.getvalue()), sep='\t', index_col=0)
+    assert list(K.index) == list(p.index) and list(K.columns) == list(p.index)
+    rd = VariantReader('kmers', os.path.join(GOLDEN, 'kmers.gz'), p)
+    with contextlib.redirect_stderr(io.StringIO()):
+        x = np.concatenate([unpack_rows(b.bits, len(p)) for b in rd.batches(100)]).astype(np.int64)
+    af = x.sum(1) / float(len(p))
+    G = x[(af >= 0.01) & (af <= 0.99)].T
+    assert np.array_equal(K.values, (G @ G.T).astype(float))
