@@ -36,6 +36,7 @@
 #include <cuda.h>
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -189,6 +190,7 @@ struct TcArgs {
     int nks;                  // K stages (Kpad / 128)
     int jtiles;
     int pitch;                // smem bit-row pitch in words (== 4 mod 32)
+    int bits_in_smem;         // 1: the tile's packed rows are staged in shared memory
     int n_bstages;
 };
 
@@ -314,21 +316,49 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 sRows[et] = t < n_tested ? args.idx[t] : -1;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int total = TC_TILE_V * chunks_per_row;
-            for (int e = et; e < total; e += 32 * TC_EXP_WARPS) {
-                int r = e / chunks_per_row, ch = e - r * chunks_per_row;
-                int row = sRows[r];
-                uint4 val = make_uint4(0u, 0u, 0u, 0u);
-                if (row >= 0 && ch * 4 < args.Wrow)
-                    val = __ldg(reinterpret_cast<const uint4 *>(args.bits + (size_t)row * args.Wrow) + ch);
-                *reinterpret_cast<uint4 *>(sBits + (size_t)r * args.pitch + ch * 4) = val;
+            if (args.bits_in_smem) {
+                const int total = TC_TILE_V * chunks_per_row;
+                for (int e = et; e < total; e += 32 * TC_EXP_WARPS) {
+                    int r = e / chunks_per_row, ch = e - r * chunks_per_row;
+                    int row = sRows[r];
+                    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+                    if (row >= 0 && ch * 4 < args.Wrow)
+                        val = __ldg(reinterpret_cast<const uint4 *>(args.bits + (size_t)row * args.Wrow) + ch);
+                    *reinterpret_cast<uint4 *>(sBits + (size_t)r * args.pitch + ch * 4) = val;
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const uint32_t *myrow = sBits + (size_t)v * args.pitch;
+            // Large N (the tile's bits would crowd the operand ring out of shared memory): each
+            // thread reads its 16 bytes per stage straight from its global row (L2-resident
+            // after the first component tile), fetched one of its stages ahead.
+            const int grow_id = sRows[v];
+            const uint4 *grow = reinterpret_cast<const uint4 *>(args.bits + (size_t)(grow_id < 0 ? 0 : grow_id) * args.Wrow);
+            const int gwords4 = args.Wrow >> 2;
+            auto gload = [&](int ks) -> uint4 {
+                return (grow_id >= 0 && ks < gwords4) ? __ldg(grow + ks) : make_uint4(0u, 0u, 0u, 0u);
+            };
+            // first stage of this group in the tile: ks = 0 if the running parity matches, else 1
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (!args.bits_in_smem) {
+                int ks0 = ((int)parity == grp) ? 0 : 1;
+                if (ks0 >= args.nks) ks0 = 0;
+                nxt = gload(ks0);
+            }
             for (int jt = 0; jt < args.jtiles; ++jt)
                 for (int ks = 0; ks < args.nks; ++ks, parity ^= 1u) {
                     if ((int)parity != grp) continue;
-                    const uint4 w4 = *reinterpret_cast<const uint4 *>(myrow + ks * 4);
+                    uint4 w4;
+                    if (args.bits_in_smem) {
+                        w4 = *reinterpret_cast<const uint4 *>(myrow + ks * 4);
+                    } else {
+                        w4 = nxt;
+                        // this group's next stage: two positions on in the (jt, ks) sequence
+                        int kn = ks + 2;
+                        if (kn >= args.nks) kn -= args.nks;
+                        if (kn >= args.nks) kn -= args.nks;       // nks == 1
+                        nxt = gload(kn);
+                    }
                     mbar_wait(empty0 + sa * 8, pha ^ 1);
                     tc_fence_after();
                     const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
@@ -648,6 +678,13 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     int smem_max = 0;
     PSB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     int nb = (512 - 2 * TC_JT * nsl) / 32;      // TMEM A-ring depth bounds the pipeline
+    // the tile's packed rows live in shared memory unless that would cost operand stages
+    a.bits_in_smem = tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max ? 1 : 0;
+    if (getenv("PSB_TC_GLOBAL_BITS")) a.bits_in_smem = 0;      // test hook: force the large-N mode
+    if (!a.bits_in_smem) {
+        pitch = 4;                               // no bit tile in shared memory
+        a.pitch = pitch;
+    }
     // (kept even: the two expander groups own the slots of their own parity)
     while (nb > 2 && tc_smem_bytes(nsl, nb, pitch) > (size_t)smem_max) nb -= 2;
     PSB_REQUIRE(tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max, PSB_ERR_UNSUPPORTED,

@@ -227,3 +227,25 @@ def test_missing_genotypes(precision):
         assert np.isnan(r.pvalue[s]) and (r.flags[s] & _lib.F_LRT_FAILED)
     assert np.isfinite(r.pvalue[[0, 1, 2, 5]]).all()
     m.close()
+
+
+def test_large_n_mode_matches_default(monkeypatch):
+    """The tensor kernel's large-N mode (packed rows read from global memory instead of a
+    shared-memory tile, used when N is too large for both the tile and the operand ring) gives
+    the same table as the default mode."""
+    from pyseer_b200 import lmm as plmm
+    from pyseer_b200.engine import synth_host
+    n, nv = 700, 2000
+    K, y = _synthetic(n, 3)
+    Kn = K * (float(n) / np.diag(K).sum())
+    bits = synth_host(5, 0, nv, n)
+    out = []
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv('PSB_TC_GLOBAL_BITS', '1')
+        m = plmm.KinshipLMM(np.ones((n, 1)), y.reshape(-1, 1), Kn.copy(), precision=5)
+        h2 = m.findH2()['h2']
+        out.append(plmm.run_lmm_bits(m, h2, bits, None, True, 1.0, 1.0, 0.01, 0.99, 0.05))
+        m.close()
+    for f in ('pvalue', 'beta', 'bse', 'extra'):
+        assert np.array_equal(getattr(out[0], f), getattr(out[1], f), equal_nan=True), f
