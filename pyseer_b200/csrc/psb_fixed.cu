@@ -19,6 +19,7 @@
 // stopping rules literally (35 steps, |dbeta| <= 1e-8; lagged 1e-4 test and step halving for
 // Firth), so the iterates -- not just the limits -- agree with the reference.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -308,8 +309,8 @@ __device__ __forceinline__ void fx_publish(const FxArgs &a, int v, uint32_t f, c
 // ---------------------------------------------------------------------------------------
 // Logit Newton (statsmodels Logit.fit(method='newton'), call site model.py:328-330)
 // ---------------------------------------------------------------------------------------
-template <int PP>
-__global__ void __launch_bounds__(128)
+template <int PP, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
     // the parameter vector lives in shared memory (one copy per warp, read by broadcast in the
     // sample loop): 2 PP registers less pressure on the X'WX accumulators
@@ -984,7 +985,10 @@ static FxArgs fx_args(psb_ctx *c, const psb_params *prm, int has_x) {
 
 template <int PP>
 static void launch_logit(psb_ctx *c, const FxArgs &a, int n, int grid) {
-    k_fixed_logit<PP><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
+    static const int minb = getenv("PSB_LOGIT_MINB") ? atoi(getenv("PSB_LOGIT_MINB")) : 2;
+    if (PP == 12 && minb == 3) k_fixed_logit<PP, 3><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
+    else if (PP == 12 && minb == 4) k_fixed_logit<PP, 4><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
+    else k_fixed_logit<PP, 2><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
 }
 template <int PP>
 static void launch_firth(psb_ctx *c, const FxArgs &a, int n, int grid) {
