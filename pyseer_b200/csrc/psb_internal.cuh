@@ -75,6 +75,7 @@ struct psb_ctx {
     int8_t *d_Lq = nullptr;       // [jtiles][slices][32 comps][Kpad] int8 (K-major)
     double *d_scale2 = nullptr;   // [Jpad32] (s_j 2^-B)^2
     int n_slices = 0, jtiles = 0;
+    bool tc_tri = false;          // regular tiles hold the triangular operand M'' (psb_lmm_tc.cu)
     int tc_special = 0;           // hi/lo column pairs carried by the special tile (0 = none)
     void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B)
 

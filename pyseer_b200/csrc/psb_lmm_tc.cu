@@ -191,7 +191,47 @@ struct TcArgs {
     int jtiles;
     int pitch;                // smem bit-row pitch in words (== 4 mod 32)
     int bits_in_smem;         // 1: the tile's packed rows are staged in shared memory
+    int tri;                  // 1: regular tiles hold the triangular operand M'' (see below)
+    int stages_per_tile;      // K stages a variant tile goes through (all component tiles)
     int n_bstages;
+};
+
+// Sequence of component tiles a variant tile goes through, and the first K stage of each.
+// Triangular form (tri): a = x'Mx with M = L L' symmetric and x binary equals
+//   sum_j x_j T_j,   T_j = sum_{i >= j} M''_ij x_i,   M''_jj = M_jj, M''_ij = 2 M_ij (i > j),
+// so column tile jt only needs the samples i >= 32 jt: K stages below (32 jt) / 128 are skipped
+// and the contraction costs N^2/2 instead of N (N - D) multiply-adds per variant.  Long and
+// short tiles alternate so that the epilogue of a short one hides behind the next long one.
+__device__ __forceinline__ void tc_tile_of(const TcArgs &a, int q, int &jt, int &ks0) {
+    const int nreg = a.jtiles - (a.n_special > 0 ? 1 : 0);
+    if (q >= nreg || !a.tri) {
+        jt = q;
+        ks0 = 0;
+        return;
+    }
+    jt = (q & 1) ? (nreg - 1 - (q >> 1)) : (q >> 1);
+    ks0 = (jt * TC_JT) / TC_KSTAGE;
+}
+
+struct TcStageIter {
+    int q, ks, jt;
+    __device__ __forceinline__ void init(const TcArgs &a) {
+        q = 0;
+        int k0;
+        tc_tile_of(a, 0, jt, k0);
+        ks = k0;
+    }
+    __device__ __forceinline__ bool valid(const TcArgs &a) const { return q < a.jtiles; }
+    __device__ __forceinline__ void next(const TcArgs &a) {
+        if (++ks >= a.nks) {
+            ++q;
+            if (q < a.jtiles) {
+                int k0;
+                tc_tile_of(a, q, jt, k0);
+                ks = k0;
+            }
+        }
+    }
 };
 
 // ---------------------------------------------------------------------------------------
@@ -257,8 +297,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         int st = 0;
         uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (int jt = 0; jt < args.jtiles; ++jt)
-                for (int ks = 0; ks < args.nks; ++ks) {
+            for (int q = 0; q < args.jtiles; ++q) {
+                int jt, ks0;
+                tc_tile_of(args, q, jt, ks0);
+                for (int ks = ks0; ks < args.nks; ++ks) {
                     mbar_wait(empty0 + st * 8, ph ^ 1);
                     if (elect_one()) {
                         const uint32_t bar = full0 + st * 8;
@@ -268,16 +310,19 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     __syncwarp();
                     if (++st == ns) { st = 0; ph ^= 1; }
                 }
+            }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops, one lane issues) ============
         int st = 0, acc = 0;
         uint32_t ph = 0, phacc = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (int jt = 0; jt < args.jtiles; ++jt) {
+            for (int q = 0; q < args.jtiles; ++q) {
+                int jt, ks0;
+                tc_tile_of(args, q, jt, ks0);
                 mbar_wait(smem_u32(&accEmpty[acc]), phacc ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * UMMA_N);
-                for (int ks = 0; ks < args.nks; ++ks) {
+                for (int ks = ks0; ks < args.nks; ++ks) {
                     mbar_wait(full0 + st * 8, ph);
                     tc_fence_after();
                     if (elect_one()) {
@@ -286,7 +331,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             tc_mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc + (uint64_t)(kk * 2), IDESC,
-                                         (ks | kk) != 0 ? 1u : 0u);
+                                         (ks != ks0 || kk != 0) ? 1u : 0u);
                         tc_commit(empty0 + st * 8);
                         if (ks == args.nks - 1) tc_commit(smem_u32(&accFull[acc]));
                     }
@@ -338,26 +383,23 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
             auto gload = [&](int ks) -> uint4 {
                 return (grow_id >= 0 && ks < gwords4) ? __ldg(grow + ks) : make_uint4(0u, 0u, 0u, 0u);
             };
-            // first stage of this group in the tile: ks = 0 if the running parity matches, else 1
+            // this group takes every second stage of the tile's (component tile, K stage)
+            // sequence, starting at the first one whose global parity matches the group
+            TcStageIter it;
+            it.init(args);
+            if ((int)parity != grp) it.next(args);
             uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (!args.bits_in_smem) {
-                int ks0 = ((int)parity == grp) ? 0 : 1;
-                if (ks0 >= args.nks) ks0 = 0;
-                nxt = gload(ks0);
-            }
-            for (int jt = 0; jt < args.jtiles; ++jt)
-                for (int ks = 0; ks < args.nks; ++ks, parity ^= 1u) {
-                    if ((int)parity != grp) continue;
+            if (!args.bits_in_smem && it.valid(args)) nxt = gload(it.ks);
+            while (it.valid(args)) {
                     uint4 w4;
+                    TcStageIter nx = it;
+                    nx.next(args);
+                    nx.next(args);
                     if (args.bits_in_smem) {
-                        w4 = *reinterpret_cast<const uint4 *>(myrow + ks * 4);
+                        w4 = *reinterpret_cast<const uint4 *>(myrow + it.ks * 4);
                     } else {
                         w4 = nxt;
-                        // this group's next stage: two positions on in the (jt, ks) sequence
-                        int kn = ks + 2;
-                        if (kn >= args.nks) kn -= args.nks;
-                        if (kn >= args.nks) kn -= args.nks;       // nks == 1
-                        nxt = gload(kn);
+                        if (nx.valid(args)) nxt = gload(nx.ks);
                     }
                     mbar_wait(empty0 + sa * 8, pha ^ 1);
                     tc_fence_after();
@@ -378,7 +420,9 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     if (lane == 0) mbar_arrive(full0 + sa * 8);
                     sa += 2;
                     if (sa >= ns) { sa -= ns; pha ^= 1u; }
-                }
+                    it = nx;
+            }
+            parity ^= (uint32_t)(args.stages_per_tile & 1);
         }
     } else {
         // ===================== epilogue (warps 10..13) =====================
@@ -393,7 +437,14 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
             double a = 0.0, bsum = 0.0, pp = 0.0;
             const int t_own = tile * TC_TILE_V + v;
             const int row_own = t_own < n_tested ? args.idx[t_own] : -1;
-            for (int jt = 0; jt < args.jtiles; ++jt) {
+            const uint32_t *grow = args.bits + (size_t)(row_own < 0 ? 0 : row_own) * args.Wrow;
+            for (int q2 = 0; q2 < args.jtiles; ++q2) {
+                int jt, ks0_unused;
+                tc_tile_of(args, q2, jt, ks0_unused);
+                // triangular form: column j of this tile counts only if the variant carries
+                // sample j -- the tile's 32 samples are word jt of the variant's packed row
+                uint32_t xword = 0u;
+                if (args.tri && jt != jt_special && row_own >= 0) xword = __ldg(grow + jt);
                 mbar_wait(smem_u32(&accFull[acc]), phacc);
                 tc_fence_after();
                 const uint32_t col0 = (uint32_t)(acc * UMMA_N);
@@ -414,7 +465,11 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                             double g = (double)d[NSL - 1][c];
 #pragma unroll
                             for (int s = NSL - 2; s >= 0; --s) g = fma(g, 256.0, (double)d[s][c]);
-                            a = fma(g * g, __ldg(sc + c), a);
+                            if (args.tri) {
+                                if ((xword >> (c0 + c)) & 1u) a = fma(g, __ldg(sc + c), a);
+                            } else {
+                                a = fma(g * g, __ldg(sc + c), a);
+                            }
                         }
                     } else {
                         // columns come in (hi, lo) pairs: pair 0 = v, pairs 1.. = Q_e
@@ -473,24 +528,67 @@ __host__ __device__ __forceinline__ int tc_kpos(int i) {
     return (i & ~31) | (((i32 & 7) << 2) | (i32 >> 3));
 }
 
+// value of the operand at (sample i, column j): L itself, or (tri) the triangular M''
+__device__ __forceinline__ double tc_src(const double *__restrict__ A, int ld, int i, int j, int tri) {
+    const double x = A[(size_t)i * ld + j];
+    if (!tri) return x;
+    return i > j ? 2.0 * x : (i == j ? x : 0.0);
+}
+
 __global__ void k_tc_colexp(const double *__restrict__ L, int N, int Jpad, int J, int nsl,
-                            int *__restrict__ expo, double *__restrict__ scale2, int Jq) {
+                            int *__restrict__ expo, double *__restrict__ scale2, int Jq, int tri) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= Jq) return;
     double mx = 0.0;
     if (j < J)
-        for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(L[(size_t)i * Jpad + j]));
+        for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(tc_src(L, Jpad, i, j, tri)));
     int e = 0;
     if (mx > 0.0) {
         frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
     }
     expo[j] = e;
-    scale2[j] = (mx > 0.0) ? ldexp(1.0, 2 * (e - (8 * nsl - 2))) : 0.0;
+    // regular tiles: squared scale (a += g^2 s^2); triangular tiles: plain scale (a += g s)
+    scale2[j] = (mx > 0.0) ? ldexp(1.0, (tri ? 1 : 2) * (e - (8 * nsl - 2))) : 0.0;
+}
+
+// M = L L' (N x N, fp64) for the triangular form; 64 x 64 tiles, 4 x 4 outputs per thread
+__global__ void __launch_bounds__(256)
+k_tc_syrk(const double *__restrict__ L, int Lrows, int Jpad, double *__restrict__ M, int ldm) {
+    __shared__ double As[16][64 + 1], Bs[16][64 + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    double acc[4][4] = {};
+    for (int k0 = 0; k0 < Jpad; k0 += 16) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+            const int r = e >> 4, kk = e & 15;       // row within the tile, k within the chunk
+            As[kk][r] = (i0 + r < Lrows) ? L[(size_t)(i0 + r) * Jpad + k0 + kk] : 0.0;
+            Bs[kk][r] = (j0 + r < Lrows) ? L[(size_t)(j0 + r) * Jpad + k0 + kk] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { a[r] = As[kk][ty * 4 + r]; b[r] = Bs[kk][tx * 4 + r]; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fma(a[r], b[c], acc[r][c]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = i0 + ty * 4 + r, j = j0 + tx * 4 + c;
+            if (i < ldm && j < ldm) M[(size_t)i * ldm + j] = acc[r][c];
+        }
 }
 
 __global__ void k_tc_quantise(const double *__restrict__ L, int N, int Jpad, int J, int nsl,
                               const int *__restrict__ expo, int8_t *__restrict__ Lq, int Kpad,
-                              int Jq) {
+                              int Jq, int tri) {
     // thread per (i, j): i fastest so that the int8 stores of a warp are contiguous
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)Jq * Kpad;
@@ -499,7 +597,7 @@ __global__ void k_tc_quantise(const double *__restrict__ L, int N, int Jpad, int
     int i = (int)(e - (size_t)j * Kpad);
     long long qv = 0;
     if (i < N && j < J) {
-        double x = L[(size_t)i * Jpad + j];
+        double x = tc_src(L, Jpad, i, j, tri);
         qv = llrint(ldexp(x, (8 * nsl - 2) - expo[j]));
     }
     int jt = j / TC_JT, c = j - jt * TC_JT;
@@ -583,8 +681,25 @@ static void tc_special_column(const double *u, int N, int nsl, int Kpad, int8_t 
 int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, int ldq) {
     const int nsl = c->precision;
     PSB_REQUIRE(nsl >= 3 && nsl <= 7, PSB_ERR_ARG, "int8 slice count must be in 3..7, got %d", nsl);
-    const int N = c->N, J = c->J;
+    const int N = c->N;
     c->n_slices = nsl;
+    // triangular form (default): the operand is M'' (N x N, from M = L L'), half the work of
+    // the rectangular L form, which stays available (PSB_TC_TRI=0) as a cross-check
+    c->tc_tri = !(getenv("PSB_TC_TRI") && atoi(getenv("PSB_TC_TRI")) == 0);
+    const int J = c->tc_tri ? N : c->J;
+    const double *src = c->d_L;
+    int src_ld = c->Jpad;
+    double *d_M = nullptr;
+    if (c->tc_tri) {
+        const int ldm = ((N + 63) / 64) * 64;
+        PSB_CUDA(cudaMalloc(&d_M, (size_t)ldm * ldm * sizeof(double)));
+        dim3 g(ldm / 64, ldm / 64);
+        k_tc_syrk<<<g, 256, 0, c->stream>>>(c->d_L, c->Lrows, c->Jpad, d_M, ldm);
+        c->launches++;
+        PSB_CUDA(cudaGetLastError());
+        src = d_M;
+        src_ld = ldm;
+    }
     const int jt_reg = (J + TC_JT - 1) / TC_JT;
     // the special tile holds 1 + r hi/lo pairs; with more than 15 covariate columns the
     // masked column sums stay on the CUDA-core path (psb_varstats.cu)
@@ -598,13 +713,14 @@ int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, in
     PSB_CUDA(cudaMalloc(&c->d_scale2, Jall * sizeof(double)));
     size_t lq_bytes = (size_t)Jall * nsl * c->Kpad;
     PSB_CUDA(cudaMalloc(&c->d_Lq, lq_bytes));
-    k_tc_colexp<<<psb_div_up(Jq, 128), 128, 0, c->stream>>>(c->d_L, N, c->Jpad, J, nsl, d_expo,
-                                                           c->d_scale2, Jq);
+    k_tc_colexp<<<psb_div_up(Jq, 128), 128, 0, c->stream>>>(src, N, src_ld, J, nsl, d_expo,
+                                                           c->d_scale2, Jq, c->tc_tri ? 1 : 0);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
     size_t total = (size_t)Jq * c->Kpad;
-    k_tc_quantise<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->d_L, N, c->Jpad, J, nsl,
-                                                                         d_expo, c->d_Lq, c->Kpad, Jq);
+    k_tc_quantise<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(src, N, src_ld, J, nsl,
+                                                                         d_expo, c->d_Lq, c->Kpad, Jq,
+                                                                         c->tc_tri ? 1 : 0);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
     if (c->tc_special) {
@@ -622,6 +738,7 @@ int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, in
     }
     PSB_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d_expo);
+    if (d_M) cudaFree(d_M);
 
     return tc_make_tensor_map(c, Jall, nsl);
 }
@@ -637,6 +754,7 @@ int psb_tc_linear_setup(psb_ctx *c, const double *cols, int ncols, int ld) {
     const int N = c->N;
     c->n_slices = nsl;
     c->tc_special = ncols;
+    c->tc_tri = false;
     c->jtiles = 1;
     c->Kpad = ((N + TC_KSTAGE - 1) / TC_KSTAGE) * TC_KSTAGE;
     const size_t tile_bytes = (size_t)nsl * TC_JT * c->Kpad;
@@ -672,6 +790,13 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.n_tested_dev = c->d_counters;      // counters[0] = tested variants
     a.nks = c->Kpad / TC_KSTAGE;
     a.jtiles = c->jtiles;
+    a.tri = c->tc_tri ? 1 : 0;
+    {
+        const int nreg = c->jtiles - (c->tc_special > 0 ? 1 : 0);
+        int stages = (c->tc_special > 0 ? a.nks : 0);
+        for (int jt = 0; jt < nreg; ++jt) stages += a.nks - (a.tri ? (jt * TC_JT) / TC_KSTAGE : 0);
+        a.stages_per_tile = stages;
+    }
     int pitch = a.nks * 4;
     while (pitch % 32 != 4) pitch += 4;
     a.pitch = pitch;
