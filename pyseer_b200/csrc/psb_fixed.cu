@@ -947,6 +947,7 @@ extern "C" int psb_fixed_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z
             }
         }
     }
+    PSB_UPLOAD_FENCE();
     return PSB_OK;
 }
 
@@ -1019,6 +1020,7 @@ static int fx_run_null(psb_ctx *c, int mode, std::vector<double> &h) {
     if (rc) return rc;
     double *d_out = nullptr;
     PSB_CUDA(cudaMalloc(&d_out, (2 * q + 3) * sizeof(double)));
+    PSB_UPLOAD_FENCE();          // design / phenotype uploads precede the first kernel
     const uint32_t *save_bits = c->d_bits;
     const int save_wrow = c->Wrow;
     c->d_bits = nullptr;
@@ -1144,6 +1146,7 @@ extern "C" int psb_lineage_setup(psb_ctx *c, int32_t N, int32_t q, const double 
     PSB_CUDA(cudaMemcpy(c->d_Zlin, Zc.data(), Zc.size() * sizeof(double), cudaMemcpyHostToDevice));
     c->q_lin = q;
     c->n_lin = n_lineage;
+    PSB_UPLOAD_FENCE();
     return PSB_OK;
 }
 

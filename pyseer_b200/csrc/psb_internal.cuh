@@ -30,6 +30,12 @@ void psb_set_error(const char *fmt, ...);
         }                                                                           \
     } while (0)
 
+// Setup uploads use plain cudaMemcpy / cudaMemset on the legacy default stream.  The library's
+// streams are non-blocking (no implicit ordering with it) and a pageable copy may return before
+// its DMA has landed, so every setup path fences once before a kernel can read the state.
+#define PSB_UPLOAD_FENCE() PSB_CUDA(cudaDeviceSynchronize())
+
+
 #define PSB_REQUIRE(cond, code, ...)                                                \
     do {                                                                            \
         if (!(cond)) {                                                              \
@@ -76,6 +82,8 @@ struct psb_ctx {
     double *d_scale2 = nullptr;   // [Jpad32] (s_j 2^-B)^2
     int n_slices = 0, jtiles = 0;
     bool tc_tri = false;          // regular tiles hold the triangular operand M'' (psb_lmm_tc.cu)
+    uint8_t *d_shift = nullptr;   // [Jq] per-column left shift of the integer epilogue (triangular form)
+    bool tc_int_epi = false;      // triangular tiles are recombined and summed in int64
     int tc_special = 0;           // hi/lo column pairs carried by the special tile (0 = none)
     void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B)
 

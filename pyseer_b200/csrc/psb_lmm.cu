@@ -410,6 +410,7 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
     PSB_CUDA(cudaMemcpy2D(c->d_L, (size_t)c->Jpad * sizeof(double), PU.data(),
                           (size_t)J * sizeof(double), (size_t)J * sizeof(double), N,
                           cudaMemcpyHostToDevice));
+    PSB_UPLOAD_FENCE();
     c->model = PSB_MODEL_LMM;
     if (precision > 0) {
         rc = psb_lmm_tc_setup(c, cols.data(), cols.data() + c->Npad, r, c->Npad);

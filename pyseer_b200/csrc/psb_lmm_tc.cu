@@ -192,6 +192,8 @@ struct TcArgs {
     int pitch;                // smem bit-row pitch in words (== 4 mod 32)
     int bits_in_smem;         // 1: the tile's packed rows are staged in shared memory
     int tri;                  // 1: regular tiles hold the triangular operand M'' (see below)
+    int int_epi;              // 1: triangular tiles are recombined and summed in int64 (below)
+    const uint8_t *shift;     // per-column left shift for int_epi
     int stages_per_tile;      // K stages a variant tile goes through (all component tiles)
     int n_bstages;
 };
@@ -448,6 +450,50 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 mbar_wait(smem_u32(&accFull[acc]), phacc);
                 tc_fence_after();
                 const uint32_t col0 = (uint32_t)(acc * UMMA_N);
+                if (args.int_epi && jt != jt_special) {
+                    // Triangular tile, integer epilogue: the columns of a tile share one scale
+                    // 2^(e_tile - shmax - B) up to a small per-column left shift, so the slices
+                    // are recombined (g = sum_s 256^s D_s) and the carried columns summed in
+                    // int64 -- exact, no per-column int->fp64 conversion -- and the tile costs
+                    // one conversion and one fused multiply-add.
+                    long long t64 = 0;
+#pragma unroll
+                    for (int c0 = 0; c0 < TC_JT; c0 += CH) {
+                        int32_t d[NSL][CH];
+#pragma unroll
+                        for (int s = 0; s < NSL; ++s) {
+                            if constexpr (CH == 16) tc_ld16(lane_addr + col0 + s * TC_JT + c0, d[s]);
+                            else tc_ld8(lane_addr + col0 + s * TC_JT + c0, d[s]);
+                        }
+                        uint32_t shw[CH / 4];
+                        if constexpr (CH == 16) {
+                            const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(args.shift + jt * TC_JT + c0));
+                            shw[0] = s4.x; shw[1] = s4.y; shw[2] = s4.z; shw[3] = s4.w;
+                        } else {
+                            const uint2 s2 = __ldg(reinterpret_cast<const uint2 *>(args.shift + jt * TC_JT + c0));
+                            shw[0] = s2.x; shw[1] = s2.y;
+                        }
+                        tc_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < CH; ++c) {
+                            // pairs of slices fit int32 (|D_s| <= 128 N, N <= 16384)
+                            long long g = 0;
+                            int s = NSL - 1;
+                            if (NSL & 1) { g = (long long)d[s][c]; --s; }
+#pragma unroll
+                            for (; s >= 1; s -= 2)
+                                g = g * 65536 + (long long)(d[s - 1][c] + d[s][c] * 256);
+                            const uint32_t sh = (shw[c >> 2] >> (8 * (c & 3))) & 0xffu;
+                            if ((xword >> (c0 + c)) & 1u) t64 += g << sh;
+                        }
+                    }
+                    a = fma((double)t64, __ldg(args.scale2 + jt * TC_JT), a);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&accEmpty[acc]));
+                    if (++acc == 2) { acc = 0; phacc ^= 1; }
+                    continue;
+                }
                 double prev = 0.0;                    // hi part of the current hi/lo pair
 #pragma unroll
                 for (int c0 = 0; c0 < TC_JT; c0 += CH) {
@@ -535,16 +581,34 @@ __device__ __forceinline__ double tc_src(const double *__restrict__ A, int ld, i
     return i > j ? 2.0 * x : (i == j ? x : 0.0);
 }
 
+// shmax >= 0: integer epilogue (triangular form).  The 32 columns of a tile share the scale
+// 2^(e_tile - shmax - B), e_tile = the largest column exponent of the tile; column j is
+// quantised with e'_j = max(e_j, e_tile - shmax) and enters the int64 tile sum shifted left by
+// e'_j - (e_tile - shmax) in [0, shmax]: full 8k-2 bit precision relative to its own maximum
+// for columns within 2^shmax of the tile's largest, graceful below.  The tile scale goes to
+// scale2[32 jt].  One warp = one tile (blockDim is a multiple of 32).
 __global__ void k_tc_colexp(const double *__restrict__ L, int N, int Jpad, int J, int nsl,
-                            int *__restrict__ expo, double *__restrict__ scale2, int Jq, int tri) {
+                            int *__restrict__ expo, double *__restrict__ scale2, int Jq, int tri,
+                            int shmax, uint8_t *__restrict__ shift) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= Jq) return;
+    if (j >= Jq) return;                      // Jq is a multiple of 32: whole warps leave
     double mx = 0.0;
     if (j < J)
         for (int i = 0; i < N; ++i) mx = fmax(mx, fabs(tc_src(L, Jpad, i, j, tri)));
     int e = 0;
     if (mx > 0.0) {
         frexp(mx, &e);          // mx = f * 2^e, f in [0.5, 1)  =>  mx < 2^e
+    }
+    if (shmax >= 0) {
+        const int INT_MIN_E = -100000;
+        const int et = __reduce_max_sync(0xffffffffu, mx > 0.0 ? e : INT_MIN_E);
+        const int base = et - shmax;          // exponent of the tile's unit
+        const int ej = (mx > 0.0 && e > base) ? e : base;
+        expo[j] = et == INT_MIN_E ? 0 : ej;
+        shift[j] = (uint8_t)(et == INT_MIN_E ? 0 : ej - base);
+        if ((threadIdx.x & 31) == 0)
+            scale2[j] = et == INT_MIN_E ? 0.0 : ldexp(1.0, base - (8 * nsl - 2));
+        return;
     }
     expo[j] = e;
     // regular tiles: squared scale (a += g^2 s^2); triangular tiles: plain scale (a += g s)
@@ -713,8 +777,20 @@ int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, in
     PSB_CUDA(cudaMalloc(&c->d_scale2, Jall * sizeof(double)));
     size_t lq_bytes = (size_t)Jall * nsl * c->Kpad;
     PSB_CUDA(cudaMalloc(&c->d_Lq, lq_bytes));
+    // integer epilogue: 2^B (digits) * N (carriers) * 2^shmax * 32 (columns) must stay below 2^62
+    int shmax = -1;
+    c->tc_int_epi = false;
+    if (c->tc_tri && N <= 16384 && !(getenv("PSB_TC_INT_EPI") && atoi(getenv("PSB_TC_INT_EPI")) == 0)) {
+        int lg = 0;
+        while ((1 << lg) < N) ++lg;
+        shmax = std::min(5, 62 - (8 * nsl - 2) - 5 - lg);
+        c->tc_int_epi = shmax >= 0;
+    }
+    PSB_CUDA(cudaMalloc(&c->d_shift, Jq));
+    PSB_CUDA(cudaMemsetAsync(c->d_shift, 0, Jq, c->stream));
     k_tc_colexp<<<psb_div_up(Jq, 128), 128, 0, c->stream>>>(src, N, src_ld, J, nsl, d_expo,
-                                                           c->d_scale2, Jq, c->tc_tri ? 1 : 0);
+                                                           c->d_scale2, Jq, c->tc_tri ? 1 : 0,
+                                                           c->tc_int_epi ? shmax : -1, c->d_shift);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
     size_t total = (size_t)Jq * c->Kpad;
@@ -755,6 +831,7 @@ int psb_tc_linear_setup(psb_ctx *c, const double *cols, int ncols, int ld) {
     c->n_slices = nsl;
     c->tc_special = ncols;
     c->tc_tri = false;
+    c->tc_int_epi = false;
     c->jtiles = 1;
     c->Kpad = ((N + TC_KSTAGE - 1) / TC_KSTAGE) * TC_KSTAGE;
     const size_t tile_bytes = (size_t)nsl * TC_JT * c->Kpad;
@@ -766,6 +843,7 @@ int psb_tc_linear_setup(psb_ctx *c, const double *cols, int ncols, int ld) {
     PSB_CUDA(cudaMalloc(&c->d_scale2, TC_JT * sizeof(double)));
     PSB_CUDA(cudaMemcpy(c->d_Lq, tile.data(), tile_bytes, cudaMemcpyHostToDevice));
     PSB_CUDA(cudaMemcpy(c->d_scale2, sc.data(), TC_JT * sizeof(double), cudaMemcpyHostToDevice));
+    PSB_UPLOAD_FENCE();
     return tc_make_tensor_map(c, TC_JT, nsl);
 }
 
@@ -791,6 +869,8 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.nks = c->Kpad / TC_KSTAGE;
     a.jtiles = c->jtiles;
     a.tri = c->tc_tri ? 1 : 0;
+    a.int_epi = c->tc_int_epi ? 1 : 0;
+    a.shift = c->d_shift;
     {
         const int nreg = c->jtiles - (c->tc_special > 0 ? 1 : 0);
         int stages = (c->tc_special > 0 ? a.nks : 0);
@@ -839,8 +919,10 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
 void psb_lmm_tc_free(psb_ctx *c) {
     if (c->d_Lq) cudaFree(c->d_Lq);
     if (c->d_scale2) cudaFree(c->d_scale2);
+    if (c->d_shift) cudaFree(c->d_shift);
     c->d_Lq = nullptr;
     c->d_scale2 = nullptr;
+    c->d_shift = nullptr;
     if (c->tmap_Lq) delete (CUtensorMap *)c->tmap_Lq;
     c->tmap_Lq = nullptr;
 }
