@@ -142,6 +142,26 @@ int psb_submit(psb_ctx *ctx, const uint32_t *bits, const uint32_t *missing,
 int psb_submit_device(psb_ctx *ctx, const void *d_bits, const void *d_missing,
                       int64_t n_variants, int32_t words_per_row);
 
+/* Burden regions (`--vcf --burden`): replaces the region branch of input.read_variant
+ * (input.py:395-411; load_burden :250-266).  `bits` / `missing` hold one packed row per VCF
+ * RECORD (read_vcf_var applied to an empty dictionary, input.py:457-502); region r is the
+ * union of the records members[region_offsets[r] .. region_offsets[r+1]) in fetch order:
+ * carrier if any member carries the alternative allele, missing if the LAST member is missing
+ * and no member carries (the dictionary semantics of input.py:489-497).  The reduction runs on
+ * the device and leaves n_regions rows submitted, as psb_submit would; region_offsets has
+ * n_regions + 1 entries starting at 0.  psb_submit_burden_device takes device-resident record
+ * rows (they must stay valid until the next psb_run_* has been queued); psb_submitted_device
+ * returns the device pointers of the rows currently submitted (e.g. by psb_synth_device). */
+int psb_submit_burden(psb_ctx *ctx, const uint32_t *bits, const uint32_t *missing,
+                      int64_t n_variants, int32_t words_per_row, const int64_t *region_offsets,
+                      const int32_t *members, int64_t n_regions);
+int psb_submit_burden_device(psb_ctx *ctx, const void *d_bits, const void *d_missing,
+                             int64_t n_variants, int32_t words_per_row,
+                             const int64_t *region_offsets, const int32_t *members,
+                             int64_t n_regions);
+int psb_submitted_device(psb_ctx *ctx, const void **d_bits, const void **d_missing,
+                         int64_t *n_variants, int32_t *words_per_row);
+
 /* ---- the hot path ------------------------------------------------------------ */
 /* replaces lmm.fit_lmm (lmm.py:125-226) for every submitted variant */
 int psb_run_lmm(psb_ctx *ctx, const psb_params *params);
@@ -179,6 +199,9 @@ int psb_counts(psb_ctx *ctx, int64_t out[4]);
 int psb_host_alloc(size_t bytes, void **out);
 int psb_host_free(void *ptr);
 int psb_download_bits(psb_ctx *ctx, uint32_t *out_bits);
+/* same, with the missing-genotype rows (skipped when the batch has none: *has_missing = 0) */
+int psb_download_rows(psb_ctx *ctx, uint32_t *out_bits, uint32_t *out_missing,
+                      int32_t *has_missing);
 
 /* ---- sample similarity (kinship) matrix ----------------------------------------------- */
 /* K = G G' of pyseer/similarity.py:99-116 over packed rows: K[i][j] = number of variants that

@@ -215,7 +215,15 @@ def main(argv=None):
         sys.stderr.write('h^2 = ' + '{0:.2f}'.format(h2) + '\n')
 
     if o.vcf:
-        reader = VcfReader(o.vcf, p, o.burden)
+        # burden regions are reduced on the device (psb_submit_burden) through the context the
+        # model already owns
+        eng = (lmm.engine(h2) if o.lmm else model.engine) if o.burden else None
+
+        def device_union(vbits, vmiss, offsets, members):
+            eng.submit_burden(vbits, vmiss, offsets, members)
+            return eng.download_rows()
+
+        reader = VcfReader(o.vcf, p, o.burden, reducer=device_union if o.burden else None)
     else:
         reader = VariantReader('kmers' if o.kmers else 'Rtab', o.kmers or o.pres, p, o.uncompressed)
 

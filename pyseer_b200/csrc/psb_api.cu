@@ -112,6 +112,7 @@ int psb_destroy(psb_ctx *c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
     psb_kinship_release(c);
+    psb_burden_release(c);
     psb_free_model(c);
     free_tables(c);
     for (int i = 0; i < 2; ++i) {
@@ -390,6 +391,23 @@ int psb_download_bits(psb_ctx *c, uint32_t *out_bits) {
     size_t bytes = (size_t)c->S * c->Wrow * sizeof(uint32_t);
     if (bytes)
         PSB_CUDA(cudaMemcpyAsync(out_bits, c->d_bits, bytes, cudaMemcpyDeviceToHost, c->stream));
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    return PSB_OK;
+}
+
+int psb_download_rows(psb_ctx *c, uint32_t *out_bits, uint32_t *out_missing, int32_t *has_missing) {
+    PSB_REQUIRE(c && out_bits, PSB_ERR_ARG, "NULL argument");
+    PSB_CUDA(cudaSetDevice(c->device));
+    int rc = psb_run_begin(c);
+    if (rc) return rc;
+    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "no rows submitted");
+    size_t bytes = (size_t)c->S * c->Wrow * sizeof(uint32_t);
+    if (bytes) {
+        PSB_CUDA(cudaMemcpyAsync(out_bits, c->d_bits, bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (out_missing && c->d_miss)
+            PSB_CUDA(cudaMemcpyAsync(out_missing, c->d_miss, bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (has_missing) *has_missing = c->d_miss ? 1 : 0;
     PSB_CUDA(cudaStreamSynchronize(c->stream));
     return PSB_OK;
 }

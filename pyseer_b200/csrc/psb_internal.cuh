@@ -145,6 +145,16 @@ struct psb_ctx {
     int64_t counts[4] = {0, 0, 0, 0};
     bool ran = false;
     void *kin = nullptr;          // psb_kinship.cu state
+
+    // ---- burden regions (psb_burden.cu) ----
+    uint32_t *bur_vbits = nullptr, *bur_vmiss = nullptr;   // member record rows (host submits)
+    uint32_t *bur_out = nullptr, *bur_outmiss = nullptr;   // region rows
+    int64_t *bur_offs = nullptr;
+    int32_t *bur_members = nullptr;
+    size_t bur_vbits_cap = 0, bur_vmiss_cap = 0, bur_out_cap = 0, bur_outmiss_cap = 0,
+           bur_offs_cap = 0, bur_members_cap = 0;
+    cudaEvent_t ev_bur_copy = nullptr, ev_bur_done = nullptr;
+    bool bur_done_valid = false;
 };
 
 int psb_ensure_capacity(psb_ctx *ctx, int64_t S, int betas_cols);
@@ -152,6 +162,7 @@ int psb_run_begin(psb_ctx *ctx);
 int psb_run_end(psb_ctx *ctx);
 int psb_free_model(psb_ctx *ctx);
 void psb_kinship_release(psb_ctx *ctx);
+void psb_burden_release(psb_ctx *ctx);
 
 // psb_varstats.cu
 int psb_launch_bitsums(psb_ctx *ctx);

@@ -137,6 +137,13 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void tc_wait_st() {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
@@ -251,13 +258,19 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int ns = args.n_bstages;                 // pipeline depth (<= NA)
+    const int ns = args.n_bstages;                 // operand (B) ring depth; may exceed NA
+    const int na = ns < NA ? ns : NA;              // A ring depth in use
     uint8_t *sB = smem;                                               // ns stages
     uint32_t *sBits = (uint32_t *)(sB + (size_t)ns * STAGE_BYTES);    // 128 x pitch words
     uint64_t *bars = (uint64_t *)(sBits + (size_t)TC_TILE_V * args.pitch);
-    // One ring for both operands of a K stage: full[s] completes when the TMA bytes of the
-    // B stage have landed AND the four expander warps have stored the A stage in TMEM;
-    // empty[s] is signalled by tcgen05.commit once the stage's MMAs have retired.
+    // One barrier pair per K stage in flight, indexed by the B slot t % ns of stage t: full[s]
+    // completes when the TMA bytes of the B stage have landed AND the four expander warps have
+    // stored the A stage in TMEM; empty[s] is signalled by tcgen05.commit once the stage's MMAs
+    // have retired.  The A stage of stage t lives in TMEM slot t % NA.  The B ring may be
+    // deeper than the A ring (ns >= NA): the producer refills B slot t % ns after the commit
+    // of stage t - ns, the expanders rewrite A slot t % NA after the commit of stage t - NA,
+    // which they observe on the same barrier array (empty[(t - NA) % ns]) -- one commit per
+    // stage serves both.  The extra depth covers the L2 latency of the TMA loads.
     uint64_t *full = bars;                        // [ns]
     uint64_t *empty = full + 16;                  // [ns]
     uint64_t *accFull = empty + 16;               // [2]
@@ -315,7 +328,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
             }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops, one lane issues) ============
-        int st = 0, acc = 0;
+        int st = 0, sta = 0, acc = 0;
         uint32_t ph = 0, phacc = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
             for (int q = 0; q < args.jtiles; ++q) {
@@ -329,7 +342,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t bdesc = make_b_desc(sB0 + st * STAGE_BYTES);
-                        const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + st * 32);
+                        const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + sta * 32);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
                             tc_mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc + (uint64_t)(kk * 2), IDESC,
@@ -339,6 +352,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     }
                     __syncwarp();
                     if (++st == ns) { st = 0; ph ^= 1; }
+                    if (++sta == na) sta = 0;
                 }
                 if (++acc == 2) { acc = 0; phacc ^= 1; }
             }
@@ -350,11 +364,32 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         const int et = (warp - 2) * 32 + lane;        // 0..255 cooperative-copy index
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const int chunks_per_row = args.nks;          // 16-byte chunks (4 words = 128 samples)
-        // ring position of the next stage this group handles (the group takes every second
-        // stage of the global sequence; ns is even, so it stays on slots of its own parity)
-        int sa = grp;
-        uint32_t pha = 0;
+        // The group takes every second stage t of the global sequence.  sb: barrier (B) slot
+        // t % ns of its next stage; sa: A slot t % na; (we, wph): slot and phase of
+        // empty[(t - na) % ns], the commit that frees the A slot -- not waited for during the
+        // first na stages of the kernel (`lead` of them belong to this group).
+        int sb = grp, sa = grp;
+        int lead = (na - grp + 1) / 2;
+        int we = grp + 2 * lead - na;
+        uint32_t wph = 0;
         uint32_t parity = 0;                          // parity of the global stage counter
+        const int nks = args.nks, jtiles = args.jtiles;
+        const int nreg_x = (args.tri != 0) ? jtiles - (args.n_special > 0 ? 1 : 0) : 0;
+        // first K stage of the q-th component tile of the sequence (tc_tile_of)
+        auto first_ks = [&](int q2) -> int {
+            if (q2 >= nreg_x) return 0;
+            const int jt = (q2 & 1) ? (nreg_x - 1 - (q2 >> 1)) : (q2 >> 1);
+            return (jt * TC_JT) / TC_KSTAGE;
+        };
+        // two stages forward in the sequence; the cursor is valid while cq < jtiles
+        auto advance2 = [&](int &cq, int &cks) {
+            cks += 2;
+            while (cks >= nks) {
+                const int over = cks - nks;
+                if (++cq >= jtiles) return;
+                cks = first_ks(cq) + over;
+            }
+        };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             // all expanders are done reading the previous tile's bits
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -375,7 +410,6 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const uint32_t *myrow = sBits + (size_t)v * args.pitch;
             // Large N (the tile's bits would crowd the operand ring out of shared memory): each
             // thread reads its 16 bytes per stage straight from its global row (L2-resident
             // after the first component tile), fetched one of its stages ahead.
@@ -385,44 +419,68 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
             auto gload = [&](int ks) -> uint4 {
                 return (grow_id >= 0 && ks < gwords4) ? __ldg(grow + ks) : make_uint4(0u, 0u, 0u, 0u);
             };
-            // this group takes every second stage of the tile's (component tile, K stage)
-            // sequence, starting at the first one whose global parity matches the group
-            TcStageIter it;
-            it.init(args);
-            if ((int)parity != grp) it.next(args);
-            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (!args.bits_in_smem && it.valid(args)) nxt = gload(it.ks);
-            while (it.valid(args)) {
-                    uint4 w4;
-                    TcStageIter nx = it;
-                    nx.next(args);
-                    nx.next(args);
-                    if (args.bits_in_smem) {
-                        w4 = *reinterpret_cast<const uint4 *>(myrow + it.ks * 4);
-                    } else {
-                        w4 = nxt;
-                        if (nx.valid(args)) nxt = gload(nx.ks);
-                    }
-                    mbar_wait(empty0 + sa * 8, pha ^ 1);
-                    tc_fence_after();
-                    const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-                    const uint32_t base = lane_addr + (uint32_t)(A_COL0 + sa * 32);
+            // This group takes every second stage of the tile's (component tile, K stage)
+            // sequence, starting at the first one whose global parity matches the group.  The
+            // cursor (cq, cks) steps two stages at a time; leaving a component tile (rare: once
+            // per ~20 stages) carries the overshoot into the next one.  Everything the loop
+            // needs from `args` sits in registers: the per-stage control flow is a handful of
+            // instructions next to the 64 ALU operations of the expansion itself.
+            int cq = 0, cks = first_ks(0) + (((int)parity != grp) ? 1 : 0) - 2;
+            advance2(cq, cks);
+            // expand one 128-sample stage of this thread's variant into A slot sa, then signal
+            auto emit = [&](const uint4 &w4) {
+                if (lead > 0) {
+                    --lead;
+                } else {
+                    mbar_wait(empty0 + we * 8, wph);
+                    we += 2;
+                    if (we >= ns) { we -= ns; wph ^= 1u; }
+                }
+                tc_fence_after();
+                const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                const uint32_t base = lane_addr + (uint32_t)(A_COL0 + sa * 32);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        // register b, byte t <- sample 8 t + b of the word (the B operand is
-                        // stored with the same permutation, see k_tc_quantise)
-                        uint32_t r[8];
+                for (int i = 0; i < 4; ++i) {
+                    // register b, byte t <- sample 8 t + b of the word (the B operand is
+                    // stored with the same permutation, see k_tc_quantise)
+                    uint32_t r[8];
 #pragma unroll
-                        for (int b = 0; b < 8; ++b) r[b] = (ws[i] >> b) & 0x01010101u;
-                        tc_st8(base + i * 8, r);
+                    for (int b = 0; b < 8; ++b) r[b] = (ws[i] >> b) & 0x01010101u;
+                    tc_st8(base + i * 8, r);
+                }
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full0 + sb * 8);
+                sb += 2;
+                if (sb >= ns) sb -= ns;
+                sa += 2;
+                if (sa >= na) sa -= na;
+            };
+            if (args.bits_in_smem) {
+                const uint32_t myrow_s = smem_u32(sBits + (size_t)v * args.pitch);
+                while (cq < jtiles) {
+                    const uint4 w4 = lds128(myrow_s + (uint32_t)cks * 16u);
+                    emit(w4);
+                    advance2(cq, cks);
+                }
+            } else {
+                // global-row mode: the words of the group's next two stages are in flight
+                int pq = cq, pks = cks;
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = make_uint4(0u, 0u, 0u, 0u);
+                if (pq < jtiles) nxt = gload(pks);
+                advance2(pq, pks);
+                if (pq < jtiles) nxt2 = gload(pks);
+                while (cq < jtiles) {
+                    const uint4 w4 = nxt;
+                    nxt = nxt2;
+                    if (pq < jtiles) {
+                        advance2(pq, pks);
+                        if (pq < jtiles) nxt2 = gload(pks);
                     }
-                    tc_wait_st();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(full0 + sa * 8);
-                    sa += 2;
-                    if (sa >= ns) { sa -= ns; pha ^= 1u; }
-                    it = nx;
+                    emit(w4);
+                    advance2(cq, cks);
+                }
             }
             parity ^= (uint32_t)(args.stages_per_tile & 1);
         }
@@ -882,16 +940,28 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.pitch = pitch;
     int smem_max = 0;
     PSB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    int nb = (512 - 2 * TC_JT * nsl) / 32;      // TMEM A-ring depth bounds the pipeline
-    // the tile's packed rows live in shared memory unless that would cost operand stages
-    a.bits_in_smem = tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max ? 1 : 0;
+    const int na = (512 - 2 * TC_JT * nsl) / 32;          // TMEM A-ring depth (kernel: NA)
+    // Operand ring depth: as many stages as shared memory holds, at most TC_MAX_BSTAGES.  The
+    // tile's packed rows share shared memory with the ring; they stay there as long as the ring
+    // keeps at least the depth of the TMEM A ring (measured at N=5000: rows in shared memory
+    // with 6-7 stages beat global rows with 11), otherwise the expanders read their rows from
+    // global memory (PSB_TC_BITS_SMEM=0/1 forces either mode, PSB_TC_STAGES caps the depth).
+    auto depth = [&](int pit) {
+        int nb = TC_MAX_BSTAGES;
+        while (nb > 2 && tc_smem_bytes(nsl, nb, pit) > (size_t)smem_max) --nb;
+        return nb;
+    };
+    const int nb_smem = depth(pitch), nb_glob = depth(4);
+    a.bits_in_smem = (tc_smem_bytes(nsl, nb_smem, pitch) <= (size_t)smem_max && nb_smem >= na) ? 1 : 0;
     if (getenv("PSB_TC_GLOBAL_BITS")) a.bits_in_smem = 0;      // test hook: force the large-N mode
+    if (getenv("PSB_TC_BITS_SMEM") && tc_smem_bytes(nsl, nb_smem, pitch) <= (size_t)smem_max)
+        a.bits_in_smem = atoi(getenv("PSB_TC_BITS_SMEM")) ? 1 : 0;
     if (!a.bits_in_smem) {
         pitch = 4;                               // no bit tile in shared memory
         a.pitch = pitch;
     }
-    // (kept even: the two expander groups own the slots of their own parity)
-    while (nb > 2 && tc_smem_bytes(nsl, nb, pitch) > (size_t)smem_max) nb -= 2;
+    int nb = a.bits_in_smem ? nb_smem : nb_glob;
+    if (getenv("PSB_TC_STAGES")) nb = std::max(2, std::min(nb, atoi(getenv("PSB_TC_STAGES"))));
     PSB_REQUIRE(tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max, PSB_ERR_UNSUPPORTED,
                 "n_samples = %d needs more shared memory than the tensor path has; use precision 0",
                 c->N);

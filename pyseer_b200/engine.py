@@ -200,6 +200,56 @@ class Engine(object):
                                   bits.shape[0], bits.shape[1]))
         self.n_variants = bits.shape[0]
 
+    def submit_burden(self, bits, missing, region_offsets, members):
+        """Burden regions (input.py:395-411): ``bits`` / ``missing`` hold one packed row per VCF
+        record; region r is the union of records ``members[region_offsets[r]:region_offsets[r+1]]``.
+        The union is formed on the device and left submitted (one row per region)."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint32)
+        if bits.ndim != 2:
+            raise ValueError('bits must be (n_records, words_per_row)')
+        mp = None
+        if missing is not None:
+            missing = np.ascontiguousarray(missing, dtype=np.uint32)
+            if missing.shape != bits.shape:
+                raise ValueError('missing must have the shape of bits')
+            mp = missing.ctypes.data_as(c_void_p)
+        offs = np.ascontiguousarray(region_offsets, dtype=np.int64)
+        mem = np.ascontiguousarray(members, dtype=np.int32)
+        if offs.ndim != 1 or offs.shape[0] < 1 or (offs.shape[0] > 1 and offs[-1] != mem.shape[0]):
+            raise ValueError('region_offsets must have n_regions + 1 entries ending at len(members)')
+        self._keep = [bits, missing]
+        check(self.lib.psb_submit_burden(self._ctx, bits.ctypes.data_as(c_void_p), mp, bits.shape[0],
+                                         bits.shape[1], offs.ctypes.data_as(c_void_p),
+                                         mem.ctypes.data_as(c_void_p), offs.shape[0] - 1))
+        self.n_variants = offs.shape[0] - 1
+
+    def submit_burden_device(self, d_bits_ptr, n_records, wpr, region_offsets, members,
+                             d_missing_ptr=None):
+        offs = np.ascontiguousarray(region_offsets, dtype=np.int64)
+        mem = np.ascontiguousarray(members, dtype=np.int32)
+        check(self.lib.psb_submit_burden_device(
+            self._ctx, c_void_p(d_bits_ptr), c_void_p(d_missing_ptr) if d_missing_ptr else None,
+            int(n_records), int(wpr), offs.ctypes.data_as(c_void_p), mem.ctypes.data_as(c_void_p),
+            offs.shape[0] - 1))
+        self.n_variants = offs.shape[0] - 1
+
+    def submitted_device(self):
+        """(device pointer of the submitted rows, of the missing rows or None, rows, words/row)"""
+        b, m = c_void_p(), c_void_p()
+        n, w = c_int64(0), ctypes.c_int32(0)
+        check(self.lib.psb_submitted_device(self._ctx, byref(b), byref(m), byref(n), byref(w)))
+        return b.value, m.value, n.value, w.value
+
+    def download_rows(self):
+        """Host copy of the submitted rows: (bits, missing or None)."""
+        _, _, n, w = self.submitted_device()
+        bits = np.zeros((n, w), dtype=np.uint32)
+        miss = np.zeros((n, w), dtype=np.uint32)
+        has = ctypes.c_int32(0)
+        check(self.lib.psb_download_rows(self._ctx, bits.ctypes.data_as(c_void_p),
+                                         miss.ctypes.data_as(c_void_p), byref(has)))
+        return bits, (miss if has.value else None)
+
     def submit_device(self, d_bits_ptr, n_variants, wpr, d_missing_ptr=None):
         check(self.lib.psb_submit_device(self._ctx, c_void_p(d_bits_ptr),
                                          c_void_p(d_missing_ptr) if d_missing_ptr else None,

@@ -195,6 +195,25 @@ class VariantReader(object):
         return x.astype(np.int64)
 
 
+def burden_union_host(vbits, vmiss, offsets, members):
+    """Union of VCF record rows per burden region (input.py:395-411 with the dictionary rules of
+    read_vcf_var, input.py:489-497), NumPy statement of what ``psb_submit_burden`` computes on the
+    device: carrier if any member record carries, missing if the LAST member record is missing
+    and none carries.  Returns (bits, missing or None)."""
+    R = len(offsets) - 1
+    W = vbits.shape[1]
+    bits = np.zeros((R, W), dtype=np.uint32)
+    miss = np.zeros((R, W), dtype=np.uint32) if vmiss is not None else None
+    for r in range(R):
+        mem = members[offsets[r]:offsets[r + 1]]
+        if len(mem) == 0:
+            continue
+        bits[r] = np.bitwise_or.reduce(vbits[mem], axis=0)
+        if miss is not None:
+            miss[r] = vmiss[mem[-1]] & ~bits[r]
+    return bits, miss
+
+
 class VcfReader(object):
     """VCF (and burden-region) input without pysam: plain or gzip text VCF, dominant encoding.
 
@@ -207,7 +226,7 @@ class VcfReader(object):
     (input.py:395-411, load_burden :250-266); the whole VCF is held in memory for that.
     Produces the same VariantBatch objects as VariantReader."""
 
-    def __init__(self, path, p, burden_file=None):
+    def __init__(self, path, p, burden_file=None, reducer=None):
         import gzip
         self.samples = [str(s) for s in p.index]
         self.index = {s: i for i, s in enumerate(self.samples)}
@@ -225,13 +244,38 @@ class VcfReader(object):
         if self.cols is None:
             raise ValueError('no #CHROM header line found; is this a VCF file?')
         self.regions = None
+        # burden regions: `reducer(vbits, vmiss, offsets, members) -> (bits, missing)` forms the
+        # per-region union of record rows; the CLI plugs the device reduction in
+        # (Engine.submit_burden), the default is the NumPy statement of the same rule
+        self.reducer = reducer or burden_union_host
         if burden_file:
             self.regions = []
             with open(burden_file) as rf:
                 for line in rf:
                     name, spec = line.rstrip().split()
                     self.regions.append((name, spec.split(',')))
-            self.records = [self._split(line) for line in self.fh if line.strip()]
+            # every record is parsed once into a packed row (read_vcf_var on an empty dictionary);
+            # skipped records (multi-allelic, filtered) never touch a region's dictionary
+            contig, start, end, states = [], [], [], []
+            for line in self.fh:
+                if not line.strip():
+                    continue
+                f = self._split(line)
+                state = np.zeros(self.n_samples, dtype=np.int8)
+                if self._apply(f, state) is None:
+                    continue
+                contig.append(f[0])
+                start.append(int(f[1]) - 1)
+                end.append(int(f[1]) - 1 + len(f[3]))
+                states.append(state)
+            self.rec_contig = np.array(contig, dtype=object)
+            self.rec_start = np.array(start, dtype=np.int64)
+            self.rec_end = np.array(end, dtype=np.int64)
+            if states:
+                packed = self._pack([''] * len(states), states)
+                self.rec_bits, self.rec_miss = packed.bits, packed.missing
+            else:
+                self.rec_bits, self.rec_miss = np.zeros((0, self.W), dtype=np.uint32), None
 
     def close(self):
         self.fh.close()
@@ -275,32 +319,52 @@ class VcfReader(object):
         return name
 
     def _rows(self):
-        if self.regions is None:
-            for line in self.fh:
-                if not line.strip():
-                    continue
-                state = np.zeros(self.n_samples, dtype=np.int8)
-                name = self._apply(self._split(line), state)
-                yield name, state
-        else:
-            import re
-            for rname, specs in self.regions:
-                state = np.zeros(self.n_samples, dtype=np.int8)
-                ok = True
-                for spec in specs:
-                    mt = re.match(r'^(.+):(\d+)-(\d+)$', spec)
-                    if not mt:
-                        sys.stderr.write('Could not parse region %s\n' % str(spec))
-                        ok = False
-                        break
-                    contig, lo, hi = mt.group(1), int(mt.group(2)) - 1, int(mt.group(3))
-                    for f in self.records:
-                        start = int(f[1]) - 1
-                        if f[0] == contig and start < hi and start + len(f[3]) > lo:
-                            self._apply(f, state)
-                yield (rname if ok else None), state
+        for line in self.fh:
+            if not line.strip():
+                continue
+            state = np.zeros(self.n_samples, dtype=np.int8)
+            name = self._apply(self._split(line), state)
+            yield name, state
+
+    def _region_members(self, specs):
+        """Record indices a burden line fetches, in fetch order (input.py:398-407), or None when
+        a region does not parse (the reference then yields its None sentinel)."""
+        import re
+        members = []
+        for spec in specs:
+            mt = re.match(r'^(.+):(\d+)-(\d+)$', spec)
+            if not mt:
+                sys.stderr.write('Could not parse region %s\n' % str(spec))
+                return None
+            contig, lo, hi = mt.group(1), int(mt.group(2)) - 1, int(mt.group(3))
+            hit = np.nonzero((self.rec_contig == contig) & (self.rec_start < hi) &
+                             (self.rec_end > lo))[0]
+            members.extend(hit.tolist())
+        return members
+
+    def _burden_batches(self, size):
+        for b0 in range(0, len(self.regions), size):
+            names, offsets, members = [], [0], []
+            for rname, specs in self.regions[b0:b0 + size]:
+                mem = self._region_members(specs)
+                names.append('NA' if mem is None else rname)
+                members.extend(mem or [])
+                offsets.append(len(members))
+            bits, miss = self.reducer(self.rec_bits, self.rec_miss, np.array(offsets, dtype=np.int64),
+                                      np.array(members, dtype=np.int32))
+            empty = ~(bits.any(axis=1) | (miss.any(axis=1) if miss is not None else False))
+            for j in np.nonzero(empty)[0]:
+                if names[j] != 'NA':
+                    sys.stderr.write('No observations of ' + names[j] + ' in selected samples\n')
+            if miss is not None and not miss.any():
+                miss = None
+            yield VariantBatch(names, bits, miss)
 
     def batches(self, size):
+        if self.regions is not None:
+            for batch in self._burden_batches(size):
+                yield batch
+            return
         names, states = [], []
         for name, state in self._rows():
             if name is None:

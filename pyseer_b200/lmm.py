@@ -215,6 +215,17 @@ def run_lmm_bits(lmm, h2, bits, missing, continuous, filter_pvalue, lrt_pvalue,
     return eng.fetch()
 
 
+def run_lmm_burden(lmm, h2, vbits, vmiss, region_offsets, members, continuous, filter_pvalue,
+                   lrt_pvalue, min_af=-1.0, max_af=2.0, max_missing=2.0):
+    """Burden test (``--vcf --burden --lmm``, input.py:395-411 feeding lmm.fit_lmm): one packed row
+    per VCF record plus the member lists of the regions; the per-region union is formed on the
+    device and every region goes through the LMM path.  Result table, one row per region."""
+    eng = lmm.engine(h2)
+    eng.submit_burden(vbits, vmiss, region_offsets, members)
+    eng.run_lmm(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous)
+    return eng.fetch()
+
+
 def fit_lmm(lmm, h2, variants, variant_mat, lineage_effects,
             lineage_clusters, covariates, continuous,
             filter_pvalue, lrt_pvalue):

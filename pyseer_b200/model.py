@@ -103,6 +103,16 @@ def run_fixed_bits(model, bits, missing, filter_pvalue, lrt_pvalue, min_af=-1.0,
     return r
 
 
+def run_fixed_burden(model, vbits, vmiss, region_offsets, members, filter_pvalue, lrt_pvalue,
+                     min_af=-1.0, max_af=2.0, max_missing=2.0):
+    """Burden test with the fixed-effects model: per-region union of VCF record rows on the
+    device (input.py:395-411), then model.fixed_effects_regression for every region."""
+    eng = model.engine
+    eng.submit_burden(vbits, vmiss, region_offsets, members)
+    eng.run_fixed(min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, model.continuous)
+    return eng.fetch()
+
+
 _cache = {'key': None, 'model': None}
 
 
