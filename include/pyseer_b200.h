@@ -34,7 +34,8 @@ typedef enum psb_status {
     PSB_ERR_STATE = -3,     /* call out of order (run before setup/submit ...)   */
     PSB_ERR_H2 = -4,        /* h2 outside [0,1): lmm_cov.py:667-670 (KeyError)   */
     PSB_ERR_NOMEM = -5,
-    PSB_ERR_UNSUPPORTED = -6
+    PSB_ERR_UNSUPPORTED = -6,
+    PSB_ERR_NUMERIC = -7    /* an iterative library routine did not converge      */
 } psb_status;
 
 /* Per-variant flag word.  Bits map 1:1 onto the reference's `notes` strings and the
@@ -106,6 +107,14 @@ int psb_sync(psb_ctx *ctx);
 int psb_lmm_setup(psb_ctx *ctx, int32_t n_samples, int32_t n_cov, const double *X,
                   const double *y, const double *U, const double *S, double h2,
                   int32_t precision);
+
+/* Symmetric eigendecomposition on the device, replacing the host `eigh` of LMM.setSU_fromK
+ * (fastlmm/lmm_cov.py:88-103) inside lmm.initialise_lmm (lmm.py:26-122) -- the O(N^3),
+ * once-per-run part.  A: n x n symmetric (host); w_out: n eigenvalues in ascending order;
+ * V_out: n x n row-major with the eigenvector of w_out[j] in column j (numpy.linalg.eigh layout).
+ * Runs cuSOLVER's fp64 syevd (loaded lazily with dlopen; PSB_ERR_UNSUPPORTED when it is not
+ * installed, in which case the host side keeps its NumPy eigh).  Needs no model set-up. */
+int psb_eigh(psb_ctx *ctx, int32_t n, const double *A, double *w_out, double *V_out);
 
 /* Fixed-effects state shared by every fixed_effects_regression call (model.py:202-205):
  * Z = [1, m, c] (N x q row-major, column 0 ones; model.py:274-297 minus the variant

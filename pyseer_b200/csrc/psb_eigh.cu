@@ -1,0 +1,137 @@
+// psb_eigh.cu -- once-per-run symmetric eigendecomposition on the device.
+//
+// Replaces the host `eigh` of LMM.setSU_fromK (fastlmm/lmm_cov.py:88-103: K_ = P (K + I) P,
+// S, U = eigh(K_)), the O(N^3) part of lmm.initialise_lmm (lmm.py:26-122): 4 s at N = 5000 and
+// 23 s at N = 10 000 in NumPy on the GPU box's host, once per run.  This is plain library work
+// (cuSOLVER's divide-and-conquer syevd in fp64), not a hand-written kernel: the library is
+// loaded lazily with dlopen so that libpyseer_b200.so itself carries no link dependency on it,
+// and PSB_ERR_UNSUPPORTED tells the caller (pyseer_b200/lmm.py) to keep its NumPy eigh.
+#include <dlfcn.h>
+
+#include "psb_internal.cuh"
+
+namespace {
+
+typedef void *solver_handle;
+typedef int (*fn_create)(solver_handle *);
+typedef int (*fn_destroy)(solver_handle);
+typedef int (*fn_set_stream)(solver_handle, cudaStream_t);
+typedef int (*fn_syevd_bufsize)(solver_handle, int jobz, int uplo, int n, const double *A, int lda,
+                                const double *W, int *lwork);
+typedef int (*fn_syevd)(solver_handle, int jobz, int uplo, int n, double *A, int lda, double *W,
+                        double *work, int lwork, int *info);
+
+struct Solver {
+    void *lib = nullptr;
+    fn_create create = nullptr;
+    fn_destroy destroy = nullptr;
+    fn_set_stream set_stream = nullptr;
+    fn_syevd_bufsize bufsize = nullptr;
+    fn_syevd syevd = nullptr;
+    bool tried = false;
+};
+Solver g_solver;
+
+bool load_solver() {
+    if (g_solver.tried) return g_solver.syevd != nullptr;
+    g_solver.tried = true;
+    const char *names[] = {"libcusolver.so.11", "libcusolver.so.12", "libcusolver.so"};
+    for (const char *nm : names) {
+        g_solver.lib = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (g_solver.lib) break;
+    }
+    if (!g_solver.lib) return false;
+    g_solver.create = (fn_create)dlsym(g_solver.lib, "cusolverDnCreate");
+    g_solver.destroy = (fn_destroy)dlsym(g_solver.lib, "cusolverDnDestroy");
+    g_solver.set_stream = (fn_set_stream)dlsym(g_solver.lib, "cusolverDnSetStream");
+    g_solver.bufsize = (fn_syevd_bufsize)dlsym(g_solver.lib, "cusolverDnDsyevd_bufferSize");
+    g_solver.syevd = (fn_syevd)dlsym(g_solver.lib, "cusolverDnDsyevd");
+    if (!(g_solver.create && g_solver.destroy && g_solver.set_stream && g_solver.bufsize && g_solver.syevd)) {
+        g_solver.syevd = nullptr;
+        return false;
+    }
+    return true;
+}
+
+// out[i][j] = in[j][i], n x n, 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+k_transpose(const double *__restrict__ in, double *__restrict__ out, int n) {
+    __shared__ double t[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;
+        if (i < n && j < n) t[r][threadIdx.x] = in[(size_t)i * n + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = bx + r, j = by + threadIdx.x;
+        if (i < n && j < n) out[(size_t)i * n + j] = t[threadIdx.x][r];
+    }
+}
+
+}  // namespace
+
+// A: n x n row-major, host; only its lower triangle is read (as numpy.linalg.eigh does).  w_out: n eigenvalues,
+// ascending.  V_out: n x n row-major, column j = eigenvector of w_out[j] (numpy.linalg.eigh layout).
+extern "C" int psb_eigh(psb_ctx *c, int32_t n, const double *A, double *w_out, double *V_out) {
+    PSB_REQUIRE(c && A && w_out && V_out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(n >= 1 && n <= 46000, PSB_ERR_ARG, "n = %d out of range", n);
+    PSB_REQUIRE(load_solver(), PSB_ERR_UNSUPPORTED,
+                "cuSOLVER (libcusolver.so.11) could not be loaded: %s", dlerror() ? dlerror() : "missing symbols");
+    PSB_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n * n * sizeof(double);
+    double *d_A = nullptr, *d_V = nullptr, *d_w = nullptr, *d_work = nullptr;
+    int *d_info = nullptr;
+    solver_handle h = nullptr;
+    int rc = PSB_OK, info = 0, lwork = 0, st = 0;
+#define EIGH_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            psb_set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(e_), \
+                          cudaGetErrorString(e_));                                        \
+            rc = PSB_ERR_CUDA;                                                            \
+            goto done;                                                                    \
+        }                                                                                 \
+    } while (0)
+    EIGH_CUDA(cudaMalloc(&d_A, bytes));
+    EIGH_CUDA(cudaMalloc(&d_V, bytes));
+    EIGH_CUDA(cudaMalloc(&d_w, (size_t)n * sizeof(double)));
+    EIGH_CUDA(cudaMalloc(&d_info, sizeof(int)));
+    EIGH_CUDA(cudaMemcpyAsync(d_A, A, bytes, cudaMemcpyHostToDevice, c->stream));
+    st = g_solver.create(&h);
+    if (st != 0) { psb_set_error("cusolverDnCreate failed (%d)", st); rc = PSB_ERR_CUDA; goto done; }
+    g_solver.set_stream(h, c->stream);
+    // jobz = CUSOLVER_EIG_MODE_VECTOR (1); uplo = CUBLAS_FILL_MODE_UPPER (1): the column-major
+    // upper triangle is the row-major LOWER triangle, the half numpy.linalg.eigh reads
+    st = g_solver.bufsize(h, 1, 1, n, d_A, n, d_w, &lwork);
+    if (st != 0) { psb_set_error("cusolverDnDsyevd_bufferSize failed (%d)", st); rc = PSB_ERR_CUDA; goto done; }
+    EIGH_CUDA(cudaMalloc(&d_work, (size_t)(lwork > 0 ? lwork : 1) * sizeof(double)));
+    st = g_solver.syevd(h, 1, 1, n, d_A, n, d_w, d_work, lwork, d_info);
+    if (st != 0) { psb_set_error("cusolverDnDsyevd failed (%d)", st); rc = PSB_ERR_CUDA; goto done; }
+    EIGH_CUDA(cudaMemcpyAsync(&info, d_info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    // cuSOLVER is column-major: eigenvector j sits in column j = d_A[j * n + i]; the caller wants
+    // the row-major matrix with eigenvectors in columns
+    {
+        dim3 g((n + 31) / 32, (n + 31) / 32), b(32, 8);
+        k_transpose<<<g, b, 0, c->stream>>>(d_A, d_V, n);
+        c->launches++;
+    }
+    EIGH_CUDA(cudaGetLastError());
+    EIGH_CUDA(cudaMemcpyAsync(V_out, d_V, bytes, cudaMemcpyDeviceToHost, c->stream));
+    EIGH_CUDA(cudaMemcpyAsync(w_out, d_w, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    EIGH_CUDA(cudaStreamSynchronize(c->stream));
+    if (info != 0) {
+        psb_set_error("syevd did not converge (info = %d)", info);
+        rc = PSB_ERR_NUMERIC;
+    }
+done:
+#undef EIGH_CUDA
+    if (h) g_solver.destroy(h);
+    if (d_work) cudaFree(d_work);
+    if (d_info) cudaFree(d_info);
+    if (d_w) cudaFree(d_w);
+    if (d_V) cudaFree(d_V);
+    if (d_A) cudaFree(d_A);
+    return rc;
+}

@@ -111,6 +111,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset in every CTA of ctaMask and
+// signals the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                               int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"(map), "r"(bar),
+        "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -120,6 +139,13 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
+}
+// arrive on the barrier at the same offset in every CTA of ctaMask
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(cta_mask)
+        : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem], int8 x int8 -> int32
 __device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
@@ -203,6 +229,7 @@ struct TcArgs {
     const uint8_t *shift;     // per-column left shift for int_epi
     int stages_per_tile;      // K stages a variant tile goes through (all component tiles)
     int n_bstages;
+    int pair;                 // 1: launched as clusters of two CTAs that share the operand stream
 };
 
 // Sequence of component tiles a variant tile goes through, and the first K stage of each.
@@ -246,7 +273,8 @@ struct TcStageIter {
 // ---------------------------------------------------------------------------------------
 template <int NSL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
+k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
+                  const TcArgs args) {
     constexpr int UMMA_N = TC_JT * NSL;                 // accumulator columns per buffer
     constexpr int A_COL0 = 2 * UMMA_N;                  // first TMEM column of the A ring
     constexpr int NA = (512 - A_COL0) / 32;             // A ring stages (32 columns = 128 samples)
@@ -282,11 +310,21 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
     const int lane = threadIdx.x & 31;
     const int n_tested = args.n_tested_dev ? *args.n_tested_dev : args.n_tested;
     const int n_tiles = (n_tested + TC_TILE_V - 1) / TC_TILE_V;
+    // Pair mode: CTAs 2i and 2i+1 form a cluster.  Both need the same operand stream (only
+    // their variants differ), so each loads HALF of every B stage and multicasts it into the
+    // shared memory of both: L2 serves every stage once per pair instead of once per CTA.  The
+    // two CTAs therefore walk the stage sequence in lockstep -- a B slot is refilled only after
+    // the MMAs of BOTH have retired (each commit arrives on the empty barrier of both) -- and
+    // run the same number of variant tiles: the even CTA's tile index decides, the odd
+    // CTA may run a last tile without variants.
+    const int pair = args.pair;
+    const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;
+    const int odd = pair ? (int)(blockIdx.x & 1u) : 0;     // tile - odd = the even CTA's tile
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < ns; ++i) {
             mbar_init(smem_u32(&full[i]), 1 + 4);
-            mbar_init(smem_u32(&empty[i]), 1);
+            mbar_init(smem_u32(&empty[i]), pair ? 2 : 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&accFull[i]), 1);
@@ -302,6 +340,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
     }
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();      // the peer's barriers exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
@@ -311,7 +350,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         // ===================== TMA producer (whole warp loops, one lane issues) ==========
         int st = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x)
             for (int q = 0; q < args.jtiles; ++q) {
                 int jt, ks0;
                 tc_tile_of(args, q, jt, ks0);
@@ -320,17 +359,33 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     if (elect_one()) {
                         const uint32_t bar = full0 + st * 8;
                         mbar_arrive_expect_tx(bar, STAGE_BYTES);
-                        tma_load_2d(sB0 + st * STAGE_BYTES, &tmap, bar, ks * TC_KSTAGE, jt * UMMA_N);
+                        if (pair)
+                            tma_load_2d_mc(sB0 + st * STAGE_BYTES + cta_rank * (STAGE_BYTES / 2), &tmap_half,
+                                           bar, ks * TC_KSTAGE, jt * UMMA_N + (int)cta_rank * (UMMA_N / 2),
+                                           (uint16_t)3);
+                        else
+                            tma_load_2d(sB0 + st * STAGE_BYTES, &tmap, bar, ks * TC_KSTAGE, jt * UMMA_N);
                     }
                     __syncwarp();
                     if (++st == ns) { st = 0; ph ^= 1; }
                 }
             }
+        // Pair mode: the peer's last commits arrive on this CTA's empty barriers; wait for them
+        // so that nothing is in flight towards this CTA's shared memory when it exits.
+        if (pair) {
+            long long total = 0;
+            for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x) total += args.stages_per_tile;
+            const int tail = total < ns ? (int)total : ns;
+            for (int i = 0; i < tail; ++i) {
+                mbar_wait(empty0 + st * 8, ph ^ 1);
+                if (++st == ns) { st = 0; ph ^= 1; }
+            }
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops, one lane issues) ============
         int st = 0, sta = 0, acc = 0;
         uint32_t ph = 0, phacc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x)
             for (int q = 0; q < args.jtiles; ++q) {
                 int jt, ks0;
                 tc_tile_of(args, q, jt, ks0);
@@ -347,7 +402,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                         for (int kk = 0; kk < 4; ++kk)
                             tc_mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc + (uint64_t)(kk * 2), IDESC,
                                          (ks != ks0 || kk != 0) ? 1u : 0u);
-                        tc_commit(empty0 + st * 8);
+                        if (pair) tc_commit_mc(empty0 + st * 8, (uint16_t)3);
+                        else tc_commit(empty0 + st * 8);
                         if (ks == args.nks - 1) tc_commit(smem_u32(&accFull[acc]));
                     }
                     __syncwarp();
@@ -390,7 +446,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 cks = first_ks(cq) + over;
             }
         };
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x) {
             // all expanders are done reading the previous tile's bits
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et < TC_TILE_V) {
@@ -493,7 +549,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         const int jt_special = args.n_special > 0 ? args.jtiles - 1 : -1;
         int acc = 0;
         uint32_t phacc = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x) {
             double a = 0.0, bsum = 0.0, pp = 0.0;
             const int t_own = tile * TC_TILE_V + v;
             const int row_own = t_own < n_tested ? args.idx[t_own] : -1;
@@ -746,7 +802,20 @@ template <int NSL>
 static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
     PSB_CUDA(cudaFuncSetAttribute(k_lmm_quadform_tc<NSL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    k_lmm_quadform_tc<NSL><<<grid, TC_THREADS, smem, c->stream>>>(*(const CUtensorMap *)c->tmap_Lq, args);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = args.pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PSB_CUDA(cudaLaunchKernelEx(&cfg, k_lmm_quadform_tc<NSL>, *(const CUtensorMap *)c->tmap_Lq,
+                                *(const CUtensorMap *)c->tmap_Lq_half, args));
     return PSB_OK;
 }
 
@@ -757,21 +826,27 @@ static int tc_make_tensor_map(psb_ctx *c, int Jall, int nsl) {
     PSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     PSB_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, PSB_ERR_CUDA,
                 "cuTensorMapEncodeTiled not available from the driver");
-    CUtensorMap *tm = new CUtensorMap;
     cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jall * nsl};
     cuuint64_t gstr[1] = {(cuuint64_t)c->Kpad};
-    cuuint32_t box[2] = {TC_KSTAGE, (cuuint32_t)(TC_JT * nsl)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult cr = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
-                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        delete tm;
-        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-        return PSB_ERR_CUDA;
+    // [0]: one whole B stage per box; [1]: half a stage (pair mode, each CTA of a cluster loads
+    // and multicasts one half)
+    CUtensorMap *tm[2] = {new CUtensorMap, new CUtensorMap};
+    for (int h = 0; h < 2; ++h) {
+        cuuint32_t box[2] = {TC_KSTAGE, (cuuint32_t)(TC_JT * nsl) >> h};
+        CUresult cr = ((PFN_encodeTiled)fn)(tm[h], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr,
+                                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            delete tm[0];
+            delete tm[1];
+            psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+            return PSB_ERR_CUDA;
+        }
     }
-    c->tmap_Lq = tm;
+    c->tmap_Lq = tm[0];
+    c->tmap_Lq_half = tm[1];
     return PSB_OK;
 }
 
@@ -968,7 +1043,10 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.n_bstages = nb;
     const size_t smem = tc_smem_bytes(nsl, nb, pitch);
     const int tiles = psb_div_up(n_tested, TC_TILE_V);
-    const int grid = std::min(tiles, c->sm_count);
+    // pair mode (default): clusters of two CTAs share the operand stream through TMA multicast
+    a.pair = (c->sm_count >= 2 && !(getenv("PSB_TC_PAIR") && atoi(getenv("PSB_TC_PAIR")) == 0)) ? 1 : 0;
+    int grid = std::min(tiles, c->sm_count);
+    if (a.pair) grid = std::min((tiles + 1) & ~1, c->sm_count & ~1);
     int rc = PSB_OK;
     switch (nsl) {
         case 3: rc = tc_launch<3>(c, a, grid, smem); break;
@@ -994,5 +1072,7 @@ void psb_lmm_tc_free(psb_ctx *c) {
     c->d_scale2 = nullptr;
     c->d_shift = nullptr;
     if (c->tmap_Lq) delete (CUtensorMap *)c->tmap_Lq;
+    if (c->tmap_Lq_half) delete (CUtensorMap *)c->tmap_Lq_half;
     c->tmap_Lq = nullptr;
+    c->tmap_Lq_half = nullptr;
 }

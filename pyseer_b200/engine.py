@@ -130,6 +130,18 @@ class Engine(object):
                                        float(null_firth)))
         self.n_samples, self.q, self.model = n, q, 'fixed'
 
+    def eigh(self, A):
+        """Symmetric eigendecomposition on the device (psb_eigh): ``(w, V)`` as numpy.linalg.eigh.
+        Raises PsbError with code ERR_UNSUPPORTED when cuSOLVER cannot be loaded."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        n = A.shape[0]
+        if A.ndim != 2 or A.shape[1] != n:
+            raise ValueError('A must be square')
+        w = np.empty(n, dtype=np.float64)
+        V = np.empty((n, n), dtype=np.float64)
+        check(self.lib.psb_eigh(self._ctx, n, self._dptr(A), self._dptr(w), self._dptr(V)))
+        return w, V
+
     # -- kinship ------------------------------------------------------------------------
     def kinship_begin(self, n_samples):
         check(self.lib.psb_kinship_begin(self._ctx, int(n_samples)))

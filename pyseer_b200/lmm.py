@@ -56,10 +56,26 @@ class KinshipLMM(object):
             self.K.flat[::N + 1] += 1.0
             K_ = self._regress(self.K)
             K_ = self._regress(K_.T)
-            S, U = np.linalg.eigh(K_)
+            S, U = self._eigh(K_)
             self.U = np.ascontiguousarray(U[:, self.D:N])
             self.S = S[self.D:N] - 1.0
         return self.S, self.U
+
+    def _eigh(self, K_):
+        """The O(N^3) step of setSU_fromK: on the device (psb_eigh, cuSOLVER syevd in fp64) for
+        N >= 256 unless PYSEER_B200_EIGH=numpy; NumPy when cuSOLVER is not installed.  Either
+        way the per-variant statistics only depend on the eigenspaces, not on the basis chosen
+        inside a degenerate one."""
+        if K_.shape[0] >= 256 and os.environ.get('PYSEER_B200_EIGH', 'device') != 'numpy':
+            if self._engine is None:
+                self._engine = Engine(self.device)
+            try:
+                return self._engine.eigh(K_)
+            except _lib.PsbError as e:
+                if e.code != _lib.ERR_UNSUPPORTED:
+                    raise
+                sys.stderr.write('cuSOLVER not available, eigendecomposition on the host\n')
+        return np.linalg.eigh(K_)
 
     def _getUY(self):
         if self._UY is None:
