@@ -86,7 +86,6 @@ struct psb_ctx {
     bool tc_int_epi = false;      // triangular tiles are recombined and summed in int64
     int tc_special = 0;           // hi/lo column pairs carried by the special tile (0 = none)
     void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B), one B stage per box
-    void *tmap_Lq_half = nullptr; // same with half a stage per box (pair mode)
 
     // ---- fixed effects ----
     int q = 0;

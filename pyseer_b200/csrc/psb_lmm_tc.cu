@@ -47,8 +47,13 @@
 #define TC_EXP_WARPS 8         // expander warps (2 groups x 4 lane quarters)
 #define TC_TILE_V 128          // variants per CTA tile (UMMA M)
 #define TC_JT 32               // components per accumulator tile
-#define TC_KSTAGE 128          // samples per pipeline stage (one 128-byte swizzle row)
-#define TC_MAX_BSTAGES 12
+#define TC_KBOX 128            // samples per TMA box / swizzle row (128 bytes of int8)
+#define TC_KSTAGE 256          // samples per pipeline stage: two boxes, eight K = 32 MMAs.  A stage
+                               // must carry enough tensor work (8 x 80 cycles at k = 5) to cover the
+                               // per-stage control path of the issuing warp (~370 cycles measured:
+                               // barrier poll, elect, descriptor arithmetic, commit) -- with 128-sample
+                               // stages that path, not the tensor pipe, set the pace.
+#define TC_MAX_BSTAGES 6
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -230,6 +235,9 @@ struct TcArgs {
     int stages_per_tile;      // K stages a variant tile goes through (all component tiles)
     int n_bstages;
     int pair;                 // 1: launched as clusters of two CTAs that share the operand stream
+    int debug;                // timing experiments only (PSB_TC_DEBUG, results are wrong when set):
+                              // 1: one MMA per stage instead of four; 2: expanders store without
+                              // expanding; 4: epilogue releases the accumulators without reading them
 };
 
 // Sequence of component tiles a variant tile goes through, and the first K stage of each.
@@ -273,13 +281,14 @@ struct TcStageIter {
 // ---------------------------------------------------------------------------------------
 template <int NSL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
-                  const TcArgs args) {
+k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
     constexpr int UMMA_N = TC_JT * NSL;                 // accumulator columns per buffer
     constexpr int A_COL0 = 2 * UMMA_N;                  // first TMEM column of the A ring
-    constexpr int NA = (512 - A_COL0) / 32;             // A ring stages (32 columns = 128 samples)
-    constexpr uint32_t STAGE_BYTES = UMMA_N * TC_KSTAGE;
-    static_assert(NA >= 2, "too many slices for the TMEM budget");
+    constexpr int A_COLS = TC_KSTAGE / 4;               // TMEM columns of one A stage (4 samples each)
+    constexpr int NA = (512 - A_COL0) / A_COLS;         // A ring stages
+    constexpr uint32_t BOX_BYTES = UMMA_N * TC_KBOX;    // one TMA box: UMMA_N rows x 128 samples
+    constexpr uint32_t STAGE_BYTES = 2 * BOX_BYTES;
+    static_assert(NA >= 1, "too many slices for the TMEM budget");
     // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N, M = 128
     constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UMMA_N >> 3) << 17) |
                                ((uint32_t)(TC_TILE_V >> 4) << 24);
@@ -359,12 +368,15 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     if (elect_one()) {
                         const uint32_t bar = full0 + st * 8;
                         mbar_arrive_expect_tx(bar, STAGE_BYTES);
-                        if (pair)
-                            tma_load_2d_mc(sB0 + st * STAGE_BYTES + cta_rank * (STAGE_BYTES / 2), &tmap_half,
-                                           bar, ks * TC_KSTAGE, jt * UMMA_N + (int)cta_rank * (UMMA_N / 2),
-                                           (uint16_t)3);
-                        else
+                        if (pair) {
+                            // each CTA of the pair fetches one of the stage's two boxes for both
+                            tma_load_2d_mc(sB0 + st * STAGE_BYTES + cta_rank * BOX_BYTES, &tmap, bar,
+                                           ks * TC_KSTAGE + (int)cta_rank * TC_KBOX, jt * UMMA_N, (uint16_t)3);
+                        } else {
                             tma_load_2d(sB0 + st * STAGE_BYTES, &tmap, bar, ks * TC_KSTAGE, jt * UMMA_N);
+                            tma_load_2d(sB0 + st * STAGE_BYTES + BOX_BYTES, &tmap, bar, ks * TC_KSTAGE + TC_KBOX,
+                                        jt * UMMA_N);
+                        }
                     }
                     __syncwarp();
                     if (++st == ns) { st = 0; ph ^= 1; }
@@ -397,11 +409,14 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t bdesc = make_b_desc(sB0 + st * STAGE_BYTES);
-                        const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + sta * 32);
+                        const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + sta * A_COLS);
+                        const int nkk = (args.debug & 1) ? 2 : 8;
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            tc_mma_i8_ts(d_tmem, a_tmem + kk * 8, bdesc + (uint64_t)(kk * 2), IDESC,
-                                         (ks != ks0 || kk != 0) ? 1u : 0u);
+                        for (int kk = 0; kk < 8; ++kk)
+                            if (kk < nkk)
+                                tc_mma_i8_ts(d_tmem, a_tmem + kk * 8,
+                                             bdesc + (uint64_t)((kk >> 2) * (BOX_BYTES >> 4) + (kk & 3) * 2), IDESC,
+                                             (ks != ks0 || kk != 0) ? 1u : 0u);
                         if (pair) tc_commit_mc(empty0 + st * 8, (uint16_t)3);
                         else tc_commit(empty0 + st * 8);
                         if (ks == args.nks - 1) tc_commit(smem_u32(&accFull[acc]));
@@ -419,12 +434,12 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int v = q * 32 + lane;                  // variant (= TMEM lane) within the tile
         const int et = (warp - 2) * 32 + lane;        // 0..255 cooperative-copy index
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const int chunks_per_row = args.nks;          // 16-byte chunks (4 words = 128 samples)
+        const int chunks_per_row = 2 * args.nks;      // 16-byte chunks (4 words = 128 samples)
         // The group takes every second stage t of the global sequence.  sb: barrier (B) slot
         // t % ns of its next stage; sa: A slot t % na; (we, wph): slot and phase of
         // empty[(t - na) % ns], the commit that frees the A slot -- not waited for during the
         // first na stages of the kernel (`lead` of them belong to this group).
-        int sb = grp, sa = grp;
+        int sb = grp % ns, sa = grp % na;
         int lead = (na - grp + 1) / 2;
         int we = grp + 2 * lead - na;
         uint32_t wph = 0;
@@ -472,8 +487,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             const int grow_id = sRows[v];
             const uint4 *grow = reinterpret_cast<const uint4 *>(args.bits + (size_t)(grow_id < 0 ? 0 : grow_id) * args.Wrow);
             const int gwords4 = args.Wrow >> 2;
-            auto gload = [&](int ks) -> uint4 {
-                return (grow_id >= 0 && ks < gwords4) ? __ldg(grow + ks) : make_uint4(0u, 0u, 0u, 0u);
+            auto gload = [&](int ch) -> uint4 {       // ch: 16-byte chunk of the row
+                return (grow_id >= 0 && ch < gwords4) ? __ldg(grow + ch) : make_uint4(0u, 0u, 0u, 0u);
             };
             // This group takes every second stage of the tile's (component tile, K stage)
             // sequence, starting at the first one whose global parity matches the group.  The
@@ -484,24 +499,29 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             int cq = 0, cks = first_ks(0) + (((int)parity != grp) ? 1 : 0) - 2;
             advance2(cq, cks);
             // expand one 128-sample stage of this thread's variant into A slot sa, then signal
-            auto emit = [&](const uint4 &w4) {
+            auto emit = [&](const uint4 &w4a, const uint4 &w4b) {
                 if (lead > 0) {
                     --lead;
                 } else {
                     mbar_wait(empty0 + we * 8, wph);
                     we += 2;
-                    if (we >= ns) { we -= ns; wph ^= 1u; }
+                    while (we >= ns) { we -= ns; wph ^= 1u; }
                 }
                 tc_fence_after();
-                const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-                const uint32_t base = lane_addr + (uint32_t)(A_COL0 + sa * 32);
+                const uint32_t ws[8] = {w4a.x, w4a.y, w4a.z, w4a.w, w4b.x, w4b.y, w4b.z, w4b.w};
+                const uint32_t base = lane_addr + (uint32_t)(A_COL0 + sa * A_COLS);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     // register b, byte t <- sample 8 t + b of the word (the B operand is
                     // stored with the same permutation, see k_tc_quantise)
                     uint32_t r[8];
+                    if (args.debug & 2) {
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) r[b] = (ws[i] >> b) & 0x01010101u;
+                        for (int b = 0; b < 8; ++b) r[b] = ws[i];
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) r[b] = (ws[i] >> b) & 0x01010101u;
+                    }
                     tc_st8(base + i * 8, r);
                 }
                 tc_wait_st();
@@ -509,32 +529,35 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full0 + sb * 8);
                 sb += 2;
-                if (sb >= ns) sb -= ns;
+                while (sb >= ns) sb -= ns;
                 sa += 2;
-                if (sa >= na) sa -= na;
+                while (sa >= na) sa -= na;
             };
             if (args.bits_in_smem) {
                 const uint32_t myrow_s = smem_u32(sBits + (size_t)v * args.pitch);
                 while (cq < jtiles) {
-                    const uint4 w4 = lds128(myrow_s + (uint32_t)cks * 16u);
-                    emit(w4);
+                    const uint4 w4a = lds128(myrow_s + (uint32_t)cks * 32u);
+                    const uint4 w4b = lds128(myrow_s + (uint32_t)cks * 32u + 16u);
+                    emit(w4a, w4b);
                     advance2(cq, cks);
                 }
             } else {
                 // global-row mode: the words of the group's next two stages are in flight
                 int pq = cq, pks = cks;
-                uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = make_uint4(0u, 0u, 0u, 0u);
-                if (pq < jtiles) nxt = gload(pks);
+                const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+                uint4 nxa = zero4, nxb = zero4, nx2a = zero4, nx2b = zero4;
+                if (pq < jtiles) { nxa = gload(2 * pks); nxb = gload(2 * pks + 1); }
                 advance2(pq, pks);
-                if (pq < jtiles) nxt2 = gload(pks);
+                if (pq < jtiles) { nx2a = gload(2 * pks); nx2b = gload(2 * pks + 1); }
                 while (cq < jtiles) {
-                    const uint4 w4 = nxt;
-                    nxt = nxt2;
+                    const uint4 w4a = nxa, w4b = nxb;
+                    nxa = nx2a;
+                    nxb = nx2b;
                     if (pq < jtiles) {
                         advance2(pq, pks);
-                        if (pq < jtiles) nxt2 = gload(pks);
+                        if (pq < jtiles) { nx2a = gload(2 * pks); nx2b = gload(2 * pks + 1); }
                     }
-                    emit(w4);
+                    emit(w4a, w4b);
                     advance2(cq, cks);
                 }
             }
@@ -564,6 +587,13 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 mbar_wait(smem_u32(&accFull[acc]), phacc);
                 tc_fence_after();
                 const uint32_t col0 = (uint32_t)(acc * UMMA_N);
+                if (args.debug & 4) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&accEmpty[acc]));
+                    if (++acc == 2) { acc = 0; phacc ^= 1; }
+                    continue;
+                }
                 if (args.int_epi && jt != jt_special) {
                     // Triangular tile, integer epilogue: the columns of a tile share one scale
                     // 2^(e_tile - shmax - B) up to a small per-column left shift, so the slices
@@ -814,8 +844,7 @@ static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PSB_CUDA(cudaLaunchKernelEx(&cfg, k_lmm_quadform_tc<NSL>, *(const CUtensorMap *)c->tmap_Lq,
-                                *(const CUtensorMap *)c->tmap_Lq_half, args));
+    PSB_CUDA(cudaLaunchKernelEx(&cfg, k_lmm_quadform_tc<NSL>, *(const CUtensorMap *)c->tmap_Lq, args));
     return PSB_OK;
 }
 
@@ -829,24 +858,19 @@ static int tc_make_tensor_map(psb_ctx *c, int Jall, int nsl) {
     cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jall * nsl};
     cuuint64_t gstr[1] = {(cuuint64_t)c->Kpad};
     cuuint32_t estr[2] = {1, 1};
-    // [0]: one whole B stage per box; [1]: half a stage (pair mode, each CTA of a cluster loads
-    // and multicasts one half)
-    CUtensorMap *tm[2] = {new CUtensorMap, new CUtensorMap};
-    for (int h = 0; h < 2; ++h) {
-        cuuint32_t box[2] = {TC_KSTAGE, (cuuint32_t)(TC_JT * nsl) >> h};
-        CUresult cr = ((PFN_encodeTiled)fn)(tm[h], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr,
-                                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) {
-            delete tm[0];
-            delete tm[1];
-            psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-            return PSB_ERR_CUDA;
-        }
+    // one box = 128 samples (one swizzle row) x all sliced rows of a component tile; a pipeline
+    // stage is two boxes (in pair mode one from each CTA of the cluster, multicast to both)
+    CUtensorMap *tm = new CUtensorMap;
+    cuuint32_t box[2] = {TC_KBOX, (cuuint32_t)(TC_JT * nsl)};
+    CUresult cr = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        delete tm;
+        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        return PSB_ERR_CUDA;
     }
-    c->tmap_Lq = tm[0];
-    c->tmap_Lq_half = tm[1];
+    c->tmap_Lq = tm;
     return PSB_OK;
 }
 
@@ -1010,12 +1034,12 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
         for (int jt = 0; jt < nreg; ++jt) stages += a.nks - (a.tri ? (jt * TC_JT) / TC_KSTAGE : 0);
         a.stages_per_tile = stages;
     }
-    int pitch = a.nks * 4;
+    int pitch = a.nks * (TC_KSTAGE / 32);
     while (pitch % 32 != 4) pitch += 4;
     a.pitch = pitch;
     int smem_max = 0;
     PSB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-    const int na = (512 - 2 * TC_JT * nsl) / 32;          // TMEM A-ring depth (kernel: NA)
+    const int na = (512 - 2 * TC_JT * nsl) / (TC_KSTAGE / 4);   // TMEM A-ring depth (kernel: NA)
     // Operand ring depth: as many stages as shared memory holds, at most TC_MAX_BSTAGES.  The
     // tile's packed rows share shared memory with the ring; they stay there as long as the ring
     // keeps at least the depth of the TMEM A ring (measured at N=5000: rows in shared memory
@@ -1044,6 +1068,7 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     const size_t smem = tc_smem_bytes(nsl, nb, pitch);
     const int tiles = psb_div_up(n_tested, TC_TILE_V);
     // pair mode (default): clusters of two CTAs share the operand stream through TMA multicast
+    a.debug = getenv("PSB_TC_DEBUG") ? atoi(getenv("PSB_TC_DEBUG")) : 0;
     a.pair = (c->sm_count >= 2 && !(getenv("PSB_TC_PAIR") && atoi(getenv("PSB_TC_PAIR")) == 0)) ? 1 : 0;
     int grid = std::min(tiles, c->sm_count);
     if (a.pair) grid = std::min((tiles + 1) & ~1, c->sm_count & ~1);
@@ -1072,7 +1097,6 @@ void psb_lmm_tc_free(psb_ctx *c) {
     c->d_scale2 = nullptr;
     c->d_shift = nullptr;
     if (c->tmap_Lq) delete (CUtensorMap *)c->tmap_Lq;
-    if (c->tmap_Lq_half) delete (CUtensorMap *)c->tmap_Lq_half;
     c->tmap_Lq = nullptr;
-    c->tmap_Lq_half = nullptr;
+
 }
