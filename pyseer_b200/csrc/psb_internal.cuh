@@ -85,7 +85,8 @@ struct psb_ctx {
     uint8_t *d_shift = nullptr;   // [Jq] per-column left shift of the integer epilogue (triangular form)
     bool tc_int_epi = false;      // triangular tiles are recombined and summed in int64
     int tc_special = 0;           // hi/lo column pairs carried by the special tile (0 = none)
-    void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B), one B stage per box
+    void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B): box = 128 samples x all sliced rows
+    void *tmap_Lq_half = nullptr; // same with half of the sliced rows per box (two-SM mode)
 
     // ---- fixed effects ----
     int q = 0;

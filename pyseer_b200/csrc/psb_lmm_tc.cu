@@ -126,6 +126,27 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *
         "r"(c0), "r"(c1), "h"(cta_mask)
         : "memory");
 }
+// cta_group::2 variant: the executing CTA loads into its own shared memory, the completion bytes
+// are signalled on `bar`, a shared::cluster address that may belong to the other CTA of the pair
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                                int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        ".cta_group::2 [%0], [%1, {%3, %4}], [%2];" ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // default semantics (release at CTA scope), as for the local arrive: the hand-over goes through
+    // TMEM and the tcgen05 fences, not through generic memory.  An explicit .release.cluster makes
+    // the compiler emit MEMBAR.ALL.GPU + ERRBAR in front of every arrive (~1000 cycles each).
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -150,6 +171,23 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
     asm volatile(
         "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
         "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(cta_mask)
+        : "memory");
+}
+// two-SM MMA: M = 256 (128 TMEM lanes in each CTA of the pair), B = the halves held by both CTAs
+__device__ __forceinline__ void tc_mma_i8_ts_2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem], int8 x int8 -> int32
@@ -234,7 +272,9 @@ struct TcArgs {
     const uint8_t *shift;     // per-column left shift for int_epi
     int stages_per_tile;      // K stages a variant tile goes through (all component tiles)
     int n_bstages;
-    int pair;                 // 1: launched as clusters of two CTAs that share the operand stream
+    int pair;                 // launched as clusters of two CTAs: 1 = each CTA issues its own MMAs, the
+                              // operand stream is shared through TMA multicast; 2 = two-SM MMAs
+                              // (cta_group::2), each CTA holds half of every B stage
     int debug;                // timing experiments only (PSB_TC_DEBUG, results are wrong when set):
                               // 1: one MMA per stage instead of four; 2: expanders store without
                               // expanding; 4: epilogue releases the accumulators without reading them
@@ -279,9 +319,10 @@ struct TcStageIter {
 };
 
 // ---------------------------------------------------------------------------------------
-template <int NSL>
+template <int NSL, bool TWO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
+k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half,
+                  const TcArgs args) {
     constexpr int UMMA_N = TC_JT * NSL;                 // accumulator columns per buffer
     constexpr int A_COL0 = 2 * UMMA_N;                  // first TMEM column of the A ring
     constexpr int A_COLS = TC_KSTAGE / 4;               // TMEM columns of one A stage (4 samples each)
@@ -292,13 +333,26 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
     // instruction descriptor: D = s32, A = B = signed 8-bit, both K-major, N, M = 128
     constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UMMA_N >> 3) << 17) |
                                ((uint32_t)(TC_TILE_V >> 4) << 24);
+    // two-SM MMA: M = 256 over the CTA pair
+    constexpr uint32_t IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(UMMA_N >> 3) << 17) |
+                                ((uint32_t)((2 * TC_TILE_V) >> 4) << 24);
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int ns = args.n_bstages;                 // operand (B) ring depth; may exceed NA
     const int na = ns < NA ? ns : NA;              // A ring depth in use
+    // Two-SM mode (args.pair == 2): the pair issues ONE MMA of M = 256 per K step -- 128 variants
+    // (TMEM lanes) in each CTA -- whose B operand is split between the two shared memories: each
+    // CTA loads and keeps only HALF of the sliced rows of every stage, so the bytes entering
+    // each SM (64 B/clk L2 port) and the shared memory per stage halve.  CTA 0 issues the MMAs;
+    // both CTAs' TMA bytes and expander arrivals complete on CTA 0's full barriers, its commits
+    // are multicast to both CTAs' empty / accFull barriers, both epilogues release on CTA 0's
+    // accEmpty barriers.
+    constexpr bool two = TWO;
+    const uint32_t box_bytes = two ? BOX_BYTES / 2 : BOX_BYTES;       // per CTA
+    const uint32_t stage_bytes = 2 * box_bytes;
     uint8_t *sB = smem;                                               // ns stages
-    uint32_t *sBits = (uint32_t *)(sB + (size_t)ns * STAGE_BYTES);    // 128 x pitch words
+    uint32_t *sBits = (uint32_t *)(sB + (size_t)ns * stage_bytes);    // 128 x pitch words
     uint64_t *bars = (uint64_t *)(sBits + (size_t)TC_TILE_V * args.pitch);
     // One barrier pair per K stage in flight, indexed by the B slot t % ns of stage t: full[s]
     // completes when the TMA bytes of the B stage have landed AND the four expander warps have
@@ -332,20 +386,27 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < ns; ++i) {
-            mbar_init(smem_u32(&full[i]), 1 + 4);
-            mbar_init(smem_u32(&empty[i]), pair ? 2 : 1);
+            mbar_init(smem_u32(&full[i]), two ? 1 + 4 + 4 : 1 + 4);
+            mbar_init(smem_u32(&empty[i]), pair == 1 ? 2 : 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&accFull[i]), 1);
-            mbar_init(smem_u32(&accEmpty[i]), 4);
+            mbar_init(smem_u32(&accEmpty[i]), two ? 8 : 4);
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(tmem_slot)),
-                     "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        if constexpr (two) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(tmem_slot)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(tmem_slot)),
+                         "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -354,6 +415,9 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
     const uint32_t sB0 = smem_u32(sB);
+    // CTA 0's full / accEmpty barriers as seen from this CTA (two-SM mode)
+    const uint32_t lead_full0 = two ? mapa_shared(full0, 0u) : full0;
+    const uint32_t lead_accEmpty0 = two ? mapa_shared(smem_u32(accEmpty), 0u) : smem_u32(accEmpty);
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp loops, one lane issues) ==========
@@ -367,12 +431,21 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     mbar_wait(empty0 + st * 8, ph ^ 1);
                     if (elect_one()) {
                         const uint32_t bar = full0 + st * 8;
-                        mbar_arrive_expect_tx(bar, STAGE_BYTES);
-                        if (pair) {
+                        if constexpr (two) {
+                            // this CTA's half of the rows of both boxes; bytes complete on CTA 0
+                            if (cta_rank == 0) mbar_arrive_expect_tx(bar, 2 * stage_bytes);
+                            const uint32_t lbar = lead_full0 + st * 8;
+                            const int row = jt * UMMA_N + (int)cta_rank * (UMMA_N / 2);
+                            tma_load_2d_cg2(sB0 + st * stage_bytes, &tmap_half, lbar, ks * TC_KSTAGE, row);
+                            tma_load_2d_cg2(sB0 + st * stage_bytes + box_bytes, &tmap_half, lbar,
+                                            ks * TC_KSTAGE + TC_KBOX, row);
+                        } else if (pair) {
+                            mbar_arrive_expect_tx(bar, STAGE_BYTES);
                             // each CTA of the pair fetches one of the stage's two boxes for both
                             tma_load_2d_mc(sB0 + st * STAGE_BYTES + cta_rank * BOX_BYTES, &tmap, bar,
                                            ks * TC_KSTAGE + (int)cta_rank * TC_KBOX, jt * UMMA_N, (uint16_t)3);
                         } else {
+                            mbar_arrive_expect_tx(bar, STAGE_BYTES);
                             tma_load_2d(sB0 + st * STAGE_BYTES, &tmap, bar, ks * TC_KSTAGE, jt * UMMA_N);
                             tma_load_2d(sB0 + st * STAGE_BYTES + BOX_BYTES, &tmap, bar, ks * TC_KSTAGE + TC_KBOX,
                                         jt * UMMA_N);
@@ -395,8 +468,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp loops, one lane issues) ============
+        // (two-SM mode: CTA 0 issues for the pair, CTA 1's warp only owns its TMEM allocation)
         int st = 0, sta = 0, acc = 0;
         uint32_t ph = 0, phacc = 0;
+        if (!(two && cta_rank != 0))
         for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x)
             for (int q = 0; q < args.jtiles; ++q) {
                 int jt, ks0;
@@ -408,18 +483,29 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     mbar_wait(full0 + st * 8, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t bdesc = make_b_desc(sB0 + st * STAGE_BYTES);
+                        const uint64_t bdesc = make_b_desc(sB0 + st * stage_bytes);
                         const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + sta * A_COLS);
                         const int nkk = (args.debug & 1) ? 2 : 8;
+                        if constexpr (two) {
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk)
-                            if (kk < nkk)
-                                tc_mma_i8_ts(d_tmem, a_tmem + kk * 8,
-                                             bdesc + (uint64_t)((kk >> 2) * (BOX_BYTES >> 4) + (kk & 3) * 2), IDESC,
-                                             (ks != ks0 || kk != 0) ? 1u : 0u);
-                        if (pair) tc_commit_mc(empty0 + st * 8, (uint16_t)3);
-                        else tc_commit(empty0 + st * 8);
-                        if (ks == args.nks - 1) tc_commit(smem_u32(&accFull[acc]));
+                            for (int kk = 0; kk < 8; ++kk)
+                                if (kk < nkk)
+                                    tc_mma_i8_ts_2(d_tmem, a_tmem + kk * 8,
+                                                   bdesc + (uint64_t)((kk >> 2) * ((BOX_BYTES / 2) >> 4) + (kk & 3) * 2),
+                                                   IDESC2, (ks != ks0 || kk != 0) ? 1u : 0u);
+                            tc_commit_2mc(empty0 + st * 8, (uint16_t)3);
+                            if (ks == args.nks - 1) tc_commit_2mc(smem_u32(&accFull[acc]), (uint16_t)3);
+                        } else {
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk)
+                                if (kk < nkk)
+                                    tc_mma_i8_ts(d_tmem, a_tmem + kk * 8,
+                                                 bdesc + (uint64_t)((kk >> 2) * (BOX_BYTES >> 4) + (kk & 3) * 2), IDESC,
+                                                 (ks != ks0 || kk != 0) ? 1u : 0u);
+                            if (pair) tc_commit_mc(empty0 + st * 8, (uint16_t)3);
+                            else tc_commit(empty0 + st * 8);
+                            if (ks == args.nks - 1) tc_commit(smem_u32(&accFull[acc]));
+                        }
                     }
                     __syncwarp();
                     if (++st == ns) { st = 0; ph ^= 1; }
@@ -527,7 +613,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(full0 + sb * 8);
+                if (lane == 0) {
+                    if (two) mbar_arrive_cluster(lead_full0 + sb * 8);
+                    else mbar_arrive(full0 + sb * 8);
+                }
                 sb += 2;
                 while (sb >= ns) sb -= ns;
                 sa += 2;
@@ -590,7 +679,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 if (args.debug & 4) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&accEmpty[acc]));
+                    if (lane == 0) {
+                        if (two) mbar_arrive_cluster(lead_accEmpty0 + acc * 8);
+                        else mbar_arrive(smem_u32(&accEmpty[acc]));
+                    }
                     if (++acc == 2) { acc = 0; phacc ^= 1; }
                     continue;
                 }
@@ -634,7 +726,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                     a = fma((double)t64, __ldg(args.scale2 + jt * TC_JT), a);
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&accEmpty[acc]));
+                    if (lane == 0) {
+                        if (two) mbar_arrive_cluster(lead_accEmpty0 + acc * 8);
+                        else mbar_arrive(smem_u32(&accEmpty[acc]));
+                    }
                     if (++acc == 2) { acc = 0; phacc ^= 1; }
                     continue;
                 }
@@ -684,7 +779,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&accEmpty[acc]));
+                if (lane == 0) {
+                        if (two) mbar_arrive_cluster(lead_accEmpty0 + acc * 8);
+                        else mbar_arrive(smem_u32(&accEmpty[acc]));
+                    }
                 if (++acc == 2) { acc = 0; phacc ^= 1; }
             }
             if (row_own >= 0) {
@@ -699,9 +797,13 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const TcArgs args) {
 
     tc_fence_before();
     __syncthreads();
+    if (pair) cluster_sync_all();      // nobody leaves while the peer may still signal or read here
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if constexpr (two)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -822,15 +924,15 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static size_t tc_smem_bytes(int nsl, int nb, int pitch) {
-    size_t stage = (size_t)TC_JT * nsl * TC_KSTAGE;
+static size_t tc_smem_bytes(int nsl, int nb, int pitch, int mode) {
+    size_t stage = (size_t)TC_JT * nsl * TC_KSTAGE / (mode == 2 ? 2 : 1);   // per CTA
     return 1024 + (size_t)nb * stage + (size_t)TC_TILE_V * pitch * 4 +
            (32 + 4) * 8 + 16 + TC_TILE_V * 4 + 64;
 }
 
-template <int NSL>
-static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
-    PSB_CUDA(cudaFuncSetAttribute(k_lmm_quadform_tc<NSL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int NSL, bool TWO>
+static int tc_launch2(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
+    PSB_CUDA(cudaFuncSetAttribute(k_lmm_quadform_tc<NSL, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -844,8 +946,14 @@ static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PSB_CUDA(cudaLaunchKernelEx(&cfg, k_lmm_quadform_tc<NSL>, *(const CUtensorMap *)c->tmap_Lq, args));
+    PSB_CUDA(cudaLaunchKernelEx(&cfg, k_lmm_quadform_tc<NSL, TWO>, *(const CUtensorMap *)c->tmap_Lq,
+                                *(const CUtensorMap *)c->tmap_Lq_half, args));
     return PSB_OK;
+}
+template <int NSL>
+static int tc_launch(psb_ctx *c, const TcArgs &args, int grid, size_t smem) {
+    return args.pair == 2 ? tc_launch2<NSL, true>(c, args, grid, smem)
+                          : tc_launch2<NSL, false>(c, args, grid, smem);
 }
 
 // Tensor map over Lq: inner dim = samples (bytes), outer = (jtile, slice, comp) rows.
@@ -858,19 +966,24 @@ static int tc_make_tensor_map(psb_ctx *c, int Jall, int nsl) {
     cuuint64_t gdim[2] = {(cuuint64_t)c->Kpad, (cuuint64_t)Jall * nsl};
     cuuint64_t gstr[1] = {(cuuint64_t)c->Kpad};
     cuuint32_t estr[2] = {1, 1};
-    // one box = 128 samples (one swizzle row) x all sliced rows of a component tile; a pipeline
-    // stage is two boxes (in pair mode one from each CTA of the cluster, multicast to both)
-    CUtensorMap *tm = new CUtensorMap;
-    cuuint32_t box[2] = {TC_KBOX, (cuuint32_t)(TC_JT * nsl)};
-    CUresult cr = ((PFN_encodeTiled)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr, box,
-                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (cr != CUDA_SUCCESS) {
-        delete tm;
-        psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-        return PSB_ERR_CUDA;
+    // one box = 128 samples (one swizzle row) x the sliced rows of a component tile ([0]: all of
+    // them; [1]: half of them, what one CTA of a two-SM pair holds); a pipeline stage is two boxes
+    CUtensorMap *tm[2] = {new CUtensorMap, new CUtensorMap};
+    for (int h = 0; h < 2; ++h) {
+        cuuint32_t box[2] = {TC_KBOX, (cuuint32_t)(TC_JT * nsl) >> h};
+        CUresult cr = ((PFN_encodeTiled)fn)(tm[h], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, c->d_Lq, gdim, gstr,
+                                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            delete tm[0];
+            delete tm[1];
+            psb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+            return PSB_ERR_CUDA;
+        }
     }
-    c->tmap_Lq = tm;
+    c->tmap_Lq = tm[0];
+    c->tmap_Lq_half = tm[1];
     return PSB_OK;
 }
 
@@ -1039,21 +1152,27 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.pitch = pitch;
     int smem_max = 0;
     PSB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    // CTA-pair mode (PSB_TC_PAIR): 2 (default) = two-SM MMAs, each CTA holds half of every B
+    // stage; 1 = independent MMAs, operand stream shared by TMA multicast; 0 = single CTAs
+    a.pair = c->sm_count >= 2 ? 2 : 0;
+    if (getenv("PSB_TC_PAIR")) a.pair = std::max(0, std::min(2, atoi(getenv("PSB_TC_PAIR"))));
+    if (c->sm_count < 2) a.pair = 0;
+    a.debug = getenv("PSB_TC_DEBUG") ? atoi(getenv("PSB_TC_DEBUG")) : 0;
     const int na = (512 - 2 * TC_JT * nsl) / (TC_KSTAGE / 4);   // TMEM A-ring depth (kernel: NA)
     // Operand ring depth: as many stages as shared memory holds, at most TC_MAX_BSTAGES.  The
     // tile's packed rows share shared memory with the ring; they stay there as long as the ring
     // keeps at least the depth of the TMEM A ring (measured at N=5000: rows in shared memory
-    // with 6-7 stages beat global rows with 11), otherwise the expanders read their rows from
+    // beat global rows with a deeper ring), otherwise the expanders read their rows from
     // global memory (PSB_TC_BITS_SMEM=0/1 forces either mode, PSB_TC_STAGES caps the depth).
     auto depth = [&](int pit) {
         int nb = TC_MAX_BSTAGES;
-        while (nb > 2 && tc_smem_bytes(nsl, nb, pit) > (size_t)smem_max) --nb;
+        while (nb > 2 && tc_smem_bytes(nsl, nb, pit, a.pair) > (size_t)smem_max) --nb;
         return nb;
     };
     const int nb_smem = depth(pitch), nb_glob = depth(4);
-    a.bits_in_smem = (tc_smem_bytes(nsl, nb_smem, pitch) <= (size_t)smem_max && nb_smem >= na) ? 1 : 0;
+    a.bits_in_smem = (tc_smem_bytes(nsl, nb_smem, pitch, a.pair) <= (size_t)smem_max && nb_smem >= na) ? 1 : 0;
     if (getenv("PSB_TC_GLOBAL_BITS")) a.bits_in_smem = 0;      // test hook: force the large-N mode
-    if (getenv("PSB_TC_BITS_SMEM") && tc_smem_bytes(nsl, nb_smem, pitch) <= (size_t)smem_max)
+    if (getenv("PSB_TC_BITS_SMEM") && tc_smem_bytes(nsl, nb_smem, pitch, a.pair) <= (size_t)smem_max)
         a.bits_in_smem = atoi(getenv("PSB_TC_BITS_SMEM")) ? 1 : 0;
     if (!a.bits_in_smem) {
         pitch = 4;                               // no bit tile in shared memory
@@ -1061,15 +1180,12 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     }
     int nb = a.bits_in_smem ? nb_smem : nb_glob;
     if (getenv("PSB_TC_STAGES")) nb = std::max(2, std::min(nb, atoi(getenv("PSB_TC_STAGES"))));
-    PSB_REQUIRE(tc_smem_bytes(nsl, nb, pitch) <= (size_t)smem_max, PSB_ERR_UNSUPPORTED,
+    PSB_REQUIRE(tc_smem_bytes(nsl, nb, pitch, a.pair) <= (size_t)smem_max, PSB_ERR_UNSUPPORTED,
                 "n_samples = %d needs more shared memory than the tensor path has; use precision 0",
                 c->N);
     a.n_bstages = nb;
-    const size_t smem = tc_smem_bytes(nsl, nb, pitch);
+    const size_t smem = tc_smem_bytes(nsl, nb, pitch, a.pair);
     const int tiles = psb_div_up(n_tested, TC_TILE_V);
-    // pair mode (default): clusters of two CTAs share the operand stream through TMA multicast
-    a.debug = getenv("PSB_TC_DEBUG") ? atoi(getenv("PSB_TC_DEBUG")) : 0;
-    a.pair = (c->sm_count >= 2 && !(getenv("PSB_TC_PAIR") && atoi(getenv("PSB_TC_PAIR")) == 0)) ? 1 : 0;
     int grid = std::min(tiles, c->sm_count);
     if (a.pair) grid = std::min((tiles + 1) & ~1, c->sm_count & ~1);
     int rc = PSB_OK;
@@ -1097,6 +1213,8 @@ void psb_lmm_tc_free(psb_ctx *c) {
     c->d_scale2 = nullptr;
     c->d_shift = nullptr;
     if (c->tmap_Lq) delete (CUtensorMap *)c->tmap_Lq;
+    if (c->tmap_Lq_half) delete (CUtensorMap *)c->tmap_Lq_half;
+    c->tmap_Lq_half = nullptr;
     c->tmap_Lq = nullptr;
 
 }
