@@ -63,10 +63,12 @@ class KinshipLMM(object):
 
     def _eigh(self, K_):
         """The O(N^3) step of setSU_fromK: on the device (psb_eigh, cuSOLVER syevd in fp64) for
-        N >= 256 unless PYSEER_B200_EIGH=numpy; NumPy when cuSOLVER is not installed.  Either
-        way the per-variant statistics only depend on the eigenspaces, not on the basis chosen
-        inside a degenerate one."""
-        if K_.shape[0] >= 256 and os.environ.get('PYSEER_B200_EIGH', 'device') != 'numpy':
+        N >= 2048 (below that the host routine takes a fraction of a second, less than loading
+        cuSOLVER) unless PYSEER_B200_EIGH=numpy / =device; NumPy when cuSOLVER is not installed.
+        Either way the per-variant statistics only depend on the eigenspaces, not on the basis
+        chosen inside a degenerate one."""
+        mode = os.environ.get('PYSEER_B200_EIGH', 'auto')
+        if mode == 'device' or (mode != 'numpy' and K_.shape[0] >= 2048):
             if self._engine is None:
                 self._engine = Engine(self.device)
             try:
