@@ -249,3 +249,34 @@ def test_large_n_mode_matches_default(monkeypatch):
         m.close()
     for f in ('pvalue', 'beta', 'bse', 'extra'):
         assert np.array_equal(getattr(out[0], f), getattr(out[1], f), equal_nan=True), f
+
+
+@pytest.mark.parametrize('n,nv', [(300, 700), (1100, 300)])
+def test_tensor_kernel_modes_agree(n, nv, monkeypatch):
+    """The launch modes of the tensor kernel -- single CTAs, multicast pairs, two-SM MMAs
+    (PSB_TC_PAIR = 0 / 1 / 2), rows in shared memory or read from global memory -- run the same
+    integer contraction: their results are bit-identical."""
+    from pyseer_b200 import lmm as plmm
+    from pyseer_b200.engine import synth_host, unpack_rows
+    rng = np.random.RandomState(n)
+    G = (rng.uniform(size=(n, 2 * n)) < rng.uniform(0.05, 0.95, 2 * n)).astype(float)
+    K = G.dot(G.T)
+    K *= n / np.diag(K).sum()
+    y = G.dot(rng.normal(size=2 * n)) + rng.normal(size=n) * np.sqrt(n)
+    snps = unpack_rows(synth_host(5, 0, nv, n), n).T.astype(float)
+    m = plmm.KinshipLMM(np.ones((n, 1)), y.reshape(-1, 1), K, precision=5)
+    m.findH2()
+    ref = None
+    for env in ({'PSB_TC_PAIR': '2'}, {'PSB_TC_PAIR': '1'}, {'PSB_TC_PAIR': '0'},
+                {'PSB_TC_PAIR': '2', 'PSB_TC_GLOBAL_BITS': '1'}, {'PSB_TC_PAIR': '2', 'PSB_TC_STAGES': '2'}):
+        for k in ('PSB_TC_PAIR', 'PSB_TC_GLOBAL_BITS', 'PSB_TC_STAGES'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = plmm.fit_lmm_block(m, 0.4, snps)
+        if ref is None:
+            ref = r
+        else:
+            for key in ('p_values', 'beta', 'bse', 'frac_h2'):
+                assert np.array_equal(r[key], ref[key], equal_nan=True), (env, key)
+    m.close()
