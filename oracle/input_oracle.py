@@ -11,6 +11,8 @@ packed-row rule in tests/test_burden_cpu.py.
 """
 import math
 
+import numpy as np
+
 
 def read_vcf_var(genotypes, d):
     """input.py:484-497: update dictionary ``d`` (sample index -> 1 or NaN) with one record.
@@ -43,3 +45,22 @@ def state_vector(d, n_samples):
     for s, v in d.items():
         out[s] = 1 if v == 1 else 2
     return out
+
+
+def burden_union(vbits, vmiss, offsets, members):
+    """Union of packed VCF record rows per burden region (input.py:395-411 with the dictionary
+    rules of read_vcf_var, input.py:489-497), the NumPy checker of what ``psb_submit_burden``
+    computes on the device: carrier if any member record carries, missing if the LAST member
+    record is missing and none carries.  Returns (bits, missing or None)."""
+    R = len(offsets) - 1
+    W = vbits.shape[1]
+    bits = np.zeros((R, W), dtype=np.uint32)
+    miss = np.zeros((R, W), dtype=np.uint32) if vmiss is not None else None
+    for r in range(R):
+        mem = members[offsets[r]:offsets[r + 1]]
+        if len(mem) == 0:
+            continue
+        bits[r] = np.bitwise_or.reduce(vbits[mem], axis=0)
+        if miss is not None:
+            miss[r] = vmiss[mem[-1]] & ~bits[r]
+    return bits, miss

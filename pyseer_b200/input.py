@@ -195,25 +195,6 @@ class VariantReader(object):
         return x.astype(np.int64)
 
 
-def burden_union_host(vbits, vmiss, offsets, members):
-    """Union of VCF record rows per burden region (input.py:395-411 with the dictionary rules of
-    read_vcf_var, input.py:489-497), NumPy statement of what ``psb_submit_burden`` computes on the
-    device: carrier if any member record carries, missing if the LAST member record is missing
-    and none carries.  Returns (bits, missing or None)."""
-    R = len(offsets) - 1
-    W = vbits.shape[1]
-    bits = np.zeros((R, W), dtype=np.uint32)
-    miss = np.zeros((R, W), dtype=np.uint32) if vmiss is not None else None
-    for r in range(R):
-        mem = members[offsets[r]:offsets[r + 1]]
-        if len(mem) == 0:
-            continue
-        bits[r] = np.bitwise_or.reduce(vbits[mem], axis=0)
-        if miss is not None:
-            miss[r] = vmiss[mem[-1]] & ~bits[r]
-    return bits, miss
-
-
 class VcfReader(object):
     """VCF (and burden-region) input without pysam: plain or gzip text VCF, dominant encoding.
 
@@ -245,9 +226,12 @@ class VcfReader(object):
             raise ValueError('no #CHROM header line found; is this a VCF file?')
         self.regions = None
         # burden regions: `reducer(vbits, vmiss, offsets, members) -> (bits, missing)` forms the
-        # per-region union of record rows; the CLI plugs the device reduction in
-        # (Engine.submit_burden), the default is the NumPy statement of the same rule
-        self.reducer = reducer or burden_union_host
+        # per-region union of record rows on the device (Engine.submit_burden + download_rows, as
+        # the CLI wires it); there is no host implementation in the package
+        if burden_file and reducer is None:
+            raise ValueError('burden regions need a `reducer` (the device union, '
+                             'Engine.submit_burden); pyseer_b200 has no CPU fallback')
+        self.reducer = reducer
         if burden_file:
             self.regions = []
             with open(burden_file) as rf:

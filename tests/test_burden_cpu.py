@@ -1,5 +1,5 @@
-"""Burden regions, host side: the packed-row union rule (pyseer_b200.input.burden_union_host, the
-NumPy statement of psb_submit_burden) against the reference's dictionary semantics restated in
+"""Burden regions, host side: the packed-row union rule (oracle.input_oracle.burden_union, the
+NumPy checker of psb_submit_burden) against the reference's dictionary semantics restated in
 oracle/input_oracle.py (input.py:395-411, 457-502), and the VcfReader region reader on the
 reference's own VCF / burden fixtures."""
 import os
@@ -27,7 +27,7 @@ def _random_records(rng, n_rec, n, diploid):
 
 def test_union_rule_matches_reference_dictionary():
     from oracle import input_oracle
-    from pyseer_b200.input import burden_union_host
+    from oracle.input_oracle import burden_union as burden_union_host
     from pyseer_b200.engine import unpack_rows
     rng = np.random.RandomState(3)
     for diploid in (False, True):
@@ -65,7 +65,7 @@ def test_vcf_reader_burden_regions():
     header, recs = lines[0], lines[1:]
     samples = header[9:]
     p = pd.Series(np.zeros(len(samples)), index=samples)
-    reader = VcfReader(vcf, p, regions)
+    reader = VcfReader(vcf, p, regions, reducer=input_oracle.burden_union)
     batches = list(reader.batches(1000))
     assert len(batches) == 1
     b = batches[0]

@@ -40,7 +40,7 @@ def _regions(rng, n_reg, n_rec):
 @pytest.mark.parametrize('with_missing', [False, True])
 def test_device_union_bit_exact(n, with_missing):
     from pyseer_b200 import lmm as plmm
-    from pyseer_b200.input import burden_union_host
+    from oracle.input_oracle import burden_union as burden_union_host
     K, y = _problem(min(n, 333))
     rng = np.random.RandomState(n)
     # the union does not depend on the model: a small LMM context with the right N
@@ -91,7 +91,7 @@ def test_burden_lmm_matches_oracle(precision):
     (bit-identical) == oracle fit_lmm_block on the unioned 0/1 matrix (1e-6)."""
     from pyseer_b200 import lmm as plmm
     from pyseer_b200.engine import unpack_rows
-    from pyseer_b200.input import burden_union_host
+    from oracle.input_oracle import burden_union as burden_union_host
     from oracle import lmm_oracle
     n = 300
     K, y = _problem(n)
@@ -126,7 +126,7 @@ def test_burden_lmm_matches_oracle(precision):
 
 def test_burden_fixed_matches_unioned_rows():
     from pyseer_b200 import model as pmodel
-    from pyseer_b200.input import burden_union_host
+    from oracle.input_oracle import burden_union as burden_union_host
     n = 200
     rng = np.random.RandomState(21)
     mds = rng.uniform(-1, 1, size=(n, 3))
