@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--model', default='lmm', choices=['lmm', 'fixed', 'fixed-cont'],
+    ap.add_argument('--model', default='lmm', choices=['lmm', 'fixed', 'fixed-cont', 'burden'],
                     help="lmm: BASELINE configs[3] (headline); fixed: configs[2], logistic + Firth, "
                          "N=2000, 10 MDS covariates, 10M k-mers")
     ap.add_argument('--samples', type=int, default=0, help='0 = the config default')
@@ -390,6 +390,66 @@ class LmmWorkload(object):
                 'traffic': ncu_traffic('lmm:n=%d:kmers=%d:k=%d' % (n, self.kpg, k))}
 
 
+class BurdenWorkload(LmmWorkload):
+    """BASELINE configs[4]: VCF burden test, 100k regions x 10000 samples, LMM, sharded by region
+    over 8 GPUs.  A region is the union of 1-20 rare variant rows (af ~ U(0.001, 0.02), dominant
+    encoding, input.py:395-407); the union runs on the device (psb_submit_burden*), then the region
+    rows take the LMM path.  `kpg` counts REGIONS per GPU; the metric's unit is regions tested/s."""
+    name = 'burden'
+    default_n, default_kpg = 10000, 12500
+
+    def __init__(self, a, n, kpg, world):
+        LmmWorkload.__init__(self, a, n, kpg, world)
+        self.config.update({
+            'workload': 'VCF burden test, LMM continuous phenotype, N=%d samples, %d burden regions per GPU, '
+                        'each the union of 1-20 rare variant rows (BASELINE configs[4]: 100k regions x '
+                        '10000 samples over 8 GPUs); unit = regions' % (n, kpg),
+            'af': 'member rows U(0.001,0.02); regions = OR of 1..20 members',
+            'cache': 'member rows (%.2f GB) + region rows per GPU'
+                     % (kpg * 10.5 * ((n + 127) // 128 * 16) / 1e9)})
+
+    def regions(self, rank):
+        rng = np.random.RandomState(SEED % (2 ** 31) + 17 + rank)
+        sizes = rng.randint(1, 21, size=self.kpg)
+        offs = np.zeros(self.kpg + 1, dtype=np.int64)
+        offs[1:] = np.cumsum(sizes)
+        return offs, np.arange(int(offs[-1]), dtype=np.int32)     # members of region r are contiguous
+
+    def prepare(self, eng, rank, ys):
+        self.offs, self.mem = self.regions(rank)
+        self.n_rec = int(self.offs[-1])
+        eng.synth_device(SEED + 5, rank * 21 * self.kpg, self.n_rec, 0.001, 0.02, 0, None)
+        self.rec_ptr, _, _, self.rec_w = eng.submitted_device()
+
+    def run(self, eng):
+        eng.event_record(4)
+        eng.submit_burden_device(self.rec_ptr, self.n_rec, self.rec_w, self.offs, self.mem)
+        eng.event_record(5)
+        LmmWorkload.run(self, eng)
+
+    def check(self, st, rec_head, cols):
+        from oracle import input_oracle as io
+        nreg = int(np.searchsorted(self.offs, rec_head.shape[0], side='right')) - 1
+        nreg = min(nreg, 300)
+        bits, _ = io.burden_union(rec_head, None, self.offs[:nreg + 1], self.mem[:int(self.offs[nreg])])
+        out = LmmWorkload.check(self, st, bits, {k: v[:nreg] for k, v in cols.items()})
+        out['regions'] = nreg
+        return out
+
+    def roofline(self, tested, k_ms, run_ms, W, pk, pk_kind):
+        r = LmmWorkload.roofline(self, tested, k_ms, run_ms, W, pk, pk_kind)
+        r['traffic'] = None
+        if getattr(self, 'or_ms', None):
+            by = (self.n_rec + self.kpg) * W * 4.0 + self.n_rec * 4.0 + self.kpg * 8.0
+            r['burden_or'] = {'bound': 'hbm', 'kernel': 'k_burden_or', 'ms': self.or_ms,
+                              'algorithmic_bytes': by, 'achieved': by / (self.or_ms / 1e3) / 1e9,
+                              'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                              'frac': by / (self.or_ms / 1e3) / 1e9 / pk['hbm_gbs'],
+                              'note': 'CUDA events around psb_submit_burden_device (member lists H2D '
+                                      'included); member rows read once, region rows written once'}
+        return r
+
+
 class FixedWorkload(object):
     name = 'fixed'
     stats = None
@@ -535,7 +595,8 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    wcls = {'lmm': LmmWorkload, 'fixed': FixedWorkload, 'fixed-cont': FixedContWorkload}[a.model]
+    wcls = {'lmm': LmmWorkload, 'fixed': FixedWorkload, 'fixed-cont': FixedContWorkload,
+            'burden': BurdenWorkload}[a.model]
     n = a.samples or wcls.default_n
     kpg = a.kmers_per_gpu or wcls.default_kpg
     wl = wcls(a, n, kpg, world)
@@ -615,7 +676,10 @@ def main():
     from pyseer_b200.engine import Engine, PinnedBuffer, words_per_row
     eng = Engine(local_rank)
     wl.setup_engine(eng, st)
-    eng.synth_device(SEED, rank * kpg, kpg, 0.02, 0.98, 1000, ys)
+    if hasattr(wl, 'prepare'):
+        wl.prepare(eng, rank, ys)
+    else:
+        eng.synth_device(SEED, rank * kpg, kpg, 0.02, 0.98, 1000, ys)
     W = words_per_row(n)
 
     from pyseer_b200 import sharding
@@ -661,6 +725,8 @@ def main():
     # the last timed step (every step launches the same grid on the same rows)
     k_ms = eng.last_ms(1)
     run_ms = eng.last_ms(0)
+    if a.model == 'burden':
+        wl.or_ms = eng.event_elapsed(4, 5)
     if dist is not None:
         t = torch.tensor([ms, float(tested)], dtype=torch.float64, device=dev)
         tmax = t.clone()
@@ -676,7 +742,43 @@ def main():
     # ---- end to end through the C ABI with host buffers -----------------------------------
     e2e = None
     check = None
-    if not a.no_e2e:
+    if not a.no_e2e and a.model == 'burden':
+        # host record rows + member lists -> psb_submit_burden (H2D, device union) -> LMM -> table
+        eng.submit_device(wl.rec_ptr, wl.n_rec, wl.rec_w)
+        pin = PinnedBuffer((wl.n_rec, W), np.uint32)
+        eng.download_bits(pin.array)
+        outs = {name: PinnedBuffer((kpg,), {4: np.int32, 8: np.float64}[b] if name != 'flags'
+                                   else np.uint32) for name, b in COLS}
+        optr = {name: outs[name].array.ctypes.data for name, _ in COLS}
+
+        def e2e_step():
+            eng.submit_burden(pin.array, None, wl.offs, wl.mem)
+            LmmWorkload.run(wl, eng)
+            eng.fetch_into(optr)
+
+        e2e_step()
+        barrier()
+        eng.sync()
+        eng.event_record(2)
+        for _ in range(a.steps):
+            e2e_step()
+        eng.event_record(3)
+        eng.sync()
+        barrier()
+        ems = eng.event_elapsed(2, 3)
+        if dist is not None:
+            t = torch.tensor([ems], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t[0])
+        e2e = {'value': tested_all * a.steps / (ems / 1e3), 'unit': UNIT,
+               'h2d_bytes_per_step': int(wl.n_rec * W * 4 + wl.mem.nbytes + wl.offs.nbytes),
+               'd2h_bytes_per_step': int(kpg * row_bytes), 'ms_per_step': ems / a.steps,
+               'chunks_per_step': 1}
+        if rank == 0 and a.check > 0:
+            nrec = int(wl.offs[min(300, kpg)])
+            cols = {name: outs[name].array[:300].copy() for name in ('pvalue', 'beta')}
+            check = wl.check(st, pin.array[:nrec].copy(), cols)
+    elif not a.no_e2e:
         pin = PinnedBuffer((kpg, W), np.uint32)
         eng.download_bits(pin.array)
         outs = {name: PinnedBuffer((kpg,), {4: np.int32, 8: np.float64}[b] if name != 'flags'
