@@ -227,7 +227,7 @@ int psb_launch_prefilter(psb_ctx *c, const psb_params *prm, int lmm_rule) {
 // 16-byte cells; a warp walks 4 variants at a time so every cell read serves 4 rows.
 // Non-carrier sums follow from the totals (T - sum over carriers).
 // ---------------------------------------------------------------------------------
-#define BST_VPW 4
+#define BST_VPW 8
 
 template <int NC>
 __global__ void __launch_bounds__(256)
