@@ -20,7 +20,7 @@ from . import __version__
 from . import _lib
 from . import classes as var_obj
 from .engine import notes_from_flags
-from .input import (VariantReader, VcfReader, hash_pattern, load_covariates, load_lineage,
+from .input import (VariantReader, open_variants, VcfReader, hash_pattern, load_covariates, load_lineage,
                     load_phenotypes, load_structure)
 from .utils import format_output
 
@@ -69,6 +69,9 @@ def get_options(argv=None):
     ot.add_argument('--print-filtered', action='store_true', default=False)
     ot.add_argument('--output-patterns', default=False)
     ot.add_argument('--uncompressed', action='store_true', default=False)
+    ot.add_argument('--bits-cache', default=None,
+                    help='packed binary cache of the --kmers / --pres file: written on the first run, '
+                         'read instead of parsing the text on later runs with the same samples')
     ot.add_argument('--cpu', type=int, default=1, help='accepted for compatibility; unused')
     ot.add_argument('--block_size', type=int, default=3000)
     ot.add_argument('--gpu', type=int, default=0, help='CUDA device index')
@@ -225,7 +228,8 @@ def main(argv=None):
 
         reader = VcfReader(o.vcf, p, o.burden, reducer=device_union if o.burden else None)
     else:
-        reader = VariantReader('kmers' if o.kmers else 'Rtab', o.kmers or o.pres, p, o.uncompressed)
+        reader = open_variants('kmers' if o.kmers else 'Rtab', o.kmers or o.pres, p, o.uncompressed,
+                               cache=o.bits_cache)
 
     header = ['variant', 'af', 'filter-pvalue', 'lrt-pvalue', 'beta', 'beta-std-err']
     if not o.lmm:

@@ -8,6 +8,8 @@ bit positions once, and per-variant sample lists are only materialised when aske
 """
 import binascii
 import hashlib
+import json
+import os
 import sys
 
 import numpy as np
@@ -193,6 +195,158 @@ class VariantReader(object):
                 k[m.astype(bool)] = np.nan
                 return k
         return x.astype(np.int64)
+
+
+class PackedCache(object):
+    """Pre-packed binary cache of a variant file: the packed rows the reader produced,
+    stored once so that later runs on the same file and the same sample order skip text parsing
+    (the reference parser manages 10^2-10^3 variants/s, input.py:301-454; the native one ~6 k/s at
+    N=5000; the cache streams at disk speed).
+
+    Layout: one JSON header line (magic, sample-order digest, source size and mtime, row width),
+    then chunks ``int64 n, int64 names_bytes, int64 has_missing | names (NUL separated) | bits
+    uint32[n][W] | missing uint32[n][W] if has_missing``; a chunk with n = 0 closes the file -- a
+    cache without it (interrupted run) is not used."""
+    MAGIC = 'pyseer_b200-bits-1'
+
+    @staticmethod
+    def _header(var_type, source, samples, W):
+        st = os.stat(source)
+        digest = hashlib.sha1('\n'.join(samples).encode()).hexdigest()
+        return {'magic': PackedCache.MAGIC, 'var_type': var_type, 'n_samples': len(samples), 'W': int(W),
+                'samples_sha1': digest, 'source_size': st.st_size, 'source_mtime_ns': st.st_mtime_ns}
+
+    @staticmethod
+    def valid(path, var_type, source, samples, W):
+        """True when ``path`` is a complete cache of ``source`` for this sample order."""
+        try:
+            want = PackedCache._header(var_type, source, samples, W)
+            with open(path, 'rb') as fh:
+                got = json.loads(fh.readline().decode())
+                if got != want:
+                    return False
+                fh.seek(-24, os.SEEK_END)
+                tail = np.frombuffer(fh.read(24), dtype='<i8')
+                return tail.shape[0] == 3 and tail[0] == 0
+        except (OSError, ValueError):
+            return False
+
+
+class PackedCacheWriter(object):
+    def __init__(self, path, var_type, source, samples, W):
+        self.fh = open(path, 'wb')
+        self.fh.write((json.dumps(PackedCache._header(var_type, source, samples, W), sort_keys=True) + '\n').encode())
+
+    def add(self, batch):
+        names = ('\0'.join(batch.names) + '\0').encode()
+        has_m = batch.missing is not None
+        self.fh.write(np.array([batch.n, len(names), int(has_m)], dtype='<i8').tobytes())
+        self.fh.write(names)
+        self.fh.write(np.ascontiguousarray(batch.bits, dtype='<u4').tobytes())
+        if has_m:
+            self.fh.write(np.ascontiguousarray(batch.missing, dtype='<u4').tobytes())
+
+    def close(self, complete=True):
+        if self.fh:
+            if complete:
+                self.fh.write(np.zeros(3, dtype='<i8').tobytes())
+            self.fh.close()
+            self.fh = None
+
+
+class CachedVariantReader(object):
+    """Same interface as VariantReader, over a PackedCache file (no parsing, no native library)."""
+
+    def __init__(self, path, p):
+        self.samples = [str(s) for s in p.index]
+        self.n_samples = len(self.samples)
+        self.W = words_per_row(self.n_samples)
+        self.fh = open(path, 'rb')
+        self.header = json.loads(self.fh.readline().decode())
+        self.var_type = self.header['var_type']
+
+    def close(self):
+        if self.fh:
+            self.fh.close()
+            self.fh = None
+
+    def _chunks(self):
+        W = self.W
+        while True:
+            head = np.frombuffer(self.fh.read(24), dtype='<i8')
+            if head.shape[0] < 3 or head[0] == 0:
+                return
+            n, nb, has_m = int(head[0]), int(head[1]), int(head[2])
+            names = self.fh.read(nb).decode().split('\0')[:n]
+            bits = np.frombuffer(self.fh.read(n * W * 4), dtype='<u4').reshape(n, W)
+            miss = np.frombuffer(self.fh.read(n * W * 4), dtype='<u4').reshape(n, W) if has_m else None
+            yield names, bits, miss
+
+    def batches(self, size):
+        names, bits, miss = [], [], []
+
+        def flush(k):
+            b = np.concatenate(bits) if len(bits) > 1 else bits[0]
+            any_m = any(m is not None for m in miss)
+            m = None
+            if any_m:
+                m = np.concatenate([mm if mm is not None else np.zeros_like(bb) for mm, bb in zip(miss, bits)])
+            out = VariantBatch(names[:k], np.ascontiguousarray(b[:k]),
+                               np.ascontiguousarray(m[:k]) if m is not None and m[:k].any() else None)
+            rest_b, rest_m = b[k:], (m[k:] if m is not None else None)
+            del names[:k]
+            bits[:] = [rest_b] if rest_b.shape[0] else []
+            miss[:] = [rest_m] if rest_b.shape[0] else []
+            empty = ~(out.bits.any(axis=1) | (out.missing.any(axis=1) if out.missing is not None else False))
+            for i in np.nonzero(empty)[0]:
+                sys.stderr.write('No observations of ' + out.names[i] + ' in selected samples\n')
+            return out
+
+        for nm, b, m in self._chunks():
+            names.extend(nm)
+            bits.append(b)
+            miss.append(m)
+            while len(names) >= size:
+                yield flush(size)
+        if names:
+            yield flush(len(names))
+
+    sample_lists = VariantReader.sample_lists
+    k_vector = VariantReader.k_vector
+
+
+def open_variants(var_type, path, p, uncompressed=False, cache=None):
+    """VariantReader, or -- with ``cache`` -- a CachedVariantReader when a valid packed cache of
+    ``path`` for this sample order exists, else a VariantReader that writes the cache as it reads
+    (``--bits-cache``)."""
+    if cache is None:
+        return VariantReader(var_type, path, p, uncompressed)
+    samples = [str(s) for s in p.index]
+    W = words_per_row(len(samples))
+    if PackedCache.valid(cache, var_type, path, samples, W):
+        sys.stderr.write('Reading packed variants from ' + str(cache) + '\n')
+        return CachedVariantReader(cache, p)
+    rd = VariantReader(var_type, path, p, uncompressed)
+    writer = PackedCacheWriter(cache, var_type, path, samples, W)
+    inner = rd.batches
+
+    def batches(size, names_cap=None):
+        done = False
+        try:
+            for b in inner(size, names_cap):
+                writer.add(b)
+                yield b
+            done = True
+        finally:
+            writer.close(complete=done)
+            if not done:
+                try:
+                    os.unlink(cache)
+                except OSError:
+                    pass
+
+    rd.batches = batches
+    return rd
 
 
 class VcfReader(object):

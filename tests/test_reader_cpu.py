@@ -84,3 +84,66 @@ def test_hash_pattern_golden(goldens):
     # tests/input_test.py:840-845: the 'binary' column of subset.pheno
     pb = pd.read_csv(os.path.join(GOLDEN, 'subset.pheno'), index_col=0, sep='\t')['binary']
     assert hash_pattern(pb.values) == goldens['hash_pattern_k'].encode()
+
+
+def test_packed_cache_roundtrip(tmp_path):
+    """--bits-cache: the first pass parses and writes the cache, later passes stream the packed
+    rows back (any batch size), and a different sample order invalidates it."""
+    from pyseer_b200.input import open_variants, CachedVariantReader, PackedCache
+    p = _pheno()
+    src = os.path.join(GOLDEN, 'kmers.gz')
+    cache = str(tmp_path / 'kmers.bits')
+    with contextlib.redirect_stderr(io.StringIO()):
+        rd = open_variants('kmers', src, p, cache=cache)
+        assert isinstance(rd, VariantReader)
+        first = list(rd.batches(64))
+        rd.close()
+    assert PackedCache.valid(cache, 'kmers', src, [str(s) for s in p.index], first[0].bits.shape[1])
+    err = io.StringIO()
+    with contextlib.redirect_stderr(err):
+        rd2 = open_variants('kmers', src, p, cache=cache)
+        assert isinstance(rd2, CachedVariantReader)
+        second = list(rd2.batches(30))
+        rd2.close()
+    assert err.getvalue().count('No observations of') == 6
+    assert [b.n for b in second] == [30] * 6 + [20]
+    assert [n for b in first for n in b.names] == [n for b in second for n in b.names]
+    assert np.array_equal(np.concatenate([b.bits for b in first]), np.concatenate([b.bits for b in second]))
+    assert all(b.missing is None for b in second)
+    assert np.array_equal(rd2.k_vector(second[0], 3), VariantReader.k_vector(rd2, first[0], 3))
+    # another sample order: the cache does not apply and is rewritten
+    p2 = p.iloc[::-1]
+    with contextlib.redirect_stderr(io.StringIO()):
+        rd3 = open_variants('kmers', src, p2, cache=cache)
+        assert isinstance(rd3, VariantReader)
+        third = list(rd3.batches(200))
+        rd3.close()
+    n = len(p.index)
+    assert np.array_equal(unpack_rows(third[0].bits, n)[:, ::-1], unpack_rows(np.concatenate([b.bits for b in first]), n))
+    # an interrupted write leaves no usable cache
+    cache2 = str(tmp_path / 'partial.bits')
+    with contextlib.redirect_stderr(io.StringIO()):
+        rd4 = open_variants('kmers', src, p, cache=cache2)
+        it = rd4.batches(64)
+        next(it)
+        it.close()
+        rd4.close()
+    assert not os.path.exists(cache2)
+
+
+def test_packed_cache_with_missing(tmp_path):
+    from pyseer_b200.input import open_variants, CachedVariantReader
+    p = _pheno()
+    samples = list(p.index)
+    f = tmp_path / 'm.Rtab'
+    f.write_text('Gene\t' + '\t'.join(samples[:4]) + '\n' + 'g1\t1\t0\t.\t1\n' + 'g2\t0\t0\t0\t0\n' + 'g3\t1\t1\t1\t.\n')
+    cache = str(tmp_path / 'm.bits')
+    with contextlib.redirect_stderr(io.StringIO()):
+        a = list(open_variants('Rtab', str(f), p, uncompressed=True, cache=cache).batches(2))
+        rd = open_variants('Rtab', str(f), p, uncompressed=True, cache=cache)
+        assert isinstance(rd, CachedVariantReader)
+        b = list(rd.batches(3))
+    assert [x for t in a for x in t.names] == b[0].names == ['g1', 'g2', 'g3']
+    assert np.array_equal(np.concatenate([t.bits for t in a]), b[0].bits)
+    ma = np.concatenate([t.missing if t.missing is not None else np.zeros_like(t.bits) for t in a])
+    assert b[0].missing is not None and np.array_equal(ma, b[0].missing)
