@@ -237,6 +237,8 @@ int psb_reader_open(const char *path, int32_t var_type, const char *const *sampl
 int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, uint32_t *missing,
                     int32_t words_per_row, char *names, int64_t names_cap, int64_t *name_off,
                     int32_t *info, int64_t *n_read, int32_t *any_missing);
+/* parser threads for psb_reader_next (pyseer's --cpu): lines are read serially, parsed in parallel */
+int psb_reader_set_threads(psb_reader *reader, int32_t n_threads);
 int psb_reader_close(psb_reader *reader);
 
 /* ---- measurement ------------------------------------------------------------- */

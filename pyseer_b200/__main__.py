@@ -72,7 +72,7 @@ def get_options(argv=None):
     ot.add_argument('--bits-cache', default=None,
                     help='packed binary cache of the --kmers / --pres file: written on the first run, '
                          'read instead of parsing the text on later runs with the same samples')
-    ot.add_argument('--cpu', type=int, default=1, help='accepted for compatibility; unused')
+    ot.add_argument('--cpu', type=int, default=1, help='parser threads of the native k-mer / Rtab reader')
     ot.add_argument('--block_size', type=int, default=3000)
     ot.add_argument('--gpu', type=int, default=0, help='CUDA device index')
     ot.add_argument('--gpu-batch', type=int, default=48000,
@@ -229,7 +229,7 @@ def main(argv=None):
         reader = VcfReader(o.vcf, p, o.burden, reducer=device_union if o.burden else None)
     else:
         reader = open_variants('kmers' if o.kmers else 'Rtab', o.kmers or o.pres, p, o.uncompressed,
-                               cache=o.bits_cache)
+                               cache=o.bits_cache, threads=o.cpu)
 
     header = ['variant', 'af', 'filter-pvalue', 'lrt-pvalue', 'beta', 'beta-std-err']
     if not o.lmm:

@@ -9,8 +9,10 @@
 // Host-only code; lives in the same shared library as the kernels.
 #include <zlib.h>
 
+#include <algorithm>
 #include <string>
 #include <string_view>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -27,6 +29,8 @@ struct psb_reader {
     size_t pos = 0, len = 0;
     bool eof = false;
     std::string line;
+    std::vector<std::string> lines;         // lines of the batch being parsed
+    int n_threads = 1;
 };
 
 static bool reader_fill(psb_reader *r) {
@@ -113,6 +117,93 @@ extern "C" int psb_reader_close(psb_reader *r) {
     return PSB_OK;
 }
 
+// One parsed line -> one packed row.  Returns PSB_OK or an error code with *err set to a static
+// message (worker threads do not touch the thread-local error text).
+struct psb_line_out {
+    int flags = 0;
+    int rc = PSB_OK;
+    const char *err = nullptr;
+};
+
+static void parse_line(const psb_reader *r, const char *L, size_t len, uint32_t *row, uint32_t *mrow,
+                       int words_per_row, psb_line_out *out) {
+    memset(row, 0, (size_t)words_per_row * 4);
+    if (mrow) memset(mrow, 0, (size_t)words_per_row * 4);
+    int flags = 0;
+    bool seen = false;
+#define LINE_REQUIRE(cond, code, msg)  \
+    do {                               \
+        if (!(cond)) {                 \
+            out->rc = (code);          \
+            out->err = (msg);          \
+            return;                    \
+        }                              \
+    } while (0)
+    if (r->var_type == 0) {
+        // samples after the first '|'
+        const char *bar = (const char *)memchr(L, '|', len);
+        LINE_REQUIRE(bar, PSB_ERR_ARG, "k-mer line without '|' separator");
+        size_t k = (size_t)(bar - L) + 1;
+        while (k < len) {
+            while (k < len && (L[k] == ' ' || L[k] == '\t')) ++k;
+            size_t e = k;
+            while (e < len && L[e] != ' ' && L[e] != '\t') ++e;
+            if (e > k) {
+                size_t c = k;
+                while (c < e && L[c] != ':') ++c;
+                auto it = r->index.find(std::string_view(L + k, c - k));
+                if (it != r->index.end()) {
+                    row[it->second >> 5] |= 1u << (it->second & 31);
+                    seen = true;
+                }
+            }
+            k = e;
+        }
+    } else {
+        size_t i = 0;
+        while (i < len && L[i] != '\t') ++i;
+        LINE_REQUIRE(i < len, PSB_ERR_ARG, "No sample data found; is this a Rtab file?");
+        size_t col = 0, k = i + 1;
+        const size_t ncol = r->rtab_col.size();
+        for (;;) {
+            size_t e = k;
+            while (e < len && L[e] != '\t') ++e;
+            LINE_REQUIRE(col < ncol, PSB_ERR_ARG, "Unexpected mismatch between header and data row");
+            const size_t fl = e - k;
+            const int s = r->rtab_col[col];
+            if (fl == 1 && L[k] == '1') {
+                if (s >= 0) { row[s >> 5] |= 1u << (s & 31); seen = true; }
+            } else if (fl == 0 || (fl == 1 && L[k] == '.')) {
+                if (s >= 0) {
+                    flags |= 1;
+                    seen = true;
+                    if (mrow) mrow[s >> 5] |= 1u << (s & 31);
+                }
+            } else {
+                LINE_REQUIRE(fl == 1 && L[k] == '0', PSB_ERR_ARG, "Rtab file not binary");
+            }
+            ++col;
+            if (e >= len) break;
+            k = e + 1;
+        }
+        LINE_REQUIRE(col == ncol, PSB_ERR_ARG, "Unexpected mismatch between header and data row");
+        LINE_REQUIRE(!(flags & 1) || mrow, PSB_ERR_ARG,
+                     "row has missing genotypes but no missing buffer was given");
+    }
+#undef LINE_REQUIRE
+    if (!seen) flags |= 2;
+    out->flags = flags;
+}
+
+// Parser threads for psb_reader_next (pyseer's --cpu, which this package uses for parsing only):
+// the lines of a batch are read and split serially (zlib is a serial stream), then parsed into
+// their rows in parallel -- lines are independent and every row is written by one thread.
+extern "C" int psb_reader_set_threads(psb_reader *r, int32_t n_threads) {
+    PSB_REQUIRE(r, PSB_ERR_ARG, "reader is NULL");
+    r->n_threads = n_threads < 1 ? 1 : (n_threads > 64 ? 64 : n_threads);
+    return PSB_OK;
+}
+
 // Reads up to max_variants rows.  bits / missing: max_variants x words_per_row (zeroed here);
 // names: concatenated NUL-terminated variant names (names_cap bytes); name_off[v] = offset of
 // name v; info[v]: bit 0 = row has missing genotypes, bit 1 = no observation in the selected
@@ -126,90 +217,59 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
     PSB_REQUIRE(words_per_row * 32 >= r->n_samples, PSB_ERR_ARG, "words_per_row too small");
     *n_read = 0;
     if (any_missing) *any_missing = 0;
+    // ---- serial: lines of the batch and their names -----------------------------------
+    std::vector<std::string> &lines = r->lines;
     int64_t n = 0, used = 0;
     while (n < max_variants) {
-        // stop early when the name buffer may not hold another name (variant names are
-        // k-mers: bounded by the longest line seen so far is not known, so keep 64 KiB free)
+        // stop early when the name buffer may not hold another name (keep 64 KiB free)
         if (names_cap - used < (1 << 16) && n > 0) break;
         if (!reader_getline(r)) break;
-        const std::string &L = r->line;
+        std::string &L = r->line;
         size_t len = L.size();
         while (len > 0 && (L[len - 1] == '\r' || L[len - 1] == ' ' || L[len - 1] == '\t')) --len;
         if (len == 0) continue;
-        uint32_t *row = bits + n * words_per_row;
-        memset(row, 0, (size_t)words_per_row * 4);
-        uint32_t *mrow = missing ? missing + n * words_per_row : nullptr;
-        if (mrow) memset(mrow, 0, (size_t)words_per_row * 4);
-        int flags = 0;
-        bool seen = false;
-        size_t name_len = 0;
-        if (r->var_type == 0) {
-            // name = first whitespace-delimited token; samples after the first '|'
-            size_t i = 0;
+        L.resize(len);
+        size_t i = 0, j = 0;
+        if (r->var_type == 0) {      // name = first whitespace-delimited token
             while (i < len && (L[i] == ' ' || L[i] == '\t')) ++i;
-            size_t j = i;
+            j = i;
             while (j < len && L[j] != ' ' && L[j] != '\t') ++j;
-            name_len = j - i;
-            PSB_REQUIRE((int64_t)name_len + 1 <= names_cap - used, PSB_ERR_NOMEM, "name buffer too small");
-            memcpy(names + used, L.data() + i, name_len);
-            const char *bar = (const char *)memchr(L.data(), '|', len);
-            PSB_REQUIRE(bar, PSB_ERR_ARG, "k-mer line without '|' separator");
-            size_t k = (size_t)(bar - L.data()) + 1;
-            while (k < len) {
-                while (k < len && (L[k] == ' ' || L[k] == '\t')) ++k;
-                size_t e = k;
-                while (e < len && L[e] != ' ' && L[e] != '\t') ++e;
-                if (e > k) {
-                    size_t c = k;
-                    while (c < e && L[c] != ':') ++c;
-                    auto it = r->index.find(std::string_view(L.data() + k, c - k));
-                    if (it != r->index.end()) {
-                        row[it->second >> 5] |= 1u << (it->second & 31);
-                        seen = true;
-                    }
-                }
-                k = e;
-            }
-        } else {
-            size_t i = 0;
-            while (i < len && L[i] != '\t') ++i;
-            name_len = i;
-            PSB_REQUIRE((int64_t)name_len + 1 <= names_cap - used, PSB_ERR_NOMEM, "name buffer too small");
-            memcpy(names + used, L.data(), name_len);
-            PSB_REQUIRE(i < len, PSB_ERR_ARG, "No sample data found; is this a Rtab file?");
-            size_t col = 0, k = i + 1;
-            const size_t ncol = r->rtab_col.size();
-            for (;;) {
-                size_t e = k;
-                while (e < len && L[e] != '\t') ++e;
-                PSB_REQUIRE(col < ncol, PSB_ERR_ARG, "Unexpected mismatch between header and data row");
-                const size_t fl = e - k;
-                const int s = r->rtab_col[col];
-                if (fl == 1 && L[k] == '1') {
-                    if (s >= 0) { row[s >> 5] |= 1u << (s & 31); seen = true; }
-                } else if (fl == 0 || (fl == 1 && L[k] == '.')) {
-                    if (s >= 0) {
-                        flags |= 1;
-                        seen = true;
-                        if (mrow) mrow[s >> 5] |= 1u << (s & 31);
-                    }
-                } else {
-                    PSB_REQUIRE(fl == 1 && L[k] == '0', PSB_ERR_ARG, "Rtab file not binary");
-                }
-                ++col;
-                if (e >= len) break;
-                k = e + 1;
-            }
-            PSB_REQUIRE(col == ncol, PSB_ERR_ARG, "Unexpected mismatch between header and data row");
-            PSB_REQUIRE(!(flags & 1) || mrow, PSB_ERR_ARG, "row has missing genotypes but no missing buffer was given");
+        } else {                     // name = first tab-delimited field
+            while (j < len && L[j] != '\t') ++j;
         }
-        if (!seen) flags |= 2;
-        if ((flags & 1) && any_missing) *any_missing = 1;
+        const size_t name_len = j - i;
+        PSB_REQUIRE((int64_t)name_len + 1 <= names_cap - used, PSB_ERR_NOMEM, "name buffer too small");
+        memcpy(names + used, L.data() + i, name_len);
         names[used + name_len] = '\0';
         name_off[n] = used;
         used += (int64_t)name_len + 1;
-        info[n] = flags;
+        if ((size_t)n >= lines.size()) lines.emplace_back();
+        lines[n].swap(L);
         ++n;
+    }
+    // ---- parallel: one row per line ------------------------------------------------------
+    std::vector<psb_line_out> outs((size_t)n);
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t v = lo; v < hi; ++v)
+            parse_line(r, lines[v].data(), lines[v].size(), bits + v * words_per_row,
+                       missing ? missing + v * words_per_row : nullptr, words_per_row, &outs[v]);
+    };
+    const int T = (int)std::min<int64_t>(r->n_threads, std::max<int64_t>(1, n / 16));
+    if (T <= 1) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(work, n * t / T, n * (t + 1) / T);
+        work(0, n / T);
+        for (auto &th : pool) th.join();
+    }
+    for (int64_t v = 0; v < n; ++v) {
+        if (outs[v].rc != PSB_OK) {
+            psb_set_error("%s", outs[v].err);
+            return outs[v].rc;
+        }
+        info[v] = outs[v].flags;
+        if ((outs[v].flags & 1) && any_missing) *any_missing = 1;
     }
     *n_read = n;
     return PSB_OK;

@@ -126,7 +126,7 @@ class VariantReader(object):
     rows).  The sample order of the bit rows is the phenotype index order (``p.index``), as
     the reference builds ``k`` (input.py:450)."""
 
-    def __init__(self, var_type, path, p, uncompressed=False):
+    def __init__(self, var_type, path, p, uncompressed=False, threads=1):
         import ctypes
         from . import _lib
         if var_type not in ('kmers', 'Rtab'):
@@ -141,6 +141,8 @@ class VariantReader(object):
         self._h = ctypes.c_void_p()
         _lib.check(self._lib.psb_reader_open(str(path).encode(), 0 if var_type == 'kmers' else 1,
                                              names, self.n_samples, ctypes.byref(self._h)))
+        if threads and threads > 1:      # pyseer's --cpu: parser threads
+            _lib.check(self._lib.psb_reader_set_threads(self._h, int(threads)))
 
     def close(self):
         if self._h:
@@ -315,18 +317,18 @@ class CachedVariantReader(object):
     k_vector = VariantReader.k_vector
 
 
-def open_variants(var_type, path, p, uncompressed=False, cache=None):
+def open_variants(var_type, path, p, uncompressed=False, cache=None, threads=1):
     """VariantReader, or -- with ``cache`` -- a CachedVariantReader when a valid packed cache of
     ``path`` for this sample order exists, else a VariantReader that writes the cache as it reads
     (``--bits-cache``)."""
     if cache is None:
-        return VariantReader(var_type, path, p, uncompressed)
+        return VariantReader(var_type, path, p, uncompressed, threads)
     samples = [str(s) for s in p.index]
     W = words_per_row(len(samples))
     if PackedCache.valid(cache, var_type, path, samples, W):
         sys.stderr.write('Reading packed variants from ' + str(cache) + '\n')
         return CachedVariantReader(cache, p)
-    rd = VariantReader(var_type, path, p, uncompressed)
+    rd = VariantReader(var_type, path, p, uncompressed, threads)
     writer = PackedCacheWriter(cache, var_type, path, samples, W)
     inner = rd.batches
 

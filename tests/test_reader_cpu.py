@@ -147,3 +147,39 @@ def test_packed_cache_with_missing(tmp_path):
     assert np.array_equal(np.concatenate([t.bits for t in a]), b[0].bits)
     ma = np.concatenate([t.missing if t.missing is not None else np.zeros_like(t.bits) for t in a])
     assert b[0].missing is not None and np.array_equal(ma, b[0].missing)
+
+
+def test_parser_threads_give_identical_rows(tmp_path):
+    """--cpu N: the lines of a batch are parsed by N threads; rows, names, flags do not change."""
+    rng = np.random.RandomState(4)
+    n, nv = 700, 900
+    samples = ['s%d' % i for i in range(n)]
+    p = pd.Series(np.zeros(n), index=samples)
+    f = tmp_path / 'k.txt'
+    with open(f, 'w') as fh:
+        for v in range(nv):
+            on = np.nonzero(rng.uniform(size=n) < rng.uniform(0.0, 0.9))[0] if v % 50 else []
+            extra = ' other:1' if v % 3 == 0 else ''
+            fh.write('K%d | %s%s\n' % (v, ' '.join('s%d:1' % i for i in on), extra))
+    outs = []
+    for threads in (1, 5):
+        rd = VariantReader('kmers', str(f), p, uncompressed=True, threads=threads)
+        err = io.StringIO()
+        with contextlib.redirect_stderr(err):
+            bs = list(rd.batches(256))
+        rd.close()
+        outs.append(([x for b in bs for x in b.names], np.concatenate([b.bits for b in bs]),
+                     err.getvalue()))
+    assert outs[0][0] == outs[1][0] == ['K%d' % v for v in range(nv)]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2] and outs[0][2].count('No observations of') == nv // 50
+    # malformed line: the error surfaces from a worker thread as from the serial path
+    g = tmp_path / 'bad.txt'
+    g.write_text(''.join('K%d | s1:1\n' % v for v in range(40)) + 'K40 s1:1\n')
+    from pyseer_b200._lib import PsbError
+    import pytest
+    for threads in (1, 4):
+        rd = VariantReader('kmers', str(g), p, uncompressed=True, threads=threads)
+        with pytest.raises(PsbError, match="without '\\|' separator"):
+            list(rd.batches(64))
+        rd.close()
