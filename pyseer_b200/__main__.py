@@ -4,9 +4,9 @@ loop running on the GPU.
 Same options, same TSV on stdout, same counters on stderr for the fixed-effects (SEER) and
 ``--lmm`` models with ``--kmers`` / ``--pres`` / ``--vcf`` (``--burden``) input.  What the reference does with a
 ``multiprocessing.Pool`` over variants (``__main__.py:517-593, 762-827``) is done here by
-submitting blocks of packed variants to the engine; ``--cpu`` is accepted and ignored.
-Whole-genome models (``--wg``) and lineage effects are not part of this path and are
-rejected with a message.
+submitting blocks of packed variants to the engine; ``--cpu`` selects the parser threads of
+the native k-mer / Rtab reader, ``--bits-cache`` keeps the packed rows for later runs.
+Whole-genome models (``--wg``) are not part of this path and are rejected with a message.
 """
 import argparse
 import operator

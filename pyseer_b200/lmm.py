@@ -1,7 +1,8 @@
 """LMM front-end with the reference's interface (pyseer/lmm.py).
 
-``initialise_lmm`` does the once-per-run host set-up (kinship normalisation, projection,
-eigendecomposition, h2 search: lmm.py:26-122, fastlmm/lmm_cov.py:88-103, 427-478);
+``initialise_lmm`` does the once-per-run set-up (kinship normalisation, projection, h2 search on
+the host; the O(N^3) eigendecomposition on the device for N >= 2048, ``psb_eigh``: lmm.py:26-122,
+fastlmm/lmm_cov.py:88-103, 427-478);
 ``fit_lmm`` / ``fit_lmm_block`` keep the reference's signatures and error behaviour but
 hand every per-variant computation to the GPU engine.
 """
