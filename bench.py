@@ -59,7 +59,7 @@ def parse_args():
                     help='0 = FP64 CUDA-core contraction, 3..8 = exact int8-slice tcgen05 path')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--e2e-chunks', type=int, default=8,
+    ap.add_argument('--e2e-chunks', type=int, default=16,
                     help='batches per e2e step (copy of batch i+1 overlaps the kernels of batch i)')
     ap.add_argument('--cpu-cores', type=int, default=0, help='0 = all available (max 64)')
     ap.add_argument('--check', type=int, default=2000,
