@@ -145,3 +145,26 @@ def test_burden_fixed_matches_unioned_rows():
     for f in ('af', 'prep', 'pvalue', 'beta', 'bse', 'extra'):
         assert np.array_equal(getattr(r, f), getattr(r2, f), equal_nan=True), f
     fm.close()
+
+
+def test_device_resident_records():
+    """psb_submit_burden_device: record rows already on the device (made by psb_synth_device, whose
+    host twin psb_synth_host gives the same rows) -> region rows equal the oracle union."""
+    from pyseer_b200 import lmm as plmm
+    from pyseer_b200.engine import synth_host
+    from oracle.input_oracle import burden_union
+    n = 777
+    rng = np.random.RandomState(9)
+    m = plmm.KinshipLMM(np.ones((n, 1)), rng.normal(size=(n, 1)), np.eye(n) + 0.01, precision=0)
+    eng = m.engine(m.findH2()['h2'])
+    n_rec = 1500
+    eng.synth_device(123, 40, n_rec, 0.001, 0.05, 0, None)
+    ptr, mptr, rows, wpr = eng.submitted_device()
+    assert rows == n_rec and mptr is None
+    offs, mem = _regions(rng, 400, n_rec)
+    eng.submit_burden_device(ptr, n_rec, wpr, offs, mem)
+    got, gm = eng.download_rows()
+    host = synth_host(123, 40, n_rec, n, 0.001, 0.05)
+    want, _ = burden_union(host, None, offs, mem)
+    assert gm is None and np.array_equal(got, want)
+    m.close()
