@@ -8,6 +8,13 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _host_eigh(monkeypatch):
+    # these tests only need an engine of the right sample count; keep the set-up off cuSOLVER
+    # (loading it costs up to a minute on a cold box)
+    monkeypatch.setenv('PYSEER_B200_EIGH', 'numpy')
+
+
 def _problem(n, seed=5):
     rng = np.random.RandomState(seed)
     G = (rng.uniform(size=(n, 2 * n)) < rng.uniform(0.05, 0.95, 2 * n)).astype(float)
