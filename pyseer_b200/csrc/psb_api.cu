@@ -318,10 +318,12 @@ int psb_counts(psb_ctx *c, int64_t out[4]) {
     int h[8];
     PSB_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     PSB_CUDA(cudaStreamSynchronize(c->stream));
-    out[0] = c->S;       // loaded
-    out[1] = h[1];       // pre-filtered (af + prefilter)
-    out[2] = h[0];       // tested
-    out[3] = h[0] - h[2];  // tested and passed the lrt filter
+    // h[5]: variants the LMM epilogue found to fail the (deferred) Welch pre-filter after they had
+    // been compacted as tested
+    out[0] = c->S;              // loaded
+    out[1] = h[1] + h[5];       // pre-filtered (af + prefilter)
+    out[2] = h[0] - h[5];       // tested
+    out[3] = h[0] - h[5] - h[2];  // tested and passed the lrt filter
     return PSB_OK;
 }
 

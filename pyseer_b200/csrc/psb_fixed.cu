@@ -1065,7 +1065,7 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
     else
         rc = psb_launch_bitsums(c);
     if (rc) return rc;
-    rc = psb_launch_prefilter(c, prm, /*lmm_rule=*/0);
+    rc = psb_launch_prefilter(c, prm, /*lmm_rule=*/0, /*defer_welch=*/0);
     if (rc) return rc;
     int h_cnt[8] = {0};
     PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, c->stream));

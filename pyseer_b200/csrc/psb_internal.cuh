@@ -85,6 +85,8 @@ struct psb_ctx {
     uint8_t *d_shift = nullptr;   // [Jq] per-column left shift of the integer epilogue (triangular form)
     bool tc_int_epi = false;      // triangular tiles are recombined and summed in int64
     int tc_special = 0;           // hi/lo column pairs carried by the special tile (0 = none)
+    bool tc_welch = false;        // the special tile also carries the Welch columns (yc, yc^2) after them
+    bool tc_welch_run = false;    // ... and this run takes the Welch sums from there (psb_run_lmm)
     void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B): box = 128 samples x all sliced rows
     void *tmap_Lq_half = nullptr; // same with half of the sliced rows per box (two-SM mode)
 
@@ -167,13 +169,14 @@ void psb_burden_release(psb_ctx *ctx);
 
 // psb_varstats.cu
 int psb_launch_bitsums(psb_ctx *ctx);
-int psb_launch_prefilter(psb_ctx *ctx, const psb_params *prm, int lmm_rule);
+int psb_launch_prefilter(psb_ctx *ctx, const psb_params *prm, int lmm_rule, int defer_welch);
 int psb_upload_welch_T(psb_ctx *ctx, const double *yc, const double *yc2);
 bool psb_bitstats_fits(psb_ctx *ctx);
 int psb_launch_bitstats(psb_ctx *ctx, int continuous);
 
 // psb_lmm_tc.cu
-int psb_lmm_tc_setup(psb_ctx *ctx, const double *h_v, const double *h_Q, int r, int ldq);
+int psb_lmm_tc_setup(psb_ctx *ctx, const double *h_v, const double *h_Q, int r, int ldq,
+                     const double *h_w1, const double *h_w2);
 int psb_lmm_tc_run(psb_ctx *ctx, int n_tested);
 int psb_tc_linear_setup(psb_ctx *ctx, const double *cols, int ncols, int ld);
 int psb_tc_run(psb_ctx *ctx, int n_tested, double *lin_out, int lin_ld);

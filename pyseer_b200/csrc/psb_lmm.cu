@@ -160,12 +160,26 @@ k_lmm_epilogue(const int *__restrict__ n_tested_dev, const int32_t *__restrict__
                double YKY, double dof1, double lrt_pvalue, double *__restrict__ pvalue,
                double *__restrict__ beta_out, double *__restrict__ bse_out,
                double *__restrict__ frac_out, uint32_t *__restrict__ flags,
-               int *__restrict__ counters) {
+               int *__restrict__ counters, int defer_welch, int col_w0, double T1, double T2,
+               double filter_pvalue, double *__restrict__ prep_out) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= *n_tested_dev) return;
     const double nan = __longlong_as_double(0x7ff8000000000000ll);
     int v = idx[t];
     uint32_t f = flags[v];
+    if (defer_welch) {
+        // pre_filtering (model.py:53-55) applied after the fact: the sums over carriers came out
+        // of the tensor pass, the sums over non-carriers follow from the totals.  lmm.py:172 rule.
+        const double *w = sums + (size_t)v * C + col_w0;
+        const double n1 = (double)(carriers[v] - nmissing[v]), n0 = (double)(N - carriers[v]);
+        const double prep = psb_welch_prep(w[0], w[1], T1 - w[0], T2 - w[1], n1, n0);
+        prep_out[v] = prep;
+        if (prep >= filter_pvalue || !isfinite(prep)) {
+            flags[v] = (f & ~PSB_F_TESTED) | PSB_F_PREFILTER_FAILED | PSB_F_PREFILTER;
+            atomicAdd(&counters[5], 1);
+            return;
+        }
+    }
     double p, beta, var_beta, frac;
     if (nmissing[v] > 0) {
         // NaN genotypes propagate through rotate()/nLLcore: every statistic is NaN
@@ -413,7 +427,8 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
     PSB_UPLOAD_FENCE();
     c->model = PSB_MODEL_LMM;
     if (precision > 0) {
-        rc = psb_lmm_tc_setup(c, cols.data(), cols.data() + c->Npad, r, c->Npad);
+        rc = psb_lmm_tc_setup(c, cols.data(), cols.data() + c->Npad, r, c->Npad,
+                              &cols[(size_t)c->col_w0 * c->Npad], &cols[(size_t)(c->col_w0 + 1) * c->Npad]);
         if (rc) {
             psb_free_model(c);
             return rc;
@@ -435,12 +450,20 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
     // With the tensor path carrying x'v and Q'x, the stats pass only needs popcounts and
     // (continuous phenotype) the two Welch sums; otherwise all masked column sums.
     const bool tc_sums = c->precision > 0 && c->tc_special > 0;
-    if (tc_sums && !c->d_miss && psb_bitstats_fits(c))
-        rc = psb_launch_bitstats(c, prm->continuous);
+    // Continuous phenotype with a pre-filter that does not gate (pyseer's default --filter-pvalue
+    // 1): the Welch sums ride the tensor pass (two more column pairs in its special tile) and the
+    // test moves into the epilogue, so the stats pass is popcounts only (HBM speed).  PSB_WELCH_TC=0
+    // keeps the CUDA-core sums.
+    static const bool welch_tc_ok = !(getenv("PSB_WELCH_TC") && atoi(getenv("PSB_WELCH_TC")) == 0);
+    const bool defer = welch_tc_ok && tc_sums && c->tc_welch && !c->d_miss && prm->continuous &&
+                       prm->filter_pvalue >= 1.0 && !(prm->options & PSB_OPT_NO_PREFILTER);
+    c->tc_welch_run = defer;
+    if (tc_sums && !c->d_miss && (defer || psb_bitstats_fits(c)))
+        rc = psb_launch_bitstats(c, defer ? 0 : prm->continuous);
     else
         rc = psb_launch_bitsums(c);
     if (rc) return rc;
-    rc = psb_launch_prefilter(c, prm, /*lmm_rule=*/1);
+    rc = psb_launch_prefilter(c, prm, /*lmm_rule=*/1, defer ? 1 : 0);
     if (rc) return rc;
     // The number of tested variants stays on the device (counters[0]): the whole run is queued
     // without a host round trip, so the next psb_submit copy overlaps these kernels.
@@ -466,7 +489,8 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
             c->d_counters, c->d_idx, c->d_a, tc_sums ? c->d_b : nullptr, tc_sums ? c->d_pp : nullptr,
             c->d_sums, c->C, c->col_b, c->col_q0, c->col_w0 - c->col_q0,
             c->N, c->d_carriers, c->d_missing, c->YKY, (double)(c->J - 1), prm->lrt_pvalue,
-            c->d_pvalue, c->d_beta, c->d_bse, c->d_extra, c->d_flags, c->d_counters);
+            c->d_pvalue, c->d_beta, c->d_bse, c->d_extra, c->d_flags, c->d_counters,
+            defer ? 1 : 0, c->col_w0, c->welch_T1, c->welch_T2, prm->filter_pvalue, c->d_prep);
         c->launches++;
         PSB_CUDA(cudaGetLastError());
     }

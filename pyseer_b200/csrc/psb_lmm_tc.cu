@@ -260,6 +260,8 @@ struct TcArgs {
     int n_special;            // hi/lo column pairs in the special tile (0 = no special tile)
     double *lin_out;          // raw pair sums x'u_p -> lin_out[variant id * lin_ld + p] (may be null)
     int lin_ld;
+    double *w_out;            // Welch sums over carriers (pairs n_special, n_special + 1 of the special
+    int w_ld;                 // tile: yc, yc^2) -> w_out[variant id * w_ld + {0, 1}] (null: not carried)
     int Wrow;                 // words per packed row in global memory
     int n_tested;             // upper bound used for the grid; the kernels read the real count:
     const int *n_tested_dev;  // device counter written by k_prefilter (no host round trip)
@@ -771,6 +773,8 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                                 int pair = (c0 + c) >> 1;
                                 if (pair == 0) bsum = val;
                                 else if (pair <= args.n_special - 1) pp = fma(val, val, pp);
+                                else if (args.w_out && row_own >= 0 && pair <= args.n_special + 1)
+                                    args.w_out[(size_t)row_own * args.w_ld + (pair - args.n_special)] = val;
                                 if (args.lin_out && row_own >= 0 && pair < args.n_special)
                                     args.lin_out[(size_t)row_own * args.lin_ld + pair] = val;
                             }
@@ -1012,7 +1016,8 @@ static void tc_special_column(const double *u, int N, int nsl, int Kpad, int8_t 
     }
 }
 
-int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, int ldq) {
+int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, int ldq,
+                     const double *h_w1, const double *h_w2) {
     const int nsl = c->precision;
     PSB_REQUIRE(nsl >= 3 && nsl <= 7, PSB_ERR_ARG, "int8 slice count must be in 3..7, got %d", nsl);
     const int N = c->N;
@@ -1038,6 +1043,8 @@ int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, in
     // the special tile holds 1 + r hi/lo pairs; with more than 15 covariate columns the
     // masked column sums stay on the CUDA-core path (psb_varstats.cu)
     c->tc_special = (1 + r) * 2 <= TC_JT ? 1 + r : 0;
+    // ... and, when two more pairs fit, the Welch columns (yc, yc^2) of pre_filtering (model.py:53-55)
+    c->tc_welch = c->tc_special > 0 && h_w1 && h_w2 && (1 + r + 2) * 2 <= TC_JT;
     c->jtiles = jt_reg + (c->tc_special ? 1 : 0);
     const int Jq = jt_reg * TC_JT;
     const int Jall = c->jtiles * TC_JT;
@@ -1076,6 +1083,10 @@ int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, in
         tc_special_column(h_v, N, nsl, c->Kpad, tile.data(), 0, sc.data());
         for (int e = 0; e < r; ++e)
             tc_special_column(h_Q + (size_t)e * ldq, N, nsl, c->Kpad, tile.data(), 2 + 2 * e, sc.data());
+        if (c->tc_welch) {
+            tc_special_column(h_w1, N, nsl, c->Kpad, tile.data(), 2 * (1 + r), sc.data());
+            tc_special_column(h_w2, N, nsl, c->Kpad, tile.data(), 2 * (2 + r), sc.data());
+        }
         PSB_CUDA(cudaMemcpyAsync(c->d_Lq + (size_t)jt_reg * tile_bytes, tile.data(), tile_bytes,
                                  cudaMemcpyHostToDevice, c->stream));
         PSB_CUDA(cudaMemcpyAsync(c->d_scale2 + Jq, sc.data(), TC_JT * sizeof(double),
@@ -1100,6 +1111,7 @@ int psb_tc_linear_setup(psb_ctx *c, const double *cols, int ncols, int ld) {
     const int N = c->N;
     c->n_slices = nsl;
     c->tc_special = ncols;
+    c->tc_welch = false;
     c->tc_tri = false;
     c->tc_int_epi = false;
     c->jtiles = 1;
@@ -1132,6 +1144,9 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.pp_out = lin_out ? nullptr : c->d_pp;
     a.lin_out = lin_out;
     a.lin_ld = lin_ld;
+    const bool welch = !lin_out && c->tc_welch && c->tc_welch_run;
+    a.w_out = welch ? c->d_sums + c->col_w0 : nullptr;
+    a.w_ld = c->C;
     a.n_special = c->tc_special;
     a.Wrow = c->Wrow;
     a.n_tested = n_tested;

@@ -14,6 +14,25 @@
 #define PSB_HD inline
 #endif
 
+PSB_HD double psb_t2_sf(double x, double dfd);
+
+// Welch t-test p-value, scipy.stats.ttest_ind(p[k==1], p[k==0], equal_var=False) (model.py:53-55),
+// from the sums over carriers (s1 = sum y, s1q = sum y^2, n1 samples) and non-carriers (s0, s0q, n0)
+PSB_HD double psb_welch_prep(double s1, double s1q, double s0, double s0q, double n1, double n0) {
+    const double nan = NAN;
+    if (n1 < 1.0 || n0 < 1.0) return nan;
+    double m1 = s1 / n1, m0 = s0 / n0;
+    double v1 = (s1q - s1 * m1) / (n1 - 1.0);   // nan when n1 == 1
+    double v0 = (s0q - s0 * m0) / (n0 - 1.0);
+    if (n1 < 2.0) v1 = nan;
+    if (n0 < 2.0) v0 = nan;
+    double vn1 = v1 / n1, vn0 = v0 / n0;
+    double df = (vn1 + vn0) * (vn1 + vn0) / (vn1 * vn1 / (n1 - 1.0) + vn0 * vn0 / (n0 - 1.0));
+    if (isnan(df)) df = 1.0;
+    double t = (m1 - m0) / sqrt(vn1 + vn0);
+    return psb_t2_sf(t * t, df);
+}
+
 // chi2.sf(x, 1) = erfc(sqrt(x / 2))
 PSB_HD double psb_chi2_sf1(double x) {
     if (isnan(x)) return x;

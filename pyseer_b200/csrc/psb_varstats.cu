@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256)
 k_prefilter(int64_t S, int N, const int32_t *__restrict__ carriers,
             const int32_t *__restrict__ nmissing, const int32_t *__restrict__ tab,
             const double *__restrict__ sums, int C, int col_w0, psb_params prm, int lmm_rule,
-            double *__restrict__ af_out, double *__restrict__ prep_out,
+            int defer_welch, double *__restrict__ af_out, double *__restrict__ prep_out,
             double *__restrict__ pvalue, double *__restrict__ beta, double *__restrict__ bse,
             double *__restrict__ extra, uint32_t *__restrict__ flags, int32_t *__restrict__ idx,
             int *__restrict__ counters) {
@@ -151,25 +151,14 @@ k_prefilter(int64_t S, int N, const int32_t *__restrict__ carriers,
     } else if (!(prm.min_af <= af && af <= prm.max_af) || missing > prm.max_missing) {
         f = PSB_F_AF_FILTER | PSB_F_PREFILTER;
     } else {
-        if (prm.continuous) {
+        if (prm.continuous && defer_welch) {
+            // the Welch sums come out of the tensor pass (special tile) and the test is applied in
+            // k_lmm_epilogue: every variant that passes the AF filter goes on
+            prep = nan;
+        } else if (prm.continuous) {
             // Welch t-test, scipy.stats.ttest_ind(p[k==1], p[k==0], equal_var=False)
             const double *s = sums + v * C + col_w0;
-            double n1 = (double)(carr - nm), n0 = (double)(N - carr);
-            if (n1 < 1.0 || n0 < 1.0) {
-                prep = nan;
-            } else {
-                double m1 = s[0] / n1, m0 = s[2] / n0;
-                double v1 = (s[1] - s[0] * m1) / (n1 - 1.0);   // nan when n1 == 1
-                double v0 = (s[3] - s[2] * m0) / (n0 - 1.0);
-                if (n1 < 2.0) v1 = nan;
-                if (n0 < 2.0) v0 = nan;
-                double vn1 = v1 / n1, vn0 = v0 / n0;
-                double df = (vn1 + vn0) * (vn1 + vn0) /
-                            (vn1 * vn1 / (n1 - 1.0) + vn0 * vn0 / (n0 - 1.0));
-                if (isnan(df)) df = 1.0;
-                double t = (m1 - m0) / sqrt(vn1 + vn0);
-                prep = psb_t2_sf(t * t, df);
-            }
+            prep = psb_welch_prep(s[0], s[1], s[2], s[3], (double)(carr - nm), (double)(N - carr));
         } else {
             int n11 = tab[v * 4 + 0], n10 = tab[v * 4 + 1], n01 = tab[v * 4 + 2], n00 = tab[v * 4 + 3];
             int le1 = (n11 <= 1) + (n10 <= 1) + (n01 <= 1) + (n00 <= 1);
@@ -188,7 +177,8 @@ k_prefilter(int64_t S, int N, const int32_t *__restrict__ carriers,
             }
         }
         bool fail = lmm_rule ? (prep >= prm.filter_pvalue) : (prep > prm.filter_pvalue);
-        if (fail || !isfinite(prep)) {
+        const bool deferred = prm.continuous && defer_welch;
+        if (!deferred && (fail || !isfinite(prep))) {
             f |= PSB_F_PREFILTER_FAILED | PSB_F_PREFILTER;
         } else {
             f |= PSB_F_TESTED;
@@ -206,12 +196,13 @@ k_prefilter(int64_t S, int N, const int32_t *__restrict__ carriers,
     flags[v] = f;
 }
 
-int psb_launch_prefilter(psb_ctx *c, const psb_params *prm, int lmm_rule) {
+int psb_launch_prefilter(psb_ctx *c, const psb_params *prm, int lmm_rule, int defer_welch) {
     PSB_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(int), c->stream));
     if (c->S == 0) return PSB_OK;
     int blocks = psb_div_up(c->S, 256);
     k_prefilter<<<blocks, 256, 0, c->stream>>>(c->S, c->N, c->d_carriers, c->d_missing, c->d_tab,
-                                               c->d_sums, c->C, c->col_w0, *prm, lmm_rule, c->d_af,
+                                               c->d_sums, c->C, c->col_w0, *prm, lmm_rule, defer_welch,
+                                               c->d_af,
                                                c->d_prep, c->d_pvalue, c->d_beta, c->d_bse,
                                                c->d_extra, c->d_flags, c->d_idx, c->d_counters);
     c->launches++;
