@@ -241,6 +241,20 @@ int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, ui
 int psb_reader_set_threads(psb_reader *reader, int32_t n_threads);
 int psb_reader_close(psb_reader *reader);
 
+/* ---- result formatting --------------------------------------------------------- */
+/* TSV lines of utils.format_output (utils.py:39-105) for a whole fetched result table, in the order
+ * and with the counters of the result loop of main() (__main__.py:547-568, 783-803): model 0 =
+ * fixed effects (af, filter-pvalue, lrt-pvalue, beta, beta-std-err, intercept, n_betas slopes,
+ * notes), 1 = LMM (..., beta-std-err, variant_h2, notes; inside every block of block_size variants
+ * the pre-filtered ones come first, lmm.py:158-226).  Numbers as '%.2E', empty when not finite or
+ * not set by the model; notes from the flag bits.  names / name_off: NUL-terminated variant names
+ * back to back and their offsets; cols: HOST pointers.  counts[0..2] += pre-filtered, tested,
+ * printed.  Host-only; covers runs without --print-samples / --lineage. */
+int psb_format_rows(int32_t model, int64_t n_variants, const char *names, const int64_t *name_off,
+                    const psb_results *cols, int32_t n_betas, int32_t block_size,
+                    int32_t print_filtered, char *out, int64_t out_cap, int64_t *out_len,
+                    int64_t counts[3]);
+
 /* ---- measurement ------------------------------------------------------------- */
 /* Work counters of the last psb_run_fixed: [0] Newton evaluations (passes over the samples)
  * summed over variants, [1] variants handed to the Firth kernel, [2] variants that failed

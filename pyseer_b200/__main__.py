@@ -22,7 +22,7 @@ from . import classes as var_obj
 from .engine import notes_from_flags
 from .input import (VariantReader, open_variants, VcfReader, hash_pattern, load_covariates, load_lineage,
                     load_phenotypes, load_structure)
-from .utils import format_output
+from .utils import format_output, format_table
 
 
 def get_options(argv=None):
@@ -265,6 +265,17 @@ def main(argv=None):
             r = fx.run_fixed_bits(model, batch.bits, batch.missing, o.filter_pvalue, o.lrt_pvalue,
                                   o.min_af, o.max_af, o.max_missing, lineage=o.lineage)
         flags = r.flags
+        if not (o.print_samples or o.lineage or patterns is not None) and \
+                os.environ.get('PYSEER_B200_NATIVE_FORMAT', '1') != '0':
+            # no per-variant extras asked for: the whole batch goes through the library's formatter
+            # (psb_format_rows: same lines, order and counters as the loop below, ~15x its speed)
+            text, n_pre, n_tested, n_printed = format_table(r, batch.names, model_name, o.block_size,
+                                                            o.print_filtered)
+            prefilter += n_pre
+            tested += n_tested
+            printed += n_printed
+            out.write(text.decode())
+            continue
         # the reference emits each block of --block_size variants as: filtered ones first
         # (LMM only, lmm.py:158-226), then the tested ones; fixed effects keep input order
         for b0 in range(0, batch.n, o.block_size):

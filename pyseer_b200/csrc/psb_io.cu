@@ -274,3 +274,107 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
     *n_read = n;
     return PSB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// TSV lines of a whole result table: utils.format_output (pyseer/utils.py:39-105) applied to the
+// Seer / LMM tuples the result loop of main() builds (__main__.py:547-568, 783-803), without the
+// per-variant Python objects.  Host-only code.
+// ---------------------------------------------------------------------------------------
+static inline char *fmt_num(char *p, double x) {        // '%.2E' % Decimal(x) if isfinite(x) else ''
+    if (isfinite(x)) p += snprintf(p, 32, "%.2E", x);
+    return p;
+}
+
+static const struct { uint32_t bit; const char *text; } k_notes[] = {
+    {PSB_F_AF_FILTER, "af-filter"},
+    {PSB_F_PREFILTER_FAILED, "pre-filtering-failed"},
+    {PSB_F_BAD_CHISQ, "bad-chisq"},
+    {PSB_F_HIGH_BSE, "high-bse"},
+    {PSB_F_PERFECT_SEP, "perfectly-separable-data"},
+    {PSB_F_MATRIX_INV, "matrix-inversion-error"},
+    {PSB_F_FIRTH_FAIL, "firth-fail"},
+    {PSB_F_MISSING_DATA, "missing-data-error"},
+    {PSB_F_LRT_FAILED, "lrt-filtering-failed"},
+};
+
+// model: 0 = fixed effects (Seer: ... bse, intercept, betas[n_betas]), 1 = LMM (... bse, variant_h2).
+// names: NUL-terminated variant names back to back, name_off[v] their offsets.  cols: HOST pointers
+// of the result table (psb_fetch).  Rows are visited in blocks of block_size; inside a block the LMM
+// model emits the pre-filtered variants first (lmm.py:158-226), fixed effects keep input order.
+// counts[0..2] += pre-filtered, tested, printed (__main__.py:549-565, 793-817).  Returns PSB_ERR_NOMEM
+// when out_cap is too small (nothing usable in `out` then).
+extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, const int64_t *name_off,
+                               const psb_results *cols, int32_t n_betas, int32_t block_size,
+                               int32_t print_filtered, char *out, int64_t out_cap, int64_t *out_len,
+                               int64_t counts[3]) {
+    PSB_REQUIRE(names && name_off && cols && out && out_len && counts, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(cols->af && cols->prep && cols->pvalue && cols->beta && cols->bse && cols->extra &&
+                    cols->flags && (n_betas == 0 || cols->betas),
+                PSB_ERR_ARG, "result columns missing");
+    PSB_REQUIRE(model == 0 || model == 1, PSB_ERR_ARG, "model must be 0 (seer) or 1 (lmm)");
+    if (block_size < 1) block_size = 1;
+    char *p = out;
+    char *const end = out + out_cap;
+    const int64_t per_row = 32 * (7 + (int64_t)n_betas) + 256;      // numbers, tabs, notes
+    for (int64_t b0 = 0; b0 < n; b0 += block_size) {
+        const int64_t b1 = std::min<int64_t>(n, b0 + block_size);
+        for (int pass = 0; pass < (model == 1 ? 2 : 1); ++pass) {
+            for (int64_t v = b0; v < b1; ++v) {
+                const uint32_t f = cols->flags[v];
+                const bool pre = (f & PSB_F_PREFILTER) != 0;
+                if (model == 1 && pre != (pass == 0)) continue;
+                if (pre) {
+                    counts[0]++;
+                    if (!print_filtered) continue;
+                } else {
+                    counts[1]++;
+                    if ((f & PSB_F_FILTER) && !print_filtered) continue;
+                }
+                const char *nm = names + name_off[v];
+                const size_t nl = strlen(nm);
+                if ((int64_t)(end - p) < (int64_t)nl + per_row) {
+                    psb_set_error("output buffer too small");
+                    return PSB_ERR_NOMEM;
+                }
+                memcpy(p, nm, nl);
+                p += nl;
+                *p++ = '\t';
+                p = fmt_num(p, cols->af[v]);
+                *p++ = '\t';
+                p = fmt_num(p, cols->prep[v]);
+                *p++ = '\t';
+                // fields the tuple leaves at NaN stay empty
+                const bool fitted = !pre && !(f & (PSB_F_FIRTH_FAIL | PSB_F_MISSING_DATA)) &&
+                                    !(model == 1 && (f & PSB_F_FILTER));
+                const bool has_p = !pre && !(model == 0 && (f & (PSB_F_FIRTH_FAIL | PSB_F_MISSING_DATA)));
+                if (has_p) p = fmt_num(p, cols->pvalue[v]);
+                *p++ = '\t';
+                if (fitted) p = fmt_num(p, cols->beta[v]);
+                *p++ = '\t';
+                if (fitted) p = fmt_num(p, cols->bse[v]);
+                *p++ = '\t';
+                if (fitted) p = fmt_num(p, cols->extra[v]);
+                if (model == 0 && fitted && n_betas > 0) {
+                    for (int c = 0; c < n_betas; ++c) {
+                        *p++ = '\t';
+                        p = fmt_num(p, cols->betas[v * n_betas + c]);
+                    }
+                }
+                *p++ = '\t';
+                bool first = true;
+                for (const auto &nt : k_notes)
+                    if (f & nt.bit) {
+                        if (!first) *p++ = ',';
+                        const size_t tl = strlen(nt.text);
+                        memcpy(p, nt.text, tl);
+                        p += tl;
+                        first = false;
+                    }
+                *p++ = '\n';
+                counts[2]++;
+            }
+        }
+    }
+    *out_len = (int64_t)(p - out);
+    return PSB_OK;
+}

@@ -30,3 +30,40 @@ def format_output(item, lineage_dict=None, model='seer', print_samples=False):
         fields.append(','.join(item.nkstrains))
     fields.append(','.join(item.notes))
     return '\t'.join(fields)
+
+
+def format_table(r, names, model='seer', block_size=1, print_filtered=False):
+    """TSV lines of a whole result table (``engine.Results``) through the library's native formatter
+    (``psb_format_rows``): what the result loop of ``main()`` prints with ``format_output`` when
+    neither samples nor lineages are asked for.  Returns ``(text_bytes, prefiltered, tested,
+    printed)``."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    n = len(names)
+    blob = ('\0'.join(names) + '\0').encode()
+    lens = np.fromiter((len(s.encode()) + 1 for s in names), dtype=np.int64, count=n)
+    off = np.zeros(n, dtype=np.int64)
+    if n > 1:
+        np.cumsum(lens[:-1], out=off[1:])
+    cols = _lib.PsbResults()
+    keep = []
+    for f, dt in (('af', np.float64), ('prep', np.float64), ('pvalue', np.float64), ('beta', np.float64),
+                  ('bse', np.float64), ('extra', np.float64), ('flags', np.uint32)):
+        a = np.ascontiguousarray(getattr(r, f), dtype=dt)
+        keep.append(a)
+        setattr(cols, f, a.ctypes.data_as(ctypes.c_void_p))
+    nb = 0
+    if model != 'lmm' and r.betas is not None and r.betas.ndim == 2 and r.betas.shape[1] > 0:
+        b = np.ascontiguousarray(r.betas, dtype=np.float64)
+        keep.append(b)
+        cols.betas = b.ctypes.data_as(ctypes.c_void_p)
+        nb = b.shape[1]
+    cap = int(len(blob) + n * (32 * (7 + nb) + 256) + 64)
+    out = ctypes.create_string_buffer(cap)
+    out_len = ctypes.c_int64(0)
+    counts = (ctypes.c_int64 * 3)(0, 0, 0)
+    _lib.check(lib.psb_format_rows(1 if model == 'lmm' else 0, n, blob, off.ctypes.data_as(ctypes.c_void_p),
+                                   ctypes.byref(cols), nb, int(block_size), int(bool(print_filtered)),
+                                   ctypes.addressof(out), cap, ctypes.byref(out_len), counts))
+    return out.raw[:out_len.value], counts[0], counts[1], counts[2]

@@ -1,0 +1,121 @@
+"""The native TSV formatter (psb_format_rows) against utils.format_output applied row by row as the
+CLI's result loop does, and against lines produced by the reference's own format_output
+(tests/golden/host_goldens.json, oracle/gen_golden_host.py)."""
+import json
+import os
+
+import numpy as np
+
+from conftest import GOLDEN
+from pyseer_b200 import _lib
+from pyseer_b200 import classes as var_obj
+from pyseer_b200.engine import Results, notes_from_flags
+from pyseer_b200.model import seer_from_row
+from pyseer_b200.utils import format_output, format_table
+
+
+def _table(rng, n, nb):
+    r = Results()
+    vals = lambda: np.where(rng.uniform(size=n) < 0.1, np.nan, rng.normal(size=n) * 10.0 ** rng.randint(-250, 6, n))
+    r.af, r.prep, r.pvalue = np.abs(vals()), np.abs(vals()), np.abs(vals())
+    r.beta, r.bse, r.extra = vals(), np.abs(vals()), vals()
+    r.betas = rng.normal(size=(n, nb)) * 10.0 ** rng.randint(-20, 3, (n, nb))
+    r.carriers = r.missing = np.zeros(n, dtype=np.int32)
+    kinds = rng.randint(0, 7, n)
+    f = np.zeros(n, dtype=np.uint32)
+    f[kinds == 0] = _lib.F_AF_FILTER | _lib.F_PREFILTER
+    f[kinds == 1] = _lib.F_PREFILTER_FAILED | _lib.F_PREFILTER
+    f[kinds == 2] = _lib.F_LRT_FAILED | _lib.F_FILTER | _lib.F_TESTED
+    f[kinds == 3] = _lib.F_BAD_CHISQ | _lib.F_FIRTH_FAIL | _lib.F_FILTER | _lib.F_TESTED
+    f[kinds == 4] = _lib.F_TESTED
+    f[kinds == 5] = _lib.F_TESTED | _lib.F_HIGH_BSE | _lib.F_FIRTH_USED
+    f[kinds == 6] = _lib.F_MISSING_DATA | _lib.F_FILTER | _lib.F_TESTED
+    r.flags = f
+    return r
+
+
+def _python_lines(r, names, model, block_size, print_filtered):
+    """The CLI's result loop (pyseer_b200/__main__.py), one tuple and one format_output per row."""
+    nan = np.nan
+    out, pre, tested, printed = [], 0, 0, 0
+    n = len(names)
+    for b0 in range(0, n, block_size):
+        idx = list(range(b0, min(b0 + block_size, n)))
+        if model == 'lmm':
+            idx = [j for j in idx if r.flags[j] & _lib.F_PREFILTER] + \
+                  [j for j in idx if not (r.flags[j] & _lib.F_PREFILTER)]
+        for j in idx:
+            f = int(r.flags[j])
+            if f & _lib.F_PREFILTER:
+                pre += 1
+                if not print_filtered:
+                    continue
+            else:
+                tested += 1
+                if (f & _lib.F_FILTER) and not print_filtered:
+                    continue
+            notes = notes_from_flags(f)
+            if model == 'lmm':
+                if f & _lib.F_PREFILTER:
+                    item = var_obj.LMM(names[j], None, r.af[j], r.prep[j], nan, nan, nan, nan, None, [], [],
+                                       notes, True, False)
+                elif f & _lib.F_FILTER:
+                    item = var_obj.LMM(names[j], None, r.af[j], r.prep[j], r.pvalue[j], nan, nan, nan, None,
+                                       [], [], notes, False, True)
+                else:
+                    item = var_obj.LMM(names[j], None, r.af[j], r.prep[j], r.pvalue[j], r.beta[j], r.bse[j],
+                                       r.extra[j], None, [], [], notes, False, False)
+            else:
+                item = seer_from_row(r, j, names[j], None, r.af[j], [], [])
+            printed += 1
+            out.append(format_output(item, None, model, False))
+    return out, pre, tested, printed
+
+
+def _same(a, b):
+    """Equal lines; the notes field (a set in the reference) is compared as a set."""
+    fa, fb = a.split('\t'), b.split('\t')
+    return fa[:-1] == fb[:-1] and set(fa[-1].split(',')) == set(fb[-1].split(','))
+
+
+def test_native_formatter_matches_result_loop():
+    rng = np.random.RandomState(3)
+    for model, nb in (('seer', 11), ('seer', 0), ('lmm', 0)):
+        for block_size, pf in ((1, False), (7, True), (3000, False), (50, True)):
+            n = 503
+            r = _table(rng, n, nb)
+            names = ['K%d_%s' % (i, 'ACGT' * (i % 9)) for i in range(n)]
+            want, pre, tested, printed = _python_lines(r, names, model, block_size, pf)
+            text, c0, c1, c2 = format_table(r, names, model, block_size, pf)
+            got = text.decode().split('\n')
+            assert got[-1] == '' and len(got) - 1 == len(want) == printed
+            assert (c0, c1, c2) == (pre, tested, printed)
+            for a, b in zip(got, want):
+                assert _same(a, b), (model, nb, a, b)
+
+
+def test_native_formatter_matches_reference_lines():
+    """Numbers, blanks and field order against pyseer.utils.format_output itself."""
+    with open(os.path.join(GOLDEN, 'host_goldens.json')) as fh:
+        cases = json.load(fh)['format_output']
+    bit = {s: b for b, s in _lib.NOTE_BITS}
+    num = lambda x: float(x) if isinstance(x, str) else (np.nan if x is None else x)
+    for model, key, extra in (('seer', 'seer|nolin|nosamples', 'intercept'), ('lmm', 'lmm|nolin|nosamples', 'frac_h2')):
+        for case in cases:
+            f = case['fields']
+            r = Results()
+            for col, src in (('af', 'af'), ('prep', 'prep'), ('pvalue', 'pvalue'), ('beta', 'kbeta'),
+                             ('bse', 'bse'), ('extra', extra)):
+                setattr(r, col, np.array([num(f[src])]))
+            r.betas = np.array([[num(b) for b in f['betas']]], dtype=float).reshape(1, -1)
+            flags = _lib.F_TESTED
+            for s in f['notes']:
+                flags |= bit[s]
+            flags &= ~_lib.F_FIRTH_FAIL          # that note blanks the row in the Seer tuple
+            r.flags = np.array([flags], dtype=np.uint32)
+            want = case['lines'][key]
+            if 'firth-fail' in f['notes']:
+                continue
+            text, _, _, printed = format_table(r, [f['kmer']], model, 1, True)
+            assert printed == 1
+            assert _same(text.decode().rstrip('\n'), want), (model, f['kmer'])
