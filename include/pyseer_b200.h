@@ -224,7 +224,8 @@ int psb_kinship_fetch(psb_ctx *ctx, double *K_out);
 
 /* ---- native variant-file reader ------------------------------------------------- */
 /* Replaces the per-line Python of input.read_variant (input.py:301-454) for the k-mer text
- * format (`name | s1:1 s2:1 ...`, var_type 0) and Rtab (var_type 1); plain or gzip files.
+ * format (`name | s1:1 s2:1 ...`, var_type 0), Rtab (var_type 1) and VCF (var_type 2, below); plain or
+ * gzip files.
  * sample_names: the phenotype index order (bit i of a row = sample_names[i]).
  * psb_reader_next fills up to max_variants packed rows (bits, and missing when non-NULL; both
  * max_variants x words_per_row, zeroed by the call), the NUL-terminated names back to back in
@@ -237,6 +238,15 @@ int psb_reader_open(const char *path, int32_t var_type, const char *const *sampl
 int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, uint32_t *missing,
                     int32_t words_per_row, char *names, int64_t names_cap, int64_t *name_off,
                     int32_t *info, int64_t *n_read, int32_t *any_missing);
+/* var_type 2 = VCF text (plain or gzip), input.read_vcf_var (input.py:457-502), dominant encoding:
+ * a sample carries the variant when a haplotype of its GT is a non-reference allele, '.' haplotypes
+ * mark it missing unless a called one follows; names are CHROM_POS_REF[_ALT]; info bit 2 (value 4):
+ * record with more than one ALT allele, bit 3 (value 8): FILTER neither empty nor PASS -- both are
+ * skipped by the reference and come back as empty rows.  psb_reader_vcf_info returns contig, 1-based
+ * position and REF length of the records of the last psb_reader_next (burden-region lookup,
+ * input.py:395-407). */
+int psb_reader_vcf_info(psb_reader *reader, int64_t n_records, char *contigs, int64_t contigs_cap,
+                        int64_t *contig_off, int64_t *pos, int32_t *ref_len);
 /* parser threads for psb_reader_next (pyseer's --cpu): lines are read serially, parsed in parallel */
 int psb_reader_set_threads(psb_reader *reader, int32_t n_threads);
 int psb_reader_close(psb_reader *reader);

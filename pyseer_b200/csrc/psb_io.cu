@@ -20,7 +20,7 @@
 
 struct psb_reader {
     gzFile fh = nullptr;
-    int var_type = 0;                       // 0 = k-mers, 1 = Rtab
+    int var_type = 0;                       // 0 = k-mers, 1 = Rtab, 2 = VCF
     int n_samples = 0;
     std::vector<std::string> names;         // owns the keys of `index`
     std::unordered_map<std::string_view, int> index;
@@ -31,6 +31,11 @@ struct psb_reader {
     std::string line;
     std::vector<std::string> lines;         // lines of the batch being parsed
     int n_threads = 1;
+    // VCF: name under construction, and contig / position / REF length of the records of the last batch
+    std::string vcf_name;
+    std::vector<std::string> vcf_contig;
+    std::vector<int64_t> vcf_pos;
+    std::vector<int32_t> vcf_reflen;
 };
 
 static bool reader_fill(psb_reader *r) {
@@ -66,7 +71,7 @@ static bool reader_getline(psb_reader *r) {
 extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *const *sample_names,
                                int32_t n_samples, psb_reader **out) {
     PSB_REQUIRE(path && sample_names && out, PSB_ERR_ARG, "NULL argument");
-    PSB_REQUIRE(var_type == 0 || var_type == 1, PSB_ERR_ARG, "var_type must be 0 (k-mers) or 1 (Rtab)");
+    PSB_REQUIRE(var_type >= 0 && var_type <= 2, PSB_ERR_ARG, "var_type must be 0 (k-mers), 1 (Rtab) or 2 (VCF)");
     PSB_REQUIRE(n_samples > 0, PSB_ERR_ARG, "no samples");
     *out = nullptr;
     gzFile fh = gzopen(path, "rb");
@@ -104,6 +109,36 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
                 ++field;
             }
             i = j;
+        }
+    }
+    if (var_type == 2) {
+        // skip the meta lines; the #CHROM line names the sample columns (9 fixed fields first)
+        bool found = false;
+        while (reader_getline(r)) {
+            const std::string &h = r->line;
+            if (h.rfind("#CHROM", 0) != 0) continue;
+            size_t i = 0, n = h.size();
+            while (n > 0 && (h[n - 1] == '\r' || h[n - 1] == '\n')) --n;
+            int field = 0;
+            while (i <= n) {
+                size_t j = i;
+                while (j < n && h[j] != '\t') ++j;
+                if (field >= 9) {
+                    auto it = r->index.find(std::string_view(h.data() + i, j - i));
+                    r->rtab_col.push_back(it == r->index.end() ? -1 : it->second);
+                }
+                ++field;
+                if (j >= n) break;
+                i = j + 1;
+            }
+            found = true;
+            break;
+        }
+        if (!found) {
+            gzclose(fh);
+            delete r;
+            psb_set_error("%s: no #CHROM header line found; is this a VCF file?", path);
+            return PSB_ERR_ARG;
         }
     }
     *out = r;
@@ -158,6 +193,97 @@ static void parse_line(const psb_reader *r, const char *L, size_t len, uint32_t 
                 }
             }
             k = e;
+        }
+    } else if (r->var_type == 2) {
+        // VCF record, input.read_vcf_var (input.py:457-502), dominant encoding.  Fields: CHROM POS ID
+        // REF ALT QUAL FILTER INFO FORMAT samples...  flags bit 2: more than one ALT allele, bit 3:
+        // FILTER neither empty nor PASS -- both skipped by the reference (the row stays empty).
+        const char *fld[9];
+        size_t fl[9];
+        size_t k = 0;
+        for (int c = 0; c < 9; ++c) {
+            size_t e = k;
+            while (e < len && L[e] != '\t') ++e;
+            fld[c] = L + k;
+            fl[c] = e - k;
+            LINE_REQUIRE(e < len || c == 8, PSB_ERR_ARG, "VCF record with fewer than 9 fields");
+            k = e + 1;
+        }
+        // ALT: '.' = none; more than one allele -> skipped
+        if (memchr(fld[4], ',', fl[4])) flags |= 4;
+        // FILTER: '.' or empty passes; otherwise one of the ';'-separated names must be PASS
+        if (!(fl[6] == 0 || (fl[6] == 1 && fld[6][0] == '.'))) {
+            bool pass = false;
+            size_t a = 0;
+            while (a <= fl[6]) {
+                size_t b = a;
+                while (b < fl[6] && fld[6][b] != ';') ++b;
+                if (b - a == 4 && memcmp(fld[6] + a, "PASS", 4) == 0) pass = true;
+                a = b + 1;
+            }
+            if (!pass && !(flags & 4)) flags |= 8;
+        }
+        if (!(flags & 12)) {
+            // position of GT among the ':'-separated FORMAT keys (-1: every genotype is missing)
+            int gi = -1, key = 0;
+            for (size_t a = 0; a <= fl[8];) {
+                size_t b = a;
+                while (b < fl[8] && fld[8][b] != ':') ++b;
+                if (b - a == 2 && fld[8][a] == 'G' && fld[8][a + 1] == 'T') { gi = key; break; }
+                ++key;
+                a = b + 1;
+            }
+            size_t col = 0;
+            const size_t ncol = r->rtab_col.size();
+            while (k <= len && col < ncol) {
+                size_t e = k;
+                while (e < len && L[e] != '\t') ++e;
+                const int s = r->rtab_col[col];
+                if (s >= 0) {
+                    int st = 0;                       // 0 absent, 1 carrier, 2 missing
+                    if (gi < 0) {
+                        st = 2;
+                    } else {
+                        // the gi-th ':' field of the cell
+                        size_t a = k;
+                        for (int q = 0; q < gi && a < e; ++q) {
+                            while (a < e && L[a] != ':') ++a;
+                            if (a < e) ++a;
+                        }
+                        size_t b = a;
+                        while (b < e && L[b] != ':') ++b;
+                        // haplotypes separated by '/' or '|'
+                        size_t h0 = a;
+                        for (;;) {
+                            size_t h1 = h0;
+                            while (h1 < b && L[h1] != '/' && L[h1] != '|') ++h1;
+                            const size_t hl = h1 - h0;
+                            if (hl == 1 && L[h0] == '.') {
+                                if (st == 0) st = 2;
+                            } else if (!(hl == 1 && L[h0] == '0')) {
+                                st = 1;
+                                break;
+                            } else if (st == 2) {
+                                st = 0;
+                            }
+                            if (h1 >= b) break;
+                            h0 = h1 + 1;
+                        }
+                    }
+                    if (st == 1) { row[s >> 5] |= 1u << (s & 31); seen = true; }
+                    if (st == 2) {
+                        flags |= 1;
+                        seen = true;
+                        if (mrow) mrow[s >> 5] |= 1u << (s & 31);
+                    }
+                }
+                ++col;
+                k = e + 1;
+            }
+            LINE_REQUIRE(!(flags & 1) || mrow, PSB_ERR_ARG,
+                         "record has missing genotypes but no missing buffer was given");
+        } else {
+            seen = true;          // no "No observations" message for skipped records
         }
     } else {
         size_t i = 0;
@@ -218,6 +344,9 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
     *n_read = 0;
     if (any_missing) *any_missing = 0;
     // ---- serial: lines of the batch and their names -----------------------------------
+    r->vcf_contig.clear();
+    r->vcf_pos.clear();
+    r->vcf_reflen.clear();
     std::vector<std::string> &lines = r->lines;
     int64_t n = 0, used = 0;
     while (n < max_variants) {
@@ -234,12 +363,40 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
             while (i < len && (L[i] == ' ' || L[i] == '\t')) ++i;
             j = i;
             while (j < len && L[j] != ' ' && L[j] != '\t') ++j;
+        } else if (r->var_type == 2) {
+            // '_'.join([contig, pos, ref] + alts)  (input.py:471-472); also record contig / pos / ref
+            // length for the burden-region lookup (psb_reader_vcf_info)
+            if (L[0] == '#') continue;
+            size_t t[5] = {0, 0, 0, 0, 0}, e[5] = {0, 0, 0, 0, 0}, k = 0;
+            bool ok = true;
+            for (int c = 0; c < 5; ++c) {
+                size_t q = k;
+                while (q < len && L[q] != '\t') ++q;
+                t[c] = k;
+                e[c] = q;
+                if (q >= len) { ok = false; break; }
+                k = q + 1;
+            }
+            PSB_REQUIRE(ok, PSB_ERR_ARG, "VCF record with fewer than 9 fields");
+            r->vcf_name.assign(L.data() + t[0], e[0] - t[0]);
+            r->vcf_name.push_back('_');
+            r->vcf_name.append(L.data() + t[1], e[1] - t[1]);
+            r->vcf_name.push_back('_');
+            r->vcf_name.append(L.data() + t[3], e[3] - t[3]);
+            if (!(e[4] - t[4] == 1 && L[t[4]] == '.')) {
+                r->vcf_name.push_back('_');
+                for (size_t q = t[4]; q < e[4]; ++q) r->vcf_name.push_back(L[q] == ',' ? '_' : L[q]);
+            }
+            r->vcf_contig.emplace_back(L.data() + t[0], e[0] - t[0]);
+            r->vcf_pos.push_back(strtoll(L.c_str() + t[1], nullptr, 10));
+            r->vcf_reflen.push_back((int32_t)(e[3] - t[3]));
         } else {                     // name = first tab-delimited field
             while (j < len && L[j] != '\t') ++j;
         }
-        const size_t name_len = j - i;
+        const char *name_ptr = r->var_type == 2 ? r->vcf_name.data() : L.data() + i;
+        const size_t name_len = r->var_type == 2 ? r->vcf_name.size() : j - i;
         PSB_REQUIRE((int64_t)name_len + 1 <= names_cap - used, PSB_ERR_NOMEM, "name buffer too small");
-        memcpy(names + used, L.data() + i, name_len);
+        memcpy(names + used, name_ptr, name_len);
         names[used + name_len] = '\0';
         name_off[n] = used;
         used += (int64_t)name_len + 1;
@@ -376,5 +533,29 @@ extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, cons
         }
     }
     *out_len = (int64_t)(p - out);
+    return PSB_OK;
+}
+
+
+// VCF only: contig (NUL-terminated, back to back in `contigs` with contig_off[v] offsets), 1-based
+// position and REF length of the records returned by the last psb_reader_next -- what the burden
+// branch needs to decide which records a region fetches (input.py:395-407).
+extern "C" int psb_reader_vcf_info(psb_reader *r, int64_t n, char *contigs, int64_t contigs_cap,
+                                   int64_t *contig_off, int64_t *pos, int32_t *ref_len) {
+    PSB_REQUIRE(r && contigs && contig_off && pos && ref_len, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(r->var_type == 2, PSB_ERR_STATE, "not a VCF reader");
+    PSB_REQUIRE(n == (int64_t)r->vcf_contig.size(), PSB_ERR_ARG, "n = %lld, last batch had %zu records",
+                (long long)n, r->vcf_contig.size());
+    int64_t used = 0;
+    for (int64_t v = 0; v < n; ++v) {
+        const std::string &c = r->vcf_contig[v];
+        PSB_REQUIRE(used + (int64_t)c.size() + 1 <= contigs_cap, PSB_ERR_NOMEM, "contig buffer too small");
+        memcpy(contigs + used, c.data(), c.size());
+        contigs[used + c.size()] = '\0';
+        contig_off[v] = used;
+        used += (int64_t)c.size() + 1;
+        pos[v] = r->vcf_pos[v];
+        ref_len[v] = r->vcf_reflen[v];
+    }
     return PSB_OK;
 }

@@ -352,7 +352,8 @@ def open_variants(var_type, path, p, uncompressed=False, cache=None, threads=1):
 
 
 class VcfReader(object):
-    """VCF (and burden-region) input without pysam: plain or gzip text VCF, dominant encoding.
+    """VCF (and burden-region) input without pysam: plain or gzip text VCF, dominant encoding, parsed
+    by the library's native reader (``psb_reader_*`` with var_type 2).
 
     Follows input.read_vcf_var (input.py:457-502): a sample carries the variant if any haplotype
     of its GT is a non-reference allele; '.' haplotypes mark the genotype missing unless a
@@ -360,26 +361,27 @@ class VcfReader(object):
     nor PASS are skipped (they still count as loaded, and end up AF-filtered like the
     reference's ``None`` sentinel).  With ``burden_file`` each row is the OR over every record
     overlapping the region(s) of one line ``name contig:start-end[,contig:start-end...]``
-    (input.py:395-411, load_burden :250-266); the whole VCF is held in memory for that.
-    Produces the same VariantBatch objects as VariantReader."""
+    (input.py:395-411, load_burden :250-266); the packed rows of the whole VCF are held in memory
+    for that.  Produces the same VariantBatch objects as VariantReader."""
 
-    def __init__(self, path, p, burden_file=None, reducer=None):
-        import gzip
+    def __init__(self, path, p, burden_file=None, reducer=None, threads=1):
+        import ctypes
+        from . import _lib
         self.samples = [str(s) for s in p.index]
-        self.index = {s: i for i, s in enumerate(self.samples)}
         self.n_samples = len(self.samples)
         self.W = words_per_row(self.n_samples)
-        with open(path, 'rb') as fh:
-            magic = fh.read(2)
-        self.fh = gzip.open(path, 'rt') if magic == b'\x1f\x8b' else open(path, 'rt')
-        self.cols = None
-        for line in self.fh:
-            if line.startswith('#CHROM'):
-                names = line.rstrip('\n').split('\t')[9:]
-                self.cols = [(9 + j, self.index[s]) for j, s in enumerate(names) if s in self.index]
-                break
-        if self.cols is None:
-            raise ValueError('no #CHROM header line found; is this a VCF file?')
+        self._lib = _lib.load()
+        names = (ctypes.c_char_p * self.n_samples)(*[s.encode() for s in self.samples])
+        self._h = ctypes.c_void_p()
+        try:
+            _lib.check(self._lib.psb_reader_open(str(path).encode(), 2, names, self.n_samples,
+                                                 ctypes.byref(self._h)))
+        except _lib.PsbError as e:
+            if 'no #CHROM header' in str(e):
+                raise ValueError('no #CHROM header line found; is this a VCF file?')
+            raise
+        if threads and threads > 1:
+            _lib.check(self._lib.psb_reader_set_threads(self._h, int(threads)))
         self.regions = None
         # burden regions: `reducer(vbits, vmiss, offsets, members) -> (bits, missing)` forms the
         # per-region union of record rows on the device (Engine.submit_burden + download_rows, as
@@ -394,77 +396,62 @@ class VcfReader(object):
                 for line in rf:
                     name, spec = line.rstrip().split()
                     self.regions.append((name, spec.split(',')))
-            # every record is parsed once into a packed row (read_vcf_var on an empty dictionary);
-            # skipped records (multi-allelic, filtered) never touch a region's dictionary
-            contig, start, end, states = [], [], [], []
-            for line in self.fh:
-                if not line.strip():
-                    continue
-                f = self._split(line)
-                state = np.zeros(self.n_samples, dtype=np.int8)
-                if self._apply(f, state) is None:
-                    continue
-                contig.append(f[0])
-                start.append(int(f[1]) - 1)
-                end.append(int(f[1]) - 1 + len(f[3]))
-                states.append(state)
+            # every record is parsed once into a packed row (read_vcf_var on an empty dictionary)
+            contig, pos, reflen, skip, bits, miss = [], [], [], [], [], []
+            for nm, b, m, info, cg, ps, rl in self._native(8192):
+                contig.extend(cg)
+                pos.append(ps)
+                reflen.append(rl)
+                skip.append(info & 12)
+                bits.append(b)
+                miss.append(m)
+            cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dtype=dt)
             self.rec_contig = np.array(contig, dtype=object)
-            self.rec_start = np.array(start, dtype=np.int64)
-            self.rec_end = np.array(end, dtype=np.int64)
-            if states:
-                packed = self._pack([''] * len(states), states)
-                self.rec_bits, self.rec_miss = packed.bits, packed.missing
-            else:
-                self.rec_bits, self.rec_miss = np.zeros((0, self.W), dtype=np.uint32), None
+            self.rec_start = cat(pos, np.int64) - 1
+            self.rec_end = self.rec_start + cat(reflen, np.int32)
+            self.rec_skip = cat(skip, np.int32)
+            self.rec_pos = cat(pos, np.int64)
+            self.rec_bits = np.concatenate(bits) if bits else np.zeros((0, self.W), dtype=np.uint32)
+            self.rec_miss = np.concatenate(miss) if bits else None
+            if self.rec_miss is not None and not self.rec_miss.any():
+                self.rec_miss = None
 
     def close(self):
-        self.fh.close()
+        if self._h:
+            self._lib.psb_reader_close(self._h)
+            self._h = None
 
-    @staticmethod
-    def _split(line):
-        f = line.rstrip('\n').split('\t')
-        return f
-
-    def _apply(self, f, state):
-        """read_vcf_var on one record: updates the per-sample state in place
-        (0 = not in d, 1 = present, 2 = NaN); returns the variant name or None if skipped."""
-        contig, pos, ref, alt, filt = f[0], f[1], f[3], f[4], f[6]
-        alts = [] if alt == '.' else alt.split(',')
-        name = '_'.join([contig, pos, ref] + alts)
-        if len(alts) > 1:
-            sys.stderr.write('Multiple alleles at %s_%s. Skipping\n' % (contig, pos))
-            return None
-        filters = [] if filt in ('.', '') else filt.split(';')
-        if len(filters) > 0 and 'PASS' not in filters:
-            return None
-        fmt = f[8].split(':')
-        gi = fmt.index('GT') if 'GT' in fmt else -1
-        for col, s in self.cols:
-            if gi < 0:
-                haps = [None]
-            else:
-                gt = f[col].split(':')[gi]
-                haps = gt.replace('|', '/').split('/')
-            st = state[s]
-            for h in haps:
-                if h is None or h == '.':
-                    if st == 0:
-                        st = 2
-                elif h != '0':
-                    st = 1
-                    break
-                elif st == 2:
-                    st = 0
-            state[s] = st
-        return name
-
-    def _rows(self):
-        for line in self.fh:
-            if not line.strip():
-                continue
-            state = np.zeros(self.n_samples, dtype=np.int8)
-            name = self._apply(self._split(line), state)
-            yield name, state
+    def _native(self, size):
+        """Batches of parsed records: names, carrier rows, missing rows, info flags (1 missing, 2 no
+        observation, 4 multi-allelic, 8 filtered), contigs, 1-based positions, REF lengths."""
+        import ctypes
+        from . import _lib
+        cap = max(1 << 20, 512 * size)
+        while True:
+            bits = np.empty((size, self.W), dtype=np.uint32)
+            miss = np.empty((size, self.W), dtype=np.uint32)
+            names = ctypes.create_string_buffer(cap)
+            off = np.empty(size, dtype=np.int64)
+            info = np.empty(size, dtype=np.int32)
+            n = ctypes.c_int64(0)
+            anym = ctypes.c_int32(0)
+            _lib.check(self._lib.psb_reader_next(
+                self._h, size, bits.ctypes.data, miss.ctypes.data, self.W, ctypes.addressof(names), cap,
+                off.ctypes.data, info.ctypes.data, ctypes.byref(n), ctypes.byref(anym)))
+            n = n.value
+            if n == 0:
+                return
+            raw = names.raw
+            nm = [raw[off[i]:raw.index(b'\0', off[i])].decode() for i in range(n)]
+            cbuf = ctypes.create_string_buffer(cap)
+            coff = np.empty(n, dtype=np.int64)
+            pos = np.empty(n, dtype=np.int64)
+            rl = np.empty(n, dtype=np.int32)
+            _lib.check(self._lib.psb_reader_vcf_info(self._h, n, ctypes.addressof(cbuf), cap,
+                                                     coff.ctypes.data, pos.ctypes.data, rl.ctypes.data))
+            craw = cbuf.raw
+            cg = [craw[coff[i]:craw.index(b'\0', coff[i])].decode() for i in range(n)]
+            yield nm, bits[:n], miss[:n], info[:n], cg, pos, rl
 
     def _region_members(self, specs):
         """Record indices a burden line fetches, in fetch order (input.py:398-407), or None when
@@ -479,7 +466,12 @@ class VcfReader(object):
             contig, lo, hi = mt.group(1), int(mt.group(2)) - 1, int(mt.group(3))
             hit = np.nonzero((self.rec_contig == contig) & (self.rec_start < hi) &
                              (self.rec_end > lo))[0]
-            members.extend(hit.tolist())
+            for j in hit.tolist():
+                if self.rec_skip[j] & 4:
+                    sys.stderr.write('Multiple alleles at %s_%s. Skipping\n' %
+                                     (self.rec_contig[j], self.rec_pos[j]))
+                elif not self.rec_skip[j]:
+                    members.append(j)
         return members
 
     def _burden_batches(self, size):
@@ -505,31 +497,18 @@ class VcfReader(object):
             for batch in self._burden_batches(size):
                 yield batch
             return
-        names, states = [], []
-        for name, state in self._rows():
-            if name is None:
-                # skipped record: the reference yields its None sentinel (counted as loaded and
-                # pre-filtered); an empty row takes the same route through the AF filter
-                state = np.zeros(self.n_samples, dtype=np.int8)
-                name = 'NA'
-            elif not state.any():
-                sys.stderr.write('No observations of ' + name + ' in selected samples\n')
-            names.append(name)
-            states.append(state)
-            if len(names) == size:
-                yield self._pack(names, states)
-                names, states = [], []
-        if names:
-            yield self._pack(names, states)
-
-    def _pack(self, names, states):
-        st = np.zeros((len(names), self.W * 32), dtype=np.int8)
-        st[:, :self.n_samples] = np.array(states)
-        bits = np.packbits(st == 1, axis=1, bitorder='little').view('<u4')
-        miss = None
-        if (st == 2).any():
-            miss = np.ascontiguousarray(np.packbits(st == 2, axis=1, bitorder='little').view('<u4'))
-        return VariantBatch(names, np.ascontiguousarray(bits), miss)
+        for nm, bits, miss, info, cg, pos, rl in self._native(size):
+            for i in range(len(nm)):
+                if info[i] & 4:
+                    sys.stderr.write('Multiple alleles at %s_%s. Skipping\n' % (cg[i], pos[i]))
+                if info[i] & 12:
+                    # skipped record: the reference yields its None sentinel (counted as loaded and
+                    # pre-filtered); an empty row takes the same route through the AF filter
+                    nm[i] = 'NA'
+                elif info[i] & 2:
+                    sys.stderr.write('No observations of ' + nm[i] + ' in selected samples\n')
+            yield VariantBatch(nm, np.ascontiguousarray(bits),
+                               np.ascontiguousarray(miss) if (info & 1).any() else None)
 
     sample_lists = VariantReader.sample_lists
     k_vector = VariantReader.k_vector
