@@ -265,6 +265,14 @@ int psb_format_rows(int32_t model, int64_t n_variants, const char *names, const 
                     int32_t print_filtered, char *out, int64_t out_cap, int64_t *out_len,
                     int64_t counts[3]);
 
+/* Pattern hashes of --output-patterns: input.hash_pattern (input.py:710-723) of the vector k the
+ * reference builds from a variant (input.py:450; int64, or float64 with NaN when genotypes are
+ * missing), from host packed rows.  25 bytes per hashed row in `out` (24 base64 characters + '\n');
+ * rows whose flags carry PSB_F_PREFILTER are skipped when `flags` is given (__main__.py:559-560). */
+int psb_hash_patterns(const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
+                      int32_t words_per_row, int32_t n_samples, const uint32_t *flags, char *out,
+                      int64_t *n_out);
+
 /* ---- measurement ------------------------------------------------------------- */
 /* Work counters of the last psb_run_fixed: [0] Newton evaluations (passes over the samples)
  * summed over variants, [1] variants handed to the Firth kernel, [2] variants that failed

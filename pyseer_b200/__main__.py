@@ -20,7 +20,7 @@ from . import __version__
 from . import _lib
 from . import classes as var_obj
 from .engine import notes_from_flags
-from .input import (VariantReader, open_variants, VcfReader, hash_pattern, load_covariates, load_lineage,
+from .input import (VariantReader, open_variants, VcfReader, hash_pattern, hash_patterns, load_covariates, load_lineage,
                     load_phenotypes, load_structure)
 from .utils import format_output, format_table
 
@@ -265,9 +265,9 @@ def main(argv=None):
             r = fx.run_fixed_bits(model, batch.bits, batch.missing, o.filter_pvalue, o.lrt_pvalue,
                                   o.min_af, o.max_af, o.max_missing, lineage=o.lineage)
         flags = r.flags
-        if not (o.print_samples or o.lineage or patterns is not None) and \
+        if not (o.print_samples or o.lineage) and \
                 os.environ.get('PYSEER_B200_NATIVE_FORMAT', '1') != '0':
-            # no per-variant extras asked for: the whole batch goes through the library's formatter
+            # no per-variant samples or lineages asked for: the whole batch goes through the library's formatter
             # (psb_format_rows: same lines, order and counters as the loop below, ~15x its speed)
             text, n_pre, n_tested, n_printed = format_table(r, batch.names, model_name, o.block_size,
                                                             o.print_filtered)
@@ -275,6 +275,9 @@ def main(argv=None):
             tested += n_tested
             printed += n_printed
             out.write(text.decode())
+            if patterns is not None:
+                # hash_pattern of every tested variant, in input order (__main__.py:559-560)
+                patterns.write(hash_patterns(batch.bits, batch.missing, reader.n_samples, flags))
             continue
         # the reference emits each block of --block_size variants as: filtered ones first
         # (LMM only, lmm.py:158-226), then the tested ones; fixed effects keep input order

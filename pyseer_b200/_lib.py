@@ -79,7 +79,7 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_lineage_setup', 'psb_run_lineage', 'psb_fetch_lineage', 'psb_last_stats', 'psb_kinship_begin', 'psb_kinship_add', 'psb_kinship_fetch',
            'psb_synth_device', 'psb_synth_host', 'psb_host_chi2_sf1', 'psb_host_f_sf_1',
            'psb_host_t2_sf', 'psb_submit_burden', 'psb_submit_burden_device',
-           'psb_submitted_device', 'psb_download_rows', 'psb_eigh', 'psb_reader_set_threads', 'psb_format_rows', 'psb_reader_vcf_info']
+           'psb_submitted_device', 'psb_download_rows', 'psb_eigh', 'psb_reader_set_threads', 'psb_format_rows', 'psb_reader_vcf_info', 'psb_hash_patterns']
 
 
 def load():
@@ -114,6 +114,8 @@ def load():
     lib.psb_download_rows.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_int32)]
     lib.psb_eigh.argtypes = [c_void_p, c_int32, dp, dp, dp]
     lib.psb_reader_set_threads.argtypes = [c_void_p, c_int32]
+    lib.psb_hash_patterns.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                      POINTER(c_int64)]
     lib.psb_reader_vcf_info.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.psb_format_rows.argtypes = [c_int32, c_int64, c_void_p, c_void_p, POINTER(PsbResults), c_int32,
                                     c_int32, c_int32, c_void_p, c_int64, POINTER(c_int64),

@@ -559,3 +559,132 @@ extern "C" int psb_reader_vcf_info(psb_reader *r, int64_t n, char *contigs, int6
     }
     return PSB_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Pattern hashes for --output-patterns: input.hash_pattern (pyseer/input.py:710-723) =
+// b2a_base64(md5(k.view(uint8))) of the presence/absence vector k the reference builds (input.py:450):
+// int64 0/1 per sample, or float64 0.0/1.0/NaN when the variant has missing genotypes.  MD5 after
+// RFC 1321, written out here (host-only code).
+// ---------------------------------------------------------------------------------------
+namespace {
+struct Md5 {
+    uint32_t a = 0x67452301u, b = 0xefcdab89u, c = 0x98badcfeu, d = 0x10325476u;
+    uint64_t total = 0;
+    unsigned char buf[64];
+    size_t fill = 0;
+
+    static inline uint32_t rol(uint32_t x, int s) { return (x << s) | (x >> (32 - s)); }
+
+    void block(const unsigned char *p) {
+        static const uint32_t K[64] = {
+            0xd76aa478, 0xe8c7b756, 0x242070db, 0xc1bdceee, 0xf57c0faf, 0x4787c62a, 0xa8304613, 0xfd469501,
+            0x698098d8, 0x8b44f7af, 0xffff5bb1, 0x895cd7be, 0x6b901122, 0xfd987193, 0xa679438e, 0x49b40821,
+            0xf61e2562, 0xc040b340, 0x265e5a51, 0xe9b6c7aa, 0xd62f105d, 0x02441453, 0xd8a1e681, 0xe7d3fbc8,
+            0x21e1cde6, 0xc33707d6, 0xf4d50d87, 0x455a14ed, 0xa9e3e905, 0xfcefa3f8, 0x676f02d9, 0x8d2a4c8a,
+            0xfffa3942, 0x8771f681, 0x6d9d6122, 0xfde5380c, 0xa4beea44, 0x4bdecfa9, 0xf6bb4b60, 0xbebfbc70,
+            0x289b7ec6, 0xeaa127fa, 0xd4ef3085, 0x04881d05, 0xd9d4d039, 0xe6db99e5, 0x1fa27cf8, 0xc4ac5665,
+            0xf4292244, 0x432aff97, 0xab9423a7, 0xfc93a039, 0x655b59c3, 0x8f0ccc92, 0xffeff47d, 0x85845dd1,
+            0x6fa87e4f, 0xfe2ce6e0, 0xa3014314, 0x4e0811a1, 0xf7537e82, 0xbd3af235, 0x2ad7d2bb, 0xeb86d391};
+        static const int S[64] = {7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22, 7, 12, 17, 22,
+                                  5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20, 5, 9,  14, 20,
+                                  4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23, 4, 11, 16, 23,
+                                  6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21, 6, 10, 15, 21};
+        uint32_t w[16];
+        for (int i = 0; i < 16; ++i)
+            w[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) |
+                   ((uint32_t)p[4 * i + 3] << 24);
+        uint32_t A = a, B = b, C = c, D = d;
+        for (int i = 0; i < 64; ++i) {
+            uint32_t f;
+            int g;
+            if (i < 16) { f = (B & C) | (~B & D); g = i; }
+            else if (i < 32) { f = (D & B) | (~D & C); g = (5 * i + 1) & 15; }
+            else if (i < 48) { f = B ^ C ^ D; g = (3 * i + 5) & 15; }
+            else { f = C ^ (B | ~D); g = (7 * i) & 15; }
+            const uint32_t t = D;
+            D = C;
+            C = B;
+            B = B + rol(A + f + K[i] + w[g], S[i]);
+            A = t;
+        }
+        a += A; b += B; c += C; d += D;
+    }
+
+    void update(const unsigned char *p, size_t n) {
+        total += n;
+        while (n > 0) {
+            const size_t take = std::min(n, (size_t)64 - fill);
+            memcpy(buf + fill, p, take);
+            fill += take;
+            p += take;
+            n -= take;
+            if (fill == 64) { block(buf); fill = 0; }
+        }
+    }
+
+    void finish(unsigned char out[16]) {
+        const uint64_t bits = total * 8;
+        const unsigned char pad = 0x80, zero = 0;
+        update(&pad, 1);
+        while (fill != 56) update(&zero, 1);
+        unsigned char len[8];
+        for (int i = 0; i < 8; ++i) len[i] = (unsigned char)(bits >> (8 * i));
+        update(len, 8);
+        const uint32_t st[4] = {a, b, c, d};
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) out[4 * i + j] = (unsigned char)(st[i] >> (8 * j));
+    }
+};
+}  // namespace
+
+// out: 25 bytes per hashed row (24 base64 characters + '\n', what binascii.b2a_base64 returns).
+// flags (nullable): rows with PSB_F_PREFILTER set are skipped -- the result loop hashes the tested
+// variants only (__main__.py:559-560).  *n_out = rows hashed.
+extern "C" int psb_hash_patterns(const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
+                                 int32_t words_per_row, int32_t n_samples, const uint32_t *flags, char *out,
+                                 int64_t *n_out) {
+    PSB_REQUIRE(bits && out && n_out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(words_per_row * 32 >= n_samples && n_samples > 0, PSB_ERR_ARG, "bad row shape");
+    static const char b64[] = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    std::vector<unsigned char> k((size_t)n_samples * 8);
+    int64_t m = 0;
+    for (int64_t v = 0; v < n_variants; ++v) {
+        if (flags && (flags[v] & PSB_F_PREFILTER)) continue;
+        const uint32_t *row = bits + v * words_per_row;
+        const uint32_t *mrow = missing ? missing + v * words_per_row : nullptr;
+        bool any_missing = false;
+        if (mrow)
+            for (int w = 0; w < (n_samples + 31) / 32 && !any_missing; ++w) any_missing = mrow[w] != 0;
+        memset(k.data(), 0, k.size());
+        for (int i = 0; i < n_samples; ++i) {
+            const bool on = (row[i >> 5] >> (i & 31)) & 1u;
+            const bool ms = any_missing && ((mrow[i >> 5] >> (i & 31)) & 1u);
+            unsigned char *c = &k[(size_t)i * 8];
+            if (!any_missing) {
+                c[0] = on ? 1 : 0;                                   // int64, little endian
+            } else if (ms) {
+                c[6] = 0xf8; c[7] = 0x7f;                            // float64 NaN (numpy.nan)
+            } else if (on) {
+                c[6] = 0xf0; c[7] = 0x3f;                            // float64 1.0
+            }
+        }
+        Md5 h;
+        h.update(k.data(), k.size());
+        unsigned char dg[18] = {0};
+        h.finish(dg);
+        char *o = out + m * 25;
+        for (int i = 0, j = 0; i < 18; i += 3, j += 4) {
+            const uint32_t t = ((uint32_t)dg[i] << 16) | ((uint32_t)dg[i + 1] << 8) | dg[i + 2];
+            o[j] = b64[(t >> 18) & 63];
+            o[j + 1] = b64[(t >> 12) & 63];
+            o[j + 2] = b64[(t >> 6) & 63];
+            o[j + 3] = b64[t & 63];
+        }
+        o[22] = '=';                                                 // 16 bytes -> 22 characters + '=='
+        o[23] = '=';
+        o[24] = '\n';
+        ++m;
+    }
+    *n_out = m;
+    return PSB_OK;
+}

@@ -109,6 +109,30 @@ def hash_pattern(k):
     return binascii.b2a_base64(hashlib.md5(np.ascontiguousarray(k).view(np.uint8)).digest())
 
 
+def hash_patterns(bits, missing, n_samples, flags=None):
+    """hash_pattern of every row of a packed batch through the library (``psb_hash_patterns``):
+    the concatenated 25-byte entries the result loop writes to ``--output-patterns`` for the
+    tested variants (rows whose flags carry F_PREFILTER are skipped when ``flags`` is given)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    bits = np.ascontiguousarray(bits, dtype=np.uint32)
+    n, W = bits.shape
+    mp = None
+    if missing is not None:
+        missing = np.ascontiguousarray(missing, dtype=np.uint32)
+        mp = missing.ctypes.data_as(ctypes.c_void_p)
+    fp = None
+    if flags is not None:
+        flags = np.ascontiguousarray(flags, dtype=np.uint32)
+        fp = flags.ctypes.data_as(ctypes.c_void_p)
+    out = ctypes.create_string_buffer(25 * n + 1)
+    m = ctypes.c_int64(0)
+    _lib.check(lib.psb_hash_patterns(bits.ctypes.data_as(ctypes.c_void_p), mp, n, W, int(n_samples), fp,
+                                     ctypes.addressof(out), ctypes.byref(m)))
+    return out.raw[:25 * m.value]
+
+
 class VariantBatch(object):
     """``n`` variants as packed rows plus what the result loop needs to print them."""
     __slots__ = ['names', 'bits', 'missing', 'n']

@@ -148,3 +148,41 @@ def test_vcf_reader_matches_read_vcf_var(hg):
         with contextlib.redirect_stderr(io.StringIO()):
             batches = list(rd.batches(100))
         _check_rows(rd, batches, hg[key]['rows'], n)
+
+
+def test_native_pattern_hashes(hg):
+    """psb_hash_patterns against the reference's hash_pattern on the k-mer, Rtab and VCF fixtures
+    (int64 vectors and float64 vectors with NaN), and the flags filter."""
+    from pyseer_b200 import _lib
+    from pyseer_b200.input import VariantReader, VcfReader, hash_patterns, hash_pattern
+    p = _pheno()
+    n = len(p.index)
+    for kind, fn, key in (('kmers', 'kmers.gz', 'kmers'), ('Rtab', 'presence_absence.Rtab.gz', 'rtab'),
+                          ('vcf', 'variants50.vcf.gz', 'vcf')):
+        rd = VcfReader(os.path.join(GOLDEN, fn), p) if kind == 'vcf' else \
+            VariantReader(kind, os.path.join(GOLDEN, fn), p)
+        with contextlib.redirect_stderr(io.StringIO()):
+            batches = list(rd.batches(400))
+        rows = hg[key]['rows']
+        j = 0
+        n_missing_rows = 0
+        for b in batches:
+            blob = hash_patterns(b.bits, b.missing, n)
+            assert len(blob) == 25 * b.n
+            for i in range(b.n):
+                want = rows[j]
+                j += 1
+                got = blob[25 * i:25 * i + 25]
+                assert got == hash_pattern(rd.k_vector(b, i))
+                if want['name'] is not None:
+                    assert got.decode() == want['hash'], want['name']
+                    n_missing_rows += want['missing'] > 0
+            # flags: pre-filtered rows are left out
+            flags = np.zeros(b.n, dtype=np.uint32)
+            flags[::3] = _lib.F_PREFILTER
+            sub = hash_patterns(b.bits, b.missing, n, flags)
+            keep = [i for i in range(b.n) if i % 3]
+            assert sub == b''.join(blob[25 * i:25 * i + 25] for i in keep)
+        rd.close()
+        if kind == 'vcf':
+            assert n_missing_rows > 0          # the float64 / NaN branch is exercised
