@@ -226,7 +226,8 @@ def main(argv=None):
             eng.submit_burden(vbits, vmiss, offsets, members)
             return eng.download_rows()
 
-        reader = VcfReader(o.vcf, p, o.burden, reducer=device_union if o.burden else None)
+        reader = VcfReader(o.vcf, p, o.burden, reducer=device_union if o.burden else None,
+                           threads=o.cpu)
     else:
         reader = open_variants('kmers' if o.kmers else 'Rtab', o.kmers or o.pres, p, o.uncompressed,
                                cache=o.bits_cache, threads=o.cpu)
