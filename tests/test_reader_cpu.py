@@ -183,3 +183,20 @@ def test_parser_threads_give_identical_rows(tmp_path):
         with pytest.raises(PsbError, match="without '\\|' separator"):
             list(rd.batches(64))
         rd.close()
+
+
+def test_vcf_parser_threads_give_identical_batches():
+    from pyseer_b200.input import VcfReader
+    p = _pheno()
+    outs = []
+    for threads in (1, 6):
+        rd = VcfReader(os.path.join(GOLDEN, 'variants50.vcf.gz'), p, threads=threads)
+        err = io.StringIO()
+        with contextlib.redirect_stderr(err):
+            bs = list(rd.batches(250))
+        rd.close()
+        outs.append(([x for b in bs for x in b.names], np.concatenate([b.bits for b in bs]),
+                     [b.missing is None for b in bs], err.getvalue()))
+    assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]
+    assert len(outs[0][0]) == 886
