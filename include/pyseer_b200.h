@@ -259,11 +259,12 @@ int psb_reader_close(psb_reader *reader);
  * the pre-filtered ones come first, lmm.py:158-226).  Numbers as '%.2E', empty when not finite or
  * not set by the model; notes from the flag bits.  names / name_off: NUL-terminated variant names
  * back to back and their offsets; cols: HOST pointers.  counts[0..2] += pre-filtered, tested,
- * printed.  Host-only; covers runs without --print-samples / --lineage. */
+ * printed.  n_threads > 1 formats ranges of whole blocks in parallel.  Host-only; covers runs without
+ * --print-samples / --lineage. */
 int psb_format_rows(int32_t model, int64_t n_variants, const char *names, const int64_t *name_off,
                     const psb_results *cols, int32_t n_betas, int32_t block_size,
-                    int32_t print_filtered, char *out, int64_t out_cap, int64_t *out_len,
-                    int64_t counts[3]);
+                    int32_t print_filtered, int32_t n_threads, char *out, int64_t out_cap,
+                    int64_t *out_len, int64_t counts[3]);
 
 /* Pattern hashes of --output-patterns: input.hash_pattern (input.py:710-723) of the vector k the
  * reference builds from a variant (input.py:450; int64, or float64 with NaN when genotypes are

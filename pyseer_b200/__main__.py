@@ -271,7 +271,7 @@ def main(argv=None):
             # no per-variant samples or lineages asked for: the whole batch goes through the library's formatter
             # (psb_format_rows: same lines, order and counters as the loop below, ~15x its speed)
             text, n_pre, n_tested, n_printed = format_table(r, batch.names, model_name, o.block_size,
-                                                            o.print_filtered)
+                                                            o.print_filtered, threads=o.cpu)
             prefilter += n_pre
             tested += n_tested
             printed += n_printed

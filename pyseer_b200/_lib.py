@@ -118,7 +118,7 @@ def load():
                                       POINTER(c_int64)]
     lib.psb_reader_vcf_info.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.psb_format_rows.argtypes = [c_int32, c_int64, c_void_p, c_void_p, POINTER(PsbResults), c_int32,
-                                    c_int32, c_int32, c_void_p, c_int64, POINTER(c_int64),
+                                    c_int32, c_int32, c_int32, c_void_p, c_int64, POINTER(c_int64),
                                     POINTER(c_int64)]
     lib.psb_run_lmm.argtypes = [c_void_p, POINTER(PsbParams)]
     lib.psb_run_fixed.argtypes = [c_void_p, POINTER(PsbParams)]

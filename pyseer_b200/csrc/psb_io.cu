@@ -454,29 +454,16 @@ static const struct { uint32_t bit; const char *text; } k_notes[] = {
     {PSB_F_LRT_FAILED, "lrt-filtering-failed"},
 };
 
-// model: 0 = fixed effects (Seer: ... bse, intercept, betas[n_betas]), 1 = LMM (... bse, variant_h2).
-// names: NUL-terminated variant names back to back, name_off[v] their offsets.  cols: HOST pointers
-// of the result table (psb_fetch).  Rows are visited in blocks of block_size; inside a block the LMM
-// model emits the pre-filtered variants first (lmm.py:158-226), fixed effects keep input order.
-// counts[0..2] += pre-filtered, tested, printed (__main__.py:549-565, 793-817).  Returns PSB_ERR_NOMEM
-// when out_cap is too small (nothing usable in `out` then).
-extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, const int64_t *name_off,
-                               const psb_results *cols, int32_t n_betas, int32_t block_size,
-                               int32_t print_filtered, char *out, int64_t out_cap, int64_t *out_len,
-                               int64_t counts[3]) {
-    PSB_REQUIRE(names && name_off && cols && out && out_len && counts, PSB_ERR_ARG, "NULL argument");
-    PSB_REQUIRE(cols->af && cols->prep && cols->pvalue && cols->beta && cols->bse && cols->extra &&
-                    cols->flags && (n_betas == 0 || cols->betas),
-                PSB_ERR_ARG, "result columns missing");
-    PSB_REQUIRE(model == 0 || model == 1, PSB_ERR_ARG, "model must be 0 (seer) or 1 (lmm)");
-    if (block_size < 1) block_size = 1;
-    char *p = out;
-    char *const end = out + out_cap;
-    const int64_t per_row = 32 * (7 + (int64_t)n_betas) + 256;      // numbers, tabs, notes
-    for (int64_t b0 = 0; b0 < n; b0 += block_size) {
-        const int64_t b1 = std::min<int64_t>(n, b0 + block_size);
+// Formats rows [b0, b1) (b0 a multiple of block_size) into `dst`; counts[0..2] += pre-filtered,
+// tested, printed.
+static void format_range(int model, int64_t b0, int64_t b1, const char *names, const int64_t *name_off,
+                         const psb_results *cols, int n_betas, int block_size, int print_filtered,
+                         std::string &dst, int64_t counts[3]) {
+    char num[40];
+    for (int64_t c0 = b0; c0 < b1; c0 += block_size) {
+        const int64_t c1 = std::min<int64_t>(b1, c0 + block_size);
         for (int pass = 0; pass < (model == 1 ? 2 : 1); ++pass) {
-            for (int64_t v = b0; v < b1; ++v) {
+            for (int64_t v = c0; v < c1; ++v) {
                 const uint32_t f = cols->flags[v];
                 const bool pre = (f & PSB_F_PREFILTER) != 0;
                 if (model == 1 && pre != (pass == 0)) continue;
@@ -487,55 +474,95 @@ extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, cons
                     counts[1]++;
                     if ((f & PSB_F_FILTER) && !print_filtered) continue;
                 }
-                const char *nm = names + name_off[v];
-                const size_t nl = strlen(nm);
-                if ((int64_t)(end - p) < (int64_t)nl + per_row) {
-                    psb_set_error("output buffer too small");
-                    return PSB_ERR_NOMEM;
-                }
-                memcpy(p, nm, nl);
-                p += nl;
-                *p++ = '\t';
-                p = fmt_num(p, cols->af[v]);
-                *p++ = '\t';
-                p = fmt_num(p, cols->prep[v]);
-                *p++ = '\t';
+                auto put = [&](double x) { dst.append(num, (size_t)(fmt_num(num, x) - num)); };
+                dst.append(names + name_off[v]);
+                dst.push_back('\t');
+                put(cols->af[v]);
+                dst.push_back('\t');
+                put(cols->prep[v]);
+                dst.push_back('\t');
                 // fields the tuple leaves at NaN stay empty
                 const bool fitted = !pre && !(f & (PSB_F_FIRTH_FAIL | PSB_F_MISSING_DATA)) &&
                                     !(model == 1 && (f & PSB_F_FILTER));
                 const bool has_p = !pre && !(model == 0 && (f & (PSB_F_FIRTH_FAIL | PSB_F_MISSING_DATA)));
-                if (has_p) p = fmt_num(p, cols->pvalue[v]);
-                *p++ = '\t';
-                if (fitted) p = fmt_num(p, cols->beta[v]);
-                *p++ = '\t';
-                if (fitted) p = fmt_num(p, cols->bse[v]);
-                *p++ = '\t';
-                if (fitted) p = fmt_num(p, cols->extra[v]);
+                if (has_p) put(cols->pvalue[v]);
+                dst.push_back('\t');
+                if (fitted) put(cols->beta[v]);
+                dst.push_back('\t');
+                if (fitted) put(cols->bse[v]);
+                dst.push_back('\t');
+                if (fitted) put(cols->extra[v]);
                 if (model == 0 && fitted && n_betas > 0) {
                     for (int c = 0; c < n_betas; ++c) {
-                        *p++ = '\t';
-                        p = fmt_num(p, cols->betas[v * n_betas + c]);
+                        dst.push_back('\t');
+                        put(cols->betas[v * n_betas + c]);
                     }
                 }
-                *p++ = '\t';
+                dst.push_back('\t');
                 bool first = true;
                 for (const auto &nt : k_notes)
                     if (f & nt.bit) {
-                        if (!first) *p++ = ',';
-                        const size_t tl = strlen(nt.text);
-                        memcpy(p, nt.text, tl);
-                        p += tl;
+                        if (!first) dst.push_back(',');
+                        dst.append(nt.text);
                         first = false;
                     }
-                *p++ = '\n';
+                dst.push_back('\n');
                 counts[2]++;
             }
         }
     }
-    *out_len = (int64_t)(p - out);
-    return PSB_OK;
 }
 
+// model: 0 = fixed effects (Seer: ... bse, intercept, betas[n_betas]), 1 = LMM (... bse, variant_h2).
+// names: NUL-terminated variant names back to back, name_off[v] their offsets.  cols: HOST pointers
+// of the result table (psb_fetch).  Rows are visited in blocks of block_size; inside a block the LMM
+// model emits the pre-filtered variants first (lmm.py:158-226), fixed effects keep input order.
+// counts[0..2] += pre-filtered, tested, printed (__main__.py:549-565, 793-817).  n_threads > 1 formats
+// ranges of whole blocks in parallel and concatenates them in order.  Returns PSB_ERR_NOMEM when
+// out_cap is too small (nothing usable in `out` then).
+extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, const int64_t *name_off,
+                               const psb_results *cols, int32_t n_betas, int32_t block_size,
+                               int32_t print_filtered, int32_t n_threads, char *out, int64_t out_cap,
+                               int64_t *out_len, int64_t counts[3]) {
+    PSB_REQUIRE(names && name_off && cols && out && out_len && counts, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(cols->af && cols->prep && cols->pvalue && cols->beta && cols->bse && cols->extra &&
+                    cols->flags && (n_betas == 0 || cols->betas),
+                PSB_ERR_ARG, "result columns missing");
+    PSB_REQUIRE(model == 0 || model == 1, PSB_ERR_ARG, "model must be 0 (seer) or 1 (lmm)");
+    if (block_size < 1) block_size = 1;
+    const int64_t n_blocks = (n + block_size - 1) / block_size;
+    int T = n_threads < 1 ? 1 : (n_threads > 64 ? 64 : n_threads);
+    T = (int)std::min<int64_t>(T, std::max<int64_t>(1, n / 2048));
+    T = (int)std::min<int64_t>(T, std::max<int64_t>(1, n_blocks));
+    std::vector<std::string> parts((size_t)T);
+    std::vector<int64_t> cnt((size_t)T * 3, 0);
+    auto work = [&](int t) {
+        const int64_t b0 = (n_blocks * t / T) * block_size;
+        const int64_t b1 = std::min<int64_t>(n, (n_blocks * (t + 1) / T) * block_size);
+        parts[t].reserve((size_t)((b1 - b0) * (64 + 10 * (7 + n_betas))));
+        format_range(model, b0, b1, names, name_off, cols, n_betas, block_size, print_filtered, parts[t],
+                     &cnt[(size_t)t * 3]);
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+    }
+    int64_t total = 0;
+    for (const auto &s2 : parts) total += (int64_t)s2.size();
+    PSB_REQUIRE(total <= out_cap, PSB_ERR_NOMEM, "output buffer too small (%lld bytes needed)", (long long)total);
+    char *p = out;
+    for (int t = 0; t < T; ++t) {
+        memcpy(p, parts[t].data(), parts[t].size());
+        p += parts[t].size();
+        for (int k = 0; k < 3; ++k) counts[k] += cnt[(size_t)t * 3 + k];
+    }
+    *out_len = total;
+    return PSB_OK;
+}
 
 // VCF only: contig (NUL-terminated, back to back in `contigs` with contig_off[v] offsets), 1-based
 // position and REF length of the records returned by the last psb_reader_next -- what the burden

@@ -32,7 +32,7 @@ def format_output(item, lineage_dict=None, model='seer', print_samples=False):
     return '\t'.join(fields)
 
 
-def format_table(r, names, model='seer', block_size=1, print_filtered=False):
+def format_table(r, names, model='seer', block_size=1, print_filtered=False, threads=1):
     """TSV lines of a whole result table (``engine.Results``) through the library's native formatter
     (``psb_format_rows``): what the result loop of ``main()`` prints with ``format_output`` when
     neither samples nor lineages are asked for.  Returns ``(text_bytes, prefiltered, tested,
@@ -65,5 +65,5 @@ def format_table(r, names, model='seer', block_size=1, print_filtered=False):
     counts = (ctypes.c_int64 * 3)(0, 0, 0)
     _lib.check(lib.psb_format_rows(1 if model == 'lmm' else 0, n, blob, off.ctypes.data_as(ctypes.c_void_p),
                                    ctypes.byref(cols), nb, int(block_size), int(bool(print_filtered)),
-                                   ctypes.addressof(out), cap, ctypes.byref(out_len), counts))
+                                   int(threads), ctypes.addressof(out), cap, ctypes.byref(out_len), counts))
     return out.raw[:out_len.value], counts[0], counts[1], counts[2]

@@ -82,11 +82,13 @@ def test_native_formatter_matches_result_loop():
     rng = np.random.RandomState(3)
     for model, nb in (('seer', 11), ('seer', 0), ('lmm', 0)):
         for block_size, pf in ((1, False), (7, True), (3000, False), (50, True)):
-            n = 503
+            n = 5003
             r = _table(rng, n, nb)
             names = ['K%d_%s' % (i, 'ACGT' * (i % 9)) for i in range(n)]
             want, pre, tested, printed = _python_lines(r, names, model, block_size, pf)
             text, c0, c1, c2 = format_table(r, names, model, block_size, pf)
+            # ranges of whole blocks formatted by several threads give the same bytes
+            assert format_table(r, names, model, block_size, pf, threads=5) == (text, c0, c1, c2)
             got = text.decode().split('\n')
             assert got[-1] == '' and len(got) - 1 == len(want) == printed
             assert (c0, c1, c2) == (pre, tested, printed)
