@@ -1,0 +1,194 @@
+"""The CLI's host side end to end WITHOUT a GPU: readers (native k-mer / Rtab / VCF parsers, burden
+regions), batching, the native formatter and pattern hashes, counters -- with the device engine
+replaced by test doubles that compute every batch through the oracle (oracle/ is test
+infrastructure; the product path has no such route).  Outputs are compared with the reference's own
+baseline logs exactly as tests/test_cli_gpu.py does on the B200."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from test_cli_gpu import CASES, _counters, _same, _table      # same cases, same comparison
+
+pytestmark = []          # (test_cli_gpu's module-level gpu mark does not apply here)
+
+
+class _FakeEngine(object):
+    """Burden unions through the oracle's packed-row rule instead of psb_submit_burden."""
+
+    def submit_burden(self, bits, missing, offsets, members):
+        from oracle.input_oracle import burden_union
+        self._rows = burden_union(bits, missing, offsets, members)
+
+    def download_rows(self):
+        bits, miss = self._rows
+        return bits, (miss if miss is not None and miss.any() else None)
+
+
+class _FakeFixedModel(object):
+    def __init__(self, p, m, cov, continuous, null_res, null_firth, device=0, lineage=None):
+        self.p = np.asarray(p, dtype=float).reshape(-1)
+        self.m = np.asarray(m)
+        self.cov = np.asarray(getattr(cov, 'values', cov))
+        self.continuous = bool(continuous)
+        self.null_llf = getattr(null_res, 'llf', null_res)
+        self.null_firth = null_firth
+        self.engine = _FakeEngine()
+
+    def close(self):
+        pass
+
+
+def _k_of(bits, missing, j, n):
+    from pyseer_b200.engine import unpack_rows
+    x = unpack_rows(bits[j:j + 1], n)[0].astype(float)
+    if missing is not None:
+        mm = unpack_rows(missing[j:j + 1], n)[0].astype(bool)
+        if mm.any():
+            x[mm] = np.nan
+            return x
+    return x.astype(np.int64)
+
+
+def _results(n, nb):
+    from pyseer_b200.engine import Results
+    r = Results()
+    for f in ('af', 'prep', 'pvalue', 'beta', 'bse', 'extra'):
+        setattr(r, f, np.full(n, np.nan))
+    r.betas = np.full((n, nb), np.nan)
+    r.flags = np.zeros(n, dtype=np.uint32)
+    r.carriers = np.zeros(n, dtype=np.int32)
+    r.missing = np.zeros(n, dtype=np.int32)
+    r.lineage = None
+    return r
+
+
+def _flags(notes, prefilter, filt):
+    from pyseer_b200 import _lib
+    bit = {s: b for b, s in _lib.NOTE_BITS}
+    f = 0
+    for s in notes:
+        f |= bit[s]
+    if prefilter:
+        f |= _lib.F_PREFILTER
+    else:
+        f |= _lib.F_TESTED
+    if filt:
+        f |= _lib.F_FILTER
+    return f
+
+
+def _fake_run_fixed_bits(model, bits, missing, filter_pvalue, lrt_pvalue, min_af=-1.0, max_af=2.0,
+                         max_missing=2.0, lineage=False):
+    """model.fixed_effects_regression per variant through the oracle, iter_variants' AF filter first
+    (input.py:608)."""
+    from oracle import fixed_oracle as fo
+    n = model.p.shape[0]
+    nb = model.m.shape[1] if model.m.ndim == 2 and model.m.shape[0] == n else 0
+    nb += model.cov.shape[1] if model.cov.ndim == 2 and model.cov.shape[0] == n else 0
+    S = bits.shape[0]
+    r = _results(S, nb)
+    for j in range(S):
+        k = _k_of(bits, missing, j, n)
+        nan_mask = np.isnan(k) if k.dtype.kind == 'f' else np.zeros(n, dtype=bool)
+        carriers = int(np.nansum(k == 1) + nan_mask.sum())          # missing count as carriers (:439)
+        af = carriers / float(n)
+        miss = nan_mask.sum() / float(n)
+        keep = (min_af <= af <= max_af) and not (miss > max_missing)
+        o = fo.fixed_effects_regression('v', model.p if keep else None, k.astype(float), model.m, model.cov, af,
+                                        'p', False, None, filter_pvalue, lrt_pvalue, model.null_llf,
+                                        model.null_firth, [], [], model.continuous)
+        r.af[j], r.prep[j], r.pvalue[j], r.beta[j], r.bse[j] = af, o.prep, o.pvalue, o.kbeta, o.bse
+        r.extra[j] = o.intercept
+        betas = np.atleast_1d(np.asarray(o.betas, dtype=float)) if nb else np.empty(0)
+        if nb and betas.shape[0] == nb:
+            r.betas[j] = betas
+        r.flags[j] = _flags(set(o.notes), o.prefilter, o.filter)
+    return r
+
+
+def _fake_run_lmm_bits(lmm, h2, bits, missing, continuous, filter_pvalue, lrt_pvalue, min_af=-1.0,
+                       max_af=2.0, max_missing=2.0):
+    """lmm.fit_lmm over the batch through the oracle (load_var_block's AF rule, input.py:693)."""
+    from oracle import lmm_oracle as lo
+    n = lmm.Y.shape[0]
+    S = bits.shape[0]
+    olmm = lo.OracleLMM(lmm.X, lmm.Y, None)
+    olmm.S, olmm.U = lmm.getSU()
+    r = _results(S, 0)
+    y = lmm.Y[:, 0]
+    nan = float('nan')
+    variants, mat = [], np.zeros((n, S))
+    for j in range(S):
+        k = _k_of(bits, missing, j, n)
+        nan_mask = np.isnan(k) if k.dtype.kind == 'f' else np.zeros(n, dtype=bool)
+        af = (int(np.nansum(k == 1)) + int(nan_mask.sum())) / float(n)
+        miss = nan_mask.sum() / float(n)
+        ok = not (af < min_af or af > max_af or miss > max_missing)
+        var = lo.LMM(str(j), 'p' if ok else None, af, nan, nan, nan, nan, nan, nan, [], [], set(), True, True)
+        variants.append((var, y, k.astype(float) if ok else None))
+        if ok:
+            mat[:, j] = k.astype(float)
+        r.af[j] = af
+    out = lo.fit_lmm(olmm, h2, variants, mat, False, [], np.empty((0, 0)), continuous, filter_pvalue,
+                     lrt_pvalue)
+    for o in out:
+        j = int(o.kmer)
+        r.prep[j], r.pvalue[j], r.beta[j], r.bse[j], r.extra[j] = o.prep, o.pvalue, o.kbeta, o.bse, o.frac_h2
+        r.flags[j] = _flags(o.notes, o.prefilter, o.filter)
+    return r
+
+
+def _fake_fit_null(p, m, cov, continuous, firth=False, device=0):
+    from oracle import fixed_oracle as fo
+    return fo.fit_null(np.asarray(p, dtype=float), np.asarray(m), np.asarray(getattr(cov, 'values', cov)),
+                       continuous, firth)
+
+
+CPU_CASES = ['1', '3', '12', '13', '37', '28', '14', '27', '23']
+
+
+@pytest.mark.parametrize('case', CPU_CASES)
+def test_baseline_with_oracle_engine(case, tmp_path, monkeypatch):
+    from pyseer_b200 import model as fx, lmm as lm
+    from pyseer_b200.__main__ import main
+    monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
+    monkeypatch.setattr(fx, 'FixedModel', _FakeFixedModel)
+    monkeypatch.setattr(fx, 'run_fixed_bits', _fake_run_fixed_bits)
+    monkeypatch.setattr(lm, 'run_lmm_bits', _fake_run_lmm_bits)
+    monkeypatch.setattr(lm.KinshipLMM, 'close', lambda self: None)
+    out, err = io.StringIO(), io.StringIO()
+    args = list(CASES[case]) + ['--cpu', '3']
+    if case == '27':
+        args += ['--output-patterns', str(tmp_path / 'patterns.txt')]
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err), np.errstate(all='ignore'):
+        main(args)
+    ref_out = open(os.path.join(GOLDEN, 'baseline', case + '.log')).read()
+    ref_err = open(os.path.join(GOLDEN, 'baseline', case + '.err')).read()
+    assert _counters(err.getvalue()) == _counters(ref_err)
+    if case == '27':
+        # one hash per tested variant, equal to the reference's hash_pattern of the same vectors
+        import json
+        pats = open(str(tmp_path / 'patterns.txt'), 'rb').read().split(b'\n')[:-1]
+        assert len(pats) == _counters(err.getvalue())['tested'] and all(len(x) == 24 for x in pats)
+        rows = json.load(open(os.path.join(GOLDEN, 'host_goldens.json')))['kmers']['rows']
+        want = set(r['hash'].strip() for r in rows)
+        assert set(x.decode() for x in pats) <= want
+    h, rows = _table(out.getvalue())
+    rh, rrows = _table(ref_out)
+    assert h == rh
+    assert list(rows) == list(rrows)                   # same variants, same order
+    bad = []
+    for name, ref in rrows.items():
+        got = rows[name]
+        for col in rh[1:]:
+            if col == 'notes':
+                ok = set(got[col].split(',')) == set(ref[col].split(','))
+            else:
+                ok = _same(got[col], ref[col], abs_only=col.startswith('PC'))
+            if not ok:
+                bad.append((name[:20], col, got[col], ref[col]))
+    assert not bad, bad[:10]
