@@ -192,3 +192,37 @@ def test_baseline_with_oracle_engine(case, tmp_path, monkeypatch):
             if not ok:
                 bad.append((name[:20], col, got[col], ref[col]))
     assert not bad, bad[:10]
+
+
+def test_bits_cache_and_formatter_paths_agree(tmp_path, monkeypatch):
+    """The same run with and without --bits-cache (first run writes it, second reads it), and with the
+    row-by-row Python formatter instead of the native one, prints the same bytes."""
+    from pyseer_b200 import model as fx, lmm as lm
+    from pyseer_b200.__main__ import main
+    monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
+    monkeypatch.setattr(fx, 'FixedModel', _FakeFixedModel)
+    monkeypatch.setattr(fx, 'run_fixed_bits', _fake_run_fixed_bits)
+    cache = str(tmp_path / 'kmers.bits')
+
+    def run(extra, env=None):
+        out, err = io.StringIO(), io.StringIO()
+        if env:
+            monkeypatch.setenv(*env)
+        with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err), np.errstate(all='ignore'):
+            main(list(CASES['3']) + ['--print-filtered'] + extra)
+        if env:
+            monkeypatch.delenv(env[0])
+        return out.getvalue(), _counters(err.getvalue()), err.getvalue()
+
+    base, counts, _ = run([])
+    first, c1, e1 = run(['--bits-cache', cache])
+    second, c2, e2 = run(['--bits-cache', cache])
+    assert 'Reading packed variants from' in e2 and 'Reading packed variants from' not in e1
+    assert base == first == second and counts == c1 == c2
+    slow, c3, _ = run([], env=('PYSEER_B200_NATIVE_FORMAT', '0'))
+    assert c3 == counts
+    a, b = base.split('\n'), slow.split('\n')
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        fx_, fy = x.split('\t'), y.split('\t')
+        assert fx_[:-1] == fy[:-1] and set(fx_[-1].split(',')) == set(fy[-1].split(','))
