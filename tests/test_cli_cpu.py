@@ -148,7 +148,7 @@ def _fake_fit_null(p, m, cov, continuous, firth=False, device=0):
                        continuous, firth)
 
 
-CPU_CASES = ['1', '3', '12', '13', '37', '28', '14', '27', '23']
+CPU_CASES = ['1', '3', '5', '6', '9', '12', '13', '14', '15', '20', '23', '24', '25', '27', '28', '29', '37']
 
 
 @pytest.mark.parametrize('case', CPU_CASES)
