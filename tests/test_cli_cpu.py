@@ -226,3 +226,76 @@ def test_bits_cache_and_formatter_paths_agree(tmp_path, monkeypatch):
     for x, y in zip(a, b):
         fx_, fy = x.split('\t'), y.split('\t')
         assert fx_[:-1] == fy[:-1] and set(fx_[-1].split(',')) == set(fy[-1].split(','))
+
+
+def _run_cli(args, monkeypatch):
+    from pyseer_b200 import model as fx, lmm as lm
+    from pyseer_b200.__main__ import main
+    monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
+    monkeypatch.setattr(fx, 'FixedModel', _FakeFixedModel)
+    monkeypatch.setattr(fx, 'run_fixed_bits', _fake_run_fixed_bits)
+    monkeypatch.setattr(lm, 'run_lmm_bits', _fake_run_lmm_bits)
+    monkeypatch.setattr(lm.KinshipLMM, 'close', lambda self: None)
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err), np.errstate(all='ignore'):
+        main(args)
+    return out.getvalue(), err.getvalue()
+
+
+def _compare(case, out, err):
+    ref_out = open(os.path.join(GOLDEN, 'baseline', case + '.log')).read()
+    ref_err = open(os.path.join(GOLDEN, 'baseline', case + '.err')).read()
+    assert _counters(err) == _counters(ref_err)
+    h, rows = _table(out)
+    rh, rrows = _table(ref_out)
+    assert h == rh and list(rows) == list(rrows)
+    bad = []
+    for name, ref in rrows.items():
+        for col in rh[1:]:
+            got = rows[name][col]
+            if col == 'notes':
+                ok = set(got.split(',')) == set(ref[col].split(','))
+            elif col in ('k-samples', 'nk-samples'):
+                ok = got == ref[col]
+            else:
+                ok = _same(got, ref[col], abs_only=col.startswith('PC'))
+            if not ok:
+                bad.append((name[:20], col, got[:40], ref[col][:40]))
+    assert not bad, bad[:10]
+
+
+def test_more_reference_invocations(tmp_path, monkeypatch):
+    """run_test.sh:21, 26-27, 29-30, 42-43, 48: --save-m / --load-m, --print-samples (the row-by-row
+    formatter with sample lists), uncompressed k-mers, --cpu 2, --save-lmm / --load-lmm."""
+    import gzip
+    G = lambda f: os.path.join(GOLDEN, f)
+    fixed = ['--kmers', G('kmers.gz'), '--phenotypes', G('subset.pheno')]
+    # 1 + 2 + 8: save the projection, load it again
+    out, err = _run_cli(fixed + ['--distances', G('distances50.tsv'), '--save-m', str(tmp_path / 'pop')],
+                        monkeypatch)
+    _compare('1', out, err)
+    pkl = str(tmp_path / 'pop.pkl')
+    for case in ('2', '8'):
+        out, err = _run_cli(fixed + ['--load-m', pkl], monkeypatch)
+        _compare(case, out, err)
+    # 7: sample lists
+    out, err = _run_cli(fixed + ['--max-dimensions', '3', '--print-samples', '--load-m', pkl], monkeypatch)
+    _compare('7', out, err)
+    # 10: uncompressed text
+    txt = str(tmp_path / 'kmers.txt')
+    with gzip.open(G('kmers.gz'), 'rb') as src, open(txt, 'wb') as dst:
+        dst.write(src.read())
+    out, err = _run_cli(['--kmers', txt, '--phenotypes', G('subset.pheno'), '--uncompressed', '--load-m', pkl],
+                        monkeypatch)
+    _compare('10', out, err)
+    # 11: --cpu 2
+    out, err = _run_cli(fixed + ['--cpu', '2', '--load-m', pkl], monkeypatch)
+    _compare('11', out, err)
+    # 20 + 21 + 26: LMM cache written, then loaded
+    cache = str(tmp_path / 'lmm.cache')
+    out, err = _run_cli(fixed + ['--similarity', G('similarity50.tsv'), '--lmm', '--save-lmm', cache], monkeypatch)
+    _compare('20', out, err)
+    out, err = _run_cli(fixed + ['--lmm', '--load-lmm', cache + '.npz'], monkeypatch)
+    _compare('21', out, err)
+    out, err = _run_cli(fixed + ['--lmm', '--load-lmm', cache + '.npz', '--cpu', '2'], monkeypatch)
+    _compare('26', out, err)
