@@ -173,7 +173,25 @@ def variant_stream(infile, p, var_type, burden=False, burden_regions=None, sampl
     return rows, err.getvalue()
 
 
+def int_fixtures():
+    """run_test.sh:52 ("sample names are all integers"): the reference's fixtures restricted to the 50
+    phenotyped samples, as gen_golden.py does for the named ones."""
+    import shutil
+    t = os.path.join(REF, 'tests')
+    shutil.copy(os.path.join(t, 'subset_int.pheno'), os.path.join(GOLDEN, 'subset_int.pheno'))
+    shutil.copy(os.path.join(t, 'kmers_int.gz'), os.path.join(GOLDEN, 'kmers_int.gz'))
+    for c in ('30.log', '30.err'):
+        shutil.copy(os.path.join(t, 'baseline', c), os.path.join(GOLDEN, 'baseline', c))
+    ph = pd.read_csv(os.path.join(t, 'subset_int.pheno'), sep='\t', index_col=0)
+    keep = [str(x) for x in ph.index]
+    d = pd.read_csv(os.path.join(t, 'distances_int.tsv.gz'), sep='\t', index_col=0)
+    d.index = d.index.astype(str)
+    d.columns = d.columns.astype(str)
+    d.loc[keep, keep].to_csv(os.path.join(GOLDEN, 'distances50_int.tsv'), sep='\t')
+
+
 def main():
+    int_fixtures()
     out = {}
     out['format_output'] = format_output_cases()
     out['hash_pattern'] = hash_cases()

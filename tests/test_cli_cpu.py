@@ -299,3 +299,11 @@ def test_more_reference_invocations(tmp_path, monkeypatch):
     _compare('21', out, err)
     out, err = _run_cli(fixed + ['--lmm', '--load-lmm', cache + '.npz', '--cpu', '2'], monkeypatch)
     _compare('26', out, err)
+
+
+def test_integer_sample_names(monkeypatch):
+    """run_test.sh:52: sample names that are all integers stay strings through every loader."""
+    G = lambda f: os.path.join(GOLDEN, f)
+    out, err = _run_cli(['--kmers', G('kmers_int.gz'), '--phenotypes', G('subset_int.pheno'), '--distances',
+                         G('distances50_int.tsv')], monkeypatch)
+    _compare('30', out, err)
