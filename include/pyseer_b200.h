@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PSB_ABI_VERSION 1
+#define PSB_ABI_VERSION 2
 
 typedef enum psb_status {
     PSB_OK = 0,
@@ -294,14 +294,17 @@ int psb_launch_count(psb_ctx *ctx, int64_t *n);
 /* Fills a library-owned device buffer with seeded Bernoulli(af_s) rows, af_s ~
  * U(af_lo, af_hi); variant id = first_variant + row (counter-based, so shards do not
  * depend on the GPU count).  planted_every > 0 plants a phenotype-correlated variant at
- * ids divisible by it (needs y_sign: N int8 of +1/-1/0, host pointer).  The rows are
+ * ids divisible by it (needs y_sign: N int8 of +1/-1/0, host pointer); separated_every > 0 makes
+ * ids = separated_every / 2 (mod separated_every) rare variants carried by positive-sign samples
+ * only (an empty cell of the 2x2 table: 'bad-chisq' -> Firth regression, model.py:326).  The rows are
  * left submitted (as by psb_submit_device).  Same generator on host: psb_synth_host. */
 int psb_synth_device(psb_ctx *ctx, uint64_t seed, int64_t first_variant,
                      int64_t n_variants, int32_t n_samples, double af_lo, double af_hi,
-                     int32_t planted_every, const int8_t *y_sign);
+                     int32_t planted_every, int32_t separated_every, const int8_t *y_sign);
 int psb_synth_host(uint64_t seed, int64_t first_variant, int64_t n_variants,
                    int32_t n_samples, double af_lo, double af_hi, int32_t planted_every,
-                   const int8_t *y_sign, uint32_t *out_bits, int32_t words_per_row);
+                   int32_t separated_every, const int8_t *y_sign, uint32_t *out_bits,
+                   int32_t words_per_row);
 
 /* ---- host-evaluated special functions (same code the kernels run; CPU tests) ---- */
 double psb_host_chi2_sf1(double x);                 /* scipy.stats.chi2.sf(x, 1)        */

@@ -96,6 +96,36 @@ def logit_newton(X, y, start, maxiter=35, tol=1e-8, raise_perfect=True):
     return LogitRes(new, bse, logit_loglike(new, X, y), it, it < maxiter)
 
 
+def logit_powell(X, y, start, maxiter=35, raise_perfect=True):
+    """statsmodels ``Logit(y, X).fit(start_params=start, method='powell')`` -- base/optimizer.py:
+    _fit_powell: ``scipy.optimize.fmin_powell(f, start, xtol=1e-4, ftol=1e-4, maxiter=maxiter,
+    maxfun=None, callback=...)`` on ``f = -loglike / nobs`` (maxiter is DiscreteModel.fit's default
+    35); the perfect-prediction callback runs after every Powell iteration.  Afterwards
+    base/model.py:fit inverts the hessian through ``eigh`` and, when it is not positive definite,
+    warns and leaves the result without bse (NaN here).  Call site: model.py:132-137."""
+    from scipy import optimize
+    _check_design(X, y)
+    n = X.shape[0]
+
+    def f(b):
+        return -logit_loglike(b, X, y) / n
+
+    def cb(b):
+        if raise_perfect and np.allclose(_cdf(X.dot(b)) - y, 0):
+            raise PerfectSeparationError()
+
+    out = optimize.fmin_powell(f, np.asarray(start, dtype=float), xtol=1e-4, ftol=1e-4,
+                               maxiter=maxiter, maxfun=None, full_output=1, disp=0, callback=cb)
+    params = np.asarray(out[0], dtype=float).reshape(-1)
+    bse = np.full(params.shape[0], np.nan)
+    H = -logit_hessian(params, X)
+    if np.all(np.isfinite(H)):
+        ev, evec = np.linalg.eigh(H)
+        if ev.min() > 0:
+            bse = np.sqrt(np.diag(evec.dot(np.diag(1.0 / ev)).dot(evec.T)))
+    return LogitRes(params, bse, logit_loglike(params, X, y), out[3], out[5] == 0)
+
+
 OLSRes = namedtuple('OLSRes', ['params', 'bse', 'pvalues', 'df_resid', 'llf'])
 
 
@@ -224,7 +254,12 @@ def fit_null(p, m, cov, continuous, firth=False):
             if firth_res is None:
                 return None
             return firth_res[4]
-        return logit_newton(v, p, start_vec)
+        try:
+            return logit_newton(v, p, start_vec)
+        except np.linalg.LinAlgError:
+            # model.py:132-137: "Null fit with default optimiser may fail, Powell optimizer
+            # might work"
+            return logit_powell(v, p, start_vec)
     except (np.linalg.LinAlgError, PerfectSeparationError, MissingDataError):
         return None
 

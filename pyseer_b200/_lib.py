@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libpyseer_b200.so')
 
 PSB_OK = 0
+ABI_VERSION = 2
 PSB_ERR_CUDA, PSB_ERR_ARG, PSB_ERR_STATE, PSB_ERR_H2, PSB_ERR_NOMEM, PSB_ERR_UNSUPPORTED = \
     -1, -2, -3, -4, -5, -6
 
@@ -94,6 +95,9 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     dp = POINTER(c_double)
     lib.psb_abi_version.restype = c_int
+    if lib.psb_abi_version() != ABI_VERSION:
+        raise LibraryMissing('%s has ABI version %d, this package needs %d: rebuild it'
+                             % (LIB_PATH, lib.psb_abi_version(), ABI_VERSION))
     lib.psb_last_error.restype = c_char_p
     lib.psb_device_count.argtypes = [POINTER(c_int)]
     lib.psb_create.argtypes = [c_int, POINTER(c_void_p)]
@@ -145,9 +149,9 @@ def load():
                                     c_double]
     lib.psb_kinship_fetch.argtypes = [c_void_p, dp]
     lib.psb_synth_device.argtypes = [c_void_p, c_uint64, c_int64, c_int64, c_int32, c_double,
-                                     c_double, c_int32, POINTER(c_int8)]
+                                     c_double, c_int32, c_int32, POINTER(c_int8)]
     lib.psb_synth_host.argtypes = [c_uint64, c_int64, c_int64, c_int32, c_double, c_double,
-                                   c_int32, POINTER(c_int8), POINTER(c_uint32), c_int32]
+                                   c_int32, c_int32, POINTER(c_int8), POINTER(c_uint32), c_int32]
     for f in ('psb_host_chi2_sf1',):
         getattr(lib, f).restype = c_double
         getattr(lib, f).argtypes = [c_double]

@@ -120,7 +120,7 @@ int psb_destroy(psb_ctx *c) {
         cudaEventDestroy(c->ev_copy[i]); cudaEventDestroy(c->ev_used[i]);
     }
     cudaStreamDestroy(c->copy_stream);
-    free_dev(c->own_bits); free_dev(c->own_miss); free_dev(c->d_counters);
+    free_dev(c->own_bits); free_dev(c->own_miss); free_dev(c->d_counters); free_dev(c->d_gen_scratch);
     cudaEventDestroy(c->ev_run0); cudaEventDestroy(c->ev_run1);
     cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev_user[i]);

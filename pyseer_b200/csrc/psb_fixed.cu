@@ -105,6 +105,51 @@ __device__ __forceinline__ double fx_chol_logdet(const double (&L)[Tri<PP>::SIZE
     return -2.0 * s;
 }
 
+// Cholesky for the Firth path: also refuses pivots below 1e-13 of the largest diagonal entry, so
+// that (numerically) singular information matrices take the pinv / det route of the reference
+// (psb_sym_pinv_logdet, psb_fixed.cuh) instead of being inverted through a meaningless pivot.
+template <int PP>
+__device__ __forceinline__ bool fx_chol_firth(double (&A)[Tri<PP>::SIZE]) {
+    double dmax = 0.0;
+#pragma unroll
+    for (int j = 0; j < PP; ++j) dmax = fmax(dmax, A[Tri<PP>::at(j, j)]);
+    bool ok = isfinite(dmax);
+    const double floor_ = 1e-13 * dmax;
+#pragma unroll
+    for (int j = 0; j < PP; ++j) {
+        const double d = A[Tri<PP>::at(j, j)];
+        if (!(d > floor_)) ok = false;
+        const double inv = rsqrt(d);
+        A[Tri<PP>::at(j, j)] = inv;
+#pragma unroll
+        for (int i = 0; i < PP; ++i)
+            if (i > j) A[Tri<PP>::at(i, j)] *= inv;
+#pragma unroll
+        for (int i = 0; i < PP; ++i)
+#pragma unroll
+            for (int k = 0; k < PP; ++k)
+                if (i > j && k > j && k <= i)
+                    A[Tri<PP>::at(i, k)] = fma(-A[Tri<PP>::at(i, j)], A[Tri<PP>::at(k, j)], A[Tri<PP>::at(i, k)]);
+    }
+    return ok;
+}
+
+// Singular H: pinv (when WANT_V) and log det by eigendecomposition, through local-memory copies so
+// that the caller's arrays stay in registers.
+template <int PP, bool WANT_V>
+__device__ __forceinline__ double fx_singular(const double (&H)[Tri<PP>::SIZE], double (&V)[Tri<PP>::SIZE],
+                                              int p_active) {
+    double Hl[Tri<PP>::SIZE], Vl[Tri<PP>::SIZE], A[PP * PP], Q[PP * PP];
+#pragma unroll
+    for (int e = 0; e < Tri<PP>::SIZE; ++e) Hl[e] = H[e];
+    const double ld = psb_sym_pinv_logdet(Hl, WANT_V ? Vl : nullptr, PP, p_active, A, Q);
+    if (WANT_V) {
+#pragma unroll
+        for (int e = 0; e < Tri<PP>::SIZE; ++e) V[e] = Vl[e];
+    }
+    return ld;
+}
+
 // statsmodels' Newton step matrix X'WX/n - 1e-10 I (the ridge lands on the NEGATIVE definite
 // hessian, base/model.py:fit + base/optimizer.py:_fit_newton) can turn indefinite in separated
 // data, where the reference's LU solve simply carries on.  L D L' without pivoting solves the
@@ -286,8 +331,7 @@ __device__ __forceinline__ void fx_publish(const FxArgs &a, int v, uint32_t f, c
                                            double bse, double fit_llf, double null_llf) {
     const double lrstat = -2.0 * (null_llf - fit_llf);          // model.py:336, :366
     double p = 1.0;
-    if (lrstat > 0.0) p = psb_chi2_sf1(lrstat);
-    else if (isnan(lrstat)) p = lrstat;
+    if (lrstat > 0.0) p = psb_chi2_sf1(lrstat);      // NaN compares false: p stays 1, as in the reference
     double kbeta = 0.0;
 #pragma unroll
     for (int c = 0; c < PP; ++c)
@@ -450,7 +494,7 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
             bse_x = fast_bse;
         } else if (!fail) {
             // bse = sqrt(diag(inv(X'WX))) at the final parameters (H holds X'WX there)
-            if (!fx_chol<PP>(H)) {
+            if (!fx_chol_firth<PP>(H)) {       // numpy.linalg.inv: 'Singular matrix'
                 fail = PSB_F_MATRIX_INV;
             } else if (a.has_x) {
                 double e[PP];
@@ -530,10 +574,18 @@ k_fixed_firth(FxArgs a, int n_list) {
         double fl_cur, fitll = NAN, hxx_fit = NAN;
         double last_step_norm = INFINITY;      // || betas[i] - betas[i-1] ||
         for (int i = 0; i < 1000 && ok; ++i) {
-            if (!fx_chol<PP>(H)) { ok = false; break; }
-            const double logdet = fx_chol_logdet<PP>(H);
+            double logdet;
+            if (fx_chol_firth<PP>(H)) {
+                logdet = fx_chol_logdet<PP>(H);
+                fx_inverse_from_chol<PP>(H, V);        // V = pinv(-hessian), model.py:450
+            } else {
+                // singular information matrix: np.linalg.pinv / det carry on (model.py:450, :410);
+                // the factorisation ran in place, so X'WX is evaluated again first
+                fx_eval<PP>(a, xrow, lane, beta, H, g, maxdev, llf_cur, true);
+                logdet = fx_singular<PP, true>(H, V, p);
+                if (isnan(V[0])) { ok = false; break; }
+            }
             fl_cur = -(llf_cur + 0.5 * logdet);
-            fx_inverse_from_chol<PP>(H, V);            // V = pinv(-hessian), model.py:450
             // U = X'(y - pi + h (1/2 - pi)),  h_i = w_i x_i' V x_i   (model.py:455-466)
             double U[PP];
 #pragma unroll
@@ -585,8 +637,9 @@ k_fixed_firth(FxArgs a, int n_list) {
                 // log det via a scratch Cholesky (V is free to be reused as scratch)
 #pragma unroll
                 for (int e = 0; e < Tri<PP>::SIZE; ++e) V[e] = H[e];
-                double ld = NAN;
-                if (fx_chol<PP>(V)) ld = fx_chol_logdet<PP>(V);
+                double ld;
+                if (fx_chol_firth<PP>(V)) ld = fx_chol_logdet<PP>(V);
+                else ld = fx_singular<PP, false>(H, V, p);
                 fl_new = -(llf_new + 0.5 * ld);
                 if (!(fl_new > fl_cur)) break;
 #pragma unroll
@@ -696,7 +749,7 @@ k_fixed_lineage(FxArgs a, const int32_t *__restrict__ idx, int n_tested, int mod
             ++it;
         }
         int best = -1;
-        if (!fail && fx_chol<PP>(H)) {
+        if (!fail && fx_chol_firth<PP>(H)) {
             double bestval = -INFINITY;
             bool seen_nan = false;
 #pragma unroll

@@ -34,6 +34,85 @@ struct FxArgs {
 };
 
 
+// Singular information matrices in Firth regression.  model.fit_firth calls np.linalg.pinv on
+// -hessian (model.py:450) and firth_likelihood takes log(det(-hessian)) (model.py:410): with an
+// exactly collinear design (the reference's own test has variant == covariate,
+// tests/model_test.py:316-338) neither raises -- pinv drops the null directions (singular values
+// <= 1e-15 sigma_max), det is 0 and the penalised likelihood becomes -log(0) = +inf, which no
+// comparison of the step-halving loop ever finds "worse".  This routine restates both for a
+// symmetric matrix given as its packed lower triangle: cyclic Jacobi eigendecomposition in the
+// caller's scratch (A, Q: P x P doubles each, any address space; p_active = columns in use), V = sum_{|l_i| > cut} q_i q_i' / l_i
+// (packed, when V != nullptr) and the return value log det = sum log l_i, -inf when an eigenvalue
+// falls under the pinv cut-off, NaN when one is negative beyond it.  A rare path (the Cholesky
+// factorisation of the caller failed or met a pivot below 1e-13 of the diagonal): one thread.
+static __device__ __noinline__ double psb_sym_pinv_logdet(const double *Hp, double *Vp, int P, int p_active, double *A,
+                                                    double *Q) {
+    for (int i = 0; i < P; ++i)
+        for (int j = 0; j < P; ++j) {
+            A[i * P + j] = Hp[i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i];
+            Q[i * P + j] = i == j ? 1.0 : 0.0;
+        }
+    bool finite = true;
+    for (int e = 0; e < P * P; ++e) finite = finite && isfinite(A[e]);
+    if (!finite) {
+        if (Vp) for (int e = 0; e < P * (P + 1) / 2; ++e) Vp[e] = NAN;
+        return NAN;
+    }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0, dia = 0.0;
+        for (int i = 0; i < P; ++i) {
+            dia = fma(A[i * P + i], A[i * P + i], dia);
+            for (int j = 0; j < i; ++j) off = fma(A[i * P + j], A[i * P + j], off);
+        }
+        if (off <= 1e-36 * dia || off == 0.0) break;
+        for (int p = 0; p < P - 1; ++p)
+            for (int q = p + 1; q < P; ++q) {
+                const double apq = A[p * P + q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q * P + q] - A[p * P + p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                const double c = rsqrt(fma(t, t, 1.0)), sn = t * c;
+                for (int k = 0; k < P; ++k) {            // columns p, q
+                    const double akp = A[k * P + p], akq = A[k * P + q];
+                    A[k * P + p] = c * akp - sn * akq;
+                    A[k * P + q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < P; ++k) {            // rows p, q
+                    const double apk = A[p * P + k], aqk = A[q * P + k];
+                    A[p * P + k] = c * apk - sn * aqk;
+                    A[q * P + k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < P; ++k) {
+                    const double qkp = Q[k * P + p], qkq = Q[k * P + q];
+                    Q[k * P + p] = c * qkp - sn * qkq;
+                    Q[k * P + q] = sn * qkp + c * qkq;
+                }
+            }
+    }
+    // (columns >= p_active are the solver's padding: unit diagonal, decoupled, never rotated)
+    double lmax = 0.0;
+    for (int i = 0; i < p_active; ++i) lmax = fmax(lmax, fabs(A[i * P + i]));
+    const double cut = 1e-15 * lmax;                     // numpy.linalg.pinv default rcond
+    double logdet = 0.0;
+    for (int i = 0; i < p_active; ++i) {
+        const double l = A[i * P + i];
+        if (fabs(l) <= cut) logdet = isnan(logdet) ? logdet : -INFINITY;
+        else if (l < 0.0) logdet = NAN;
+        else logdet += log(l);
+    }
+    if (Vp)
+        for (int i = 0; i < P; ++i)
+            for (int j = 0; j <= i; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < P; ++k) {
+                    const double l = A[k * P + k];
+                    if (fabs(l) > cut || k >= p_active) acc = fma(Q[i * P + k] / l, Q[j * P + k], acc);
+                }
+                Vp[i * (i + 1) / 2 + j] = acc;
+            }
+    return logdet;
+}
+
 // modes of the generic kernel
 #define FXG_LOGIT 0     // variant fit: Logit Newton + LRT, failures pushed to the Firth list
 #define FXG_FIRTH 1     // Firth regression over the Firth list

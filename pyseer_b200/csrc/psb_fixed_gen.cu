@@ -113,11 +113,11 @@ __device__ void gen_eval(const FxArgs &a, const GenWs &ws, const uint32_t *xrow,
 
 // In-place right-looking Cholesky of the packed matrix (diagonal stored as 1 / L_jj); returns
 // false when a pivot is not positive / finite.
-__device__ bool gen_chol(double *A, int P, int lane) {
+__device__ bool gen_chol(double *A, int P, int lane, double floor_abs = 0.0) {
     bool ok = true;
     for (int j = 0; j < P; ++j) {
         const double d = A[tri_at(j, j)];
-        if (!(d > 0.0) || !isfinite(d)) ok = false;
+        if (!(d > floor_abs) || !isfinite(d)) ok = false;
         const double inv = rsqrt(d);
         __syncwarp();
         if (lane == 0) A[tri_at(j, j)] = inv;
@@ -210,7 +210,7 @@ __device__ void gen_publish(const FxArgs &a, int v, uint32_t f, const double *be
     const double lrstat = -2.0 * (null_llf - fit_llf);
     double p = 1.0;
     if (lrstat > 0.0) p = psb_chi2_sf1(lrstat);
-    else if (isnan(lrstat)) p = lrstat;
+    // (a NaN statistic compares false and leaves p = 1, as in the reference)
     const double kbeta = beta[a.q];
     if (p > a.lrt_pvalue || !isfinite(p) || !isfinite(kbeta)) {
         f |= PSB_F_LRT_FAILED | PSB_F_FILTER;
@@ -224,9 +224,28 @@ __device__ void gen_publish(const FxArgs &a, int v, uint32_t f, const double *be
     a.flags[v] = f;
 }
 
+// Firth path: pivots below 1e-13 of the largest diagonal entry count as singular (fx_chol_firth)
+__device__ bool gen_chol_firth(double *A, int P, int lane) {
+    double dmax = 0.0;
+    for (int j = 0; j < P; ++j) dmax = fmax(dmax, A[tri_at(j, j)]);
+    if (!isfinite(dmax)) return false;
+    return gen_chol(A, P, lane, 1e-13 * dmax);
+}
+
+// Singular information matrix (psb_sym_pinv_logdet, psb_fixed.cuh): lane 0 works in the design-tile
+// area of the warp's shared memory (A) and the warp's global scratch (Q).
+__device__ double gen_singular(const GenWs &ws, double *Vout, int p, double *scratchQ, int lane) {
+    double ld = 0.0;
+    __syncwarp();
+    if (lane == 0) ld = psb_sym_pinv_logdet(ws.H, Vout, ws.P, p, ws.zt, scratchQ);
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, ld, 0);
+}
+
 __global__ void __launch_bounds__(FXG_WARPS * 32)
 k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode, int P, int lineage_mode,
-                int n_lin, const int32_t *__restrict__ nmissing, int32_t *__restrict__ lineage_out) {
+                int n_lin, const int32_t *__restrict__ nmissing, int32_t *__restrict__ lineage_out,
+                double *__restrict__ scratch) {
     extern __shared__ __align__(16) double gsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     GenWs ws;
@@ -249,6 +268,7 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
     const int p = a.q + (a.has_x ? 1 : 0);
     const int warps_total = gridDim.x * FXG_WARPS;
     const double inv_n = 1.0 / (double)a.N;
+    double *scratchQ = scratch ? scratch + (size_t)(blockIdx.x * FXG_WARPS + warp) * P * P : nullptr;
 
     for (int t = blockIdx.x * FXG_WARPS + warp; t < n_items; t += warps_total) {
         int v = 0;
@@ -288,14 +308,22 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
             gen_eval(a, ws, xrow, yrow, lane, ws.beta, p, maxdev, llf_cur);
             double hxx_new = 0.0;
             for (int i = 0; i < 1000 && ok; ++i) {
-                if (!gen_chol(ws.H, P, lane)) { ok = false; break; }
-                fl_cur = -(llf_cur + 0.5 * gen_logdet(ws.H, P));
-                // V = (L L')^-1, column by column (only the lower triangle is kept)
-                for (int c0 = 0; c0 < P; ++c0) {
-                    for (int c = lane; c < P; c += 32) ws.tmp[c] = (c == c0) ? 1.0 : 0.0;
-                    gen_solve(ws.H, ws.tmp, P, lane);
-                    for (int c = c0 + lane; c < P; c += 32) ws.V[tri_at(c, c0)] = ws.tmp[c];
-                    __syncwarp();
+                if (gen_chol_firth(ws.H, P, lane)) {
+                    fl_cur = -(llf_cur + 0.5 * gen_logdet(ws.H, P));
+                    // V = (L L')^-1, column by column (only the lower triangle is kept)
+                    for (int c0 = 0; c0 < P; ++c0) {
+                        for (int c = lane; c < P; c += 32) ws.tmp[c] = (c == c0) ? 1.0 : 0.0;
+                        gen_solve(ws.H, ws.tmp, P, lane);
+                        for (int c = c0 + lane; c < P; c += 32) ws.V[tri_at(c, c0)] = ws.tmp[c];
+                        __syncwarp();
+                    }
+                } else {
+                    // singular information matrix: pinv / det as the reference (model.py:450, :410);
+                    // the factorisation ran in place, so X'WX is evaluated again first
+                    gen_eval(a, ws, xrow, yrow, lane, ws.beta, p, maxdev, llf_cur);
+                    const double ld0 = gen_singular(ws, ws.V, p, scratchQ, lane);
+                    if (isnan(ws.V[0])) { ok = false; break; }
+                    fl_cur = -(llf_cur + 0.5 * ld0);
                 }
                 // U = X'(y - pi + h (1/2 - pi)),  h_i = w_i x_i' V x_i
                 for (int c = lane; c < P; c += 32) ws.U[c] = 0.0;
@@ -356,8 +384,9 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
                     hxx_new = a.has_x ? ws.H[tri_at(a.q, a.q)] : 0.0;
                     for (int e = lane; e < ws.tri; e += 32) ws.V[e] = ws.H[e];
                     __syncwarp();
-                    double ld = NAN;
-                    if (gen_chol(ws.V, P, lane)) ld = gen_logdet(ws.V, P);
+                    double ld;
+                    if (gen_chol_firth(ws.V, P, lane)) ld = gen_logdet(ws.V, P);
+                    else ld = gen_singular(ws, nullptr, p, scratchQ, lane);
                     fl_new = -(llf_new + 0.5 * ld);
                     if (!(fl_new > fl_cur)) break;
                     __syncwarp();
@@ -433,7 +462,7 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
         // factor X'WX at the final parameters for the standard errors
         bool have_factor = false;
         if (!fail) {
-            have_factor = gen_chol(ws.H, P, lane);
+            have_factor = gen_chol_firth(ws.H, P, lane);
             if (!have_factor) fail = PSB_F_MATRIX_INV;
         }
         if (mode == FXG_LINEAGE) {
@@ -509,8 +538,22 @@ int psb_fixed_gen_launch(psb_ctx *c, const FxArgs &a, int mode, int n, int linea
     const size_t smem = per_warp * FXG_WARPS * sizeof(double);
     PSB_CUDA(cudaFuncSetAttribute(k_fixed_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::min(psb_div_up(n, FXG_WARPS), c->sm_count * 4);
+    double *scratch = nullptr;
+    if (mode == FXG_FIRTH || mode == FXG_NULL_FIRTH) {
+        // per-warp P x P scratch of the singular-matrix path (gen_singular)
+        const size_t need = (size_t)grid * FXG_WARPS * P * P * sizeof(double);
+        if (need > c->gen_scratch_cap) {
+            PSB_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->d_gen_scratch) cudaFree(c->d_gen_scratch);
+            c->d_gen_scratch = nullptr;
+            c->gen_scratch_cap = 0;
+            PSB_CUDA(cudaMalloc(&c->d_gen_scratch, need));
+            c->gen_scratch_cap = need;
+        }
+        scratch = c->d_gen_scratch;
+    }
     k_fixed_generic<<<grid, FXG_WARPS * 32, smem, c->stream>>>(a, c->d_idx, n, mode, P, lineage_mode,
-                                                              n_lin, c->d_missing, lineage_out);
+                                                              n_lin, c->d_missing, lineage_out, scratch);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
     return PSB_OK;

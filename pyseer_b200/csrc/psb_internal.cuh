@@ -140,6 +140,8 @@ struct psb_ctx {
     size_t sums_cap = 0;
     int32_t *d_idx = nullptr;     // compacted tested variant ids (cap + 256)
     int32_t *d_idx2 = nullptr;    // second list (Firth candidates)
+    double *d_gen_scratch = nullptr;   // generic solver: per-warp scratch of the singular-matrix path
+    size_t gen_scratch_cap = 0;
     int *d_counters = nullptr;    // [8] device counters
     int32_t *d_lineage = nullptr; // [cap] index of the strongest lineage, -1 = None
     double *d_a = nullptr;        // [cap] quadratic forms

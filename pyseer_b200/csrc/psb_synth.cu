@@ -17,19 +17,25 @@ struct psb_synth_row {
     uint64_t key;
     double af;
     double delta;   // 0 unless planted
+    double sep;     // 0 unless "separated": carried by positive-sign samples only, with this probability
 };
 
 __host__ __device__ __forceinline__ psb_synth_row psb_synth_rowinfo(uint64_t seed, int64_t vid,
                                                                     double af_lo, double af_hi,
-                                                                    int planted_every) {
+                                                                    int planted_every, int separated_every) {
     psb_synth_row r;
     r.key = psb_mix64(seed ^ psb_mix64((uint64_t)vid));
     double u = (double)(r.key >> 11) * (1.0 / 9007199254740992.0);
     r.af = af_lo + (af_hi - af_lo) * u;
     r.delta = 0.0;
+    r.sep = 0.0;
     if (planted_every > 0 && vid % planted_every == 0) {
         r.af = 0.5;
         r.delta = 0.30 * (double)((r.key >> 3) & 0xFFFFull) * (1.0 / 65536.0);
+    } else if (separated_every > 0 && vid % separated_every == separated_every / 2) {
+        // rare variant found in positive-sign samples only (a k-mer private to a clade of cases):
+        // an empty cell of the 2x2 table -> 'bad-chisq' -> Firth regression (model.py:326, 355)
+        r.sep = 0.02 + 0.04 * (double)((r.key >> 19) & 0xFFFFull) * (1.0 / 65536.0);
     }
     return r;
 }
@@ -46,6 +52,7 @@ __host__ __device__ __forceinline__ uint32_t psb_synth_word(const psb_synth_row 
             uint32_t u32 = e ? (uint32_t)(z >> 32) : (uint32_t)z;
             double p = r.af;
             if (r.delta != 0.0 && y_sign) p += r.delta * (double)y_sign[i];
+            if (r.sep != 0.0 && y_sign) p = y_sign[i] > 0 ? r.sep : 0.0;
             double thr = p * 4294967296.0;
             uint32_t t = thr >= 4294967295.0 ? 0xFFFFFFFFu : (thr <= 0.0 ? 0u : (uint32_t)thr);
             if (u32 < t) out |= 1u << (h * 2 + e);
@@ -56,7 +63,7 @@ __host__ __device__ __forceinline__ uint32_t psb_synth_word(const psb_synth_row 
 
 __global__ void k_synth(uint32_t *__restrict__ bits, int64_t n_variants, int Wrow, int N,
                         uint64_t seed, int64_t first, double af_lo, double af_hi,
-                        int planted_every, const int8_t *__restrict__ y_sign) {
+                        int planted_every, int separated_every, const int8_t *__restrict__ y_sign) {
     int64_t total = n_variants * Wrow;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
@@ -64,7 +71,7 @@ __global__ void k_synth(uint32_t *__restrict__ bits, int64_t n_variants, int Wro
         int w = (int)(e - s * Wrow);
         uint32_t word = 0;
         if (w * 32 < N) {
-            psb_synth_row r = psb_synth_rowinfo(seed, first + s, af_lo, af_hi, planted_every);
+            psb_synth_row r = psb_synth_rowinfo(seed, first + s, af_lo, af_hi, planted_every, separated_every);
             word = psb_synth_word(r, w, N, y_sign);
         }
         bits[e] = word;
@@ -73,11 +80,11 @@ __global__ void k_synth(uint32_t *__restrict__ bits, int64_t n_variants, int Wro
 
 extern "C" int psb_synth_device(psb_ctx *c, uint64_t seed, int64_t first_variant, int64_t n_variants,
                                 int32_t n_samples, double af_lo, double af_hi,
-                                int32_t planted_every, const int8_t *y_sign) {
+                                int32_t planted_every, int32_t separated_every, const int8_t *y_sign) {
     PSB_REQUIRE(c, PSB_ERR_ARG, "ctx is NULL");
     PSB_REQUIRE(c->model != PSB_MODEL_NONE && n_samples == c->N, PSB_ERR_STATE,
                 "psb_synth_device needs a model set up with the same n_samples");
-    PSB_REQUIRE(planted_every <= 0 || y_sign, PSB_ERR_ARG, "planted variants need y_sign");
+    PSB_REQUIRE((planted_every <= 0 && separated_every <= 0) || y_sign, PSB_ERR_ARG, "planted variants need y_sign");
     PSB_CUDA(cudaSetDevice(c->device));
     int Wrow = ((c->Wn + 3) / 4) * 4;
     size_t bytes = (size_t)n_variants * Wrow * sizeof(uint32_t);
@@ -97,7 +104,7 @@ extern "C" int psb_synth_device(psb_ctx *c, uint64_t seed, int64_t first_variant
     if (n_variants > 0) {
         k_synth<<<c->sm_count * 8, 256, 0, c->stream>>>(c->own_bits, n_variants, Wrow, n_samples,
                                                        seed, first_variant, af_lo, af_hi,
-                                                       planted_every, d_sign);
+                                                       planted_every, separated_every, d_sign);
         c->launches++;
         PSB_CUDA(cudaGetLastError());
     }
@@ -114,13 +121,13 @@ extern "C" int psb_synth_device(psb_ctx *c, uint64_t seed, int64_t first_variant
 
 extern "C" int psb_synth_host(uint64_t seed, int64_t first_variant, int64_t n_variants,
                               int32_t n_samples, double af_lo, double af_hi,
-                              int32_t planted_every, const int8_t *y_sign, uint32_t *out_bits,
-                              int32_t words_per_row) {
+                              int32_t planted_every, int32_t separated_every, const int8_t *y_sign,
+                              uint32_t *out_bits, int32_t words_per_row) {
     PSB_REQUIRE(out_bits, PSB_ERR_ARG, "out_bits is NULL");
     PSB_REQUIRE(words_per_row * 32 >= n_samples, PSB_ERR_ARG, "words_per_row too small");
-    PSB_REQUIRE(planted_every <= 0 || y_sign, PSB_ERR_ARG, "planted variants need y_sign");
+    PSB_REQUIRE((planted_every <= 0 && separated_every <= 0) || y_sign, PSB_ERR_ARG, "planted variants need y_sign");
     for (int64_t s = 0; s < n_variants; ++s) {
-        psb_synth_row r = psb_synth_rowinfo(seed, first_variant + s, af_lo, af_hi, planted_every);
+        psb_synth_row r = psb_synth_rowinfo(seed, first_variant + s, af_lo, af_hi, planted_every, separated_every);
         for (int w = 0; w < words_per_row; ++w)
             out_bits[s * words_per_row + w] = (w * 32 < n_samples) ? psb_synth_word(r, w, n_samples, y_sign) : 0u;
     }

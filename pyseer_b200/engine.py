@@ -269,13 +269,14 @@ class Engine(object):
         self.n_variants = int(n_variants)
 
     def synth_device(self, seed, first_variant, n_variants, af_lo=0.02, af_hi=0.98,
-                     planted_every=0, y_sign=None):
+                     planted_every=0, y_sign=None, separated_every=0):
         ys = None
         if y_sign is not None:
             y_sign = np.ascontiguousarray(y_sign, dtype=np.int8)
             ys = y_sign.ctypes.data_as(ctypes.POINTER(c_int8))
         check(self.lib.psb_synth_device(self._ctx, int(seed), int(first_variant), int(n_variants),
-                                        self.n_samples, af_lo, af_hi, int(planted_every), ys))
+                                        self.n_samples, af_lo, af_hi, int(planted_every),
+                                        int(separated_every), ys))
         self.n_variants = int(n_variants)
 
     # -- run ---------------------------------------------------------------------------
@@ -396,7 +397,7 @@ def device_count():
 
 
 def synth_host(seed, first_variant, n_variants, n_samples, af_lo=0.02, af_hi=0.98,
-               planted_every=0, y_sign=None):
+               planted_every=0, y_sign=None, separated_every=0):
     """Host twin of Engine.synth_device (same generator, same rows)."""
     lib = _lib.load()
     W = words_per_row(n_samples)
@@ -406,6 +407,6 @@ def synth_host(seed, first_variant, n_variants, n_samples, af_lo=0.02, af_hi=0.9
         y_sign = np.ascontiguousarray(y_sign, dtype=np.int8)
         ys = y_sign.ctypes.data_as(ctypes.POINTER(c_int8))
     check(lib.psb_synth_host(int(seed), int(first_variant), int(n_variants), int(n_samples),
-                             af_lo, af_hi, int(planted_every), ys,
+                             af_lo, af_hi, int(planted_every), int(separated_every), ys,
                              out.ctypes.data_as(ctypes.POINTER(c_uint32)), W))
     return out

@@ -59,6 +59,10 @@ def fit_null(p, m, cov, continuous, firth=False, device=0):
         sys.stderr.write('Perfectly separable data error for null model\n')
         return None
     if st & _lib.F_MATRIX_INV:
+        if not continuous and not firth:
+            # model.py:132-137: "Null fit with default optimiser may fail, Powell optimizer might
+            # work" -- once-per-run host set-up, as the reference does it
+            return _powell_null(v, p)
         sys.stderr.write('Matrix inversion error for null model\n')
         return None
     if firth:
@@ -67,6 +71,42 @@ def fit_null(p, m, cov, continuous, firth=False, device=0):
             return None
         return llf
     return NullFit(params, bse, llf)
+
+
+def _powell_null(v, p):
+    """``Logit.fit(start_params, method='powell')`` of model.py:135-137 -- statsmodels'
+    ``_fit_powell``: scipy's ``fmin_powell`` (xtol = ftol = 1e-4, maxiter 35) on ``-loglike / nobs``
+    with the perfect-prediction check as callback.  The singular information matrix that sent the
+    Newton fit here leaves the result without standard errors (statsmodels warns and carries on)."""
+    from scipy import optimize
+    n = v.shape[0]
+    q = 2.0 * p - 1.0
+
+    def cdf(x):
+        with np.errstate(over='ignore'):
+            return 1.0 / (1.0 + np.exp(-x))
+
+    def loglike(b):
+        with np.errstate(divide='ignore', over='ignore'):
+            return np.sum(np.log(cdf(q * v.dot(b))))
+
+    class _Separated(Exception):
+        pass
+
+    def check(b):
+        if np.allclose(cdf(v.dot(b)) - p, 0):
+            raise _Separated()
+
+    start = np.zeros(v.shape[1])
+    start[0] = np.log(np.mean(p) / (1 - np.mean(p)))
+    try:
+        out = optimize.fmin_powell(lambda b: -loglike(b) / n, start, xtol=1e-4, ftol=1e-4, maxiter=35,
+                                   maxfun=None, full_output=1, disp=0, callback=check)
+    except _Separated:
+        sys.stderr.write('Perfectly separable data error for null model\n')
+        return None
+    params = np.asarray(out[0], dtype=float).reshape(-1)
+    return NullFit(params, np.full(params.shape[0], np.nan), float(loglike(params)))
 
 
 class FixedModel(object):

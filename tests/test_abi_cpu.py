@@ -20,7 +20,7 @@ def test_header_symbols_exported():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.psb_abi_version() == 1
+    assert lib.psb_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly():

@@ -90,10 +90,12 @@ def test_fixed_effects_binary_goldens(goldens, utd):
     mb = pb.reshape(-1, 1).copy()
     s = pm.fixed_effects_regression(p=pb, k=pb.copy(), m=mb, c=NONE, lineage_effects=False,
                                     lin=None, pret=1, lrtt=1, **args)
-    # k == m: exactly collinear design.  The reference ploughs on through pinv / det of a
-    # singular information matrix and returns rounding noise (kbeta -88.7, bse 0.0,
-    # tests/model_test.py:327-335); the device solver reports the singularity instead.
-    assert s.notes == {'bad-chisq', 'firth-fail'} and s.filter and not s.prefilter
+    # k == m: exactly collinear (and separated) design.  The reference goes through pinv / det of
+    # a singular information matrix (model.py:450, :410) and asserts notes == {'bad-chisq'} only
+    # (tests/model_test.py:327-338: the value comparison is commented out there; its numbers are
+    # kbeta -88.7, bse 0.0, lrt-pvalue 1)
+    assert s.notes == {'bad-chisq'} and not s.filter and not s.prefilter
+    assert s.pvalue == 1 and s.bse == 0.0 and np.isfinite(s.kbeta) and np.isfinite(s.intercept)
     s = pm.fixed_effects_regression(p=p, k=k, m=m, c=utd['cov'], lineage_effects=False, lin=None,
                                     pret=1, lrtt=1, **args)
     _check_golden(s, goldens['fe_binary_cov'], set(), False, False)
@@ -256,3 +258,59 @@ def test_batched_lineage_matches_oracle(n_lin, ncov):
         checked += 1
     assert checked > 40 and differ <= 0.1 * checked, (checked, differ)
     model.close()
+
+
+@pytest.mark.parametrize('dims', [2, 14])
+def test_collinear_designs_follow_the_reference(dims):
+    """Variant identical to a binary covariate column: singular information matrix in every fit.
+    Newton ends in numpy's 'Singular matrix' -> 'matrix-inversion-error' -> Firth with pinv / det
+    (model.py:347-350, 355-369, 450, 410); register solver for the narrow design, generic solver for
+    the wide one."""
+    from oracle import fixed_oracle as fo
+    from pyseer_b200 import model as pm, _lib
+    from pyseer_b200.engine import notes_from_flags, pack_rows
+    n = 240
+    m, y, rng = _problem(n, dims, 21, True)
+    m = m.copy()
+    m[:, 1] = (rng.uniform(size=n) < 0.4).astype(float)           # a binary covariate
+    x = np.array([m[:, 1], 1.0 - m[:, 1], (rng.uniform(size=n) < 0.3).astype(float)])
+    bits, _ = pack_rows(x)
+    onull = fo.fit_null(y, m, NONE, False)
+    ofirth = fo.fit_null(y, m, NONE, False, True)
+    model = pm.FixedModel(y, m, NONE, False, onull.llf, float(ofirth))
+    r = pm.run_fixed_bits(model, bits, None, 1.0, 1.0, 0.01, 0.99, 0.05)
+    for s in range(3):
+        o = fo.fixed_effects_regression('v', y, x[s], m, NONE, 0.5, 'p', False, None, 1.0, 1.0,
+                                        onull.llf, ofirth, [], [], False)
+        f = int(r.flags[s])
+        notes = notes_from_flags(f)
+        assert bool(f & _lib.F_FILTER) == o.filter and bool(f & _lib.F_PREFILTER) == o.prefilter
+        if s == 2:
+            assert notes == o.notes == set()
+            assert _rel(r.pvalue[s], o.pvalue) < RTOL and _rel(r.beta[s], o.kbeta) < RTOL
+            continue
+        # Which exit the reference's Newton fit takes on an exactly collinear design is decided by
+        # the last bits of LAPACK's LU: an exact zero pivot raises ('matrix-inversion-error'), a
+        # pivot of 1e-17 gives a huge bse ('high-bse') or a negative variance (NaN bse, no note).
+        # The device solver calls every pivot below 1e-13 of the diagonal singular.  Either note
+        # sends the variant to Firth regression, whose pinv / det path is deterministic:
+        assert notes == {'matrix-inversion-error'}, notes
+        assert o.notes <= {'matrix-inversion-error', 'high-bse'}
+        assert r.pvalue[s] == 1 and (f & _lib.F_FIRTH_USED)
+        if o.notes:
+            assert _rel(r.beta[s], o.kbeta) < 1e-5 and _rel(r.bse[s], o.bse) < 1e-5
+    model.close()
+
+
+def test_null_fit_powell_fallback():
+    """model.py:132-137: a null design with a duplicated column ends Newton in 'Singular matrix';
+    the reference retries with statsmodels' Powell optimiser and carries on."""
+    from oracle import fixed_oracle as fo
+    from pyseer_b200 import model as pm
+    m, y, rng = _problem(200, 3, 5, True)
+    m2 = np.c_[m, m[:, 1]]
+    o = fo.fit_null(y, m2, NONE, False)
+    r = pm.fit_null(y, m2, NONE, False)
+    assert o is not None and r is not None
+    assert abs(r.llf - o.llf) < 1e-9 * abs(o.llf) and np.allclose(r.params, o.params, rtol=1e-9, atol=1e-12)
+    assert abs(r.llf - fo.fit_null(y, m, NONE, False).llf) < 1e-4

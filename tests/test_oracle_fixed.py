@@ -112,3 +112,18 @@ def test_fixed_effects_continuous(goldens, utd):
     _check(s, goldens['fe_cont'], {'lrt-filtering-failed'}, False, True)
     s = fo.fixed_effects_regression(p=p, k=k, m=m, c=utd['cov'], pret=1, lrtt=1, **args)
     _check(s, goldens['fe_cont_cov'], set(), False, False)
+
+
+def test_null_fit_powell_fallback_oracle():
+    """model.py:132-137 restated: Newton's 'Singular matrix' on a duplicated column -> statsmodels'
+    Powell optimiser; the likelihood reaches the value of the fit without the duplicate."""
+    import numpy as np
+    from oracle import fixed_oracle as fo
+    rng = np.random.RandomState(0)
+    n = 200
+    m = rng.uniform(-1, 1, size=(n, 3))
+    y = (m[:, 0] + rng.normal(size=n) > 0).astype(float)
+    none = np.empty((0, 0))
+    a = fo.fit_null(y, m, none, False)
+    b = fo.fit_null(y, np.c_[m, m[:, 1]], none, False)
+    assert b is not None and abs(a.llf - b.llf) < 1e-4 and np.all(np.isnan(b.bse))
