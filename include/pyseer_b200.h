@@ -200,6 +200,42 @@ int psb_results_device(psb_ctx *ctx, psb_results *out_device_ptrs);
  * (__main__.py:831-834 semantics, printed == tested - filtered unless --print-filtered) */
 int psb_counts(psb_ctx *ctx, int64_t out[4]);
 
+/* ---- multi-GPU: the gather of the result table ---------------------------------------- */
+/* Replaces multiprocessing.Pool(options.cpu) and the ordered pool.starmap of the worker map
+ * (__main__.py:517-519, :541-546, :777-780): variants are independent given the once-per-run state,
+ * ranks take contiguous variant ranges, and the one exchange of the path is the gather of the
+ * per-variant result table on a root rank, in rank order (= input order).  NCCL is loaded with dlopen
+ * (libnccl.so.2, or the file named by $PSB_NCCL_LIB); PSB_ERR_UNSUPPORTED when it is absent.
+ * A psb_comm holds the LOCAL members of the communicator: one context per process
+ * (psb_comm_init_rank; rank 0 makes the id with psb_comm_unique_id and hands it to the other ranks
+ * by any means -- the Python side uses a file) or all contexts of a process (psb_comm_init_all: rank
+ * i = ctxs[i]).
+ * psb_comm_gather_begin queues, behind the last psb_run_* of every local member: a device-side
+ * pack of its table (header + columns, rows_max rows; the same rows_max on every rank, >= the
+ * rows of any rank), then ncclSend to `root` / the root's ncclRecv from every rank, on a stream of
+ * the communicator -- the next psb_run_* only waits for the pack, so the transfer overlaps its
+ * kernels.  psb_comm_gather_wait joins that stream into the contexts' streams and the host.
+ * psb_comm_gather_fetch (root's process) copies rank src_rank's table out of the receive buffer to
+ * host or device pointers and reports its row count and psb_counts[4].
+ * bcast / allreduce (op 0 = sum, 1 = max, fp64) / barrier work on HOST buffers and need
+ * one-context communicators: what a launcher needs for the once-per-run state and the timing. */
+typedef struct psb_comm psb_comm;
+#define PSB_COMM_ID_BYTES 128
+int psb_comm_unique_id(uint8_t id[PSB_COMM_ID_BYTES]);
+int psb_comm_init_rank(psb_ctx *ctx, int32_t world, int32_t rank, const uint8_t id[PSB_COMM_ID_BYTES],
+                       psb_comm **out);
+int psb_comm_init_all(psb_ctx *const *ctxs, int32_t n, psb_comm **out);
+int psb_comm_destroy(psb_comm *comm);
+int psb_comm_info(psb_comm *comm, int32_t *world, int32_t *n_local, int32_t *nccl_version);
+int psb_comm_bcast(psb_comm *comm, void *host_buf, size_t bytes, int32_t root);
+int psb_comm_allreduce(psb_comm *comm, double *vals, int32_t n, int32_t op);
+int psb_comm_barrier(psb_comm *comm);
+int psb_comm_gather_begin(psb_comm *comm, int32_t root, int64_t rows_max);
+int psb_comm_gather_wait(psb_comm *comm);
+int psb_comm_gather_fetch(psb_comm *comm, int32_t src_rank, const psb_results *out, int64_t *n_rows,
+                          int64_t counts[4]);
+int psb_comm_gather_bytes(psb_comm *comm, int64_t *bytes_per_rank);
+
 /* ---- pinned host staging -------------------------------------------------------- */
 /* Page-locked host buffers for psb_submit / psb_fetch (input.py's k-mer streaming becomes
  * a pinned-host -> device staging pipeline).  psb_download_bits copies the currently
@@ -231,13 +267,18 @@ int psb_kinship_fetch(psb_ctx *ctx, double *K_out);
  * max_variants x words_per_row, zeroed by the call), the NUL-terminated names back to back in
  * `names` with name_off[v] their offsets, and info[v] (bit 0: row has missing genotypes,
  * bit 1: no observation in the selected samples, input.py:447-448).  *n_read == 0 at end of
- * file; *any_missing != 0 when at least one row had missing genotypes. */
+ * file; *any_missing != 0 when at least one row had missing genotypes.  Only the first *n_read rows
+ * of bits / missing are written. */
 typedef struct psb_reader psb_reader;
 int psb_reader_open(const char *path, int32_t var_type, const char *const *sample_names,
                     int32_t n_samples, psb_reader **out);
 int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, uint32_t *missing,
                     int32_t words_per_row, char *names, int64_t names_cap, int64_t *name_off,
                     int32_t *info, int64_t *n_read, int32_t *any_missing);
+/* A batch shorter than max_variants ended either at the end of the file (*at_eof != 0) or because the
+ * next name did not fit `names` (the line is kept for the next call; PSB_ERR_NOMEM when not even the
+ * first name of a call fits: come back with a larger buffer). */
+int psb_reader_at_eof(psb_reader *reader, int32_t *at_eof);
 /* var_type 2 = VCF text (plain or gzip), input.read_vcf_var (input.py:457-502), dominant encoding:
  * a sample carries the variant when a haplotype of its GT is a non-reference allele, '.' haplotypes
  * mark it missing unless a called one follows; names are CHROM_POS_REF[_ALT]; info bit 2 (value 4):
@@ -289,6 +330,12 @@ int psb_event_record(psb_ctx *ctx, int32_t slot);
 int psb_event_elapsed(psb_ctx *ctx, int32_t slot_a, int32_t slot_b, float *ms);
 /* number of kernels the library launched on this context since creation */
 int psb_launch_count(psb_ctx *ctx, int64_t *n);
+/* Measured peak rates of the pipes the hot kernels are bound by, under the clocks the board holds
+ * right now (roofline denominators): out[0] = dense int8 tensor TOP/s (tcgen05.mma kind::i8,
+ * M128 N256 K32, A from tensor memory, issued back to back on all SMs; accumulators verified),
+ * out[1] = fp64 FMA TFLOP/s (8 independent chains per thread), out[2], out[3] = the two probes'
+ * durations in ms. */
+int psb_measure_peaks(psb_ctx *ctx, double out[4]);
 
 /* ---- synthetic inputs (bench / tests) ----------------------------------------- */
 /* Fills a library-owned device buffer with seeded Bernoulli(af_s) rows, af_s ~

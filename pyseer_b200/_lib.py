@@ -80,7 +80,11 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_lineage_setup', 'psb_run_lineage', 'psb_fetch_lineage', 'psb_last_stats', 'psb_kinship_begin', 'psb_kinship_add', 'psb_kinship_fetch',
            'psb_synth_device', 'psb_synth_host', 'psb_host_chi2_sf1', 'psb_host_f_sf_1',
            'psb_host_t2_sf', 'psb_submit_burden', 'psb_submit_burden_device',
-           'psb_submitted_device', 'psb_download_rows', 'psb_eigh', 'psb_reader_set_threads', 'psb_format_rows', 'psb_reader_vcf_info', 'psb_hash_patterns']
+           'psb_submitted_device', 'psb_download_rows', 'psb_eigh', 'psb_reader_set_threads', 'psb_format_rows', 'psb_reader_vcf_info', 'psb_hash_patterns',
+           'psb_comm_unique_id', 'psb_comm_init_rank', 'psb_comm_init_all', 'psb_comm_destroy',
+           'psb_comm_info', 'psb_comm_bcast', 'psb_comm_allreduce', 'psb_comm_barrier',
+           'psb_comm_gather_begin', 'psb_comm_gather_wait', 'psb_comm_gather_fetch',
+           'psb_comm_gather_bytes', 'psb_measure_peaks', 'psb_reader_at_eof']
 
 
 def load():
@@ -140,6 +144,7 @@ def load():
     lib.psb_reader_next.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_int64,
                                     c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int32)]
     lib.psb_reader_close.argtypes = [c_void_p]
+    lib.psb_reader_at_eof.argtypes = [c_void_p, POINTER(c_int32)]
     lib.psb_lineage_setup.argtypes = [c_void_p, c_int32, c_int32, dp, c_int32]
     lib.psb_run_lineage.argtypes = [c_void_p, c_int32]
     lib.psb_fetch_lineage.argtypes = [c_void_p, c_void_p]
@@ -148,6 +153,20 @@ def load():
     lib.psb_kinship_add.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_double, c_double,
                                     c_double]
     lib.psb_kinship_fetch.argtypes = [c_void_p, dp]
+    lib.psb_comm_unique_id.argtypes = [c_void_p]
+    lib.psb_comm_init_rank.argtypes = [c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p)]
+    lib.psb_comm_init_all.argtypes = [POINTER(c_void_p), c_int32, POINTER(c_void_p)]
+    lib.psb_comm_destroy.argtypes = [c_void_p]
+    lib.psb_comm_info.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]
+    lib.psb_comm_bcast.argtypes = [c_void_p, c_void_p, ctypes.c_size_t, c_int32]
+    lib.psb_comm_allreduce.argtypes = [c_void_p, dp, c_int32, c_int32]
+    lib.psb_comm_barrier.argtypes = [c_void_p]
+    lib.psb_comm_gather_begin.argtypes = [c_void_p, c_int32, c_int64]
+    lib.psb_comm_gather_wait.argtypes = [c_void_p]
+    lib.psb_comm_gather_fetch.argtypes = [c_void_p, c_int32, POINTER(PsbResults), POINTER(c_int64),
+                                          POINTER(c_int64)]
+    lib.psb_comm_gather_bytes.argtypes = [c_void_p, POINTER(c_int64)]
+    lib.psb_measure_peaks.argtypes = [c_void_p, dp]
     lib.psb_synth_device.argtypes = [c_void_p, c_uint64, c_int64, c_int64, c_int32, c_double,
                                      c_double, c_int32, c_int32, POINTER(c_int8)]
     lib.psb_synth_host.argtypes = [c_uint64, c_int64, c_int64, c_int32, c_double, c_double,

@@ -494,7 +494,11 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
             bse_x = fast_bse;
         } else if (!fail) {
             // bse = sqrt(diag(inv(X'WX))) at the final parameters (H holds X'WX there)
-            if (!fx_chol_firth<PP>(H)) {       // numpy.linalg.inv: 'Singular matrix'
+            // numpy.linalg.inv: 'Singular matrix'.  Variant fits keep the plain test (quasi-separated fits
+            // have legitimately tiny pivots, and the reference's LU carries on through them); the null
+            // fit, where the answer decides between Newton's result and the Powell fallback
+            // (model.py:132-137), calls every pivot below 1e-13 of the diagonal singular.
+            if (!(a.has_x ? fx_chol<PP>(H) : fx_chol_firth<PP>(H))) {
                 fail = PSB_F_MATRIX_INV;
             } else if (a.has_x) {
                 double e[PP];
@@ -749,7 +753,7 @@ k_fixed_lineage(FxArgs a, const int32_t *__restrict__ idx, int n_tested, int mod
             ++it;
         }
         int best = -1;
-        if (!fail && fx_chol_firth<PP>(H)) {
+        if (!fail && fx_chol<PP>(H)) {
             double bestval = -INFINITY;
             bool seen_nan = false;
 #pragma unroll

@@ -462,7 +462,8 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
         // factor X'WX at the final parameters for the standard errors
         bool have_factor = false;
         if (!fail) {
-            have_factor = gen_chol_firth(ws.H, P, lane);
+            // (pivot floor for the null fit only: see k_fixed_logit)
+            have_factor = mode == FXG_NULL ? gen_chol_firth(ws.H, P, lane) : gen_chol(ws.H, P, lane);
             if (!have_factor) fail = PSB_F_MATRIX_INV;
         }
         if (mode == FXG_LINEAGE) {

@@ -29,6 +29,9 @@ struct psb_reader {
     size_t pos = 0, len = 0;
     bool eof = false;
     std::string line;
+    std::string pending;                    // a line whose name did not fit the caller's buffer:
+    bool have_pending = false;              //   first line of the next psb_reader_next
+    bool drained = false;                   // reader_getline has returned false
     std::vector<std::string> lines;         // lines of the batch being parsed
     int n_threads = 1;
     // VCF: name under construction, and contig / position / REF length of the records of the last batch
@@ -258,7 +261,9 @@ static void parse_line(const psb_reader *r, const char *L, size_t len, uint32_t 
                             size_t h1 = h0;
                             while (h1 < b && L[h1] != '/' && L[h1] != '|') ++h1;
                             const size_t hl = h1 - h0;
-                            if (hl == 1 && L[h0] == '.') {
+                            // an empty token (cell shorter than FORMAT, empty cell, trailing '/'):
+                            // pysam reports None, which read_vcf_var treats like '.' (input.py:486-488)
+                            if (hl == 0 || (hl == 1 && L[h0] == '.')) {
                                 if (st == 0) st = 2;
                             } else if (!(hl == 1 && L[h0] == '0')) {
                                 st = 1;
@@ -334,7 +339,9 @@ extern "C" int psb_reader_set_threads(psb_reader *r, int32_t n_threads) {
 // names: concatenated NUL-terminated variant names (names_cap bytes); name_off[v] = offset of
 // name v; info[v]: bit 0 = row has missing genotypes, bit 1 = no observation in the selected
 // samples (the reference writes "No observations of ..." to stderr, input.py:447-448).
-// *n_read = rows produced (0 at end of file).  Returns PSB_ERR_NOMEM when names_cap is too
+// *n_read = rows produced (0 at end of file).  A batch also ends when the next name does not fit
+// what is left of `names`: that line is kept and opens the next call (psb_reader_at_eof tells the
+// two apart).  Returns PSB_ERR_NOMEM (line kept as well) when names_cap is too
 // small for a single name, PSB_ERR_ARG on a malformed row.
 extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bits, uint32_t *missing,
                                int32_t words_per_row, char *names, int64_t names_cap,
@@ -350,15 +357,20 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
     std::vector<std::string> &lines = r->lines;
     int64_t n = 0, used = 0;
     while (n < max_variants) {
-        // stop early when the name buffer may not hold another name (keep 64 KiB free)
-        if (names_cap - used < (1 << 16) && n > 0) break;
-        if (!reader_getline(r)) break;
+        if (r->have_pending) {
+            r->line.swap(r->pending);
+            r->have_pending = false;
+        } else if (!reader_getline(r)) {
+            r->drained = true;
+            break;
+        }
         std::string &L = r->line;
         size_t len = L.size();
         while (len > 0 && (L[len - 1] == '\r' || L[len - 1] == ' ' || L[len - 1] == '\t')) --len;
         if (len == 0) continue;
         L.resize(len);
         size_t i = 0, j = 0;
+        size_t vt0 = 0, ve0 = 0, vt1 = 0, vreflen = 0;
         if (r->var_type == 0) {      // name = first whitespace-delimited token
             while (i < len && (L[i] == ' ' || L[i] == '\t')) ++i;
             j = i;
@@ -387,15 +399,25 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
                 r->vcf_name.push_back('_');
                 for (size_t q = t[4]; q < e[4]; ++q) r->vcf_name.push_back(L[q] == ',' ? '_' : L[q]);
             }
-            r->vcf_contig.emplace_back(L.data() + t[0], e[0] - t[0]);
-            r->vcf_pos.push_back(strtoll(L.c_str() + t[1], nullptr, 10));
-            r->vcf_reflen.push_back((int32_t)(e[3] - t[3]));
+            vt0 = t[0]; ve0 = e[0]; vt1 = t[1]; vreflen = e[3] - t[3];
         } else {                     // name = first tab-delimited field
             while (j < len && L[j] != '\t') ++j;
         }
         const char *name_ptr = r->var_type == 2 ? r->vcf_name.data() : L.data() + i;
         const size_t name_len = r->var_type == 2 ? r->vcf_name.size() : j - i;
-        PSB_REQUIRE((int64_t)name_len + 1 <= names_cap - used, PSB_ERR_NOMEM, "name buffer too small");
+        if ((int64_t)name_len + 1 > names_cap - used) {
+            // the name does not fit what is left of the caller's buffer: the line opens the next
+            // call (nothing is lost; with n == 0 the caller has to come back with a larger buffer)
+            r->pending.swap(L);
+            r->have_pending = true;
+            PSB_REQUIRE(n > 0, PSB_ERR_NOMEM, "name buffer too small for a name of %zu bytes", name_len);
+            break;
+        }
+        if (r->var_type == 2) {
+            r->vcf_contig.emplace_back(L.data() + vt0, ve0 - vt0);
+            r->vcf_pos.push_back(strtoll(L.c_str() + vt1, nullptr, 10));
+            r->vcf_reflen.push_back((int32_t)vreflen);
+        }
         memcpy(names + used, name_ptr, name_len);
         names[used + name_len] = '\0';
         name_off[n] = used;
@@ -429,6 +451,14 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
         if ((outs[v].flags & 1) && any_missing) *any_missing = 1;
     }
     *n_read = n;
+    return PSB_OK;
+}
+
+// *at_eof != 0 once the file has been read to its end and no line is held back: tells a short batch
+// that ended at the end of the file from one that ended because the names buffer was full.
+extern "C" int psb_reader_at_eof(psb_reader *r, int32_t *at_eof) {
+    PSB_REQUIRE(r && at_eof, PSB_ERR_ARG, "NULL argument");
+    *at_eof = (r->drained && !r->have_pending) ? 1 : 0;
     return PSB_OK;
 }
 

@@ -359,6 +359,12 @@ class Engine(object):
         check(self.lib.psb_last_ms(self._ctx, which, byref(ms)))
         return ms.value
 
+    def measure_peaks(self):
+        """Measured int8-tensor and fp64 peak rates under the current clocks (psb_measure_peaks)."""
+        v = (ctypes.c_double * 4)()
+        check(self.lib.psb_measure_peaks(self._ctx, v))
+        return {'int8_tops': v[0], 'fp64_tflops': v[1], 'int8_probe_ms': v[2], 'fp64_probe_ms': v[3]}
+
     def launch_count(self):
         n = c_int64(0)
         check(self.lib.psb_launch_count(self._ctx, byref(n)))

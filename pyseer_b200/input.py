@@ -135,13 +135,15 @@ def hash_patterns(bits, missing, n_samples, flags=None):
 
 class VariantBatch(object):
     """``n`` variants as packed rows plus what the result loop needs to print them."""
-    __slots__ = ['names', 'bits', 'missing', 'n']
+    __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped']
 
     def __init__(self, names, bits, missing):
         self.names = names
         self.bits = bits
         self.missing = missing
         self.n = len(names)
+        self.token = None          # buffer-pool token (pipeline.py), released by the consumer
+        self.skipped = None        # bool mask: records the reference never hands to a model
 
 
 class VariantReader(object):
@@ -173,30 +175,64 @@ class VariantReader(object):
             self._lib.psb_reader_close(self._h)
             self._h = None
 
-    def batches(self, size, names_cap=None):
+    def batches(self, size, names_cap=None, pool=None):
+        """Batches of exactly ``size`` variants (the last one shorter): block boundaries of the LMM
+        path (lmm.py:158-226 works on blocks of --block_size lines) must not depend on how long the
+        variant names are.  A call of the native reader that stops because its names buffer is full
+        is continued into the same rows; a name longer than the whole buffer gets a larger one.
+        ``pool``: optional source of (pinned) row buffers, ``pool.get() -> (bits, missing_or_None,
+        token)``; the token comes back in ``VariantBatch.token`` for the consumer to release."""
         import ctypes
         from . import _lib
         cap = int(names_cap or max(1 << 20, 160 * size))
-        while True:
-            bits = np.empty((size, self.W), dtype=np.uint32)
-            miss = np.empty((size, self.W), dtype=np.uint32) if self.var_type == 'Rtab' else None
-            names = ctypes.create_string_buffer(cap)
+        with_missing = self.var_type == 'Rtab'
+        done = False
+        while not done:
+            token = None
+            if pool is not None:
+                bits, miss, token = pool.get()
+                if not with_missing:
+                    miss = None
+            else:
+                bits = np.empty((size, self.W), dtype=np.uint32)
+                miss = np.empty((size, self.W), dtype=np.uint32) if with_missing else None
             off = np.empty(size, dtype=np.int64)
             info = np.empty(size, dtype=np.int32)
-            n = ctypes.c_int64(0)
-            anym = ctypes.c_int32(0)
-            _lib.check(self._lib.psb_reader_next(
-                self._h, size, bits.ctypes.data, miss.ctypes.data if miss is not None else None,
-                self.W, ctypes.addressof(names), cap, off.ctypes.data, info.ctypes.data,
-                ctypes.byref(n), ctypes.byref(anym)))
-            n = n.value
-            if n == 0:
+            nm = []
+            any_missing = False
+            filled = 0
+            while filled < size:
+                names = ctypes.create_string_buffer(cap)
+                n = ctypes.c_int64(0)
+                anym = ctypes.c_int32(0)
+                rc = self._lib.psb_reader_next(
+                    self._h, size - filled, bits[filled:].ctypes.data,
+                    miss[filled:].ctypes.data if miss is not None else None, self.W,
+                    ctypes.addressof(names), cap, off[filled:].ctypes.data, info[filled:].ctypes.data,
+                    ctypes.byref(n), ctypes.byref(anym))
+                if rc == _lib.PSB_ERR_NOMEM:
+                    cap *= 4                     # a single name longer than the buffer: the line was kept
+                    continue
+                _lib.check(rc)
+                n = n.value
+                raw = names.raw
+                nm.extend(raw[off[filled + i]:raw.index(b'\0', off[filled + i])].decode() for i in range(n))
+                any_missing = any_missing or bool(anym.value)
+                filled += n
+                eof = ctypes.c_int32(0)
+                _lib.check(self._lib.psb_reader_at_eof(self._h, ctypes.byref(eof)))
+                if eof.value:
+                    done = True
+                    break
+            if filled == 0:
+                if pool is not None:
+                    pool.put(token)
                 return
-            raw = names.raw
-            nm = [raw[off[i]:raw.index(b'\0', off[i])].decode() for i in range(n)]
-            for i in np.nonzero(info[:n] & 2)[0]:
+            for i in np.nonzero(info[:filled] & 2)[0]:
                 sys.stderr.write('No observations of ' + nm[i] + ' in selected samples\n')
-            yield VariantBatch(nm, bits[:n], miss[:n] if (miss is not None and anym.value) else None)
+            b = VariantBatch(nm, bits[:filled], miss[:filled] if (miss is not None and any_missing) else None)
+            b.token = token
+            yield b
 
     # -- per-variant detail, only when needed ------------------------------------------
     def sample_lists(self, batch, j):
