@@ -74,7 +74,10 @@ def get_options(argv=None):
                          'read instead of parsing the text on later runs with the same samples')
     ot.add_argument('--cpu', type=int, default=1, help='parser threads of the native k-mer / Rtab reader')
     ot.add_argument('--block_size', type=int, default=3000)
-    ot.add_argument('--gpu', type=int, default=0, help='CUDA device index')
+    ot.add_argument('--gpu', type=int, default=0, help='CUDA device index (the first one with --gpus)')
+    ot.add_argument('--gpus', type=int, default=1,
+                    help='number of GPUs: batches of variants are dealt to the GPUs in input order and the '
+                         'result tables gathered over NCCL on the first one (what --cpu is to pyseer)')
     ot.add_argument('--gpu-batch', type=int, default=48000,
                     help='variants per GPU submission (rounded to a multiple of --block_size)')
     ot.add_argument('--lmm-precision', type=int, default=None,
@@ -249,37 +252,35 @@ def main(argv=None):
     print('\t'.join(header))
 
     patterns = open(o.output_patterns, 'wb') if o.output_patterns else None
-    prefilter = tested = printed = 0
     out = sys.stdout
     nan = np.nan
     model_name = 'lmm' if o.lmm else 'seer'
     gpu_batch = max(1, o.gpu_batch // o.block_size) * o.block_size
+    counters = {'prefilter': 0, 'tested': 0, 'printed': 0}
 
     def samples_of(batch, j):
         return reader.sample_lists(batch, j) if o.print_samples else ([], [])
 
-    for batch in reader.batches(gpu_batch):
-        if o.lmm:
-            r = lm.run_lmm_bits(lmm, h2, batch.bits, batch.missing, o.continuous, o.filter_pvalue,
-                                o.lrt_pvalue, o.min_af, o.max_af, o.max_missing)
-        else:
-            r = fx.run_fixed_bits(model, batch.bits, batch.missing, o.filter_pvalue, o.lrt_pvalue,
-                                  o.min_af, o.max_af, o.max_missing, lineage=o.lineage)
+    def emit(batch, r):
+        """Result loop of main() (__main__.py:547-568, 783-803) for one batch."""
         flags = r.flags
+        if batch.skipped is not None and batch.skipped.any():
+            # records the reference never hands to a model (k is None, input.py:603-611)
+            flags[batch.skipped] = _lib.F_AF_FILTER | _lib.F_PREFILTER
         if not (o.print_samples or o.lineage) and \
                 os.environ.get('PYSEER_B200_NATIVE_FORMAT', '1') != '0':
             # no per-variant samples or lineages asked for: the whole batch goes through the library's formatter
             # (psb_format_rows: same lines, order and counters as the loop below, ~15x its speed)
             text, n_pre, n_tested, n_printed = format_table(r, batch.names, model_name, o.block_size,
                                                             o.print_filtered, threads=o.cpu)
-            prefilter += n_pre
-            tested += n_tested
-            printed += n_printed
+            counters['prefilter'] += n_pre
+            counters['tested'] += n_tested
+            counters['printed'] += n_printed
             out.write(text.decode())
             if patterns is not None:
                 # hash_pattern of every tested variant, in input order (__main__.py:559-560)
                 patterns.write(hash_patterns(batch.bits, batch.missing, reader.n_samples, flags))
-            continue
+            return
         # the reference emits each block of --block_size variants as: filtered ones first
         # (LMM only, lmm.py:158-226), then the tested ones; fixed effects keep input order
         for b0 in range(0, batch.n, o.block_size):
@@ -298,11 +299,11 @@ def main(argv=None):
             for j in order:
                 f = int(flags[j])
                 if f & _lib.F_PREFILTER:
-                    prefilter += 1
+                    counters['prefilter'] += 1
                     if not o.print_filtered:
                         continue
                 else:
-                    tested += 1
+                    counters['tested'] += 1
                     if patterns is not None:
                         patterns.write(hash_pattern(reader.k_vector(batch, j)))
                     if (f & _lib.F_FILTER) and not o.print_filtered:
@@ -324,9 +325,94 @@ def main(argv=None):
                     item = fx.seer_from_row(r, j, batch.names[j], None, r.af[j], ks, nks)
                     if o.lineage and not (f & _lib.F_PREFILTER) and r.lineage[j] >= 0:
                         item = item._replace(max_lineage=int(r.lineage[j]))
-                printed += 1
+                counters['printed'] += 1
                 out.write(format_output(item, lineage_dict if o.lineage else None, model_name,
                                         o.print_samples) + '\n')
+
+    # ---- the streaming pipeline (pipeline.py): reader thread -> pinned staging -> GPU(s) -> output
+    # thread, all in input order ------------------------------------------------------------------
+    import queue
+    import threading
+    from . import pipeline
+    from .pipeline import BatchRunner, Prefetch
+    from .engine import Engine
+    n_gpus = max(1, o.gpus)
+    thresholds = dict(min_af=o.min_af, max_af=o.max_af, max_missing=o.max_missing,
+                      filter_pvalue=o.filter_pvalue, lrt_pvalue=o.lrt_pvalue, continuous=o.continuous)
+    extra_models = []
+    if o.lmm:
+        engines = [lmm.engine(h2)]
+        S_, U_ = lmm.getSU()
+        for g in range(1, n_gpus):
+            e = Engine(o.gpu + g)
+            e.lmm_setup(lmm.X, lmm.Y[:, 0], U_, S_, h2, engines[0].lmm_precision)
+            engines.append(e)
+        run_one = lambda e: e.run_lmm(**thresholds)                                   # noqa: E731
+        n_betas = 0
+    else:
+        engines = [model.engine]
+        for g in range(1, n_gpus):
+            extra_models.append(fx.FixedModel(p.values, m, cov, o.continuous, null_fit.llf,
+                                              firth_null if not o.continuous else 0.0, device=o.gpu + g,
+                                              lineage=(lineage_clusters, cov) if o.lineage else None))
+            engines.append(extra_models[-1].engine)
+        run_one = lambda e: e.run_fixed(**thresholds)                                 # noqa: E731
+        n_betas = max(model.Z.shape[1] - 1, 0)
+    comm = None
+    if n_gpus > 1:
+        from .comm import Comm
+        comm = Comm.local(engines)
+    runner = BatchRunner(engines, run_one, n_betas=n_betas,
+                         lineage=(False if (o.lineage and not o.lmm) else None), comm=comm,
+                         rows_max=gpu_batch)
+    pool = None
+    if isinstance(reader, VariantReader):
+        pool = pipeline.PinnedPool(5 * n_gpus + 3, gpu_batch, reader.W, reader.var_type == 'Rtab')
+        source = reader.batches(gpu_batch, pool=pool)
+    else:
+        source = reader.batches(gpu_batch)
+    batches = Prefetch(source, depth=n_gpus + 1)
+    outq = queue.Queue(maxsize=2 * n_gpus)
+    out_err = []
+
+    def output_loop():
+        while True:
+            item = outq.get()
+            if item is None:
+                return
+            if out_err:
+                continue                    # keep draining so that the producer never blocks
+            try:
+                emit(*item)
+                if pool is not None:
+                    pool.put(item[0].token)
+            except BaseException as e:      # noqa: BLE001 -- re-raised in the main thread
+                out_err.append(e)
+
+    writer = threading.Thread(target=output_loop, daemon=True)
+    writer.start()
+    try:
+        for batch, r in runner.results(batches):
+            if out_err:
+                break
+            outq.put((batch, r))
+    finally:
+        batches.cancel()
+        outq.put(None)
+        writer.join()
+        runner.close()
+        if comm is not None:
+            comm.close()
+        for e in engines[1:]:
+            if o.lmm:
+                e.close()
+        for fm in extra_models:
+            fm.close()
+        if pool is not None:
+            pool.close()
+    if out_err:
+        raise out_err[0]
+    prefilter, tested, printed = counters['prefilter'], counters['tested'], counters['printed']
     reader.close()
     if patterns is not None:
         patterns.close()

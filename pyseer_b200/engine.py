@@ -117,6 +117,7 @@ class Engine(object):
         check(self.lib.psb_lmm_setup(self._ctx, n, d, self._dptr(X), self._dptr(y),
                                      self._dptr(U), self._dptr(S), float(h2), int(precision)))
         self.n_samples, self.q, self.model = n, 0, 'lmm'
+        self.lmm_precision = int(precision)
 
     def fixed_setup(self, Z, y, continuous, null_llf, null_firth):
         """Shared arguments of fixed_effects_regression (model.py:202-205)."""

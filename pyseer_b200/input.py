@@ -392,10 +392,10 @@ def open_variants(var_type, path, p, uncompressed=False, cache=None, threads=1):
     writer = PackedCacheWriter(cache, var_type, path, samples, W)
     inner = rd.batches
 
-    def batches(size, names_cap=None):
+    def batches(size, names_cap=None, pool=None):
         done = False
         try:
-            for b in inner(size, names_cap):
+            for b in inner(size, names_cap, pool):
                 writer.add(b)
                 yield b
             done = True
@@ -550,7 +550,10 @@ class VcfReader(object):
                     sys.stderr.write('No observations of ' + names[j] + ' in selected samples\n')
             if miss is not None and not miss.any():
                 miss = None
-            yield VariantBatch(names, bits, miss)
+            vb = VariantBatch(names, bits, miss)
+            # a burden line whose region does not parse is the reference's None sentinel: never fitted
+            vb.skipped = np.array([nm == 'NA' for nm in names], dtype=bool)
+            yield vb
 
     def batches(self, size):
         if self.regions is not None:
@@ -567,8 +570,12 @@ class VcfReader(object):
                     nm[i] = 'NA'
                 elif info[i] & 2:
                     sys.stderr.write('No observations of ' + nm[i] + ' in selected samples\n')
-            yield VariantBatch(nm, np.ascontiguousarray(bits),
-                               np.ascontiguousarray(miss) if (info & 1).any() else None)
+            vb = VariantBatch(nm, np.ascontiguousarray(bits),
+                              np.ascontiguousarray(miss) if (info & 1).any() else None)
+            # skipped records never reach a model in the reference (k is None: input.py:603-611), whatever
+            # --min-af says: the result loop forces them to 'af-filter' from this mask
+            vb.skipped = (info & 12) != 0
+            yield vb
 
     sample_lists = VariantReader.sample_lists
     k_vector = VariantReader.k_vector

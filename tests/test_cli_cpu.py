@@ -17,7 +17,13 @@ pytestmark = []          # (test_cli_gpu's module-level gpu mark does not apply 
 
 
 class _FakeEngine(object):
-    """Burden unions through the oracle's packed-row rule instead of psb_submit_burden."""
+    """The engine calls the CLI's pipeline makes (submit / run_* / fetch, pipeline.py), answered by
+    the oracle; burden unions through the oracle's packed-row rule instead of psb_submit_burden."""
+    lmm_precision = 5
+
+    def __init__(self, fixed_model=None, lmm=None, h2=None):
+        self.fixed_model, self.lmm, self.h2 = fixed_model, lmm, h2
+        self._sub = self._res = None
 
     def submit_burden(self, bits, missing, offsets, members):
         from oracle.input_oracle import burden_union
@@ -26,6 +32,49 @@ class _FakeEngine(object):
     def download_rows(self):
         bits, miss = self._rows
         return bits, (miss if miss is not None and miss.any() else None)
+
+    def submit(self, bits, missing=None):
+        self._sub = (np.array(bits), None if missing is None else np.array(missing))
+
+    def run_fixed(self, min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous):
+        self._res = _fake_run_fixed_bits(self.fixed_model, self._sub[0], self._sub[1], filter_pvalue,
+                                         lrt_pvalue, min_af, max_af, max_missing)
+
+    def run_lmm(self, min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous):
+        self._res = _fake_run_lmm_bits(self.lmm, self.h2, self._sub[0], self._sub[1], continuous,
+                                       filter_pvalue, lrt_pvalue, min_af, max_af, max_missing)
+
+    def fetch(self):
+        return self._res
+
+    def close(self):
+        pass
+
+
+class _FakePool(object):
+    """pipeline.PinnedPool without cudaHostAlloc (no GPU in the CPU suite)."""
+
+    def __init__(self, n, rows, W, with_missing):
+        self.shape, self.with_missing = (rows, W), with_missing
+
+    def get(self):
+        return (np.empty(self.shape, dtype=np.uint32),
+                np.empty(self.shape, dtype=np.uint32) if self.with_missing else None, 0)
+
+    def put(self, token):
+        pass
+
+    def close(self):
+        pass
+
+
+def _patch(monkeypatch):
+    from pyseer_b200 import model as fx, lmm as lm, pipeline
+    monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
+    monkeypatch.setattr(fx, 'FixedModel', _FakeFixedModel)
+    monkeypatch.setattr(lm.KinshipLMM, 'close', lambda self: None)
+    monkeypatch.setattr(lm.KinshipLMM, 'engine', lambda self, h2: _FakeEngine(lmm=self, h2=h2))
+    monkeypatch.setattr(pipeline, 'PinnedPool', _FakePool)
 
 
 class _FakeFixedModel(object):
@@ -36,7 +85,9 @@ class _FakeFixedModel(object):
         self.continuous = bool(continuous)
         self.null_llf = getattr(null_res, 'llf', null_res)
         self.null_firth = null_firth
-        self.engine = _FakeEngine()
+        self.Z = np.ones((self.p.shape[0], 1 + (self.m.shape[1] if self.m.ndim == 2 and self.m.shape[0] == self.p.shape[0] else 0)
+                          + (self.cov.shape[1] if self.cov.ndim == 2 and self.cov.shape[0] == self.p.shape[0] else 0)))
+        self.engine = _FakeEngine(fixed_model=self)
 
     def close(self):
         pass
@@ -153,13 +204,8 @@ CPU_CASES = ['1', '3', '5', '6', '9', '12', '13', '14', '15', '20', '23', '24', 
 
 @pytest.mark.parametrize('case', CPU_CASES)
 def test_baseline_with_oracle_engine(case, tmp_path, monkeypatch):
-    from pyseer_b200 import model as fx, lmm as lm
     from pyseer_b200.__main__ import main
-    monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
-    monkeypatch.setattr(fx, 'FixedModel', _FakeFixedModel)
-    monkeypatch.setattr(fx, 'run_fixed_bits', _fake_run_fixed_bits)
-    monkeypatch.setattr(lm, 'run_lmm_bits', _fake_run_lmm_bits)
-    monkeypatch.setattr(lm.KinshipLMM, 'close', lambda self: None)
+    _patch(monkeypatch)
     out, err = io.StringIO(), io.StringIO()
     args = list(CASES[case]) + ['--cpu', '3']
     if case == '27':
@@ -197,11 +243,8 @@ def test_baseline_with_oracle_engine(case, tmp_path, monkeypatch):
 def test_bits_cache_and_formatter_paths_agree(tmp_path, monkeypatch):
     """The same run with and without --bits-cache (first run writes it, second reads it), and with the
     row-by-row Python formatter instead of the native one, prints the same bytes."""
-    from pyseer_b200 import model as fx, lmm as lm
     from pyseer_b200.__main__ import main
-    monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
-    monkeypatch.setattr(fx, 'FixedModel', _FakeFixedModel)
-    monkeypatch.setattr(fx, 'run_fixed_bits', _fake_run_fixed_bits)
+    _patch(monkeypatch)
     cache = str(tmp_path / 'kmers.bits')
 
     def run(extra, env=None):
@@ -229,13 +272,8 @@ def test_bits_cache_and_formatter_paths_agree(tmp_path, monkeypatch):
 
 
 def _run_cli(args, monkeypatch):
-    from pyseer_b200 import model as fx, lmm as lm
     from pyseer_b200.__main__ import main
-    monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
-    monkeypatch.setattr(fx, 'FixedModel', _FakeFixedModel)
-    monkeypatch.setattr(fx, 'run_fixed_bits', _fake_run_fixed_bits)
-    monkeypatch.setattr(lm, 'run_lmm_bits', _fake_run_lmm_bits)
-    monkeypatch.setattr(lm.KinshipLMM, 'close', lambda self: None)
+    _patch(monkeypatch)
     out, err = io.StringIO(), io.StringIO()
     with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err), np.errstate(all='ignore'):
         main(args)

@@ -143,3 +143,72 @@ def test_baseline(case, tmp_path):
                 bad.append((name[:20], col, got[col], ref[col]))
     assert not bad, bad[:10]
     assert lineage_diff <= 0.25 * len(rrows)
+
+
+def _write_kmers(path, n_samples, n_kmers, seed=3):
+    """Synthetic --kmers text file (plain) + phenotype and similarity files next to it."""
+    import benchdata
+    from oracle import synth
+    X, y, K = benchdata.lmm_problem(n_samples, seed=seed)
+    ys = np.where(y > np.median(y), 1, -1).astype(np.int8)
+    bits = synth.synth_rows(77, 0, n_kmers, n_samples, 0.0, 1.0, 50, ys, 0)
+    x = synth.unpack_rows(bits, n_samples)
+    names = np.array(['s%d' % i for i in range(n_samples)])
+    with open(path, 'w') as fh:
+        for s in range(n_kmers):
+            fh.write('K%07d | ' % s + ' '.join(t + ':1' for t in names[x[s] != 0]) + '\n')
+    base = os.path.dirname(path)
+    with open(os.path.join(base, 'pheno.tsv'), 'w') as fh:
+        fh.write('samples\tcontinuous\tbinary\n')
+        for i in range(n_samples):
+            fh.write('s%d\t%r\t%d\n' % (i, float(y[i]), int(y[i] > np.median(y))))
+    import pandas as pd
+    pd.DataFrame(K, index=names, columns=names).to_csv(os.path.join(base, 'sim.tsv'), sep='\t')
+    pd.DataFrame(np.sqrt(np.maximum(0, np.add.outer(np.diag(K), np.diag(K)) - 2 * K)), index=names,
+                 columns=names).to_csv(os.path.join(base, 'dist.tsv'), sep='\t')
+    return base
+
+
+def _cli(args):
+    from pyseer_b200.__main__ import main
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        main(args)
+    return out.getvalue(), err.getvalue()
+
+
+@pytest.mark.parametrize('mode', ['lmm', 'fixed'])
+def test_pipeline_batches_do_not_change_output(mode, tmp_path):
+    """The streaming pipeline (reader thread, pinned staging, submit k+1 while k runs, output thread):
+    many small batches in flight print the same bytes as one batch."""
+    base = _write_kmers(str(tmp_path / 'kmers.txt'), 200, 5000)
+    common = ['--kmers', str(tmp_path / 'kmers.txt'), '--uncompressed', '--phenotypes',
+              os.path.join(base, 'pheno.tsv'), '--print-filtered', '--block_size', '100']
+    if mode == 'lmm':
+        common += ['--lmm', '--similarity', os.path.join(base, 'sim.tsv'), '--phenotype-column', 'continuous']
+    else:
+        common += ['--distances', os.path.join(base, 'dist.tsv'), '--max-dimensions', '4',
+                   '--phenotype-column', 'binary']
+    one, e1 = _cli(common + ['--gpu-batch', '100000'])
+    many, e2 = _cli(common + ['--gpu-batch', '300', '--cpu', '4'])
+    assert one == many and _counters(e1) == _counters(e2) and _counters(e1)['loaded'] == 5000
+
+
+@pytest.mark.parametrize('mode', ['lmm', 'fixed'])
+def test_two_gpus_print_the_same_table(mode, tmp_path):
+    """--gpus 2: batches dealt to two GPUs, tables gathered over NCCL on the first one, output in input
+    order -- byte-identical to the one-GPU run.  Needs two GPUs (`gpurun --gpus 2`)."""
+    from pyseer_b200.engine import device_count
+    if device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    base = _write_kmers(str(tmp_path / 'kmers.txt'), 200, 5000)
+    common = ['--kmers', str(tmp_path / 'kmers.txt'), '--uncompressed', '--phenotypes',
+              os.path.join(base, 'pheno.tsv'), '--print-filtered', '--block_size', '100', '--gpu-batch', '700']
+    if mode == 'lmm':
+        common += ['--lmm', '--similarity', os.path.join(base, 'sim.tsv'), '--phenotype-column', 'continuous']
+    else:
+        common += ['--distances', os.path.join(base, 'dist.tsv'), '--max-dimensions', '4',
+                   '--phenotype-column', 'binary']
+    one, e1 = _cli(common)
+    two, e2 = _cli(common + ['--gpus', '2'])
+    assert one == two and _counters(e1) == _counters(e2)

@@ -200,3 +200,53 @@ def test_vcf_parser_threads_give_identical_batches():
     assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]
     assert len(outs[0][0]) == 886
+
+
+def test_long_names_do_not_shrink_batches(tmp_path):
+    """Batches keep their requested size whatever the length of the variant names (unitig names run
+    to kilobytes): a native call that stops because its names buffer is full is continued into the
+    same batch, a name longer than the whole buffer gets a larger one -- and no line is lost.  The
+    LMM path walks blocks of --block_size lines from the start of every batch (lmm.py:158-226), so
+    batch boundaries must not depend on the names."""
+    p = _pheno()
+    samples = list(p.index)
+    rng = np.random.RandomState(4)
+    path = str(tmp_path / 'long.txt')
+    names, rows = [], []
+    with open(path, 'w') as fh:
+        for i in range(700):
+            ln = 70000 if i == 333 else int(rng.randint(150, 260))
+            nm = ''.join(rng.choice(list('ACGT'), ln)) + str(i)
+            carriers = [s for s in samples if rng.uniform() < 0.4]
+            fh.write(nm + ' | ' + ' '.join(s + ':1' for s in carriers) + '\n')
+            names.append(nm)
+            rows.append(set(carriers))
+    rd = VariantReader('kmers', path, p)
+    batches = list(rd.batches(300, names_cap=4096))        # ~20 names per native call
+    rd.close()
+    assert [b.n for b in batches] == [300, 300, 100]
+    got = [n for b in batches for n in b.names]
+    assert got == names
+    x = np.concatenate([unpack_rows(b.bits, len(samples)) for b in batches])
+    for i in (0, 299, 300, 333, 334, 699):
+        assert set(s for s, on in zip(samples, x[i]) if on) == rows[i]
+
+
+def test_vcf_short_and_empty_genotype_cells(tmp_path):
+    """A sample cell with fewer ':' fields than FORMAT, an empty cell or a trailing '/': pysam reports
+    None for such a haplotype, which read_vcf_var treats like '.' (input.py:484-497) -- missing, unless
+    another haplotype of the cell is called."""
+    from pyseer_b200.input import VcfReader
+    p = pd.Series([0.0, 1.0, 0.0, 1.0, 1.0], index=['a', 'b', 'c', 'd', 'e'])
+    vcf = str(tmp_path / 't.vcf')
+    with open(vcf, 'w') as fh:
+        fh.write('##fileformat=VCFv4.2\n')
+        fh.write('#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ta\tb\tc\td\te\n')
+        fh.write('chr\t10\t.\tA\tT\t.\tPASS\t.\tDP:GT\t3\t3:1\t3:0\t3:\t3:1/\n')
+    rd = VcfReader(vcf, p)
+    b = list(rd.batches(10))[0]
+    rd.close()
+    x = unpack_rows(b.bits, 5)[0]
+    m = unpack_rows(b.missing, 5)[0]
+    assert list(x) == [0, 1, 0, 0, 1]          # e: '1/' carries through its called haplotype
+    assert list(m) == [1, 0, 0, 1, 0]          # a: no GT field at all; d: empty GT
