@@ -115,6 +115,13 @@ int psb_lmm_setup(psb_ctx *ctx, int32_t n_samples, int32_t n_cov, const double *
  * Runs cuSOLVER's fp64 syevd (loaded lazily with dlopen; PSB_ERR_UNSUPPORTED when it is not
  * installed, in which case the host side keeps its NumPy eigh).  Needs no model set-up. */
 int psb_eigh(psb_ctx *ctx, int32_t n, const double *A, double *w_out, double *V_out);
+/* All of LMM.setSU_fromK (fastlmm/lmm_cov.py:88-103) on the device: K (n x n row-major, host; the
+ * normalised kinship, before the + I), covariate design X (n x d row-major) and its pseudo-inverse
+ * Xp (d x n, Linreg's Xdagger, lmm_cov.py:861-880) -> K_ = regress(regress(K + I)') formed as the
+ * reference forms it (two rank-d updates), then syevd.  w_out / V_out as psb_eigh; the caller keeps the
+ * pairs d..n-1 and subtracts 1 from the eigenvalues.  1 <= d <= 16. */
+int psb_spectral(psb_ctx *ctx, int32_t n, int32_t d, const double *K, const double *X, const double *Xp,
+                 double *w_out, double *V_out);
 
 /* Fixed-effects state shared by every fixed_effects_regression call (model.py:202-205):
  * Z = [1, m, c] (N x q row-major, column 0 ones; model.py:274-297 minus the variant

@@ -5,6 +5,7 @@
 
 #include "psb_internal.cuh"
 #include "psb_math.cuh"
+#include "psb_fixed.cuh"
 
 static thread_local char g_err[1024] = "";
 
@@ -86,6 +87,7 @@ int psb_free_model(psb_ctx *c) {
     free_dev(c->d_sums); c->d_sums = nullptr; c->sums_cap = 0;
     c->h_warm.clear();
     c->logit_first_step = false;
+    psb_fixed_fast_free(c);
     c->model = PSB_MODEL_NONE;
     c->ran = false;
     return PSB_OK;
@@ -98,10 +100,10 @@ static void free_tables(psb_ctx *c) {
     free_dev(c->d_carriers); free_dev(c->d_missing); free_dev(c->d_af); free_dev(c->d_prep);
     free_dev(c->d_pvalue); free_dev(c->d_beta); free_dev(c->d_bse); free_dev(c->d_extra);
     free_dev(c->d_betas); free_dev(c->d_flags); free_dev(c->d_tab); free_dev(c->d_idx);
-    free_dev(c->d_idx2); free_dev(c->d_a); free_dev(c->d_b); free_dev(c->d_pp); free_dev(c->d_lineage);
+    free_dev(c->d_idx2); free_dev(c->d_idx3); free_dev(c->d_a); free_dev(c->d_b); free_dev(c->d_pp); free_dev(c->d_lineage);
     c->d_carriers = c->d_missing = nullptr;
     c->d_af = c->d_prep = c->d_pvalue = c->d_beta = c->d_bse = c->d_extra = c->d_betas = nullptr;
-    c->d_flags = nullptr; c->d_tab = nullptr; c->d_idx = c->d_idx2 = nullptr; c->d_a = c->d_b = c->d_pp = nullptr; c->d_lineage = nullptr;
+    c->d_flags = nullptr; c->d_tab = nullptr; c->d_idx = c->d_idx2 = c->d_idx3 = nullptr; c->d_a = c->d_b = c->d_pp = nullptr; c->d_lineage = nullptr;
     c->cap = 0; c->betas_cols = 0;
 }
 
@@ -185,6 +187,7 @@ int psb_ensure_capacity(psb_ctx *c, int64_t S, int betas_cols) {
         PSB_CUDA(cudaMalloc(&c->d_tab, cap * 4 * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_idx, (cap + 256) * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_idx2, (cap + 256) * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->d_idx3, (cap + 256) * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_lineage, cap * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_a, cap * sizeof(double)));
         PSB_CUDA(cudaMalloc(&c->d_b, cap * sizeof(double)));
@@ -231,6 +234,7 @@ static int stage_reserve(psb_ctx *c, uint32_t **buf, size_t *cap, size_t bytes) 
 
 int psb_submit(psb_ctx *c, const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
                int32_t words_per_row) {
+    PSB_NVTX("psb_submit");
     int rc = check_rows(c, n_variants, words_per_row);
     if (rc) return rc;
     PSB_REQUIRE(bits || n_variants == 0, PSB_ERR_ARG, "bits is NULL");
@@ -277,6 +281,7 @@ int psb_submit_device(psb_ctx *c, const void *d_bits, const void *d_missing, int
 }
 
 int psb_fetch(psb_ctx *c, const psb_results *out) {
+    PSB_NVTX("psb_fetch");
     PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(c->ran, PSB_ERR_STATE, "psb_fetch before psb_run_*");
     PSB_CUDA(cudaSetDevice(c->device));

@@ -324,6 +324,7 @@ int psb_comm_barrier(psb_comm *c) {
 
 // ---- the gather of the result table ----
 int psb_comm_gather_begin(psb_comm *c, int32_t root, int64_t rows_max) {
+    PSB_NVTX("psb_comm_gather_begin");
     PSB_REQUIRE(c, PSB_ERR_ARG, "comm is NULL");
     PSB_REQUIRE(root >= 0 && root < c->world && rows_max >= 0, PSB_ERR_ARG, "bad root / rows_max");
     int nb = 0;
@@ -387,6 +388,7 @@ int psb_comm_gather_begin(psb_comm *c, int32_t root, int64_t rows_max) {
 }
 
 int psb_comm_gather_wait(psb_comm *c) {
+    PSB_NVTX("psb_comm_gather_wait");
     PSB_REQUIRE(c, PSB_ERR_ARG, "comm is NULL");
     for (auto &mb : c->m) {
         PSB_CUDA(cudaSetDevice(mb.ctx->device));

@@ -69,11 +69,106 @@ k_transpose(const double *__restrict__ in, double *__restrict__ out, int n) {
     }
 }
 
+// T[k][j] (+)= sum_i Xp[k][i] A[i][j] over this block's slice of i   (T zeroed by the caller)
+__global__ void __launch_bounds__(256)
+k_proj_T(const double *__restrict__ A, const double *__restrict__ Xp, double *__restrict__ T, int n, int d,
+         int rows_per_block) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = blockIdx.y * rows_per_block, i1 = min(n, i0 + rows_per_block);
+    if (j >= n) return;
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    for (int i = i0; i < i1; ++i) {
+        const double a = A[(size_t)i * n + j];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < d) acc[k] = fma(__ldg(Xp + (size_t)k * n + i), a, acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < d) atomicAdd(T + (size_t)k * n + j, acc[k]);
+}
+
+// T[k][j] = sum_i Xp[k][i] A[j][i]   (the same for the transposed matrix): one warp per row j
+__global__ void __launch_bounds__(256)
+k_proj_Tt(const double *__restrict__ A, const double *__restrict__ Xp, double *__restrict__ T, int n, int d) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= n) return;
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    for (int i = lane; i < n; i += 32) {
+        const double a = A[(size_t)j * n + i];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            if (k < d) acc[k] = fma(__ldg(Xp + (size_t)k * n + i), a, acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < d) {
+            double v = acc[k];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) T[(size_t)k * n + j] = v;
+        }
+}
+
+// out[i][j] = (TR ? A[j][i] : A[i][j]) - sum_k X[i][k] T[k][j]      (Linreg.regress, lmm_cov.py:874-880)
+template <bool TR>
+__global__ void __launch_bounds__(256)
+k_proj_apply(const double *__restrict__ A, const double *__restrict__ X, const double *__restrict__ T,
+             double *__restrict__ out, int n, int d, double diag_add) {
+    __shared__ double t[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    if (TR) {
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int i = bx + r, j = by + threadIdx.x;          // read A[j'][i'] tile transposed
+            if (i < n && j < n) t[r][threadIdx.x] = A[(size_t)i * n + j];
+        }
+        __syncthreads();
+    }
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int i = by + r, j = bx + threadIdx.x;
+        if (i < n && j < n) {
+            double v = TR ? t[threadIdx.x][r] : A[(size_t)i * n + j];
+            if (!TR && i == j) v += diag_add;
+            double s = 0.0;
+            for (int k = 0; k < d; ++k) s = fma(__ldg(X + (size_t)i * d + k), __ldg(T + (size_t)k * n + j), s);
+            out[(size_t)i * n + j] = v - s;
+        }
+    }
+}
+
+__global__ void k_add_diag(double *A, int n, double v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[(size_t)i * n + i] += v;
+}
+
 }  // namespace
+
+static int eigh_core(psb_ctx *c, int32_t n, const double *A, const double *X, const double *Xp, int32_t d,
+                     double *w_out, double *V_out);
 
 // A: n x n row-major, host; only its lower triangle is read (as numpy.linalg.eigh does).  w_out: n eigenvalues,
 // ascending.  V_out: n x n row-major, column j = eigenvector of w_out[j] (numpy.linalg.eigh layout).
 extern "C" int psb_eigh(psb_ctx *c, int32_t n, const double *A, double *w_out, double *V_out) {
+    return eigh_core(c, n, A, nullptr, nullptr, 0, w_out, V_out);
+}
+
+// LMM.setSU_fromK (fastlmm/lmm_cov.py:88-103) in one call: K (n x n row-major, host) and the covariate
+// design X (n x d) with its pseudo-inverse Xp (d x n, Linreg's Xdagger) -> eigendecomposition of
+// K_ = P (K + I) P formed on the device exactly as the reference forms it (regress the matrix, then
+// regress its transpose: two rank-d updates), eigenvalues ascending in w_out, eigenvectors in the
+// columns of V_out (numpy.linalg.eigh layout).  The caller drops the first d pairs and subtracts 1.
+extern "C" int psb_spectral(psb_ctx *c, int32_t n, int32_t d, const double *K, const double *X,
+                            const double *Xp, double *w_out, double *V_out) {
+    PSB_REQUIRE(X && Xp, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(d >= 1 && d <= 16, PSB_ERR_UNSUPPORTED, "psb_spectral supports 1..16 covariate columns, got %d", d);
+    return eigh_core(c, n, K, X, Xp, d, w_out, V_out);
+}
+
+static int eigh_core(psb_ctx *c, int32_t n, const double *A, const double *X, const double *Xp, int32_t d,
+                     double *w_out, double *V_out) {
     PSB_REQUIRE(c && A && w_out && V_out, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(n >= 1 && n <= 46000, PSB_ERR_ARG, "n = %d out of range", n);
     PSB_REQUIRE(load_solver(), PSB_ERR_UNSUPPORTED,
@@ -81,6 +176,7 @@ extern "C" int psb_eigh(psb_ctx *c, int32_t n, const double *A, double *w_out, d
     PSB_CUDA(cudaSetDevice(c->device));
     const size_t bytes = (size_t)n * n * sizeof(double);
     double *d_A = nullptr, *d_V = nullptr, *d_w = nullptr, *d_work = nullptr;
+    double *d_X = nullptr, *d_Xp = nullptr, *d_T = nullptr;
     int *d_info = nullptr;
     solver_handle h = nullptr;
     int rc = PSB_OK, info = 0, lwork = 0, st = 0;
@@ -99,6 +195,25 @@ extern "C" int psb_eigh(psb_ctx *c, int32_t n, const double *A, double *w_out, d
     EIGH_CUDA(cudaMalloc(&d_w, (size_t)n * sizeof(double)));
     EIGH_CUDA(cudaMalloc(&d_info, sizeof(int)));
     EIGH_CUDA(cudaMemcpyAsync(d_A, A, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (X) {
+        // K_ = regress(regress(K + I)')  -- K_ = self.regress(self.K); K_ = self.regress(K_.T)
+        const size_t xb = (size_t)n * d * sizeof(double);
+        EIGH_CUDA(cudaMalloc(&d_X, xb));
+        EIGH_CUDA(cudaMalloc(&d_Xp, xb));
+        EIGH_CUDA(cudaMalloc(&d_T, xb));
+        EIGH_CUDA(cudaMemcpyAsync(d_X, X, xb, cudaMemcpyHostToDevice, c->stream));
+        EIGH_CUDA(cudaMemcpyAsync(d_Xp, Xp, xb, cudaMemcpyHostToDevice, c->stream));
+        k_add_diag<<<(n + 255) / 256, 256, 0, c->stream>>>(d_A, n, 1.0);
+        EIGH_CUDA(cudaMemsetAsync(d_T, 0, xb, c->stream));
+        const int rpb = 256;
+        k_proj_T<<<dim3((n + 255) / 256, (n + rpb - 1) / rpb), 256, 0, c->stream>>>(d_A, d_Xp, d_T, n, d, rpb);
+        dim3 g((n + 31) / 32, (n + 31) / 32), b(32, 8);
+        k_proj_apply<false><<<g, b, 0, c->stream>>>(d_A, d_X, d_T, d_V, n, d, 0.0);          // d_V = regress(K + I)
+        k_proj_Tt<<<(n + 7) / 8, 256, 0, c->stream>>>(d_V, d_Xp, d_T, n, d);
+        k_proj_apply<true><<<g, b, 0, c->stream>>>(d_V, d_X, d_T, d_A, n, d, 0.0);           // d_A = regress(d_V')
+        c->launches += 5;
+        EIGH_CUDA(cudaGetLastError());
+    }
     st = g_solver.create(&h);
     if (st != 0) { psb_set_error("cusolverDnCreate failed (%d)", st); rc = PSB_ERR_CUDA; goto done; }
     g_solver.set_stream(h, c->stream);
@@ -130,6 +245,9 @@ done:
     if (h) g_solver.destroy(h);
     if (d_work) cudaFree(d_work);
     if (d_info) cudaFree(d_info);
+    if (d_X) cudaFree(d_X);
+    if (d_Xp) cudaFree(d_Xp);
+    if (d_T) cudaFree(d_T);
     if (d_w) cudaFree(d_w);
     if (d_V) cudaFree(d_V);
     if (d_A) cudaFree(d_A);

@@ -28,191 +28,7 @@
 #include "psb_math.cuh"
 
 #include "psb_fixed.cuh"
-
-template <int PP>
-struct Tri {
-    static constexpr int SIZE = PP * (PP + 1) / 2;
-    __host__ __device__ static constexpr int at(int a, int b) { return a * (a + 1) / 2 + b; }   // b <= a
-};
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// In-place lower Cholesky of the packed symmetric matrix; returns false when a pivot is not
-// positive (matrix not PD) or not finite.
-// (all loops run over the full constant range with constant-foldable guards, so that the
-// unroller turns every index into a literal and the arrays stay in registers)
-//
-// Right-looking (outer-product) form: after column j is scaled, the trailing submatrix
-// update is (PP-j)^2/2 independent FMAs, so the dependency chain per column is just
-// sqrt -> reciprocal -> multiply -> FMA.  The diagonal is stored as 1 / L_jj.
-template <int PP>
-__device__ __forceinline__ bool fx_chol(double (&A)[Tri<PP>::SIZE]) {
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < PP; ++j) {
-        const double d = A[Tri<PP>::at(j, j)];
-        if (!(d > 0.0) || !isfinite(d)) ok = false;
-        const double inv = rsqrt(d);
-        A[Tri<PP>::at(j, j)] = inv;
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-            if (i > j) A[Tri<PP>::at(i, j)] *= inv;
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-#pragma unroll
-            for (int k = 0; k < PP; ++k)
-                if (i > j && k > j && k <= i)
-                    A[Tri<PP>::at(i, k)] = fma(-A[Tri<PP>::at(i, j)], A[Tri<PP>::at(k, j)], A[Tri<PP>::at(i, k)]);
-    }
-    return ok;
-}
-
-// b := (L L')^-1 b   (column-oriented substitutions; diagonal of L holds reciprocals)
-template <int PP>
-__device__ __forceinline__ void fx_chol_solve(const double (&L)[Tri<PP>::SIZE], double (&b)[PP]) {
-#pragma unroll
-    for (int i = 0; i < PP; ++i) {
-        b[i] *= L[Tri<PP>::at(i, i)];
-#pragma unroll
-        for (int k = 0; k < PP; ++k)
-            if (k > i) b[k] = fma(-L[Tri<PP>::at(k, i)], b[i], b[k]);
-    }
-#pragma unroll
-    for (int ii = 0; ii < PP; ++ii) {
-        const int i = PP - 1 - ii;
-        b[i] *= L[Tri<PP>::at(i, i)];
-#pragma unroll
-        for (int k = 0; k < PP; ++k)
-            if (k < i) b[k] = fma(-L[Tri<PP>::at(i, k)], b[i], b[k]);
-    }
-}
-
-// log det of the factored matrix: -2 sum log(1 / L_jj)
-template <int PP>
-__device__ __forceinline__ double fx_chol_logdet(const double (&L)[Tri<PP>::SIZE]) {
-    double s = 0.0;
-#pragma unroll
-    for (int c = 0; c < PP; ++c) s += log(L[Tri<PP>::at(c, c)]);
-    return -2.0 * s;
-}
-
-// Cholesky for the Firth path: also refuses pivots below 1e-13 of the largest diagonal entry, so
-// that (numerically) singular information matrices take the pinv / det route of the reference
-// (psb_sym_pinv_logdet, psb_fixed.cuh) instead of being inverted through a meaningless pivot.
-template <int PP>
-__device__ __forceinline__ bool fx_chol_firth(double (&A)[Tri<PP>::SIZE]) {
-    double dmax = 0.0;
-#pragma unroll
-    for (int j = 0; j < PP; ++j) dmax = fmax(dmax, A[Tri<PP>::at(j, j)]);
-    bool ok = isfinite(dmax);
-    const double floor_ = 1e-13 * dmax;
-#pragma unroll
-    for (int j = 0; j < PP; ++j) {
-        const double d = A[Tri<PP>::at(j, j)];
-        if (!(d > floor_)) ok = false;
-        const double inv = rsqrt(d);
-        A[Tri<PP>::at(j, j)] = inv;
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-            if (i > j) A[Tri<PP>::at(i, j)] *= inv;
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-#pragma unroll
-            for (int k = 0; k < PP; ++k)
-                if (i > j && k > j && k <= i)
-                    A[Tri<PP>::at(i, k)] = fma(-A[Tri<PP>::at(i, j)], A[Tri<PP>::at(k, j)], A[Tri<PP>::at(i, k)]);
-    }
-    return ok;
-}
-
-// Singular H: pinv (when WANT_V) and log det by eigendecomposition, through local-memory copies so
-// that the caller's arrays stay in registers.
-template <int PP, bool WANT_V>
-__device__ __forceinline__ double fx_singular(const double (&H)[Tri<PP>::SIZE], double (&V)[Tri<PP>::SIZE],
-                                              int p_active) {
-    double Hl[Tri<PP>::SIZE], Vl[Tri<PP>::SIZE], A[PP * PP], Q[PP * PP];
-#pragma unroll
-    for (int e = 0; e < Tri<PP>::SIZE; ++e) Hl[e] = H[e];
-    const double ld = psb_sym_pinv_logdet(Hl, WANT_V ? Vl : nullptr, PP, p_active, A, Q);
-    if (WANT_V) {
-#pragma unroll
-        for (int e = 0; e < Tri<PP>::SIZE; ++e) V[e] = Vl[e];
-    }
-    return ld;
-}
-
-// statsmodels' Newton step matrix X'WX/n - 1e-10 I (the ridge lands on the NEGATIVE definite
-// hessian, base/model.py:fit + base/optimizer.py:_fit_newton) can turn indefinite in separated
-// data, where the reference's LU solve simply carries on.  L D L' without pivoting solves the
-// same system for any matrix with non-zero leading minors; a zero / non-finite pivot is the
-// analogue of numpy's "Singular matrix".  Unit lower L below the diagonal, 1 / d_j on it.
-template <int PP>
-__device__ __forceinline__ bool fx_ldl(double (&A)[Tri<PP>::SIZE]) {
-    bool ok = true;
-#pragma unroll
-    for (int j = 0; j < PP; ++j) {
-        const double d = A[Tri<PP>::at(j, j)];
-        if (d == 0.0 || !isfinite(d)) ok = false;
-        const double inv = 1.0 / d;
-        A[Tri<PP>::at(j, j)] = inv;
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-#pragma unroll
-            for (int k = 0; k < PP; ++k)
-                if (i > j && k > j && k <= i)
-                    A[Tri<PP>::at(i, k)] = fma(-A[Tri<PP>::at(i, j)] * inv, A[Tri<PP>::at(k, j)], A[Tri<PP>::at(i, k)]);
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-            if (i > j) A[Tri<PP>::at(i, j)] *= inv;
-    }
-    return ok;
-}
-
-// b := (L D L')^-1 b
-template <int PP>
-__device__ __forceinline__ void fx_ldl_solve(const double (&L)[Tri<PP>::SIZE], double (&b)[PP]) {
-#pragma unroll
-    for (int i = 0; i < PP; ++i) {
-#pragma unroll
-        for (int k = 0; k < PP; ++k)
-            if (k > i) b[k] = fma(-L[Tri<PP>::at(k, i)], b[i], b[k]);
-    }
-#pragma unroll
-    for (int i = 0; i < PP; ++i) b[i] *= L[Tri<PP>::at(i, i)];
-#pragma unroll
-    for (int ii = 0; ii < PP; ++ii) {
-        const int i = PP - 1 - ii;
-#pragma unroll
-        for (int k = 0; k < PP; ++k)
-            if (k < i) b[k] = fma(-L[Tri<PP>::at(i, k)], b[i], b[k]);
-    }
-}
-
-// Straightforward, register-friendly inverse: solve for each unit vector (PP solves).  Used by
-// the Firth path only; V is returned packed (lower triangle).
-template <int PP>
-__device__ __forceinline__ void fx_inverse_from_chol(const double (&L)[Tri<PP>::SIZE],
-                                                     double (&V)[Tri<PP>::SIZE]) {
-#pragma unroll
-    for (int c = 0; c < PP; ++c) {
-        double e[PP];
-#pragma unroll
-        for (int i = 0; i < PP; ++i) e[i] = (i == c) ? 1.0 : 0.0;
-        fx_chol_solve<PP>(L, e);
-#pragma unroll
-        for (int i = 0; i < PP; ++i)
-            if (i >= c) V[Tri<PP>::at(i, c)] = e[i];
-    }
-}
+#include "psb_fixed_dev.cuh"
 
 // Row of the design for sample i (internal order: Z_0 = 1, Z_1.., then k, then zero padding).
 template <int PP>
@@ -322,31 +138,6 @@ __device__ __forceinline__ double fx_loglike(const FxArgs &a, const uint32_t *xr
 }
 
 __device__ __forceinline__ void fx_write_failed(const FxArgs &a, int v, uint32_t f) {
-    a.flags[v] = f;
-}
-
-// Publishes a fitted variant: LRT against the matching null, lrt filter, result columns.
-template <int PP, class BetaT>
-__device__ __forceinline__ void fx_publish(const FxArgs &a, int v, uint32_t f, const BetaT &beta,
-                                           double bse, double fit_llf, double null_llf) {
-    const double lrstat = -2.0 * (null_llf - fit_llf);          // model.py:336, :366
-    double p = 1.0;
-    if (lrstat > 0.0) p = psb_chi2_sf1(lrstat);      // NaN compares false: p stays 1, as in the reference
-    double kbeta = 0.0;
-#pragma unroll
-    for (int c = 0; c < PP; ++c)
-        if (c == a.q) kbeta = beta[c];
-    if (p > a.lrt_pvalue || !isfinite(p) || !isfinite(kbeta)) {   // model.py:384
-        f |= PSB_F_LRT_FAILED | PSB_F_FILTER;
-        atomicAdd(&a.counters[2], 1);
-    }
-    a.pvalue[v] = p;
-    a.beta[v] = kbeta;
-    a.bse[v] = bse;
-    a.intercept[v] = beta[0];
-#pragma unroll
-    for (int c = 1; c < PP; ++c)
-        if (c < a.q) a.betas[(size_t)v * (a.q - 1) + (c - 1)] = beta[c];
     a.flags[v] = f;
 }
 
@@ -497,7 +288,7 @@ k_fixed_logit(FxArgs a, const int32_t *__restrict__ idx, int n_tested) {
             // numpy.linalg.inv: 'Singular matrix'.  Variant fits keep the plain test (quasi-separated fits
             // have legitimately tiny pivots, and the reference's LU carries on through them); the null
             // fit, where the answer decides between Newton's result and the Powell fallback
-            // (model.py:132-137), calls every pivot below 1e-13 of the diagonal singular.
+            // (model.py:132-137), recognises numerically dependent columns (fx_chol_firth).
             if (!(a.has_x ? fx_chol<PP>(H) : fx_chol_firth<PP>(H))) {
                 fail = PSB_F_MATRIX_INV;
             } else if (a.has_x) {
@@ -1001,6 +792,10 @@ extern "C" int psb_fixed_setup(psb_ctx *c, int32_t N, int32_t q, const double *Z
                 PSB_CUDA(cudaMemcpy(c->d_fixed_const, Hzz.data(), Hzz.size() * sizeof(double),
                                     cudaMemcpyHostToDevice));
                 c->logit_first_step = true;
+                if (!getenv("PSB_LOGIT_FAST") || atoi(getenv("PSB_LOGIT_FAST")) != 0) {
+                    rc = psb_fixed_fast_setup(c, Z, c->h_warm.data());
+                    if (rc) return rc;
+                }
             }
         }
     }
@@ -1021,7 +816,8 @@ static FxArgs fx_args(psb_ctx *c, const psb_params *prm, int has_x) {
     a.q = c->q;
     a.has_x = has_x;
     a.start0 = log(c->y_mean / (1.0 - c->y_mean));
-    a.use_warm = (has_x && (int)c->h_warm.size() == c->q && c->q + 1 <= FX_MAXP) ? 1 : 0;
+    static const bool warm_ok = !(getenv("PSB_LOGIT_WARM") && atoi(getenv("PSB_LOGIT_WARM")) == 0);   // debugging
+    a.use_warm = (warm_ok && has_x && (int)c->h_warm.size() == c->q && c->q + 1 <= FX_MAXP) ? 1 : 0;
     for (int k = 0; k < FX_MAXP; ++k) a.warm[k] = (a.use_warm && k < c->q) ? c->h_warm[k] : 0.0;
     a.null_llf = c->null_llf;
     a.null_firth = c->null_firth;
@@ -1042,25 +838,26 @@ static FxArgs fx_args(psb_ctx *c, const psb_params *prm, int has_x) {
 }
 
 template <int PP>
-static void launch_logit(psb_ctx *c, const FxArgs &a, int n, int grid) {
+static void launch_logit(psb_ctx *c, const FxArgs &a, int n, int grid, const int32_t *list) {
     static const int minb = getenv("PSB_LOGIT_MINB") ? atoi(getenv("PSB_LOGIT_MINB")) : 2;
-    if (PP == 12 && minb == 3) k_fixed_logit<PP, 3><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
-    else if (PP == 12 && minb == 4) k_fixed_logit<PP, 4><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
-    else k_fixed_logit<PP, 2><<<grid, 128, 0, c->stream>>>(a, c->d_idx, n);
+    if (PP == 12 && minb == 3) k_fixed_logit<PP, 3><<<grid, 128, 0, c->stream>>>(a, list, n);
+    else if (PP == 12 && minb == 4) k_fixed_logit<PP, 4><<<grid, 128, 0, c->stream>>>(a, list, n);
+    else k_fixed_logit<PP, 2><<<grid, 128, 0, c->stream>>>(a, list, n);
 }
 template <int PP>
 static void launch_firth(psb_ctx *c, const FxArgs &a, int n, int grid) {
     k_fixed_firth<PP><<<grid, 128, 0, c->stream>>>(a, n);
 }
 
-static int fx_dispatch(psb_ctx *c, const FxArgs &a, int n, bool firth) {
+static int fx_dispatch(psb_ctx *c, const FxArgs &a, int n, bool firth, const int32_t *list = nullptr) {
     if (n <= 0) return PSB_OK;
+    if (!list) list = c->d_idx;
     const int p = a.q + (a.has_x ? 1 : 0);
     const int warps = 4;
     int grid = std::min(psb_div_up(n, warps), c->sm_count * 8);
-    if (p <= 4) firth ? launch_firth<4>(c, a, n, grid) : launch_logit<4>(c, a, n, grid);
-    else if (p <= 8) firth ? launch_firth<8>(c, a, n, grid) : launch_logit<8>(c, a, n, grid);
-    else if (p <= 12) firth ? launch_firth<12>(c, a, n, grid) : launch_logit<12>(c, a, n, grid);
+    if (p <= 4) firth ? launch_firth<4>(c, a, n, grid) : launch_logit<4>(c, a, n, grid, list);
+    else if (p <= 8) firth ? launch_firth<8>(c, a, n, grid) : launch_logit<8>(c, a, n, grid, list);
+    else if (p <= 12) firth ? launch_firth<12>(c, a, n, grid) : launch_logit<12>(c, a, n, grid, list);
     else   // wider designs: generic shared-memory solver (psb_fixed_gen.cu)
         return psb_fixed_gen_launch(c, a, firth ? (a.has_x ? FXG_FIRTH : FXG_NULL_FIRTH)
                                                 : (a.has_x ? FXG_LOGIT : FXG_NULL), n, 0, 0, nullptr);
@@ -1101,6 +898,7 @@ static int fx_run_null(psb_ctx *c, int mode, std::vector<double> &h) {
 }
 
 extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
+    PSB_NVTX("psb_run_fixed");
     PSB_REQUIRE(c && prm, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(c->model == PSB_MODEL_FIXED, PSB_ERR_STATE, "psb_run_fixed without psb_fixed_setup");
     PSB_REQUIRE((prm->continuous != 0) == (c->continuous != 0), PSB_ERR_ARG,
@@ -1156,7 +954,24 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
                 a.sums_ld = c->C;
                 a.HzzInv = c->d_fixed_const;
             }
-            rc = fx_dispatch(c, a, n_tested, false);
+            if (c->fx_Q > 0 && a.sums) {
+                // fast path over every tested variant; what it hands back (no clean convergence, a
+                // fit far from the null model) goes through the reference-faithful kernel from the
+                // reference's start vector
+                rc = psb_fixed_fast_launch(c, a, n_tested);
+                if (rc) return rc;
+                PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost,
+                                         c->stream));
+                PSB_CUDA(cudaStreamSynchronize(c->stream));
+                c->fixed_slow = h_cnt[6];
+                FxArgs as = a;
+                as.use_warm = 0;
+                as.sums = nullptr;
+                rc = fx_dispatch(c, as, h_cnt[6], false, c->d_idx3);
+            } else {
+                c->fixed_slow = 0;
+                rc = fx_dispatch(c, a, n_tested, false);
+            }
             if (rc) return rc;
             PSB_CUDA(cudaMemcpyAsync(h_cnt, c->d_counters, sizeof(h_cnt), cudaMemcpyDeviceToHost,
                                      c->stream));
@@ -1208,6 +1023,7 @@ extern "C" int psb_lineage_setup(psb_ctx *c, int32_t N, int32_t q, const double 
 }
 
 extern "C" int psb_run_lineage(psb_ctx *c, int32_t mode) {
+    PSB_NVTX("psb_run_lineage");
     PSB_REQUIRE(c, PSB_ERR_ARG, "ctx is NULL");
     PSB_REQUIRE(c->d_Zlin && c->ran, PSB_ERR_STATE, "psb_run_lineage needs psb_lineage_setup and a finished psb_run_*");
     PSB_CUDA(cudaSetDevice(c->device));

@@ -34,6 +34,19 @@ struct FxArgs {
 };
 
 
+// extra arguments of the fast Logit path (psb_fixed_fast.cu)
+struct FxFast {
+    const double *Zi;     // [Wn][Q-1][32] covariate columns 1..Q-1 interleaved per 32-sample word (fp64)
+    const float *Zf;      // the same in fp32
+    const double *W0;     // [Wn * 32] null-model weights pi0 (1 - pi0), 0 on padding samples
+    const double *Hzz0;   // packed lower triangle of Z'W0Z (Q columns; unit diagonal on padding columns)
+    double zmax[FX_MAXP]; // max |z_c| per column
+    int32_t *slow_list;   // variants handed to the reference-faithful kernel (length in counters[6])
+};
+int psb_fixed_fast_setup(psb_ctx *c, const double *Z, const double *warm);
+void psb_fixed_fast_free(psb_ctx *c);
+int psb_fixed_fast_launch(psb_ctx *c, const FxArgs &a, int n);
+
 // Singular information matrices in Firth regression.  model.fit_firth calls np.linalg.pinv on
 // -hessian (model.py:450) and firth_likelihood takes log(det(-hessian)) (model.py:410): with an
 // exactly collinear design (the reference's own test has variant == covariate,

@@ -113,11 +113,11 @@ __device__ void gen_eval(const FxArgs &a, const GenWs &ws, const uint32_t *xrow,
 
 // In-place right-looking Cholesky of the packed matrix (diagonal stored as 1 / L_jj); returns
 // false when a pivot is not positive / finite.
-__device__ bool gen_chol(double *A, int P, int lane, double floor_abs = 0.0) {
+__device__ bool gen_chol(double *A, int P, int lane, const double *orig_diag = nullptr, double rel_floor = 0.0) {
     bool ok = true;
     for (int j = 0; j < P; ++j) {
         const double d = A[tri_at(j, j)];
-        if (!(d > floor_abs) || !isfinite(d)) ok = false;
+        if (!(d > (orig_diag ? rel_floor * orig_diag[j] : 0.0)) || !isfinite(d)) ok = false;
         const double inv = rsqrt(d);
         __syncwarp();
         if (lane == 0) A[tri_at(j, j)] = inv;
@@ -224,12 +224,13 @@ __device__ void gen_publish(const FxArgs &a, int v, uint32_t f, const double *be
     a.flags[v] = f;
 }
 
-// Firth path: pivots below 1e-13 of the largest diagonal entry count as singular (fx_chol_firth)
-__device__ bool gen_chol_firth(double *A, int P, int lane) {
-    double dmax = 0.0;
-    for (int j = 0; j < P; ++j) dmax = fmax(dmax, A[tri_at(j, j)]);
-    if (!isfinite(dmax)) return false;
-    return gen_chol(A, P, lane, 1e-13 * dmax);
+// Numerically singular matrices (fx_chol_firth, psb_fixed_dev.cuh): a pivot below rel_floor of its
+// column's own diagonal entry.  `diag`: P doubles of scratch for the original diagonal.
+__device__ bool gen_chol_firth(double *A, int P, int lane, double *diag, double rel_floor = 1e-13) {
+    __syncwarp();
+    for (int j = lane; j < P; j += 32) diag[j] = A[tri_at(j, j)];
+    __syncwarp();
+    return gen_chol(A, P, lane, diag, rel_floor);
 }
 
 // Singular information matrix (psb_sym_pinv_logdet, psb_fixed.cuh): lane 0 works in the design-tile
@@ -308,7 +309,7 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
             gen_eval(a, ws, xrow, yrow, lane, ws.beta, p, maxdev, llf_cur);
             double hxx_new = 0.0;
             for (int i = 0; i < 1000 && ok; ++i) {
-                if (gen_chol_firth(ws.H, P, lane)) {
+                if (gen_chol_firth(ws.H, P, lane, ws.g)) {
                     fl_cur = -(llf_cur + 0.5 * gen_logdet(ws.H, P));
                     // V = (L L')^-1, column by column (only the lower triangle is kept)
                     for (int c0 = 0; c0 < P; ++c0) {
@@ -385,7 +386,7 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
                     for (int e = lane; e < ws.tri; e += 32) ws.V[e] = ws.H[e];
                     __syncwarp();
                     double ld;
-                    if (gen_chol_firth(ws.V, P, lane)) ld = gen_logdet(ws.V, P);
+                    if (gen_chol_firth(ws.V, P, lane, ws.g)) ld = gen_logdet(ws.V, P);
                     else ld = gen_singular(ws, nullptr, p, scratchQ, lane);
                     fl_new = -(llf_new + 0.5 * ld);
                     if (!(fl_new > fl_cur)) break;
@@ -463,7 +464,7 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
         bool have_factor = false;
         if (!fail) {
             // (pivot floor for the null fit only: see k_fixed_logit)
-            have_factor = mode == FXG_NULL ? gen_chol_firth(ws.H, P, lane) : gen_chol(ws.H, P, lane);
+            have_factor = mode == FXG_NULL ? gen_chol_firth(ws.H, P, lane, ws.g, 1e-13) : gen_chol(ws.H, P, lane);
             if (!have_factor) fail = PSB_F_MATRIX_INV;
         }
         if (mode == FXG_LINEAGE) {

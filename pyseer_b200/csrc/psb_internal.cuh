@@ -20,6 +20,15 @@
 
 void psb_set_error(const char *fmt, ...);
 
+// NVTX ranges around the phases of the C ABI (visible in Nsight Systems / ncu --nvtx; header-only
+// NVTX 3, no link dependency, a no-op without an attached tool)
+#include <nvtx3/nvToolsExt.h>
+struct psb_nvtx_range {
+    explicit psb_nvtx_range(const char *name) { nvtxRangePushA(name); }
+    ~psb_nvtx_range() { nvtxRangePop(); }
+};
+#define PSB_NVTX(name) psb_nvtx_range psb_nvtx_range_##__LINE__(name)
+
 #define PSB_CUDA(call)                                                              \
     do {                                                                            \
         cudaError_t e_ = (call);                                                    \
@@ -102,6 +111,12 @@ struct psb_ctx {
     double *d_Zlin = nullptr;     // lineage design [q_lin][Npad] (model.fit_lineage_effect)
     int q_lin = 0, n_lin = 0;
     bool logit_first_step = false; // closed-form first Newton step operands are set up
+    // fast Logit path (psb_fixed_fast.cu): interleaved covariates (fp64, fp32), null weights, Z'W0Z
+    double *d_fx_Zi = nullptr, *d_fx_W0 = nullptr, *d_fx_H0 = nullptr;
+    float *d_fx_Zf = nullptr;
+    std::vector<double> fx_zmax;
+    int fx_Q = 0;                  // 0: not set up
+    int fixed_slow = 0;            // variants of the last run that took the exact kernel after the fast one
     std::vector<double> h_warm;   // null-model Logit parameters (warm start), q
 
     // ---- variants ----
@@ -140,6 +155,7 @@ struct psb_ctx {
     size_t sums_cap = 0;
     int32_t *d_idx = nullptr;     // compacted tested variant ids (cap + 256)
     int32_t *d_idx2 = nullptr;    // second list (Firth candidates)
+    int32_t *d_idx3 = nullptr;    // third list (variants the fast Logit kernel hands to the exact one)
     double *d_gen_scratch = nullptr;   // generic solver: per-warp scratch of the singular-matrix path
     size_t gen_scratch_cap = 0;
     int *d_counters = nullptr;    // [8] device counters

@@ -9,7 +9,11 @@
 // Host-only code; lives in the same shared library as the kernels.
 #include <zlib.h>
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
+#include <atomic>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -20,6 +24,9 @@
 
 struct psb_reader {
     gzFile fh = nullptr;
+    FILE *raw = nullptr;                    // BGZF input: read and inflated block-parallel (bgzf_fill)
+    std::vector<unsigned char> bgzf_in;
+    bool bgzf_err = false;
     int var_type = 0;                       // 0 = k-mers, 1 = Rtab, 2 = VCF
     int n_samples = 0;
     std::vector<std::string> names;         // owns the keys of `index`
@@ -41,8 +48,102 @@ struct psb_reader {
     std::vector<int32_t> vcf_reflen;
 };
 
+// ---- BGZF (bgzip) input: independent deflate blocks of <= 64 KiB, inflated on the parser threads ----
+// A bgzip file is a series of gzip members whose extra field carries the member's size ('B','C'
+// subfield, SAM specification 4.1).  Members do not depend on each other, so a group of them is
+// inflated in parallel -- plain gzip is one serial deflate stream (18.8 k variants/s at N = 5000
+// however many threads parse); bgzip'ed k-mer files decompress at (threads) x that rate.
+static bool bgzf_probe(FILE *f) {
+    unsigned char h[18];
+    const size_t got = fread(h, 1, sizeof(h), f);
+    rewind(f);
+    return got == sizeof(h) && h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4) && h[10] == 6 && h[11] == 0 &&
+           h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
+}
+
+struct bgzf_block {
+    size_t in_off, in_len;      // deflate payload inside r->bgzf_in
+    size_t out_off, out_len;    // where its text lands in r->buf
+};
+
+static int bgzf_inflate_one(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_len) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return -1;
+    zs.next_in = const_cast<unsigned char *>(in);
+    zs.avail_in = (uInt)in_len;
+    zs.next_out = out;
+    zs.avail_out = (uInt)out_len;
+    const int rc = inflate(&zs, Z_FINISH);
+    const bool ok = rc == Z_STREAM_END && zs.total_out == out_len;
+    inflateEnd(&zs);
+    return ok ? 0 : -1;
+}
+
+// next group of blocks -> r->buf; false at end of file (or on a corrupt block: r->bgzf_err set)
+static bool bgzf_fill(psb_reader *r) {
+    const size_t group_bytes = 8u << 20;                 // compressed bytes per group
+    std::vector<unsigned char> &in = r->bgzf_in;
+    in.clear();
+    std::vector<bgzf_block> blocks;
+    size_t out_total = 0;
+    while (in.size() < group_bytes) {
+        unsigned char h[18];
+        const size_t got = fread(h, 1, sizeof(h), r->raw);
+        if (got == 0) break;
+        if (got != sizeof(h) || h[0] != 0x1f || h[1] != 0x8b || !(h[3] & 4) || h[12] != 'B' || h[13] != 'C') {
+            r->bgzf_err = true;
+            return false;
+        }
+        const size_t bsize = (size_t)h[16] + ((size_t)h[17] << 8) + 1;       // whole member
+        const size_t xlen = (size_t)h[10] + ((size_t)h[11] << 8);
+        const size_t head = 12 + xlen;
+        if (bsize < head + 8) { r->bgzf_err = true; return false; }
+        const size_t rest = bsize - sizeof(h);
+        const size_t at = in.size();
+        in.resize(at + rest);
+        if (fread(in.data() + at, 1, rest, r->raw) != rest) { r->bgzf_err = true; return false; }
+        const size_t payload_off = at + (head - sizeof(h));
+        const size_t payload_len = bsize - head - 8;
+        const unsigned char *tr = in.data() + at + rest - 8;
+        const size_t isize = (size_t)tr[4] | ((size_t)tr[5] << 8) | ((size_t)tr[6] << 16) | ((size_t)tr[7] << 24);
+        if (isize == 0) continue;                                            // the empty end-of-file member
+        blocks.push_back({payload_off, payload_len, out_total, isize});
+        out_total += isize;
+    }
+    if (blocks.empty()) return false;
+    if (r->buf.size() < out_total) r->buf.resize(out_total);
+    std::atomic<int> next(0), bad(0);
+    auto work = [&]() {
+        for (;;) {
+            const int b = next.fetch_add(1);
+            if (b >= (int)blocks.size()) return;
+            const bgzf_block &k = blocks[b];
+            if (bgzf_inflate_one(in.data() + k.in_off, k.in_len, (unsigned char *)r->buf.data() + k.out_off, k.out_len))
+                bad.store(1);
+        }
+    };
+    const int T = std::max(1, std::min<int>(r->n_threads, (int)blocks.size()));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work);
+    work();
+    for (auto &th : pool) th.join();
+    if (bad.load()) { r->bgzf_err = true; return false; }
+    r->pos = 0;
+    r->len = out_total;
+    return true;
+}
+
 static bool reader_fill(psb_reader *r) {
     if (r->eof) return false;
+    if (r->raw) {
+        if (!bgzf_fill(r)) {
+            r->eof = true;
+            r->pos = r->len = 0;
+            return false;
+        }
+        return true;
+    }
     int got = gzread(r->fh, r->buf.data(), (unsigned)r->buf.size());
     if (got <= 0) {
         r->eof = true;
@@ -77,11 +178,20 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
     PSB_REQUIRE(var_type >= 0 && var_type <= 2, PSB_ERR_ARG, "var_type must be 0 (k-mers), 1 (Rtab) or 2 (VCF)");
     PSB_REQUIRE(n_samples > 0, PSB_ERR_ARG, "no samples");
     *out = nullptr;
-    gzFile fh = gzopen(path, "rb");
-    PSB_REQUIRE(fh, PSB_ERR_ARG, "cannot open %s", path);
-    gzbuffer(fh, 1 << 20);
+    FILE *raw = fopen(path, "rb");
+    PSB_REQUIRE(raw, PSB_ERR_ARG, "cannot open %s", path);
+    const bool bgzf = bgzf_probe(raw) && !(getenv("PSB_BGZF") && atoi(getenv("PSB_BGZF")) == 0);
+    gzFile fh = nullptr;
+    if (!bgzf) {
+        fclose(raw);
+        raw = nullptr;
+        fh = gzopen(path, "rb");
+        PSB_REQUIRE(fh, PSB_ERR_ARG, "cannot open %s", path);
+        gzbuffer(fh, 1 << 20);
+    }
     psb_reader *r = new psb_reader();
     r->fh = fh;
+    r->raw = raw;
     r->var_type = var_type;
     r->n_samples = n_samples;
     r->buf.resize(4 << 20);
@@ -92,7 +202,8 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
     if (var_type == 1) {
         // header: first field is the row label, the rest are sample names in column order
         if (!reader_getline(r)) {
-            gzclose(fh);
+            if (fh) gzclose(fh);
+            if (raw) fclose(raw);
             delete r;
             psb_set_error("%s: empty Rtab file", path);
             return PSB_ERR_ARG;
@@ -138,7 +249,8 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
             break;
         }
         if (!found) {
-            gzclose(fh);
+            if (fh) gzclose(fh);
+            if (raw) fclose(raw);
             delete r;
             psb_set_error("%s: no #CHROM header line found; is this a VCF file?", path);
             return PSB_ERR_ARG;
@@ -151,6 +263,7 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
 extern "C" int psb_reader_close(psb_reader *r) {
     if (!r) return PSB_OK;
     if (r->fh) gzclose(r->fh);
+    if (r->raw) fclose(r->raw);
     delete r;
     return PSB_OK;
 }
@@ -361,6 +474,7 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
             r->line.swap(r->pending);
             r->have_pending = false;
         } else if (!reader_getline(r)) {
+            PSB_REQUIRE(!r->bgzf_err, PSB_ERR_ARG, "corrupt BGZF block in the variant file");
             r->drained = true;
             break;
         }

@@ -438,6 +438,7 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
 }
 
 extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
+    PSB_NVTX("psb_run_lmm");
     PSB_REQUIRE(c && prm, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(c->model == PSB_MODEL_LMM, PSB_ERR_STATE, "psb_run_lmm without psb_lmm_setup");
     PSB_CUDA(cudaSetDevice(c->device));

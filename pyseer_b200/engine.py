@@ -143,6 +143,20 @@ class Engine(object):
         check(self.lib.psb_eigh(self._ctx, n, self._dptr(A), self._dptr(w), self._dptr(V)))
         return w, V
 
+    def spectral(self, K, X, Xdagger):
+        """LMM.setSU_fromK on the device (psb_spectral): eigh of regress(regress(K + I)')."""
+        K = np.ascontiguousarray(K, dtype=np.float64)
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Xd = np.ascontiguousarray(Xdagger, dtype=np.float64)
+        n, d = X.shape
+        if K.shape != (n, n) or Xd.shape != (d, n):
+            raise ValueError('shape mismatch')
+        w = np.empty(n, dtype=np.float64)
+        V = np.empty((n, n), dtype=np.float64)
+        check(self.lib.psb_spectral(self._ctx, n, d, self._dptr(K), self._dptr(X), self._dptr(Xd),
+                                    self._dptr(w), self._dptr(V)))
+        return w, V
+
     # -- kinship ------------------------------------------------------------------------
     def kinship_begin(self, n_samples):
         check(self.lib.psb_kinship_begin(self._ctx, int(n_samples)))

@@ -54,10 +54,25 @@ class KinshipLMM(object):
             if self.K is None:
                 raise Exception("No Kernel is set. Cannot return U and S.")
             N = self.K.shape[0]
-            self.K.flat[::N + 1] += 1.0
-            K_ = self._regress(self.K)
-            K_ = self._regress(K_.T)
-            S, U = self._eigh(K_)
+            S = U = None
+            mode = os.environ.get('PYSEER_B200_EIGH', 'auto')
+            if (mode == 'device' or (mode != 'numpy' and N >= 2048)) and self.D <= 16:
+                # projection P (K + I) P and eigh in one device call (psb_spectral)
+                if self._Xdagger is None:
+                    self._Xdagger = np.linalg.pinv(self.X)
+                if self._engine is None:
+                    self._engine = Engine(self.device)
+                try:
+                    S, U = self._engine.spectral(self.K, self.X, self._Xdagger)
+                except _lib.PsbError as e:
+                    if e.code != _lib.ERR_UNSUPPORTED:
+                        raise
+                    sys.stderr.write('cuSOLVER not available, eigendecomposition on the host\n')
+            if S is None:
+                self.K.flat[::N + 1] += 1.0
+                K_ = self._regress(self.K)
+                K_ = self._regress(K_.T)
+                S, U = self._eigh(K_)
             self.U = np.ascontiguousarray(U[:, self.D:N])
             self.S = S[self.D:N] - 1.0
         return self.S, self.U

@@ -77,7 +77,7 @@ def _compare(cols, ref, names, what, firth_noise=0):
         a, b = cols[name][keep], ref['res'][keep, j]
         fin = np.isfinite(b)
         mism = np.where(np.isfinite(a) != fin)[0]
-        assert mism.size == 0, (what, name, mism[:10], a[mism[:10]], b[mism[:10]], ref['flags'][mism[:10]])
+        assert mism.size == 0, (what, name, np.where(keep)[0][mism[:10]], a[mism[:10]], b[mism[:10]])
         big = fin & (np.abs(b) > 1e-290)
         # Signed coefficients pass through zero: among 1e5 variants x 12 coefficients some are 1e-6
         # of their standard error by chance, and a relative error against such a value measures
@@ -92,7 +92,7 @@ def _compare(cols, ref, names, what, firth_noise=0):
             floor = 1e-9 if name == 'extra' else 0.0
         err = np.abs(a[big] - b[big]) / np.maximum(np.abs(b[big]), floor)
         worst[name] = float(err.max()) if err.size else 0.0
-        assert worst[name] < RTOL, (what, name, worst[name], np.where(big)[0][int(np.argmax(err))])
+        assert worst[name] < RTOL, (what, name, worst[name], np.where(keep)[0][np.where(big)[0][int(np.argmax(err))]])
         assert np.all(np.abs(a[fin & ~big]) < 1e-280), (what, name)
     return worst
 

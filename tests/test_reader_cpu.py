@@ -250,3 +250,43 @@ def test_vcf_short_and_empty_genotype_cells(tmp_path):
     m = unpack_rows(b.missing, 5)[0]
     assert list(x) == [0, 1, 0, 0, 1]          # e: '1/' carries through its called haplotype
     assert list(m) == [1, 0, 0, 1, 0]          # a: no GT field at all; d: empty GT
+
+
+def _write_bgzf(path, data, block=60000):
+    """bgzip-style file: independent gzip members with the 'BC' extra field (SAM spec 4.1)."""
+    import struct
+    import zlib
+    with open(path, 'wb') as fh:
+        for o in list(range(0, len(data), block)) + [None]:
+            chunk = b'' if o is None else data[o:o + block]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = co.compress(chunk) + co.flush()
+            bsize = 12 + 6 + len(payload) + 8
+            fh.write(b'\x1f\x8b\x08\x04' + b'\x00' * 4 + b'\x00\xff' + struct.pack('<H', 6) +
+                     b'BC' + struct.pack('<HH', 2, bsize - 1) + payload +
+                     struct.pack('<II', zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+
+
+def test_bgzf_input_equals_gzip_input(tmp_path):
+    """bgzip'ed k-mer files are inflated block-parallel on the parser threads; rows, names and batch
+    boundaries equal those of the plain-gzip file, whatever the thread count (lines straddle blocks)."""
+    p = _pheno()
+    with gzip.open(os.path.join(GOLDEN, 'kmers.gz'), 'rb') as fh:
+        text = fh.read()
+    text = text * 8                                    # 1600 lines, many blocks
+    bg = str(tmp_path / 'kmers.bgz')
+    _write_bgzf(bg, text, block=7001)
+    gz = str(tmp_path / 'kmers.gz')
+    with gzip.open(gz, 'wb') as fh:
+        fh.write(text)
+    out = {}
+    for tag, path, threads in (('gz', gz, 1), ('bg1', bg, 1), ('bg5', bg, 5)):
+        rd = VariantReader('kmers', path, p, threads=threads)
+        with contextlib.redirect_stderr(io.StringIO()):
+            out[tag] = [(b.names, b.bits.copy()) for b in rd.batches(300)]
+        rd.close()
+    assert len(out['gz']) == 6
+    for tag in ('bg1', 'bg5'):
+        assert len(out[tag]) == len(out['gz'])
+        for (n1, b1), (n2, b2) in zip(out['gz'], out[tag]):
+            assert n1 == n2 and np.array_equal(b1, b2)
