@@ -68,8 +68,9 @@ def parse_args(argv=None):
     ap.add_argument('--samples', type=int, default=0, help='0 = the config default')
     ap.add_argument('--kmers-per-gpu', type=int, default=0, help='0 = the config default')
     ap.add_argument('--precision', type=int,
-                    default=int(os.environ.get('PYSEER_B200_LMM_PRECISION', '5')),
-                    help='0 = FP64 CUDA-core contraction, 3..8 = exact int8-slice tcgen05 path')
+                    default=int(os.environ.get('PYSEER_B200_LMM_PRECISION', '46')),
+                    help='0 = FP64 CUDA-core contraction, 3..7 = exact int8-slice tcgen05 path, 46 = two passes '
+                         '(4 slices, 6 again for the far tail)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-secondary', action='store_true')
@@ -371,8 +372,14 @@ class LmmWorkload(object):
     def run(self, eng):
         eng.run_lmm(continuous=self.continuous, **THRESH)
 
+    def slices(self):
+        """int8 slices of the working precision (precision 46: 4, with 6 again for the far tail)."""
+        return 4 if self.a.precision == 46 else self.a.precision
+
     def dtype(self):
         k = self.a.precision
+        if k == 46:
+            return 's8 x4 slices (x6 for F > 30) -> s32 (tcgen05) -> f64'
         return ('s8 x%d slices -> s32 (tcgen05) -> f64' % k) if k else 'f64'
 
     def check(self, st, bits_head, cols):
@@ -389,7 +396,7 @@ class LmmWorkload(object):
                 'min_pvalue': float(np.min(pv[ok]))}
 
     def roofline(self, tested, k_ms, run_ms, W, pk, pk_kind, dev_peaks):
-        n, J, k = self.n, self.n - 1, self.a.precision
+        n, J, k = self.n, self.n - 1, self.slices()
         tri = os.environ.get('PSB_TC_TRI', '1') != '0'
         # int8 multiply-adds the kernel issues per k-mer: k slices over N^2/2 (triangular form,
         # K stages of 256 samples from the diagonal down) or N (N-D) entries
@@ -421,7 +428,7 @@ class LmmWorkload(object):
                 'side_kernels_ms': run_ms - k_ms,
                 'hbm_read_frac': (tested * (W * 4 + 56) / (k_ms / 1e3) / 1e9) / pk['hbm_gbs'],
                 'algorithmic_bytes': tested * (W * 4 + 24.0),
-                'traffic': ncu_traffic('lmm:n=%d:kmers=%d:k=%d' % (n, self.kpg, k))}
+                'traffic': ncu_traffic('lmm:n=%d:kmers=%d:k=%d' % (n, self.kpg, self.a.precision))}
 
 
 class LmmBinaryWorkload(LmmWorkload):

@@ -103,7 +103,9 @@ int psb_sync(psb_ctx *ctx);
  * row-major) and eigenvalues S (lmm_cov.py:88-103) and h2 (lmm_cov.findH2).  Builds
  * the rotated operands used by fit_lmm_block (lmm.py:228-260).
  * precision: 0 = FP64 CUDA-core contraction; k in [3,7] = exact k-slice int8
- * tensor-core contraction (tcgen05).  Returns PSB_ERR_H2 when h2 is outside [0,1). */
+ * tensor-core contraction (tcgen05); 46 = two passes, 4 slices for every variant and 6 slices again
+ * for those whose F statistic exceeds 30 (the far tail, where the relative error of a p-value is
+ * F / 2 times that of the quadratic form).  Returns PSB_ERR_H2 when h2 is outside [0,1). */
 int psb_lmm_setup(psb_ctx *ctx, int32_t n_samples, int32_t n_cov, const double *X,
                   const double *y, const double *U, const double *S, double h2,
                   int32_t precision);

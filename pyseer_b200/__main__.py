@@ -81,8 +81,8 @@ def get_options(argv=None):
     ot.add_argument('--gpu-batch', type=int, default=48000,
                     help='variants per GPU submission (rounded to a multiple of --block_size)')
     ot.add_argument('--lmm-precision', type=int, default=None,
-                    help='0 = FP64 contraction, 3..7 = exact int8-slice tensor-core contraction '
-                         '(default 5)')
+                    help='0 = FP64 contraction, 3..7 = exact int8-slice tensor-core contraction, 46 = two '
+                         'passes: 4 slices, 6 again for the far tail (default)')
     ot.add_argument('--version', action='version', version='%(prog)s ' + __version__)
     return ap.parse_args(argv)
 
@@ -391,6 +391,8 @@ def main(argv=None):
 
     writer = threading.Thread(target=output_loop, daemon=True)
     writer.start()
+    import time
+    t_stream = time.time()
     try:
         for batch, r in runner.results(batches):
             if out_err:
@@ -413,6 +415,11 @@ def main(argv=None):
     if out_err:
         raise out_err[0]
     prefilter, tested, printed = counters['prefilter'], counters['tested'], counters['printed']
+    if os.environ.get('PYSEER_B200_TIMING'):
+        # streaming part only (reader -> GPU -> output), without the once-per-run set-up
+        dt = time.time() - t_stream
+        sys.stderr.write('pipeline: %d variants in %.3f s = %.0f variants/s\n'
+                         % (prefilter + tested, dt, (prefilter + tested) / max(dt, 1e-9)))
     reader.close()
     if patterns is not None:
         patterns.close()

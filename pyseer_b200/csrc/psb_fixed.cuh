@@ -39,6 +39,7 @@ struct FxFast {
     const double *Zi;     // [Wn][Q-1][32] covariate columns 1..Q-1 interleaved per 32-sample word (fp64)
     const float *Zf;      // the same in fp32
     const double *W0;     // [Wn * 32] null-model weights pi0 (1 - pi0), 0 on padding samples
+    const uint32_t *vbits; // [Wn padded to whole chunks] sample-valid bits (0 on padding words)
     const double *Hzz0;   // packed lower triangle of Z'W0Z (Q columns; unit diagonal on padding columns)
     double zmax[FX_MAXP]; // max |z_c| per column
     int32_t *slow_list;   // variants handed to the reference-faithful kernel (length in counters[6])

@@ -65,89 +65,174 @@ struct FastAcc {
     }
 };
 
-// exp(x) to ~1e-12 relative: x = (32 k + j) ln2/32 + r, |r| <= ln2/64, exp = 2^k * 2^(j/32) * e^r with
-// a 32-entry table (shared memory) and a degree-5 polynomial; 9 FP64 operations against ~35 of the
-// correctly rounded library exp.  The power of two is clamped to 2^+-1000 with two integer operations
-// (exp(-eta) only feeds 1 / (1 + .), which saturates long before).
-__constant__ double c_ff_exp[8] = {46.16624130844682903551758979206, /* 32 / ln 2 */
-                                   0.021660849392498290195, /* ln 2 / 32 */
-                                   1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 6755399441055744.0 /* 1.5 * 2^52 */, 0.0};
+// exp(x) to ~1e-14 relative: x = (32 k + j) ln2/32 + r, |r| <= ln2/64, exp = 2^k * 2^(j/32) * e^r with
+// a 32-entry table (shared memory) and a degree-5 polynomial (Estrin form: dependency depth 3); 10 FP64
+// operations against ~35 of the correctly rounded library exp.  The power of two is clamped to
+// 2^+-1000 with two integer operations (exp(-eta) only feeds 1 / (1 + .), which saturates long before).
+__constant__ double c_ff[16] = {46.16624130844682903551758979206, /* [0] 32 / ln 2 */
+                                0.021660849392498290195,          /* [1] ln 2 / 32 */
+                                1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, /* [2..5] */
+                                6755399441055744.0,               /* [6] 1.5 * 2^52 */
+                                0.69314718055994530942,           /* [7] ln 2 */
+                                2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0, /* [8..14] */
+                                2.0 / 17.0};
 __device__ __forceinline__ double ff_exp(double x, const double *__restrict__ tab) {
-    const double t = fma(x, c_ff_exp[0], c_ff_exp[6]);          // low word of t = rint(x * 32 / ln2)
+    const double t = fma(x, c_ff[0], c_ff[6]);                  // low word of t = rint(x * 32 / ln2)
     const int n = __double2loint(t);
-    const double kf = t - c_ff_exp[6];
-    const double r = fma(-kf, c_ff_exp[1], x);
-    double p = fma(r, c_ff_exp[2], c_ff_exp[3]);
-    p = fma(p, r, c_ff_exp[4]);
-    p = fma(p, r, c_ff_exp[5]);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    const double kf = t - c_ff[6];
+    const double r = fma(-kf, c_ff[1], x);
+    const double r2 = r * r;
+    const double pa = fma(r, c_ff[2], c_ff[3]);                 // 1/24 + r/120
+    const double pb = fma(r, c_ff[4], c_ff[5]);                 // 1/2 + r/6
+    const double pc = 1.0 + r;
+    const double p = fma(fma(pa, r2, pb), r2, pc);
     const double s = tab[n & 31] * p;
-    // scale by 2^(n >> 5): add to the exponent field
     const int k = max(min(n >> 5, 1000), -1000);
     return __hiloint2double(__double2hiint(s) + (k << 20), __double2loint(s));
 }
-// 1 / d for d in [1, inf]: hardware seed (MUFU.RCP64H, ~2^-23) and one Newton step (2^-46)
+// 1 / d for d >= 2^-1000: hardware seed (MUFU.RCP64H, ~2^-23) and one Newton step (2^-46)
 __device__ __forceinline__ double ff_rcp(double d) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
     const double e = fma(-d, y, 1.0);
     return fma(y, e, y);
 }
+// the same with two Newton steps (full double precision): the log-likelihood evaluations, where the
+// one-step error -- always of one sign -- would add up over the N samples
+__device__ __forceinline__ double ff_rcp2(double d) {
+    double y = ff_rcp(d);
+    const double e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+// log(p) for p in (0, 1] to ~1e-15 absolute: p = m 2^k, m in [0.75, 1.5), log m = 2 atanh(s),
+// s = (m - 1) / (m + 1), |s| <= 0.2, odd series to s^17
+__device__ __forceinline__ double ff_log(double p) {
+    int hi = __double2hiint(p);
+    int k = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                        // m in [1, 2)
+    if (hi >= 0x3ff80000) { hi -= 0x00100000; ++k; }            // m in [0.75, 1.5)
+    const double m = __hiloint2double(hi, __double2loint(p));
+    const double sgm = (m - 1.0) * ff_rcp2(m + 1.0);
+    const double s2 = sgm * sgm;
+    double q = fma(s2, c_ff[15], c_ff[14]);
+    q = fma(q, s2, c_ff[13]);
+    q = fma(q, s2, c_ff[12]);
+    q = fma(q, s2, c_ff[11]);
+    q = fma(q, s2, c_ff[10]);
+    q = fma(q, s2, c_ff[9]);
+    q = fma(q, s2, c_ff[8]);
+    q = fma(q, s2, 2.0);
+    return fma((double)k, c_ff[7], q * sgm);
+}
 
-// one 32-sample word; zp / fp / w0p point at this word's covariates in the staged tile
-template <int Q>
-__device__ __forceinline__ void fast_word(const double *__restrict__ zp, const float *__restrict__ fp,
-                                          const double w0, const bool xb, const bool yb, const bool ok,
-                                          const bool want_llf, const double *__restrict__ beta,
-                                          const double *__restrict__ etab, FastAcc<Q> &acc) {
-    double z[Q];
-    float zf[Q];
+// Two 32-sample words at once, in straight-line code: the two dependency chains (eta -> exp ->
+// reciprocal -> weights -> accumulations) interleave in the instruction stream, which is what keeps
+// the pipes busy at two warps per scheduler.  zp / fp / wp point at the first word's covariates in the
+// staged tile (the second word follows at +ZW / +32).
+template <int Q, bool LLF>
+__device__ __forceinline__ void fast_pair(const double *__restrict__ zp, const float *__restrict__ fp,
+                                          const double *__restrict__ wp, const uint32_t xbits,
+                                          const uint32_t ybits, const uint32_t okbits,
+                                          const double *__restrict__ beta, const double *__restrict__ etab,
+                                          FastAcc<Q> &acc) {
+    constexpr int ZW = (Q - 1) * 32;
+    double z[2][Q];
+    float zf[2][Q];
+    double w0[2];
 #pragma unroll
-    for (int c = 1; c < Q; ++c) {
-        z[c] = zp[(c - 1) * 32];
-        zf[c] = fp[(c - 1) * 32];
-    }
-    // eta = beta_0 + sum_c beta_c z_c + x beta_x  (two chains)
-    double e0 = beta[0], e1 = xb ? beta[Q] : 0.0;
+    for (int u = 0; u < 2; ++u) {
 #pragma unroll
-    for (int c = 1; c < Q; c += 2) {
-        e0 = fma(beta[c], z[c], e0);
-        if (c + 1 < Q) e1 = fma(beta[c + 1], z[c + 1], e1);
+        for (int c = 1; c < Q; ++c) {
+            z[u][c] = zp[u * ZW + (c - 1) * 32];
+            zf[u][c] = fp[u * ZW + (c - 1) * 32];
+        }
+        w0[u] = wp[u * 32];
     }
-    const double eta = e0 + e1;
+    double b[Q + 1];
+#pragma unroll
+    for (int c = 0; c <= Q; ++c) b[c] = beta[c];
+    double ex[2], pi[2], w[2], r[2], eta[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        // eta = beta_0 + sum_c beta_c z_c + x beta_x  (four chains)
+        const bool xb = (xbits >> u) & 1u;
+        double e0 = b[0], e1 = xb ? b[Q] : 0.0, e2 = 0.0, e3 = 0.0;
+#pragma unroll
+        for (int c = 1; c < Q; c += 4) {
+            e0 = fma(b[c], z[u][c], e0);
+            if (c + 1 < Q) e1 = fma(b[c + 1], z[u][c + 1], e1);
+            if (c + 2 < Q) e2 = fma(b[c + 2], z[u][c + 2], e2);
+            if (c + 3 < Q) e3 = fma(b[c + 3], z[u][c + 3], e3);
+        }
+        eta[u] = (e0 + e1) + (e2 + e3);
+    }
     // pi = 1 / (1 + exp(-eta)), w = pi (1 - pi) as statsmodels writes them, with exp and the
-    // reciprocal evaluated to 1e-12 relative (ff_exp, ff_rcp): the score only needs pi to ~1e-9
-    // for coefficients good to 1e-10 (random errors average out over N samples), the exact kernel
-    // keeps the correctly rounded library functions where saturation decides flags
-    const double ex = ff_exp(-eta, etab);
-    const double pi = ff_rcp(1.0 + ex);
-    double w = pi * (1.0 - pi);
-    double r = (yb ? 1.0 : 0.0) - pi;
-    if (!ok) { w = 0.0; r = 0.0; }
-    acc.maxdev = fmax(acc.maxdev, fabs(r));
-    if (want_llf) {
-        // log cdf((2y-1) eta) = -log1p(exp(-eta)) - (1 - y) eta
-        const double l = -log1p(ex) - (yb ? 0.0 : eta);
-        acc.llf += ok ? l : 0.0;
+    // reciprocal evaluated to 1e-13 relative (ff_exp, ff_rcp): the score only needs pi to ~1e-9 for
+    // coefficients good to 1e-10 (random errors average out over N samples); the exact kernel keeps
+    // the correctly rounded library functions where saturation decides flags
+#pragma unroll
+    for (int u = 0; u < 2; ++u) ex[u] = ff_exp(-eta[u], etab);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) pi[u] = LLF ? ff_rcp2(1.0 + ex[u]) : ff_rcp(1.0 + ex[u]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const bool yb = (ybits >> u) & 1u, ok = (okbits >> u) & 1u;
+        w[u] = ok ? pi[u] * (1.0 - pi[u]) : 0.0;
+        r[u] = ok ? (yb ? 1.0 : 0.0) - pi[u] : 0.0;
+        acc.maxdev = fmax(acc.maxdev, fabs(r[u]));
+        if (LLF) {
+            // log cdf((2y-1) eta) = log(pi) - (1 - y) eta ; pi is clamped away from an underflowing 0
+            const double l = ff_log(fmax(pi[u], 1e-300)) - (yb ? 0.0 : eta[u]);
+            acc.llf += ok ? l : 0.0;
+        }
     }
-    acc.g[0] += r;
-    acc.gx += xb ? r : 0.0;
 #pragma unroll
-    for (int c = 1; c < Q; ++c) acc.g[c] = fma(r, z[c], acc.g[c]);
+    for (int u = 0; u < 2; ++u) {
+        const bool xb = (xbits >> u) & 1u;
+        acc.g[0] += r[u];
+        acc.gx += xb ? r[u] : 0.0;
+#pragma unroll
+        for (int c = 1; c < Q; ++c) acc.g[c] = fma(r[u], z[u][c], acc.g[c]);
+    }
     // FP32: differences to the null-model values of the Z block and of the variant's border
-    const float dw = (float)(w - w0);
-    const float dwx = xb ? dw : 0.f;
-    acc.dH[0] += dw;
-    acc.dhz[0] += dwx;
 #pragma unroll
-    for (int c = 1; c < Q; ++c) {
-        const float wz = dw * zf[c];
-        acc.dhz[c] = fmaf(dwx, zf[c], acc.dhz[c]);
-        acc.dH[c * (c + 1) / 2] += wz;
+    for (int u = 0; u < 2; ++u) {
+        const bool xb = (xbits >> u) & 1u;
+        const float dw = (float)(w[u] - w0[u]);
+        const float dwx = xb ? dw : 0.f;
+        acc.dH[0] += dw;
+        acc.dhz[0] += dwx;
 #pragma unroll
-        for (int d = 1; d < Q; ++d)
-            if (d <= c) acc.dH[c * (c + 1) / 2 + d] = fmaf(wz, zf[d], acc.dH[c * (c + 1) / 2 + d]);
+        for (int c = 1; c < Q; ++c) {
+            const float wz = dw * zf[u][c];
+            acc.dhz[c] = fmaf(dwx, zf[u][c], acc.dhz[c]);
+            acc.dH[c * (c + 1) / 2] += wz;
+#pragma unroll
+            for (int d = 1; d < Q; ++d)
+                if (d <= c) acc.dH[c * (c + 1) / 2 + d] = fmaf(wz, zf[u][d], acc.dH[c * (c + 1) / 2 + d]);
+        }
+    }
+}
+
+template <int Q, bool LLF>
+__device__ __forceinline__ void fast_chunk(const double *__restrict__ zt, const float *__restrict__ ft,
+                                           const double *__restrict__ wt, const uint32_t *__restrict__ xrow,
+                                           const uint32_t *__restrict__ y1, const uint32_t *__restrict__ vbits,
+                                           int t0, int wlast, int lane, const double *__restrict__ beta,
+                                           const double *__restrict__ etab, FastAcc<Q> &acc) {
+    constexpr int ZW = (Q - 1) * 32;
+#pragma unroll 1
+    for (int k = 0; k < FF_CH; k += 2) {
+        // words beyond the last one are zero padded in the staged arrays and masked by vbits; the
+        // variant row and the phenotype row are read at a clamped index
+        const int ta = min(t0 + k, wlast), tb = min(t0 + k + 1, wlast);
+        const uint32_t xa = __ldg(xrow + ta), xb = __ldg(xrow + tb);
+        const uint32_t ya = __ldg(y1 + ta), yb = __ldg(y1 + tb);
+        const uint32_t va = __ldg(vbits + t0 + k), vb = __ldg(vbits + t0 + k + 1);
+        const uint32_t xbits = ((xa >> lane) & 1u) | (((xb >> lane) & 1u) << 1);
+        const uint32_t ybits = ((ya >> lane) & 1u) | (((yb >> lane) & 1u) << 1);
+        const uint32_t okbits = ((va >> lane) & 1u) | (((vb >> lane) & 1u) << 1);
+        fast_pair<Q, LLF>(zt + k * ZW, ft + k * ZW, wt + k * 32, xbits, ybits, okbits, beta, etab, acc);
     }
 }
 
@@ -164,6 +249,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // chunk of FF_CH words (fp64 + fp32 + null weights: 32 KB at q = 11) are staged once per CTA into a
 // double-buffered shared-memory tile with cp.async, so that the sample loop reads them at
 // shared-memory latency and the L2 -> SM traffic is a quarter of what per-warp loads would cost.
+// (A ring of bulk copies completing on mbarriers, which lets the warps drift apart by a chunk or two
+// instead of meeting at a CTA barrier per chunk, was measured SLOWER -- 9.8 against 11.2 M k-mers/s:
+// the warps spinning on mbarrier.try_wait take issue slots from the one still computing, while a
+// warp parked at bar.sync costs nothing.)
 // Between passes every warp solves its Newton step and either keeps its variant for another pass,
 // publishes it, or hands it to the exact kernel; free warps take the next variant from a global
 // work counter.
@@ -184,7 +273,6 @@ k_fixed_logit_fast(FxArgs a, FxFast ff, const int32_t *__restrict__ idx, int n_t
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *beta = s_beta + warp * P;
     const double inv_n = 1.0 / (double)a.N;
-    const int wfull = a.N >> 5;
     const int nch = (a.Wn + FF_CH - 1) / FF_CH;
 
     int v = -1;                 // variant owned by this warp (-1: none)
@@ -282,18 +370,10 @@ k_fixed_logit_fast(FxArgs a, FxFast ff, const int32_t *__restrict__ idx, int n_t
                 const double *zt = sZ + (size_t)buf * FF_CH * ZW + lane;
                 const float *ft = sZf + (size_t)buf * FF_CH * ZW + lane;
                 const double *wt = sW0 + (size_t)buf * FF_CH * 32 + lane;
-                const int t0 = ch * FF_CH;
-#pragma unroll 2
-                for (int k = 0; k < FF_CH; ++k) {
-                    const int t = t0 + k;
-                    if (t >= a.Wn) break;
-                    const uint32_t xw = __ldg(xrow + t);
-                    const uint32_t yw = __ldg(a.y1 + t);
-                    bool ok = true;
-                    if (t >= wfull) ok = (__ldg(a.valid + t) >> lane) & 1u;
-                    fast_word<Q>(zt + k * ZW, ft + k * ZW, wt[k * 32], (xw >> lane) & 1u, (yw >> lane) & 1u, ok,
-                                 want_llf, beta, s_etab, acc);
-                }
+                if (want_llf)
+                    fast_chunk<Q, true>(zt, ft, wt, xrow, a.y1, ff.vbits, ch * FF_CH, a.Wn - 1, lane, beta, s_etab, acc);
+                else
+                    fast_chunk<Q, false>(zt, ft, wt, xrow, a.y1, ff.vbits, ch * FF_CH, a.Wn - 1, lane, beta, s_etab, acc);
             }
             __syncthreads();           // the tile is free before the stage after next overwrites it
         }
@@ -426,6 +506,8 @@ int psb_fixed_fast_setup(psb_ctx *c, const double *Z, const double *warm) {
     const int Wn = (c->Wn + FF_CH - 1) / FF_CH * FF_CH;          // whole chunks (zero padded)
     std::vector<double> Zi((size_t)Wn * (Q - 1) * 32, 0.0), W0((size_t)Wn * 32, 0.0), H0((size_t)Q * (Q + 1) / 2, 0.0);
     std::vector<float> Zf(Zi.size(), 0.f);
+    std::vector<uint32_t> vb(Wn, 0u);                      // sample < N, zero on the padding words
+    for (int i = 0; i < N; ++i) vb[i >> 5] |= 1u << (i & 31);
     std::vector<double> zmax(FX_MAXP, 0.0);
     for (int i = 0; i < N; ++i) {
         const double *zi = Z + (size_t)i * q;
@@ -458,6 +540,7 @@ int psb_fixed_fast_setup(psb_ctx *c, const double *Z, const double *warm) {
     if ((rc = up((void **)&c->d_fx_Zf, Zf.data(), Zf.size() * sizeof(float)))) return rc;
     if ((rc = up((void **)&c->d_fx_W0, W0.data(), W0.size() * sizeof(double)))) return rc;
     if ((rc = up((void **)&c->d_fx_H0, H0.data(), H0.size() * sizeof(double)))) return rc;
+    if ((rc = up((void **)&c->d_fx_vb, vb.data(), vb.size() * sizeof(uint32_t)))) return rc;
     c->fx_zmax.assign(zmax.begin(), zmax.end());
     c->fx_Q = Q;
     return PSB_OK;
@@ -468,6 +551,8 @@ void psb_fixed_fast_free(psb_ctx *c) {
     if (c->d_fx_Zf) cudaFree(c->d_fx_Zf);
     if (c->d_fx_W0) cudaFree(c->d_fx_W0);
     if (c->d_fx_H0) cudaFree(c->d_fx_H0);
+    if (c->d_fx_vb) cudaFree(c->d_fx_vb);
+    c->d_fx_vb = nullptr;
     c->d_fx_Zi = nullptr;
     c->d_fx_Zf = nullptr;
     c->d_fx_W0 = c->d_fx_H0 = nullptr;
@@ -506,6 +591,7 @@ int psb_fixed_fast_launch(psb_ctx *c, const FxArgs &a, int n) {
     ff.Zf = c->d_fx_Zf;
     ff.W0 = c->d_fx_W0;
     ff.Hzz0 = c->d_fx_H0;
+    ff.vbits = c->d_fx_vb;
     ff.slow_list = c->d_idx3;
     for (int k = 0; k < FX_MAXP; ++k) ff.zmax[k] = c->fx_zmax[k];
     int *work = c->d_counters + 7;          // counters[7]: the work counter of this launch (zeroed by k_prefilter's memset)

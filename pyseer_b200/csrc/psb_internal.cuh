@@ -98,6 +98,8 @@ struct psb_ctx {
     bool tc_welch_run = false;    // ... and this run takes the Welch sums from there (psb_run_lmm)
     void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B): box = 128 samples x all sliced rows
     void *tmap_Lq_half = nullptr; // same with half of the sliced rows per box (two-SM mode)
+    void *tc_alt = nullptr;       // two-pass mode: the refinement precision's operand image (psb_lmm_tc.cu: TcState)
+    double refine_F = 30.0;       // ... applied to variants whose F statistic exceeds this
 
     // ---- fixed effects ----
     int q = 0;
@@ -114,6 +116,7 @@ struct psb_ctx {
     // fast Logit path (psb_fixed_fast.cu): interleaved covariates (fp64, fp32), null weights, Z'W0Z
     double *d_fx_Zi = nullptr, *d_fx_W0 = nullptr, *d_fx_H0 = nullptr;
     float *d_fx_Zf = nullptr;
+    uint32_t *d_fx_vb = nullptr;
     std::vector<double> fx_zmax;
     int fx_Q = 0;                  // 0: not set up
     int fixed_slow = 0;            // variants of the last run that took the exact kernel after the fast one
@@ -196,6 +199,9 @@ int psb_launch_bitstats(psb_ctx *ctx, int continuous);
 int psb_lmm_tc_setup(psb_ctx *ctx, const double *h_v, const double *h_Q, int r, int ldq,
                      const double *h_w1, const double *h_w2);
 int psb_lmm_tc_run(psb_ctx *ctx, int n_tested);
+int psb_lmm_tc_run_list(psb_ctx *ctx, int upper, const int32_t *list, const int *count_dev);
+void psb_lmm_tc_swap(psb_ctx *ctx);
+int psb_lmm_tc_stash(psb_ctx *ctx);
 int psb_tc_linear_setup(psb_ctx *ctx, const double *cols, int ncols, int ld);
 int psb_tc_run(psb_ctx *ctx, int n_tested, double *lin_out, int lin_ld);
 void psb_lmm_tc_free(psb_ctx *ctx);

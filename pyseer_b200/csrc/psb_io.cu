@@ -24,7 +24,8 @@
 
 struct psb_reader {
     gzFile fh = nullptr;
-    FILE *raw = nullptr;                    // BGZF input: read and inflated block-parallel (bgzf_fill)
+    FILE *raw = nullptr;                    // plain text, or BGZF input inflated block-parallel (bgzf_fill)
+    bool bgzf = false;
     std::vector<unsigned char> bgzf_in;
     bool bgzf_err = false;
     int var_type = 0;                       // 0 = k-mers, 1 = Rtab, 2 = VCF
@@ -136,12 +137,23 @@ static bool bgzf_fill(psb_reader *r) {
 
 static bool reader_fill(psb_reader *r) {
     if (r->eof) return false;
-    if (r->raw) {
+    if (r->raw && r->bgzf) {
         if (!bgzf_fill(r)) {
             r->eof = true;
             r->pos = r->len = 0;
             return false;
         }
+        return true;
+    }
+    if (r->raw) {                       // plain text: straight from the file
+        const size_t got = fread(r->buf.data(), 1, r->buf.size(), r->raw);
+        if (got == 0) {
+            r->eof = true;
+            r->pos = r->len = 0;
+            return false;
+        }
+        r->pos = 0;
+        r->len = got;
         return true;
     }
     int got = gzread(r->fh, r->buf.data(), (unsigned)r->buf.size());
@@ -181,8 +193,11 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
     FILE *raw = fopen(path, "rb");
     PSB_REQUIRE(raw, PSB_ERR_ARG, "cannot open %s", path);
     const bool bgzf = bgzf_probe(raw) && !(getenv("PSB_BGZF") && atoi(getenv("PSB_BGZF")) == 0);
+    unsigned char magic[2] = {0, 0};
+    const bool gz = fread(magic, 1, 2, raw) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    rewind(raw);
     gzFile fh = nullptr;
-    if (!bgzf) {
+    if (gz && !bgzf) {
         fclose(raw);
         raw = nullptr;
         fh = gzopen(path, "rb");
@@ -192,6 +207,7 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
     psb_reader *r = new psb_reader();
     r->fh = fh;
     r->raw = raw;
+    r->bgzf = bgzf;
     r->var_type = var_type;
     r->n_samples = n_samples;
     r->buf.resize(4 << 20);

@@ -313,8 +313,9 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
                              const double *U, const double *S, double h2, int32_t precision) {
     PSB_REQUIRE(c && X && y && U && S, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(N > 1 && D >= 1 && D < N, PSB_ERR_ARG, "bad shape N=%d D=%d", N, D);
-    PSB_REQUIRE(precision == 0 || (precision >= 3 && precision <= 7), PSB_ERR_ARG,
-                "precision must be 0 (fp64) or 3..7 int8 slices, got %d", precision);
+    PSB_REQUIRE(precision == 0 || (precision >= 3 && precision <= 7) || precision == 46, PSB_ERR_ARG,
+                "precision must be 0 (fp64), 3..7 int8 slices or 46 (two passes: 4 slices, 6 for the tail), got %d",
+                precision);
     // lmm_cov.py:667-670: nLLeval returns no 'beta' for h2 outside [0,1) -> KeyError in
     // fit_lmm_block (tests/lmm_test.py:416-417)
     PSB_REQUIRE(h2 >= 0.0 && h2 < 1.0, PSB_ERR_H2, "h2 = %g outside [0, 1)", h2);
@@ -427,14 +428,41 @@ extern "C" int psb_lmm_setup(psb_ctx *c, int32_t N, int32_t D, const double *X, 
     PSB_UPLOAD_FENCE();
     c->model = PSB_MODEL_LMM;
     if (precision > 0) {
-        rc = psb_lmm_tc_setup(c, cols.data(), cols.data() + c->Npad, r, c->Npad,
-                              &cols[(size_t)c->col_w0 * c->Npad], &cols[(size_t)(c->col_w0 + 1) * c->Npad]);
-        if (rc) {
-            psb_free_model(c);
-            return rc;
+        // precision 46: two operand images -- 6 slices for the variants whose F statistic exceeds
+        // refine_F (built first and stashed), 4 slices for everyone (the working image)
+        const int passes = precision == 46 ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+            if (precision == 46) c->precision = pass == 0 ? 6 : 4;
+            rc = psb_lmm_tc_setup(c, cols.data(), cols.data() + c->Npad, r, c->Npad,
+                                  &cols[(size_t)c->col_w0 * c->Npad], &cols[(size_t)(c->col_w0 + 1) * c->Npad]);
+            if (rc) {
+                psb_free_model(c);
+                return rc;
+            }
+            if (passes == 2 && pass == 0) {
+                if (c->tc_special == 0) break;       // no x'v from the tensor pass: single pass at 6 slices
+                psb_lmm_tc_stash(c);
+            }
         }
+        if (getenv("PSB_REFINE_F")) c->refine_F = atof(getenv("PSB_REFINE_F"));
     }
     return PSB_OK;
+}
+
+// Two-pass mode: which tested variants go through the contraction again at the refinement precision.
+// F = beta^2 / var(beta) = (J - 1) b^2 / (a YKY - b^2)  (lmm.py:248, lmm_cov.py:799-815).  The relative
+// error of the p-value is about F / 2 times that of a (1e-8 at 4 slices), so everything above
+// refine_F is redone (and everything that is not finite).
+__global__ void __launch_bounds__(256)
+k_lmm_select_refine(const int *__restrict__ n_tested_dev, const int32_t *__restrict__ idx,
+                    const double *__restrict__ a_in, const double *__restrict__ b_in, double YKY, double dof1,
+                    double thr, int32_t *__restrict__ list, int *__restrict__ n_list) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= *n_tested_dev) return;
+    const int v = idx[t];
+    const double a = a_in[v], b = b_in[v];
+    const double F = dof1 * b * b / (a * YKY - b * b);
+    if (!(F <= thr)) list[atomicAdd(n_list, 1)] = v;
 }
 
 extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
@@ -481,6 +509,19 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
         } else {
             rc = psb_lmm_tc_run(c, upper);
             if (rc) return rc;
+            if (c->tc_alt && tc_sums) {
+                // second pass at the refinement precision over the (few) variants in the far tail;
+                // the list is in no particular order, every variant writes its own slots
+                k_lmm_select_refine<<<psb_div_up(upper, 256), 256, 0, c->stream>>>(
+                    c->d_counters, c->d_idx, c->d_a, c->d_b, c->YKY, (double)(c->J - 1), c->refine_F,
+                    c->d_idx3, c->d_counters + 6);
+                c->launches++;
+                PSB_CUDA(cudaGetLastError());
+                psb_lmm_tc_swap(c);
+                rc = psb_lmm_tc_run_list(c, upper, c->d_idx3, c->d_counters + 6);
+                psb_lmm_tc_swap(c);
+                if (rc) return rc;
+            }
         }
     }
     PSB_CUDA(cudaEventRecord(c->ev_k1, c->stream));

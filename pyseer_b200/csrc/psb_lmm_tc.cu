@@ -707,9 +707,25 @@ k_tc_syrk(const double *__restrict__ L, int Lrows, int Jpad, double *__restrict_
         }
 }
 
+// Uniform [0, 1) from a counter (splitmix64 finaliser): the dither of the stochastic rounding below.
+__device__ __forceinline__ double tc_u01(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Rounding to the (8k-2)-bit grid is STOCHASTIC (floor(v + u), u uniform and keyed by the entry):
+// unbiased, so the rounding errors of the ~N^2/4 entries a quadratic form sums add up like a random
+// walk whatever the matrix looks like.  Round-to-nearest is biased on structured operands: with
+// h2 = 0 every off-diagonal entry of M'' is the same number (-2/N) and takes the same rounding
+// error, which a variant with c carriers collects c^2/2 times -- measured on a clonal kinship at
+// N = 5000: p-values off by 1e-4 relative at k = 4 (4e-7 at k = 5) with round-to-nearest, 1e-9 with
+// the dither.  PSB_TC_DITHER=0 restores round-to-nearest.
 __global__ void k_tc_quantise(const double *__restrict__ L, int N, int Jpad, int J, int nsl,
                               const int *__restrict__ expo, int8_t *__restrict__ Lq, int Kpad,
-                              int Jq, int tri) {
+                              int Jq, int tri, int dither) {
     // thread per (i, j): i fastest so that the int8 stores of a warp are contiguous
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)Jq * Kpad;
@@ -719,7 +735,8 @@ __global__ void k_tc_quantise(const double *__restrict__ L, int N, int Jpad, int
     long long qv = 0;
     if (i < N && j < J) {
         double x = tc_src(L, Jpad, i, j, tri);
-        qv = llrint(ldexp(x, (8 * nsl - 2) - expo[j]));
+        const double v = ldexp(x, (8 * nsl - 2) - expo[j]);
+        qv = dither ? (long long)floor(v + tc_u01((uint64_t)e)) : llrint(v);
     }
     int jt = j / TC_JT, c = j - jt * TC_JT;
     for (int s = 0; s < nsl; ++s) {
@@ -880,7 +897,8 @@ int psb_lmm_tc_setup(psb_ctx *c, const double *h_v, const double *h_Q, int r, in
     size_t total = (size_t)Jq * c->Kpad;
     k_tc_quantise<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(src, N, src_ld, J, nsl,
                                                                          d_expo, c->d_Lq, c->Kpad, Jq,
-                                                                         c->tc_tri ? 1 : 0);
+                                                                         c->tc_tri ? 1 : 0,
+                                                                         (getenv("PSB_TC_DITHER") && atoi(getenv("PSB_TC_DITHER")) == 0) ? 0 : 1);
     c->launches++;
     PSB_CUDA(cudaGetLastError());
     if (c->tc_special) {
@@ -938,13 +956,25 @@ int psb_tc_linear_setup(psb_ctx *c, const double *cols, int ncols, int ld) {
 
 int psb_lmm_tc_run(psb_ctx *c, int n_tested) { return psb_tc_run(c, n_tested, nullptr, 0); }
 
+// the same over another list of variants (ids in `list`, their number in *count_dev on the device)
+static const int32_t *g_tc_list = nullptr;
+static const int *g_tc_count = nullptr;
+int psb_lmm_tc_run_list(psb_ctx *c, int upper, const int32_t *list, const int *count_dev) {
+    g_tc_list = list;
+    g_tc_count = count_dev;
+    const int rc = psb_tc_run(c, upper, nullptr, 0);
+    g_tc_list = nullptr;
+    g_tc_count = nullptr;
+    return rc;
+}
+
 // lin_out != null: linear-only use (psb_tc_linear_setup): the pair sums go to
 // lin_out[variant * lin_ld + pair] and no quadratic form is produced.
 int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     const int nsl = c->n_slices;
     TcArgs a;
     a.bits = c->d_bits;
-    a.idx = c->d_idx;
+    a.idx = g_tc_list ? g_tc_list : c->d_idx;
     a.scale2 = c->d_scale2;
     a.a_out = lin_out ? nullptr : c->d_a;
     a.b_out = lin_out ? nullptr : c->d_b;
@@ -957,7 +987,7 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     a.n_special = c->tc_special;
     a.Wrow = c->Wrow;
     a.n_tested = n_tested;
-    a.n_tested_dev = c->d_counters;      // counters[0] = tested variants
+    a.n_tested_dev = g_tc_count ? g_tc_count : c->d_counters;      // counters[0] = tested variants
     a.nks = c->Kpad / TC_KSTAGE;
     a.jtiles = c->jtiles;
     a.tri = c->tc_tri ? 1 : 0;
@@ -1027,7 +1057,60 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     return PSB_OK;
 }
 
+// ---- two operand images in one context: the working precision and the refinement precision of
+// the two-pass mode (psb_lmm_setup, precision 46) ---------------------------------------------------
+struct TcState {
+    int8_t *d_Lq;
+    double *d_scale2;
+    uint8_t *d_shift;
+    void *tmap_Lq, *tmap_Lq_half;
+    int n_slices, jtiles, Kpad, tc_special;
+    bool tc_tri, tc_int_epi, tc_welch;
+};
+static void tc_save(const psb_ctx *c, TcState &s) {
+    s.d_Lq = c->d_Lq; s.d_scale2 = c->d_scale2; s.d_shift = c->d_shift;
+    s.tmap_Lq = c->tmap_Lq; s.tmap_Lq_half = c->tmap_Lq_half;
+    s.n_slices = c->n_slices; s.jtiles = c->jtiles; s.Kpad = c->Kpad; s.tc_special = c->tc_special;
+    s.tc_tri = c->tc_tri; s.tc_int_epi = c->tc_int_epi; s.tc_welch = c->tc_welch;
+}
+static void tc_load(psb_ctx *c, const TcState &s) {
+    c->d_Lq = s.d_Lq; c->d_scale2 = s.d_scale2; c->d_shift = s.d_shift;
+    c->tmap_Lq = s.tmap_Lq; c->tmap_Lq_half = s.tmap_Lq_half;
+    c->n_slices = s.n_slices; c->jtiles = s.jtiles; c->Kpad = s.Kpad; c->tc_special = s.tc_special;
+    c->tc_tri = s.tc_tri; c->tc_int_epi = s.tc_int_epi; c->tc_welch = s.tc_welch;
+}
+// swaps the context's current operand image with the alternate one
+void psb_lmm_tc_swap(psb_ctx *c) {
+    if (!c->tc_alt) return;
+    TcState cur;
+    tc_save(c, cur);
+    tc_load(c, *(TcState *)c->tc_alt);
+    *(TcState *)c->tc_alt = cur;
+}
+// the image just built by psb_lmm_tc_setup becomes the alternate one; the context is left without
+// a current image (the caller builds the working one next)
+int psb_lmm_tc_stash(psb_ctx *c) {
+    TcState *s = new TcState;
+    tc_save(c, *s);
+    c->tc_alt = s;
+    c->d_Lq = nullptr;
+    c->d_scale2 = nullptr;
+    c->d_shift = nullptr;
+    c->tmap_Lq = c->tmap_Lq_half = nullptr;
+    return PSB_OK;
+}
+
 void psb_lmm_tc_free(psb_ctx *c) {
+    if (c->tc_alt) {
+        TcState *s = (TcState *)c->tc_alt;
+        if (s->d_Lq) cudaFree(s->d_Lq);
+        if (s->d_scale2) cudaFree(s->d_scale2);
+        if (s->d_shift) cudaFree(s->d_shift);
+        if (s->tmap_Lq) delete (CUtensorMap *)s->tmap_Lq;
+        if (s->tmap_Lq_half) delete (CUtensorMap *)s->tmap_Lq_half;
+        delete s;
+        c->tc_alt = nullptr;
+    }
     if (c->d_Lq) cudaFree(c->d_Lq);
     if (c->d_scale2) cudaFree(c->d_scale2);
     if (c->d_shift) cudaFree(c->d_shift);

@@ -153,7 +153,7 @@ class KinshipLMM(object):
             S, U = self.getSU()
             prec = self.precision
             if prec is None:
-                prec = int(os.environ.get('PYSEER_B200_LMM_PRECISION', '5'))
+                prec = int(os.environ.get('PYSEER_B200_LMM_PRECISION', '46'))
             self._engine.lmm_setup(self.X, self.Y[:, 0], U, S, h2, prec)
             self._engine_h2 = h2
         return self._engine

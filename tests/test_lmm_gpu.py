@@ -12,8 +12,8 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-6
 # contraction back-ends under test: 0 = FP64 CUDA cores, k = k exact int8 slices on tcgen05
-PRECISIONS = [int(t) for t in os.environ.get('PSB_TEST_PRECISIONS', '0,4,5,6,7').split(',')]
-PREC2 = [p for p in PRECISIONS if p in (0, 5)] or PRECISIONS[:1]
+PRECISIONS = [int(t) for t in os.environ.get('PSB_TEST_PRECISIONS', '0,4,5,6,7,46').split(',')]
+PREC2 = [p for p in PRECISIONS if p in (0, 5, 46)] or PRECISIONS[:1]
 
 
 def _close(a, b, rtol=RTOL):
