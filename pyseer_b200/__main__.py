@@ -94,13 +94,15 @@ def _die(msg):
 
 def main(argv=None):
     o = get_options(argv)
-    # option checks of __main__.py:257-306 that concern the supported models
+    # option checks of __main__.py:257-306, in the reference's order and with its messages
+    if o.lmm and o.wg:
+        _die('Choose only one alternative model. Either --lmm, --wg or neither')
     if o.wg:
         _die('Whole-genome models (--wg) are not part of the GPU path; use pyseer for them')
-    if o.burden and not o.vcf:
-        _die('Burden test can only be performed with VCF input')
     if o.max_dimensions < 1:
         _die('Minimum number of dimensions after MDS is 1')
+    if o.burden and not o.vcf:
+        _die('Burden test can only be performed with VCF input')
     if o.lmm and not o.similarity and not o.load_lmm:
         _die('Must provide a similarity matrix or lmm cache for random effects')
     if not o.no_distances:
@@ -108,20 +110,22 @@ def main(argv=None):
                 (not o.lmm and (o.similarity or o.load_lmm)):
             _die('Must use distance matrix with fixed effects, or similarity matrix with random '
                  'effects\nUnless performing a lineage analysis with random effects')
-        if o.lmm and not (o.distances or o.load_m) and o.lineage and not o.lineage_clusters:
+        if o.lmm and not (o.distances or o.load_m) and o.lineage:
             _die('Must also provide a distance matrix to report lineage effects')
         if not o.lmm and not o.distances and not o.load_m:
             _die('Option --no-distances must be used when no distance matrix is provided')
     else:
+        if not o.lmm and not o.lineage_clusters and o.lineage:
+            _die('Must provide a lineage clusters file when --no-distances and --lineage are used '
+                 'together in fixed-effects mode')
         if o.distances or o.load_m:
             _die('Cannot use --no-distances with --distances or --load-m')
         if o.lmm:
             _die('Cannot use --no-distances with --lmm')
-        if not o.lmm and not o.lineage_clusters and o.lineage:
-            _die('Must provide a lineage clusters file when --no-distances and --lineage are used '
-                 'together in fixed-effects mode')
     if o.block_size < 1:
         _die('Block size must be at least 1')
+    if o.gpus < 1:
+        _die('--gpus must be at least 1')
 
     p = load_phenotypes(o.phenotypes, o.phenotype_column)
     sys.stderr.write('Read ' + str(len(p)) + ' phenotypes\n')

@@ -44,6 +44,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 #define FF_CH 8          // 32-sample words per staged chunk
 #define FF_WARPS 4
+#define FF_NBUF 3        // staged tiles: chunk ch + 2 is fetched while chunk ch is consumed
 
 template <int Q>
 struct FastAcc {
@@ -52,7 +53,9 @@ struct FastAcc {
     float dhz[Q];       // sum over carriers of (w - w0) z_c   (dhz[0]: of w - w0); the null-model part
                         // sum over carriers of w0 z_c is exact (masked sums of the linear tensor tile)
     float dH[Q * (Q + 1) / 2];   // sum (w - w0) z_c z_d, d <= c
-    double llf, maxdev;
+    double lprod;       // running product of the samples' likelihoods, exponent kept apart in lexp:
+    int lexp;           //   llf = log(lprod) + lexp ln 2  (one log per lane and pass instead of one per sample)
+    double maxdev;
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int c = 0; c < Q; ++c) {
@@ -61,7 +64,9 @@ struct FastAcc {
         }
 #pragma unroll
         for (int e = 0; e < Q * (Q + 1) / 2; ++e) dH[e] = 0.f;
-        gx = llf = maxdev = 0.0;
+        gx = maxdev = 0.0;
+        lprod = 1.0;
+        lexp = 0;
     }
 };
 
@@ -129,11 +134,11 @@ __device__ __forceinline__ double ff_log(double p) {
 // reciprocal -> weights -> accumulations) interleave in the instruction stream, which is what keeps
 // the pipes busy at two warps per scheduler.  zp / fp / wp point at the first word's covariates in the
 // staged tile (the second word follows at +ZW / +32).
-template <int Q, bool LLF>
+template <int Q>
 __device__ __forceinline__ void fast_pair(const double *__restrict__ zp, const float *__restrict__ fp,
                                           const double *__restrict__ wp, const uint32_t xbits,
                                           const uint32_t ybits, const uint32_t okbits,
-                                          const double *__restrict__ beta, const double *__restrict__ etab,
+                                          const double (&b)[Q + 1], const double *__restrict__ etab,
                                           FastAcc<Q> &acc) {
     constexpr int ZW = (Q - 1) * 32;
     double z[2][Q];
@@ -148,9 +153,6 @@ __device__ __forceinline__ void fast_pair(const double *__restrict__ zp, const f
         }
         w0[u] = wp[u * 32];
     }
-    double b[Q + 1];
-#pragma unroll
-    for (int c = 0; c <= Q; ++c) b[c] = beta[c];
     double ex[2], pi[2], w[2], r[2], eta[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -173,18 +175,24 @@ __device__ __forceinline__ void fast_pair(const double *__restrict__ zp, const f
 #pragma unroll
     for (int u = 0; u < 2; ++u) ex[u] = ff_exp(-eta[u], etab);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) pi[u] = LLF ? ff_rcp2(1.0 + ex[u]) : ff_rcp(1.0 + ex[u]);
+    for (int u = 0; u < 2; ++u) pi[u] = ff_rcp2(1.0 + ex[u]);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const bool yb = (ybits >> u) & 1u, ok = (okbits >> u) & 1u;
         w[u] = ok ? pi[u] * (1.0 - pi[u]) : 0.0;
         r[u] = ok ? (yb ? 1.0 : 0.0) - pi[u] : 0.0;
         acc.maxdev = fmax(acc.maxdev, fabs(r[u]));
-        if (LLF) {
-            // log cdf((2y-1) eta) = log(pi) - (1 - y) eta ; pi is clamped away from an underflowing 0
-            const double l = ff_log(fmax(pi[u], 1e-300)) - (yb ? 0.0 : eta[u]);
-            acc.llf += ok ? l : 0.0;
-        }
+        // likelihood of the sample: cdf((2y-1) eta) = pi (y = 1) or 1 - pi = exp(-eta) pi (y = 0),
+        // multiplied into the running product (relative rounding 1e-16 per factor: the log of the
+        // product is good to 1e-14 absolute, better than a sum of N rounded logs)
+        acc.lprod *= ok ? (yb ? pi[u] : ex[u] * pi[u]) : 1.0;
+    }
+    {
+        // renormalise the product: its binary exponent moves to lexp (two factors >= 2^-1022 each per
+        // step cannot underflow a product kept in [1, 2))
+        const int hi = __double2hiint(acc.lprod);
+        acc.lexp += (hi >> 20) - 1023;
+        acc.lprod = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(acc.lprod));
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -214,11 +222,11 @@ __device__ __forceinline__ void fast_pair(const double *__restrict__ zp, const f
     }
 }
 
-template <int Q, bool LLF>
+template <int Q>
 __device__ __forceinline__ void fast_chunk(const double *__restrict__ zt, const float *__restrict__ ft,
                                            const double *__restrict__ wt, const uint32_t *__restrict__ xrow,
                                            const uint32_t *__restrict__ y1, const uint32_t *__restrict__ vbits,
-                                           int t0, int wlast, int lane, const double *__restrict__ beta,
+                                           int t0, int wlast, int lane, const double (&b)[Q + 1],
                                            const double *__restrict__ etab, FastAcc<Q> &acc) {
     constexpr int ZW = (Q - 1) * 32;
 #pragma unroll 1
@@ -232,7 +240,7 @@ __device__ __forceinline__ void fast_chunk(const double *__restrict__ zt, const 
         const uint32_t xbits = ((xa >> lane) & 1u) | (((xb >> lane) & 1u) << 1);
         const uint32_t ybits = ((ya >> lane) & 1u) | (((yb >> lane) & 1u) << 1);
         const uint32_t okbits = ((va >> lane) & 1u) | (((vb >> lane) & 1u) << 1);
-        fast_pair<Q, LLF>(zt + k * ZW, ft + k * ZW, wt + k * 32, xbits, ybits, okbits, beta, etab, acc);
+        fast_pair<Q>(zt + k * ZW, ft + k * ZW, wt + k * 32, xbits, ybits, okbits, b, etab, acc);
     }
 }
 
@@ -247,7 +255,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // Execution model.  A CTA of FF_WARPS warps sweeps the samples in lockstep PASSES: every pass is one
 // evaluation (score, X'WX, llf) of the variant each warp currently owns.  The covariate columns of a
 // chunk of FF_CH words (fp64 + fp32 + null weights: 32 KB at q = 11) are staged once per CTA into a
-// double-buffered shared-memory tile with cp.async, so that the sample loop reads them at
+// ring of three shared-memory tiles with cp.async (one CTA barrier per chunk), so that the sample loop reads them at
 // shared-memory latency and the L2 -> SM traffic is a quarter of what per-warp loads would cost.
 // (A ring of bulk copies completing on mbarriers, which lets the warps drift apart by a chunk or two
 // instead of meeting at a CTA barrier per chunk, was measured SLOWER -- 9.8 against 11.2 M k-mers/s:
@@ -262,10 +270,10 @@ k_fixed_logit_fast(FxArgs a, FxFast ff, const int32_t *__restrict__ idx, int n_t
     constexpr int P = Q + 1;                 // columns: Z_0 .. Z_{Q-1} (zero padded beyond a.q), x
     constexpr int ZW = (Q - 1) * 32;         // covariate values per word
     extern __shared__ __align__(16) unsigned char ff_smem[];
-    double *sZ = reinterpret_cast<double *>(ff_smem);                         // [2][FF_CH][Q-1][32]
-    double *sW0 = sZ + 2 * FF_CH * ZW;                                        // [2][FF_CH][32]
-    float *sZf = reinterpret_cast<float *>(sW0 + 2 * FF_CH * 32);            // [2][FF_CH][Q-1][32]
-    double *s_H0 = reinterpret_cast<double *>(sZf + 2 * FF_CH * ZW);          // packed Tri<Q>
+    double *sZ = reinterpret_cast<double *>(ff_smem);                         // [FF_NBUF][FF_CH][Q-1][32]
+    double *sW0 = sZ + FF_NBUF * FF_CH * ZW;                                  // [FF_NBUF][FF_CH][32]
+    float *sZf = reinterpret_cast<float *>(sW0 + FF_NBUF * FF_CH * 32);      // [FF_NBUF][FF_CH][Q-1][32]
+    double *s_H0 = reinterpret_cast<double *>(sZf + FF_NBUF * FF_CH * ZW);    // packed Tri<Q>
     double *s_beta = s_H0 + Q * (Q + 1) / 2;                                  // [FF_WARPS][P]
     double *s_etab = s_beta + FF_WARPS * P;                                   // 2^(j/32), j = 0..31
     for (int e = threadIdx.x; e < Q * (Q + 1) / 2; e += blockDim.x) s_H0[e] = ff.Hzz0[e];
@@ -353,30 +361,30 @@ k_fixed_logit_fast(FxArgs a, FxFast ff, const int32_t *__restrict__ idx, int n_t
 
         // ---- one pass over the samples -----------------------------------------------------------
         const bool active = v >= 0;
-        const bool want_llf = maxstep <= 1e-3;
         FastAcc<Q> acc;
         acc.clear();
+        double breg[Q + 1];                  // this pass's parameters, in registers for the whole sweep
+#pragma unroll
+        for (int c = 0; c <= Q; ++c) breg[c] = beta[c];
+        // Three tiles, ONE barrier per chunk: the tile refilled during chunk ch (for chunk ch + 2) was
+        // read during chunk ch - 1, which every warp left before it passed this chunk's barrier.
         stage(0, 0);
+        if (nch > 1) stage(1, 1);
         for (int ch = 0; ch < nch; ++ch) {
-            const int buf = ch & 1;
-            if (ch + 1 < nch) {
-                stage(ch + 1, buf ^ 1);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
+            const int buf = ch % FF_NBUF;
+            if (ch + 1 < nch) cp_async_wait<1>();
+            else cp_async_wait<0>();
             __syncthreads();
+            if (ch + 2 < nch) stage(ch + 2, (ch + 2) % FF_NBUF);
+            else cp_async_commit();        // keep one group per iteration so that wait<1> counts right
             if (active) {
                 const double *zt = sZ + (size_t)buf * FF_CH * ZW + lane;
                 const float *ft = sZf + (size_t)buf * FF_CH * ZW + lane;
                 const double *wt = sW0 + (size_t)buf * FF_CH * 32 + lane;
-                if (want_llf)
-                    fast_chunk<Q, true>(zt, ft, wt, xrow, a.y1, ff.vbits, ch * FF_CH, a.Wn - 1, lane, beta, s_etab, acc);
-                else
-                    fast_chunk<Q, false>(zt, ft, wt, xrow, a.y1, ff.vbits, ch * FF_CH, a.Wn - 1, lane, beta, s_etab, acc);
+                fast_chunk<Q>(zt, ft, wt, xrow, a.y1, ff.vbits, ch * FF_CH, a.Wn - 1, lane, breg, s_etab, acc);
             }
-            __syncthreads();           // the tile is free before the stage after next overwrites it
         }
+        __syncthreads();                   // the tiles are free before the next pass refills them
         if (!active) continue;
 
         // ---- this warp's Newton step -----------------------------------------------------------
@@ -389,7 +397,8 @@ k_fixed_logit_fast(FxArgs a, FxFast ff, const int32_t *__restrict__ idx, int n_t
 #pragma unroll
         for (int e = 0; e < Q * (Q + 1) / 2; ++e) acc.dH[e] = warp_sum_f(acc.dH[e]);
         acc.maxdev = warp_max(acc.maxdev);
-        if (want_llf) acc.llf = warp_sum(acc.llf);
+        // log-likelihood at the evaluation point: one log per lane
+        const double pass_llf = warp_sum(fma((double)acc.lexp, 0.69314718055994530942, log(acc.lprod)));
         ++n_eval;
         bool slow = false, done = false;
         double bse = NAN, llf = NAN;
@@ -433,7 +442,7 @@ k_fixed_logit_fast(FxArgs a, FxFast ff, const int32_t *__restrict__ idx, int n_t
                 ++it;
                 if (!(maxstep < 1e3)) {
                     slow = true;                                       // NaN or running away
-                } else if (want_llf && maxstep <= 1e-7) {
+                } else if (maxstep <= 1e-7) {
                     // converged: llf(beta + d) = llf(beta) + g'd/2 + O(d^3), bse from the factored matrix
                     double e[P];
 #pragma unroll
@@ -442,7 +451,7 @@ k_fixed_logit_fast(FxArgs a, FxFast ff, const int32_t *__restrict__ idx, int n_t
                     const double var_x = e[Q] * inv_n;
                     if (var_x > 0.0 && isfinite(var_x)) {
                         bse = sqrt(var_x);
-                        llf = acc.llf + 0.5 * (double)a.N * gd;
+                        llf = pass_llf + 0.5 * (double)a.N * gd;
                         done = true;
                     } else {
                         slow = true;
@@ -561,7 +570,7 @@ void psb_fixed_fast_free(psb_ctx *c) {
 
 template <int Q>
 static size_t fast_smem() {
-    return (size_t)2 * FF_CH * (Q - 1) * 32 * (8 + 4) + (size_t)2 * FF_CH * 32 * 8 +
+    return (size_t)FF_NBUF * FF_CH * (Q - 1) * 32 * (8 + 4) + (size_t)FF_NBUF * FF_CH * 32 * 8 +
            ((size_t)Q * (Q + 1) / 2 + FF_WARPS * (Q + 1) + 32) * 8;
 }
 

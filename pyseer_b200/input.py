@@ -267,9 +267,10 @@ class PackedCache(object):
 
     Layout: one JSON header line (magic, sample-order digest, source size and mtime, row width),
     then chunks ``int64 n, int64 names_bytes, int64 has_missing | names (NUL separated) | bits
-    uint32[n][W] | missing uint32[n][W] if has_missing``; a chunk with n = 0 closes the file -- a
-    cache without it (interrupted run) is not used."""
-    MAGIC = 'pyseer_b200-bits-1'
+    uint32[n][W] | missing uint32[n][W] if has_missing``; the closing chunk ``0, total rows, TRAILER``
+    ends the file -- a cache without it (interrupted run, truncated copy) is not used."""
+    MAGIC = 'pyseer_b200-bits-2'
+    TRAILER = 0x7073625F62697473            # 'psb_bits': third word of the closing chunk
 
     @staticmethod
     def _header(var_type, source, samples, W):
@@ -289,7 +290,8 @@ class PackedCache(object):
                     return False
                 fh.seek(-24, os.SEEK_END)
                 tail = np.frombuffer(fh.read(24), dtype='<i8')
-                return tail.shape[0] == 3 and tail[0] == 0
+                return tail.shape[0] == 3 and tail[0] == 0 and tail[1] >= 0 and \
+                    int(tail[2]) == PackedCache.TRAILER
         except (OSError, ValueError):
             return False
 
@@ -297,11 +299,13 @@ class PackedCache(object):
 class PackedCacheWriter(object):
     def __init__(self, path, var_type, source, samples, W):
         self.fh = open(path, 'wb')
+        self.rows = 0
         self.fh.write((json.dumps(PackedCache._header(var_type, source, samples, W), sort_keys=True) + '\n').encode())
 
     def add(self, batch):
         names = ('\0'.join(batch.names) + '\0').encode()
         has_m = batch.missing is not None
+        self.rows += batch.n
         self.fh.write(np.array([batch.n, len(names), int(has_m)], dtype='<i8').tobytes())
         self.fh.write(names)
         self.fh.write(np.ascontiguousarray(batch.bits, dtype='<u4').tobytes())
@@ -311,7 +315,7 @@ class PackedCacheWriter(object):
     def close(self, complete=True):
         if self.fh:
             if complete:
-                self.fh.write(np.zeros(3, dtype='<i8').tobytes())
+                self.fh.write(np.array([0, self.rows, PackedCache.TRAILER], dtype='<i8').tobytes())
             self.fh.close()
             self.fh = None
 

@@ -3,7 +3,14 @@
 Same interface and output as pyseer's ``similarity`` tool (pyseer/similarity.py): a list of
 sample names, a variant file (``--kmers`` / ``--pres`` / ``--vcf``), AF / missing filters;
 writes the N x N matrix ``K = G G'`` as a TSV with sample names.  The product runs on the GPU
-as an AND + POPCOUNT contraction over packed rows (``psb_kinship_*``)."""
+as an AND + POPCOUNT contraction over packed rows (``psb_kinship_*``).
+
+One deliberate difference: a MISSING genotype counts as absent (0).  The reference keeps NaN in its
+variant matrix for variants that pass ``--max-missing`` (input.py:428-430, similarity.py:99-113), so
+``np.matmul`` turns the whole row and column of every sample with a missing call into NaN, and the
+kinship is unusable for the LMM (``eigh`` of a NaN matrix).  Inputs without missing calls -- k-mer
+files, and Rtab / VCF files with complete genotypes -- give the reference's matrix exactly
+(tests/test_kinship_gpu.py)."""
 import argparse
 import sys
 

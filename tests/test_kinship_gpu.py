@@ -49,3 +49,26 @@ def test_similarity_tool_on_reference_kmers(tmp_path):
     af = x.sum(1) / float(len(p))
     G = x[(af >= 0.01) & (af <= 0.99)].T
     assert np.array_equal(K.values, (G @ G.T).astype(float))
+
+
+def test_kinship_with_missing_genotypes():
+    """Missing calls count as absent (documented difference, pyseer_b200/similarity.py): the matrix
+    equals the reference's G G' with NaN replaced by 0, for variants within --max-missing; the AF
+    of the filter counts missing samples as carriers (input.py:439-446)."""
+    from pyseer_b200.engine import Engine, pack_rows
+    n, nv = 120, 400
+    rng = np.random.RandomState(2)
+    k = (rng.uniform(size=(nv, n)) < rng.uniform(0.05, 0.9, size=(nv, 1))).astype(float)
+    k[rng.uniform(size=(nv, n)) < 0.01] = np.nan
+    k[7, :30] = np.nan                                   # 25 % missing: beyond --max-missing
+    bits, miss = pack_rows(k)
+    nanmask = np.isnan(k)
+    af = (np.nansum(k, axis=1) + nanmask.sum(1)) / float(n)
+    keep = (af >= 0.01) & (af <= 0.99) & (nanmask.sum(1) / float(n) <= 0.05)
+    G = np.nan_to_num(k[keep]).T.astype(np.int64)
+    eng = Engine(0)
+    eng.kinship_begin(n)
+    eng.kinship_add(bits, miss, 0.01, 0.99, 0.05)
+    K = eng.kinship_fetch()
+    eng.close()
+    assert not keep[7] and np.array_equal(K, (G @ G.T).astype(float))

@@ -290,3 +290,24 @@ def test_bgzf_input_equals_gzip_input(tmp_path):
         assert len(out[tag]) == len(out['gz'])
         for (n1, b1), (n2, b2) in zip(out['gz'], out[tag]):
             assert n1 == n2 and np.array_equal(b1, b2)
+
+
+def test_truncated_cache_is_rejected(tmp_path):
+    """A cache cut off in the middle -- even where the cut leaves zero bytes at the end -- is not
+    used: the closing chunk carries the row count and a trailer word."""
+    from pyseer_b200.input import PackedCache, open_variants
+    p = _pheno()
+    src = os.path.join(GOLDEN, 'kmers.gz')
+    cache = str(tmp_path / 'k.bits')
+    rd = open_variants('kmers', src, p, cache=cache)
+    with contextlib.redirect_stderr(io.StringIO()):
+        n = sum(b.n for b in rd.batches(64))
+    rd.close()
+    samples = [str(s) for s in p.index]
+    W = rd.W
+    assert n == 200 and PackedCache.valid(cache, 'kmers', src, samples, W)
+    data = open(cache, 'rb').read()
+    cut = str(tmp_path / 'cut.bits')
+    with open(cut, 'wb') as fh:
+        fh.write(data[:len(data) // 2] + b'\0' * 64)
+    assert not PackedCache.valid(cut, 'kmers', src, samples, W)
