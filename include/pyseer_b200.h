@@ -288,6 +288,32 @@ int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, ui
  * next name did not fit `names` (the line is kept for the next call; PSB_ERR_NOMEM when not even the
  * first name of a call fits: come back with a larger buffer). */
 int psb_reader_at_eof(psb_reader *reader, int32_t *at_eof);
+/* ---- k-mer text parsed on the device ------------------------------------------------ */
+/* input.py's k-mer streaming (pyseer/input.py:505-707 -> read_variant :377-388, :438-452) as a
+ * page-locked host -> device staging pipeline: the host cuts the decompressed text into lines,
+ * the GPU tokenises them.
+ * psb_reader_next_text (var_type 0 readers): fills dst (dst_cap bytes; allocate it with
+ * psb_host_alloc) with the text of up to max_lines lines, read straight into it (plain text:
+ * pread on the reader's threads; bgzip: block-parallel inflate; gzip: zlib).  line_start[v] /
+ * line_len[v] locate line v inside dst without its newline and trailing blanks (empty lines are
+ * skipped); names / name_off as psb_reader_next.  The *n_read lines occupy dst[0, *n_bytes).  A short
+ * batch ends at the end of the file (psb_reader_at_eof) or where dst / names are full -- then *n_read is
+ * a multiple of line_multiple (PSB_ERR_NOMEM if not even that many lines fit).  Do not mix with
+ * psb_reader_next on the same reader.
+ * psb_text_setup: device lookup table of the sample names (phenotype order), once per context after
+ * the model set-up.  psb_submit_text: psb_submit for such a batch -- copies text / line_start /
+ * line_len on the staging copy stream and parses every line there into the packed row psb_submit
+ * would have been given (samples after the first '|', blank-separated tokens, name up to ':',
+ * unknown samples ignored); `text` must stay valid until the batch has been fetched.
+ * psb_text_info (after psb_run_*): per line, bit 1 (value 2) = no observation in the selected samples
+ * (input.py:447-448), bit 2 (value 4) = no '|' separator on the line (psb_reader_next: PSB_ERR_ARG). */
+int psb_reader_next_text(psb_reader *reader, int64_t max_lines, int64_t line_multiple, char *dst,
+                         int64_t dst_cap, int64_t *line_start, int32_t *line_len, char *names,
+                         int64_t names_cap, int64_t *name_off, int64_t *n_read, int64_t *n_bytes);
+int psb_text_setup(psb_ctx *ctx, const char *const *sample_names, int32_t n_samples);
+int psb_submit_text(psb_ctx *ctx, const char *text, int64_t text_bytes, const int64_t *line_start,
+                    const int32_t *line_len, int64_t n_lines);
+int psb_text_info(psb_ctx *ctx, int32_t *info, int64_t n_lines);
 /* var_type 2 = VCF text (plain or gzip), input.read_vcf_var (input.py:457-502), dominant encoding:
  * a sample carries the variant when a haplotype of its GT is a non-reference allele, '.' haplotypes
  * mark it missing unless a called one follows; names are CHROM_POS_REF[_ALT]; info bit 2 (value 4):

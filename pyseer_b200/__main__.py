@@ -268,6 +268,13 @@ def main(argv=None):
     def emit(batch, r):
         """Result loop of main() (__main__.py:547-568, 783-803) for one batch."""
         flags = r.flags
+        if batch.info is not None:
+            # batch parsed on the device: what the host reader reports while it reads
+            if (batch.info & 4).any():
+                raise ValueError("k-mer line without '|' separator: " +
+                                 batch.names[int(np.nonzero(batch.info & 4)[0][0])])
+            for i in np.nonzero(batch.info & 2)[0]:
+                sys.stderr.write('No observations of ' + batch.names[i] + ' in selected samples\n')
         if batch.skipped is not None and batch.skipped.any():
             # records the reference never hands to a model (k is None, input.py:603-611)
             flags[batch.skipped] = _lib.F_AF_FILTER | _lib.F_PREFILTER
@@ -370,7 +377,22 @@ def main(argv=None):
                          lineage=(False if (o.lineage and not o.lmm) else None), comm=comm,
                          rows_max=gpu_batch)
     pool = None
-    if isinstance(reader, VariantReader):
+    # k-mer text is tokenised on the device (psb_submit_text) unless something downstream needs the
+    # packed rows on the host: sample lists, lineage fits, pattern hashes, the packed cache
+    text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and \
+        not (o.print_samples or o.lineage or o.output_patterns or o.bits_cache) and \
+        os.environ.get('PYSEER_B200_TEXT', '1') != '0'
+    if text_mode:
+        # page-locked text buffers sized for a full batch at an allele frequency of 0.5 (a batch cut
+        # short by its buffer keeps whole blocks, see psb_reader_next_text)
+        name_bytes = sum(len(x) for x in reader.samples) + 3 * reader.n_samples
+        per_line = name_bytes // 2 + 512
+        text_bytes = int(min(max(32 << 20, gpu_batch * per_line), 768 << 20))
+        for e in engines:
+            e.text_setup(reader.samples)
+        pool = pipeline.TextPool(2 * n_gpus + 2, gpu_batch, text_bytes)
+        source = reader.text_batches(gpu_batch, block_size=o.block_size, pool=pool)
+    elif isinstance(reader, VariantReader):
         pool = pipeline.PinnedPool(5 * n_gpus + 3, gpu_batch, reader.W, reader.var_type == 'Rtab')
         source = reader.batches(gpu_batch, pool=pool)
     else:

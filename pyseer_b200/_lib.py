@@ -84,7 +84,8 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_comm_unique_id', 'psb_comm_init_rank', 'psb_comm_init_all', 'psb_comm_destroy',
            'psb_comm_info', 'psb_comm_bcast', 'psb_comm_allreduce', 'psb_comm_barrier',
            'psb_comm_gather_begin', 'psb_comm_gather_wait', 'psb_comm_gather_fetch',
-           'psb_comm_gather_bytes', 'psb_measure_peaks', 'psb_reader_at_eof', 'psb_spectral']
+           'psb_comm_gather_bytes', 'psb_measure_peaks', 'psb_reader_at_eof', 'psb_spectral',
+           'psb_reader_next_text', 'psb_text_setup', 'psb_submit_text', 'psb_text_info']
 
 
 def load():
@@ -123,6 +124,11 @@ def load():
     lib.psb_eigh.argtypes = [c_void_p, c_int32, dp, dp, dp]
     lib.psb_spectral.argtypes = [c_void_p, c_int32, c_int32, dp, dp, dp, dp, dp]
     lib.psb_reader_set_threads.argtypes = [c_void_p, c_int32]
+    lib.psb_reader_next_text.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                         c_void_p, c_int64, c_void_p, POINTER(c_int64), POINTER(c_int64)]
+    lib.psb_text_setup.argtypes = [c_void_p, POINTER(ctypes.c_char_p), c_int32]
+    lib.psb_submit_text.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64]
+    lib.psb_text_info.argtypes = [c_void_p, c_void_p, c_int64]
     lib.psb_hash_patterns.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                       POINTER(c_int64)]
     lib.psb_reader_vcf_info.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]

@@ -115,6 +115,7 @@ int psb_destroy(psb_ctx *c) {
     cudaStreamSynchronize(c->copy_stream);
     psb_kinship_release(c);
     psb_burden_release(c);
+    psb_text_release(c);
     psb_free_model(c);
     free_tables(c);
     for (int i = 0; i < 2; ++i) {

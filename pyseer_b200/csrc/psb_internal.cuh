@@ -169,6 +169,7 @@ struct psb_ctx {
     int64_t counts[4] = {0, 0, 0, 0};
     bool ran = false;
     void *kin = nullptr;          // psb_kinship.cu state
+    void *text = nullptr;         // psb_text.cu state (device k-mer text parser)
 
     // ---- burden regions (psb_burden.cu) ----
     uint32_t *bur_vbits = nullptr, *bur_vmiss = nullptr;   // member record rows (host submits)
@@ -187,6 +188,7 @@ int psb_run_end(psb_ctx *ctx);
 int psb_free_model(psb_ctx *ctx);
 void psb_kinship_release(psb_ctx *ctx);
 void psb_burden_release(psb_ctx *ctx);
+void psb_text_release(psb_ctx *ctx);
 
 // psb_varstats.cu
 int psb_launch_bitsums(psb_ctx *ctx);

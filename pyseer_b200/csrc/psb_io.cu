@@ -17,6 +17,7 @@
 #include <string>
 #include <string_view>
 #include <thread>
+#include <unistd.h>
 #include <unordered_map>
 #include <vector>
 
@@ -47,6 +48,12 @@ struct psb_reader {
     std::vector<std::string> vcf_contig;
     std::vector<int64_t> vcf_pos;
     std::vector<int32_t> vcf_reflen;
+    // text mode (psb_reader_next_text): bytes read past the end of the last batch, file offset of the
+    // plain-text reads, mean line length seen so far
+    std::vector<char> carry;
+    int64_t file_off = 0;
+    double text_bytes_seen = 0.0, text_lines_seen = 0.0;
+    bool text_eof = false;
 };
 
 // ---- BGZF (bgzip) input: independent deflate blocks of <= 64 KiB, inflated on the parser threads ----
@@ -581,6 +588,223 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
         if ((outs[v].flags & 1) && any_missing) *any_missing = 1;
     }
     *n_read = n;
+    return PSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Text mode: the decompressed k-mer text itself, cut into lines, for the device parser
+// (psb_submit_text, psb_text.cu).  The host no longer tokenises: it reads (plain: pread on --cpu
+// threads; BGZF: block-parallel inflate; gzip: zlib) STRAIGHT into the caller's page-locked buffer,
+// finds the newlines (on the same threads) and copies the variant names out.  Rules of the row
+// reader kept: trailing '\r', ' ', '\t' are trimmed, empty lines skipped, the name is the first
+// blank-delimited token.
+// ---------------------------------------------------------------------------------------
+static int64_t text_read_more(psb_reader *r, char *dst, int64_t want) {
+    if (r->text_eof || want <= 0) return 0;
+    int64_t got = 0;
+    if (r->raw && !r->bgzf) {
+        const int fd = fileno(r->raw);
+        const int T = (int)std::max<int64_t>(1, std::min<int64_t>(r->n_threads, want >> 22));
+        std::vector<int64_t> part(T, 0);
+        auto work = [&](int t) {
+            const int64_t lo = want * t / T, hi = want * (t + 1) / T;
+            int64_t done = 0;
+            while (lo + done < hi) {
+                const ssize_t k = pread(fd, dst + lo + done, (size_t)(hi - lo - done), (off_t)(r->file_off + lo + done));
+                if (k <= 0) break;
+                done += k;
+            }
+            part[t] = done;
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+        // a short slice can only be the one that met the end of the file
+        for (int t = 0; t < T; ++t) {
+            got += part[t];
+            if (part[t] < want * (t + 1) / T - want * t / T) break;
+        }
+        r->file_off += got;
+        if (got < want) r->text_eof = true;
+        return got;
+    }
+    if (r->raw && r->bgzf) {
+        // whole blocks whose text fits `want`, inflated in parallel into their final place
+        std::vector<unsigned char> &in = r->bgzf_in;
+        in.clear();
+        std::vector<bgzf_block> blocks;
+        int64_t out_total = 0;
+        for (;;) {
+            unsigned char h[18];
+            const long at_file = ftell(r->raw);
+            const size_t n = fread(h, 1, sizeof(h), r->raw);
+            if (n == 0) { r->text_eof = true; break; }
+            if (n != sizeof(h) || h[0] != 0x1f || h[1] != 0x8b || !(h[3] & 4) || h[12] != 'B' || h[13] != 'C') {
+                r->bgzf_err = true;
+                return -1;
+            }
+            const size_t bsize = (size_t)h[16] + ((size_t)h[17] << 8) + 1;
+            const size_t xlen = (size_t)h[10] + ((size_t)h[11] << 8);
+            const size_t head = 12 + xlen;
+            if (bsize < head + 8) { r->bgzf_err = true; return -1; }
+            const size_t rest = bsize - sizeof(h);
+            const size_t at = in.size();
+            in.resize(at + rest);
+            if (fread(in.data() + at, 1, rest, r->raw) != rest) { r->bgzf_err = true; return -1; }
+            const unsigned char *tr = in.data() + at + rest - 8;
+            const size_t isize = (size_t)tr[4] | ((size_t)tr[5] << 8) | ((size_t)tr[6] << 16) | ((size_t)tr[7] << 24);
+            if (isize == 0) { in.resize(at); continue; }
+            if (out_total + (int64_t)isize > want) {
+                // does not fit any more: this block opens the next call
+                in.resize(at);
+                fseek(r->raw, at_file, SEEK_SET);
+                break;
+            }
+            blocks.push_back({at + (head - sizeof(h)), bsize - head - 8, (size_t)out_total, isize});
+            out_total += (int64_t)isize;
+        }
+        if (blocks.empty()) return 0;
+        std::atomic<int> next(0), bad(0);
+        auto work = [&]() {
+            for (;;) {
+                const int b = next.fetch_add(1);
+                if (b >= (int)blocks.size()) return;
+                const bgzf_block &k = blocks[b];
+                if (bgzf_inflate_one(in.data() + k.in_off, k.in_len, (unsigned char *)dst + k.out_off, k.out_len))
+                    bad.store(1);
+            }
+        };
+        const int T = std::max(1, std::min<int>(r->n_threads, (int)blocks.size()));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(work);
+        work();
+        for (auto &th : pool) th.join();
+        if (bad.load()) { r->bgzf_err = true; return -1; }
+        return out_total;
+    }
+    while (got < want) {
+        const int k = gzread(r->fh, dst + got, (unsigned)std::min<int64_t>(want - got, 1 << 30));
+        if (k <= 0) { r->text_eof = true; break; }
+        got += k;
+    }
+    return got;
+}
+
+// positions of the '\n' bytes of dst[lo, hi), on up to n_threads threads
+static void text_find_newlines(const char *dst, int64_t lo, int64_t hi, int n_threads, std::vector<int64_t> &nl) {
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, (hi - lo) >> 22));
+    std::vector<std::vector<int64_t>> part(T);
+    auto work = [&](int t) {
+        const int64_t a = lo + (hi - lo) * t / T, b = lo + (hi - lo) * (t + 1) / T;
+        const char *p = dst + a, *e = dst + b;
+        while (p < e) {
+            const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+            if (!q) break;
+            part[t].push_back(q - dst);
+            p = q + 1;
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    for (int t = 0; t < T; ++t) nl.insert(nl.end(), part[t].begin(), part[t].end());
+}
+
+// Fills dst (dst_cap bytes, ideally page-locked) with the text of up to max_lines k-mer lines.
+// line_start[v] / line_len[v]: line v inside dst, trimmed; names / name_off as psb_reader_next.
+// *n_read lines use the first *n_bytes bytes of dst.  Fewer than max_lines lines come back at the
+// end of the file (psb_reader_at_eof) or when dst / names cannot take more: then *n_read is a
+// multiple of line_multiple (the caller's block size) so that block boundaries do not move, and
+// the rest opens the next call.  PSB_ERR_NOMEM: not even line_multiple lines fit.
+extern "C" int psb_reader_next_text(psb_reader *r, int64_t max_lines, int64_t line_multiple, char *dst,
+                                    int64_t dst_cap, int64_t *line_start, int32_t *line_len, char *names,
+                                    int64_t names_cap, int64_t *name_off, int64_t *n_read, int64_t *n_bytes) {
+    PSB_REQUIRE(r && dst && line_start && line_len && names && name_off && n_read && n_bytes, PSB_ERR_ARG,
+                "NULL argument");
+    PSB_REQUIRE(r->var_type == 0, PSB_ERR_ARG, "text mode reads k-mer files only");
+    PSB_REQUIRE(!r->have_pending && r->pos == r->len, PSB_ERR_STATE, "text mode cannot follow psb_reader_next");
+    PSB_REQUIRE(max_lines > 0 && dst_cap > 0, PSB_ERR_ARG, "empty buffer");
+    if (line_multiple < 1) line_multiple = 1;
+    *n_read = 0;
+    *n_bytes = 0;
+    int64_t have = (int64_t)r->carry.size();
+    PSB_REQUIRE(have <= dst_cap, PSB_ERR_NOMEM, "text buffer of %lld bytes too small", (long long)dst_cap);
+    if (have) memcpy(dst, r->carry.data(), (size_t)have);
+    r->carry.clear();
+    int64_t n = 0, used = 0, scanned = 0, line_at = 0, consumed = 0;
+    bool full = false;
+    std::vector<int64_t> nl;
+    auto take_line = [&](int64_t a, int64_t b) -> bool {      // dst[a, b) without its newline
+        int64_t e = b;
+        while (e > a && (dst[e - 1] == '\r' || dst[e - 1] == ' ' || dst[e - 1] == '\t')) --e;
+        if (e == a) return true;                              // empty line: skipped
+        int64_t i = a;
+        while (i < e && (dst[i] == ' ' || dst[i] == '\t')) ++i;
+        int64_t j = i;
+        while (j < e && dst[j] != ' ' && dst[j] != '\t') ++j;
+        if (j - i + 1 > names_cap - used || e - a > 0x7fffffffll) return false;
+        memcpy(names + used, dst + i, (size_t)(j - i));
+        names[used + (j - i)] = '\0';
+        name_off[n] = used;
+        used += j - i + 1;
+        line_start[n] = a;
+        line_len[n] = (int32_t)(e - a);
+        ++n;
+        return true;
+    };
+    for (;;) {
+        // lines complete in dst[scanned, have)
+        nl.clear();
+        text_find_newlines(dst, scanned, have, r->n_threads, nl);
+        scanned = have;
+        for (size_t k = 0; k < nl.size() && n < max_lines && !full; ++k) {
+            if (!take_line(line_at, nl[k])) { full = true; break; }
+            line_at = nl[k] + 1;
+            consumed = line_at;
+        }
+        if (n >= max_lines || full) break;
+        if (r->text_eof) {
+            // the last line of the file may come without a newline
+            if (line_at < have) {
+                if (take_line(line_at, have)) {
+                    line_at = have;
+                    consumed = have;
+                } else {
+                    full = true;
+                }
+            }
+            break;
+        }
+        // more text: what the missing lines should take at the mean line length seen so far
+        const double mean = r->text_lines_seen > 0 ? r->text_bytes_seen / r->text_lines_seen
+                                                   : (n > 0 ? (double)consumed / (double)n : 0.0);
+        int64_t want = mean > 0 ? (int64_t)((double)(max_lines - n) * mean * 1.01) - (have - line_at) + (256 << 10)
+                                : (int64_t)8 << 20;
+        if (want < (1 << 20)) want = 1 << 20;
+        if (want > dst_cap - have) want = dst_cap - have;
+        if (want <= 0 || (r->bgzf && want < (1 << 16))) { full = true; break; }
+        const int64_t got = text_read_more(r, dst + have, want);
+        PSB_REQUIRE(got >= 0, PSB_ERR_ARG, "corrupt BGZF block in the variant file");
+        if (got == 0 && !r->text_eof) { full = true; break; }     // BGZF: the next block does not fit
+        have += got;
+    }
+    if (full && n < max_lines) {
+        // cut short by a buffer: keep whole blocks of the caller's block size
+        const int64_t keep = n / line_multiple * line_multiple;
+        PSB_REQUIRE(keep > 0, PSB_ERR_NOMEM, "text / name buffers too small for %lld lines", (long long)line_multiple);
+        if (keep < n) {
+            n = keep;
+            consumed = line_start[keep];      // the first dropped line opens the next call
+        }
+    }
+    r->carry.assign(dst + consumed, dst + have);
+    r->text_bytes_seen += (double)consumed;
+    r->text_lines_seen += (double)n;
+    r->drained = r->text_eof && r->carry.empty();
+    *n_read = n;
+    *n_bytes = consumed;
     return PSB_OK;
 }
 

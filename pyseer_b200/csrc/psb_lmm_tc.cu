@@ -395,6 +395,17 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             advance2(cq, cks);
             // expand one 128-sample stage of this thread's variant into A slot sa, then signal
             auto emit = [&](const uint4 &w4a, const uint4 &w4b) {
+                const uint32_t ws[8] = {w4a.x, w4a.y, w4a.z, w4a.w, w4b.x, w4b.y, w4b.z, w4b.w};
+                // register 8 i + b, byte t <- sample 8 t + b of word i (the B operand is stored
+                // with the same permutation, see k_tc_quantise).  The expansion does not depend
+                // on the A slot being free, so it runs BEFORE the wait: what is left on the
+                // critical path between the commit that frees the slot and this stage's arrival
+                // is one 32-register tcgen05.st, the expansion of the second half and its store.
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) r[i * 8 + b] = (ws[i] >> b) & 0x01010101u;
                 if (lead > 0) {
                     --lead;
                 } else {
@@ -403,22 +414,14 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     while (we >= ns) { we -= ns; wph ^= 1u; }
                 }
                 tc_fence_after();
-                const uint32_t ws[8] = {w4a.x, w4a.y, w4a.z, w4a.w, w4b.x, w4b.y, w4b.z, w4b.w};
                 const uint32_t base = lane_addr + (uint32_t)(A_COL0 + sa * A_COLS);
+                tc_st32(base, r);
+                // second half: the store above has read its registers when it issued
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    // register b, byte t <- sample 8 t + b of the word (the B operand is
-                    // stored with the same permutation, see k_tc_quantise)
-                    uint32_t r[8];
-                    if (args.debug & 2) {
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int b = 0; b < 8; ++b) r[b] = ws[i];
-                    } else {
-#pragma unroll
-                        for (int b = 0; b < 8; ++b) r[b] = (ws[i] >> b) & 0x01010101u;
-                    }
-                    tc_st8(base + i * 8, r);
-                }
+                    for (int b = 0; b < 8; ++b) r[i * 8 + b] = (ws[4 + i] >> b) & 0x01010101u;
+                tc_st32(base + 32, r);
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();

@@ -53,29 +53,34 @@ PSB_HD double psb_lgamma_half_diff(double a) {
     return lgamma(a + 0.5) - lgamma(a);
 }
 
-// Continued fraction for the incomplete beta function (modified Lentz).
+// Continued fraction for the incomplete beta function, evaluated by the forward recurrence of its
+// numerators and denominators (Wallis), renormalised by the last denominator after every double
+// step: two reciprocals per step -- one shared by both partial numerators, one for the
+// renormalisation -- where the modified Lentz scheme divides six times.  This is the per-variant
+// cost of the Welch pre-filter and of F.sf in the LMM epilogue (fp64 divisions are ~25 instructions).
 PSB_HD double psb_betacf(double a, double b, double x) {
-    const double FPMIN = 1e-300, EPS = 1e-16;
-    double qab = a + b, qap = a + 1.0, qam = a - 1.0;
-    double c = 1.0, d = 1.0 - qab * x / qap;
-    if (fabs(d) < FPMIN) d = FPMIN;
-    d = 1.0 / d;
-    double h = d;
+    const double TINY = 1e-290, EPS = 2.3e-16;
+    const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double am = 1.0, bm = 1.0, az = 1.0, bz = 1.0 - qab * x / qap;
     for (int m = 1; m <= 20000; ++m) {
-        double m2 = 2.0 * m;
-        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
-        d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
-        c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
-        d = 1.0 / d; h *= d * c;
-        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
-        d = 1.0 + aa * d; if (fabs(d) < FPMIN) d = FPMIN;
-        c = 1.0 + aa / c; if (fabs(c) < FPMIN) c = FPMIN;
-        d = 1.0 / d;
-        double del = d * c;
-        h *= del;
-        if (fabs(del - 1.0) <= EPS) break;
+        const double em = (double)m, tem = em + em;
+        const double u = qam + tem, v = a + tem, w = qap + tem;
+        const double rden = x / (u * v * w);
+        const double d1 = em * (b - em) * w * rden;
+        const double ap = fma(d1, am, az), bp = fma(d1, bm, bz);
+        const double d2 = -(a + em) * (qab + em) * u * rden;
+        const double app = fma(d2, az, ap);
+        double bpp = fma(d2, bz, bp);
+        if (fabs(bpp) < TINY) bpp = TINY;
+        const double r = 1.0 / bpp;
+        const double aold = az;
+        am = ap * r;
+        bm = bp * r;
+        az = app * r;
+        bz = 1.0;
+        if (fabs(az - aold) <= EPS * fabs(az)) break;
     }
-    return h;
+    return az;
 }
 
 // Survival function of t^2 with df degrees of freedom evaluated at t2 >= 0:
@@ -93,7 +98,29 @@ PSB_HD double psb_t2_sf(double t2, double df) {
     // ln B(a, 1/2) = lgamma(a) + lgamma(1/2) - lgamma(a + 1/2)
     double lnB = 0.5723649429247000870717135 - psb_lgamma_half_diff(a);
     double bt = exp(a * lnx + b * ln1mx - lnB);
-    if (x < (a + 1.0) / (a + b + 2.0))
-        return bt * psb_betacf(a, b, x) / a;
+    // Tail: I_x(a, 1/2) by its continued fraction, which is fast and well conditioned for
+    // x < (a + 1) / (a + b + 2) once t2 is past ~12 (<= 20 steps).
+    // Bulk: p = 1 - I_{1-x}(1/2, a) with the hypergeometric series
+    //     I_xc(1/2, a) = 2 bt sum_n T_n,  T_0 = 1,  T_{n+1} = T_n xc (a + 1/2 + n) / (n + 3/2)
+    // -- positive terms, one reciprocal and four multiply-adds each, <= ~50 of them for t2 <= 12 --
+    // instead of the textbook switch between the two continued fractions at t2 ~ 3, which puts the
+    // slow side of BOTH (50 steps of six divisions at t2 = 3.1, df = 5000) where most null variants
+    // are; a warp runs as long as its slowest lane.  Past the textbook switch point the
+    // complementary continued fraction is also ill conditioned (its value grows to ~150 at t2 = 12),
+    // the series is not.  Small df (a < 16) keep the textbook rule: the series converges like xc^n.
+    const bool direct = x < (a + 1.0) / (a + b + 2.0);
+    if (direct && (t2 > 12.0 || a < 16.0)) return bt * psb_betacf(a, b, x) / a;
+    if (direct || a >= 16.0) {
+        double term = 1.0, sum = 1.0;
+        const double am = a - 1.0;
+        for (int n = 0; n < 4000; ++n) {
+            // (a + 1/2 + n) / (n + 3/2) = 1 + (a - 1) / (n + 3/2)
+            const double r = 1.0 / ((double)n + 1.5);
+            term *= xc * fma(am, r, 1.0);
+            sum += term;
+            if (term <= 1e-17 * sum) break;
+        }
+        return 1.0 - 2.0 * bt * sum;
+    }
     return 1.0 - bt * psb_betacf(b, a, xc) / b;
 }

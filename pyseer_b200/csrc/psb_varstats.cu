@@ -309,6 +309,101 @@ k_bitstats(const uint32_t *__restrict__ bits, int64_t S, int Wrow, int Wn,
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Popcount-only stats pass at HBM speed (no missing genotypes, no fp64 columns): carriers and
+// the 2x2 table.  G lanes share a row and read it in 16-byte cells (G = 32 / 16 / 8 by row
+// width, so short rows still fill the warp: 32 / G rows side by side); BSV_U row groups are in
+// flight per warp, i.e. every lane has up to 16 independent 16-byte loads outstanding.  The three
+// counts of a row travel as one packed 64-bit word (21 bits each) through a transposing butterfly:
+// each exchange halves the number of live values, 2.25 shuffles per row instead of 15.
+// The phenotype masks sit in shared memory, zero padded to the row width.
+// ---------------------------------------------------------------------------------
+#define BSV_U 8
+
+template <int G>
+__global__ void __launch_bounds__(256)
+k_bitstats_v(const uint32_t *__restrict__ bits, int64_t S, int Wrow, int Wn,
+             const uint32_t *__restrict__ y1, const uint32_t *__restrict__ y0,
+             const uint32_t *__restrict__ valid, int n_y1, int n_y0,
+             int32_t *__restrict__ carriers, int32_t *__restrict__ nmissing, int32_t *__restrict__ tab) {
+    extern __shared__ __align__(16) unsigned char bsv_smem[];
+    uint4 *sV = reinterpret_cast<uint4 *>(bsv_smem);          // [Wq] valid, then y1, then y0
+    const int Wq = Wrow >> 2;
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *>(bsv_smem);
+        for (int e = threadIdx.x; e < Wrow; e += blockDim.x) {
+            const bool in = e < Wn;
+            w[e] = in ? valid[e] : 0u;
+            w[Wrow + e] = in ? y1[e] : 0u;
+            w[2 * Wrow + e] = in ? y0[e] : 0u;
+        }
+        __syncthreads();
+    }
+    const uint4 *s1 = sV + Wq, *s0 = sV + 2 * Wq;
+    constexpr int RPG = 32 / G;                  // rows side by side in a warp
+    constexpr int RPP = RPG * BSV_U;             // rows per warp pass
+    const int lane = threadIdx.x & 31, sg = lane / G, ql = lane % G;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPP;
+    const uint4 *rows = reinterpret_cast<const uint4 *>(bits);
+    for (; base < S; base += warps_total * RPP) {
+        int c_all[BSV_U], n11[BSV_U], n01[BSV_U];
+#pragma unroll
+        for (int u = 0; u < BSV_U; ++u) c_all[u] = n11[u] = n01[u] = 0;
+        for (int q = ql; q < Wq; q += G) {
+            uint4 x[BSV_U];
+#pragma unroll
+            for (int u = 0; u < BSV_U; ++u) {
+                const int64_t r = base + u * RPG + sg;
+                x[u] = r < S ? __ldcs(rows + r * Wq + q) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            const uint4 vb = sV[q], a1 = s1[q], a0 = s0[q];
+#pragma unroll
+            for (int u = 0; u < BSV_U; ++u) {
+                const uint32_t xa = x[u].x & vb.x, xb = x[u].y & vb.y, xc = x[u].z & vb.z, xd = x[u].w & vb.w;
+                c_all[u] += __popc(xa) + __popc(xb) + __popc(xc) + __popc(xd);
+                n11[u] += __popc(xa & a1.x) + __popc(xb & a1.y) + __popc(xc & a1.z) + __popc(xd & a1.w);
+                n01[u] += __popc(xa & a0.x) + __popc(xb & a0.y) + __popc(xc & a0.z) + __popc(xd & a0.w);
+            }
+        }
+        unsigned long long v[BSV_U];
+#pragma unroll
+        for (int u = 0; u < BSV_U; ++u)
+            v[u] = (unsigned long long)c_all[u] | ((unsigned long long)n11[u] << 21) |
+                   ((unsigned long long)n01[u] << 42);
+        // transposing butterfly inside the G lanes of a row group: offsets G/2 .. 1; while more than
+        // one value is live a lane keeps one half and hands the other half over
+        int usel = 0;
+#pragma unroll
+        for (int o = G / 2, n = BSV_U; o > 0; o >>= 1) {
+            if (n > 1) {
+                const int half = n / 2;
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int i = 0; i < half; ++i) {
+                    const unsigned long long send = up ? v[i] : v[i + half];
+                    const unsigned long long keep = up ? v[i + half] : v[i];
+                    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+                usel = usel * 2 + (up ? 1 : 0);
+                n = half;
+            } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+            }
+        }
+        // G >= BSV_U, so one value is left: row group `usel`, complete in the lanes whose low
+        // log2(G / BSV_U) bits are zero
+        const int64_t r = base + usel * RPG + sg;
+        if ((ql & (G / BSV_U - 1)) == 0 && r < S) {
+            const int ca = (int)(v[0] & 0x1fffffu), a11 = (int)((v[0] >> 21) & 0x1fffffu),
+                      a01 = (int)((v[0] >> 42) & 0x1fffffu);
+            carriers[r] = ca;
+            nmissing[r] = 0;
+            *reinterpret_cast<int4 *>(tab + r * 4) = make_int4(a11, n_y1 - a11, a01, n_y0 - a01);
+        }
+    }
+}
+
 int psb_upload_welch_T(psb_ctx *c, const double *yc, const double *yc2) {
     const int Wn = c->Wn, N = c->N;
     std::vector<double> t((size_t)32 * Wn * 2, 0.0);
@@ -346,6 +441,22 @@ int psb_launch_bitstats(psb_ctx *c, int continuous) {
         k_bitstats<2><<<(int)blocks, 256, smem, c->stream>>>(
             c->d_bits, c->S, c->Wrow, c->Wn, c->d_y1bits, c->d_y0bits, c->d_valid, ct, c->welch_T1,
             c->welch_T2, c->n_y1, c->n_y0, c->C, c->col_w0, c->d_carriers, c->d_missing, c->d_tab, c->d_sums);
+    } else if (c->N < (1 << 21) && (size_t)c->Wrow * 12 <= 48 * 1024 &&
+               !(getenv("PSB_BITSTATS_V") && atoi(getenv("PSB_BITSTATS_V")) == 0)) {
+        // popcounts only: 16-byte loads, G lanes per row
+        const int Wq = c->Wrow >> 2;
+        const size_t sm = (size_t)c->Wrow * 12;
+        const int G = Wq <= 8 ? 8 : Wq <= 16 ? 16 : 32;
+        const int64_t rpp = (int64_t)(32 / G) * BSV_U * 8;             // rows per block pass
+        int64_t nb = std::min<int64_t>((c->S + rpp - 1) / rpp, (int64_t)c->sm_count * 4);
+#define BSV_LAUNCH(GG)                                                                                  \
+        k_bitstats_v<GG><<<(int)nb, 256, sm, c->stream>>>(c->d_bits, c->S, c->Wrow, c->Wn, c->d_y1bits, \
+                                                          c->d_y0bits, c->d_valid, c->n_y1, c->n_y0,     \
+                                                          c->d_carriers, c->d_missing, c->d_tab)
+        if (G == 8) BSV_LAUNCH(8);
+        else if (G == 16) BSV_LAUNCH(16);
+        else BSV_LAUNCH(32);
+#undef BSV_LAUNCH
     } else {
         k_bitstats<0><<<(int)blocks, 256, 0, c->stream>>>(
             c->d_bits, c->S, c->Wrow, c->Wn, c->d_y1bits, c->d_y0bits, c->d_valid, ct, c->welch_T1,

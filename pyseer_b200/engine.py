@@ -227,6 +227,29 @@ class Engine(object):
                                   bits.shape[0], bits.shape[1]))
         self.n_variants = bits.shape[0]
 
+    def text_setup(self, samples):
+        """Device lookup table of the sample names (phenotype order) for ``submit_text``."""
+        names = (ctypes.c_char_p * len(samples))(*[str(x).encode() for x in samples])
+        check(self.lib.psb_text_setup(self._ctx, names, len(samples)))
+        self._text_ready = True
+
+    def submit_text(self, text, n_bytes, line_start, line_len, n_lines):
+        """``submit`` for k-mer text (``psb_submit_text``): ``text`` (uint8, ideally page-locked) holds
+        ``n_lines`` lines located by ``line_start`` (int64) / ``line_len`` (int32), as
+        ``TextKmerReader`` produces them; the rows are built on the device."""
+        self._keep = [text, line_start, line_len]
+        check(self.lib.psb_submit_text(self._ctx, c_void_p(text.ctypes.data), int(n_bytes),
+                                       c_void_p(line_start.ctypes.data), c_void_p(line_len.ctypes.data),
+                                       int(n_lines)))
+        self.n_variants = int(n_lines)
+
+    def text_info(self, n_lines):
+        """Per-line flags of the text batch the last run worked on (2: no observation in the selected
+        samples, 4: line without '|')."""
+        info = np.zeros(int(n_lines), dtype=np.int32)
+        check(self.lib.psb_text_info(self._ctx, c_void_p(info.ctypes.data), int(n_lines)))
+        return info
+
     def submit_burden(self, bits, missing, region_offsets, members):
         """Burden regions (input.py:395-411): ``bits`` / ``missing`` hold one packed row per VCF
         record; region r is the union of records ``members[region_offsets[r]:region_offsets[r+1]]``.

@@ -135,7 +135,7 @@ def hash_patterns(bits, missing, n_samples, flags=None):
 
 class VariantBatch(object):
     """``n`` variants as packed rows plus what the result loop needs to print them."""
-    __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped']
+    __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped', 'text', 'info']
 
     def __init__(self, names, bits, missing):
         self.names = names
@@ -144,6 +144,8 @@ class VariantBatch(object):
         self.n = len(names)
         self.token = None          # buffer-pool token (pipeline.py), released by the consumer
         self.skipped = None        # bool mask: records the reference never hands to a model
+        self.text = None           # (uint8 text, n_bytes, line_start, line_len): rows are built on the device
+        self.info = None           # ... and their per-line flags (Engine.text_info), set by the runner
 
 
 class VariantReader(object):
@@ -233,6 +235,57 @@ class VariantReader(object):
             b = VariantBatch(nm, bits[:filled], miss[:filled] if (miss is not None and any_missing) else None)
             b.token = token
             yield b
+
+    def text_batches(self, size, block_size=1, pool=None, text_cap=None, names_cap=None):
+        """The same batches as TEXT for the device parser (``psb_reader_next_text`` ->
+        ``Engine.submit_text``): the host only reads / inflates and cuts lines, ``VariantBatch.text``
+        carries ``(text, n_bytes, line_start, line_len)`` and ``bits`` is None.  Batches hold ``size``
+        lines; a batch cut short by the text buffer keeps a multiple of ``block_size`` lines.
+        ``pool``: ``pool.get() -> (text, line_start, line_len, token)`` page-locked buffers."""
+        import ctypes
+        from . import _lib
+        if self.var_type != 'kmers':
+            raise ValueError('text batches exist for k-mer files only')
+        ncap = int(names_cap or max(1 << 20, 160 * size))
+        while True:
+            token = None
+            if pool is not None:
+                text, lstart, llen, token = pool.get()
+            else:
+                cap = int(text_cap or max(64 << 20, size * (6 * self.n_samples + 256)))
+                text = np.empty(cap, dtype=np.uint8)
+                lstart = np.empty(size, dtype=np.int64)
+                llen = np.empty(size, dtype=np.int32)
+            rows = min(size, lstart.shape[0])
+            off = np.empty(rows, dtype=np.int64)
+            while True:
+                names = ctypes.create_string_buffer(ncap)
+                n, nb = ctypes.c_int64(0), ctypes.c_int64(0)
+                rc = self._lib.psb_reader_next_text(
+                    self._h, rows, int(block_size), text.ctypes.data, text.shape[0], lstart.ctypes.data,
+                    llen.ctypes.data, ctypes.addressof(names), ncap, off.ctypes.data, ctypes.byref(n),
+                    ctypes.byref(nb))
+                if rc == _lib.PSB_ERR_NOMEM and ncap < (1 << 30) and pool is None and text_cap is None:
+                    ncap *= 4
+                    continue
+                _lib.check(rc)
+                break
+            n = n.value
+            if n == 0:
+                if pool is not None:
+                    pool.put(token)
+                return
+            nm = names.raw[:int(off[n - 1])].decode().split('\0')[:n - 1] if n > 1 else []
+            raw = names.raw
+            nm.append(raw[off[n - 1]:raw.index(b'\0', off[n - 1])].decode())
+            b = VariantBatch(nm, None, None)
+            b.text = (text, nb.value, lstart, llen)
+            b.token = token
+            yield b
+            eof = ctypes.c_int32(0)
+            _lib.check(self._lib.psb_reader_at_eof(self._h, ctypes.byref(eof)))
+            if eof.value:
+                return
 
     # -- per-variant detail, only when needed ------------------------------------------
     def sample_lists(self, batch, j):

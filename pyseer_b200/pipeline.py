@@ -6,7 +6,9 @@ Three stages run concurrently, each in its own thread (the native parser, the CU
 native formatter all release the GIL):
 
   reader     parses batch k+1 of the variant file straight into a page-locked buffer of a small pool
-             (``PinnedPool``), so that ``psb_submit`` is a true asynchronous DMA;
+             (``PinnedPool``), so that ``psb_submit`` is a true asynchronous DMA; plain k-mer files go
+             one step further (``TextPool``): the reader only reads / inflates the TEXT into the
+             page-locked buffer and cuts it into lines, the device tokenises it (``psb_submit_text``);
   GPU        ``BatchRunner``: submit(k+1) on the copy stream while the kernels of batch k run, then
              fetch(k); with several GPUs a *super-step* deals one batch to every GPU (contiguous,
              in input order), the runs are queued from one thread per GPU, and the result tables come
@@ -50,6 +52,42 @@ class PinnedPool(object):
             if m is not None:
                 m.free()
         self._bufs = []
+
+
+class TextPool(object):
+    """``n`` page-locked (text, line_start, line_len) buffer sets for ``VariantReader.text_batches``."""
+
+    def __init__(self, n, rows, text_bytes):
+        self._bufs = []
+        self._free = queue.Queue()
+        for i in range(n):
+            self._bufs.append((PinnedBuffer((text_bytes,), np.uint8), PinnedBuffer((rows,), np.int64),
+                               PinnedBuffer((rows,), np.int32)))
+            self._free.put(i)
+
+    def get(self):
+        i = self._free.get()
+        t, a, b = self._bufs[i]
+        return t.array, a.array, b.array, i
+
+    def put(self, token):
+        if token is not None:
+            self._free.put(token)
+
+    def close(self):
+        for bufs in self._bufs:
+            for b in bufs:
+                b.free()
+        self._bufs = []
+
+
+def submit_batch(eng, b):
+    """Rows of a batch to the engine: packed rows from the host, or k-mer text for the device parser."""
+    if b.text is not None:
+        text, n_bytes, lstart, llen = b.text
+        eng.submit_text(text, n_bytes, lstart, llen, b.n)
+    else:
+        eng.submit(b.bits, b.missing)
 
 
 class _Stop(object):
@@ -115,11 +153,19 @@ class BatchRunner(object):
             self._pool.shutdown()
             self._pool = None
 
-    def _fetch(self, eng):
+    def _fetch(self, eng, b):
         r = eng.fetch()
         if self.lineage is not None:
             r.lineage = eng.run_lineage(self.lineage)
+        self._text_info(eng, b)
         return r
+
+    @staticmethod
+    def _text_info(eng, b):
+        # a batch parsed on the device: its per-line flags (no observation / malformed line) are read
+        # while the engine still holds it, i.e. before the next run is queued
+        if b.text is not None:
+            b.info = eng.text_info(b.n)
 
     def results(self, batches):
         if len(self.engines) == 1:
@@ -133,13 +179,13 @@ class BatchRunner(object):
         eng = self.engines[0]
         prev = None
         for b in batches:
-            eng.submit(b.bits, b.missing)          # H2D of batch k+1 on the copy stream ...
+            submit_batch(eng, b)                   # H2D of batch k+1 on the copy stream ...
             if prev is not None:
-                yield prev, self._fetch(eng)       # ... while batch k finishes and comes back
+                yield prev, self._fetch(eng, prev)  # ... while batch k finishes and comes back
             self.run(eng)
             prev = b
         if prev is not None:
-            yield prev, self._fetch(eng)
+            yield prev, self._fetch(eng, prev)
 
     def _multi(self, batches):
         n = len(self.engines)
@@ -150,14 +196,15 @@ class BatchRunner(object):
                 self.comm.gather_wait()
                 for g, b in enumerate(grp):
                     r, _, _ = self.comm.gather_fetch(g, n_betas=self.n_betas)
+                    self._text_info(self.engines[g], b)
                     yield b, r
             else:
                 for g, b in enumerate(grp):
-                    yield b, self._fetch(self.engines[g])
+                    yield b, self._fetch(self.engines[g], b)
 
         def launch(grp):
             for g, b in enumerate(grp):
-                self.engines[g].submit(b.bits, b.missing)
+                submit_batch(self.engines[g], b)
 
         def run_group(grp):
             list(self._pool.map(self.run, self.engines[:len(grp)]))

@@ -33,11 +33,27 @@ def write_bgzf(path, src, block=65000, level=1):
                 break
 
 
+def _write_part(job):
+    d, i, lo, hi, n, ys = job
+    from oracle import synth
+    names = np.array(['s%d' % k for k in range(n)])
+    tok = np.char.add(names, ':1')
+    f = os.path.join(d, 'part%04d.txt' % i)
+    with open(f, 'w') as fh:
+        for a in range(lo, hi, 2000):
+            x = synth.unpack_rows(synth.synth_rows(7, a, min(2000, hi - a), n, 0.02, 0.98, 1000, ys), n)
+            for s in range(x.shape[0]):
+                fh.write('K%08d | ' % (a + s) + ' '.join(tok[x[s] != 0]) + '\n')
+    subprocess.check_call('gzip -1 -k -c %s > %s.gz' % (f, f), shell=True)
+    write_bgzf(f + '.bgz', f)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--samples', type=int, default=5000)
     ap.add_argument('--kmers', type=int, default=40000)
     ap.add_argument('--cpu', type=int, default=0)
+    ap.add_argument('--part', type=int, default=10000, help='k-mers per generator job')
     a = ap.parse_args()
     import benchdata
     from oracle import synth
@@ -46,12 +62,6 @@ def main():
     cores = a.cpu or len(os.sched_getaffinity(0))
     d = tempfile.mkdtemp(prefix='psb_cli_')
     X, y, K = benchdata.lmm_problem(n)
-    lm = KinshipLMM(X, y.reshape(-1, 1), K)
-    h2 = float(lm.findH2()['h2'])
-    S, U = lm.getSU()
-    lm.close()
-    np.savez(os.path.join(d, 'lmm.npz'), U, S, np.array([h2]))
-    names = np.array(['s%d' % i for i in range(n)])
     with open(os.path.join(d, 'pheno.tsv'), 'w') as fh:
         fh.write('samples\tpheno\n')
         for i in range(n):
@@ -59,16 +69,31 @@ def main():
     ys = np.where(y > np.median(y), 1, -1).astype(np.int8)
     txt = os.path.join(d, 'kmers.txt')
     t0 = time.time()
-    with open(txt, 'w') as fh:
-        for lo in range(0, m, 2000):
-            x = synth.unpack_rows(synth.synth_rows(7, lo, min(2000, m - lo), n, 0.02, 0.98, 1000, ys), n)
-            tok = np.char.add(names, ':1')
-            for s in range(x.shape[0]):
-                fh.write('K%08d | ' % (lo + s) + ' '.join(tok[x[s] != 0]) + '\n')
+    # the text, its gzip and its bgzip image, written in parts on all cores and concatenated (a series
+    # of gzip members is a gzip file, a series of BGZF files a BGZF file)
+    parts = [(d, i, lo, min(lo + a.part, m), n, ys) for i, lo in enumerate(range(0, m, a.part))]
+    import multiprocessing as mp
+    with mp.get_context('fork').Pool(min(cores, len(parts))) as pool:
+        pool.map(_write_part, parts)
+    for ext in ('', '.gz', '.bgz'):
+        with open(txt + ext, 'wb') as fo:
+            for i in range(len(parts)):
+                f = os.path.join(d, 'part%04d.txt%s' % (i, ext))
+                with open(f, 'rb') as fi:
+                    while True:
+                        blk = fi.read(64 << 20)
+                        if not blk:
+                            break
+                        fo.write(blk)
+                os.unlink(f)
     gen_s = time.time() - t0
     size_txt = os.path.getsize(txt)
-    subprocess.check_call('gzip -1 -k -c %s > %s.gz' % (txt, txt), shell=True)
-    write_bgzf(txt + '.bgz', txt)
+    # (the device is touched only after the generator processes were forked)
+    lm = KinshipLMM(X, y.reshape(-1, 1), K)
+    h2 = float(lm.findH2()['h2'])
+    S, U = lm.getSU()
+    lm.close()
+    np.savez(os.path.join(d, 'lmm.npz'), U, S, np.array([h2]))
     base = [sys.executable, '-m', 'pyseer_b200', '--phenotypes', os.path.join(d, 'pheno.tsv'), '--lmm',
             '--load-lmm', os.path.join(d, 'lmm.npz'), '--cpu', str(cores)]
     # set-up time of a run (load the LMM cache, psb_lmm_setup): one-line input
@@ -76,9 +101,9 @@ def main():
     with open(txt) as fi, open(one, 'w') as fo:
         fo.write(fi.readline())
 
-    def run(extra, tag):
+    def run(extra, tag, text='1'):
         t = time.time()
-        env = dict(os.environ, PYSEER_B200_TIMING='1')
+        env = dict(os.environ, PYSEER_B200_TIMING='1', PYSEER_B200_TEXT=text)
         with open(os.devnull, 'w') as null:
             err = subprocess.run(base + extra, stdout=null, stderr=subprocess.PIPE, cwd=ROOT, env=env,
                                  check=True).stderr.decode()
@@ -90,14 +115,19 @@ def main():
     cache = os.path.join(d, 'kmers.bits')
     res = {'n_samples': n, 'kmers': m, 'parser_threads': cores, 'text_bytes': size_txt, 'setup_s': setup_s,
            'generate_text_s': gen_s, 'runs': {}}
-    for tag, extra in (('gzip_text', ['--kmers', txt + '.gz']),
-                       ('bgzip_text', ['--kmers', txt + '.bgz']),
-                       ('plain_text', ['--kmers', txt, '--uncompressed']),
-                       ('gzip_text_writing_bits_cache', ['--kmers', txt + '.gz', '--bits-cache', cache]),
-                       ('bits_cache', ['--kmers', txt + '.gz', '--bits-cache', cache])):
-        w, rate = run(extra, tag)
+    # device parser (psb_submit_text, the default) and host parser (PYSEER_B200_TEXT=0) on each format
+    for tag, extra, text in (('plain_text_device_parser', ['--kmers', txt, '--uncompressed'], '1'),
+                             ('bgzip_text_device_parser', ['--kmers', txt + '.bgz'], '1'),
+                             ('gzip_text_device_parser', ['--kmers', txt + '.gz'], '1'),
+                             ('plain_text_host_parser', ['--kmers', txt, '--uncompressed'], '0'),
+                             ('bgzip_text_host_parser', ['--kmers', txt + '.bgz'], '0'),
+                             ('gzip_text_host_parser', ['--kmers', txt + '.gz'], '0'),
+                             ('gzip_text_writing_bits_cache', ['--kmers', txt + '.gz', '--bits-cache', cache], '0'),
+                             ('bits_cache', ['--kmers', txt + '.gz', '--bits-cache', cache], '0')):
+        w, rate = run(extra, tag, text)
         res['runs'][tag] = {'wall_s': w, 'variants_per_s_whole_run': m / w,
                             'variants_per_s_streaming': rate}
+        sys.stderr.write('%s: %.2f s, streaming %s variants/s\n' % (tag, w, rate))
     print(json.dumps(res))
     for f in os.listdir(d):
         os.unlink(os.path.join(d, f))

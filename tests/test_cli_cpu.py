@@ -35,12 +35,44 @@ class _FakeEngine(object):
 
     def submit(self, bits, missing=None):
         self._sub = (np.array(bits), None if missing is None else np.array(missing))
+        self._info = None
+
+    # the device text parser's contract (psb_submit_text), restated in Python: samples after the first
+    # '|', blank-separated tokens, name up to ':', unknown samples ignored
+    def text_setup(self, samples):
+        self._index = {}
+        for i, x in enumerate(samples):
+            self._index.setdefault(str(x), i)
+        self._n = len(samples)
+
+    def submit_text(self, text, n_bytes, line_start, line_len, n_lines):
+        from pyseer_b200.engine import words_per_row
+        bits = np.zeros((n_lines, words_per_row(self._n)), dtype=np.uint32)
+        info = np.zeros(n_lines, dtype=np.int32)
+        for v in range(n_lines):
+            line = bytes(text[line_start[v]:line_start[v] + line_len[v]]).decode()
+            if '|' not in line:
+                info[v] = 4 | 2
+                continue
+            for tok in line.split('|', 1)[1].replace('\t', ' ').split(' '):
+                i = self._index.get(tok.split(':')[0]) if tok else None
+                if i is not None:
+                    bits[v, i >> 5] |= np.uint32(1 << (i & 31))
+            if not bits[v].any():
+                info[v] |= 2
+        self._sub = (bits, None)
+        self._info = info
+
+    def text_info(self, n_lines):
+        return self._cur_info[:n_lines]
 
     def run_fixed(self, min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous):
+        self._cur_info = self._info
         self._res = _fake_run_fixed_bits(self.fixed_model, self._sub[0], self._sub[1], filter_pvalue,
                                          lrt_pvalue, min_af, max_af, max_missing)
 
     def run_lmm(self, min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous):
+        self._cur_info = self._info
         self._res = _fake_run_lmm_bits(self.lmm, self.h2, self._sub[0], self._sub[1], continuous,
                                        filter_pvalue, lrt_pvalue, min_af, max_af, max_missing)
 
@@ -68,6 +100,23 @@ class _FakePool(object):
         pass
 
 
+class _FakeTextPool(object):
+    """pipeline.TextPool without cudaHostAlloc."""
+
+    def __init__(self, n, rows, text_bytes):
+        self.rows, self.text_bytes = rows, text_bytes
+
+    def get(self):
+        return (np.empty(self.text_bytes, dtype=np.uint8), np.empty(self.rows, dtype=np.int64),
+                np.empty(self.rows, dtype=np.int32), 0)
+
+    def put(self, token):
+        pass
+
+    def close(self):
+        pass
+
+
 def _patch(monkeypatch):
     from pyseer_b200 import model as fx, lmm as lm, pipeline
     monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
@@ -75,6 +124,7 @@ def _patch(monkeypatch):
     monkeypatch.setattr(lm.KinshipLMM, 'close', lambda self: None)
     monkeypatch.setattr(lm.KinshipLMM, 'engine', lambda self, h2: _FakeEngine(lmm=self, h2=h2))
     monkeypatch.setattr(pipeline, 'PinnedPool', _FakePool)
+    monkeypatch.setattr(pipeline, 'TextPool', _FakeTextPool)
 
 
 class _FakeFixedModel(object):

@@ -311,3 +311,49 @@ def test_truncated_cache_is_rejected(tmp_path):
     with open(cut, 'wb') as fh:
         fh.write(data[:len(data) // 2] + b'\0' * 64)
     assert not PackedCache.valid(cut, 'kmers', src, samples, W)
+
+
+def _text_lines(rd, size, block=1, text_cap=None):
+    """(names, lines) of every batch of the text mode, lines as bytes cut out of the text buffer"""
+    out = []
+    for b in rd.text_batches(size, block_size=block, text_cap=text_cap):
+        text, nb, ls, ll = b.text
+        assert b.bits is None and nb <= text.shape[0]
+        lines = [bytes(text[ls[i]:ls[i] + ll[i]]) for i in range(b.n)]
+        assert all(ls[i] + ll[i] <= nb for i in range(b.n))
+        out.append((list(b.names), lines))
+    return out
+
+
+def test_text_mode_cuts_the_same_lines(tmp_path):
+    """psb_reader_next_text (the host half of the device parser): same names, same line order and
+    batch sizes as the row reader, lines trimmed like it does -- for gzip, bgzip-style and plain
+    input, one thread and several, and with a text buffer that forces short batches."""
+    p = _pheno()
+    src = os.path.join(GOLDEN, 'kmers.gz')
+    raw = gzip.open(src, 'rb').read()
+    ref_lines = [l.rstrip(b'\r \t') for l in raw.split(b'\n')]
+    ref_lines = [l for l in ref_lines if l]
+    plain = str(tmp_path / 'k.txt')
+    with open(plain, 'wb') as fh:
+        fh.write(raw.rstrip(b'\n'))                 # last line without a newline
+    crlf = str(tmp_path / 'k_crlf.txt')
+    with open(crlf, 'wb') as fh:
+        fh.write(raw.replace(b'\n', b' \r\n\r\n'))  # trailing blanks, CRLF and empty lines
+    for path in (src, plain, crlf):
+        for threads in (1, 4):
+            rd = VariantReader('kmers', path, p, threads=threads)
+            got = _text_lines(rd, 64)
+            rd.close()
+            assert [len(n) for n, _ in got] == [64, 64, 64, 8]
+            lines = [l for _, ls in got for l in ls]
+            names = [x for n, _ in got for x in n]
+            assert lines == ref_lines
+            assert names == [l.split()[0].decode() for l in ref_lines]
+    # a text buffer that holds a fifth of the file: batches shrink to whole blocks of 8, nothing is lost
+    rd = VariantReader('kmers', plain, p)
+    got = _text_lines(rd, 64, block=8, text_cap=max(len(raw) // 5, 9 * max(len(l) for l in ref_lines)))
+    rd.close()
+    sizes = [len(n) for n, _ in got]
+    assert sum(sizes) == 200 and all(s % 8 == 0 for s in sizes[:-1]) and max(sizes) < 64
+    assert [l for _, ls in got for l in ls] == ref_lines
