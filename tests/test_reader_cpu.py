@@ -357,3 +357,26 @@ def test_text_mode_cuts_the_same_lines(tmp_path):
     sizes = [len(n) for n, _ in got]
     assert sum(sizes) == 200 and all(s % 8 == 0 for s in sizes[:-1]) and max(sizes) < 64
     assert [l for _, ls in got for l in ls] == ref_lines
+
+
+def test_text_mode_threads_on_a_large_file(tmp_path):
+    """Reads and newline scans split over threads (slices of >= 4 MB): same lines as one thread."""
+    rng = np.random.RandomState(3)
+    n = 600
+    samples = ['sample_%04d' % i for i in range(n)]
+    p = pd.Series(rng.uniform(size=n), index=samples)
+    toks = np.array([s + ':1' for s in samples])
+    path = str(tmp_path / 'big.txt')
+    with open(path, 'w') as fh:
+        for v in range(9000):
+            fh.write('K%06d | ' % v + ' '.join(toks[rng.uniform(size=n) < rng.uniform(0.05, 0.95)]) + '\n')
+    assert os.path.getsize(path) > (24 << 20)
+    out = {}
+    for threads in (1, 5):
+        rd = VariantReader('kmers', path, p, threads=threads)
+        out[threads] = _text_lines(rd, 4000, block=100)
+        rd.close()
+    assert [len(a) for a, _ in out[1]] == [4000, 4000, 1000]
+    assert out[1] == out[5]
+    with open(path, 'rb') as fh:
+        assert [l for _, ls in out[5] for l in ls] == [l.rstrip() for l in fh.read().split(b'\n') if l]
