@@ -124,6 +124,13 @@ int psb_eigh(psb_ctx *ctx, int32_t n, const double *A, double *w_out, double *V_
  * pairs d..n-1 and subtracts 1 from the eigenvalues.  1 <= d <= 16. */
 int psb_spectral(psb_ctx *ctx, int32_t n, int32_t d, const double *K, const double *X, const double *Xp,
                  double *w_out, double *V_out);
+/* The O(N) sums of the null-model likelihood LMM.nLLeval(h2) (fastlmm/lmm_cov.py:597-684) that
+ * LMM.findH2's grid + Brent search (lmm_cov.py:427-478, mingrid.py:13-73) evaluates ~30 times:
+ * for each of the n_h2 values, yky_out = sum_j uy2[j] / (h2 S[j] + 1 - h2) and logdet_out =
+ * sum_j log(h2 S[j] + 1 - h2) over the J = N - D spectrum (S: eigenvalues, uy2: squares of the rotated
+ * phenotype U'Py; both host arrays).  Needs no model set-up. */
+int psb_lmm_nll_terms(psb_ctx *ctx, int32_t J, const double *S, const double *uy2, int32_t n_h2,
+                      const double *h2, double *yky_out, double *logdet_out);
 
 /* Fixed-effects state shared by every fixed_effects_regression call (model.py:202-205):
  * Z = [1, m, c] (N x q row-major, column 0 ones; model.py:274-297 minus the variant

@@ -85,7 +85,8 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_comm_info', 'psb_comm_bcast', 'psb_comm_allreduce', 'psb_comm_barrier',
            'psb_comm_gather_begin', 'psb_comm_gather_wait', 'psb_comm_gather_fetch',
            'psb_comm_gather_bytes', 'psb_measure_peaks', 'psb_reader_at_eof', 'psb_spectral',
-           'psb_reader_next_text', 'psb_text_setup', 'psb_submit_text', 'psb_text_info']
+           'psb_reader_next_text', 'psb_text_setup', 'psb_submit_text', 'psb_text_info',
+           'psb_lmm_nll_terms']
 
 
 def load():
@@ -129,6 +130,7 @@ def load():
     lib.psb_text_setup.argtypes = [c_void_p, POINTER(ctypes.c_char_p), c_int32]
     lib.psb_submit_text.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64]
     lib.psb_text_info.argtypes = [c_void_p, c_void_p, c_int64]
+    lib.psb_lmm_nll_terms.argtypes = [c_void_p, c_int32, dp, dp, c_int32, dp, dp, dp]
     lib.psb_hash_patterns.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p,
                                       POINTER(c_int64)]
     lib.psb_reader_vcf_info.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]

@@ -253,3 +253,72 @@ done:
     if (d_A) cudaFree(d_A);
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------
+// The h2 search of LMM.findH2 (fastlmm/lmm_cov.py:427-478 through mingrid.minimize1D,
+// mingrid.py:13-73) evaluates the null-model likelihood nLLeval(h2) (lmm_cov.py:597-684) ~30 times;
+// with the rotated phenotype U'Py fixed, each evaluation is two sums over the J = N - D spectrum:
+//     yKy(h2) = sum_j uy_j^2 / (h2 S_j + 1 - h2),    logdetK(h2) = sum_j log(h2 S_j + 1 - h2).
+// One block per requested h2 (the grid of the search goes in one launch, Brent's points one by
+// one); fixed reduction tree, so the value of a given h2 is reproducible.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_nll_terms(const double *__restrict__ S, const double *__restrict__ uy2, int J,
+            const double *__restrict__ h2, double *__restrict__ out) {
+    __shared__ double red[2][8];
+    const double h = h2[blockIdx.x];
+    double a = 0.0, b = 0.0;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const double sd = h * S[j] + (1.0 - h);
+        a += uy2[j] / sd;
+        b += log(sd);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = a;
+        red[1][threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0.0, tb = 0.0;
+        for (int w = 0; w < 8; ++w) {
+            ta += red[0][w];
+            tb += red[1][w];
+        }
+        out[2 * blockIdx.x] = ta;
+        out[2 * blockIdx.x + 1] = tb;
+    }
+}
+
+extern "C" int psb_lmm_nll_terms(psb_ctx *c, int32_t J, const double *S, const double *uy2, int32_t n_h2,
+                                 const double *h2, double *yky_out, double *logdet_out) {
+    PSB_REQUIRE(c && S && uy2 && h2 && yky_out && logdet_out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(J > 0 && n_h2 > 0 && n_h2 <= 4096, PSB_ERR_ARG, "J = %d, n_h2 = %d out of range", J, n_h2);
+    PSB_CUDA(cudaSetDevice(c->device));
+    double *d = nullptr;
+    const size_t nd = 2 * (size_t)J + 3 * (size_t)n_h2;
+    PSB_CUDA(cudaMalloc(&d, nd * sizeof(double)));
+    double *dS = d, *du = d + J, *dh = d + 2 * (size_t)J, *dout = dh + n_h2;
+    cudaError_t e = cudaMemcpyAsync(dS, S, (size_t)J * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(du, uy2, (size_t)J * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dh, h2, (size_t)n_h2 * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    std::vector<double> out(2 * (size_t)n_h2);
+    if (e == cudaSuccess) {
+        k_nll_terms<<<n_h2, 256, 0, c->stream>>>(dS, du, J, dh, dout);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out.data(), dout, out.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    PSB_CUDA(e);
+    for (int i = 0; i < n_h2; ++i) {
+        yky_out[i] = out[2 * i];
+        logdet_out[i] = out[2 * i + 1];
+    }
+    return PSB_OK;
+}

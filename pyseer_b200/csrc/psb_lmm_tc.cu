@@ -84,6 +84,7 @@ struct TcArgs {
     int pair;                 // launched as clusters of two CTAs: 1 = each CTA issues its own MMAs, the
                               // operand stream is shared through TMA multicast; 2 = two-SM MMAs
                               // (cta_group::2), each CTA holds half of every B stage
+    int skip_box;             // triangular form: skip the all-zero first box of a diagonal stage
     int debug;                // timing experiments only (PSB_TC_DEBUG, results are wrong when set):
                               // 1: one MMA per stage instead of four; 2: expanders store without
                               // expanding; 4: epilogue releases the accumulators without reading them
@@ -280,6 +281,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         // (two-SM mode: CTA 0 issues for the pair, CTA 1's warp only owns its TMEM allocation)
         int st = 0, sta = 0, acc = 0;
         uint32_t ph = 0, phacc = 0;
+        const int jt_first_special = args.jtiles - (args.n_special > 0 ? 1 : 0);
         if (!(two && cta_rank != 0))
         for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x)
             for (int q = 0; q < args.jtiles; ++q) {
@@ -295,22 +297,27 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                         const uint64_t bdesc = make_b_desc(sB0 + st * stage_bytes);
                         const uint32_t a_tmem = tmem_base + (uint32_t)(A_COL0 + sta * A_COLS);
                         const int nkk = (args.debug & 1) ? 2 : 8;
+                        // triangular form: the first stage of a column tile starts at a multiple of 256
+                        // samples; when the tile's first sample lies in its second box, the first box
+                        // (four MMAs) only meets zeros of M'' and is skipped
+                        const int kk0 = (args.skip_box && ks == ks0 && jt < jt_first_special &&
+                                         ((jt * TC_JT) & (TC_KSTAGE - 1)) >= TC_KBOX) ? 4 : 0;
                         if constexpr (two) {
 #pragma unroll
                             for (int kk = 0; kk < 8; ++kk)
-                                if (kk < nkk)
+                                if (kk < nkk && kk >= kk0)
                                     tc_mma_i8_ts_2(d_tmem, a_tmem + kk * 8,
                                                    bdesc + (uint64_t)((kk >> 2) * ((BOX_BYTES / 2) >> 4) + (kk & 3) * 2),
-                                                   IDESC2, (ks != ks0 || kk != 0) ? 1u : 0u);
+                                                   IDESC2, (ks != ks0 || kk != kk0) ? 1u : 0u);
                             tc_commit_2mc(empty0 + st * 8, (uint16_t)3);
                             if (ks == args.nks - 1) tc_commit_2mc(smem_u32(&accFull[acc]), (uint16_t)3);
                         } else {
 #pragma unroll
                             for (int kk = 0; kk < 8; ++kk)
-                                if (kk < nkk)
+                                if (kk < nkk && kk >= kk0)
                                     tc_mma_i8_ts(d_tmem, a_tmem + kk * 8,
                                                  bdesc + (uint64_t)((kk >> 2) * (BOX_BYTES >> 4) + (kk & 3) * 2), IDESC,
-                                                 (ks != ks0 || kk != 0) ? 1u : 0u);
+                                                 (ks != ks0 || kk != kk0) ? 1u : 0u);
                             if (pair) tc_commit_mc(empty0 + st * 8, (uint16_t)3);
                             else tc_commit(empty0 + st * 8);
                             if (ks == args.nks - 1) tc_commit(smem_u32(&accFull[acc]));
@@ -1013,6 +1020,7 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     if (getenv("PSB_TC_PAIR")) a.pair = std::max(0, std::min(2, atoi(getenv("PSB_TC_PAIR"))));
     if (c->sm_count < 2) a.pair = 0;
     a.debug = getenv("PSB_TC_DEBUG") ? atoi(getenv("PSB_TC_DEBUG")) : 0;
+    a.skip_box = (a.tri && !(getenv("PSB_TC_SKIP") && atoi(getenv("PSB_TC_SKIP")) == 0)) ? 1 : 0;
     const int na = (512 - 2 * TC_JT * nsl) / (TC_KSTAGE / 4);   // TMEM A-ring depth (kernel: NA)
     // Operand ring depth: as many stages as shared memory holds, at most TC_MAX_BSTAGES.  The
     // tile's packed rows share shared memory with the ring; they stay there as long as the ring

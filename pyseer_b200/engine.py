@@ -158,6 +158,17 @@ class Engine(object):
         return w, V
 
     # -- kinship ------------------------------------------------------------------------
+    def nll_terms(self, S, uy2, h2):
+        """(yKy, logdetK) of LMM.nLLeval at each h2 (``psb_lmm_nll_terms``)."""
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        uy2 = np.ascontiguousarray(uy2, dtype=np.float64)
+        h2 = np.ascontiguousarray(np.atleast_1d(h2), dtype=np.float64)
+        yky = np.empty(h2.shape[0])
+        ld = np.empty(h2.shape[0])
+        check(self.lib.psb_lmm_nll_terms(self._ctx, S.shape[0], self._dptr(S), self._dptr(uy2), h2.shape[0],
+                                         self._dptr(h2), self._dptr(yky), self._dptr(ld)))
+        return yky, ld
+
     def kinship_begin(self, n_samples):
         check(self.lib.psb_kinship_begin(self._ctx, int(n_samples)))
         self._kin_n = int(n_samples)

@@ -1,8 +1,10 @@
 """LMM front-end with the reference's interface (pyseer/lmm.py).
 
-``initialise_lmm`` does the once-per-run set-up (kinship normalisation, projection, h2 search on
-the host; the O(N^3) eigendecomposition on the device for N >= 2048, ``psb_eigh``: lmm.py:26-122,
-fastlmm/lmm_cov.py:88-103, 427-478);
+``initialise_lmm`` does the once-per-run set-up (lmm.py:26-122): kinship normalisation on the host;
+for N >= 2048 the projection and O(N^3) eigendecomposition of setSU_fromK (``psb_spectral``,
+fastlmm/lmm_cov.py:88-103) and the O(N) sums of every likelihood evaluation of the h2 search
+(``psb_lmm_nll_terms``, lmm_cov.py:427-478, 597-684) on the device, the grid / Brent logic of
+mingrid.minimize1D around them on the host;
 ``fit_lmm`` / ``fit_lmm_block`` keep the reference's signatures and error behaviour but
 hand every per-variant computation to the GPU engine.
 """
@@ -31,6 +33,8 @@ class KinshipLMM(object):
         self.U = None
         self.S = None
         self._UY = None
+        self._uy2 = None
+        self._nll_grid = None
         self._Xdagger = None
         self.device = device
         self.precision = precision
@@ -103,17 +107,41 @@ class KinshipLMM(object):
             self._UY = U.T.dot(A)
         return self._UY
 
+    def _device_h2(self):
+        """The O(N) sums of nLLeval on the device (``psb_lmm_nll_terms``) under the same rule as the
+        eigendecomposition: N >= 2048 unless PYSEER_B200_EIGH says otherwise; one phenotype column."""
+        mode = os.environ.get('PYSEER_B200_EIGH', 'auto')
+        return self.Y.shape[1] == 1 and mode != 'numpy' and \
+            (mode == 'device' or self.Y.shape[0] >= 2048)
+
+    def _nll_terms(self, h2s):
+        """(YKY [n, P], logdetK [n]) of nLLeval at the given h2 values."""
+        S, U = self.getSU()
+        UY = self._getUY()
+        h2s = np.atleast_1d(np.asarray(h2s, dtype=float))
+        if self._device_h2():
+            if self._engine is None:
+                self._engine = Engine(self.device)
+            if self._uy2 is None:
+                self._uy2 = np.ascontiguousarray(UY[:, 0] ** 2)
+            yky, ld = self._engine.nll_terms(S, self._uy2, h2s)
+            return yky.reshape(-1, 1), ld
+        with np.errstate(all='ignore'):
+            Sd = h2s.reshape(-1, 1) * S.reshape(1, -1) + (1.0 - h2s.reshape(-1, 1))
+            YKY = np.stack([(UY / sd.reshape(-1, 1) * UY).sum(0) for sd in Sd])
+            return YKY, np.log(Sd).sum(1)
+
     def nLLeval(self, h2=0.0):
         """Null-model negative log-likelihood at h2 (lmm_cov.py:597-684, 726-727, 817-825)."""
         N = self.Y.shape[0] - self.D
-        S, U = self.getSU()
         if h2 < 0.0 or h2 >= 1.0:
             return {'nLL': 3e20, 'h2': h2, 'scale': 1.0}
-        Sd = h2 * S + (1.0 - h2)
-        UY = self._getUY()
+        terms = self._nll_grid.pop(float(h2), None) if self._nll_grid else None
+        if terms is None:
+            YKY, logdetK = self._nll_terms([h2])
+            terms = (YKY[0], logdetK[0])
+        YKY, logdetK = terms
         with np.errstate(all='ignore'):
-            YKY = (UY / Sd.reshape(-1, 1) * UY).sum(0)
-            logdetK = np.log(Sd).sum()
             sigma2 = YKY / N
             nLL = 0.5 * (logdetK + N * (np.log(2.0 * np.pi * sigma2) + 1))
         return {'nLL': nLL, 'h2': h2, 'scale': 1.0, 'dof': None}
@@ -131,7 +159,13 @@ class KinshipLMM(object):
 
         step = (maxH2 - minH2) / nGridH2
         grid = np.arange(minH2, maxH2 + step, step)
+        # the grid of the search in one device launch (Brent's points follow one by one)
+        inside = [float(x) for x in grid if 0.0 <= x < 1.0]
+        if inside and self._device_h2():
+            YKY, ld = self._nll_terms(inside)
+            self._nll_grid = {x: (YKY[i], ld[i]) for i, x in enumerate(inside)}
         vals = np.array([f(x) for x in grid])
+        self._nll_grid = None
         if vals[0] < vals[1]:
             opt.fminbound(f, grid[0], grid[1], full_output=True)
         if vals[-1] < vals[-2]:

@@ -47,3 +47,19 @@ def test_lmm_statistics_do_not_depend_on_the_eigensolver(monkeypatch):
     assert abs(out['numpy'][0] - out['device'][0]) < 1e-6
     for key in ('p_values', 'beta', 'bse', 'frac_h2'):
         assert np.allclose(out['numpy'][1][key], out['device'][1][key], rtol=1e-9, atol=0), key
+
+
+def test_nll_terms_match_numpy():
+    """psb_lmm_nll_terms: the two O(N) sums of LMM.nLLeval (lmm_cov.py:597-684) for a grid of h2"""
+    from pyseer_b200.engine import Engine
+    rng = np.random.RandomState(5)
+    for J in (7, 999, 4999):
+        S = np.sort(rng.gamma(0.7, 2.0, size=J))
+        S[:3] = [0.0, 1e-12, 1e-7]                    # null directions of a clonal kinship
+        uy2 = rng.normal(size=J) ** 2
+        h2 = np.concatenate([[0.0, 0.99999], rng.uniform(size=9)])
+        with Engine(0) as eng:
+            yky, ld = eng.nll_terms(S, uy2, h2)
+        Sd = h2[:, None] * S[None, :] + (1.0 - h2[:, None])
+        assert np.allclose(yky, (uy2[None, :] / Sd).sum(1), rtol=1e-13, atol=0)
+        assert np.allclose(ld, np.log(Sd).sum(1), rtol=1e-12, atol=1e-10)
