@@ -222,7 +222,7 @@ def reference_arm(a):
             'config': config_of(model, n, kpg, max(a.gpus, 1)), 'cpu_baseline': cpu,
             'e2e': {'value': rate, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0, 'setup_s': setup_s}
-    print(json.dumps(line))
+    _emit(line)
     return 0
 
 
@@ -757,8 +757,32 @@ def gpu_line(a, model, n, kpg, rank, local_rank, world, comm, eng, steps, warmup
     return line
 
 
+def _emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = json.dumps(line) + '\n'
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, out.encode())
+    else:
+        sys.stdout.write(out)
+        sys.stdout.flush()
+
+
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Libraries below us write to file descriptor 1 (NCCL prints its version banner there when the
+    box sets NCCL_DEBUG): everything but the JSON line goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
 def main(argv=None):
     a = parse_args(argv)
+    _guard_stdout()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -791,7 +815,7 @@ def main(argv=None):
                 sec.append({'config': config_of(model, *workload_spec(model, 0, kp), 1), 'error': repr(exc)})
         line['secondary'] = sec
     if rank == 0:
-        print(json.dumps(line))
+        _emit(line)
     return 0
 
 

@@ -404,6 +404,129 @@ k_bitstats_v(const uint32_t *__restrict__ bits, int64_t S, int Wrow, int Wn,
     }
 }
 
+// ---------------------------------------------------------------------------------
+// The same pass as a streaming kernel: tiles of whole rows come in through the bulk-copy engine
+// (cp.async.bulk on an mbarrier, two tiles per CTA: one lands while the other is counted); four
+// threads share a row of the tile and walk it in 16-byte cells of shared memory, so the loads in
+// flight do not depend on how many warps are resident and the only cross-lane traffic is two
+// shuffle steps per row.  Thread (row r, part p) visits cells (4 i + p + rot_r) mod Wq with rot_r
+// chosen so that the 32 lanes of a warp (8 rows x 4 parts) spread evenly over the eight 16-byte bank
+// groups for any row width.  MODE 0: no 0/1 phenotype classes (continuous phenotype: carriers only,
+// one popcount per word); 1: every valid sample is a case or a control (carriers = n11 + n01, two
+// popcounts); 2: general (three).
+// ---------------------------------------------------------------------------------
+#define BSS_THREADS 512
+
+__device__ __forceinline__ uint32_t bss_smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void bss_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(BSS_THREADS)
+k_bitstats_stream(const uint32_t *__restrict__ bits, int64_t S, int Wrow, int Wn, int tile_rows,
+                  const uint32_t *__restrict__ y1, const uint32_t *__restrict__ y0,
+                  const uint32_t *__restrict__ valid, int n_y1, int n_y0,
+                  int32_t *__restrict__ carriers, int32_t *__restrict__ nmissing, int32_t *__restrict__ tab) {
+    extern __shared__ __align__(128) unsigned char bss_smem[];
+    const int Wq = Wrow >> 2;
+    const size_t tile_cells = (size_t)tile_rows * Wq;
+    uint4 *sTile = reinterpret_cast<uint4 *>(bss_smem);                          // two tiles
+    uint4 *sV = sTile + 2 * tile_cells;                                          // valid | y1 | y0
+    uint64_t *mb = reinterpret_cast<uint64_t *>(sV + 3 * (size_t)Wq);
+    {
+        uint32_t *w = reinterpret_cast<uint32_t *>(sV);
+        for (int e = threadIdx.x; e < Wrow; e += blockDim.x) {
+            const bool in = e < Wn;
+            w[e] = in ? valid[e] : 0u;
+            w[Wrow + e] = in ? y1[e] : 0u;
+            w[2 * Wrow + e] = in ? y0[e] : 0u;
+        }
+        if (threadIdx.x == 0) {
+            for (int b = 0; b < 2; ++b)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bss_smem_u32(&mb[b])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    const uint4 *s1 = sV + Wq, *s0 = sV + 2 * Wq;
+    const int64_t n_tiles = (S + tile_rows - 1) / tile_rows;
+    auto post = [&](int64_t tile, int buf) {          // one thread: bulk copy of a tile
+        const int64_t r0 = tile * tile_rows;
+        const uint32_t bytes = (uint32_t)(min((int64_t)tile_rows, S - r0) * Wrow * 4);
+        const uint32_t bar = bss_smem_u32(&mb[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         bss_smem_u32(sTile + (size_t)buf * tile_cells)),
+                     "l"(bits + (size_t)r0 * Wrow), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    int64_t tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        if (tile < n_tiles) post(tile, 0);
+        if (tile + gridDim.x < n_tiles) post(tile + gridDim.x, 1);
+    }
+    const int part = threadIdx.x & 3;
+    uint32_t phase = 0;
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        bss_wait(bss_smem_u32(&mb[buf]), (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        const int64_t r0 = tile * tile_rows;
+        const int rows = (int)min((int64_t)tile_rows, S - r0);
+        const uint4 *tbase = sTile + (size_t)buf * tile_cells;
+        for (int rb = 0; rb < rows; rb += BSS_THREADS / 4) {
+            const int r = rb + (threadIdx.x >> 2);
+            const bool live = r < rows;
+            const uint4 *row = tbase + (size_t)(live ? r : 0) * Wq;
+            int c_all = 0, n11 = 0, n01 = 0;
+            if (live) {
+                // (r Wq + rot) mod 8 alternates between 0 and 4 from row to row
+                int c = (part + ((4 * (r & 1) - r * Wq) & 7)) % Wq;
+                for (int k = part; k < Wq; k += 4) {
+                    const uint4 x = row[c];
+                    const uint4 vb = sV[c];
+                    const uint32_t xa = x.x & vb.x, xb = x.y & vb.y, xc = x.z & vb.z, xd = x.w & vb.w;
+                    if (MODE != 1) c_all += __popc(xa) + __popc(xb) + __popc(xc) + __popc(xd);
+                    if (MODE != 0) {
+                        const uint4 a1 = s1[c], a0 = s0[c];
+                        n11 += __popc(xa & a1.x) + __popc(xb & a1.y) + __popc(xc & a1.z) + __popc(xd & a1.w);
+                        n01 += __popc(xa & a0.x) + __popc(xb & a0.y) + __popc(xc & a0.z) + __popc(xd & a0.w);
+                    }
+                    c += 4;
+                    while (c >= Wq) c -= Wq;
+                }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                if (MODE != 1) c_all += __shfl_xor_sync(0xffffffffu, c_all, o);
+                if (MODE != 0) {
+                    n11 += __shfl_xor_sync(0xffffffffu, n11, o);
+                    n01 += __shfl_xor_sync(0xffffffffu, n01, o);
+                }
+            }
+            if (MODE == 1) c_all = n11 + n01;
+            if (live && part == 0) {
+                const int64_t v = r0 + r;
+                carriers[v] = c_all;
+                nmissing[v] = 0;
+                *reinterpret_cast<int4 *>(tab + v * 4) = make_int4(n11, n_y1 - n11, n01, n_y0 - n01);
+            }
+        }
+        __syncthreads();                              // every thread has left the tile: refill it
+        if (threadIdx.x == 0 && tile + 2 * (int64_t)gridDim.x < n_tiles) post(tile + 2 * (int64_t)gridDim.x, buf);
+    }
+}
+
 int psb_upload_welch_T(psb_ctx *c, const double *yc, const double *yc2) {
     const int Wn = c->Wn, N = c->N;
     std::vector<double> t((size_t)32 * Wn * 2, 0.0);
@@ -441,6 +564,24 @@ int psb_launch_bitstats(psb_ctx *c, int continuous) {
         k_bitstats<2><<<(int)blocks, 256, smem, c->stream>>>(
             c->d_bits, c->S, c->Wrow, c->Wn, c->d_y1bits, c->d_y0bits, c->d_valid, ct, c->welch_T1,
             c->welch_T2, c->n_y1, c->n_y0, c->C, c->col_w0, c->d_carriers, c->d_missing, c->d_tab, c->d_sums);
+    } else if ((size_t)c->Wrow * 4 <= 16 * 1024 && !(getenv("PSB_BITSTATS_STREAM") && atoi(getenv("PSB_BITSTATS_STREAM")) == 0)) {
+        // popcounts only, streamed through shared memory by the bulk-copy engine
+        const size_t row_bytes = (size_t)c->Wrow * 4;
+        int tile_rows = (int)std::min<size_t>(512, (80 * 1024) / row_bytes);
+        tile_rows = std::max(tile_rows, 1);
+        const size_t sm = 2 * (size_t)tile_rows * row_bytes + (size_t)c->Wrow * 12 + 16;
+        const int64_t n_tiles = (c->S + tile_rows - 1) / tile_rows;
+        const int nb = (int)std::min<int64_t>(n_tiles, c->sm_count);
+        const int mode = (c->n_y1 == 0 && c->n_y0 == 0) ? 0 : (c->n_y1 + c->n_y0 == c->N ? 1 : 2);
+#define BSS_LAUNCH(M)                                                                                          \
+        PSB_CUDA(cudaFuncSetAttribute(k_bitstats_stream<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        k_bitstats_stream<M><<<nb, BSS_THREADS, sm, c->stream>>>(c->d_bits, c->S, c->Wrow, c->Wn, tile_rows,    \
+                                                                c->d_y1bits, c->d_y0bits, c->d_valid, c->n_y1, \
+                                                                c->n_y0, c->d_carriers, c->d_missing, c->d_tab)
+        if (mode == 0) { BSS_LAUNCH(0); }
+        else if (mode == 1) { BSS_LAUNCH(1); }
+        else { BSS_LAUNCH(2); }
+#undef BSS_LAUNCH
     } else if (c->N < (1 << 21) && (size_t)c->Wrow * 12 <= 48 * 1024 &&
                !(getenv("PSB_BITSTATS_V") && atoi(getenv("PSB_BITSTATS_V")) == 0)) {
         // popcounts only: 16-byte loads, G lanes per row

@@ -315,3 +315,44 @@ def test_null_fit_powell_fallback():
     assert o is not None and r is not None
     assert abs(r.llf - o.llf) < 1e-9 * abs(o.llf) and np.allclose(r.params, o.params, rtol=1e-9, atol=1e-12)
     assert abs(r.llf - fo.fit_null(y, m, NONE, False).llf) < 1e-4
+
+
+@pytest.mark.parametrize('n', [100, 130, 1000, 4999, 10000])
+@pytest.mark.parametrize('pheno', ['binary', 'continuous', 'mixed'])
+def test_popcount_pass_variants_agree(monkeypatch, n, pheno):
+    """carriers / af / pre-filter (2x2 table) from the three popcount kernels -- bulk-copy streaming
+    (default), 16-byte loads with the transposing butterfly, and the scalar one -- are identical and
+    equal NumPy's counts; phenotype classes: all 0/1 (table from two popcounts), none (carriers only),
+    some (general)."""
+    from pyseer_b200.engine import Engine, synth_host, unpack_rows
+    rng = np.random.RandomState(n)
+    if pheno == 'binary':
+        y = (rng.uniform(size=n) < 0.4).astype(float)
+    elif pheno == 'continuous':
+        y = rng.normal(size=n)
+    else:
+        y = rng.normal(size=n)
+        y[::3] = 1.0
+        y[1::7] = 0.0
+    nv = 777
+    bits = synth_host(5, 0, nv, n, af_lo=0.0, af_hi=1.0)
+    x = unpack_rows(bits, n)
+    out = {}
+    for tag, env in (('stream', {}), ('vector', {'PSB_BITSTATS_STREAM': '0'}),
+                     ('scalar', {'PSB_BITSTATS_STREAM': '0', 'PSB_BITSTATS_V': '0'})):
+        for k in ('PSB_BITSTATS_STREAM', 'PSB_BITSTATS_V'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with Engine(0) as eng:
+            # binary model whatever the phenotype: the popcount-only pass is the binary path's, and a
+            # pre-filter threshold nothing passes keeps the (meaningless) fits from running
+            eng.fixed_setup(np.ones((n, 1)), y, False, 0.0, 0.0)
+            eng.submit(bits)
+            eng.run_fixed(min_af=0.0, max_af=1.0, filter_pvalue=1e-300, continuous=False)
+            r = eng.fetch()
+        out[tag] = (r.carriers.copy(), r.af.copy(), r.prep.copy(), r.flags.copy())
+    assert np.array_equal(out['stream'][0], x.sum(1))
+    for tag in ('vector', 'scalar'):
+        for a, b in zip(out['stream'], out[tag]):
+            assert np.array_equal(a, b, equal_nan=True), tag
