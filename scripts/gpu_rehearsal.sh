@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-end rehearsal on one GPU: the whole -m gpu suite, smoke, default bench, reference arm
+# round-end rehearsal (what the driver runs) on one GPU: the whole -m gpu suite, smoke, default bench, reference arm
 cd "$GRAFT_REPO_ROOT" || exit 1
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2t_tests.log 2>&1
 echo "exit $?" >> gpurun_out/r2t_tests.log; tail -5 gpurun_out/r2t_tests.log | cut -c1-300
