@@ -74,7 +74,7 @@ def parse_args(argv=None):
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-secondary', action='store_true')
-    ap.add_argument('--e2e-chunks', type=int, default=16,
+    ap.add_argument('--e2e-chunks', type=int, default=0,
                     help='batches per e2e step (copy of batch i+1 overlaps the kernels of batch i)')
     ap.add_argument('--cpu-cores', type=int, default=0, help='0 = all available (max 64)')
     ap.add_argument('--check', type=int, default=2000,
@@ -688,20 +688,36 @@ def gpu_line(a, model, n, kpg, rank, local_rank, world, comm, eng, steps, warmup
             # One step = the whole shard through the public calls a user makes, in `chunks`
             # batches: psb_submit copies batch i+1 (copy stream, second staging slot) while the
             # kernels of batch i run; psb_fetch of batch i then brings its rows of the table back.
-            chunks = max(1, a.e2e_chunks)
-            bounds = [(kpg * i // chunks, kpg * (i + 1) // chunks) for i in range(chunks)]
+            chunks = max(1, a.e2e_chunks or {'lmm': 8, 'lmm-binary': 4, 'fixed': 6, 'fixed-cont': 8}.get(model, 8))
+            # a short first batch (its copy is the only one nothing hides) and a short last one (so is
+            # its table's way back); the batches between them are large, which keeps the partial last
+            # wave of every tensor-kernel launch and the per-launch costs small
+            if chunks >= 4:
+                edge = max(256, (kpg // (4 * chunks)) // 256 * 256)
+                mid = [edge + (kpg - 2 * edge) * i // (chunks - 2) for i in range(chunks - 1)]
+                cuts = [0] + mid + [kpg]
+            else:
+                cuts = [kpg * i // chunks for i in range(chunks + 1)]
+            bounds = [(cuts[i], cuts[i + 1]) for i in range(chunks)]
             h2d = int(kpg * W * 4)
 
             def e2e_step():
+                # submit(i+1) on the copy stream, the table of batch i on the fetch stream
+                # (psb_fetch_begin) and the kernels of batch i+1 all overlap; every table has landed
+                # on the host before the step ends (psb_fetch_wait)
                 lo, hi = bounds[0]
                 eng.submit(pin.array[lo:hi])
                 wl.run(eng)
                 for i in range(1, chunks):
                     nlo, nhi = bounds[i]
                     eng.submit(pin.array[nlo:nhi])
-                    eng.fetch_into(ptrs_at(lo))
+                    if i > 1:
+                        eng.fetch_wait()
+                    eng.fetch_begin(ptrs_at(lo))
                     wl.run(eng)
                     lo, hi = nlo, nhi
+                if chunks > 1:
+                    eng.fetch_wait()
                 eng.fetch_into(ptrs_at(lo))
 
         e2e_step()

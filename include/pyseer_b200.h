@@ -209,6 +209,14 @@ int psb_fetch_lineage(psb_ctx *ctx, int32_t *out);
  * destination pointers may be host memory (pinned or pageable) or device memory (e.g. a
  * buffer that is then gathered across ranks with NCCL). */
 int psb_fetch(psb_ctx *ctx, const psb_results *out);
+/* Asynchronous form: psb_fetch_begin queues the copies of the last run's table on the library's fetch
+ * stream and returns; the next psb_run_* (which writes a second set of result columns) may be queued
+ * at once, so the device does not idle while a table travels to the host -- the result loop of
+ * __main__.py:547-568 overlapped with the next block's fits.  psb_fetch_wait blocks until the copies of
+ * the last psb_fetch_begin have landed; counts_out (nullable) = that run's psb_counts.  `out` and the
+ * buffers it names must stay valid until then. */
+int psb_fetch_begin(psb_ctx *ctx, const psb_results *out);
+int psb_fetch_wait(psb_ctx *ctx, int64_t counts_out[4]);
 /* Device pointers of the result table of the last run (valid until the next run);
  * lets the caller gather tables across ranks with NCCL without a host round trip. */
 int psb_results_device(psb_ctx *ctx, psb_results *out_device_ptrs);

@@ -268,12 +268,10 @@ def main(argv=None):
     def emit(batch, r):
         """Result loop of main() (__main__.py:547-568, 783-803) for one batch."""
         flags = r.flags
-        if batch.info is not None:
-            # batch parsed on the device: what the host reader reports while it reads
-            if (batch.info & 4).any():
-                raise ValueError("k-mer line without '|' separator: " +
-                                 batch.names[int(np.nonzero(batch.info & 4)[0][0])])
-            for i in np.nonzero(batch.info & 2)[0]:
+        if batch.text is not None:
+            # batch parsed on the device: what the host reader reports while it reads (a k-mer row has
+            # no missing genotypes, so "no observation" is carriers == 0)
+            for i in np.nonzero(r.carriers[:batch.n] == 0)[0]:
                 sys.stderr.write('No observations of ' + batch.names[i] + ' in selected samples\n')
         if batch.skipped is not None and batch.skipped.any():
             # records the reference never hands to a model (k is None, input.py:603-611)

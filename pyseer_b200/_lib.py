@@ -86,7 +86,7 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_comm_gather_begin', 'psb_comm_gather_wait', 'psb_comm_gather_fetch',
            'psb_comm_gather_bytes', 'psb_measure_peaks', 'psb_reader_at_eof', 'psb_spectral',
            'psb_reader_next_text', 'psb_text_setup', 'psb_submit_text', 'psb_text_info',
-           'psb_lmm_nll_terms']
+           'psb_lmm_nll_terms', 'psb_fetch_begin', 'psb_fetch_wait']
 
 
 def load():
@@ -140,6 +140,8 @@ def load():
     lib.psb_run_lmm.argtypes = [c_void_p, POINTER(PsbParams)]
     lib.psb_run_fixed.argtypes = [c_void_p, POINTER(PsbParams)]
     lib.psb_fetch.argtypes = [c_void_p, POINTER(PsbResults)]
+    lib.psb_fetch_begin.argtypes = [c_void_p, POINTER(PsbResults)]
+    lib.psb_fetch_wait.argtypes = [c_void_p, POINTER(c_int64)]
     lib.psb_results_device.argtypes = [c_void_p, POINTER(PsbResults)]
     lib.psb_counts.argtypes = [c_void_p, POINTER(c_int64)]
     lib.psb_last_ms.argtypes = [c_void_p, c_int32, POINTER(c_float)]

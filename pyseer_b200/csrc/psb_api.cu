@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "psb_internal.cuh"
+#include <utility>
 #include "psb_math.cuh"
 #include "psb_fixed.cuh"
 
@@ -62,6 +63,14 @@ int psb_create(int device_id, psb_ctx **out) {
     PSB_CUDA(cudaEventCreate(&c->ev_k1));
     for (int i = 0; i < 8; ++i) PSB_CUDA(cudaEventCreate(&c->ev_user[i]));
     PSB_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
+    PSB_CUDA(cudaMalloc(&c->alt_counters, 8 * sizeof(int)));
+    PSB_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(int)));
+    PSB_CUDA(cudaMemset(c->alt_counters, 0, 8 * sizeof(int)));
+    PSB_CUDA(cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        PSB_CUDA(cudaEventCreateWithFlags(&c->ev_fetch[i], cudaEventDisableTiming));
+        PSB_CUDA(cudaHostAlloc((void **)&c->h_counters[i], 8 * sizeof(int), cudaHostAllocDefault));
+    }
     *out = c;
     return PSB_OK;
 }
@@ -101,6 +110,13 @@ static void free_tables(psb_ctx *c) {
     free_dev(c->d_pvalue); free_dev(c->d_beta); free_dev(c->d_bse); free_dev(c->d_extra);
     free_dev(c->d_betas); free_dev(c->d_flags); free_dev(c->d_tab); free_dev(c->d_idx);
     free_dev(c->d_idx2); free_dev(c->d_idx3); free_dev(c->d_a); free_dev(c->d_b); free_dev(c->d_pp); free_dev(c->d_lineage);
+    free_dev(c->alt_carriers); free_dev(c->alt_missing); free_dev(c->alt_af); free_dev(c->alt_prep);
+    free_dev(c->alt_pvalue); free_dev(c->alt_beta); free_dev(c->alt_bse); free_dev(c->alt_extra);
+    free_dev(c->alt_betas); free_dev(c->alt_flags);
+    c->alt_carriers = c->alt_missing = nullptr;
+    c->alt_af = c->alt_prep = c->alt_pvalue = c->alt_beta = c->alt_bse = c->alt_extra = c->alt_betas = nullptr;
+    c->alt_flags = nullptr;
+    c->fetch_valid[0] = c->fetch_valid[1] = false;
     c->d_carriers = c->d_missing = nullptr;
     c->d_af = c->d_prep = c->d_pvalue = c->d_beta = c->d_bse = c->d_extra = c->d_betas = nullptr;
     c->d_flags = nullptr; c->d_tab = nullptr; c->d_idx = c->d_idx2 = c->d_idx3 = nullptr; c->d_a = c->d_b = c->d_pp = nullptr; c->d_lineage = nullptr;
@@ -113,6 +129,7 @@ int psb_destroy(psb_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->fetch_stream);
     psb_kinship_release(c);
     psb_burden_release(c);
     psb_text_release(c);
@@ -124,6 +141,12 @@ int psb_destroy(psb_ctx *c) {
     }
     cudaStreamDestroy(c->copy_stream);
     free_dev(c->own_bits); free_dev(c->own_miss); free_dev(c->d_counters); free_dev(c->d_gen_scratch);
+    free_dev(c->alt_counters);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(c->ev_fetch[i]);
+        if (c->h_counters[i]) cudaFreeHost(c->h_counters[i]);
+    }
+    cudaStreamDestroy(c->fetch_stream);
     cudaEventDestroy(c->ev_run0); cudaEventDestroy(c->ev_run1);
     cudaEventDestroy(c->ev_k0); cudaEventDestroy(c->ev_k1);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev_user[i]);
@@ -169,9 +192,32 @@ int psb_run_end(psb_ctx *c) {
     return PSB_OK;
 }
 
+// psb_run_lmm / psb_run_fixed write the OTHER set of result columns than the run before them; a
+// psb_fetch_begin that is still draining that set (two runs back) is waited for on the device.
+int psb_table_flip(psb_ctx *c) {
+    std::swap(c->d_carriers, c->alt_carriers);
+    std::swap(c->d_missing, c->alt_missing);
+    std::swap(c->d_af, c->alt_af);
+    std::swap(c->d_prep, c->alt_prep);
+    std::swap(c->d_pvalue, c->alt_pvalue);
+    std::swap(c->d_beta, c->alt_beta);
+    std::swap(c->d_bse, c->alt_bse);
+    std::swap(c->d_extra, c->alt_extra);
+    std::swap(c->d_betas, c->alt_betas);
+    std::swap(c->d_flags, c->alt_flags);
+    std::swap(c->d_counters, c->alt_counters);
+    c->tab_cur ^= 1;
+    if (c->fetch_valid[c->tab_cur]) {
+        PSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_fetch[c->tab_cur], 0));
+        c->fetch_valid[c->tab_cur] = false;
+    }
+    return PSB_OK;
+}
+
 int psb_ensure_capacity(psb_ctx *c, int64_t S, int betas_cols) {
     if (S > c->cap || betas_cols > c->betas_cols) {
         PSB_CUDA(cudaStreamSynchronize(c->stream));
+        PSB_CUDA(cudaStreamSynchronize(c->fetch_stream));
         free_tables(c);
         int64_t cap = S < 1024 ? 1024 : S;
         PSB_CUDA(cudaMalloc(&c->d_carriers, cap * sizeof(int32_t)));
@@ -185,6 +231,17 @@ int psb_ensure_capacity(psb_ctx *c, int64_t S, int betas_cols) {
         if (betas_cols > 0)
             PSB_CUDA(cudaMalloc(&c->d_betas, cap * betas_cols * sizeof(double)));
         PSB_CUDA(cudaMalloc(&c->d_flags, cap * sizeof(uint32_t)));
+        PSB_CUDA(cudaMalloc(&c->alt_carriers, cap * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->alt_missing, cap * sizeof(int32_t)));
+        PSB_CUDA(cudaMalloc(&c->alt_af, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->alt_prep, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->alt_pvalue, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->alt_beta, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->alt_bse, cap * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->alt_extra, cap * sizeof(double)));
+        if (betas_cols > 0)
+            PSB_CUDA(cudaMalloc(&c->alt_betas, cap * betas_cols * sizeof(double)));
+        PSB_CUDA(cudaMalloc(&c->alt_flags, cap * sizeof(uint32_t)));
         PSB_CUDA(cudaMalloc(&c->d_tab, cap * 4 * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_idx, (cap + 256) * sizeof(int32_t)));
         PSB_CUDA(cudaMalloc(&c->d_idx2, (cap + 256) * sizeof(int32_t)));
@@ -264,6 +321,59 @@ int psb_submit(psb_ctx *c, const uint32_t *bits, const uint32_t *missing, int64_
     c->sub_Wrow = words_per_row;
     c->sub_slot = slot;
     c->sub_valid = true;
+    return PSB_OK;
+}
+
+// Asynchronous psb_fetch: queues the copies of the current table (the last psb_run_*) on the
+// library's fetch stream, behind the run's last kernel, and returns.  The next psb_run_* writes the
+// other set of columns, so it may be queued right away -- the device never idles while a table
+// travels.  psb_fetch_wait blocks until the copies of the last psb_fetch_begin have landed and
+// returns that run's counters (as psb_counts).  `out` must stay valid until then.
+int psb_fetch_begin(psb_ctx *c, const psb_results *out) {
+    PSB_NVTX("psb_fetch_begin");
+    PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
+    PSB_REQUIRE(c->ran && c->have_run_ev, PSB_ERR_STATE, "psb_fetch_begin before psb_run_*");
+    PSB_CUDA(cudaSetDevice(c->device));
+    const int64_t S = c->S;
+    cudaStream_t st = c->fetch_stream;
+    PSB_CUDA(cudaStreamWaitEvent(st, c->ev_run1, 0));
+#define CP(field, src, type)                                                                 \
+    if (out->field && S > 0)                                                                 \
+        PSB_CUDA(cudaMemcpyAsync(out->field, src, S * sizeof(type), cudaMemcpyDefault, st));
+    CP(carriers, c->d_carriers, int32_t)
+    CP(missing, c->d_missing, int32_t)
+    CP(af, c->d_af, double)
+    CP(prep, c->d_prep, double)
+    CP(pvalue, c->d_pvalue, double)
+    CP(beta, c->d_beta, double)
+    CP(bse, c->d_bse, double)
+    CP(extra, c->d_extra, double)
+    CP(flags, c->d_flags, uint32_t)
+#undef CP
+    if (out->betas && S > 0 && c->model == PSB_MODEL_FIXED && c->q > 1)
+        PSB_CUDA(cudaMemcpyAsync(out->betas, c->d_betas, S * (c->q - 1) * sizeof(double),
+                                 cudaMemcpyDefault, st));
+    PSB_CUDA(cudaMemcpyAsync(c->h_counters[c->tab_cur], c->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaEventRecord(c->ev_fetch[c->tab_cur], st));
+    c->fetch_valid[c->tab_cur] = true;
+    c->fetch_set = c->tab_cur;
+    c->fetch_S[c->tab_cur] = S;
+    return PSB_OK;
+}
+
+int psb_fetch_wait(psb_ctx *c, int64_t counts_out[4]) {
+    PSB_REQUIRE(c, PSB_ERR_ARG, "ctx is NULL");
+    PSB_REQUIRE(c->fetch_set >= 0, PSB_ERR_STATE, "psb_fetch_wait before psb_fetch_begin");
+    PSB_CUDA(cudaSetDevice(c->device));
+    const int s = c->fetch_set;
+    PSB_CUDA(cudaEventSynchronize(c->ev_fetch[s]));
+    if (counts_out) {
+        const int *h = c->h_counters[s];
+        counts_out[0] = c->fetch_S[s];
+        counts_out[1] = h[1] + h[5];
+        counts_out[2] = h[0] - h[5];
+        counts_out[3] = h[0] - h[5] - h[2];
+    }
     return PSB_OK;
 }
 

@@ -909,6 +909,8 @@ extern "C" int psb_run_fixed(psb_ctx *c, const psb_params *prm) {
     PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "psb_run_fixed without psb_submit");
     rc = psb_ensure_capacity(c, c->S, c->q > 1 ? c->q - 1 : 1);
     if (rc) return rc;
+    rc = psb_table_flip(c);
+    if (rc) return rc;
     PSB_CUDA(cudaEventRecord(c->ev_run0, c->stream));
     if (c->S > 0 && c->q > 1)
         PSB_CUDA(cudaMemsetAsync(c->d_betas, 0xFF, (size_t)c->S * (c->q - 1) * sizeof(double), c->stream));

@@ -98,6 +98,7 @@ struct psb_ctx {
     bool tc_welch_run = false;    // ... and this run takes the Welch sums from there (psb_run_lmm)
     void *tmap_Lq = nullptr;      // host copy of the CUtensorMap (128 B): box = 128 samples x all sliced rows
     void *tmap_Lq_half = nullptr; // same with half of the sliced rows per box (two-SM mode)
+    double *d_tc_part = nullptr;  // partial quadratic forms of a split launch (psb_lmm_tc.cu)
     void *tc_alt = nullptr;       // two-pass mode: the refinement precision's operand image (psb_lmm_tc.cu: TcState)
     double refine_F = 30.0;       // ... applied to variants whose F statistic exceeds this
 
@@ -168,6 +169,21 @@ struct psb_ctx {
     double *d_pp = nullptr;       // [cap] ||Q'x||^2 from the tensor path
     int64_t counts[4] = {0, 0, 0, 0};
     bool ran = false;
+    // Second set of the columns psb_fetch returns (and of the counters): psb_run_lmm / psb_run_fixed
+    // alternate between the two sets, so that the table of run i can travel to the host on its own
+    // stream (psb_fetch_begin) while run i + 1 is computed.  d_* above always name the CURRENT set.
+    int32_t *alt_carriers = nullptr, *alt_missing = nullptr;
+    double *alt_af = nullptr, *alt_prep = nullptr, *alt_pvalue = nullptr, *alt_beta = nullptr,
+           *alt_bse = nullptr, *alt_extra = nullptr, *alt_betas = nullptr;
+    uint32_t *alt_flags = nullptr;
+    int *alt_counters = nullptr;
+    int tab_cur = 0;                       // which set d_* name
+    cudaStream_t fetch_stream = nullptr;
+    cudaEvent_t ev_fetch[2] = {nullptr, nullptr};   // psb_fetch_begin of set s has landed on the host
+    bool fetch_valid[2] = {false, false};
+    int fetch_set = -1;                    // set of the last psb_fetch_begin
+    int64_t fetch_S[2] = {0, 0};
+    int *h_counters[2] = {nullptr, nullptr};        // pinned: counters of the fetched run
     void *kin = nullptr;          // psb_kinship.cu state
     void *text = nullptr;         // psb_text.cu state (device k-mer text parser)
 
@@ -185,6 +201,7 @@ struct psb_ctx {
 int psb_ensure_capacity(psb_ctx *ctx, int64_t S, int betas_cols);
 int psb_run_begin(psb_ctx *ctx);
 int psb_run_end(psb_ctx *ctx);
+int psb_table_flip(psb_ctx *ctx);
 int psb_free_model(psb_ctx *ctx);
 void psb_kinship_release(psb_ctx *ctx);
 void psb_burden_release(psb_ctx *ctx);

@@ -734,7 +734,7 @@ extern "C" int psb_reader_next_text(psb_reader *r, int64_t max_lines, int64_t li
     if (have) memcpy(dst, r->carry.data(), (size_t)have);
     r->carry.clear();
     int64_t n = 0, used = 0, scanned = 0, line_at = 0, consumed = 0;
-    bool full = false;
+    bool full = false, bad_line = false;
     std::vector<int64_t> nl;
     auto take_line = [&](int64_t a, int64_t b) -> bool {      // dst[a, b) without its newline
         int64_t e = b;
@@ -745,6 +745,9 @@ extern "C" int psb_reader_next_text(psb_reader *r, int64_t max_lines, int64_t li
         int64_t j = i;
         while (j < e && dst[j] != ' ' && dst[j] != '\t') ++j;
         if (j - i + 1 > names_cap - used || e - a > 0x7fffffffll) return false;
+        // the row reader's check (parse_line): the sample list starts after the first '|' (found within
+        // the first bytes of a well-formed line)
+        if (!memchr(dst + a, '|', (size_t)(e - a))) bad_line = true;
         memcpy(names + used, dst + i, (size_t)(j - i));
         names[used + (j - i)] = '\0';
         name_off[n] = used;
@@ -790,6 +793,7 @@ extern "C" int psb_reader_next_text(psb_reader *r, int64_t max_lines, int64_t li
         if (got == 0 && !r->text_eof) { full = true; break; }     // BGZF: the next block does not fit
         have += got;
     }
+    PSB_REQUIRE(!bad_line, PSB_ERR_ARG, "k-mer line without '|' separator");
     if (full && n < max_lines) {
         // cut short by a buffer: keep whole blocks of the caller's block size
         const int64_t keep = n / line_multiple * line_multiple;

@@ -475,6 +475,8 @@ extern "C" int psb_run_lmm(psb_ctx *c, const psb_params *prm) {
     PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "psb_run_lmm without psb_submit");
     rc = psb_ensure_capacity(c, c->S, 0);
     if (rc) return rc;
+    rc = psb_table_flip(c);
+    if (rc) return rc;
     PSB_CUDA(cudaEventRecord(c->ev_run0, c->stream));
     // With the tensor path carrying x'v and Q'x, the stats pass only needs popcounts and
     // (continuous phenotype) the two Welch sums; otherwise all masked column sums.

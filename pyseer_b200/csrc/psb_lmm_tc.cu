@@ -84,6 +84,9 @@ struct TcArgs {
     int pair;                 // launched as clusters of two CTAs: 1 = each CTA issues its own MMAs, the
                               // operand stream is shared through TMA multicast; 2 = two-SM MMAs
                               // (cta_group::2), each CTA holds half of every B stage
+    int split_max;            // > 1: component tiles of a variant tile may be dealt to up to this many units
+    double *a_part;           // [split_max][part_ld] partial quadratic forms of a split launch
+    int part_ld;
     int skip_box;             // triangular form: skip the all-zero first box of a diagonal stage
     int debug;                // timing experiments only (PSB_TC_DEBUG, results are wrong when set):
                               // 1: one MMA per stage instead of four; 2: expanders store without
@@ -105,6 +108,17 @@ __device__ __forceinline__ void tc_tile_of(const TcArgs &a, int q, int &jt, int 
     }
     jt = (q & 1) ? (nreg - 1 - (q >> 1)) : (q >> 1);
     ks0 = (jt * TC_JT) / TC_KSTAGE;
+}
+
+// how many units share the component tiles of one variant tile (1: no split)
+__host__ __device__ __forceinline__ int tc_split_of(int split_max, int n_tile_units, int n_units, int jtiles) {
+    int G = 1;
+    if (split_max > 1 && n_tile_units > 0 && n_tile_units * 2 <= n_units) {
+        G = n_units / n_tile_units;
+        if (G > split_max) G = split_max;
+        if (G > jtiles / 4) G = jtiles / 4 > 0 ? jtiles / 4 : 1;
+    }
+    return G;
 }
 
 struct TcStageIter {
@@ -193,6 +207,36 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int pair = args.pair;
     const uint32_t cta_rank = pair ? cluster_ctarank() : 0u;
     const int odd = pair ? (int)(blockIdx.x & 1u) : 0;     // tile - odd = the even CTA's tile
+    // Work items.  A unit is a CTA (or a CTA pair, which walks its two tiles in lockstep); with
+    // enough variant tiles an item is a whole tile (pair of tiles).  When there are FEWER tiles than
+    // units -- the refinement pass of the two-pass mode (the few variants with F > 30), small batches
+    // -- the component tiles of a variant tile are dealt to G units, each adding its part of
+    // a = x'M''x with one atomicAdd per variant (a_out is zeroed by the host wrapper), so that a
+    // handful of variants costs a G-th of a tile's latency instead of all of it.  The special tile
+    // (last of the sequence) belongs to the last group, which alone writes b, ||Q'x||^2 and the sums.
+    const int unit0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_tile_units = pair ? (n_tiles + 1) / 2 : n_tiles;
+    const int G = tc_split_of(args.split_max, n_tile_units, n_units, args.jtiles);
+    const int n_items = n_tile_units * G;
+    // item -> this CTA's tile and its range [q_lo, q_hi) of the component-tile sequence
+    auto item_of = [&](int item, int &tile, int &q_lo, int &q_hi) {
+        const int tu = item / G, g = item - tu * G;
+        tile = pair ? 2 * tu + odd : tu;
+        q_lo = args.jtiles * g / G;
+        q_hi = args.jtiles * (g + 1) / G;
+    };
+    // K stages of the component tiles [q_lo, q_hi)
+    auto item_stages = [&](int q_lo, int q_hi) -> int {
+        if (G == 1) return args.stages_per_tile;
+        int n = 0;
+        for (int q = q_lo; q < q_hi; ++q) {
+            int jt, ks0;
+            tc_tile_of(args, q, jt, ks0);
+            n += args.nks - ks0;
+        }
+        return n;
+    };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < ns; ++i) {
@@ -233,8 +277,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         // ===================== TMA producer (whole warp loops, one lane issues) ==========
         int st = 0;
         uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x)
-            for (int q = 0; q < args.jtiles; ++q) {
+        for (int item = unit0; item < n_items; item += n_units) {
+            int tile_u, q_lo, q_hi;
+            item_of(item, tile_u, q_lo, q_hi);
+            for (int q = q_lo; q < q_hi; ++q) {
                 int jt, ks0;
                 tc_tile_of(args, q, jt, ks0);
                 for (int ks = ks0; ks < args.nks; ++ks) {
@@ -265,11 +311,16 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                     if (++st == ns) { st = 0; ph ^= 1; }
                 }
             }
+        }
         // Pair mode: the peer's last commits arrive on this CTA's empty barriers; wait for them
         // so that nothing is in flight towards this CTA's shared memory when it exits.
         if (pair) {
             long long total = 0;
-            for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x) total += args.stages_per_tile;
+            for (int item = unit0; item < n_items; item += n_units) {
+                int tile_u, q_lo, q_hi;
+                item_of(item, tile_u, q_lo, q_hi);
+                total += item_stages(q_lo, q_hi);
+            }
             const int tail = total < ns ? (int)total : ns;
             for (int i = 0; i < tail; ++i) {
                 mbar_wait(empty0 + st * 8, ph ^ 1);
@@ -283,8 +334,10 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         uint32_t ph = 0, phacc = 0;
         const int jt_first_special = args.jtiles - (args.n_special > 0 ? 1 : 0);
         if (!(two && cta_rank != 0))
-        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x)
-            for (int q = 0; q < args.jtiles; ++q) {
+        for (int item = unit0; item < n_items; item += n_units) {
+            int tile_u, q_lo, q_hi;
+            item_of(item, tile_u, q_lo, q_hi);
+            for (int q = q_lo; q < q_hi; ++q) {
                 int jt, ks0;
                 tc_tile_of(args, q, jt, ks0);
                 mbar_wait(smem_u32(&accEmpty[acc]), phacc ^ 1);
@@ -329,6 +382,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 }
                 if (++acc == 2) { acc = 0; phacc ^= 1; }
             }
+        }
     } else if (warp < 2 + TC_EXP_WARPS) {
         // ===================== expanders (warps 2..9) =====================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -354,16 +408,20 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             const int jt = (q2 & 1) ? (nreg_x - 1 - (q2 >> 1)) : (q2 >> 1);
             return (jt * TC_JT) / TC_KSTAGE;
         };
-        // two stages forward in the sequence; the cursor is valid while cq < jtiles
+        // two stages forward in the sequence; the cursor is valid while cq < q_end (the end of the
+        // item's component-tile range)
+        int q_end = jtiles;
         auto advance2 = [&](int &cq, int &cks) {
             cks += 2;
             while (cks >= nks) {
                 const int over = cks - nks;
-                if (++cq >= jtiles) return;
+                if (++cq >= q_end) return;
                 cks = first_ks(cq) + over;
             }
         };
-        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x) {
+        for (int item = unit0; item < n_items; item += n_units) {
+            int tile, q_lo;
+            item_of(item, tile, q_lo, q_end);
             // all expanders are done reading the previous tile's bits
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et < TC_TILE_V) {
@@ -398,7 +456,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             // per ~20 stages) carries the overshoot into the next one.  Everything the loop
             // needs from `args` sits in registers: the per-stage control flow is a handful of
             // instructions next to the 64 ALU operations of the expansion itself.
-            int cq = 0, cks = first_ks(0) + (((int)parity != grp) ? 1 : 0) - 2;
+            int cq = q_lo, cks = first_ks(q_lo) + (((int)parity != grp) ? 1 : 0) - 2;
             advance2(cq, cks);
             // expand one 128-sample stage of this thread's variant into A slot sa, then signal
             auto emit = [&](const uint4 &w4a, const uint4 &w4b) {
@@ -443,7 +501,7 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
             };
             if (args.bits_in_smem) {
                 const uint32_t myrow_s = smem_u32(sBits + (size_t)v * args.pitch);
-                while (cq < jtiles) {
+                while (cq < q_end) {
                     const uint4 w4a = lds128(myrow_s + (uint32_t)cks * 32u);
                     const uint4 w4b = lds128(myrow_s + (uint32_t)cks * 32u + 16u);
                     emit(w4a, w4b);
@@ -454,22 +512,22 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 int pq = cq, pks = cks;
                 const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
                 uint4 nxa = zero4, nxb = zero4, nx2a = zero4, nx2b = zero4;
-                if (pq < jtiles) { nxa = gload(2 * pks); nxb = gload(2 * pks + 1); }
+                if (pq < q_end) { nxa = gload(2 * pks); nxb = gload(2 * pks + 1); }
                 advance2(pq, pks);
-                if (pq < jtiles) { nx2a = gload(2 * pks); nx2b = gload(2 * pks + 1); }
-                while (cq < jtiles) {
+                if (pq < q_end) { nx2a = gload(2 * pks); nx2b = gload(2 * pks + 1); }
+                while (cq < q_end) {
                     const uint4 w4a = nxa, w4b = nxb;
                     nxa = nx2a;
                     nxb = nx2b;
-                    if (pq < jtiles) {
+                    if (pq < q_end) {
                         advance2(pq, pks);
-                        if (pq < jtiles) { nx2a = gload(2 * pks); nx2b = gload(2 * pks + 1); }
+                        if (pq < q_end) { nx2a = gload(2 * pks); nx2b = gload(2 * pks + 1); }
                     }
                     emit(w4a, w4b);
                     advance2(cq, cks);
                 }
             }
-            parity ^= (uint32_t)(args.stages_per_tile & 1);
+            parity ^= (uint32_t)(item_stages(q_lo, q_end) & 1);
         }
     } else {
         // ===================== epilogue (warps 10..13) =====================
@@ -480,12 +538,14 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
         const int jt_special = args.n_special > 0 ? args.jtiles - 1 : -1;
         int acc = 0;
         uint32_t phacc = 0;
-        for (int tile = blockIdx.x; tile - odd < n_tiles; tile += gridDim.x) {
+        for (int item = unit0; item < n_items; item += n_units) {
+            int tile, q_lo, q_hi;
+            item_of(item, tile, q_lo, q_hi);
             double a = 0.0, bsum = 0.0, pp = 0.0;
             const int t_own = tile * TC_TILE_V + v;
             const int row_own = t_own < n_tested ? args.idx[t_own] : -1;
             const uint32_t *grow = args.bits + (size_t)(row_own < 0 ? 0 : row_own) * args.Wrow;
-            for (int q2 = 0; q2 < args.jtiles; ++q2) {
+            for (int q2 = q_lo; q2 < q_hi; ++q2) {
                 int jt, ks0_unused;
                 tc_tile_of(args, q2, jt, ks0_unused);
                 // triangular form: column j of this tile counts only if the variant carries
@@ -607,8 +667,11 @@ k_lmm_quadform_tc(const __grid_constant__ CUtensorMap tmap, const __grid_constan
                 if (++acc == 2) { acc = 0; phacc ^= 1; }
             }
             if (row_own >= 0) {
-                if (args.a_out) args.a_out[row_own] = a;
-                if (jt_special >= 0 && args.b_out) {
+                if (args.a_out) {
+                    if (G == 1) args.a_out[row_own] = a;
+                    else args.a_part[(size_t)(item % G) * args.part_ld + t_own] = a;   // summed by k_tc_split_reduce
+                }
+                if (jt_special >= 0 && args.b_out && q_hi == args.jtiles) {
                     args.b_out[row_own] = bsum;
                     args.pp_out[row_own] = pp;
                 }
@@ -980,6 +1043,22 @@ int psb_lmm_tc_run_list(psb_ctx *c, int upper, const int32_t *list, const int *c
 
 // lin_out != null: linear-only use (psb_tc_linear_setup): the pair sums go to
 // lin_out[variant * lin_ld + pair] and no quadratic form is produced.
+// Second half of a split launch: a[row] = sum_g a_part[g][t] in a fixed order (the kernel's G is
+// recomputed from the same device-side count; nothing to do when it was 1).
+__global__ void k_tc_split_reduce(const int32_t *__restrict__ idx, const int *__restrict__ count_dev, int upper,
+                                  int split_max, int n_units, int pair, int jtiles,
+                                  const double *__restrict__ part, int part_ld, double *__restrict__ a) {
+    const int n = count_dev ? min(*count_dev, upper) : upper;
+    const int n_tiles = (n + TC_TILE_V - 1) / TC_TILE_V;
+    const int G = tc_split_of(split_max, pair ? (n_tiles + 1) / 2 : n_tiles, n_units, jtiles);
+    if (G == 1) return;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int g = 0; g < G; ++g) s += part[(size_t)g * part_ld + t];
+        a[idx[t]] = s;
+    }
+}
+
 int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     const int nsl = c->n_slices;
     TcArgs a;
@@ -1051,6 +1130,18 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     const int tiles = psb_div_up(n_tested, TC_TILE_V);
     int grid = std::min(tiles, c->sm_count);
     if (a.pair) grid = std::min((tiles + 1) & ~1, c->sm_count & ~1);
+    // Few variant tiles (the device-side count decides: the refinement pass, small batches): their
+    // component tiles are dealt to several units (see the kernel), which needs the whole grid and a
+    // zeroed accumulator.
+    a.split_max = (a.a_out && !(getenv("PSB_TC_SPLIT") && atoi(getenv("PSB_TC_SPLIT")) == 0)) ? 16 : 1;
+    a.a_part = nullptr;
+    a.part_ld = 0;
+    if (a.split_max > 1 && n_tested > 0) {
+        grid = a.pair ? (c->sm_count & ~1) : c->sm_count;
+        a.part_ld = (c->sm_count / 2 + 1) * TC_TILE_V;         // a split launch has at most this many variants
+        if (!c->d_tc_part) PSB_CUDA(cudaMalloc(&c->d_tc_part, (size_t)16 * a.part_ld * sizeof(double)));
+        a.a_part = c->d_tc_part;
+    }
     int rc = PSB_OK;
     switch (nsl) {
         case 3: rc = tc_launch<3>(c, a, grid, smem); break;
@@ -1065,6 +1156,11 @@ int psb_tc_run(psb_ctx *c, int n_tested, double *lin_out, int lin_ld) {
     if (rc) return rc;
     c->launches++;
     PSB_CUDA(cudaGetLastError());
+    if (a.split_max > 1 && n_tested > 0) {
+        k_tc_split_reduce<<<37, 256, 0, c->stream>>>(a.idx, a.n_tested_dev, n_tested, a.split_max, a.pair ? grid / 2 : grid,
+                                                    a.pair ? 1 : 0, a.jtiles, a.a_part, a.part_ld, c->d_a);
+        PSB_CUDA(cudaGetLastError());
+    }
     return PSB_OK;
 }
 
@@ -1112,6 +1208,8 @@ int psb_lmm_tc_stash(psb_ctx *c) {
 }
 
 void psb_lmm_tc_free(psb_ctx *c) {
+    if (c->d_tc_part) cudaFree(c->d_tc_part);
+    c->d_tc_part = nullptr;
     if (c->tc_alt) {
         TcState *s = (TcState *)c->tc_alt;
         if (s->d_Lq) cudaFree(s->d_Lq);

@@ -375,6 +375,22 @@ class Engine(object):
             setattr(out, f, c_void_p(int(ptr)))
         check(self.lib.psb_fetch(self._ctx, byref(out)))
 
+    def fetch_begin(self, pointers):
+        """Asynchronous ``fetch_into`` (``psb_fetch_begin``): the copies are queued behind the last run
+        on the library's fetch stream; the next ``run_*`` may be queued at once.  The buffers must be
+        page-locked for the copies to be truly asynchronous, and stay valid until ``fetch_wait``."""
+        out = PsbResults()
+        for f, ptr in pointers.items():
+            setattr(out, f, c_void_p(int(ptr)))
+        self._fetch_keep = out
+        check(self.lib.psb_fetch_begin(self._ctx, byref(out)))
+
+    def fetch_wait(self):
+        """Blocks until the last ``fetch_begin`` has landed; returns that run's counts."""
+        c = (c_int64 * 4)()
+        check(self.lib.psb_fetch_wait(self._ctx, c))
+        return {'loaded': c[0], 'prefiltered': c[1], 'tested': c[2], 'passed': c[3]}
+
     def download_bits(self, out):
         """Copy the submitted device rows into ``out`` (uint32 (S, W) array, ideally pinned)."""
         assert out.dtype == np.uint32 and out.flags['C_CONTIGUOUS']

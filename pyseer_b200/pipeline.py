@@ -9,8 +9,8 @@ native formatter all release the GIL):
              (``PinnedPool``), so that ``psb_submit`` is a true asynchronous DMA; plain k-mer files go
              one step further (``TextPool``): the reader only reads / inflates the TEXT into the
              page-locked buffer and cuts it into lines, the device tokenises it (``psb_submit_text``);
-  GPU        ``BatchRunner``: submit(k+1) on the copy stream while the kernels of batch k run, then
-             fetch(k); with several GPUs a *super-step* deals one batch to every GPU (contiguous,
+  GPU        ``BatchRunner``: submit(k+1) on the copy stream and the table of batch k on the fetch
+             stream (``psb_fetch_begin``) while the kernels of batch k+1 run; with several GPUs a *super-step* deals one batch to every GPU (contiguous,
              in input order), the runs are queued from one thread per GPU, and the result tables come
              back through the library's NCCL gather on GPU 0 (``comm.gather_begin`` / ``gather_fetch``)
              in rank order = input order, as the reference's ordered ``pool.starmap`` keeps it;
@@ -79,6 +79,44 @@ class TextPool(object):
             for b in bufs:
                 b.free()
         self._bufs = []
+
+
+class AsyncFetch(object):
+    """One page-locked set of result columns for ``Engine.fetch_begin`` / ``fetch_wait``; ``wait``
+    returns a ``Results`` holding copies, so the set is free for the next ``begin``."""
+    COLS = (('carriers', np.int32), ('missing', np.int32), ('af', np.float64), ('prep', np.float64),
+            ('pvalue', np.float64), ('beta', np.float64), ('bse', np.float64), ('extra', np.float64),
+            ('flags', np.uint32))
+
+    def __init__(self, eng, rows, n_betas):
+        self.eng, self.nb = eng, int(n_betas)
+        self.bufs = {name: PinnedBuffer((rows,), dt) for name, dt in self.COLS}
+        self.betas = PinnedBuffer((rows * max(self.nb, 1),), np.float64)
+        self.n = 0
+
+    def begin(self, n):
+        ptrs = {name: self.bufs[name].array.ctypes.data for name, _ in self.COLS}
+        if self.nb:
+            ptrs['betas'] = self.betas.array.ctypes.data
+        self.n = n
+        self.eng.fetch_begin(ptrs)
+
+    def wait(self):
+        from .engine import Results
+        counts = self.eng.fetch_wait()
+        r = Results()
+        for name, _ in self.COLS:
+            setattr(r, name, self.bufs[name].array[:self.n].copy())
+        r.betas = self.betas.array[:self.n * self.nb].reshape(self.n, self.nb).copy()
+        r.counts = counts
+        r.lineage = None
+        return r
+
+    def close(self):
+        for b in self.bufs.values():
+            b.free()
+        self.betas.free()
+        self.bufs = {}
 
 
 def submit_batch(eng, b):
@@ -157,15 +195,7 @@ class BatchRunner(object):
         r = eng.fetch()
         if self.lineage is not None:
             r.lineage = eng.run_lineage(self.lineage)
-        self._text_info(eng, b)
         return r
-
-    @staticmethod
-    def _text_info(eng, b):
-        # a batch parsed on the device: its per-line flags (no observation / malformed line) are read
-        # while the engine still holds it, i.e. before the next run is queued
-        if b.text is not None:
-            b.info = eng.text_info(b.n)
 
     def results(self, batches):
         if len(self.engines) == 1:
@@ -177,15 +207,40 @@ class BatchRunner(object):
 
     def _single(self, batches):
         eng = self.engines[0]
-        prev = None
-        for b in batches:
-            submit_batch(eng, b)                   # H2D of batch k+1 on the copy stream ...
+        if self.lineage is not None or self.rows_max <= 0:
+            # lineage effects are fitted on the device table of the run they belong to: one run at a time
+            prev = None
+            for b in batches:
+                submit_batch(eng, b)                   # H2D of batch k+1 on the copy stream ...
+                if prev is not None:
+                    yield prev, self._fetch(eng, prev)  # ... while batch k finishes and comes back
+                self.run(eng)
+                prev = b
             if prev is not None:
-                yield prev, self._fetch(eng, prev)  # ... while batch k finishes and comes back
-            self.run(eng)
-            prev = b
-        if prev is not None:
-            yield prev, self._fetch(eng, prev)
+                yield prev, self._fetch(eng, prev)
+            return
+        # Three things in flight: the copy of batch k+1 (copy stream), the table of batch k on its way
+        # to the host (psb_fetch_begin, fetch stream) and the kernels of batch k+1, which write the
+        # other set of result columns -- the device never waits for the host.
+        fetcher = AsyncFetch(eng, self.rows_max, self.n_betas)
+        try:
+            prev = inflight = None
+            for b in batches:
+                submit_batch(eng, b)
+                if prev is not None:
+                    if inflight is not None:
+                        yield inflight, fetcher.wait()
+                    fetcher.begin(prev.n)
+                    inflight = prev
+                self.run(eng)
+                prev = b
+            if inflight is not None:
+                yield inflight, fetcher.wait()
+            if prev is not None:
+                fetcher.begin(prev.n)
+                yield prev, fetcher.wait()
+        finally:
+            fetcher.close()
 
     def _multi(self, batches):
         n = len(self.engines)
@@ -196,7 +251,6 @@ class BatchRunner(object):
                 self.comm.gather_wait()
                 for g, b in enumerate(grp):
                     r, _, _ = self.comm.gather_fetch(g, n_betas=self.n_betas)
-                    self._text_info(self.engines[g], b)
                     yield b, r
             else:
                 for g, b in enumerate(grp):

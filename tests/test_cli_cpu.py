@@ -117,6 +117,23 @@ class _FakeTextPool(object):
         pass
 
 
+class _FakeAsyncFetch(object):
+    """pipeline.AsyncFetch for the engine double: the 'copy' is taken when it is begun (the double's runs
+    are synchronous), in the place the pipeline begins it -- before the next run is queued."""
+
+    def __init__(self, eng, rows, n_betas):
+        self.eng = eng
+
+    def begin(self, n):
+        self.r = self.eng.fetch()
+
+    def wait(self):
+        return self.r
+
+    def close(self):
+        pass
+
+
 def _patch(monkeypatch):
     from pyseer_b200 import model as fx, lmm as lm, pipeline
     monkeypatch.setattr(fx, 'fit_null', _fake_fit_null)
@@ -125,6 +142,7 @@ def _patch(monkeypatch):
     monkeypatch.setattr(lm.KinshipLMM, 'engine', lambda self, h2: _FakeEngine(lmm=self, h2=h2))
     monkeypatch.setattr(pipeline, 'PinnedPool', _FakePool)
     monkeypatch.setattr(pipeline, 'TextPool', _FakeTextPool)
+    monkeypatch.setattr(pipeline, 'AsyncFetch', _FakeAsyncFetch)
 
 
 class _FakeFixedModel(object):

@@ -356,3 +356,52 @@ def test_popcount_pass_variants_agree(monkeypatch, n, pheno):
     for tag in ('vector', 'scalar'):
         for a, b in zip(out['stream'], out[tag]):
             assert np.array_equal(a, b, equal_nan=True), tag
+
+
+def test_async_fetch_equals_fetch():
+    """psb_fetch_begin / psb_fetch_wait: the table of run i copied on the fetch stream while runs i+1,
+    i+2 are computed into the other set of result columns equals what psb_fetch returns for the same
+    rows, counters included."""
+    from pyseer_b200.engine import Engine, PinnedBuffer, synth_host
+    n, nv = 500, 3000
+    rng = np.random.RandomState(12)
+    y = (rng.uniform(size=n) < 0.45).astype(float)
+    Z = np.column_stack([np.ones(n), rng.normal(size=(n, 2))])
+    batches = [synth_host(40 + i, 0, nv - 100 * i, n, af_lo=0.0, af_hi=1.0) for i in range(4)]
+    cols = (('carriers', np.int32), ('missing', np.int32), ('af', np.float64), ('prep', np.float64),
+            ('pvalue', np.float64), ('beta', np.float64), ('bse', np.float64), ('extra', np.float64),
+            ('flags', np.uint32))
+    with Engine(0) as eng:
+        eng.fixed_setup(Z, y, False, -340.0, -330.0)
+        ref = []
+        for b in batches:
+            eng.submit(b)
+            eng.run_fixed(filter_pvalue=0.5, lrt_pvalue=0.9)
+            ref.append(eng.fetch())
+        bufs = [{name: PinnedBuffer((nv,), dt) for name, dt in cols} for _ in batches]
+        betas = [PinnedBuffer((nv, 2), np.float64) for _ in batches]
+        counts = []
+        eng.submit(batches[0])
+        eng.run_fixed(filter_pvalue=0.5, lrt_pvalue=0.9)
+        for i in range(1, len(batches) + 1):
+            if i < len(batches):
+                eng.submit(batches[i])
+            if i > 1:
+                counts.append(eng.fetch_wait())
+            ptrs = {name: bufs[i - 1][name].array.ctypes.data for name, _ in cols}
+            ptrs['betas'] = betas[i - 1].array.ctypes.data
+            eng.fetch_begin(ptrs)
+            if i < len(batches):
+                eng.run_fixed(filter_pvalue=0.5, lrt_pvalue=0.9)
+        counts.append(eng.fetch_wait())
+        for i, b in enumerate(batches):
+            m = b.shape[0]
+            for name, _ in cols:
+                assert np.array_equal(bufs[i][name].array[:m], getattr(ref[i], name), equal_nan=True), (i, name)
+            assert np.array_equal(betas[i].array.reshape(-1)[:m * 2].reshape(m, 2), ref[i].betas, equal_nan=True)
+            assert counts[i] == ref[i].counts
+        for d in bufs:
+            for pb in d.values():
+                pb.free()
+        for pb in betas:
+            pb.free()

@@ -109,14 +109,30 @@ def test_adversarial_lines(tmp_path, n):
     assert dn2 == hn and np.array_equal(db2, hb)
 
 
-def test_line_without_separator_is_flagged(tmp_path):
+def test_line_without_separator(tmp_path):
+    """the host half refuses it like the row reader does (PSB_ERR_ARG); the kernel flags it when it is
+    handed such a line all the same"""
+    from pyseer_b200 import _lib
+    from pyseer_b200.input import VariantReader
     p = pd.Series([0.0, 1.0, 1.0], index=['a', 'b', 'c'])
     path = str(tmp_path / 'bad.txt')
-    with open(path, 'w') as fh:
-        fh.write('AAA | a:1 b:1\nCCC a:1\nGGG | c:1\n')
-    dn, db, info = _device_rows(path, p, 8)
-    assert dn == ['AAA', 'CCC', 'GGG'] and list(info & 4) == [0, 4, 0]
-    assert list(db[:, 0]) == [3, 0, 4]
+    text = b'AAA | a:1 b:1\nCCC a:1\nGGG | c:1\n'
+    with open(path, 'wb') as fh:
+        fh.write(text)
+    rd = VariantReader('kmers', path, p)
+    with pytest.raises(_lib.PsbError, match='separator'):
+        list(rd.text_batches(8))
+    rd.close()
+    eng = _engine(3)
+    eng.text_setup(['a', 'b', 'c'])
+    buf = np.frombuffer(text, dtype=np.uint8).copy()
+    ls = np.array([0, 14, 22], dtype=np.int64)
+    ll = np.array([13, 7, 9], dtype=np.int32)
+    eng.submit_text(buf, buf.shape[0], ls, ll, 3)
+    bits, _ = eng.download_rows()
+    info = eng.text_info(3)
+    eng.close()
+    assert list(info & 4) == [0, 4, 0] and list(bits[:, 0]) == [3, 0, 4]
 
 
 def test_cli_prints_the_same_with_and_without_device_parser(tmp_path, monkeypatch):
