@@ -688,7 +688,7 @@ def gpu_line(a, model, n, kpg, rank, local_rank, world, comm, eng, steps, warmup
             # One step = the whole shard through the public calls a user makes, in `chunks`
             # batches: psb_submit copies batch i+1 (copy stream, second staging slot) while the
             # kernels of batch i run; psb_fetch of batch i then brings its rows of the table back.
-            chunks = max(1, a.e2e_chunks or {'lmm': 8, 'lmm-binary': 4, 'fixed': 6, 'fixed-cont': 8}.get(model, 8))
+            chunks = max(1, a.e2e_chunks or {'lmm': 8, 'lmm-binary': 4, 'fixed': 4, 'fixed-cont': 8}.get(model, 8))
             # a short first batch (its copy is the only one nothing hides) and a short last one (so is
             # its table's way back); the batches between them are large, which keeps the partial last
             # wave of every tensor-kernel launch and the per-launch costs small

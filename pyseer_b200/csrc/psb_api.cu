@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "psb_internal.cuh"
+#include <stdlib.h>
 #include <utility>
 #include "psb_math.cuh"
 #include "psb_fixed.cuh"
@@ -62,14 +63,14 @@ int psb_create(int device_id, psb_ctx **out) {
     PSB_CUDA(cudaEventCreate(&c->ev_k0));
     PSB_CUDA(cudaEventCreate(&c->ev_k1));
     for (int i = 0; i < 8; ++i) PSB_CUDA(cudaEventCreate(&c->ev_user[i]));
-    PSB_CUDA(cudaMalloc(&c->d_counters, 8 * sizeof(int)));
-    PSB_CUDA(cudaMalloc(&c->alt_counters, 8 * sizeof(int)));
-    PSB_CUDA(cudaMemset(c->d_counters, 0, 8 * sizeof(int)));
-    PSB_CUDA(cudaMemset(c->alt_counters, 0, 8 * sizeof(int)));
+    PSB_CUDA(cudaMalloc(&c->d_counters, PSB_N_COUNTERS * sizeof(int)));
+    PSB_CUDA(cudaMalloc(&c->alt_counters, PSB_N_COUNTERS * sizeof(int)));
+    PSB_CUDA(cudaMemset(c->d_counters, 0, PSB_N_COUNTERS * sizeof(int)));
+    PSB_CUDA(cudaMemset(c->alt_counters, 0, PSB_N_COUNTERS * sizeof(int)));
     PSB_CUDA(cudaStreamCreateWithFlags(&c->fetch_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         PSB_CUDA(cudaEventCreateWithFlags(&c->ev_fetch[i], cudaEventDisableTiming));
-        PSB_CUDA(cudaHostAlloc((void **)&c->h_counters[i], 8 * sizeof(int), cudaHostAllocDefault));
+        PSB_CUDA(cudaHostAlloc((void **)&c->h_counters[i], PSB_N_COUNTERS * sizeof(int), cudaHostAllocDefault));
     }
     *out = c;
     return PSB_OK;
@@ -353,7 +354,7 @@ int psb_fetch_begin(psb_ctx *c, const psb_results *out) {
     if (out->betas && S > 0 && c->model == PSB_MODEL_FIXED && c->q > 1)
         PSB_CUDA(cudaMemcpyAsync(out->betas, c->d_betas, S * (c->q - 1) * sizeof(double),
                                  cudaMemcpyDefault, st));
-    PSB_CUDA(cudaMemcpyAsync(c->h_counters[c->tab_cur], c->d_counters, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaMemcpyAsync(c->h_counters[c->tab_cur], c->d_counters, PSB_N_COUNTERS * sizeof(int), cudaMemcpyDeviceToHost, st));
     PSB_CUDA(cudaEventRecord(c->ev_fetch[c->tab_cur], st));
     c->fetch_valid[c->tab_cur] = true;
     c->fetch_set = c->tab_cur;
@@ -431,7 +432,7 @@ int psb_counts(psb_ctx *c, int64_t out[4]) {
     PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(c->ran, PSB_ERR_STATE, "psb_counts before psb_run_*");
     PSB_CUDA(cudaSetDevice(c->device));
-    int h[8];
+    int h[PSB_N_COUNTERS];
     PSB_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     PSB_CUDA(cudaStreamSynchronize(c->stream));
     // h[5]: variants the LMM epilogue found to fail the (deferred) Welch pre-filter after they had
@@ -447,13 +448,15 @@ int psb_last_stats(psb_ctx *c, int64_t out[4]) {
     PSB_REQUIRE(c && out, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(c->ran, PSB_ERR_STATE, "psb_last_stats before psb_run_*");
     PSB_CUDA(cudaSetDevice(c->device));
-    int h[8];
+    int h[PSB_N_COUNTERS];
     PSB_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     PSB_CUDA(cudaStreamSynchronize(c->stream));
     out[0] = h[4];      // Newton evaluations (passes over the samples) of the Logit kernel
     out[1] = h[3];      // variants handed to the Firth kernel
     out[2] = h[2];      // variants that failed the lrt filter
-    out[3] = 0;
+    if (getenv("PSB_DEBUG_STATS"))
+        fprintf(stderr, "psb stats: firth max iterations %d (variant %d), max halvings of a fit %d (variant %d)\n", h[9], h[11], h[10], h[12]);
+    out[3] = h[8];      // penalised-likelihood evaluations of the Firth kernel that met a singular matrix
     return PSB_OK;
 }
 

@@ -368,7 +368,9 @@ k_fixed_firth(FxArgs a, int n_list) {
             if (c == a.q) hxx_cur = H[Tri<PP>::at(c, c)];
         double fl_cur, fitll = NAN, hxx_fit = NAN;
         double last_step_norm = INFINITY;      // || betas[i] - betas[i-1] ||
+        int n_iter = 0, n_halve = 0;
         for (int i = 0; i < 1000 && ok; ++i) {
+            ++n_iter;
             double logdet;
             if (fx_chol_firth<PP>(H)) {
                 logdet = fx_chol_logdet<PP>(H);
@@ -377,6 +379,7 @@ k_fixed_firth(FxArgs a, int n_list) {
                 // singular information matrix: np.linalg.pinv / det carry on (model.py:450, :410);
                 // the factorisation ran in place, so X'WX is evaluated again first
                 fx_eval<PP>(a, xrow, lane, beta, H, g, maxdev, llf_cur, true);
+                if (lane == 0 && a.has_x) atomicAdd(&a.counters[8], 1);
                 logdet = fx_singular<PP, true>(H, V, p);
                 if (isnan(V[0])) { ok = false; break; }
             }
@@ -434,13 +437,24 @@ k_fixed_firth(FxArgs a, int n_list) {
                 for (int e = 0; e < Tri<PP>::SIZE; ++e) V[e] = H[e];
                 double ld;
                 if (fx_chol_firth<PP>(V)) ld = fx_chol_logdet<PP>(V);
-                else ld = fx_singular<PP, false>(H, V, p);
+                else {
+                    if (lane == 0 && a.has_x) atomicAdd(&a.counters[8], 1);
+                    ld = fx_singular<PP, false>(H, V, p);
+                }
                 fl_new = -(llf_new + 0.5 * ld);
-                if (!(fl_new > fl_cur)) break;
+                // model.py:470: `while firth_likelihood(new) > firth_likelihood(old)`.  Near convergence the
+                // two values agree to the last few bits and the comparison is decided by rounding noise;
+                // a step that halves down to one ulp above the old vector (0.5 ulp rounds back up when the
+                // old mantissa is odd) can then stay "worse" for all 1000 halvings -- the reference has
+                // this coin flip too (about one Firth fit in 2000 here), with its own noise.  A difference
+                // within 16 ulp of the likelihood is treated as "not worse": the fit then follows the path
+                // the reference takes whenever its own rounding is not the unlucky one.
+                if (!(fl_new > fl_cur + 2e-15 * fabs(fl_cur))) break;
 #pragma unroll
                 for (int c = 0; c < PP; ++c) cand[c] = beta[c] + 0.5 * (cand[c] - beta[c]);
                 if (++j > 1000) { ok = false; break; }
             }
+            n_halve += j;
             if (!ok) break;
             // betas.append(new_beta)
             double nrm = 0.0;
@@ -463,6 +477,12 @@ k_fixed_firth(FxArgs a, int n_list) {
             if (i > 0 && prev_step < 1e-4) { converged = true; break; }    // model.py:480-483
         }
         (void)hxx_cur;
+        if (lane == 0 && a.has_x) {                        // diagnostics: longest fit of the launch
+            const int old = atomicMax(&a.counters[9], n_iter);
+            if (n_iter > old) a.counters[11] = v;
+            const int oldh = atomicMax(&a.counters[10], n_halve);
+            if (n_halve > oldh) a.counters[12] = v;
+        }
         if (ok && !converged) ok = false;                  // model.py:485-486 (limit reached)
         (void)last_step_norm;
         if (!a.has_x) {

@@ -389,7 +389,7 @@ k_fixed_generic(FxArgs a, const int32_t *__restrict__ idx, int n_items, int mode
                     if (gen_chol_firth(ws.V, P, lane, ws.g)) ld = gen_logdet(ws.V, P);
                     else ld = gen_singular(ws, nullptr, p, scratchQ, lane);
                     fl_new = -(llf_new + 0.5 * ld);
-                    if (!(fl_new > fl_cur)) break;
+                    if (!(fl_new > fl_cur + 2e-15 * fabs(fl_cur))) break;   // see k_fixed_firth: noise-level differences are "not worse"
                     __syncwarp();
                     for (int c = lane; c < P; c += 32) ws.cand[c] = ws.beta[c] + 0.5 * (ws.cand[c] - ws.beta[c]);
                     __syncwarp();

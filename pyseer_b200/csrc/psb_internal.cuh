@@ -9,6 +9,7 @@
 
 #include "../../include/pyseer_b200.h"
 
+#define PSB_N_COUNTERS 16  // device counters per result set (see psb_varstats.cu: psb_launch_prefilter)
 #define PSB_MODEL_NONE 0
 #define PSB_MODEL_LMM 1
 #define PSB_MODEL_FIXED 2

@@ -197,7 +197,7 @@ k_prefilter(int64_t S, int N, const int32_t *__restrict__ carriers,
 }
 
 int psb_launch_prefilter(psb_ctx *c, const psb_params *prm, int lmm_rule, int defer_welch) {
-    PSB_CUDA(cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(int), c->stream));
+    PSB_CUDA(cudaMemsetAsync(c->d_counters, 0, PSB_N_COUNTERS * sizeof(int), c->stream));
     if (c->S == 0) return PSB_OK;
     int blocks = psb_div_up(c->S, 256);
     k_prefilter<<<blocks, 256, 0, c->stream>>>(c->S, c->N, c->d_carriers, c->d_missing, c->d_tab,

@@ -417,7 +417,8 @@ class Engine(object):
     def last_stats(self):
         c = (c_int64 * 4)()
         check(self.lib.psb_last_stats(self._ctx, c))
-        return {'newton_evaluations': c[0], 'firth_fits': c[1], 'lrt_filtered': c[2]}
+        return {'newton_evaluations': c[0], 'firth_fits': c[1], 'lrt_filtered': c[2],
+                'firth_singular_evaluations': c[3]}
 
     def last_ms(self, which=0):
         ms = c_float(0)

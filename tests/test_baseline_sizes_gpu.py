@@ -58,8 +58,9 @@ def _compare(cols, ref, names, what, firth_noise=0):
     convergence the two values differ by rounding noise (1e-13 relative), and when the noise says
     "worse" the halving can park one ulp away from the old iterate for all 1000 tries -> None ->
     'firth-fail'.  Which variants that happens to is decided by the last bits of LAPACK's det / pinv
-    in the reference and of the Cholesky factor here; the rows are excluded from the value columns
-    and counted."""
+    in the reference (the device kernel treats a difference within 16 ulp as "not worse", so it no
+    longer loses fits -- or 85 ms per lost fit -- to its own noise; what remains are the reference's
+    unlucky rows); the rows are excluded from the value columns and counted."""
     vis = np.uint32(0x07FF)                       # note bits + prefilter + filter
     assert np.array_equal(cols['carriers'], ref['carriers']), what
     assert np.array_equal(cols['af'], ref['res'][:, 0]), what
