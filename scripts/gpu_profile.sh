@@ -11,6 +11,6 @@ timeout 900 $NCU --set full --import-source on -k regex:k_lmm_quadform_tc -s 1 -
     python bench.py --precision 4 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-secondary > gpurun_out/ncu_tc.log 2>&1
 timeout 900 $NCU --set full --import-source on -k regex:k_fixed_logit_fast -s 1 -c 1 -o gpurun_out/r02_logit_fast \
     python bench.py --model fixed --kmers-per-gpu 1000000 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_logit.log 2>&1
-timeout 600 $NCU --set full -k regex:k_bitstats_v -s 1 -c 1 -o gpurun_out/r02_bitstats_v \
+timeout 600 $NCU --set full -k regex:k_bitstats_stream -s 1 -c 1 -o gpurun_out/r02_bitstats_stream \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-secondary > gpurun_out/ncu_bitstats.log 2>&1
 ls -la gpurun_out/*.ncu-rep
