@@ -380,12 +380,16 @@ def main(argv=None):
     text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and \
         not (o.print_samples or o.lineage or o.output_patterns or o.bits_cache) and \
         os.environ.get('PYSEER_B200_TEXT', '1') != '0'
+    name_bytes = sum(len(x) for x in reader.samples) + 3 * reader.n_samples if text_mode else 0
+    if text_mode and o.block_size * (name_bytes + 4096) > (2 << 30):
+        text_mode = False      # one block of worst-case lines would not fit a 2 GB text buffer: host parser
     if text_mode:
         # page-locked text buffers sized for a full batch at an allele frequency of 0.5 (a batch cut
-        # short by its buffer keeps whole blocks, see psb_reader_next_text)
-        name_bytes = sum(len(x) for x in reader.samples) + 3 * reader.n_samples
+        # short by its buffer keeps whole blocks, see psb_reader_next_text) and never smaller than one
+        # block of lines that list every sample
         per_line = name_bytes // 2 + 512
         text_bytes = int(min(max(32 << 20, gpu_batch * per_line), 768 << 20))
+        text_bytes = max(text_bytes, o.block_size * (name_bytes + 4096))
         for e in engines:
             e.text_setup(reader.samples)
         pool = pipeline.TextPool(2 * n_gpus + 2, gpu_batch, text_bytes)

@@ -797,7 +797,12 @@ extern "C" int psb_reader_next_text(psb_reader *r, int64_t max_lines, int64_t li
     if (full && n < max_lines) {
         // cut short by a buffer: keep whole blocks of the caller's block size
         const int64_t keep = n / line_multiple * line_multiple;
-        PSB_REQUIRE(keep > 0, PSB_ERR_NOMEM, "text / name buffers too small for %lld lines", (long long)line_multiple);
+        if (keep <= 0) {
+            // nothing is lost: the text read so far opens the next call (with larger buffers)
+            r->carry.assign(dst, dst + have);
+            psb_set_error("text / name buffers too small for %lld lines", (long long)line_multiple);
+            return PSB_ERR_NOMEM;
+        }
         if (keep < n) {
             n = keep;
             consumed = line_start[keep];      // the first dropped line opens the next call

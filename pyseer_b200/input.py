@@ -265,7 +265,7 @@ class VariantReader(object):
                     self._h, rows, int(block_size), text.ctypes.data, text.shape[0], lstart.ctypes.data,
                     llen.ctypes.data, ctypes.addressof(names), ncap, off.ctypes.data, ctypes.byref(n),
                     ctypes.byref(nb))
-                if rc == _lib.PSB_ERR_NOMEM and ncap < (1 << 30) and pool is None and text_cap is None:
+                if rc == _lib.PSB_ERR_NOMEM and ncap < (1 << 30):      # the text read so far is kept by the reader
                     ncap *= 4
                     continue
                 _lib.check(rc)

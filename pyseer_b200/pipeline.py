@@ -89,12 +89,17 @@ class AsyncFetch(object):
             ('flags', np.uint32))
 
     def __init__(self, eng, rows, n_betas):
-        self.eng, self.nb = eng, int(n_betas)
+        self.eng, self.nb, self.rows = eng, int(n_betas), int(rows)
         self.bufs = {name: PinnedBuffer((rows,), dt) for name, dt in self.COLS}
         self.betas = PinnedBuffer((rows * max(self.nb, 1),), np.float64)
         self.n = 0
 
     def begin(self, n):
+        if n > self.rows:                      # a batch larger than announced: larger buffers
+            self.close()
+            self.rows = int(n)
+            self.bufs = {name: PinnedBuffer((self.rows,), dt) for name, dt in self.COLS}
+            self.betas = PinnedBuffer((self.rows * max(self.nb, 1),), np.float64)
         ptrs = {name: self.bufs[name].array.ctypes.data for name, _ in self.COLS}
         if self.nb:
             ptrs['betas'] = self.betas.array.ctypes.data

@@ -380,3 +380,15 @@ def test_text_mode_threads_on_a_large_file(tmp_path):
     assert out[1] == out[5]
     with open(path, 'rb') as fh:
         assert [l for _, ls in out[5] for l in ls] == [l.rstrip() for l in fh.read().split(b'\n') if l]
+
+
+def test_text_mode_keeps_its_text_when_a_buffer_is_too_small(tmp_path):
+    """PSB_ERR_NOMEM (here: a names buffer shorter than the first name) loses nothing: the text read so
+    far opens the next call, which Python makes with a larger buffer."""
+    p = _pheno()
+    raw = gzip.open(os.path.join(GOLDEN, 'kmers.gz'), 'rb').read()
+    ref = [l.split()[0].decode() for l in raw.split(b'\n') if l.strip()]
+    rd = VariantReader('kmers', os.path.join(GOLDEN, 'kmers.gz'), p)
+    names = [x for b in rd.text_batches(64, names_cap=8) for x in b.names]
+    rd.close()
+    assert names == ref
