@@ -3,7 +3,7 @@
 Same interface and output as pyseer's ``similarity`` tool (pyseer/similarity.py): a list of
 sample names, a variant file (``--kmers`` / ``--pres`` / ``--vcf``), AF / missing filters;
 writes the N x N matrix ``K = G G'`` as a TSV with sample names.  The product runs on the GPU
-as an AND + POPCOUNT contraction over packed rows (``psb_kinship_*``).
+as an int8 tensor-core contraction of the bit-expanded packed rows (``psb_kinship_*``).
 
 One deliberate difference: a MISSING genotype counts as absent (0).  The reference keeps NaN in its
 variant matrix for variants that pass ``--max-missing`` (input.py:428-430, similarity.py:99-113), so

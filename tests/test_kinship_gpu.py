@@ -12,8 +12,19 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('n,nv', [(50, 333), (333, 5000), (1000, 4097)])
-def test_kinship_matches_numpy(n, nv):
+@pytest.fixture(params=['tensor', 'popcount'])
+def kin_mode(request, monkeypatch):
+    """Both contraction paths of psb_kinship_add: tcgen05 int8 (default) and AND + POPCOUNT
+    (PSB_KIN_TC=0, read on every call)."""
+    if request.param == 'popcount':
+        monkeypatch.setenv('PSB_KIN_TC', '0')
+    else:
+        monkeypatch.delenv('PSB_KIN_TC', raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize('n,nv', [(50, 333), (333, 5000), (1000, 4097), (128, 128), (129, 1)])
+def test_kinship_matches_numpy(n, nv, kin_mode):
     from pyseer_b200.engine import Engine, synth_host, unpack_rows
     bits = synth_host(11, 0, nv, n, af_lo=0.0, af_hi=1.0)
     x = unpack_rows(bits, n).astype(np.int64)
@@ -29,6 +40,55 @@ def test_kinship_matches_numpy(n, nv):
     K = eng.kinship_fetch()
     eng.close()
     assert np.array_equal(K, ref.astype(float))
+
+
+def test_kinship_tensor_path_chunks_and_splits():
+    """More variants than one expansion chunk (65536), a sample count that leaves a ragged last
+    tile, fewer tiles than SMs (variant axis split over CTAs, 64-bit atomic adds) -- against BLAS in
+    float64 (exact: every entry < 2^53) and against the popcount path bit for bit."""
+    from pyseer_b200.engine import Engine, synth_host, unpack_rows
+    n, nv = 1300, 70001
+    bits = synth_host(5, 0, nv, n, af_lo=0.0, af_hi=1.0)
+    x = unpack_rows(bits, n)
+    af = x.sum(1) / float(n)
+    keep = ~((af < 0.02) | (af > 0.97))
+    G = x[keep].T.astype(np.float64)
+    ref = G @ G.T
+    out = {}
+    for mode in ('1', '0'):
+        os.environ['PSB_KIN_TC'] = mode
+        try:
+            eng = Engine(0)
+            eng.kinship_begin(n)
+            eng.kinship_add(bits, None, 0.02, 0.97, 0.05)
+            eng.kinship_add(bits[:1000], None, 0.02, 0.97, 0.05)      # a second, short batch
+            out[mode] = eng.kinship_fetch()
+            eng.close()
+        finally:
+            del os.environ['PSB_KIN_TC']
+    G2 = G[:, :int(keep[:1000].sum())]
+    assert np.array_equal(out['1'], ref + G2 @ G2.T)
+    assert np.array_equal(out['1'], out['0'])
+
+
+def test_kinship_tensor_path_many_tiles():
+    """N = 2500 (210 upper-triangular tiles: no split, ragged last tile), both paths bit for bit."""
+    from pyseer_b200.engine import Engine, synth_host
+    n, nv = 2500, 20000
+    bits = synth_host(9, 0, nv, n, af_lo=0.0, af_hi=1.0)
+    out = {}
+    for mode in ('1', '0'):
+        os.environ['PSB_KIN_TC'] = mode
+        try:
+            eng = Engine(0)
+            eng.kinship_begin(n)
+            eng.kinship_add(bits, None, 0.01, 0.99, 0.05)
+            out[mode] = eng.kinship_fetch()
+            eng.close()
+        finally:
+            del os.environ['PSB_KIN_TC']
+    assert out['1'].max() > 0 and np.array_equal(out['1'], out['1'].T)
+    assert np.array_equal(out['1'], out['0'])
 
 
 def test_similarity_tool_on_reference_kmers(tmp_path):
@@ -51,7 +111,7 @@ def test_similarity_tool_on_reference_kmers(tmp_path):
     assert np.array_equal(K.values, (G @ G.T).astype(float))
 
 
-def test_kinship_with_missing_genotypes():
+def test_kinship_with_missing_genotypes(kin_mode):
     """Missing calls count as absent (documented difference, pyseer_b200/similarity.py): the matrix
     equals the reference's G G' with NaN replaced by 0, for variants within --max-missing; the AF
     of the filter counts missing samples as carriers (input.py:439-446)."""
