@@ -303,13 +303,23 @@ int psb_reader_next(psb_reader *reader, int64_t max_variants, uint32_t *bits, ui
  * next name did not fit `names` (the line is kept for the next call; PSB_ERR_NOMEM when not even the
  * first name of a call fits: come back with a larger buffer). */
 int psb_reader_at_eof(psb_reader *reader, int32_t *at_eof);
+/* Compressed input (input.open_variant_file, input.py:268-298, reads it through Python's gzip): bgzip
+ * files are inflated block-parallel; PLAIN gzip files of 4 MB and more -- one serial deflate stream --
+ * are inflated on the reader's threads too (csrc/psb_pgz.cu: block starts searched per chunk, chunks
+ * decoded to 16-bit symbols with markers for the unknown 32 KiB window, only the chunks the serial
+ * chain confirms are kept, CRC-32 and length checked against the trailer; PSB_PGZ=0 selects zlib).
+ * psb_pgz_selftest inflates a whole gzip file that way on n_threads threads with chunk_bytes
+ * compressed bytes per work item (0: default 1 MiB) and reports the CRC-32 (NULL: not computed) and
+ * length of the text and stats[0..1] = work items decoded / thrown away; < 0 on a corrupt stream. */
+int psb_pgz_selftest(const char *path, int32_t n_threads, int64_t chunk_bytes, uint32_t *crc_out,
+                     int64_t *len_out, int64_t stats_out[2]);
 /* ---- k-mer text parsed on the device ------------------------------------------------ */
 /* input.py's k-mer streaming (pyseer/input.py:505-707 -> read_variant :377-388, :438-452) as a
  * page-locked host -> device staging pipeline: the host cuts the decompressed text into lines,
  * the GPU tokenises them.
  * psb_reader_next_text (var_type 0 readers): fills dst (dst_cap bytes; allocate it with
  * psb_host_alloc) with the text of up to max_lines lines, read straight into it (plain text:
- * pread on the reader's threads; bgzip: block-parallel inflate; gzip: zlib).  line_start[v] /
+ * pread on the reader's threads; bgzip: block-parallel inflate; gzip: chunk-parallel inflate, above).  line_start[v] /
  * line_len[v] locate line v inside dst without its newline and trailing blanks (empty lines are
  * skipped); names / name_off as psb_reader_next.  The *n_read lines occupy dst[0, *n_bytes).  A short
  * batch ends at the end of the file (psb_reader_at_eof) or where dst / names are full -- then *n_read is

@@ -22,9 +22,12 @@
 #include <vector>
 
 #include "psb_internal.cuh"
+#include "psb_pgz.h"
 
 struct psb_reader {
     gzFile fh = nullptr;
+    psb_pgz *pgz = nullptr;                 // plain gzip of some size: inflated on the parser threads (psb_pgz.cu)
+    bool pgz_err = false;
     FILE *raw = nullptr;                    // plain text, or BGZF input inflated block-parallel (bgzf_fill)
     bool bgzf = false;
     std::vector<unsigned char> bgzf_in;
@@ -163,7 +166,13 @@ static bool reader_fill(psb_reader *r) {
         r->len = got;
         return true;
     }
-    int got = gzread(r->fh, r->buf.data(), (unsigned)r->buf.size());
+    int64_t got;
+    if (r->pgz) {
+        got = psb_pgz_read(r->pgz, r->buf.data(), (int64_t)r->buf.size());
+        if (got < 0) r->pgz_err = true;
+    } else {
+        got = gzread(r->fh, r->buf.data(), (unsigned)r->buf.size());
+    }
     if (got <= 0) {
         r->eof = true;
         r->pos = r->len = 0;
@@ -204,15 +213,26 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
     const bool gz = fread(magic, 1, 2, raw) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
     rewind(raw);
     gzFile fh = nullptr;
+    psb_pgz *pgz = nullptr;
     if (gz && !bgzf) {
+        // files of some size go through the parallel inflater (PSB_PGZ=0: always zlib; PSB_PGZ_MIN /
+        // PSB_PGZ_CHUNK: size threshold and compressed bytes per work item, for the tests)
+        fseek(raw, 0, SEEK_END);
+        const long fsize = ftell(raw);
         fclose(raw);
         raw = nullptr;
-        fh = gzopen(path, "rb");
-        PSB_REQUIRE(fh, PSB_ERR_ARG, "cannot open %s", path);
-        gzbuffer(fh, 1 << 20);
+        const long pgz_min = getenv("PSB_PGZ_MIN") ? atol(getenv("PSB_PGZ_MIN")) : (4l << 20);
+        if (!(getenv("PSB_PGZ") && atoi(getenv("PSB_PGZ")) == 0) && fsize >= pgz_min)
+            pgz = psb_pgz_open(path, 1, getenv("PSB_PGZ_CHUNK") ? (size_t)atol(getenv("PSB_PGZ_CHUNK")) : 0);
+        if (!pgz) {
+            fh = gzopen(path, "rb");
+            PSB_REQUIRE(fh, PSB_ERR_ARG, "cannot open %s", path);
+            gzbuffer(fh, 1 << 20);
+        }
     }
     psb_reader *r = new psb_reader();
     r->fh = fh;
+    r->pgz = pgz;
     r->raw = raw;
     r->bgzf = bgzf;
     r->var_type = var_type;
@@ -226,6 +246,7 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
         // header: first field is the row label, the rest are sample names in column order
         if (!reader_getline(r)) {
             if (fh) gzclose(fh);
+            if (pgz) psb_pgz_close(pgz);
             if (raw) fclose(raw);
             delete r;
             psb_set_error("%s: empty Rtab file", path);
@@ -273,6 +294,7 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
         }
         if (!found) {
             if (fh) gzclose(fh);
+            if (pgz) psb_pgz_close(pgz);
             if (raw) fclose(raw);
             delete r;
             psb_set_error("%s: no #CHROM header line found; is this a VCF file?", path);
@@ -286,6 +308,7 @@ extern "C" int psb_reader_open(const char *path, int32_t var_type, const char *c
 extern "C" int psb_reader_close(psb_reader *r) {
     if (!r) return PSB_OK;
     if (r->fh) gzclose(r->fh);
+    if (r->pgz) psb_pgz_close(r->pgz);
     if (r->raw) fclose(r->raw);
     delete r;
     return PSB_OK;
@@ -468,6 +491,7 @@ static void parse_line(const psb_reader *r, const char *L, size_t len, uint32_t 
 extern "C" int psb_reader_set_threads(psb_reader *r, int32_t n_threads) {
     PSB_REQUIRE(r, PSB_ERR_ARG, "reader is NULL");
     r->n_threads = n_threads < 1 ? 1 : (n_threads > 64 ? 64 : n_threads);
+    if (r->pgz) psb_pgz_set_threads(r->pgz, r->n_threads);
     return PSB_OK;
 }
 
@@ -498,6 +522,7 @@ extern "C" int psb_reader_next(psb_reader *r, int64_t max_variants, uint32_t *bi
             r->have_pending = false;
         } else if (!reader_getline(r)) {
             PSB_REQUIRE(!r->bgzf_err, PSB_ERR_ARG, "corrupt BGZF block in the variant file");
+            PSB_REQUIRE(!r->pgz_err, PSB_ERR_ARG, "variant file: %s", psb_pgz_error(r->pgz));
             r->drained = true;
             break;
         }
@@ -683,6 +708,12 @@ static int64_t text_read_more(psb_reader *r, char *dst, int64_t want) {
         if (bad.load()) { r->bgzf_err = true; return -1; }
         return out_total;
     }
+    if (r->pgz) {
+        got = psb_pgz_read(r->pgz, dst, want);
+        if (got < 0) { r->pgz_err = true; return -1; }
+        if (got < want) r->text_eof = true;
+        return got;
+    }
     while (got < want) {
         const int k = gzread(r->fh, dst + got, (unsigned)std::min<int64_t>(want - got, 1 << 30));
         if (k <= 0) { r->text_eof = true; break; }
@@ -789,6 +820,7 @@ extern "C" int psb_reader_next_text(psb_reader *r, int64_t max_lines, int64_t li
         if (want > dst_cap - have) want = dst_cap - have;
         if (want <= 0 || (r->bgzf && want < (1 << 16))) { full = true; break; }
         const int64_t got = text_read_more(r, dst + have, want);
+        PSB_REQUIRE(got >= 0 || !r->pgz_err, PSB_ERR_ARG, "variant file: %s", psb_pgz_error(r->pgz));
         PSB_REQUIRE(got >= 0, PSB_ERR_ARG, "corrupt BGZF block in the variant file");
         if (got == 0 && !r->text_eof) { full = true; break; }     // BGZF: the next block does not fit
         have += got;

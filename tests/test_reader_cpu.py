@@ -392,3 +392,110 @@ def test_text_mode_keeps_its_text_when_a_buffer_is_too_small(tmp_path):
     names = [x for b in rd.text_batches(64, names_cap=8) for x in b.names]
     rd.close()
     assert names == ref
+
+
+# ---- plain gzip inflated on several threads (csrc/psb_pgz.cu) ----
+
+def _pgz(path, threads, chunk):
+    import ctypes
+    from pyseer_b200 import _lib
+    lib = _lib.load()
+    crc, n, st = ctypes.c_uint32(), ctypes.c_int64(), (ctypes.c_int64 * 2)()
+    rc = lib.psb_pgz_selftest(path.encode(), threads, chunk, ctypes.cast(ctypes.byref(crc), ctypes.c_void_p),
+                              ctypes.byref(n), st)
+    return rc, crc.value, n.value, list(st)
+
+
+def _kmer_text(n_lines, n_samples, seed):
+    rng = np.random.RandomState(seed)
+    toks = np.array(['sample_%d:1' % i for i in range(n_samples)])
+    acgt = np.array(list('ACGT'))
+    return ('\n'.join(''.join(rng.choice(acgt, size=31)) + ' | ' +
+                      ' '.join(toks[rng.uniform(size=n_samples) < rng.uniform(0.02, 0.98)])
+                      for _ in range(n_lines)) + '\n').encode()
+
+
+def test_parallel_gzip_equals_zlib(tmp_path):
+    """The chunk-parallel inflater against zlib's CRC-32 and length: k-mer text, incompressible bytes
+    (stored blocks), runs (long matches at distance 1), a mix, the empty and a tiny stream; compression
+    levels 1 / 6 / 9; one thread and several; chunks far smaller than a deflate block (most chunks find
+    no block start and are decoded by their predecessor) up to one chunk for the whole file."""
+    import zlib
+    cases = {'kmers': _kmer_text(700, 700, 1), 'random': os.urandom(1 << 20), 'zeros': b'\0' * (3 << 20),
+             'mixed': _kmer_text(150, 300, 2) + os.urandom(300000) + _kmer_text(150, 300, 3) + b'A' * 100000,
+             'empty': b'', 'tiny': b'hello\n'}
+    for name, data in cases.items():
+        want = (zlib.crc32(data) & 0xffffffff, len(data))
+        for level in (1, 6, 9):
+            path = str(tmp_path / ('%s_%d.gz' % (name, level)))
+            with open(path, 'wb') as fh:
+                fh.write(gzip.compress(data, level))
+            for threads, chunk in ((1, 0), (4, 4096), (8, 65536), (5, 20000)):
+                rc, crc, n, st = _pgz(path, threads, chunk)
+                assert rc == 0 and (crc, n) == want, (name, level, threads, chunk, rc, n)
+    # chunks of 64 KiB on the k-mer text: block starts are found and confirmed (work is shared)
+    rc, crc, n, st = _pgz(str(tmp_path / 'kmers_6.gz'), 4, 65536)
+    assert st[0] >= 4 and st[1] <= st[0] // 2, st
+
+
+def test_parallel_gzip_members_header_fields_and_corruption(tmp_path):
+    import subprocess
+    import zlib
+    a, b = _kmer_text(300, 400, 5), _kmer_text(200, 300, 6) + os.urandom(50000)
+    multi = str(tmp_path / 'multi.gz')
+    with open(multi, 'wb') as fh:                  # two members and zero padding, as `cat a.gz b.gz` gives
+        fh.write(gzip.compress(a, 6) + gzip.compress(b, 1) + b'\0' * 64)
+    for threads, chunk in ((1, 0), (4, 4096), (8, 65536)):
+        rc, crc, n, _ = _pgz(multi, threads, chunk)
+        assert rc == 0 and (crc, n) == (zlib.crc32(a + b) & 0xffffffff, len(a) + len(b))
+    named = tmp_path / 'named.txt'                 # gzip(1) stores the file name in the header
+    named.write_bytes(a)
+    subprocess.check_call(['gzip', '-k', str(named)])
+    rc, crc, n, _ = _pgz(str(named) + '.gz', 3, 30000)
+    assert rc == 0 and (crc, n) == (zlib.crc32(a) & 0xffffffff, len(a))
+    raw = bytearray(gzip.compress(a, 6))
+    for at in (len(raw) // 3, len(raw) // 2, len(raw) - 6):       # damaged data / damaged CRC
+        bad = bytearray(raw)
+        bad[at] ^= 0x41
+        p = str(tmp_path / ('bad%d.gz' % at))
+        with open(p, 'wb') as fh:
+            fh.write(bad)
+        with contextlib.redirect_stderr(io.StringIO()):
+            assert _pgz(p, 4, 16384)[0] < 0
+    trunc = str(tmp_path / 'trunc.gz')
+    with open(trunc, 'wb') as fh:
+        fh.write(raw[:len(raw) // 2])
+    assert _pgz(trunc, 4, 16384)[0] < 0
+
+
+def test_reader_on_parallel_gzip(tmp_path, monkeypatch):
+    """The row reader and the text reader over a gzip file through the parallel inflater (forced onto
+    the small fixture: PSB_PGZ_MIN=0, 8 KiB chunks) give what they give through zlib (PSB_PGZ=0)."""
+    p = _pheno()
+    with gzip.open(os.path.join(GOLDEN, 'kmers.gz'), 'rb') as fh:
+        text = fh.read() * 6
+    gz = str(tmp_path / 'k.gz')
+    with gzip.open(gz, 'wb') as fh:
+        fh.write(text)
+    out = {}
+    for tag, env in (('zlib', {'PSB_PGZ': '0'}), ('pgz', {'PSB_PGZ_MIN': '0', 'PSB_PGZ_CHUNK': '8192'})):
+        for k in ('PSB_PGZ', 'PSB_PGZ_MIN', 'PSB_PGZ_CHUNK'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for threads in (1, 4):
+            rd = VariantReader('kmers', gz, p, threads=threads)
+            with contextlib.redirect_stderr(io.StringIO()):
+                rows = [(b.names, b.bits.copy()) for b in rd.batches(250)]
+            rd.close()
+            rd = VariantReader('kmers', gz, p, threads=threads)
+            lines = _text_lines(rd, 250)
+            rd.close()
+            out[tag, threads] = (rows, lines)
+    ref_rows, ref_lines = out['zlib', 1]
+    assert sum(len(n) for n, _ in ref_rows) == 1200
+    for key, (rows, lines) in out.items():
+        assert lines == ref_lines, key
+        assert len(rows) == len(ref_rows), key
+        for (n1, b1), (n2, b2) in zip(ref_rows, rows):
+            assert n1 == n2 and np.array_equal(b1, b2), key
