@@ -46,6 +46,16 @@ def _write_part(job):
                 fh.write('K%08d | ' % (a + s) + ' '.join(tok[x[s] != 0]) + '\n')
     subprocess.check_call('gzip -1 -k -c %s > %s.gz' % (f, f), shell=True)
     write_bgzf(f + '.bgz', f)
+    # this part's share of ONE gzip member (what `gzip` or `pigz` make of the whole text): raw deflate,
+    # no final block, flushed to a byte boundary
+    co = zlib.compressobj(1, zlib.DEFLATED, -15)
+    with open(f, 'rb') as fi, open(f + '.gz1', 'wb') as fo:
+        while True:
+            blk = fi.read(16 << 20)
+            if not blk:
+                break
+            fo.write(co.compress(blk))
+        fo.write(co.flush(zlib.Z_FULL_FLUSH))
 
 
 def main():
@@ -75,8 +85,11 @@ def main():
     import multiprocessing as mp
     with mp.get_context('fork').Pool(min(cores, len(parts))) as pool:
         pool.map(_write_part, parts)
-    for ext in ('', '.gz', '.bgz'):
+    crc, total = 0, 0
+    for ext in ('', '.gz', '.bgz', '.gz1'):
         with open(txt + ext, 'wb') as fo:
+            if ext == '.gz1':
+                fo.write(b'\x1f\x8b\x08\x00' + b'\x00' * 4 + b'\x00\xff')
             for i in range(len(parts)):
                 f = os.path.join(d, 'part%04d.txt%s' % (i, ext))
                 with open(f, 'rb') as fi:
@@ -84,8 +97,13 @@ def main():
                         blk = fi.read(64 << 20)
                         if not blk:
                             break
+                        if ext == '':
+                            crc = zlib.crc32(blk, crc)
+                            total += len(blk)
                         fo.write(blk)
                 os.unlink(f)
+            if ext == '.gz1':                   # empty final block, CRC-32 and length of the whole text
+                fo.write(b'\x03\x00' + struct.pack('<II', crc & 0xffffffff, total & 0xffffffff))
     gen_s = time.time() - t0
     size_txt = os.path.getsize(txt)
     # (the device is touched only after the generator processes were forked)
@@ -103,7 +121,9 @@ def main():
 
     def run(extra, tag, text='1'):
         t = time.time()
-        env = dict(os.environ, PYSEER_B200_TIMING='1', PYSEER_B200_TEXT=text)
+        env = dict(os.environ, PYSEER_B200_TIMING='1', PYSEER_B200_TEXT='1' if text == 'zlib' else text)
+        if text == 'zlib':
+            env['PSB_PGZ'] = '0'                # the serial inflater, for comparison
         with open(os.devnull, 'w') as null:
             err = subprocess.run(base + extra, stdout=null, stderr=subprocess.PIPE, cwd=ROOT, env=env,
                                  check=True).stderr.decode()
@@ -127,6 +147,8 @@ def main():
     for tag, extra, text in (('plain_text_device_parser', ['--kmers', txt, '--uncompressed'], '1'),
                              ('bgzip_text_device_parser', ['--kmers', txt + '.bgz'], '1'),
                              ('gzip_text_device_parser', ['--kmers', txt + '.gz'], '1'),
+                             ('gzip_one_member_device_parser', ['--kmers', txt + '.gz1'], '1'),
+                             ('gzip_one_member_zlib_device_parser', ['--kmers', txt + '.gz1'], 'zlib'),
                              ('plain_text_host_parser', ['--kmers', txt, '--uncompressed'], '0'),
                              ('bgzip_text_host_parser', ['--kmers', txt + '.bgz'], '0'),
                              ('gzip_text_host_parser', ['--kmers', txt + '.gz'], '0'),
