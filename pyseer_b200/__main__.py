@@ -78,8 +78,10 @@ def get_options(argv=None):
     ot.add_argument('--gpus', type=int, default=1,
                     help='number of GPUs: batches of variants are dealt to the GPUs in input order and the '
                          'result tables gathered over NCCL on the first one (what --cpu is to pyseer)')
-    ot.add_argument('--gpu-batch', type=int, default=48000,
-                    help='variants per GPU submission (rounded to a multiple of --block_size)')
+    ot.add_argument('--gpu-batch', type=int, default=None,
+                    help='variants per GPU submission (rounded to a multiple of --block_size); default '
+                         '48000, or 12000 for k-mer text tokenised on the device (its page-locked text '
+                         'buffers stay small and more batches are in flight)')
     ot.add_argument('--lmm-precision', type=int, default=None,
                     help='0 = FP64 contraction, 3..7 = exact int8-slice tensor-core contraction, 46 = two '
                          'passes: 4 slices, 6 again for the far tail (default)')
@@ -259,7 +261,15 @@ def main(argv=None):
     out = sys.stdout
     nan = np.nan
     model_name = 'lmm' if o.lmm else 'seer'
-    gpu_batch = max(1, o.gpu_batch // o.block_size) * o.block_size
+    # k-mer text is tokenised on the device (psb_submit_text) unless something downstream needs the
+    # packed rows on the host: sample lists, lineage fits, pattern hashes, the packed cache
+    text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and \
+        not (o.print_samples or o.lineage or o.output_patterns or o.bits_cache) and \
+        os.environ.get('PYSEER_B200_TEXT', '1') != '0'
+    # measured at N = 5000 (profiles/r02_cli_batch_sweep.json): plain text streams at 84 k variants/s in
+    # batches of 24000 lines, 550 k/s in batches of 12000, 640 k/s in batches of 6000
+    gpu_batch = o.gpu_batch if o.gpu_batch else (12000 if text_mode else 48000)
+    gpu_batch = max(1, gpu_batch // o.block_size) * o.block_size
     counters = {'prefilter': 0, 'tested': 0, 'printed': 0}
 
     def samples_of(batch, j):
@@ -375,11 +385,6 @@ def main(argv=None):
                          lineage=(False if (o.lineage and not o.lmm) else None), comm=comm,
                          rows_max=gpu_batch)
     pool = None
-    # k-mer text is tokenised on the device (psb_submit_text) unless something downstream needs the
-    # packed rows on the host: sample lists, lineage fits, pattern hashes, the packed cache
-    text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and \
-        not (o.print_samples or o.lineage or o.output_patterns or o.bits_cache) and \
-        os.environ.get('PYSEER_B200_TEXT', '1') != '0'
     name_bytes = sum(len(x) for x in reader.samples) + 3 * reader.n_samples if text_mode else 0
     if text_mode and o.block_size * (name_bytes + 4096) > (2 << 30):
         text_mode = False      # one block of worst-case lines would not fit a 2 GB text buffer: host parser

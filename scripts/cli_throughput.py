@@ -64,6 +64,7 @@ def main():
     ap.add_argument('--kmers', type=int, default=40000)
     ap.add_argument('--cpu', type=int, default=0)
     ap.add_argument('--part', type=int, default=10000, help='k-mers per generator job')
+    ap.add_argument('--sweep', default='', help='comma-separated --gpu-batch values to try on the text formats')
     a = ap.parse_args()
     import benchdata
     from oracle import synth
@@ -158,6 +159,14 @@ def main():
         res['runs'][tag] = {'wall_s': w, 'variants_per_s_whole_run': m / w,
                             'variants_per_s_streaming': rate}
         sys.stderr.write('%s: %.2f s, streaming %s variants/s\n' % (tag, w, rate))
+    if a.sweep:
+        res['gpu_batch_sweep'] = {}
+        for gb in [int(x) for x in a.sweep.split(',')]:
+            for tag, extra in (('plain_text_device_parser', ['--kmers', txt, '--uncompressed']),
+                               ('gzip_one_member_device_parser', ['--kmers', txt + '.gz1'])):
+                w, rate = run(extra + ['--gpu-batch', str(gb)], tag, '1')
+                res['gpu_batch_sweep']['%s@%d' % (tag, gb)] = {'wall_s': w, 'variants_per_s_streaming': rate}
+                sys.stderr.write('%s gpu-batch %d: %.2f s, streaming %s variants/s\n' % (tag, gb, w, rate))
     print(json.dumps(res))
     for f in os.listdir(d):
         os.unlink(os.path.join(d, f))
