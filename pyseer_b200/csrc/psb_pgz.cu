@@ -548,19 +548,20 @@ void psb_pgz_close(psb_pgz *z) {
 }
 
 // Decodes the next batch into z->out.  false: error (z->err) or end of file (z->eof).
-static bool pgz_batch(psb_pgz *z) {
+// Whole chunks that fit `direct` (direct_cap bytes) are written there and counted in *direct_used;
+// the rest of the batch goes to z->out.
+static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *direct_used) {
     z->out_len = z->out_pos = 0;
+    *direct_used = 0;
     if (z->failed || z->eof) return false;
     const uint8_t *base = z->map, *end = z->map + z->size;
     const int T = std::min(z->n_threads, 32);        // work items per batch (symbol buffers: ~12-20 MB each)
-    const uint64_t cbits = (uint64_t)z->chunk_bytes * 8;
     const uint64_t total_bits = (uint64_t)z->size * 8;
     // nominal chunk boundaries: byte aligned, chunk_bytes apart, from the current position
     const uint64_t p0 = z->pos;
     std::vector<uint64_t> nominal(T + 1);
     nominal[0] = p0;
     for (int k = 1; k <= T; ++k) nominal[k] = std::min(total_bits, ((p0 >> 3) + (uint64_t)k * z->chunk_bytes) * 8);
-    (void)cbits;
     int n = T;
     while (n > 1 && nominal[n - 1] >= total_bits) --n;          // chunks that would start at the end of the file
     const uint64_t limit = nominal[n];
@@ -639,10 +640,18 @@ static bool pgz_batch(psb_pgz *z) {
     z->n_chunks += n;
     z->n_wasted += n - (int64_t)used.size();
     // ---- 4. windows (serial, 32 KiB per chunk), then markers -> bytes and CRC in parallel ----
-    size_t total = 0;
-    for (int k : used) {
-        ch[k].out_off = total;
-        total += ch[k].n;
+    // destinations: the leading chunks that fit the caller's buffer go straight there
+    size_t total = 0, n_direct = 0, direct_bytes = 0;
+    for (size_t u = 0; u < used.size(); ++u) {
+        Chunk &c = ch[used[u]];
+        if (n_direct == u && direct && direct_bytes + c.n <= direct_cap) {
+            c.out_off = direct_bytes;
+            direct_bytes += c.n;
+            ++n_direct;
+        } else {
+            c.out_off = total;
+            total += c.n;
+        }
     }
     if (total > z->out_cap) {
         free(z->out);
@@ -685,7 +694,7 @@ static bool pgz_batch(psb_pgz *z) {
                 const uint8_t *w = wins[u].data();
                 const size_t lowest = WIN - win_len[u];         // markers below this index name bytes that do not exist
                 const uint16_t *s = c.sym + WIN;
-                uint8_t *o = z->out + c.out_off;
+                uint8_t *o = ((size_t)u < n_direct ? direct : z->out) + c.out_off;
                 bool bad = false;
                 if (lowest > 0) {                               // only the first 32 KiB of a member can hold such markers
                     for (size_t i = 0; i < c.n; ++i) bad |= s[i] >= 0x8000u && (size_t)(s[i] & 0x7fffu) < lowest;
@@ -736,6 +745,7 @@ static bool pgz_batch(psb_pgz *z) {
         z->member_out += ch[k].n;
     }
     z->out_len = total;
+    *direct_used = direct_bytes;
     const Chunk &last = ch[used.back()];
     if (member_end) {
         const size_t tr = (size_t)(last.end >> 3);
@@ -764,10 +774,11 @@ int64_t psb_pgz_read(psb_pgz *z, char *dst, int64_t want) {
         if (z->out_pos == z->out_len) {
             if (z->failed) return -1;
             if (z->eof) break;
-            if (!pgz_batch(z)) {
-                if (z->failed) return -1;
-                break;
-            }
+            size_t direct = 0;
+            const bool ok = pgz_batch(z, (uint8_t *)dst + got, (size_t)(want - got), &direct);
+            if (z->failed) return -1;
+            got += (int64_t)direct;
+            if (!ok) break;
             continue;
         }
         const size_t n = std::min<size_t>((size_t)(want - got), z->out_len - z->out_pos);
@@ -783,7 +794,9 @@ extern "C" int psb_pgz_selftest(const char *path, int32_t n_threads, int64_t chu
                                 int64_t *len_out, int64_t stats_out[2]) {
     psb_pgz *z = psb_pgz_open(path, n_threads, (size_t)chunk_bytes);
     if (!z) return -1;
-    std::vector<char> buf((size_t)8 << 20);
+    // reads of an odd size of about 1 MiB: chunks that fit land in the caller's buffer, larger ones come
+    // through the reader's own buffer (PSB_PGZ_SELFTEST_BUF: another size, for timing)
+    std::vector<char> buf(getenv("PSB_PGZ_SELFTEST_BUF") ? (size_t)atol(getenv("PSB_PGZ_SELFTEST_BUF")) : ((size_t)1 << 20) + 4099);
     uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
     int64_t total = 0;
     int rc = 0;

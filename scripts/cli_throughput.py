@@ -167,6 +167,21 @@ def main():
                 w, rate = run(extra + ['--gpu-batch', str(gb)], tag, '1')
                 res['gpu_batch_sweep']['%s@%d' % (tag, gb)] = {'wall_s': w, 'variants_per_s_streaming': rate}
                 sys.stderr.write('%s gpu-batch %d: %.2f s, streaming %s variants/s\n' % (tag, gb, w, rate))
+    if a.sweep:
+        # the inflater alone (psb_pgz_selftest into a 256 MB buffer), phases on stderr
+        import ctypes
+        from pyseer_b200 import _lib
+        lib = _lib.load()
+        os.environ['PSB_PGZ_TIMES'] = '1'
+        os.environ['PSB_PGZ_SELFTEST_BUF'] = str(256 << 20)
+        res['inflate_only'] = {}
+        for th in (1, 4, 8, 16):
+            ln, st = ctypes.c_int64(), (ctypes.c_int64 * 2)()
+            t = time.time()
+            rc = lib.psb_pgz_selftest((txt + '.gz1').encode(), th, 0, None, ctypes.byref(ln), st)
+            dt = time.time() - t
+            res['inflate_only']['threads_%d' % th] = {'rc': rc, 's': dt, 'GB_per_s': ln.value / dt / 1e9, 'chunks': list(st)}
+            sys.stderr.write('inflate only, %d threads: %.2f s = %.2f GB/s %s\n' % (th, dt, ln.value / dt / 1e9, list(st)))
     print(json.dumps(res))
     for f in os.listdir(d):
         os.unlink(os.path.join(d, f))
