@@ -42,6 +42,9 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -269,8 +272,20 @@ struct Chunk {
 // Decodes blocks from bit `start` until a block boundary that is one of stops[] (ascending), or lies
 // at / beyond `limit`, or the member ends.  window_known: number of bytes before `start` that exist at
 // all (member start: 0) -- matches reaching further back are errors, not markers.
+constexpr uint64_t NONE = ~(uint64_t)0, PENDING = ~(uint64_t)0 - 1;
+
+// The starts the chunks of a batch found, published while the batch is being decoded: a chunk that
+// reaches the range of chunk j at a block boundary compares with live[j] (waiting for it if the
+// search of chunk j has not finished -- it started at the same time and takes a millisecond).
+struct LiveStarts {
+    const std::atomic<uint64_t> *start;     // [n]
+    const uint64_t *nominal;                // [n + 1]
+    int k, n;                               // this chunk, chunks in the batch
+};
+
 void decode_range(const uint8_t *base, const uint8_t *end, uint64_t start, const uint64_t *stops, int n_stops,
-                  uint64_t limit, uint64_t known_before, Chunk &c, const Tables &fixed, size_t max_blocks = ~(size_t)0) {
+                  uint64_t limit, uint64_t known_before, Chunk &c, const Tables &fixed, size_t max_blocks = ~(size_t)0,
+                  const LiveStarts *live = nullptr) {
     c.start = start;
     c.status = -1;
     c.n = 0;
@@ -285,14 +300,25 @@ void decode_range(const uint8_t *base, const uint8_t *end, uint64_t start, const
     BitIn in;
     in.init(base, end, start);
     Tables *dyn = new Tables;
-    int si = 0;
+    int si = 0, lj = live ? live->k : 0;
     size_t blocks = 0;
     for (;;) {
         const uint64_t pos = in.pos();
         if (in.cnt < 0) { c.why = "unexpected end of the deflate stream"; break; }
         if (blocks > 0) {
-            while (si < n_stops && stops[si] < pos) ++si;
-            if ((si < n_stops && stops[si] == pos) || pos >= limit || blocks >= max_blocks) {
+            bool at_stop = false;
+            if (live) {
+                while (lj + 1 < live->n && pos >= live->nominal[lj + 1]) ++lj;     // the chunk whose range holds pos
+                if (lj > live->k) {
+                    uint64_t s;
+                    while ((s = live->start[lj].load(std::memory_order_acquire)) == PENDING) std::this_thread::yield();
+                    at_stop = s == pos;
+                }
+            } else {
+                while (si < n_stops && stops[si] < pos) ++si;
+                at_stop = si < n_stops && stops[si] == pos;
+            }
+            if (at_stop || pos >= limit || blocks >= max_blocks) {
                 c.status = 0;
                 c.end = pos;
                 break;
@@ -450,6 +476,78 @@ uint64_t find_block(const uint8_t *base, const uint8_t *end, uint64_t from, uint
     return found;
 }
 
+// Worker threads kept for the life of a reader: a batch is three short parallel regions, and creating
+// 3 x 15 threads per 16 MB of input cost a sixth of the run.  run() hands items 0 .. n-1 to up to
+// `threads` threads (the caller is one of them) and returns when all are done.
+class WorkPool {
+  public:
+    ~WorkPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void run(int threads, int n, const std::function<void(int)> &f) {
+        if (threads > n) threads = n;
+        if (threads <= 1) {
+            for (int i = 0; i < n; ++i) f(i);
+            return;
+        }
+        while ((int)th_.size() < threads - 1) {
+            const int id = (int)th_.size();
+            th_.emplace_back([this, id]() { loop(id); });
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &f;
+            n_items_ = n;
+            next_.store(0);
+            want_ = threads - 1;
+            pending_ = want_;
+            ++gen_;
+        }
+        cv_work_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+  private:
+    void work() {
+        for (;;) {
+            const int i = next_.fetch_add(1);
+            if (i >= n_items_) return;
+            (*fn_)(i);
+        }
+    }
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return stop_ || (gen_ != seen && id < want_); });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) cv_done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_items_ = 0, want_ = 0, pending_ = 0;
+    std::atomic<int> next_{0};
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace
 
 struct psb_pgz {
@@ -470,6 +568,7 @@ struct psb_pgz {
     Tables fixed;
     int64_t n_chunks = 0, n_wasted = 0;
     std::vector<Chunk> pool;            // symbol buffers, kept from batch to batch
+    WorkPool workers;
     double t_phase[4] = {0, 0, 0, 0};   // seconds in: block search, decoding, windows, markers + CRC
 };
 
@@ -571,51 +670,27 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
         ch[k].status = -2;
         ch[k].n = 0;
     }
-    std::vector<uint64_t> starts(n, ~(uint64_t)0);
     const auto t0 = std::chrono::steady_clock::now();
-    starts[0] = p0;
-    // ---- 1. block starts ----
-    {
-        std::atomic<int> next(1);
-        auto work = [&]() {
-            for (;;) {
-                const int k = next.fetch_add(1);
-                if (k >= n) return;
-                starts[k] = find_block(base, end, nominal[k], nominal[k + 1], z->fixed);
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < std::min(T, n - 1); ++t) pool.emplace_back(work);
-        if (n > 1) work();
-        for (auto &th : pool) th.join();
-    }
-    const auto t1 = std::chrono::steady_clock::now();
-    // ---- 2. decode ----
+    // ---- 1 + 2. every chunk: find its block start (all but the first), publish it, decode ----
+    std::vector<std::atomic<uint64_t>> live(n);
+    live[0].store(p0);
+    for (int k = 1; k < n; ++k) live[k].store(PENDING);
+    z->workers.run(T, n, [&](int k) {
+        if (k > 0) live[k].store(find_block(base, end, nominal[k], nominal[k + 1], z->fixed), std::memory_order_release);
+        const uint64_t st = live[k].load();
+        if (st == NONE) return;
+        const LiveStarts ls = {live.data(), nominal.data(), k, n};
+        decode_range(base, end, st, nullptr, 0, limit, k == 0 ? (uint64_t)z->window_len : (uint64_t)WIN, ch[k],
+                     z->fixed, ~(size_t)0, &ls);
+    });
+    const auto t1 = t0;
     std::vector<uint64_t> stops;
     std::vector<int> stop_owner;
     for (int k = 1; k < n; ++k)
-        if (starts[k] != ~(uint64_t)0) {
-            stops.push_back(starts[k]);
+        if (live[k].load() != NONE) {
+            stops.push_back(live[k].load());
             stop_owner.push_back(k);
         }
-    {
-        std::atomic<int> next(0);
-        auto work = [&]() {
-            for (;;) {
-                const int k = next.fetch_add(1);
-                if (k >= n) return;
-                if (starts[k] == ~(uint64_t)0) continue;
-                // stops after this chunk's own start
-                size_t s0 = std::upper_bound(stops.begin(), stops.end(), starts[k]) - stops.begin();
-                decode_range(base, end, starts[k], stops.data() + s0, (int)(stops.size() - s0), limit,
-                             k == 0 ? (uint64_t)z->window_len : (uint64_t)WIN, ch[k], z->fixed);
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < std::min(T, n); ++t) pool.emplace_back(work);
-        work();
-        for (auto &th : pool) th.join();
-    }
     const auto t2 = std::chrono::steady_clock::now();
     // ---- 3. the chain of chunks the serial decoding confirms ----
     std::vector<int> used;
@@ -684,56 +759,45 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
         z->window_len = wl;
     }
     const auto t3 = std::chrono::steady_clock::now();
-    {
-        std::atomic<int> next(0);
-        auto work = [&]() {
-            for (;;) {
-                const int u = next.fetch_add(1);
-                if (u >= (int)used.size()) return;
-                Chunk &c = ch[used[u]];
-                const uint8_t *w = wins[u].data();
-                const size_t lowest = WIN - win_len[u];         // markers below this index name bytes that do not exist
-                const uint16_t *s = c.sym + WIN;
-                uint8_t *o = ((size_t)u < n_direct ? direct : z->out) + c.out_off;
-                bool bad = false;
-                if (lowest > 0) {                               // only the first 32 KiB of a member can hold such markers
-                    for (size_t i = 0; i < c.n; ++i) bad |= s[i] >= 0x8000u && (size_t)(s[i] & 0x7fffu) < lowest;
-                }
-                // symbol -> byte through one flat table (identity for literals, the window for markers);
-                // runs of 16 literals are packed without it
-                std::vector<uint8_t> lut(65536);
-                for (int b = 0; b < 256; ++b) lut[b] = (uint8_t)b;
-                memcpy(lut.data() + 0x8000, w, WIN);
-                const uint8_t *L = lut.data();
-                size_t i = 0;
+    z->workers.run(T, (int)used.size(), [&](int u) {
+        Chunk &c = ch[used[u]];
+        const uint8_t *w = wins[u].data();
+        const size_t lowest = WIN - win_len[u];         // markers below this index name bytes that do not exist
+        const uint16_t *s = c.sym + WIN;
+        uint8_t *o = ((size_t)u < n_direct ? direct : z->out) + c.out_off;
+        bool bad = false;
+        if (lowest > 0) {                               // only the first 32 KiB of a member can hold such markers
+            for (size_t i = 0; i < c.n; ++i) bad |= s[i] >= 0x8000u && (size_t)(s[i] & 0x7fffu) < lowest;
+        }
+        // symbol -> byte through one flat table (identity for literals, the window for markers);
+        // runs of 16 literals are packed without it
+        std::vector<uint8_t> lut(65536);
+        for (int b = 0; b < 256; ++b) lut[b] = (uint8_t)b;
+        memcpy(lut.data() + 0x8000, w, WIN);
+        const uint8_t *L = lut.data();
+        size_t i = 0;
 #if defined(__SSE2__)
-                for (; i + 16 <= c.n; i += 16) {
-                    const __m128i a = _mm_loadu_si128((const __m128i *)(s + i));
-                    const __m128i b = _mm_loadu_si128((const __m128i *)(s + i + 8));
-                    if (_mm_movemask_epi8(_mm_or_si128(a, b)) & 0xAAAA) {
-                        for (int j = 0; j < 16; ++j) o[i + j] = L[s[i + j]];
-                    } else {
-                        _mm_storeu_si128((__m128i *)(o + i), _mm_packus_epi16(a, b));
-                    }
-                }
-#endif
-                for (; i < c.n; ++i) o[i] = L[s[i]];
-                c.bad_marker = bad;
-                size_t done = 0;
-                uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
-                while (done < c.n) {
-                    const size_t step = std::min<size_t>(c.n - done, (size_t)1 << 30);
-                    crc = (uint32_t)crc32(crc, o + done, (uInt)step);
-                    done += step;
-                }
-                c.crc = crc;
+        for (; i + 16 <= c.n; i += 16) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(s + i));
+            const __m128i b = _mm_loadu_si128((const __m128i *)(s + i + 8));
+            if (_mm_movemask_epi8(_mm_or_si128(a, b)) & 0xAAAA) {
+                for (int j = 0; j < 16; ++j) o[i + j] = L[s[i + j]];
+            } else {
+                _mm_storeu_si128((__m128i *)(o + i), _mm_packus_epi16(a, b));
             }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < std::min<int>(T, (int)used.size()); ++t) pool.emplace_back(work);
-        work();
-        for (auto &th : pool) th.join();
-    }
+        }
+#endif
+        for (; i < c.n; ++i) o[i] = L[s[i]];
+        c.bad_marker = bad;
+        size_t done = 0;
+        uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
+        while (done < c.n) {
+            const size_t step = std::min<size_t>(c.n - done, (size_t)1 << 30);
+            crc = (uint32_t)crc32(crc, o + done, (uInt)step);
+            done += step;
+        }
+        c.crc = crc;
+    });
     const auto t4 = std::chrono::steady_clock::now();
     z->t_phase[0] += std::chrono::duration<double>(t1 - t0).count();
     z->t_phase[1] += std::chrono::duration<double>(t2 - t1).count();
