@@ -258,8 +258,10 @@ struct Chunk {
         return *this;
     }
     ~Chunk() { free(sym); }
+    size_t max_syms = (size_t)1 << 28;      // 512 MB of symbols: beyond that the serial inflater takes over
     bool reserve(size_t want) {
         if (want <= cap) return true;
+        if (want > max_syms + WIN + 8192) return false;
         size_t nc = std::max(want, cap + cap / 2 + 4096);
         uint16_t *q = (uint16_t *)realloc(sym, nc * sizeof(uint16_t));
         if (!q) return false;
@@ -569,6 +571,13 @@ struct psb_pgz {
     int64_t n_chunks = 0, n_wasted = 0;
     std::vector<Chunk> pool;            // symbol buffers, kept from batch to batch
     WorkPool workers;
+    size_t max_syms = (size_t)1 << 28;
+    // serial continuation (zlib from the last confirmed block boundary): taken when a chunk the chain
+    // needs could not be decoded here -- a stream this decoder mishandles, a chunk that inflates
+    // beyond the symbol budget -- so that only streams zlib rejects as well are reported corrupt
+    bool serial = false, zs_open = false;
+    z_stream zs;
+    int64_t n_serial = 0;               // bytes that came through the serial continuation
     double t_phase[4] = {0, 0, 0, 0};   // seconds in: block search, decoding, windows, markers + CRC
 };
 
@@ -619,6 +628,7 @@ psb_pgz *psb_pgz_open(const char *path, int n_threads, size_t chunk_bytes) {
     z->size = (size_t)st.st_size;
     z->n_threads = n_threads < 1 ? 1 : n_threads;
     if (chunk_bytes) z->chunk_bytes = chunk_bytes < 4096 ? 4096 : chunk_bytes;
+    if (getenv("PSB_PGZ_MAX_SYMS")) z->max_syms = (size_t)atol(getenv("PSB_PGZ_MAX_SYMS"));   // test hook
     fixed_tables(z->fixed);
     if (!pgz_header(z, 0)) {
         psb_pgz_close(z);
@@ -640,6 +650,7 @@ void psb_pgz_stats(const psb_pgz *z, int64_t out[2]) {
 
 void psb_pgz_close(psb_pgz *z) {
     if (!z) return;
+    if (z->zs_open) inflateEnd(&z->zs);
     if (z->map) munmap((void *)z->map, z->size);
     if (z->fd >= 0) close(z->fd);
     free(z->out);
@@ -669,6 +680,7 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
     for (int k = 0; k < n; ++k) {
         ch[k].status = -2;
         ch[k].n = 0;
+        ch[k].max_syms = z->max_syms;
     }
     const auto t0 = std::chrono::steady_clock::now();
     // ---- 1 + 2. every chunk: find its block start (all but the first), publish it, decode ----
@@ -699,9 +711,10 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
     for (;;) {
         Chunk &c = ch[cur];
         if (c.status < 0) {
-            z->err = std::string("corrupt gzip stream: ") + c.why;
-            z->failed = true;
-            return false;
+            // what was confirmed so far is delivered; zlib continues from the boundary this chunk started at
+            z->serial = true;
+            z->err = c.why;
+            break;
         }
         used.push_back(cur);
         if (c.status == 1) { member_end = true; break; }
@@ -714,6 +727,7 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
     }
     z->n_chunks += n;
     z->n_wasted += n - (int64_t)used.size();
+    if (used.empty()) return true;                              // nothing confirmed: the serial reader starts at z->pos
     // ---- 4. windows (serial, 32 KiB per chunk), then markers -> bytes and CRC in parallel ----
     // destinations: the leading chunks that fit the caller's buffer go straight there
     size_t total = 0, n_direct = 0, direct_bytes = 0;
@@ -811,6 +825,10 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
     z->out_len = total;
     *direct_used = direct_bytes;
     const Chunk &last = ch[used.back()];
+    if (z->serial) {
+        z->pos = last.end;                                      // a confirmed boundary; window and CRC are current
+        return true;
+    }
     if (member_end) {
         const size_t tr = (size_t)(last.end >> 3);
         if (tr + 8 > z->size) return pgz_fail(z, "corrupt gzip stream: truncated trailer");
@@ -831,12 +849,75 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
     return true;
 }
 
+// zlib from z->pos (a block boundary of the current member, window known) to the end of the file
+static int64_t pgz_serial_read(psb_pgz *z, char *dst, int64_t want) {
+    int64_t got = 0;
+    while (got < want) {
+        if (!z->zs_open) {
+            if (z->eof) break;
+            memset(&z->zs, 0, sizeof(z->zs));
+            if (inflateInit2(&z->zs, -15) != Z_OK) { pgz_fail(z, "inflateInit2 failed"); return -1; }
+            size_t byte = (size_t)(z->pos >> 3);
+            const int bit = (int)(z->pos & 7);
+            if (bit) {
+                inflatePrime(&z->zs, 8 - bit, z->map[byte] >> bit);
+                ++byte;
+            }
+            if (z->window_len)
+                inflateSetDictionary(&z->zs, z->window + (WIN - z->window_len), (uInt)z->window_len);
+            z->zs.next_in = const_cast<Bytef *>(z->map + byte);
+            z->zs.avail_in = 0;
+            z->zs_open = true;
+        }
+        if (z->zs.avail_in == 0) {
+            const size_t left = (size_t)((z->map + z->size) - z->zs.next_in);
+            z->zs.avail_in = (uInt)std::min<size_t>(left, (size_t)1 << 30);
+        }
+        const size_t room = (size_t)std::min<int64_t>(want - got, (int64_t)1 << 30);
+        z->zs.next_out = (Bytef *)dst + got;
+        z->zs.avail_out = (uInt)room;
+        const int rc = inflate(&z->zs, Z_NO_FLUSH);
+        const size_t made = room - z->zs.avail_out;
+        z->crc = (uint32_t)crc32(z->crc, (const Bytef *)dst + got, (uInt)made);
+        z->member_out += made;
+        z->n_serial += (int64_t)made;
+        got += (int64_t)made;
+        if (rc == Z_STREAM_END) {
+            const uint8_t *t = z->zs.next_in;
+            inflateEnd(&z->zs);
+            z->zs_open = false;
+            if (t + 8 > z->map + z->size) { pgz_fail(z, "corrupt gzip stream: truncated trailer"); return -1; }
+            const uint32_t want_crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            const uint32_t want_len = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+            if (want_crc != z->crc) { pgz_fail(z, "corrupt gzip stream: CRC-32 mismatch"); return -1; }
+            if (want_len != (uint32_t)(z->member_out & 0xffffffffu)) { pgz_fail(z, "corrupt gzip stream: length mismatch"); return -1; }
+            size_t nx = (size_t)(t + 8 - z->map);
+            while (nx < z->size && z->map[nx] == 0) ++nx;
+            if (nx >= z->size || !pgz_header(z, nx)) z->eof = true;
+        } else if (rc != Z_OK && !(rc == Z_BUF_ERROR && made > 0)) {
+            inflateEnd(&z->zs);
+            z->zs_open = false;
+            z->err = std::string("corrupt gzip stream: ") + (z->zs.msg ? z->zs.msg : (rc == Z_BUF_ERROR ? "unexpected end of file" : "inflate failed")) +
+                     (z->err.empty() ? std::string() : " (parallel decoder: " + z->err + ")");
+            z->failed = true;
+            return -1;
+        }
+    }
+    return got;
+}
+
 int64_t psb_pgz_read(psb_pgz *z, char *dst, int64_t want) {
     if (!z || want < 0) return -1;
     int64_t got = 0;
     while (got < want) {
         if (z->out_pos == z->out_len) {
             if (z->failed) return -1;
+            if (z->serial) {
+                const int64_t k = pgz_serial_read(z, dst + got, want - got);
+                if (k < 0) return -1;
+                got += k;
+                break;
+            }
             if (z->eof) break;
             size_t direct = 0;
             const bool ok = pgz_batch(z, (uint8_t *)dst + got, (size_t)(want - got), &direct);
@@ -874,6 +955,7 @@ extern "C" int psb_pgz_selftest(const char *path, int32_t n_threads, int64_t chu
     if (crc_out) *crc_out = crc;
     if (len_out) *len_out = total;
     if (stats_out) psb_pgz_stats(z, stats_out);
+    if (getenv("PSB_PGZ_TIMES") && z->n_serial) fprintf(stderr, "psb_pgz: %lld bytes through the serial continuation\n", (long long)z->n_serial);
     if (getenv("PSB_PGZ_TIMES"))
         fprintf(stderr, "psb_pgz phases: search %.3f decode %.3f windows %.3f resolve %.3f s\n", z->t_phase[0], z->t_phase[1],
                 z->t_phase[2], z->t_phase[3]);

@@ -438,6 +438,44 @@ def test_parallel_gzip_equals_zlib(tmp_path):
     assert st[0] >= 4 and st[1] <= st[0] // 2, st
 
 
+def test_parallel_gzip_falls_back_to_zlib(tmp_path, monkeypatch):
+    """A chunk the chain needs but that cannot be decoded here (test hook: a symbol budget of 200 k per
+    chunk) hands the stream to zlib at the last confirmed block boundary -- mid-member, at a bit offset,
+    with the 32 KiB window -- and the text, CRC-32 and length still come out right."""
+    import zlib
+    monkeypatch.setenv('PSB_PGZ_MAX_SYMS', '200000')
+    for name, data in (('kmers', _kmer_text(700, 700, 1)), ('zeros', b'\0' * (3 << 20)),
+                       ('two', None)):
+        path = str(tmp_path / (name + '.gz'))
+        if data is None:
+            a, b = _kmer_text(200, 300, 8), _kmer_text(300, 200, 9)
+            data = a + b
+            with open(path, 'wb') as fh:
+                fh.write(gzip.compress(a, 6) + gzip.compress(b, 9))
+        else:
+            with open(path, 'wb') as fh:
+                fh.write(gzip.compress(data, 6))
+        for threads, chunk in ((1, 0), (4, 8192), (8, 65536)):
+            rc, crc, n, _ = _pgz(path, threads, chunk)
+            assert rc == 0 and (crc, n) == (zlib.crc32(data) & 0xffffffff, len(data)), (name, threads, chunk, rc, n)
+    # the switch in the middle of a member: k-mer text decodes within a budget of 1 M symbols per chunk,
+    # the run of zeros behind it does not
+    monkeypatch.setenv('PSB_PGZ_MAX_SYMS', '1000000')
+    data = _kmer_text(700, 700, 1) + b'\0' * (8 << 20) + _kmer_text(100, 100, 2)
+    path = str(tmp_path / 'mid.gz')
+    with open(path, 'wb') as fh:
+        fh.write(gzip.compress(data, 6))
+    for threads, chunk in ((2, 30000), (8, 16384)):
+        rc, crc, n, _ = _pgz(path, threads, chunk)
+        assert rc == 0 and (crc, n) == (zlib.crc32(data) & 0xffffffff, len(data))
+    bad = bytearray(gzip.compress(_kmer_text(400, 300, 4), 6))
+    bad[len(bad) // 2] ^= 0x10
+    with open(str(tmp_path / 'bad.gz'), 'wb') as fh:
+        fh.write(bad)
+    with contextlib.redirect_stderr(io.StringIO()):
+        assert _pgz(str(tmp_path / 'bad.gz'), 4, 8192)[0] < 0
+
+
 def test_parallel_gzip_members_header_fields_and_corruption(tmp_path):
     import subprocess
     import zlib
