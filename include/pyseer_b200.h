@@ -374,6 +374,11 @@ int psb_format_rows(int32_t model, int64_t n_variants, const char *names, const 
 int psb_hash_patterns(const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
                       int32_t words_per_row, int32_t n_samples, const uint32_t *flags, char *out,
                       int64_t *n_out);
+/* The same hashes computed on the device from the rows of the batch last submitted / run (one thread
+ * per row, the 8 N byte message generated from the packed bits on the fly): out = n_variants x 16
+ * bytes, the MD5 digest of each row's vector k (int64 0/1, or float64 with NaN when the row has a
+ * missing genotype); base64 of a digest + '\n' is the reference's 25-byte entry. */
+int psb_pattern_digests(psb_ctx *ctx, uint8_t *out);
 
 /* ---- measurement ------------------------------------------------------------- */
 /* Work counters of the last psb_run_fixed: [0] Newton evaluations (passes over the samples)

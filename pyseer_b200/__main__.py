@@ -9,6 +9,7 @@ the native k-mer / Rtab reader, ``--bits-cache`` keeps the packed rows for later
 Whole-genome models (``--wg``) are not part of this path and are rejected with a message.
 """
 import argparse
+from binascii import b2a_base64
 import operator
 import os
 import sys
@@ -262,9 +263,10 @@ def main(argv=None):
     nan = np.nan
     model_name = 'lmm' if o.lmm else 'seer'
     # k-mer text is tokenised on the device (psb_submit_text) unless something downstream needs the
-    # packed rows on the host: sample lists, lineage fits, pattern hashes, the packed cache
+    # packed rows on the host: sample lists, lineage fits, the packed cache (pattern hashes do not:
+    # psb_pattern_digests computes them where the rows are)
     text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and \
-        not (o.print_samples or o.lineage or o.output_patterns or o.bits_cache) and \
+        not (o.print_samples or o.lineage or o.bits_cache) and \
         os.environ.get('PYSEER_B200_TEXT', '1') != '0'
     # measured at N = 5000 (profiles/r02_cli_batch_sweep.json): plain text streams at 84 k variants/s in
     # batches of 24000 lines, 550 k/s in batches of 12000, 640 k/s in batches of 6000
@@ -298,7 +300,11 @@ def main(argv=None):
             out.write(text.decode())
             if patterns is not None:
                 # hash_pattern of every tested variant, in input order (__main__.py:559-560)
-                patterns.write(hash_patterns(batch.bits, batch.missing, reader.n_samples, flags))
+                if batch.digests is not None:
+                    keep = (np.asarray(flags[:batch.n]) & _lib.F_PREFILTER) == 0
+                    patterns.write(b''.join(b2a_base64(d.tobytes()) for d in batch.digests[:batch.n][keep]))
+                else:
+                    patterns.write(hash_patterns(batch.bits, batch.missing, reader.n_samples, flags))
             return
         # the reference emits each block of --block_size variants as: filtered ones first
         # (LMM only, lmm.py:158-226), then the tested ones; fixed effects keep input order
@@ -324,7 +330,8 @@ def main(argv=None):
                 else:
                     counters['tested'] += 1
                     if patterns is not None:
-                        patterns.write(hash_pattern(reader.k_vector(batch, j)))
+                        patterns.write(b2a_base64(batch.digests[j].tobytes()) if batch.digests is not None
+                                       else hash_pattern(reader.k_vector(batch, j)))
                     if (f & _lib.F_FILTER) and not o.print_filtered:
                         continue
                 ks, nks = samples_of(batch, j)
@@ -383,7 +390,7 @@ def main(argv=None):
         comm = Comm.local(engines)
     runner = BatchRunner(engines, run_one, n_betas=n_betas,
                          lineage=(False if (o.lineage and not o.lmm) else None), comm=comm,
-                         rows_max=gpu_batch)
+                         rows_max=gpu_batch, digests=patterns is not None)
     pool = None
     name_bytes = sum(len(x) for x in reader.samples) + 3 * reader.n_samples if text_mode else 0
     if text_mode and o.block_size * (name_bytes + 4096) > (2 << 30):

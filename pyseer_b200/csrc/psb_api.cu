@@ -134,6 +134,7 @@ int psb_destroy(psb_ctx *c) {
     psb_kinship_release(c);
     psb_burden_release(c);
     psb_text_release(c);
+    psb_patterns_release(c);
     psb_free_model(c);
     free_tables(c);
     for (int i = 0; i < 2; ++i) {

@@ -186,6 +186,8 @@ struct psb_ctx {
     int64_t fetch_S[2] = {0, 0};
     int *h_counters[2] = {nullptr, nullptr};        // pinned: counters of the fetched run
     void *kin = nullptr;          // psb_kinship.cu state
+    void *d_dig = nullptr;        // psb_patterns.cu: MD5 digests of the batch's rows
+    int64_t dig_cap = 0;
     void *text = nullptr;         // psb_text.cu state (device k-mer text parser)
 
     // ---- burden regions (psb_burden.cu) ----
@@ -207,6 +209,7 @@ int psb_free_model(psb_ctx *ctx);
 void psb_kinship_release(psb_ctx *ctx);
 void psb_burden_release(psb_ctx *ctx);
 void psb_text_release(psb_ctx *ctx);
+void psb_patterns_release(psb_ctx *ctx);
 
 // psb_varstats.cu
 int psb_launch_bitsums(psb_ctx *ctx);

@@ -311,6 +311,14 @@ class Engine(object):
                                          miss.ctypes.data_as(c_void_p), byref(has)))
         return bits, (miss if has.value else None)
 
+    def pattern_digests(self):
+        """MD5 digests (n x 16 uint8) of the vectors ``input.hash_pattern`` hashes, for every row of
+        the batch last submitted / run, computed on the device (``psb_pattern_digests``)."""
+        _, _, n, _ = self.submitted_device()
+        out = np.zeros((n, 16), dtype=np.uint8)
+        check(self.lib.psb_pattern_digests(self._ctx, out.ctypes.data_as(c_void_p)))
+        return out
+
     def submit_device(self, d_bits_ptr, n_variants, wpr, d_missing_ptr=None):
         check(self.lib.psb_submit_device(self._ctx, c_void_p(d_bits_ptr),
                                          c_void_p(d_missing_ptr) if d_missing_ptr else None,

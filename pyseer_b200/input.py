@@ -135,7 +135,7 @@ def hash_patterns(bits, missing, n_samples, flags=None):
 
 class VariantBatch(object):
     """``n`` variants as packed rows plus what the result loop needs to print them."""
-    __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped', 'text', 'info']
+    __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped', 'text', 'info', 'digests']
 
     def __init__(self, names, bits, missing):
         self.names = names
@@ -146,6 +146,7 @@ class VariantBatch(object):
         self.skipped = None        # bool mask: records the reference never hands to a model
         self.text = None           # (uint8 text, n_bytes, line_start, line_len): rows are built on the device
         self.info = None           # ... and their per-line flags (Engine.text_info), set by the runner
+        self.digests = None        # ... and the MD5 digests of their patterns (Engine.pattern_digests), on request
 
 
 class VariantReader(object):

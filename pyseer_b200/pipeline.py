@@ -182,9 +182,10 @@ class BatchRunner(object):
     engine; ``lineage``: None, or the ``lmm_rule`` flag of ``Engine.run_lineage`` (fixed effects:
     False) whose result is attached to ``results.lineage``."""
 
-    def __init__(self, engines, run, n_betas=0, lineage=None, comm=None, rows_max=0):
+    def __init__(self, engines, run, n_betas=0, lineage=None, comm=None, rows_max=0, digests=False):
         self.engines = list(engines)
-        self.run = run
+        self._run = run
+        self.digests = digests          # --output-patterns on batches parsed on the device
         self.n_betas = n_betas
         self.lineage = lineage
         self.comm = comm if len(self.engines) > 1 else None
@@ -195,6 +196,13 @@ class BatchRunner(object):
         if self._pool is not None:
             self._pool.shutdown()
             self._pool = None
+
+    def run(self, eng, b=None):
+        """Queues the model run for the rows last submitted to ``eng``; a batch whose rows only exist on
+        the device gets the MD5 digests of its patterns (``psb_pattern_digests``) while they are there."""
+        self._run(eng)
+        if self.digests and b is not None and b.bits is None:
+            b.digests = eng.pattern_digests()
 
     def _fetch(self, eng, b):
         r = eng.fetch()
@@ -219,7 +227,7 @@ class BatchRunner(object):
                 submit_batch(eng, b)                   # H2D of batch k+1 on the copy stream ...
                 if prev is not None:
                     yield prev, self._fetch(eng, prev)  # ... while batch k finishes and comes back
-                self.run(eng)
+                self.run(eng, b)
                 prev = b
             if prev is not None:
                 yield prev, self._fetch(eng, prev)
@@ -237,7 +245,7 @@ class BatchRunner(object):
                         yield inflight, fetcher.wait()
                     fetcher.begin(prev.n)
                     inflight = prev
-                self.run(eng)
+                self.run(eng, b)
                 prev = b
             if inflight is not None:
                 yield inflight, fetcher.wait()
@@ -266,7 +274,7 @@ class BatchRunner(object):
                 submit_batch(self.engines[g], b)
 
         def run_group(grp):
-            list(self._pool.map(self.run, self.engines[:len(grp)]))
+            list(self._pool.map(self.run, self.engines[:len(grp)], grp))
             # the NCCL gather needs every rank: a short last super-step (fewer batches than GPUs)
             # and runs with lineage effects are fetched from their own GPUs instead
             use_gather = self.comm is not None and len(grp) == n and self.lineage is None

@@ -150,6 +150,10 @@ def main():
                              ('gzip_text_device_parser', ['--kmers', txt + '.gz'], '1'),
                              ('gzip_one_member_device_parser', ['--kmers', txt + '.gz1'], '1'),
                              ('gzip_one_member_zlib_device_parser', ['--kmers', txt + '.gz1'], 'zlib'),
+                             ('plain_text_device_parser_output_patterns',
+                              ['--kmers', txt, '--uncompressed', '--output-patterns', os.path.join(d, 'pat1.txt')], '1'),
+                             ('plain_text_host_parser_output_patterns',
+                              ['--kmers', txt, '--uncompressed', '--output-patterns', os.path.join(d, 'pat0.txt')], '0'),
                              ('plain_text_host_parser', ['--kmers', txt, '--uncompressed'], '0'),
                              ('bgzip_text_host_parser', ['--kmers', txt + '.bgz'], '0'),
                              ('gzip_text_host_parser', ['--kmers', txt + '.gz'], '0'),

@@ -1,8 +1,8 @@
 #!/bin/bash
 # round-end rehearsal (what the driver runs) on one GPU: the whole -m gpu suite, smoke, default bench, reference arm
 cd "$GRAFT_REPO_ROOT" || exit 1
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2t_tests.log 2>&1
-echo "exit $?" >> gpurun_out/r2t_tests.log; tail -5 gpurun_out/r2t_tests.log | cut -c1-300
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2y_tests.log 2>&1
+echo "exit $?" >> gpurun_out/r2y_tests.log; tail -5 gpurun_out/r2y_tests.log | cut -c1-300
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py > gpurun_out/r02_bench_default.json 2> gpurun_out/r02_bench_default.err
 echo "bench exit $?"

@@ -66,6 +66,13 @@ class _FakeEngine(object):
     def text_info(self, n_lines):
         return self._cur_info[:n_lines]
 
+    def pattern_digests(self):
+        # psb_pattern_digests' contract: md5 of the vector k the reference hashes (input.py:710-723)
+        import hashlib
+        bits, miss = self._sub
+        return np.array([np.frombuffer(hashlib.md5(_k_of(bits, miss, j, self._n).tobytes()).digest(), dtype=np.uint8)
+                         for j in range(bits.shape[0])]).reshape(-1, 16)
+
     def run_fixed(self, min_af, max_af, max_missing, filter_pvalue, lrt_pvalue, continuous):
         self._cur_info = self._info
         self._res = _fake_run_fixed_bits(self.fixed_model, self._sub[0], self._sub[1], filter_pvalue,

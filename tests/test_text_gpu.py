@@ -158,3 +158,56 @@ def test_cli_prints_the_same_with_and_without_device_parser(tmp_path, monkeypatc
     for key, (a, b) in outs.items():
         assert a[0] == b[0], key
         assert sorted(a[1].split('\n')) == sorted(b[1].split('\n')), key
+
+
+@pytest.mark.parametrize('n', [1, 7, 8, 9, 50, 55, 56, 57, 63, 64, 65, 333, 5000])
+def test_pattern_digests_equal_host_hashes(n):
+    """psb_pattern_digests (one thread per row, the 8 N byte message generated from the packed bits)
+    against hashlib on the vector the reference hashes (input.py:710-723: int64 0/1, float64 with NaN
+    for rows with a missing genotype) and against the host psb_hash_patterns, for every tail length of
+    the last MD5 block."""
+    import hashlib
+    from binascii import b2a_base64
+    from pyseer_b200.engine import pack_rows
+    from pyseer_b200.input import hash_patterns
+    rng = np.random.RandomState(n)
+    nv = 300
+    k = (rng.uniform(size=(nv, n)) < rng.uniform(0.05, 0.95, size=(nv, 1))).astype(float)
+    k[rng.uniform(size=(nv, n)) < 0.01] = np.nan
+    k[::2] = np.nan_to_num(k[::2])                      # every second row without missing genotypes
+    bits, miss = pack_rows(k)
+    if miss is None:
+        miss = np.zeros_like(bits)
+    eng = _engine(n)
+    for m in (miss, None):
+        kk = k if m is not None else np.nan_to_num(k)
+        eng.submit(bits, m)
+        dig = eng.pattern_digests()
+        assert dig.shape == (nv, 16)
+        for v in range(nv):
+            vec = kk[v] if np.isnan(kk[v]).any() else kk[v].astype(np.int64)
+            assert dig[v].tobytes() == hashlib.md5(vec.tobytes()).digest(), (n, v)
+        assert b''.join(b2a_base64(d.tobytes()) for d in dig) == hash_patterns(bits, m, n)
+    eng.close()
+
+
+def test_cli_output_patterns_through_device_parser(tmp_path, monkeypatch):
+    """--output-patterns with the k-mer text tokenised on the device (hashes from psb_pattern_digests)
+    writes the same file as the host path (rows parsed and hashed on the host)."""
+    from pyseer_b200.__main__ import main
+    G = lambda f: os.path.join(GOLDEN, f)   # noqa: E731
+    files = {}
+    for mode in ('1', '0'):
+        for extra in (['--lmm', '--similarity', G('similarity50.tsv')],
+                      ['--distances', G('distances50.tsv'), '--max-dimensions', '3']):
+            monkeypatch.setenv('PYSEER_B200_TEXT', mode)
+            pat = str(tmp_path / ('patterns_%s_%s.txt' % (mode, extra[0].strip('-'))))
+            out, err = io.StringIO(), io.StringIO()
+            with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+                rc = main(['--kmers', G('kmers.gz'), '--phenotypes', G('subset.pheno'), '--gpu-batch', '30',
+                           '--block_size', '10', '--output-patterns', pat] + extra)
+            assert rc == 0
+            files.setdefault(extra[0], []).append((open(pat, 'rb').read(), out.getvalue()))
+    for key, (a, b) in files.items():
+        assert a[0] == b[0] and len(a[0]) > 25 * 100, key
+        assert a[1] == b[1], key
