@@ -160,7 +160,7 @@ def test_cli_prints_the_same_with_and_without_device_parser(tmp_path, monkeypatc
         assert sorted(a[1].split('\n')) == sorted(b[1].split('\n')), key
 
 
-@pytest.mark.parametrize('n', [1, 7, 8, 9, 50, 55, 56, 57, 63, 64, 65, 333, 5000])
+@pytest.mark.parametrize('n', [3, 7, 8, 9, 50, 55, 56, 57, 63, 64, 65, 333, 5000])
 def test_pattern_digests_equal_host_hashes(n):
     """psb_pattern_digests (one thread per row, the 8 N byte message generated from the packed bits)
     against hashlib on the vector the reference hashes (input.py:710-723: int64 0/1, float64 with NaN
