@@ -21,7 +21,7 @@ from . import __version__
 from . import _lib
 from . import classes as var_obj
 from .engine import notes_from_flags
-from .input import (VariantReader, open_variants, VcfReader, hash_pattern, hash_patterns, load_covariates, load_lineage,
+from .input import (VariantReader, CachedVariantReader, open_variants, VcfReader, hash_pattern, hash_patterns, load_covariates, load_lineage,
                     load_phenotypes, load_structure)
 from .utils import format_output, format_table
 
@@ -406,7 +406,7 @@ def main(argv=None):
             e.text_setup(reader.samples)
         pool = pipeline.TextPool(2 * n_gpus + 2, gpu_batch, text_bytes)
         source = reader.text_batches(gpu_batch, block_size=o.block_size, pool=pool)
-    elif isinstance(reader, VariantReader):
+    elif isinstance(reader, (VariantReader, CachedVariantReader)):
         pool = pipeline.PinnedPool(5 * n_gpus + 3, gpu_batch, reader.W, reader.var_type == 'Rtab')
         source = reader.batches(gpu_batch, pool=pool)
     else:

@@ -383,6 +383,7 @@ class CachedVariantReader(object):
         self.W = words_per_row(self.n_samples)
         self.fh = open(path, 'rb')
         self.header = json.loads(self.fh.readline().decode())
+        self._data_pos = self.fh.tell()             # first chunk
         self.var_type = self.header['var_type']
 
     def close(self):
@@ -390,46 +391,71 @@ class CachedVariantReader(object):
             self.fh.close()
             self.fh = None
 
-    def _chunks(self):
-        W = self.W
-        while True:
-            head = np.frombuffer(self.fh.read(24), dtype='<i8')
-            if head.shape[0] < 3 or head[0] == 0:
+    def batches(self, size, pool=None):
+        """Batches of exactly ``size`` variants (the last one shorter), the rows read STRAIGHT into the
+        batch's buffers with ``pread`` -- page-locked ones when ``pool`` hands them out (``pool.get() ->
+        (bits, missing_or_None, token)``), so that ``psb_submit`` is a plain DMA; no intermediate copies."""
+        W, fd = self.W, self.fh.fileno()
+        row_bytes = W * 4
+        pos = self._data_pos
+        # the chunk being consumed: rows, names, file offsets of its bits / missing rows, rows taken
+        n = taken = 0
+        cnames, bits_off, miss_off = [], 0, None
+
+        def read_into(arr, off):
+            mv = memoryview(arr).cast('B')
+            done = 0
+            while done < len(mv):
+                k = os.preadv(fd, [mv[done:]], off + done)
+                if k <= 0:
+                    raise IOError('packed cache truncated')
+                done += k
+
+        at_end = False
+        while not at_end:
+            token = None
+            if pool is not None:
+                bits, miss, token = pool.get()
+            else:
+                bits, miss = np.empty((size, W), dtype=np.uint32), None
+            names, filled, any_m = [], 0, False
+            while filled < size:
+                if taken == n:
+                    head = np.frombuffer(os.pread(fd, 24, pos), dtype='<i8')
+                    if head.shape[0] < 3 or head[0] == 0:
+                        at_end = True
+                        break
+                    n, nb, has_m = int(head[0]), int(head[1]), int(head[2])
+                    cnames = os.pread(fd, nb, pos + 24).decode().split('\0')[:n]
+                    bits_off = pos + 24 + nb
+                    miss_off = bits_off + n * row_bytes if has_m else None
+                    pos = bits_off + n * row_bytes * (2 if has_m else 1)
+                    taken = 0
+                k = min(size - filled, n - taken)
+                read_into(bits[filled:filled + k], bits_off + taken * row_bytes)
+                if miss_off is not None:
+                    if miss is None:
+                        miss = np.zeros((size, W), dtype=np.uint32)
+                    elif not any_m:
+                        miss[:filled] = 0
+                    read_into(miss[filled:filled + k], miss_off + taken * row_bytes)
+                    any_m = True
+                elif any_m:
+                    miss[filled:filled + k] = 0
+                names.extend(cnames[taken:taken + k])
+                taken += k
+                filled += k
+            if filled == 0:
+                if pool is not None:
+                    pool.put(token)
                 return
-            n, nb, has_m = int(head[0]), int(head[1]), int(head[2])
-            names = self.fh.read(nb).decode().split('\0')[:n]
-            bits = np.frombuffer(self.fh.read(n * W * 4), dtype='<u4').reshape(n, W)
-            miss = np.frombuffer(self.fh.read(n * W * 4), dtype='<u4').reshape(n, W) if has_m else None
-            yield names, bits, miss
-
-    def batches(self, size):
-        names, bits, miss = [], [], []
-
-        def flush(k):
-            b = np.concatenate(bits) if len(bits) > 1 else bits[0]
-            any_m = any(m is not None for m in miss)
-            m = None
-            if any_m:
-                m = np.concatenate([mm if mm is not None else np.zeros_like(bb) for mm, bb in zip(miss, bits)])
-            out = VariantBatch(names[:k], np.ascontiguousarray(b[:k]),
-                               np.ascontiguousarray(m[:k]) if m is not None and m[:k].any() else None)
-            rest_b, rest_m = b[k:], (m[k:] if m is not None else None)
-            del names[:k]
-            bits[:] = [rest_b] if rest_b.shape[0] else []
-            miss[:] = [rest_m] if rest_b.shape[0] else []
-            empty = ~(out.bits.any(axis=1) | (out.missing.any(axis=1) if out.missing is not None else False))
+            m = miss[:filled] if any_m and miss[:filled].any() else None
+            out = VariantBatch(names, bits[:filled], m)
+            out.token = token
+            empty = ~(out.bits.any(axis=1) | (m.any(axis=1) if m is not None else False))
             for i in np.nonzero(empty)[0]:
                 sys.stderr.write('No observations of ' + out.names[i] + ' in selected samples\n')
-            return out
-
-        for nm, b, m in self._chunks():
-            names.extend(nm)
-            bits.append(b)
-            miss.append(m)
-            while len(names) >= size:
-                yield flush(size)
-        if names:
-            yield flush(len(names))
+            yield out
 
     sample_lists = VariantReader.sample_lists
     k_vector = VariantReader.k_vector
