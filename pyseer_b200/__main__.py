@@ -280,9 +280,9 @@ def main(argv=None):
     def emit(batch, r):
         """Result loop of main() (__main__.py:547-568, 783-803) for one batch."""
         flags = r.flags
-        if batch.text is not None:
-            # batch parsed on the device: what the host reader reports while it reads (a k-mer row has
-            # no missing genotypes, so "no observation" is carriers == 0)
+        if batch.text is not None or batch.report_empty:
+            # batch parsed on the device, or read from the packed cache: what the host reader reports while
+            # it reads (a row without missing genotypes: "no observation" is carriers == 0)
             for i in np.nonzero(r.carriers[:batch.n] == 0)[0]:
                 sys.stderr.write('No observations of ' + batch.names[i] + ' in selected samples\n')
         if batch.skipped is not None and batch.skipped.any():
@@ -406,7 +406,10 @@ def main(argv=None):
             e.text_setup(reader.samples)
         pool = pipeline.TextPool(2 * n_gpus + 2, gpu_batch, text_bytes)
         source = reader.text_batches(gpu_batch, block_size=o.block_size, pool=pool)
-    elif isinstance(reader, (VariantReader, CachedVariantReader)):
+    elif isinstance(reader, CachedVariantReader):
+        pool = pipeline.PinnedPool(5 * n_gpus + 3, gpu_batch, reader.W, reader.var_type == 'Rtab')
+        source = reader.batches(gpu_batch, pool=pool, defer_empty=True)
+    elif isinstance(reader, VariantReader):
         pool = pipeline.PinnedPool(5 * n_gpus + 3, gpu_batch, reader.W, reader.var_type == 'Rtab')
         source = reader.batches(gpu_batch, pool=pool)
     else:

@@ -135,7 +135,7 @@ def hash_patterns(bits, missing, n_samples, flags=None):
 
 class VariantBatch(object):
     """``n`` variants as packed rows plus what the result loop needs to print them."""
-    __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped', 'text', 'info', 'digests']
+    __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped', 'text', 'info', 'digests', 'report_empty']
 
     def __init__(self, names, bits, missing):
         self.names = names
@@ -147,6 +147,7 @@ class VariantBatch(object):
         self.text = None           # (uint8 text, n_bytes, line_start, line_len): rows are built on the device
         self.info = None           # ... and their per-line flags (Engine.text_info), set by the runner
         self.digests = None        # ... and the MD5 digests of their patterns (Engine.pattern_digests), on request
+        self.report_empty = False  # 'No observations of ...' still to be reported, from the run's carrier counts
 
 
 class VariantReader(object):
@@ -377,24 +378,37 @@ class PackedCacheWriter(object):
 class CachedVariantReader(object):
     """Same interface as VariantReader, over a PackedCache file (no parsing, no native library)."""
 
-    def __init__(self, path, p):
+    def __init__(self, path, p, threads=1):
         self.samples = [str(s) for s in p.index]
         self.n_samples = len(self.samples)
         self.W = words_per_row(self.n_samples)
+        self.threads = max(1, min(int(threads), 8))
+        self._tp = None
         self.fh = open(path, 'rb')
         self.header = json.loads(self.fh.readline().decode())
         self._data_pos = self.fh.tell()             # first chunk
         self.var_type = self.header['var_type']
 
     def close(self):
+        if self._tp is not None:
+            self._tp.shutdown()
+            self._tp = None
         if self.fh:
             self.fh.close()
             self.fh = None
 
-    def batches(self, size, pool=None):
+    def _pool(self):
+        if self._tp is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._tp = ThreadPoolExecutor(self.threads)
+        return self._tp
+
+    def batches(self, size, pool=None, defer_empty=False):
         """Batches of exactly ``size`` variants (the last one shorter), the rows read STRAIGHT into the
         batch's buffers with ``pread`` -- page-locked ones when ``pool`` hands them out (``pool.get() ->
-        (bits, missing_or_None, token)``), so that ``psb_submit`` is a plain DMA; no intermediate copies."""
+        (bits, missing_or_None, token)``), so that ``psb_submit`` is a plain DMA; no intermediate copies.
+        ``defer_empty``: rows without any observation are reported by the consumer from the carrier counts
+        of the run (``VariantBatch.report_empty``) instead of a pass over the rows here."""
         W, fd = self.W, self.fh.fileno()
         row_bytes = W * 4
         pos = self._data_pos
@@ -402,14 +416,23 @@ class CachedVariantReader(object):
         n = taken = 0
         cnames, bits_off, miss_off = [], 0, None
 
-        def read_into(arr, off):
-            mv = memoryview(arr).cast('B')
+        def read_slice(mv, off):
             done = 0
             while done < len(mv):
                 k = os.preadv(fd, [mv[done:]], off + done)
                 if k <= 0:
                     raise IOError('packed cache truncated')
                 done += k
+
+        def read_into(arr, off):
+            # slices of >= 4 MB on a few threads (preadv releases the GIL): one thread copies ~5 GB/s
+            # out of the page cache
+            mv = memoryview(arr).cast('B')
+            parts = min(self.threads, max(1, len(mv) >> 22))
+            if parts <= 1:
+                return read_slice(mv, off)
+            cut = [len(mv) * i // parts for i in range(parts + 1)]
+            list(self._pool().map(lambda i: read_slice(mv[cut[i]:cut[i + 1]], off + cut[i]), range(parts)))
 
         at_end = False
         while not at_end:
@@ -452,9 +475,12 @@ class CachedVariantReader(object):
             m = miss[:filled] if any_m and miss[:filled].any() else None
             out = VariantBatch(names, bits[:filled], m)
             out.token = token
-            empty = ~(out.bits.any(axis=1) | (m.any(axis=1) if m is not None else False))
-            for i in np.nonzero(empty)[0]:
-                sys.stderr.write('No observations of ' + out.names[i] + ' in selected samples\n')
+            if m is None and defer_empty:
+                out.report_empty = True     # no missing genotypes: "no observation" is carriers == 0 in the results
+            else:
+                empty = ~(out.bits.any(axis=1) | (m.any(axis=1) if m is not None else False))
+                for i in np.nonzero(empty)[0]:
+                    sys.stderr.write('No observations of ' + out.names[i] + ' in selected samples\n')
             yield out
 
     sample_lists = VariantReader.sample_lists
@@ -471,7 +497,7 @@ def open_variants(var_type, path, p, uncompressed=False, cache=None, threads=1):
     W = words_per_row(len(samples))
     if PackedCache.valid(cache, var_type, path, samples, W):
         sys.stderr.write('Reading packed variants from ' + str(cache) + '\n')
-        return CachedVariantReader(cache, p)
+        return CachedVariantReader(cache, p, threads)
     rd = VariantReader(var_type, path, p, uncompressed, threads)
     writer = PackedCacheWriter(cache, var_type, path, samples, W)
     inner = rd.batches
