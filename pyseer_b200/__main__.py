@@ -297,7 +297,11 @@ def main(argv=None):
             counters['prefilter'] += n_pre
             counters['tested'] += n_tested
             counters['printed'] += n_printed
-            out.write(text.decode())
+            if hasattr(out, 'buffer'):          # a real stream: the bytes go out as they are
+                out.flush()
+                out.buffer.write(text)
+            else:
+                out.write(text.decode())
             if patterns is not None:
                 # hash_pattern of every tested variant, in input order (__main__.py:559-560)
                 if batch.digests is not None:

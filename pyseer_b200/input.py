@@ -133,6 +133,35 @@ def hash_patterns(bits, missing, n_samples, flags=None):
     return out.raw[:25 * m.value]
 
 
+class NameBlob(object):
+    """The variant names of a batch as the packed cache stores them -- one blob of NUL-terminated names
+    plus their offsets -- behaving like the list of strings the result loop expects; the native
+    formatter takes blob and offsets as they are (48000 names per batch are otherwise split into
+    strings only to be joined again)."""
+    __slots__ = ['blob', 'off']
+
+    def __init__(self, blob, off):
+        self.blob, self.off = blob, off
+
+    def __len__(self):
+        return int(self.off.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        a = int(self.off[i])
+        return self.blob[a:self.blob.index(b'\0', a)].decode()
+
+    def __iter__(self):
+        return iter(self.blob[:-1].decode().split('\0')) if len(self) else iter(())
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __ne__(self, other):
+        return not self == other
+
+
 class VariantBatch(object):
     """``n`` variants as packed rows plus what the result loop needs to print them."""
     __slots__ = ['names', 'bits', 'missing', 'n', 'token', 'skipped', 'text', 'info', 'digests', 'report_empty']
@@ -414,7 +443,7 @@ class CachedVariantReader(object):
         pos = self._data_pos
         # the chunk being consumed: rows, names, file offsets of its bits / missing rows, rows taken
         n = taken = 0
-        cnames, bits_off, miss_off = [], 0, None
+        craw, cstart, cnul, bits_off, miss_off = b'', None, None, 0, None
 
         def read_slice(mv, off):
             done = 0
@@ -441,7 +470,7 @@ class CachedVariantReader(object):
                 bits, miss, token = pool.get()
             else:
                 bits, miss = np.empty((size, W), dtype=np.uint32), None
-            names, filled, any_m = [], 0, False
+            pieces, offs, blob_len, filled, any_m = [], [], 0, 0, False
             while filled < size:
                 if taken == n:
                     head = np.frombuffer(os.pread(fd, 24, pos), dtype='<i8')
@@ -449,7 +478,11 @@ class CachedVariantReader(object):
                         at_end = True
                         break
                     n, nb, has_m = int(head[0]), int(head[1]), int(head[2])
-                    cnames = os.pread(fd, nb, pos + 24).decode().split('\0')[:n]
+                    craw = os.pread(fd, nb, pos + 24)
+                    cnul = np.flatnonzero(np.frombuffer(craw, dtype=np.uint8) == 0)[:n].astype(np.int64)
+                    if cnul.shape[0] != n:
+                        raise IOError('packed cache: names of a chunk are damaged')
+                    cstart = np.concatenate(([0], cnul[:-1] + 1))
                     bits_off = pos + 24 + nb
                     miss_off = bits_off + n * row_bytes if has_m else None
                     pos = bits_off + n * row_bytes * (2 if has_m else 1)
@@ -465,7 +498,10 @@ class CachedVariantReader(object):
                     any_m = True
                 elif any_m:
                     miss[filled:filled + k] = 0
-                names.extend(cnames[taken:taken + k])
+                a0, a1 = int(cstart[taken]), int(cnul[taken + k - 1]) + 1
+                pieces.append(craw[a0:a1])
+                offs.append(cstart[taken:taken + k] - a0 + blob_len)
+                blob_len += a1 - a0
                 taken += k
                 filled += k
             if filled == 0:
@@ -473,6 +509,8 @@ class CachedVariantReader(object):
                     pool.put(token)
                 return
             m = miss[:filled] if any_m and miss[:filled].any() else None
+            names = NameBlob(pieces[0] if len(pieces) == 1 else b''.join(pieces),
+                             offs[0] if len(offs) == 1 else np.concatenate(offs))
             out = VariantBatch(names, bits[:filled], m)
             out.token = token
             if m is None and defer_empty:

@@ -41,11 +41,19 @@ def format_table(r, names, model='seer', block_size=1, print_filtered=False, thr
     from . import _lib
     lib = _lib.load()
     n = len(names)
-    blob = ('\0'.join(names) + '\0').encode()
-    lens = np.fromiter((len(s.encode()) + 1 for s in names), dtype=np.int64, count=n)
-    off = np.zeros(n, dtype=np.int64)
-    if n > 1:
-        np.cumsum(lens[:-1], out=off[1:])
+    if hasattr(names, 'blob'):          # input.NameBlob: already in the formatter's layout
+        blob, off = names.blob, np.ascontiguousarray(names.off, dtype=np.int64)
+    else:
+        blob = ('\0'.join(names) + '\0').encode()
+        off = np.zeros(n, dtype=np.int64)
+    # offsets of the names inside the blob: one past every NUL but the last (names hold no NUL)
+    if n > 1 and not hasattr(names, 'blob'):
+        nul = np.flatnonzero(np.frombuffer(blob, dtype=np.uint8) == 0)
+        if nul.shape[0] == n:
+            off[1:] = nul[:-1] + 1
+        else:                       # a name with an embedded NUL: the slow, exact way
+            lens = np.fromiter((len(s.encode()) + 1 for s in names), dtype=np.int64, count=n)
+            np.cumsum(lens[:-1], out=off[1:])
     cols = _lib.PsbResults()
     keep = []
     for f, dt in (('af', np.float64), ('prep', np.float64), ('pvalue', np.float64), ('beta', np.float64),
@@ -60,10 +68,16 @@ def format_table(r, names, model='seer', block_size=1, print_filtered=False, thr
         cols.betas = b.ctypes.data_as(ctypes.c_void_p)
         nb = b.shape[1]
     cap = int(len(blob) + n * (32 * (7 + nb) + 256) + 64)
-    out = ctypes.create_string_buffer(cap)
+    global _fmt_buf
+    if _fmt_buf is None or _fmt_buf.shape[0] < cap:      # kept between calls (one output thread): no 20 MB
+        _fmt_buf = np.empty(cap, dtype=np.uint8)         # of zeroed memory per batch
+    out = _fmt_buf
     out_len = ctypes.c_int64(0)
     counts = (ctypes.c_int64 * 3)(0, 0, 0)
     _lib.check(lib.psb_format_rows(1 if model == 'lmm' else 0, n, blob, off.ctypes.data_as(ctypes.c_void_p),
                                    ctypes.byref(cols), nb, int(block_size), int(bool(print_filtered)),
-                                   int(threads), ctypes.addressof(out), cap, ctypes.byref(out_len), counts))
-    return out.raw[:out_len.value], counts[0], counts[1], counts[2]
+                                   int(threads), out.ctypes.data, cap, ctypes.byref(out_len), counts))
+    return out[:out_len.value].tobytes(), counts[0], counts[1], counts[2]
+
+
+_fmt_buf = None

@@ -121,3 +121,32 @@ def test_native_formatter_matches_reference_lines():
             text, _, _, printed = format_table(r, [f['kmer']], model, 1, True)
             assert printed == 1
             assert _same(text.decode().rstrip('\n'), want), (model, f['kmer'])
+
+
+def test_fast_number_formatting_equals_printf():
+    """fmt_num's fast path (scale into [100, 1000) by a table of powers of ten, round, hand the cases
+    within 1e-6 of a tie to snprintf) against '%.2E' on ties of exact binary fractions, decimal half-way
+    cases, powers of ten, both ends of the fast range, subnormals and signed zeros."""
+    rng = np.random.RandomState(1)
+    vals = [0.0, -0.0, 1.0, -1.0, 1.125, 1.135, 1.145, 1.115, 9.995, 9.985, 99.95e-7, 9.995e22, 9.995e-23, 999.5,
+            99.95, 1e-5, 1e5, 1e22, 1e23, 1e-22, 1e-23, 5e-324, 2.2e-308, 1e-300, 1e300, 1.7976931348623157e308,
+            1e-290, 1e290, 1e-291, 9.994999999999999, 9.995000000000001, 0.001005, 1.005, 1.015, 1.025, 2.675,
+            123456789.0, 0.000123456]
+    vals += list((rng.randint(1, 2000, 4000) / 8.0) * 10.0 ** rng.randint(-30, 30, 4000))
+    vals += list(rng.randint(100, 1000, 3000) / 100.0 + 0.005)
+    vals += list(rng.normal(size=20000) * 10.0 ** rng.randint(-300, 300, 20000))
+    edge = np.array([1.125, 9.995, 99.95, 2.5e-7, 1e-290, 1e290])
+    vals += list(np.nextafter(edge, np.inf)) + list(np.nextafter(edge, -np.inf))
+    v = np.array(vals, dtype=float)
+    n = len(v)
+    r = Results()
+    r.af, r.prep, r.pvalue, r.beta, r.bse, r.extra = v.copy(), np.abs(v), np.abs(v), v.copy(), np.abs(v), v.copy()
+    r.flags = np.full(n, _lib.F_TESTED, dtype=np.uint32)
+    r.betas = None
+    r.carriers = r.missing = np.zeros(n, dtype=np.int32)
+    text, _, _, _ = format_table(r, ['v%d' % i for i in range(n)], 'lmm', 3000, True, threads=4)
+    lines = text.decode().split('\n')[:-1]
+    assert len(lines) == n
+    for i, line in enumerate(lines):
+        f = line.split('\t')
+        assert f[1] == '%.2E' % v[i] and f[5] == '%.2E' % abs(v[i]), (repr(v[i]), f)
