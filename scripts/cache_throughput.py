@@ -22,6 +22,7 @@ def main():
     ap.add_argument('--samples', type=int, default=5000)
     ap.add_argument('--kmers', type=int, default=2000000)
     ap.add_argument('--profile', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='default batch only, with and without an lrt filter')
     a = ap.parse_args()
     import benchdata
     from pyseer_b200.engine import synth_host
@@ -58,7 +59,8 @@ def main():
         ['-m', 'pyseer_b200', '--phenotypes', os.path.join(d, 'pheno.tsv'), '--lmm', '--load-lmm',
          os.path.join(d, 'lmm.npz'), '--cpu', str(cores), '--kmers', src, '--uncompressed', '--bits-cache', cache]
     res = {'n_samples': n, 'kmers': m, 'cache_bytes': os.path.getsize(cache), 'write_cache_s': gen_s, 'runs': {}}
-    for tag, extra in (('default', []), ('gpu_batch_24000', ['--gpu-batch', '24000']), ('gpu_batch_12000', ['--gpu-batch', '12000']),
+    runs = (('default', []), ('lrt_1e-4', ['--lrt-pvalue', '1e-4']), ('default_again', [])) if a.quick else None
+    for tag, extra in runs or (('default', []), ('gpu_batch_24000', ['--gpu-batch', '24000']), ('gpu_batch_12000', ['--gpu-batch', '12000']),
                        ('lrt_1e-4', ['--lrt-pvalue', '1e-4']), ('default_again', [])):
         t = time.time()
         env = dict(os.environ, PYSEER_B200_TIMING='1')
