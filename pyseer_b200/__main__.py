@@ -266,8 +266,10 @@ def main(argv=None):
     # packed rows on the host: sample lists, lineage fits, the packed cache (pattern hashes do not:
     # psb_pattern_digests computes them where the rows are)
     text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and \
-        not (o.print_samples or o.lineage or o.bits_cache) and \
+        not (o.print_samples or o.lineage) and \
         os.environ.get('PYSEER_B200_TEXT', '1') != '0'
+    # --bits-cache being written by this run: from the rows the device parsed, brought back per batch
+    cache_writer = getattr(reader, 'cache_writer', None) if text_mode else None
     # measured at N = 5000 (profiles/r02_cli_batch_sweep.json): plain text streams at 84 k variants/s in
     # batches of 24000 lines, 550 k/s in batches of 12000, 640 k/s in batches of 6000
     gpu_batch = o.gpu_batch if o.gpu_batch else (12000 if text_mode else 48000)
@@ -280,6 +282,8 @@ def main(argv=None):
     def emit(batch, r):
         """Result loop of main() (__main__.py:547-568, 783-803) for one batch."""
         flags = r.flags
+        if cache_writer is not None and batch.text is not None:
+            cache_writer.add(batch)
         if batch.text is not None or batch.report_empty:
             # batch parsed on the device, or read from the packed cache: what the host reader reports while
             # it reads (a row without missing genotypes: "no observation" is carriers == 0)
@@ -394,11 +398,12 @@ def main(argv=None):
         comm = Comm.local(engines)
     runner = BatchRunner(engines, run_one, n_betas=n_betas,
                          lineage=(False if (o.lineage and not o.lmm) else None), comm=comm,
-                         rows_max=gpu_batch, digests=patterns is not None)
+                         rows_max=gpu_batch, digests=patterns is not None, rows=cache_writer is not None)
     pool = None
     name_bytes = sum(len(x) for x in reader.samples) + 3 * reader.n_samples if text_mode else 0
     if text_mode and o.block_size * (name_bytes + 4096) > (2 << 30):
         text_mode = False      # one block of worst-case lines would not fit a 2 GB text buffer: host parser
+        cache_writer = None    # ... which writes the cache while it reads
     if text_mode:
         # page-locked text buffers sized for a full batch at an allele frequency of 0.5 (a batch cut
         # short by its buffer keeps whole blocks, see psb_reader_next_text) and never smaller than one
@@ -440,15 +445,26 @@ def main(argv=None):
     writer.start()
     import time
     t_stream = time.time()
+    streamed = False
     try:
         for batch, r in runner.results(batches):
             if out_err:
                 break
             outq.put((batch, r))
+        streamed = True
     finally:
         batches.cancel()
         outq.put(None)
         writer.join()
+        if cache_writer is not None:
+            # complete only when every batch went through; an interrupted cache is discarded
+            complete = streamed and not out_err
+            cache_writer.close(complete=complete)
+            if not complete:
+                try:
+                    os.unlink(reader.cache_path)
+                except OSError:
+                    pass
         runner.close()
         if comm is not None:
             comm.close()

@@ -556,6 +556,10 @@ def open_variants(var_type, path, p, uncompressed=False, cache=None, threads=1):
                     pass
 
     rd.batches = batches
+    # a run that tokenises the text on the device (text_batches) writes the cache itself, from the rows
+    # it brings back (pyseer_b200/__main__.py)
+    rd.cache_writer = writer
+    rd.cache_path = cache
     return rd
 
 

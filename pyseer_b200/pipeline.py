@@ -182,10 +182,11 @@ class BatchRunner(object):
     engine; ``lineage``: None, or the ``lmm_rule`` flag of ``Engine.run_lineage`` (fixed effects:
     False) whose result is attached to ``results.lineage``."""
 
-    def __init__(self, engines, run, n_betas=0, lineage=None, comm=None, rows_max=0, digests=False):
+    def __init__(self, engines, run, n_betas=0, lineage=None, comm=None, rows_max=0, digests=False, rows=False):
         self.engines = list(engines)
         self._run = run
         self.digests = digests          # --output-patterns on batches parsed on the device
+        self.rows = rows                # --bits-cache being written from batches parsed on the device
         self.n_betas = n_betas
         self.lineage = lineage
         self.comm = comm if len(self.engines) > 1 else None
@@ -203,6 +204,8 @@ class BatchRunner(object):
         self._run(eng)
         if self.digests and b is not None and b.bits is None:
             b.digests = eng.pattern_digests()
+        if self.rows and b is not None and b.bits is None:
+            b.bits, b.missing = eng.download_rows()
 
     def _fetch(self, eng, b):
         r = eng.fetch()

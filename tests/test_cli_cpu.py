@@ -30,7 +30,7 @@ class _FakeEngine(object):
         self._rows = burden_union(bits, missing, offsets, members)
 
     def download_rows(self):
-        bits, miss = self._rows
+        bits, miss = self._rows if getattr(self, '_rows', None) is not None else self._sub
         return bits, (miss if miss is not None and miss.any() else None)
 
     def submit(self, bits, missing=None):

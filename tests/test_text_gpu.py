@@ -211,3 +211,35 @@ def test_cli_output_patterns_through_device_parser(tmp_path, monkeypatch):
     for key, (a, b) in files.items():
         assert a[0] == b[0] and len(a[0]) > 25 * 100, key
         assert a[1] == b[1], key
+
+
+def test_bits_cache_written_from_device_rows(tmp_path, monkeypatch):
+    """--bits-cache on a first run that tokenises the text on the device: the cache holds the rows the
+    device parsed (brought back per batch) -- the same names and rows as the cache the host parser
+    writes -- and a run from it prints what the parsing runs printed."""
+    from pyseer_b200.__main__ import main
+    from pyseer_b200.input import CachedVariantReader, load_phenotypes
+    G = lambda f: os.path.join(GOLDEN, f)   # noqa: E731
+    p = load_phenotypes(G('subset.pheno'), None)
+    outs, caches = {}, {}
+    for mode in ('1', '0', 'read'):
+        monkeypatch.setenv('PYSEER_B200_TEXT', '1' if mode == 'read' else mode)
+        cache = str(tmp_path / ('k%s.bits' % ('1' if mode == 'read' else mode)))
+        out, err = io.StringIO(), io.StringIO()
+        with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+            rc = main(['--kmers', G('kmers.gz'), '--phenotypes', G('subset.pheno'), '--lmm', '--similarity',
+                       G('similarity50.tsv'), '--gpu-batch', '60', '--block_size', '20', '--bits-cache', cache])
+        assert rc == 0
+        assert ('Reading packed variants from' in err.getvalue()) == (mode == 'read')
+        outs[mode] = out.getvalue()
+        caches[mode] = cache
+    assert outs['1'] == outs['0'] == outs['read'] and len(outs['1'].split('\n')) > 150
+    rows = {}
+    for mode in ('1', '0'):
+        rd = CachedVariantReader(caches[mode], p)
+        with contextlib.redirect_stderr(io.StringIO()):
+            bs = list(rd.batches(1000))
+        rd.close()
+        rows[mode] = ([x for b in bs for x in b.names], np.concatenate([b.bits for b in bs]))
+    assert rows['1'][0] == rows['0'][0] and len(rows['1'][0]) == 200
+    assert np.array_equal(rows['1'][1], rows['0'][1])
