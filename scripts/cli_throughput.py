@@ -157,8 +157,8 @@ def main():
                              ('plain_text_host_parser', ['--kmers', txt, '--uncompressed'], '0'),
                              ('bgzip_text_host_parser', ['--kmers', txt + '.bgz'], '0'),
                              ('gzip_text_host_parser', ['--kmers', txt + '.gz'], '0'),
-                             ('gzip_text_writing_bits_cache', ['--kmers', txt + '.gz', '--bits-cache', cache], '0'),
-                             ('bits_cache', ['--kmers', txt + '.gz', '--bits-cache', cache], '0')):
+                             ('gzip_one_member_writing_bits_cache', ['--kmers', txt + '.gz1', '--bits-cache', cache], '1'),
+                             ('bits_cache', ['--kmers', txt + '.gz1', '--bits-cache', cache], '1')):
         w, rate = run(extra, tag, text)
         res['runs'][tag] = {'wall_s': w, 'variants_per_s_whole_run': m / w,
                             'variants_per_s_streaming': rate}
