@@ -366,6 +366,14 @@ int psb_format_rows(int32_t model, int64_t n_variants, const char *names, const 
                     const psb_results *cols, int32_t n_betas, int32_t block_size,
                     int32_t print_filtered, int32_t n_threads, char *out, int64_t out_cap,
                     int64_t *out_len, int64_t counts[3]);
+/* The same with the lineage column of --lineage runs (utils.py:93-97) between the coefficients and the
+ * notes: lineage[v] >= 0 indexes the n_lineages NUL-terminated names back to back in lineage_names
+ * (lineage_off their offsets), a negative index prints NA. */
+int psb_format_rows_lineage(int32_t model, int64_t n_variants, const char *names, const int64_t *name_off,
+                            const psb_results *cols, int32_t n_betas, int32_t block_size,
+                            int32_t print_filtered, int32_t n_threads, const int32_t *lineage,
+                            const char *lineage_names, const int64_t *lineage_off, int32_t n_lineages,
+                            char *out, int64_t out_cap, int64_t *out_len, int64_t counts[3]);
 
 /* Pattern hashes of --output-patterns: input.hash_pattern (input.py:710-723) of the vector k the
  * reference builds from a variant (input.py:450; int64, or float64 with NaN when genotypes are

@@ -262,14 +262,15 @@ def main(argv=None):
     out = sys.stdout
     nan = np.nan
     model_name = 'lmm' if o.lmm else 'seer'
-    # k-mer text is tokenised on the device (psb_submit_text) unless something downstream needs the
-    # packed rows on the host: sample lists, lineage fits, the packed cache (pattern hashes do not:
-    # psb_pattern_digests computes them where the rows are)
-    text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and \
-        not (o.print_samples or o.lineage) and \
+    # k-mer text is tokenised on the device (psb_submit_text) unless sample lists are printed; what else
+    # needs the packed rows on the host (the packed cache being written, the LMM's per-block lineage fits)
+    # gets them back per batch; pattern hashes and fixed-effects lineage fits happen where the rows are
+    text_mode = type(reader) is VariantReader and reader.var_type == 'kmers' and not o.print_samples and \
         os.environ.get('PYSEER_B200_TEXT', '1') != '0'
     # --bits-cache being written by this run: from the rows the device parsed, brought back per batch
     cache_writer = getattr(reader, 'cache_writer', None) if text_mode else None
+    # the rows come back from the device for the cache, and for the LMM's per-block lineage fits
+    rows_back = cache_writer is not None or (text_mode and o.lmm and o.lineage)
     # measured at N = 5000 (profiles/r02_cli_batch_sweep.json): plain text streams at 84 k variants/s in
     # batches of 24000 lines, 550 k/s in batches of 12000, 640 k/s in batches of 6000
     gpu_batch = o.gpu_batch if o.gpu_batch else (12000 if text_mode else 48000)
@@ -292,12 +293,32 @@ def main(argv=None):
         if batch.skipped is not None and batch.skipped.any():
             # records the reference never hands to a model (k is None, input.py:603-611)
             flags[batch.skipped] = _lib.F_AF_FILTER | _lib.F_PREFILTER
-        if not (o.print_samples or o.lineage) and \
-                os.environ.get('PYSEER_B200_NATIVE_FORMAT', '1') != '0':
-            # no per-variant samples or lineages asked for: the whole batch goes through the library's formatter
-            # (psb_format_rows: same lines, order and counters as the loop below, ~15x its speed)
+        if not o.print_samples and os.environ.get('PYSEER_B200_NATIVE_FORMAT', '1') != '0':
+            # no per-variant sample lists asked for: the whole batch goes through the library's formatter
+            # (psb_format_rows[_lineage]: same lines, order and counters as the loop below, far faster)
+            lin = None
+            if o.lineage:
+                # the lineage column as the loop below fills it: NA (-1) for pre-filtered variants; LMM: the
+                # lineage of the block's LAST variant for every fitted variant of the block (lmm.py:160-162
+                # / :209-211, the loop variable `k` is reused), NA for the lrt-filtered ones; fixed effects:
+                # the variant's own lineage (model.py:379-380)
+                fl = np.asarray(flags[:batch.n])
+                lin = np.full(batch.n, -1, dtype=np.int32)
+                if o.lmm:
+                    fitted = (fl & (_lib.F_PREFILTER | _lib.F_FILTER)) == 0
+                    for b0 in range(0, batch.n, o.block_size):
+                        b1 = min(b0 + o.block_size, batch.n)
+                        bl = fx.fit_lineage_effect(lineage_clusters, cov.values, reader.k_vector(batch, b1 - 1),
+                                                   device=o.gpu)
+                        if bl is not None and np.isfinite(bl):
+                            lin[b0:b1][fitted[b0:b1]] = int(bl)
+                else:
+                    rl = np.asarray(r.lineage[:batch.n])
+                    sel = ((fl & _lib.F_PREFILTER) == 0) & (rl >= 0)
+                    lin[sel] = rl[sel]
             text, n_pre, n_tested, n_printed = format_table(r, batch.names, model_name, o.block_size,
-                                                            o.print_filtered, threads=o.cpu)
+                                                            o.print_filtered, threads=o.cpu, lineage=lin,
+                                                            lineage_names=lineage_dict if o.lineage else None)
             counters['prefilter'] += n_pre
             counters['tested'] += n_tested
             counters['printed'] += n_printed
@@ -398,7 +419,7 @@ def main(argv=None):
         comm = Comm.local(engines)
     runner = BatchRunner(engines, run_one, n_betas=n_betas,
                          lineage=(False if (o.lineage and not o.lmm) else None), comm=comm,
-                         rows_max=gpu_batch, digests=patterns is not None, rows=cache_writer is not None)
+                         rows_max=gpu_batch, digests=patterns is not None, rows=rows_back)
     pool = None
     name_bytes = sum(len(x) for x in reader.samples) + 3 * reader.n_samples if text_mode else 0
     if text_mode and o.block_size * (name_bytes + 4096) > (2 << 30):

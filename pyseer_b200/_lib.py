@@ -80,7 +80,7 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_lineage_setup', 'psb_run_lineage', 'psb_fetch_lineage', 'psb_last_stats', 'psb_kinship_begin', 'psb_kinship_add', 'psb_kinship_fetch',
            'psb_synth_device', 'psb_synth_host', 'psb_host_chi2_sf1', 'psb_host_f_sf_1',
            'psb_host_t2_sf', 'psb_submit_burden', 'psb_submit_burden_device',
-           'psb_submitted_device', 'psb_download_rows', 'psb_eigh', 'psb_reader_set_threads', 'psb_pgz_selftest', 'psb_format_rows', 'psb_reader_vcf_info', 'psb_hash_patterns', 'psb_pattern_digests',
+           'psb_submitted_device', 'psb_download_rows', 'psb_eigh', 'psb_reader_set_threads', 'psb_pgz_selftest', 'psb_format_rows', 'psb_format_rows_lineage', 'psb_reader_vcf_info', 'psb_hash_patterns', 'psb_pattern_digests',
            'psb_comm_unique_id', 'psb_comm_init_rank', 'psb_comm_init_all', 'psb_comm_destroy',
            'psb_comm_info', 'psb_comm_bcast', 'psb_comm_allreduce', 'psb_comm_barrier',
            'psb_comm_gather_begin', 'psb_comm_gather_wait', 'psb_comm_gather_fetch',
@@ -137,6 +137,9 @@ def load():
     lib.psb_format_rows.argtypes = [c_int32, c_int64, c_void_p, c_void_p, POINTER(PsbResults), c_int32,
                                     c_int32, c_int32, c_int32, c_void_p, c_int64, POINTER(c_int64),
                                     POINTER(c_int64)]
+    lib.psb_format_rows_lineage.argtypes = [c_int32, c_int64, c_void_p, c_void_p, POINTER(PsbResults), c_int32,
+                                            c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32,
+                                            c_void_p, c_int64, POINTER(c_int64), POINTER(c_int64)]
     lib.psb_run_lmm.argtypes = [c_void_p, POINTER(PsbParams)]
     lib.psb_run_fixed.argtypes = [c_void_p, POINTER(PsbParams)]
     lib.psb_fetch.argtypes = [c_void_p, POINTER(PsbResults)]

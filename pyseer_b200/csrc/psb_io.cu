@@ -942,9 +942,16 @@ static const struct { uint32_t bit; const char *text; } k_notes[] = {
 
 // Formats rows [b0, b1) (b0 a multiple of block_size) into `dst`; counts[0..2] += pre-filtered,
 // tested, printed.
+struct fmt_lineage {                 // --lineage column: name of lineage[v], "NA" for a negative index
+    const int32_t *idx = nullptr;    // nullptr: no such column
+    const char *names = nullptr;
+    const int64_t *off = nullptr;
+    int32_t n = 0;
+};
+
 static void format_range(int model, int64_t b0, int64_t b1, const char *names, const int64_t *name_off,
                          const psb_results *cols, int n_betas, int block_size, int print_filtered,
-                         std::string &dst, int64_t counts[3]) {
+                         const fmt_lineage &lin, std::string &dst, int64_t counts[3]) {
     char num[40];
     for (int64_t c0 = b0; c0 < b1; c0 += block_size) {
         const int64_t c1 = std::min<int64_t>(b1, c0 + block_size);
@@ -984,6 +991,12 @@ static void format_range(int model, int64_t b0, int64_t b1, const char *names, c
                         put(cols->betas[v * n_betas + c]);
                     }
                 }
+                if (lin.idx) {                                   // utils.py:93-97
+                    dst.push_back('\t');
+                    const int32_t l = lin.idx[v];
+                    if (l >= 0 && l < lin.n) dst.append(lin.names + lin.off[l]);
+                    else dst.append("NA");
+                }
                 dst.push_back('\t');
                 bool first = true;
                 for (const auto &nt : k_notes)
@@ -1006,10 +1019,10 @@ static void format_range(int model, int64_t b0, int64_t b1, const char *names, c
 // counts[0..2] += pre-filtered, tested, printed (__main__.py:549-565, 793-817).  n_threads > 1 formats
 // ranges of whole blocks in parallel and concatenates them in order.  Returns PSB_ERR_NOMEM when
 // out_cap is too small (nothing usable in `out` then).
-extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, const int64_t *name_off,
-                               const psb_results *cols, int32_t n_betas, int32_t block_size,
-                               int32_t print_filtered, int32_t n_threads, char *out, int64_t out_cap,
-                               int64_t *out_len, int64_t counts[3]) {
+static int format_rows_impl(int32_t model, int64_t n, const char *names, const int64_t *name_off,
+                            const psb_results *cols, int32_t n_betas, int32_t block_size,
+                            int32_t print_filtered, int32_t n_threads, const fmt_lineage &lin, char *out,
+                            int64_t out_cap, int64_t *out_len, int64_t counts[3]) {
     PSB_REQUIRE(names && name_off && cols && out && out_len && counts, PSB_ERR_ARG, "NULL argument");
     PSB_REQUIRE(cols->af && cols->prep && cols->pvalue && cols->beta && cols->bse && cols->extra &&
                     cols->flags && (n_betas == 0 || cols->betas),
@@ -1025,8 +1038,8 @@ extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, cons
     auto work = [&](int t) {
         const int64_t b0 = (n_blocks * t / T) * block_size;
         const int64_t b1 = std::min<int64_t>(n, (n_blocks * (t + 1) / T) * block_size);
-        parts[t].reserve((size_t)((b1 - b0) * (64 + 10 * (7 + n_betas))));
-        format_range(model, b0, b1, names, name_off, cols, n_betas, block_size, print_filtered, parts[t],
+        parts[t].reserve((size_t)((b1 - b0) * (64 + 10 * (7 + n_betas) + (lin.idx ? 16 : 0))));
+        format_range(model, b0, b1, names, name_off, cols, n_betas, block_size, print_filtered, lin, parts[t],
                      &cnt[(size_t)t * 3]);
     };
     if (T == 1) {
@@ -1048,6 +1061,33 @@ extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, cons
     }
     *out_len = total;
     return PSB_OK;
+}
+
+extern "C" int psb_format_rows(int32_t model, int64_t n, const char *names, const int64_t *name_off,
+                               const psb_results *cols, int32_t n_betas, int32_t block_size,
+                               int32_t print_filtered, int32_t n_threads, char *out, int64_t out_cap,
+                               int64_t *out_len, int64_t counts[3]) {
+    return format_rows_impl(model, n, names, name_off, cols, n_betas, block_size, print_filtered, n_threads,
+                            fmt_lineage(), out, out_cap, out_len, counts);
+}
+
+// The same with the lineage column of --lineage runs (utils.py:93-97) between the coefficients and the
+// notes: lineage[v] indexes the n_lineages NUL-terminated names in lineage_names (lineage_off their
+// offsets); a negative index prints NA.
+extern "C" int psb_format_rows_lineage(int32_t model, int64_t n, const char *names, const int64_t *name_off,
+                                       const psb_results *cols, int32_t n_betas, int32_t block_size,
+                                       int32_t print_filtered, int32_t n_threads, const int32_t *lineage,
+                                       const char *lineage_names, const int64_t *lineage_off,
+                                       int32_t n_lineages, char *out, int64_t out_cap, int64_t *out_len,
+                                       int64_t counts[3]) {
+    PSB_REQUIRE(lineage && lineage_names && lineage_off && n_lineages >= 0, PSB_ERR_ARG, "NULL lineage argument");
+    fmt_lineage lin;
+    lin.idx = lineage;
+    lin.names = lineage_names;
+    lin.off = lineage_off;
+    lin.n = n_lineages;
+    return format_rows_impl(model, n, names, name_off, cols, n_betas, block_size, print_filtered, n_threads, lin,
+                            out, out_cap, out_len, counts);
 }
 
 // VCF only: contig (NUL-terminated, back to back in `contigs` with contig_off[v] offsets), 1-based

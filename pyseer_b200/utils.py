@@ -32,10 +32,12 @@ def format_output(item, lineage_dict=None, model='seer', print_samples=False):
     return '\t'.join(fields)
 
 
-def format_table(r, names, model='seer', block_size=1, print_filtered=False, threads=1):
+def format_table(r, names, model='seer', block_size=1, print_filtered=False, threads=1, lineage=None,
+                 lineage_names=None):
     """TSV lines of a whole result table (``engine.Results``) through the library's native formatter
     (``psb_format_rows``): what the result loop of ``main()`` prints with ``format_output`` when
-    neither samples nor lineages are asked for.  Returns ``(text_bytes, prefiltered, tested,
+    no sample lists are asked for.  ``lineage``: int32 index per row into ``lineage_names`` (negative:
+    ``NA``) for the lineage column of ``--lineage`` runs.  Returns ``(text_bytes, prefiltered, tested,
     printed)``."""
     import ctypes
     from . import _lib
@@ -67,16 +69,28 @@ def format_table(r, names, model='seer', block_size=1, print_filtered=False, thr
         keep.append(b)
         cols.betas = b.ctypes.data_as(ctypes.c_void_p)
         nb = b.shape[1]
-    cap = int(len(blob) + n * (32 * (7 + nb) + 256) + 64)
+    cap = int(len(blob) + n * (32 * (7 + nb) + 256 + (max(len(str(x)) for x in lineage_names) + 1 if lineage is not None and len(lineage_names) else 4)) + 64)
     global _fmt_buf
     if _fmt_buf is None or _fmt_buf.shape[0] < cap:      # kept between calls (one output thread): no 20 MB
         _fmt_buf = np.empty(cap, dtype=np.uint8)         # of zeroed memory per batch
     out = _fmt_buf
     out_len = ctypes.c_int64(0)
     counts = (ctypes.c_int64 * 3)(0, 0, 0)
-    _lib.check(lib.psb_format_rows(1 if model == 'lmm' else 0, n, blob, off.ctypes.data_as(ctypes.c_void_p),
-                                   ctypes.byref(cols), nb, int(block_size), int(bool(print_filtered)),
-                                   int(threads), out.ctypes.data, cap, ctypes.byref(out_len), counts))
+    if lineage is None:
+        _lib.check(lib.psb_format_rows(1 if model == 'lmm' else 0, n, blob, off.ctypes.data_as(ctypes.c_void_p),
+                                       ctypes.byref(cols), nb, int(block_size), int(bool(print_filtered)),
+                                       int(threads), out.ctypes.data, cap, ctypes.byref(out_len), counts))
+    else:
+        lin = np.ascontiguousarray(lineage, dtype=np.int32)
+        lnames = [str(x) for x in lineage_names]
+        lblob = ('\0'.join(lnames) + '\0').encode()
+        loff = np.zeros(max(len(lnames), 1), dtype=np.int64)
+        if len(lnames) > 1:
+            loff[1:len(lnames)] = np.cumsum([len(x.encode()) + 1 for x in lnames[:-1]])
+        _lib.check(lib.psb_format_rows_lineage(
+            1 if model == 'lmm' else 0, n, blob, off.ctypes.data_as(ctypes.c_void_p), ctypes.byref(cols), nb,
+            int(block_size), int(bool(print_filtered)), int(threads), lin.ctypes.data_as(ctypes.c_void_p), lblob,
+            loff.ctypes.data_as(ctypes.c_void_p), len(lnames), out.ctypes.data, cap, ctypes.byref(out_len), counts))
     return out[:out_len.value].tobytes(), counts[0], counts[1], counts[2]
 
 

@@ -212,3 +212,24 @@ def test_two_gpus_print_the_same_table(mode, tmp_path):
     one, e1 = _cli(common)
     two, e2 = _cli(common + ['--gpus', '2'])
     assert one == two and _counters(e1) == _counters(e2)
+
+
+@pytest.mark.parametrize('case', ['18', '19', '22'])
+def test_lineage_runs_fast_path_equals_result_loop(case, tmp_path, monkeypatch):
+    """--lineage runs: k-mer text tokenised on the device (rows brought back for the LMM's per-block
+    lineage fits) + psb_format_rows_lineage print what the host parser + the row-by-row result loop
+    print -- same lines, same lineage labels, same counters, in small blocks and batches."""
+    extra = ['--lineage-file', str(tmp_path / 'lineage.txt'), '--block_size', '30', '--gpu-batch', '60',
+             '--print-filtered']
+    outs = {}
+    for tag, env in (('fast', {'PYSEER_B200_TEXT': '1', 'PYSEER_B200_NATIVE_FORMAT': '1'}),
+                     ('loop', {'PYSEER_B200_TEXT': '0', 'PYSEER_B200_NATIVE_FORMAT': '0'})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        outs[tag] = _cli(list(CASES[case]) + extra)
+    a, b = outs['fast'][0].split('\n'), outs['loop'][0].split('\n')
+    assert len(a) == len(b) > 150
+    for x, y in zip(a, b):
+        fx_, fy = x.split('\t'), y.split('\t')
+        assert fx_[:-1] == fy[:-1] and set(fx_[-1].split(',')) == set(fy[-1].split(',')), (x, y)
+    assert _counters(outs['fast'][1]) == _counters(outs['loop'][1])

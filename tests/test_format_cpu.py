@@ -150,3 +150,33 @@ def test_fast_number_formatting_equals_printf():
     for i, line in enumerate(lines):
         f = line.split('\t')
         assert f[1] == '%.2E' % v[i] and f[5] == '%.2E' % abs(v[i]), (repr(v[i]), f)
+
+
+def test_native_formatter_lineage_column():
+    """psb_format_rows_lineage: the lineage column of --lineage runs (utils.py:93-97) sits between the
+    coefficients and the notes, holds the lineage's name or NA; against format_output row by row."""
+    rng = np.random.RandomState(5)
+    lineage_dict = ['MDS1', 'MDS2', 'BAPS_cluster_3', 'x']
+    for model, nb in (('seer', 4), ('seer', 0), ('lmm', 0)):
+        n = 2003
+        r = _table(rng, n, nb)
+        names = ['K%d' % i for i in range(n)]
+        lin = rng.randint(-1, len(lineage_dict), n).astype(np.int32)
+        text, c0, c1, c2 = format_table(r, names, model, 50, True, threads=3, lineage=lin,
+                                        lineage_names=lineage_dict)
+        got = text.decode().split('\n')[:-1]
+        plain, p0, p1, p2 = format_table(r, names, model, 50, True, threads=3)
+        base = plain.decode().split('\n')[:-1]
+        assert len(got) == len(base) == c2 and (c0, c1, c2) == (p0, p1, p2)
+        # the rows come out in the formatter's order: recover each row's index from its name
+        for a, b in zip(got, base):
+            fa, fb = a.split('\t'), b.split('\t')
+            j = int(fa[0][1:])
+            want = lineage_dict[lin[j]] if lin[j] >= 0 else 'NA'
+            assert fa[:-2] == fb[:-1] and fa[-2] == want and fa[-1] == fb[-1], (model, a, b)
+        # and one tuple through the reference-mirroring format_output
+        j = int(got[0].split('\t')[0][1:])
+        item = var_obj.LMM(names[j], None, r.af[j], r.prep[j], np.nan, np.nan, np.nan, np.nan,
+                           int(lin[j]) if lin[j] >= 0 else None, [], [], notes_from_flags(int(r.flags[j])), True, False)
+        if model == 'lmm' and (int(r.flags[j]) & _lib.F_PREFILTER):
+            assert _same(got[0], format_output(item, lineage_dict, 'lmm', False))
