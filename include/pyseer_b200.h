@@ -280,6 +280,9 @@ int psb_download_rows(psb_ctx *ctx, uint32_t *out_bits, uint32_t *out_missing,
 int psb_kinship_begin(psb_ctx *ctx, int32_t n_samples);
 int psb_kinship_add(psb_ctx *ctx, const uint32_t *bits, const uint32_t *missing, int64_t n_variants,
                     int32_t words_per_row, double min_af, double max_af, double max_missing);
+/* the same for the rows of the batch last submitted to the context (psb_submit, psb_submit_text: k-mer
+ * text tokenised on the device, psb_submit_device) -- the variant file then never exists as host rows */
+int psb_kinship_add_submitted(psb_ctx *ctx, double min_af, double max_af, double max_missing);
 int psb_kinship_fetch(psb_ctx *ctx, double *K_out);
 
 /* ---- native variant-file reader ------------------------------------------------- */

@@ -313,7 +313,7 @@ struct psb_kin {
     long long *d_K = nullptr;
     uint32_t *d_bits = nullptr, *d_miss = nullptr, *d_XT = nullptr;
     uint8_t *d_keep = nullptr, *d_E = nullptr;
-    size_t cap_bytes = 0, cap_xt = 0, cap_e = 0;
+    size_t cap_bytes = 0, cap_xt = 0, cap_e = 0, cap_keep = 0;
     int64_t kept = 0, seen = 0;
 };
 
@@ -325,7 +325,7 @@ static void kin_free(psb_kin *k) {
 }
 
 // K += E E' over the kept variants of the rows in d_bits, chunk by chunk through the tensor cores
-static int kin_accum_tc(psb_ctx *c, psb_kin *k, int64_t n_variants, int words_per_row) {
+static int kin_accum_tc(psb_ctx *c, psb_kin *k, const uint32_t *d_rows, int64_t n_variants, int words_per_row) {
     static void *fn = nullptr;
     if (!fn) {
         cudaDriverEntryPointQueryResult qres;
@@ -351,7 +351,7 @@ static int kin_accum_tc(psb_ctx *c, psb_kin *k, int64_t n_variants, int words_pe
         const int n_stages = (int)((vc + KT_KSTAGE - 1) / KT_KSTAGE);
         const int Vpad = n_stages * KT_KSTAGE;
         k_kin_expand<<<dim3(n_stages, (k->NpadT + 1023) / 1024), 256, 0, c->stream>>>(
-            k->d_bits, k->d_keep, v0, n_variants, words_per_row, k->Wn, k->NpadT, Vpad, k->d_E);
+            d_rows, k->d_keep, v0, n_variants, words_per_row, k->Wn, k->NpadT, Vpad, k->d_E);
         CUtensorMap tm;
         cuuint64_t gdim[2] = {(cuuint64_t)Vpad, (cuuint64_t)k->NpadT};
         cuuint64_t gstr[1] = {(cuuint64_t)Vpad};
@@ -374,6 +374,49 @@ static int kin_accum_tc(psb_ctx *c, psb_kin *k, int64_t n_variants, int words_pe
         c->launches += 2;
         PSB_CUDA(cudaGetLastError());
     }
+    return PSB_OK;
+}
+
+// K += (kept rows)' (kept rows) for n_variants packed rows already on the device
+static int kin_accumulate(psb_ctx *c, psb_kin *k, const uint32_t *d_rows, const uint32_t *d_miss, int64_t n_variants,
+                          int words_per_row, double min_af, double max_af, double max_missing) {
+    const int64_t n_chunks = (n_variants + 31) / 32;
+    // test hook: PSB_KIN_TC=0 keeps the contraction on the CUDA cores (AND + POPCOUNT)
+    const bool use_tc = !(getenv("PSB_KIN_TC") && atoi(getenv("PSB_KIN_TC")) == 0);
+    if ((size_t)n_variants > k->cap_keep) {
+        PSB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(k->d_keep);
+        k->d_keep = nullptr;
+        k->cap_keep = 0;
+        PSB_CUDA(cudaMalloc(&k->d_keep, (size_t)n_variants));
+        k->cap_keep = (size_t)n_variants;
+    }
+    const int blocks = (int)std::min<int64_t>((n_variants + 7) / 8, (int64_t)c->sm_count * 16);
+    k_kin_keep<<<blocks, 256, 0, c->stream>>>(d_rows, d_miss, n_variants, words_per_row, k->Wn, k->N, min_af, max_af,
+                                             max_missing, k->d_keep);
+    c->launches += 1;
+    if (use_tc) {
+        int rc = kin_accum_tc(c, k, d_rows, n_variants, words_per_row);
+        if (rc != PSB_OK) return rc;
+    } else {
+        const size_t xt_bytes = (size_t)n_chunks * k->Npad * 4;
+        if (xt_bytes > k->cap_xt) {
+            PSB_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(k->d_XT);
+            k->d_XT = nullptr;
+            k->cap_xt = 0;
+            PSB_CUDA(cudaMalloc(&k->d_XT, xt_bytes));
+            k->cap_xt = xt_bytes;
+        }
+        PSB_CUDA(cudaMemsetAsync(k->d_XT, 0, xt_bytes, c->stream));
+        const int tb = (int)std::min<int64_t>((n_chunks * k->Wn + 7) / 8, (int64_t)c->sm_count * 16);
+        k_kin_transpose<<<tb, 256, 0, c->stream>>>(d_rows, k->d_keep, n_variants, words_per_row, k->Wn, k->Npad,
+                                                   n_chunks, k->d_XT);
+        const int nt = k->Npad / KIN_TILE;
+        k_kin_accum<<<nt * (nt + 1) / 2, 256, 0, c->stream>>>(k->d_XT, n_chunks, k->Npad, k->N, nt, k->d_K);
+        c->launches += 2;
+    }
+    PSB_CUDA(cudaGetLastError());
     return PSB_OK;
 }
 
@@ -407,51 +450,44 @@ extern "C" int psb_kinship_add(psb_ctx *c, const uint32_t *bits, const uint32_t 
     if (n_variants == 0) return PSB_OK;
     PSB_CUDA(cudaSetDevice(c->device));
     const size_t bytes = (size_t)n_variants * words_per_row * 4;
-    const int64_t n_chunks = (n_variants + 31) / 32;
-    // test hook: PSB_KIN_TC=0 keeps the contraction on the CUDA cores (AND + POPCOUNT)
-    const bool use_tc = !(getenv("PSB_KIN_TC") && atoi(getenv("PSB_KIN_TC")) == 0);
     if (bytes > k->cap_bytes || (missing && !k->d_miss)) {
         PSB_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(k->d_bits); cudaFree(k->d_miss); cudaFree(k->d_keep);
+        cudaFree(k->d_bits); cudaFree(k->d_miss);
         k->d_bits = k->d_miss = nullptr;
-        k->d_keep = nullptr;
         k->cap_bytes = 0;
         PSB_CUDA(cudaMalloc(&k->d_bits, bytes));
         if (missing) PSB_CUDA(cudaMalloc(&k->d_miss, bytes));
-        PSB_CUDA(cudaMalloc(&k->d_keep, (size_t)n_variants));
         k->cap_bytes = bytes;
     }
     PSB_CUDA(cudaMemcpyAsync(k->d_bits, bits, bytes, cudaMemcpyHostToDevice, c->stream));
     if (missing) PSB_CUDA(cudaMemcpyAsync(k->d_miss, missing, bytes, cudaMemcpyHostToDevice, c->stream));
-    const int blocks = (int)std::min<int64_t>((n_variants + 7) / 8, (int64_t)c->sm_count * 16);
-    k_kin_keep<<<blocks, 256, 0, c->stream>>>(k->d_bits, missing ? k->d_miss : nullptr, n_variants,
-                                             words_per_row, k->Wn, k->N, min_af, max_af, max_missing,
-                                             k->d_keep);
-    c->launches += 1;
-    if (use_tc) {
-        int rc = kin_accum_tc(c, k, n_variants, words_per_row);
-        if (rc != PSB_OK) return rc;
-    } else {
-        const size_t xt_bytes = (size_t)n_chunks * k->Npad * 4;
-        if (xt_bytes > k->cap_xt) {
-            PSB_CUDA(cudaStreamSynchronize(c->stream));
-            cudaFree(k->d_XT);
-            k->d_XT = nullptr;
-            k->cap_xt = 0;
-            PSB_CUDA(cudaMalloc(&k->d_XT, xt_bytes));
-            k->cap_xt = xt_bytes;
-        }
-        PSB_CUDA(cudaMemsetAsync(k->d_XT, 0, xt_bytes, c->stream));
-        const int tb = (int)std::min<int64_t>((n_chunks * k->Wn + 7) / 8, (int64_t)c->sm_count * 16);
-        k_kin_transpose<<<tb, 256, 0, c->stream>>>(k->d_bits, k->d_keep, n_variants, words_per_row, k->Wn,
-                                                   k->Npad, n_chunks, k->d_XT);
-        const int nt = k->Npad / KIN_TILE;
-        k_kin_accum<<<nt * (nt + 1) / 2, 256, 0, c->stream>>>(k->d_XT, n_chunks, k->Npad, k->N, nt, k->d_K);
-        c->launches += 2;
-    }
+    int rc = kin_accumulate(c, k, k->d_bits, missing ? k->d_miss : nullptr, n_variants, words_per_row, min_af, max_af,
+                            max_missing);
+    if (rc != PSB_OK) return rc;
     PSB_CUDA(cudaGetLastError());
     PSB_CUDA(cudaStreamSynchronize(c->stream));      // the host buffers may be reused
     k->seen += n_variants;
+    return PSB_OK;
+}
+
+// The same for the rows of the batch last submitted to the context (psb_submit / psb_submit_text /
+// psb_submit_device): no host rows at all when the k-mer text was tokenised on the device.
+extern "C" int psb_kinship_add_submitted(psb_ctx *c, double min_af, double max_af, double max_missing) {
+    PSB_REQUIRE(c && c->kin, PSB_ERR_STATE, "psb_kinship_add_submitted before psb_kinship_begin");
+    psb_kin *k = (psb_kin *)c->kin;
+    PSB_CUDA(cudaSetDevice(c->device));
+    int rc = psb_run_begin(c);                       // adopt the submitted rows, order the stream after their copy
+    if (rc) return rc;
+    PSB_REQUIRE(c->d_bits || c->S == 0, PSB_ERR_STATE, "no rows submitted");
+    PSB_REQUIRE(c->N == k->N && c->Wrow >= k->Wn, PSB_ERR_ARG, "the submitted rows are over %d samples, the matrix over %d",
+                c->N, k->N);
+    if (c->S == 0) return PSB_OK;
+    rc = kin_accumulate(c, k, c->d_bits, c->d_miss, c->S, c->Wrow, min_af, max_af, max_missing);
+    if (rc != PSB_OK) return rc;
+    rc = psb_run_end(c);                             // the staging slot has been read
+    if (rc) return rc;
+    PSB_CUDA(cudaStreamSynchronize(c->stream));
+    k->seen += c->S;
     return PSB_OK;
 }
 

@@ -183,6 +183,10 @@ class Engine(object):
                                        bits.shape[1], float(min_af), float(max_af),
                                        float(max_missing)))
 
+    def kinship_add_submitted(self, min_af=0.01, max_af=0.99, max_missing=0.05):
+        """``kinship_add`` for the rows of the batch last submitted (``submit`` / ``submit_text``)."""
+        check(self.lib.psb_kinship_add_submitted(self._ctx, float(min_af), float(max_af), float(max_missing)))
+
     def kinship_fetch(self):
         K = np.empty((self._kin_n, self._kin_n), dtype=np.float64)
         check(self.lib.psb_kinship_fetch(self._ctx, self._dptr(K)))

@@ -3,7 +3,8 @@
 Same interface and output as pyseer's ``similarity`` tool (pyseer/similarity.py): a list of
 sample names, a variant file (``--kmers`` / ``--pres`` / ``--vcf``), AF / missing filters;
 writes the N x N matrix ``K = G G'`` as a TSV with sample names.  The product runs on the GPU
-as an int8 tensor-core contraction of the bit-expanded packed rows (``psb_kinship_*``).
+as an int8 tensor-core contraction of the bit-expanded packed rows (``psb_kinship_*``); k-mer text is
+tokenised on the device as well, so that such a file never exists as host rows.
 
 One deliberate difference: a MISSING genotype counts as absent (0).  The reference keeps NaN in its
 variant matrix for variants that pass ``--max-missing`` (input.py:428-430, similarity.py:99-113), so
@@ -41,15 +42,53 @@ def get_options(argv=None):
     return ap.parse_args(argv)
 
 
+TEXT_BLOCK = 12000       # lines per batch when the k-mer text is tokenised on the device
+
+
 def similarity(p, reader, min_af, max_af, max_missing, device=0):
-    """K = G G' over every variant the reader yields (filters as input.load_var_block)."""
+    """K = G G' over every variant the reader yields (filters as input.load_var_block).  k-mer text
+    is tokenised on the device (``psb_submit_text``) and accumulated from there
+    (``psb_kinship_add_submitted``): the rows never exist on the host."""
+    import os
     eng = Engine(device)
-    eng.kinship_begin(len(p))
+    n_samples = len(p)
+    eng.kinship_begin(n_samples)
     n = 0
-    for batch in reader.batches(BLOCK):
-        eng.kinship_add(batch.bits, batch.missing, min_af, max_af, max_missing)
-        n += batch.n
-        sys.stderr.write('Matrix size ' + str(n) + '\n')
+    text = type(reader) is VariantReader and reader.var_type == 'kmers' and \
+        os.environ.get('PYSEER_B200_TEXT', '1') != '0'
+    name_bytes = sum(len(x) for x in reader.samples) + 3 * n_samples if text else 0
+    if text and name_bytes + 4096 > (1 << 30):
+        text = False
+    if text:
+        from . import pipeline
+        # the text parser reads the sample count from a model: the smallest one there is
+        eng.fixed_setup(np.ones((n_samples, 1)), np.arange(n_samples, dtype=float) / n_samples, True, 0.0, 0.0)
+        eng.text_setup(reader.samples)
+        text_bytes = int(min(max(32 << 20, TEXT_BLOCK * (name_bytes // 2 + 512)), 768 << 20))
+        text_bytes = max(text_bytes, name_bytes + 4096)
+        pool = pipeline.TextPool(3, TEXT_BLOCK, text_bytes)
+        batches = pipeline.Prefetch(reader.text_batches(TEXT_BLOCK, pool=pool), depth=1)
+        try:
+            for batch in batches:
+                buf, n_bytes, lstart, llen = batch.text
+                eng.submit_text(buf, n_bytes, lstart, llen, batch.n)
+                eng.kinship_add_submitted(min_af, max_af, max_missing)      # returns when the device is done
+                info = eng.text_info(batch.n)
+                for i in np.nonzero(info & 2)[0]:
+                    sys.stderr.write('No observations of ' + batch.names[i] + ' in selected samples\n')
+                if (info & 4).any():
+                    raise ValueError("k-mer line without '|' separator")
+                pool.put(batch.token)
+                n += batch.n
+                sys.stderr.write('Matrix size ' + str(n) + '\n')
+        finally:
+            batches.cancel()
+            pool.close()
+    else:
+        for batch in reader.batches(BLOCK):
+            eng.kinship_add(batch.bits, batch.missing, min_af, max_af, max_missing)
+            n += batch.n
+            sys.stderr.write('Matrix size ' + str(n) + '\n')
     K = eng.kinship_fetch()
     eng.close()
     return K

@@ -91,8 +91,12 @@ def test_kinship_tensor_path_many_tiles():
     assert np.array_equal(out['1'], out['0'])
 
 
-def test_similarity_tool_on_reference_kmers(tmp_path):
+@pytest.mark.parametrize('text', ['1', '0'])
+def test_similarity_tool_on_reference_kmers(tmp_path, monkeypatch, text):
+    """The similarity tool on the reference's k-mer fixture, with the text tokenised on the device and
+    accumulated from the device rows (psb_kinship_add_submitted) and with the host parser."""
     from pyseer_b200.similarity import main
+    monkeypatch.setenv('PYSEER_B200_TEXT', text)
     from pyseer_b200.input import VariantReader, load_phenotypes
     from pyseer_b200.engine import unpack_rows
     p = load_phenotypes(os.path.join(GOLDEN, 'subset.pheno'), None)
