@@ -16,4 +16,8 @@ for tool in memcheck racecheck; do
   timeout 1500 $CS --tool $tool --print-limit 20 python -m pytest "tests/test_comm_gpu.py::test_gather_one_gpu" "tests/test_fixed_gpu.py::test_oracle_parity_fixed" -q -x > gpurun_out/r02_sanitizer_${tool}_fixed_comm.log 2>&1
   echo "exit $?" >> gpurun_out/r02_sanitizer_${tool}_fixed_comm.log
   tail -4 gpurun_out/r02_sanitizer_${tool}_fixed_comm.log
+  echo "=== $tool kinship tensor path"
+  timeout 600 $CS --tool $tool --print-limit 20 python -m pytest "tests/test_kinship_gpu.py::test_kinship_matches_numpy" "tests/test_kinship_gpu.py::test_kinship_with_missing_genotypes" -q -x > gpurun_out/r02_sanitizer_${tool}_kinship.log 2>&1
+  echo "exit $?" >> gpurun_out/r02_sanitizer_${tool}_kinship.log
+  tail -4 gpurun_out/r02_sanitizer_${tool}_kinship.log
 done
