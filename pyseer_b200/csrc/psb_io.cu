@@ -78,6 +78,9 @@ struct bgzf_block {
 };
 
 static int bgzf_inflate_one(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_len) {
+    // the library's own inflate (psb_pgz.cu; ~1.5x zlib on k-mer text), zlib when it declines
+    static const bool own = !(getenv("PSB_PGZ") && atoi(getenv("PSB_PGZ")) == 0);
+    if (own && psb_pgz_inflate_exact(in, in_len, out, out_len) == 0) return 0;
     z_stream zs;
     memset(&zs, 0, sizeof(zs));
     if (inflateInit2(&zs, -15) != Z_OK) return -1;

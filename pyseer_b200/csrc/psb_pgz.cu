@@ -429,6 +429,85 @@ void decode_range(const uint8_t *base, const uint8_t *end, uint64_t start, const
     c.n = o - WIN;
 }
 
+// A whole raw deflate stream whose decompressed size is known (a BGZF block: <= 64 KiB, no window before
+// it) straight to bytes -- the decoder above without markers.  false: not a valid stream of that size.
+bool inflate_exact(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len, const Tables &fixed, Tables &dyn) {
+    BitIn b;
+    b.init(in, in + in_len, 0);
+    size_t o = 0;
+    for (;;) {
+        b.refill();
+        if (b.cnt < 3) return false;
+        const uint32_t bfinal = b.bits(1), btype = b.bits(2);
+        if (btype == 0) {
+            b.drop(b.cnt & 7);
+            b.refill();
+            const uint32_t len = b.bits(16), nlen = b.bits(16);
+            if (b.cnt < 0 || (len ^ 0xffffu) != nlen) return false;
+            const uint64_t q = b.pos() >> 3;
+            if (q + len > in_len || o + len > out_len) return false;
+            memcpy(out + o, in + q, len);
+            o += len;
+            b.init(in, in + in_len, (q + len) * 8);
+        } else if (btype == 3) {
+            return false;
+        } else {
+            const Tables *t = &fixed;
+            if (btype == 2) {
+                if (!read_dynamic(b, dyn, false)) return false;
+                t = &dyn;
+            }
+            const uint32_t *lt = t->lt, *dt = t->dt;
+            for (;;) {
+                b.refill();
+                if (b.cnt < 0) return false;
+                uint32_t e = lt[b.buf & ((1u << LP) - 1)];
+                if (e & SUB) e = lt[((e >> 4) & 0x7ffffffu) + ((b.buf >> LP) & ((1u << (e & 15)) - 1))];
+                if (!e) return false;
+                b.drop((int)(e & 0xff));
+                uint32_t s = e >> 8;
+                if (s < 256) {
+                    if (o >= out_len) return false;
+                    out[o++] = (uint8_t)s;
+                    e = lt[b.buf & ((1u << LP) - 1)];
+                    if (!(e & SUB) && e && (e >> 8) < 256 && o < out_len) {
+                        b.drop((int)(e & 0xff));
+                        out[o++] = (uint8_t)(e >> 8);
+                    }
+                    continue;
+                }
+                if (s == 256) break;
+                s -= 257;
+                if (s >= 29) return false;
+                const uint32_t len = LEN_BASE[s] + b.bits(LEN_EXTRA[s]);
+                uint32_t d = dt[b.buf & ((1u << DP) - 1)];
+                if (d & SUB) d = dt[((d >> 4) & 0x7ffffffu) + ((b.buf >> DP) & ((1u << (d & 15)) - 1))];
+                if (!d) return false;
+                b.drop((int)(d & 0xff));
+                d >>= 8;
+                if (d >= 30) return false;
+                const uint32_t dist = DIST_BASE[d] + b.bits(DIST_EXTRA[d]);
+                if (dist > o || o + len > out_len) return false;
+                uint8_t *dp = out + o;
+                const uint8_t *sp = dp - dist;
+                if (dist >= 16 && o + len + 16 <= out_len) {         // 16 bytes at a time, may run over by < 16
+                    uint8_t *de = dp + len;
+                    do {
+                        memcpy(dp, sp, 16);
+                        dp += 16;
+                        sp += 16;
+                    } while (dp < de);
+                } else {
+                    for (uint32_t i = 0; i < len; ++i) dp[i] = sp[i];
+                }
+                o += len;
+            }
+        }
+        if (bfinal) break;
+    }
+    return b.cnt >= 0 && o == out_len;
+}
+
 inline uint64_t peek64(const uint8_t *base, const uint8_t *end, uint64_t bit) {
     const uint8_t *p = base + (bit >> 3);
     uint64_t w = 0;
@@ -612,6 +691,17 @@ static bool pgz_header(psb_pgz *z, size_t at) {
     z->crc = (uint32_t)crc32(0L, Z_NULL, 0);
     z->member_out = 0;
     return true;
+}
+
+// One raw deflate stream of known decompressed size -> bytes (thread safe; 0 = ok).
+int psb_pgz_inflate_exact(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_len) {
+    static const Tables *fixed = []() {
+        Tables *t = new Tables;
+        fixed_tables(*t);
+        return t;
+    }();
+    Tables dyn;                                     // 27 KB on the stack: no allocator traffic per 64 KiB block
+    return inflate_exact(in, in_len, out, out_len, *fixed, dyn) ? 0 : -1;
 }
 
 psb_pgz *psb_pgz_open(const char *path, int n_threads, size_t chunk_bytes) {

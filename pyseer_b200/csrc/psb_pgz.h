@@ -19,3 +19,6 @@ void psb_pgz_set_threads(psb_pgz *z, int n_threads);
 // diagnostics: work items decoded / of them thrown away (false block starts, overrun by a neighbour)
 void psb_pgz_stats(const psb_pgz *z, int64_t out[2]);
 void psb_pgz_close(psb_pgz *z);
+// One raw deflate stream of known decompressed size (a BGZF block) -> bytes, with the decoder of this
+// file and without markers (no window before it); thread safe; 0 = ok, -1 = not a valid stream of that size.
+int psb_pgz_inflate_exact(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_len);
