@@ -64,6 +64,7 @@ def main():
     ap.add_argument('--kmers', type=int, default=40000)
     ap.add_argument('--cpu', type=int, default=0)
     ap.add_argument('--part', type=int, default=10000, help='k-mers per generator job')
+    ap.add_argument('--similarity-only', action='store_true', help='time the similarity tool on the text file and stop')
     ap.add_argument('--sweep', default='', help='comma-separated --gpu-batch values to try on the text formats')
     a = ap.parse_args()
     import benchdata
@@ -107,6 +108,29 @@ def main():
                 fo.write(b'\x03\x00' + struct.pack('<II', crc & 0xffffffff, total & 0xffffffff))
     gen_s = time.time() - t0
     size_txt = os.path.getsize(txt)
+    if a.similarity_only:
+        # the similarity tool (K = G G') on the same k-mer text: device parser + psb_kinship_add_submitted
+        # against the host parser + psb_kinship_add
+        with open(os.path.join(d, 'samples.txt'), 'w') as fh:
+            fh.write('\n'.join('s%d' % i for i in range(n)) + '\n')
+        res = {'n_samples': n, 'kmers': m, 'text_bytes': size_txt, 'runs': {}}
+        for tag, src, extra, text in (('plain_text_device_parser', txt, ['--uncompressed'], '1'),
+                                      ('gzip_one_member_device_parser', txt + '.gz1', [], '1'),
+                                      ('plain_text_host_parser', txt, ['--uncompressed'], '0')):
+            t = time.time()
+            with open(os.path.join(d, 'K_%s.tsv' % tag), 'w') as fo:
+                subprocess.run([sys.executable, '-m', 'pyseer_b200.similarity', os.path.join(d, 'samples.txt'),
+                                '--kmers', src] + extra, stdout=fo, stderr=subprocess.DEVNULL, cwd=ROOT,
+                               env=dict(os.environ, PYSEER_B200_TEXT=text), check=True)
+            res['runs'][tag] = {'wall_s': time.time() - t}
+            sys.stderr.write('similarity %s: %.2f s\n' % (tag, time.time() - t))
+        ref = open(os.path.join(d, 'K_plain_text_host_parser.tsv')).read()
+        res['equal'] = all(open(os.path.join(d, 'K_%s.tsv' % t)).read() == ref for t in res['runs'])
+        print(json.dumps(res))
+        for f in os.listdir(d):
+            os.unlink(os.path.join(d, f))
+        os.rmdir(d)
+        return
     # (the device is touched only after the generator processes were forked)
     lm = KinshipLMM(X, y.reshape(-1, 1), K)
     h2 = float(lm.findH2()['h2'])
