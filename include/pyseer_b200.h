@@ -284,6 +284,13 @@ int psb_kinship_add(psb_ctx *ctx, const uint32_t *bits, const uint32_t *missing,
  * text tokenised on the device, psb_submit_device) -- the variant file then never exists as host rows */
 int psb_kinship_add_submitted(psb_ctx *ctx, double min_af, double max_af, double max_missing);
 int psb_kinship_fetch(psb_ctx *ctx, double *K_out);
+/* The tool's output, DataFrame(K, index=samples, columns=samples).to_csv(sep='\t') of
+ * pyseer/similarity.py:118-120, written natively: a header line of the sample names after an empty index
+ * label, then a line per sample with the counts as pandas prints float64 ('1234.0').  names: NUL-terminated
+ * sample names back to back, name_off their offsets.  PSB_ERR_UNSUPPORTED when an entry is not a
+ * non-negative integer below 1e15 (use pandas then); PSB_ERR_NOMEM when out_cap is too small. */
+int psb_format_matrix(const double *K, int32_t n, const char *names, const int64_t *name_off, int32_t n_threads,
+                      char *out, int64_t out_cap, int64_t *out_len);
 
 /* ---- native variant-file reader ------------------------------------------------- */
 /* Replaces the per-line Python of input.read_variant (input.py:301-454) for the k-mer text

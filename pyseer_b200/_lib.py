@@ -77,7 +77,7 @@ SYMBOLS = ['psb_abi_version', 'psb_last_error', 'psb_device_count', 'psb_create'
            'psb_results_device', 'psb_counts', 'psb_last_ms', 'psb_launch_count',
            'psb_host_alloc', 'psb_host_free', 'psb_download_bits', 'psb_event_record',
            'psb_event_elapsed', 'psb_reader_open', 'psb_reader_next', 'psb_reader_close',
-           'psb_lineage_setup', 'psb_run_lineage', 'psb_fetch_lineage', 'psb_last_stats', 'psb_kinship_begin', 'psb_kinship_add', 'psb_kinship_add_submitted', 'psb_kinship_fetch',
+           'psb_lineage_setup', 'psb_run_lineage', 'psb_fetch_lineage', 'psb_last_stats', 'psb_kinship_begin', 'psb_kinship_add', 'psb_kinship_add_submitted', 'psb_kinship_fetch', 'psb_format_matrix',
            'psb_synth_device', 'psb_synth_host', 'psb_host_chi2_sf1', 'psb_host_f_sf_1',
            'psb_host_t2_sf', 'psb_submit_burden', 'psb_submit_burden_device',
            'psb_submitted_device', 'psb_download_rows', 'psb_eigh', 'psb_reader_set_threads', 'psb_pgz_selftest', 'psb_format_rows', 'psb_format_rows_lineage', 'psb_reader_vcf_info', 'psb_hash_patterns', 'psb_pattern_digests',
@@ -170,6 +170,7 @@ def load():
                                     c_double]
     lib.psb_kinship_add_submitted.argtypes = [c_void_p, c_double, c_double, c_double]
     lib.psb_kinship_fetch.argtypes = [c_void_p, dp]
+    lib.psb_format_matrix.argtypes = [dp, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_int64, POINTER(c_int64)]
     lib.psb_comm_unique_id.argtypes = [c_void_p]
     lib.psb_comm_init_rank.argtypes = [c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p)]
     lib.psb_comm_init_all.argtypes = [POINTER(c_void_p), c_int32, POINTER(c_void_p)]

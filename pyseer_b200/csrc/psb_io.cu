@@ -1093,6 +1093,74 @@ extern "C" int psb_format_rows_lineage(int32_t model, int64_t n, const char *nam
                             out, out_cap, out_len, counts);
 }
 
+// The similarity tool's output (pyseer/similarity.py:118-120: DataFrame(K, index, columns).to_csv(sep='\t')):
+// header line of sample names after an empty index label, then one line per sample, entries printed as
+// pandas prints the float64 counts ('1234.0').  pandas needs ~12 s for N = 5000; this is a memory-bound
+// loop.  PSB_ERR_UNSUPPORTED when an entry is not a non-negative integer below 1e15 (the caller falls back
+// to pandas; K = G G' never holds such values).  names: NUL-terminated, name_off their offsets.
+extern "C" int psb_format_matrix(const double *K, int32_t n, const char *names, const int64_t *name_off,
+                                 int32_t n_threads, char *out, int64_t out_cap, int64_t *out_len) {
+    PSB_REQUIRE(K && names && name_off && out && out_len && n > 0, PSB_ERR_ARG, "NULL argument");
+    int T = n_threads < 1 ? 1 : (n_threads > 64 ? 64 : n_threads);
+    T = std::min(T, std::max(1, n / 64));
+    std::vector<std::string> parts((size_t)T);
+    std::atomic<int> bad(0);
+    auto work = [&](int t) {
+        const int r0 = (int)((int64_t)n * t / T), r1 = (int)((int64_t)n * (t + 1) / T);
+        std::string &dst = parts[t];
+        dst.reserve((size_t)(r1 - r0) * ((size_t)n * 8 + 64));
+        char num[32];
+        for (int i = r0; i < r1 && !bad.load(std::memory_order_relaxed); ++i) {
+            dst.append(names + name_off[i]);
+            const double *row = K + (size_t)i * n;
+            for (int j = 0; j < n; ++j) {
+                const double x = row[j];
+                if (!(x >= 0.0 && x < 1e15) || x != floor(x)) { bad.store(1); break; }
+                unsigned long long v = (unsigned long long)x;
+                char *e = num + sizeof(num), *p2 = e;
+                do {
+                    *--p2 = (char)('0' + v % 10);
+                    v /= 10;
+                } while (v);
+                dst.push_back('\t');
+                dst.append(p2, (size_t)(e - p2));
+                dst.append(".0", 2);
+            }
+            dst.push_back('\n');
+        }
+    };
+    if (T == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto &th : pool) th.join();
+    }
+    if (bad.load()) {
+        psb_set_error("matrix entries are not small non-negative integers");
+        return PSB_ERR_UNSUPPORTED;
+    }
+    std::string head;
+    for (int j = 0; j < n; ++j) {
+        head.push_back('\t');
+        head.append(names + name_off[j]);
+    }
+    head.push_back('\n');
+    int64_t total = (int64_t)head.size();
+    for (const auto &s2 : parts) total += (int64_t)s2.size();
+    PSB_REQUIRE(total <= out_cap, PSB_ERR_NOMEM, "output buffer too small (%lld bytes needed)", (long long)total);
+    char *p = out;
+    memcpy(p, head.data(), head.size());
+    p += head.size();
+    for (const auto &s2 : parts) {
+        memcpy(p, s2.data(), s2.size());
+        p += s2.size();
+    }
+    *out_len = total;
+    return PSB_OK;
+}
+
 // VCF only: contig (NUL-terminated, back to back in `contigs` with contig_off[v] offsets), 1-based
 // position and REF length of the records returned by the last psb_reader_next -- what the burden
 // branch needs to decide which records a region fetches (input.py:395-407).

@@ -180,3 +180,27 @@ def test_native_formatter_lineage_column():
                            int(lin[j]) if lin[j] >= 0 else None, [], [], notes_from_flags(int(r.flags[j])), True, False)
         if model == 'lmm' and (int(r.flags[j]) & _lib.F_PREFILTER):
             assert _same(got[0], format_output(item, lineage_dict, 'lmm', False))
+
+
+def test_similarity_matrix_writer_equals_pandas():
+    """similarity.write_matrix (psb_format_matrix) against DataFrame.to_csv(sep='\\t'), the reference's
+    output call (similarity.py:118-120): integer counts incl. 0 and 12-digit values, one sample and many;
+    non-integer matrices and names a csv writer would quote go through pandas itself."""
+    import io
+    import pandas as pd
+    from pyseer_b200.similarity import write_matrix
+    rng = np.random.RandomState(0)
+    for n in (1, 2, 65, 300):
+        K = rng.randint(0, 200000, (n, n)).astype(float)
+        K[0, 0] = 0
+        K[-1, 0] = 999999999999.0
+        names = ['s%d_x' % i for i in range(n)]
+        a, b = io.StringIO(), io.StringIO()
+        write_matrix(K, names, a)
+        pd.DataFrame(K, index=names, columns=names).to_csv(b, sep='\t')
+        assert a.getvalue() == b.getvalue()
+    for K, names in ((rng.uniform(size=(5, 5)), list('abcde')), (np.ones((3, 3)), ['a b', 'c,d', 'e"f'])):
+        a, b = io.StringIO(), io.StringIO()
+        write_matrix(K, names, a)
+        pd.DataFrame(K, index=names, columns=names).to_csv(b, sep='\t')
+        assert a.getvalue() == b.getvalue()
