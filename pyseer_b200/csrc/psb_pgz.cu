@@ -24,7 +24,8 @@
 //
 // Stored and fixed-Huffman blocks are decoded but never searched for (gzip emits dynamic blocks for
 // text; a region without them is decoded serially by the preceding chunk).  Several gzip members in
-// one file are handled one after the other.
+// one file: a member that ends inside a batch is followed through (the chain walk decodes the first
+// blocks of the next member up to the next start a chunk found; window and CRC start afresh).
 #include "psb_pgz.h"
 
 #include <fcntl.h>
@@ -244,6 +245,7 @@ struct Chunk {
     size_t out_off = 0;
     uint32_t crc = 0;
     bool bad_marker = false;
+    bool member_start = false;       // first chunk of a gzip member (nothing exists before it)
     Chunk() = default;
     Chunk(const Chunk &) = delete;
     Chunk &operator=(const Chunk &) = delete;
@@ -252,7 +254,7 @@ struct Chunk {
         if (this != &o) {
             free(sym);
             sym = o.sym; cap = o.cap; n = o.n; start = o.start; end = o.end; status = o.status; why = o.why;
-            out_off = o.out_off; crc = o.crc; bad_marker = o.bad_marker;
+            out_off = o.out_off; crc = o.crc; bad_marker = o.bad_marker; member_start = o.member_start;
             o.sym = nullptr; o.cap = 0;
         }
         return *this;
@@ -649,6 +651,7 @@ struct psb_pgz {
     Tables fixed;
     int64_t n_chunks = 0, n_wasted = 0;
     std::vector<Chunk> pool;            // symbol buffers, kept from batch to batch
+    std::vector<Chunk> bridge;          // ... and of the chunks that open a further member inside a batch
     WorkPool workers;
     size_t max_syms = (size_t)1 << 28;
     // serial continuation (zlib from the last confirmed block boundary): taken when a chunk the chain
@@ -664,6 +667,36 @@ static bool pgz_fail(psb_pgz *z, const char *msg) {
     z->failed = true;
     z->err = msg;
     return false;
+}
+
+// gzip member header at byte `at` -> *first = byte of the first deflate block; false when there is no
+// (complete) header there
+static bool pgz_header_end(const psb_pgz *z, size_t at, size_t *first) {
+    const uint8_t *m = z->map;
+    const size_t n = z->size;
+    if (at + 18 > n || m[at] != 0x1f || m[at + 1] != 0x8b || m[at + 2] != 8) return false;
+    const int flg = m[at + 3];
+    size_t p = at + 10;
+    if (flg & 4) {
+        if (p + 2 > n) return false;
+        p += 2 + ((size_t)m[p] | ((size_t)m[p + 1] << 8));
+    }
+    for (int k = 0; k < 2; ++k)
+        if (flg & (k == 0 ? 8 : 16)) {
+            while (p < n && m[p]) ++p;
+            ++p;
+        }
+    if (flg & 2) p += 2;
+    if (p >= n) return false;
+    *first = p;
+    return true;
+}
+
+// the member after the trailer that starts at byte `tr`: *first = byte of its first deflate block
+static bool pgz_next_member(const psb_pgz *z, size_t tr, size_t *first) {
+    size_t nx = tr + 8;
+    while (nx < z->size && z->map[nx] == 0) ++nx;               // zero padding after a member (gzip ignores it)
+    return nx < z->size && pgz_header_end(z, nx, first);
 }
 
 // gzip member header at byte `at` -> bit position of the first deflate block; false when there is
@@ -795,11 +828,18 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
         }
     const auto t2 = std::chrono::steady_clock::now();
     // ---- 3. the chain of chunks the serial decoding confirms ----
-    std::vector<int> used;
-    int cur = 0;
+    // A member that ends inside the batch does not end the batch: the first block of the next member is
+    // decoded here (a "bridge", serial, at most up to the next start a chunk found) and the chain goes on
+    // through the chunks already decoded -- concatenated gzip files keep all their threads busy.
+    constexpr int MAX_BRIDGES = 8;
+    if (z->bridge.size() < (size_t)MAX_BRIDGES) z->bridge.resize(MAX_BRIDGES);
+    for (int k = 0; k < n; ++k) ch[k].member_start = false;
+    std::vector<Chunk *> used;
+    Chunk *cur = &ch[0];
+    int n_bridges = 0;
     bool member_end = false;
     for (;;) {
-        Chunk &c = ch[cur];
+        Chunk &c = *cur;
         if (c.status < 0) {
             // what was confirmed so far is delivered; zlib continues from the boundary this chunk started at
             z->serial = true;
@@ -807,22 +847,50 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
             break;
         }
         used.push_back(cur);
-        if (c.status == 1) { member_end = true; break; }
+        if (c.status == 1) {
+            size_t first = 0;
+            const size_t tr = (size_t)(c.end >> 3);
+            if (tr + 8 <= z->size && n_bridges < MAX_BRIDGES && pgz_next_member(z, tr, &first) &&
+                (uint64_t)first * 8 < limit) {
+                Chunk &b = z->bridge[n_bridges];
+                b.max_syms = z->max_syms;
+                const uint64_t at = (uint64_t)first * 8;
+                const size_t s0 = std::upper_bound(stops.begin(), stops.end(), at) - stops.begin();
+                decode_range(base, end, at, stops.data() + s0, (int)(stops.size() - s0), limit, 0, b, z->fixed);
+                b.member_start = true;
+                if (b.status >= 0) {
+                    ++n_bridges;
+                    cur = &b;
+                    continue;
+                }
+                // the new member does not decode here: it opens the next batch (and goes to zlib there)
+            }
+            member_end = true;
+            break;
+        }
         const auto it = std::lower_bound(stops.begin(), stops.end(), c.end);
         if (it != stops.end() && *it == c.end) {
-            cur = stop_owner[it - stops.begin()];
+            cur = &ch[stop_owner[it - stops.begin()]];
             continue;
         }
         break;                                                  // stopped at / beyond the batch limit
     }
     z->n_chunks += n;
-    z->n_wasted += n - (int64_t)used.size();
+    z->n_wasted += n + n_bridges - (int64_t)used.size();
+    if (getenv("PSB_PGZ_DEBUG")) {
+        fprintf(stderr, "batch at %llu: n %d bridges %d used %zu member_end %d serial %d; starts:", (unsigned long long)p0, n,
+                n_bridges, used.size(), (int)member_end, (int)z->serial);
+        for (int k = 0; k < n; ++k)
+            fprintf(stderr, " %lld(%d,%lld)", live[k].load() == NONE ? -1ll : (long long)(live[k].load() - nominal[k]), ch[k].status,
+                    ch[k].status >= 0 ? (long long)(ch[k].end - nominal[k]) : -1ll);
+        fprintf(stderr, "\n");
+    }
     if (used.empty()) return true;                              // nothing confirmed: the serial reader starts at z->pos
     // ---- 4. windows (serial, 32 KiB per chunk), then markers -> bytes and CRC in parallel ----
     // destinations: the leading chunks that fit the caller's buffer go straight there
     size_t total = 0, n_direct = 0, direct_bytes = 0;
     for (size_t u = 0; u < used.size(); ++u) {
-        Chunk &c = ch[used[u]];
+        Chunk &c = *used[u];
         if (n_direct == u && direct && direct_bytes + c.n <= direct_cap) {
             c.out_off = direct_bytes;
             direct_bytes += c.n;
@@ -844,9 +912,13 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
         std::vector<uint8_t> w(z->window, z->window + WIN);     // right aligned: w[WIN-1] = last byte
         size_t wl = z->window_len;
         for (size_t u = 0; u < used.size(); ++u) {
+            const Chunk &c = *used[u];
+            if (c.member_start) {                               // a new member: nothing before its first byte
+                std::fill(w.begin(), w.end(), (uint8_t)0);
+                wl = 0;
+            }
             wins[u] = w;
             win_len[u] = wl;
-            const Chunk &c = ch[used[u]];
             // next window = last WIN bytes of (w ++ resolved chunk)
             std::vector<uint8_t> nw(WIN);
             const size_t take = std::min(c.n, WIN);
@@ -864,7 +936,7 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
     }
     const auto t3 = std::chrono::steady_clock::now();
     z->workers.run(T, (int)used.size(), [&](int u) {
-        Chunk &c = ch[used[u]];
+        Chunk &c = *used[u];
         const uint8_t *w = wins[u].data();
         const size_t lowest = WIN - win_len[u];         // markers below this index name bytes that do not exist
         const uint16_t *s = c.sym + WIN;
@@ -907,26 +979,37 @@ static bool pgz_batch(psb_pgz *z, uint8_t *direct, size_t direct_cap, size_t *di
     z->t_phase[1] += std::chrono::duration<double>(t2 - t1).count();
     z->t_phase[2] += std::chrono::duration<double>(t3 - t2).count();
     z->t_phase[3] += std::chrono::duration<double>(t4 - t3).count();
-    for (int k : used) {
-        if (ch[k].bad_marker) return pgz_fail(z, "corrupt gzip stream: invalid distance too far back");
-        z->crc = (uint32_t)crc32_combine(z->crc, ch[k].crc, (z_off_t)ch[k].n);
-        z->member_out += ch[k].n;
-    }
-    z->out_len = total;
-    *direct_used = direct_bytes;
-    const Chunk &last = ch[used.back()];
-    if (z->serial) {
-        z->pos = last.end;                                      // a confirmed boundary; window and CRC are current
-        return true;
-    }
-    if (member_end) {
-        const size_t tr = (size_t)(last.end >> 3);
+    auto trailer_ok = [&](const Chunk &c) -> bool {            // CRC-32 and length of the member that ends with c
+        const size_t tr = (size_t)(c.end >> 3);
         if (tr + 8 > z->size) return pgz_fail(z, "corrupt gzip stream: truncated trailer");
         const uint8_t *t = z->map + tr;
         const uint32_t want_crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
         const uint32_t want_len = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
         if (want_crc != z->crc) return pgz_fail(z, "corrupt gzip stream: CRC-32 mismatch");
         if (want_len != (uint32_t)(z->member_out & 0xffffffffu)) return pgz_fail(z, "corrupt gzip stream: length mismatch");
+        return true;
+    };
+    for (size_t u = 0; u < used.size(); ++u) {
+        const Chunk &c = *used[u];
+        if (c.bad_marker) return pgz_fail(z, "corrupt gzip stream: invalid distance too far back");
+        if (c.member_start) {
+            z->crc = (uint32_t)crc32(0L, Z_NULL, 0);
+            z->member_out = 0;
+        }
+        z->crc = (uint32_t)crc32_combine(z->crc, c.crc, (z_off_t)c.n);
+        z->member_out += c.n;
+        if (c.status == 1 && u + 1 < used.size() && !trailer_ok(c)) return false;   // a member that ended inside the batch
+    }
+    z->out_len = total;
+    *direct_used = direct_bytes;
+    const Chunk &last = *used.back();
+    if (z->serial) {
+        z->pos = last.end;                                      // a confirmed boundary; window and CRC are current
+        return true;
+    }
+    if (member_end) {
+        if (!trailer_ok(last)) return false;
+        const size_t tr = (size_t)(last.end >> 3);
         z->in_member = false;
         size_t nx = tr + 8;
         while (nx < z->size && z->map[nx] == 0) ++nx;           // zero padding after a member (gzip ignores it)
